@@ -1,0 +1,101 @@
+/* plink2_b200.h - C-ABI kernel face of the B200-native pairwise-genotype path.
+ *
+ * This is the drop-in boundary ("kernel face").  It is shaped like the reference's
+ * only existing GPU seam, 2.0/cuda/plink2_matrix_cuda.h:23-108: plain C, extern "C", no CUDA
+ * headers leaked, opaque handles, `int` return 0 = ok / 1 = fail (the caller maps 1 to
+ * kPglRetGpuFail, 2.0/include/plink2_base.h:380, as 2.0/plink2_matrix_calc.cc:9128 does),
+ * idempotent cleanup, one handle per host thread / device.
+ *
+ * Every entry point names the reference function whose inner loop it replaces.  Data contracts
+ * are the reference's own in-memory layouts so results drop into its writers unchanged:
+ *
+ *  - genotype block ("genovecs"): variant-major packed 2-bit genotypes exactly as PgrGet returns
+ *    them (2.0/include/pgenlib_read.h:537): sample s of a variant lives in bits 2*(s%32) of
+ *    64-bit word s/32 (little-endian, so also bits 2*(s%16) of 32-bit word s/16);
+ *    0 = hom-REF, 1 = het, 2 = hom-ALT, 3 = missing.  Trailing entries of the last word need not
+ *    be initialised (the library forces them to "missing", as SetTrailingNyps does at
+ *    plink2_matrix_calc.cc:2060).
+ *  - KING counts: uint32 king_counts[pair][5] in the order {IBS0, HETHET, HET2HOM1, HET1HOM2,
+ *    HOMHOM} (plink2_matrix_calc.cc:864-868), pairs ordered "for row j in [row_start,row_end):
+ *    for i in [0,j)" (:1545-1547); index 1 = smaller sample index, 2 = larger.
+ *
+ * There is no CPU fallback: every call fails (returns 1, message in pl2gpu_last_error()) when no
+ * sm_100 device is usable.
+ */
+#ifndef PLINK2_B200_H_
+#define PLINK2_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- context (replaces CudaGetDeviceCount/CudaSetDevice + CublasFmultiplier{Preinit,Init,Cleanup},
+ * plink2_matrix_cuda.h:30-104) ---- */
+typedef struct Pl2GpuCtx Pl2GpuCtx;
+
+int pl2gpu_device_count(void);
+/* Thread-local description of the last failure on this thread ("" if none). */
+const char* pl2gpu_last_error(void);
+/* Library/ABI version, bumped on any signature change. */
+int pl2gpu_abi_version(void);
+
+int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr);
+/* Idempotent; accepts NULL. */
+int pl2gpu_ctx_destroy(Pl2GpuCtx* ctx);
+/* Blocks until all work queued on the context's stream is complete. */
+int pl2gpu_ctx_synchronize(Pl2GpuCtx* ctx);
+/* The context's cudaStream_t as an opaque pointer (so a caller that owns device buffers, e.g. a
+ * torch.distributed process, can order its own work against ours). */
+void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx);
+
+/* ---- KING-robust pair counts: replaces the CalcKingDenseThread -> IncrKing/IncrKingHomhom hot
+ * loop (plink2_matrix_calc.cc:1255-1334, :1533-1552) together with the reader-thread
+ * SplitHomRef2hetUnsafeW + TransposeBitblock staging (:2055-2099).  The sparse pre-scan
+ * (CalcKingSparseThread, :904-1250) is a CPU-side optimisation whose result is identical to
+ * all-dense counting; here every variant goes through the dense path and the singleton vectors
+ * are implicitly zero. ---- */
+typedef struct Pl2KingJob Pl2KingJob;
+
+enum {
+  kPl2KingAlgoAuto = 0,
+  kPl2KingAlgoPopcount = 1, /* bit-plane AND/XOR + __popc over smem tiles */
+  kPl2KingAlgoTensor = 2    /* exact int8 tcgen05 contraction over {0,+-1} indicator planes */
+};
+
+/* Rows [row_start, row_end) of the strict lower triangle over sample_ct samples (row = larger
+ * sample index), i.e. one `--parallel` piece / one TriangleLoadBalance slab.  Device accumulators
+ * for those rows are allocated here; fails with "insufficient device memory" if they do not fit
+ * (the caller then narrows the row range - the reference's CountTrianglePasses multipass). */
+int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr);
+/* Bytes of device memory pl2gpu_king_begin would need for that row range (for pass planning). */
+uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add);
+/* Accumulate `variant_ct` more variants.  `genovecs` is host memory unless src_is_device != 0;
+ * consecutive variants are `variant_stride_bytes` apart (>= 8*ceil(sample_ct/32), multiple of 8).
+ * Asynchronous with respect to the host when the source is device memory or pinned host memory. */
+int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device);
+/* Copy out uint32 counts[pair][5] for rows [out_row_start, out_row_end) (a sub-range of the job's
+ * rows) in the reference's pair order.  dst is host memory unless dst_is_device != 0. */
+int pl2gpu_king_get_counts(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, uint32_t* dst, int dst_is_device);
+/* Same pairs, KING-robust kinship as fp64 (ComputeKinship, plink2_matrix_calc.cc:1566-1573, with
+ * zero singleton terms): 0.5 - (4*IBS0 + HET1HOM2 + HET2HOM1) / (4*(HETHET + min(HET1HOM2, HET2HOM1))). */
+int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, double* dst, int dst_is_device);
+uint64_t pl2gpu_king_variants_added(Pl2KingJob* job);
+/* Idempotent; accepts NULL. */
+int pl2gpu_king_end(Pl2KingJob* job);
+
+/* ---- self-test of the tcgen05 operand path (descriptor/layout probe); returns 0 iff an int8
+ * UMMA over library-written shared-memory tiles reproduces a scalar device-side reference. ---- */
+int pl2gpu_selftest_umma(Pl2GpuCtx* ctx, int verbose);
+/* Debug probe used by tests to pin the operand layout: runs `k_steps` int8 UMMAs (M = 128) over the
+ * given shared-memory images / descriptor fields and returns D as int32 [128][n] (host memory). */
+int pl2gpu_debug_umma(Pl2GpuCtx* ctx, const uint8_t* a_img, uint32_t a_bytes, const uint8_t* b_img, uint32_t b_bytes, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_step_bytes, uint32_t b_step_bytes, uint32_t k_steps, uint32_t idesc, uint32_t n, int32_t* d_out_host);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif  /* PLINK2_B200_H_ */

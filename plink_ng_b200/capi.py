@@ -1,0 +1,63 @@
+"""ctypes binding of include/plink2_b200.h.  Fails loudly if the CUDA library is missing."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libpl2gpu.so")
+
+
+class Pl2Error(RuntimeError):
+    pass
+
+
+if not os.path.exists(_LIB_PATH):
+    raise ImportError(
+        f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(nvcc, sm_100a).  There is no CPU fallback."
+    )
+
+lib = C.CDLL(_LIB_PATH)
+
+u8p = C.POINTER(C.c_uint8)
+u32p = C.POINTER(C.c_uint32)
+i32p = C.POINTER(C.c_int32)
+f64p = C.POINTER(C.c_double)
+vp = C.c_void_p
+
+# name -> (restype, argtypes); must list every symbol include/plink2_b200.h declares
+SIGNATURES = {
+    "pl2gpu_device_count": (C.c_int, []),
+    "pl2gpu_last_error": (C.c_char_p, []),
+    "pl2gpu_abi_version": (C.c_int, []),
+    "pl2gpu_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
+    "pl2gpu_ctx_destroy": (C.c_int, [vp]),
+    "pl2gpu_ctx_synchronize": (C.c_int, [vp]),
+    "pl2gpu_ctx_stream": (vp, [vp]),
+    "pl2gpu_ctx_launch_count": (C.c_uint64, [vp]),
+    "pl2gpu_king_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
+    "pl2gpu_king_mem_required": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "pl2gpu_king_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int]),
+    "pl2gpu_king_get_counts": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
+    "pl2gpu_king_get_kinship": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
+    "pl2gpu_king_variants_added": (C.c_uint64, [vp]),
+    "pl2gpu_king_end": (C.c_int, [vp]),
+    "pl2gpu_selftest_umma": (C.c_int, [vp, C.c_int]),
+    "pl2gpu_debug_umma": (
+        C.c_int,
+        [vp, vp, C.c_uint32, vp, C.c_uint32] + [C.c_uint32] * 9 + [vp],
+    ),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+
+def last_error() -> str:
+    return lib.pl2gpu_last_error().decode("utf-8", "replace")
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise Pl2Error(f"{what} failed: {last_error()}")

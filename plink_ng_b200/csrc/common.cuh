@@ -1,0 +1,73 @@
+// common.cuh - shared declarations of the pl2gpu library (internal; the public face is
+// include/plink2_b200.h).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace pl2 {
+
+// ---- error plumbing: every CUDA call is checked; failures become `return 1` + message ----
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define PL2_CUDA_OK(expr)                                                                                  \
+  do {                                                                                                     \
+    cudaError_t err__ = (expr);                                                                            \
+    if (err__ != cudaSuccess) {                                                                            \
+      pl2::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, cudaGetErrorString(err__));      \
+      return 1;                                                                                            \
+    }                                                                                                      \
+  } while (0)
+
+#define PL2_TRY(expr)  \
+  do {                 \
+    if ((expr)) {      \
+      return 1;        \
+    }                  \
+  } while (0)
+
+// ---- pair-tile geometry shared by every N x N kernel ----
+// Output tiles are kTileRows (larger-index samples, "sample 2") x kTileCols (smaller-index
+// samples, "sample 1").  128 rows = the UMMA M dimension / the 128 TMEM lanes; 96 columns so that
+// five 32-bit accumulators (5 * 96 = 480) fit the 512 TMEM columns of one SM.
+constexpr uint32_t kTileRows = 128;
+constexpr uint32_t kTileCols = 96;
+constexpr uint32_t kKingAccs = 5;                                   // TT, TH, HT, HH, SS
+constexpr uint32_t kKingTileAccCols = kKingAccs * kTileCols;        // 480
+constexpr uint32_t kKingTileAccWords = kKingTileAccCols * kTileRows;  // int32 per tile
+// Samples are padded to a multiple of lcm(128, 96) with "missing" so every tile read is in-bounds.
+constexpr uint32_t kSamplePad = 384;
+
+// Position p of a 16-byte expanded vector holds sample kPosToSample(p) of the 16-sample group
+// (a by-product of the PRMT expansion, which handles even and odd samples separately).
+__host__ __device__ constexpr uint32_t PosToSample(uint32_t p) { return (p < 8) ? (2 * p) : (2 * (p - 8) + 1); }
+__host__ __device__ constexpr uint32_t SampleToPos(uint32_t s) { return (s & 1) ? (8 + (s >> 1)) : (s >> 1); }
+
+struct Ctx {
+  int device = -1;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;
+  int sm_count = 0;
+  uint64_t launches = 0;
+};
+
+struct TileList {
+  // tiles of the strict lower triangle restricted to rows [row_start, row_end)
+  uint32_t row_tile_first = 0;  // row_start / kTileRows
+  uint32_t row_tile_ct = 0;
+  uint32_t tile_ct = 0;
+  uint32_t* d_tile_rt = nullptr;       // [tile_ct] row-tile index (absolute)
+  uint32_t* d_tile_tc = nullptr;       // [tile_ct] col-tile index
+  uint32_t* d_rowtile_offset = nullptr;  // [row_tile_ct + 1] first tile of each row tile
+  std::vector<uint32_t> h_rowtile_offset;  // host copy of the same
+};
+
+static inline uint32_t DivUpU32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+static inline uint64_t DivUpU64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline uint32_t RoundUpU32(uint32_t a, uint32_t b) { return DivUpU32(a, b) * b; }
+
+}  // namespace pl2

@@ -1,0 +1,461 @@
+// king_kernels.cuh - device kernels of the KING-robust pair-count path.
+//
+// Replaces the reference's IncrKing / IncrKingHomhom (2.0/plink2_matrix_calc.cc:1255-1334) and
+// the SplitHomRef2hetUnsafeW + TransposeBitblock staging in front of it (:2055-2099).
+//
+// Device-resident accumulators ("raw tiles"): for every 128 x 96 pair tile, int32
+//   raw[tile][q * 96 + c][r],  q in {TT, TH, HT, HH, SS},  r = row sample - 128*rt (larger index),
+//   c = col sample - 96*tc (smaller index),
+// with T = het indicator, H = hom indicator, S = +1 hom-REF / -1 hom-ALT:
+//   TT = HETHET, TH = (row het, col hom) = HET2HOM1, HT = HET1HOM2, HH = HOMHOM,
+//   SS = HH - 2*IBS0  (so IBS0 = (HH - SS) / 2, always an exact integer).
+// Both algorithms (popcount and int8 tcgen05) accumulate into the same layout, bit-identically.
+#pragma once
+#include "common.cuh"
+#include "geno_expand.cuh"
+#include "umma.cuh"
+
+namespace pl2 {
+
+// ---------------------------------------------------------------------------------------------
+// Staging: force samples >= sample_ct and variant rows >= variant_ct of the padded raw block to
+// "missing" (SetTrailingNyps, plink2_matrix_calc.cc:2060; zero-filled block tail, :2089-2099).
+// raw: [variant_ct_padded][pitch bytes], pitch = sample_ct_padded / 4.
+// ---------------------------------------------------------------------------------------------
+__global__ void pad_genotypes_kernel(uint8_t* __restrict__ raw, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded) {
+  const uint32_t v = blockIdx.x;
+  if (v >= variant_ct_padded) return;
+  uint8_t* row = raw + static_cast<uint64_t>(v) * pitch;
+  if (v >= variant_ct) {
+    for (uint32_t b = threadIdx.x; b < pitch; b += blockDim.x) row[b] = 0xFF;
+    return;
+  }
+  const uint32_t first = sample_ct >> 2;
+  const uint32_t rem = sample_ct & 3;
+  for (uint32_t b = first + threadIdx.x; b < pitch; b += blockDim.x) {
+    if (b == first && rem) {
+      row[b] = row[b] | static_cast<uint8_t>(0xFFu << (2 * rem));
+    } else {
+      row[b] = 0xFF;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Popcount path, step 1: variant-major 2-bit -> sample-addressable bit planes
+//   planes[p][kw][s], p in {hom, ref2het, het}, kw = 32-variant word index, s = sample.
+// One warp transposes a 32-variant x 32-sample block with ballots (lane = variant on input,
+// lane = sample on output); reads are 8-byte, writes 128-byte coalesced.
+// Algorithmic bytes: N*M/4 read + 3*N*M/8 written.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) split_transpose_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t sample_ct_padded, uint32_t word_ct /* variant_ct_padded / 32 */, uint32_t* __restrict__ planes) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp_in_block = threadIdx.x >> 5;
+  const uint32_t sample_groups = sample_ct_padded >> 5;
+  const uint64_t warp_global = static_cast<uint64_t>(blockIdx.x) * (blockDim.x >> 5) + warp_in_block;
+  if (warp_global >= static_cast<uint64_t>(sample_groups) * word_ct) return;
+  const uint32_t kw = static_cast<uint32_t>(warp_global / sample_groups);
+  const uint32_t sg = static_cast<uint32_t>(warp_global % sample_groups);
+  const uint64_t w = *reinterpret_cast<const uint64_t*>(raw + static_cast<uint64_t>(kw * 32 + lane) * pitch + static_cast<uint64_t>(sg) * 8);
+  uint32_t my_hom = 0, my_r2h = 0, my_het = 0;
+#pragma unroll
+  for (uint32_t s = 0; s < 32; ++s) {
+    const uint32_t code = static_cast<uint32_t>(w >> (2 * s)) & 3u;
+    const uint32_t hom = __ballot_sync(0xFFFFFFFFu, (code & 1u) == 0u);
+    const uint32_t r2h = __ballot_sync(0xFFFFFFFFu, (code & 2u) == 0u);
+    const uint32_t het = __ballot_sync(0xFFFFFFFFu, code == 1u);
+    if (lane == s) {
+      my_hom = hom;
+      my_r2h = r2h;
+      my_het = het;
+    }
+  }
+  const uint64_t plane_words = static_cast<uint64_t>(word_ct) * sample_ct_padded;
+  const uint64_t off = static_cast<uint64_t>(kw) * sample_ct_padded + sg * 32 + lane;
+  planes[off] = my_hom;
+  planes[plane_words + off] = my_r2h;
+  planes[2 * plane_words + off] = my_het;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Popcount path, step 2: the IncrKingHomhom inner loop (plink2_matrix_calc.cc:1309-1322) as a
+// register-tiled kernel.  One CTA = half a pair tile (64 rows x 96 cols); each of 256 threads owns
+// a 4 x 6 block of pairs (5 counters each) and walks the variant words staged in shared memory by
+// cp.async double buffering.  Per pair and 32 variants: 5 LOP3 + 5 POPC + 5 IADD.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kPopcKw = 8;  // 32-variant words per smem chunk
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 1)
+king_popc_kernel(const uint32_t* __restrict__ planes, uint32_t sample_ct_padded, uint32_t word_ct, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
+  __shared__ __align__(16) uint32_t s_rows[2][3][kPopcKw][64];
+  __shared__ __align__(16) uint32_t s_cols[2][3][kPopcKw][96];
+  const uint32_t tile = blockIdx.x >> 1;
+  const uint32_t half = blockIdx.x & 1;
+  const uint32_t row0 = tile_rt[tile] * kTileRows + half * 64;
+  const uint32_t col0 = tile_tc[tile] * kTileCols;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t ry = tid >> 4;  // rows 4*ry .. 4*ry+3
+  const uint32_t cx = tid & 15;  // cols 6*cx .. 6*cx+5
+  const uint64_t plane_words = static_cast<uint64_t>(word_ct) * sample_ct_padded;
+
+  uint32_t cnt[4][6][5];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < 6; ++b)
+#pragma unroll
+      for (int q = 0; q < 5; ++q) cnt[a][b][q] = 0;
+
+  const uint32_t chunk_ct = word_ct / kPopcKw;
+  auto issue = [&](uint32_t chunk, uint32_t buf) {
+    // rows: 3 planes x kPopcKw words x 64 samples = 384 x 16B; cols: 3 x kPopcKw x 96 = 576 x 16B
+    for (uint32_t i = tid; i < 960; i += 256) {
+      if (i < 384) {
+        const uint32_t p = i / 128, rem = i % 128, kk = rem / 16, seg = rem % 16;
+        const uint32_t* src = planes + p * plane_words + static_cast<uint64_t>(chunk * kPopcKw + kk) * sample_ct_padded + row0 + seg * 4;
+        cp_async16(&s_rows[buf][p][kk][seg * 4], src);
+      } else {
+        const uint32_t j = i - 384;
+        const uint32_t p = j / 192, rem = j % 192, kk = rem / 24, seg = rem % 24;
+        const uint32_t* src = planes + p * plane_words + static_cast<uint64_t>(chunk * kPopcKw + kk) * sample_ct_padded + col0 + seg * 4;
+        cp_async16(&s_cols[buf][p][kk][seg * 4], src);
+      }
+    }
+    cp_async_commit();
+  };
+
+  if (chunk_ct) issue(0, 0);
+  for (uint32_t chunk = 0; chunk < chunk_ct; ++chunk) {
+    const uint32_t buf = chunk & 1;
+    if (chunk + 1 < chunk_ct) {
+      issue(chunk + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (uint32_t kk = 0; kk < kPopcKw; ++kk) {
+      const uint4 rh = *reinterpret_cast<const uint4*>(&s_rows[buf][0][kk][4 * ry]);
+      const uint4 rr = *reinterpret_cast<const uint4*>(&s_rows[buf][1][kk][4 * ry]);
+      const uint4 rt = *reinterpret_cast<const uint4*>(&s_rows[buf][2][kk][4 * ry]);
+      const uint32_t row_h[4] = {rh.x, rh.y, rh.z, rh.w};
+      const uint32_t row_r[4] = {rr.x, rr.y, rr.z, rr.w};
+      const uint32_t row_t[4] = {rt.x, rt.y, rt.z, rt.w};
+      uint32_t col_h[6], col_r[6], col_t[6];
+#pragma unroll
+      for (int b = 0; b < 6; b += 2) {
+        const uint2 ch = *reinterpret_cast<const uint2*>(&s_cols[buf][0][kk][6 * cx + b]);
+        const uint2 cr = *reinterpret_cast<const uint2*>(&s_cols[buf][1][kk][6 * cx + b]);
+        const uint2 ct = *reinterpret_cast<const uint2*>(&s_cols[buf][2][kk][6 * cx + b]);
+        col_h[b] = ch.x; col_h[b + 1] = ch.y;
+        col_r[b] = cr.x; col_r[b + 1] = cr.y;
+        col_t[b] = ct.x; col_t[b + 1] = ct.y;
+      }
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+#pragma unroll
+        for (int b = 0; b < 6; ++b) {
+          const uint32_t hh = row_h[a] & col_h[b];
+          cnt[a][b][0] += __popc(row_t[a] & col_t[b]);           // TT
+          cnt[a][b][1] += __popc(row_t[a] & col_h[b]);           // TH: row het, col hom
+          cnt[a][b][2] += __popc(row_h[a] & col_t[b]);           // HT
+          cnt[a][b][3] += __popc(hh);                            // HH
+          cnt[a][b][4] += __popc((row_r[a] ^ col_r[b]) & hh);    // IBS0
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kKingTileAccWords;
+#pragma unroll
+  for (int b = 0; b < 6; ++b) {
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+      int4* p = reinterpret_cast<int4*>(acc_tile + static_cast<uint64_t>(q * kTileCols + 6 * cx + b) * kTileRows + half * 64 + 4 * ry);
+      int4 v = *p;
+      if (q < 4) {
+        v.x += cnt[0][b][q]; v.y += cnt[1][b][q]; v.z += cnt[2][b][q]; v.w += cnt[3][b][q];
+      } else {  // SS = HH - 2 * IBS0
+        v.x += static_cast<int32_t>(cnt[0][b][3]) - 2 * static_cast<int32_t>(cnt[0][b][4]);
+        v.y += static_cast<int32_t>(cnt[1][b][3]) - 2 * static_cast<int32_t>(cnt[1][b][4]);
+        v.z += static_cast<int32_t>(cnt[2][b][3]) - 2 * static_cast<int32_t>(cnt[2][b][4]);
+        v.w += static_cast<int32_t>(cnt[3][b][3]) - 2 * static_cast<int32_t>(cnt[3][b][4]);
+      }
+      *p = v;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tensor path: the same five counts as an exact int8 contraction on tcgen05.
+//   D[r][c] += sum_v A_plane[r][v] * B_plane[c][v],  planes in {T, H, S}, int32 accumulators in TMEM.
+// One CTA per pair tile.  Warps 0-7 expand 2-bit genotypes into MN-major int8 operand tiles in
+// shared memory (geno_expand.cuh), warp 8 lane 0 issues the UMMAs, and at the end of the variant
+// loop warps 0-7 drain TMEM into the raw accumulators.
+//   per 32-variant k-step:  T_I x [T_J;H_J] (N=192) -> cols [0,192)    = TT | TH
+//                           H_I x [T_J;H_J] (N=192) -> cols [192,384)  = HT | HH
+//                           S_I x  S_J      (N=96)  -> cols [384,480)  = SS
+// Algorithmic work: 5 * 128 * 96 * variants MACs per tile.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t kTcKc = 64;       // variants per pipeline stage (two K=32 UMMA steps)
+constexpr uint32_t kTcStages = 4;
+constexpr uint32_t kTcLookahead = 4; // register-prefetched stages of raw genotype words
+constexpr uint32_t kTcSuperI = 3 * kTileRows;  // 384 "samples" (3 planes x 128)
+constexpr uint32_t kTcSuperJ = 3 * kTileCols;  // 288
+constexpr uint32_t kTcLboI = operand_lbo(kTcSuperI);  // 3072
+constexpr uint32_t kTcLboJ = operand_lbo(kTcSuperJ);  // 2304
+constexpr uint32_t kTcStageBytesI = kTcSuperI * kTcKc;  // 24576
+constexpr uint32_t kTcStageBytesJ = kTcSuperJ * kTcKc;  // 18432
+constexpr uint32_t kTcStageBytes = kTcStageBytesI + kTcStageBytesJ;
+constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024;
+constexpr uint32_t kTcProducerThreads = 256;
+constexpr uint32_t kTcThreads = kTcProducerThreads + 32;
+
+struct KingTcTables {
+  uint32_t tab[3];
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_ct_padded /* multiple of kTcKc */, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full[kTcStages];
+  __shared__ __align__(8) uint64_t bar_empty[kTcStages];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5;
+  const uint32_t lane = tid & 31;
+  const uint32_t tile = blockIdx.x;
+  const uint32_t i0 = tile_rt[tile] * kTileRows;
+  const uint32_t j0 = tile_tc[tile] * kTileCols;
+  const uint32_t stage_iters = variant_ct_padded / kTcKc;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < kTcStages; ++s) {
+      mbar_init(&bar_full[s], kTcProducerThreads);
+      mbar_init(&bar_empty[s], 1);
+    }
+    mbar_init(&bar_acc, 1);
+    mbar_fence_init();
+  }
+  if (warp == 8) {
+    tmem_alloc<512>(&tmem_base_slot);
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < 8) {
+    // ---------------- producers ----------------
+    const bool is_i = tid < 128;
+    const uint32_t half = (tid >> 6) & 1;
+    const uint32_t k = tid & 63;
+    const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + (is_i ? (i0 / 4 + 16 * half) : (j0 / 4 + 12 * half));
+    const uint64_t stage_stride = static_cast<uint64_t>(kTcKc) * pitch;
+    const uint32_t lbo = is_i ? kTcLboI : kTcLboJ;
+    const uint32_t groups_per_plane = is_i ? 8u : 6u;
+    const uint32_t words = is_i ? 4u : 3u;
+    const uint32_t g0 = words * half;
+    const uint32_t side_off = is_i ? 0u : kTcStageBytesI;
+    const uint32_t dst_k = operand_offset(k, 0, lbo) + side_off;
+
+    auto load_words = [&](uint32_t it) -> uint4 {
+      uint4 w = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+      if (it < stage_iters) {
+        const uint8_t* p = src + it * stage_stride;
+        if (is_i) {
+          w = __ldg(reinterpret_cast<const uint4*>(p));
+        } else {
+          const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+          w.x = __ldg(q);
+          w.y = __ldg(q + 1);
+          w.z = __ldg(q + 2);
+        }
+      }
+      return w;
+    };
+
+    uint4 pre[kTcLookahead];
+#pragma unroll
+    for (uint32_t d = 0; d < kTcLookahead; ++d) pre[d] = load_words(d);
+
+    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTcLookahead) {
+#pragma unroll
+      for (uint32_t d = 0; d < kTcLookahead; ++d) {
+        const uint32_t it = it0 + d;
+        if (it < stage_iters) {
+          const uint32_t s = it % kTcStages;
+          const uint32_t ph = (it / kTcStages) & 1;
+          const uint4 cur = pre[d];
+          pre[d] = load_words(it + kTcLookahead);
+          mbar_wait(&bar_empty[s], ph ^ 1);
+          const uint32_t dst = smem_base + s * kTcStageBytes + dst_k;
+          const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+          for (uint32_t q = 0; q < 4; ++q) {
+            if (q < words) {
+              const Sel4 sel = make_selectors(wv[q]);
+              const uint32_t g = g0 + q;
+              const uint4 vt = expand16(kTabHet, sel);
+              const uint4 vh = expand16(kTabHom, sel);
+              const uint4 vs = expand16(kTabSgn, sel);
+              const uint32_t a0 = dst + g * kCoreBytes;
+              const uint32_t a1 = a0 + groups_per_plane * kCoreBytes;
+              const uint32_t a2 = a1 + groups_per_plane * kCoreBytes;
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
+              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a2), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
+            }
+          }
+          fence_proxy_async_smem();
+          mbar_arrive(&bar_full[s]);
+        }
+      }
+    }
+
+    // ---------------- epilogue: TMEM -> raw accumulators (+=) ----------------
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after_sync();
+    const uint32_t lane_grp = warp & 3;
+    const uint32_t col_half = warp >> 2;
+    const uint32_t rpos = 32 * lane_grp + lane;
+    const uint32_t rsample = (rpos & ~15u) + PosToSample(rpos & 15u);
+    int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kKingTileAccWords + rsample;
+#pragma unroll 1
+    for (uint32_t chunk = 0; chunk < 15; ++chunk) {
+      const uint32_t col0 = col_half * 240 + chunk * 16;
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((32u * lane_grp) << 16) + col0, v);
+      tmem_ld_wait();
+      const uint32_t grp = col0 / 16;         // 16-column group
+      const uint32_t q = grp / 6;             // accumulator
+      const uint32_t cgrp = grp % 6;          // 16-sample group within the 96 columns
+      int32_t* base = acc_tile + static_cast<uint64_t>(q * kTileCols + cgrp * 16) * kTileRows;
+#pragma unroll
+      for (uint32_t c = 0; c < 16; ++c) {
+        int32_t* p = base + PosToSample(c) * kTileRows;
+        *p += static_cast<int32_t>(v[c]);
+      }
+    }
+    tc_fence_before_sync();
+  } else {
+    // ---------------- UMMA issuer (warp 8, one lane) ----------------
+    if (lane == 0) {
+      constexpr uint32_t idesc_n192 = make_idesc_i8(128, 192, true, true);
+      constexpr uint32_t idesc_n96 = make_idesc_i8(128, 96, true, true);
+      for (uint32_t it = 0; it < stage_iters; ++it) {
+        const uint32_t s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1;
+        mbar_wait(&bar_full[s], ph);
+        tc_fence_after_sync();
+        const uint32_t si = smem_base + s * kTcStageBytes;
+        const uint32_t sj = si + kTcStageBytesI;
+#pragma unroll
+        for (uint32_t kk = 0; kk < kTcKc / 32; ++kk) {
+          const uint32_t acc = (it | kk) ? 1u : 0u;
+          const uint32_t ai = si + kk * 4 * kTcLboI;
+          const uint32_t bj = sj + kk * 4 * kTcLboJ;
+          const uint64_t a_t = make_smem_desc(ai, kTcLboI, kCoreBytes);
+          const uint64_t a_h = make_smem_desc(ai + 8 * kCoreBytes, kTcLboI, kCoreBytes);
+          const uint64_t a_s = make_smem_desc(ai + 16 * kCoreBytes, kTcLboI, kCoreBytes);
+          const uint64_t b_th = make_smem_desc(bj, kTcLboJ, kCoreBytes);
+          const uint64_t b_s = make_smem_desc(bj + 12 * kCoreBytes, kTcLboJ, kCoreBytes);
+          umma_i8_ss(tmem_base + 0, a_t, b_th, idesc_n192, acc);
+          umma_i8_ss(tmem_base + 192, a_h, b_th, idesc_n192, acc);
+          umma_i8_ss(tmem_base + 384, a_s, b_s, idesc_n96, acc);
+        }
+        umma_commit(&bar_empty[s]);
+      }
+      umma_commit(&bar_acc);
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Finalisation: raw tiles -> the reference's in-memory results for rows [out_row_start, out_row_end).
+//   counts : uint32 [pair][5] = {IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM} (plink2_matrix_calc.cc:864-868)
+//   kinship: fp64 per pair (ComputeKinship, :1566-1573)
+// pair order: for j in rows: for i in [0, j)  (:1545-1547).
+// One CTA per (tile, 16-row sub-block): coalesced tile reads -> smem -> row-contiguous writes.
+// ---------------------------------------------------------------------------------------------
+template <bool kKinship>
+__global__ void __launch_bounds__(256)
+king_finalize_kernel(const int32_t* __restrict__ raw_acc, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, uint32_t sample_ct, uint32_t out_row_start, uint32_t out_row_end, uint32_t* __restrict__ out_counts, double* __restrict__ out_kinship) {
+  __shared__ int32_t s_acc[16][kKingTileAccCols + 1];
+  const uint32_t tile = blockIdx.x >> 3;
+  const uint32_t sub = blockIdx.x & 7;
+  const uint32_t rt = tile_rt[tile];
+  const uint32_t tc = tile_tc[tile];
+  const uint32_t row_base = rt * kTileRows + sub * 16;
+  if (row_base >= out_row_end || row_base + 16 <= out_row_start) return;
+  const uint32_t col_base = tc * kTileCols;
+  if (col_base + 1 > row_base + 15) return;  // no strict-lower-triangle pair in this block
+  const int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kKingTileAccWords + sub * 16;
+  const uint32_t r = threadIdx.x & 15;
+  for (uint32_t cidx = threadIdx.x >> 4; cidx < kKingTileAccCols; cidx += 16) {
+    s_acc[r][cidx] = acc_tile[static_cast<uint64_t>(cidx) * kTileRows + r];
+  }
+  __syncthreads();
+  const uint64_t tri_base = static_cast<uint64_t>(out_row_start) * (out_row_start - (out_row_start ? 1 : 0)) / 2;
+  for (uint32_t rr = 0; rr < 16; ++rr) {
+    const uint32_t j = row_base + rr;
+    if (j < out_row_start || j >= out_row_end || j >= sample_ct) continue;
+    const uint64_t pair_row = static_cast<uint64_t>(j) * (j - 1) / 2 - tri_base;  // j >= 1 whenever any i < j exists
+    if (kKinship) {
+      for (uint32_t cl = threadIdx.x; cl < kTileCols; cl += 256) {
+        const uint32_t i = col_base + cl;
+        if (i >= j) continue;
+        const int32_t tt = s_acc[rr][cl];
+        const int32_t th = s_acc[rr][kTileCols + cl];
+        const int32_t ht = s_acc[rr][2 * kTileCols + cl];
+        const int32_t hh = s_acc[rr][3 * kTileCols + cl];
+        const int32_t ss = s_acc[rr][4 * kTileCols + cl];
+        const int64_t ibs0 = (hh - ss) >> 1;
+        const int64_t het2hom1 = th, het1hom2 = ht;
+        const int64_t smaller_het = tt + (het1hom2 < het2hom1 ? het1hom2 : het2hom1);
+        out_kinship[pair_row + i] = 0.5 - static_cast<double>(4 * ibs0 + het1hom2 + het2hom1) / static_cast<double>(4 * smaller_het);
+      }
+    } else {
+      for (uint32_t idx = threadIdx.x; idx < kTileCols * 5; idx += 256) {
+        const uint32_t cl = idx / 5, q = idx % 5;
+        const uint32_t i = col_base + cl;
+        if (i >= j) continue;
+        uint32_t val;
+        if (q == 0) {
+          val = static_cast<uint32_t>((s_acc[rr][3 * kTileCols + cl] - s_acc[rr][4 * kTileCols + cl]) >> 1);  // IBS0
+        } else if (q == 1) {
+          val = static_cast<uint32_t>(s_acc[rr][cl]);  // HETHET = TT
+        } else if (q == 2) {
+          val = static_cast<uint32_t>(s_acc[rr][kTileCols + cl]);  // HET2HOM1 = TH
+        } else if (q == 3) {
+          val = static_cast<uint32_t>(s_acc[rr][2 * kTileCols + cl]);  // HET1HOM2 = HT
+        } else {
+          val = static_cast<uint32_t>(s_acc[rr][3 * kTileCols + cl]);  // HOMHOM = HH
+        }
+        out_counts[(pair_row + i) * 5 + q] = val;
+      }
+    }
+  }
+}
+
+}  // namespace pl2

@@ -1,0 +1,476 @@
+// pl2gpu.cu - C-ABI entry points (include/plink2_b200.h): context, staging, KING job driver.
+#include <cstdarg>
+#include <cstring>
+#include <vector>
+
+#include "../../include/plink2_b200.h"
+#include "common.cuh"
+#include "king_kernels.cuh"
+#include "umma_probe.cuh"
+
+namespace pl2 {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+// ---- tile list over the strict lower triangle restricted to rows [row_start,row_end) ----
+static uint32_t ColTilesForRowTile(uint32_t rt, uint32_t row_end) {
+  uint32_t tile_row_end = (rt + 1) * kTileRows;
+  if (tile_row_end > row_end) tile_row_end = row_end;
+  // columns 0 .. tile_row_end-2 are needed
+  if (tile_row_end < 2) return 0;
+  return DivUpU32(tile_row_end - 1, kTileCols);
+}
+
+static uint64_t CountTiles(uint32_t row_start, uint32_t row_end) {
+  if (row_end <= row_start) return 0;
+  uint64_t n = 0;
+  for (uint32_t rt = row_start / kTileRows; rt * kTileRows < row_end; ++rt) n += ColTilesForRowTile(rt, row_end);
+  return n;
+}
+
+static int BuildTileList(uint32_t row_start, uint32_t row_end, TileList* tl) {
+  std::vector<uint32_t> rt_v, tc_v, off_v;
+  tl->row_tile_first = row_start / kTileRows;
+  uint32_t rt = tl->row_tile_first;
+  for (; rt * kTileRows < row_end; ++rt) {
+    off_v.push_back(static_cast<uint32_t>(rt_v.size()));
+    const uint32_t nct = ColTilesForRowTile(rt, row_end);
+    for (uint32_t tc = 0; tc < nct; ++tc) {
+      rt_v.push_back(rt);
+      tc_v.push_back(tc);
+    }
+  }
+  off_v.push_back(static_cast<uint32_t>(rt_v.size()));
+  tl->row_tile_ct = rt - tl->row_tile_first;
+  tl->tile_ct = static_cast<uint32_t>(rt_v.size());
+  const size_t nb = (rt_v.size() + 1) * sizeof(uint32_t);
+  PL2_CUDA_OK(cudaMalloc(&tl->d_tile_rt, nb));
+  PL2_CUDA_OK(cudaMalloc(&tl->d_tile_tc, nb));
+  PL2_CUDA_OK(cudaMalloc(&tl->d_rowtile_offset, off_v.size() * sizeof(uint32_t)));
+  if (!rt_v.empty()) {
+    PL2_CUDA_OK(cudaMemcpy(tl->d_tile_rt, rt_v.data(), rt_v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    PL2_CUDA_OK(cudaMemcpy(tl->d_tile_tc, tc_v.data(), tc_v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  }
+  PL2_CUDA_OK(cudaMemcpy(tl->d_rowtile_offset, off_v.data(), off_v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  tl->h_rowtile_offset = off_v;
+  return 0;
+}
+
+static void FreeTileList(TileList* tl) {
+  cudaFree(tl->d_tile_rt);
+  cudaFree(tl->d_tile_tc);
+  cudaFree(tl->d_rowtile_offset);
+  tl->d_tile_rt = tl->d_tile_tc = tl->d_rowtile_offset = nullptr;
+}
+
+// ---- staged genotype block on the device ----
+struct GenoStage {
+  uint8_t* d_raw = nullptr;  // [variant_cap][pitch]
+  uint32_t pitch = 0;        // bytes per variant row = sample_ct_padded / 4
+  uint32_t sample_ct = 0;
+  uint32_t sample_ct_padded = 0;
+  uint32_t variant_cap = 0;  // multiple of kVariantPad
+};
+constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
+constexpr uint32_t kMaxStageVariants = 65536;
+
+static int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs) {
+  gs->sample_ct = sample_ct;
+  gs->sample_ct_padded = RoundUpU32(sample_ct, kSamplePad);
+  gs->pitch = gs->sample_ct_padded / 4;
+  gs->variant_cap = RoundUpU32(variant_cap, kVariantPad);
+  PL2_CUDA_OK(cudaMalloc(&gs->d_raw, static_cast<uint64_t>(gs->variant_cap) * gs->pitch));
+  return 0;
+}
+
+// Copies variant_ct (<= variant_cap) rows and pads; returns the padded variant count.
+static int StageUpload(Ctx* ctx, GenoStage* gs, const void* src, uint64_t src_stride, uint32_t variant_ct, int src_is_device, uint32_t* padded_ct_ptr) {
+  const uint32_t padded = RoundUpU32(variant_ct, kVariantPad);
+  const uint32_t width = DivUpU32(gs->sample_ct, 4);
+  PL2_CUDA_OK(cudaMemcpy2DAsync(gs->d_raw, gs->pitch, src, src_stride, width, variant_ct, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  pad_genotypes_kernel<<<padded, 128, 0, ctx->stream>>>(gs->d_raw, gs->pitch, gs->sample_ct, variant_ct, padded);
+  ctx->launches++;
+  PL2_CUDA_OK(cudaGetLastError());
+  *padded_ct_ptr = padded;
+  return 0;
+}
+
+}  // namespace pl2
+
+using namespace pl2;
+
+struct Pl2GpuCtx {
+  Ctx c;
+};
+
+struct Pl2KingJob {
+  Pl2GpuCtx* ctx = nullptr;
+  uint32_t sample_ct = 0, row_start = 0, row_end = 0;
+  int algo = kPl2KingAlgoTensor;
+  TileList tiles;
+  GenoStage stage;
+  uint32_t* d_planes = nullptr;  // popcount path only
+  int32_t* d_raw_acc = nullptr;
+  void* d_out_stage = nullptr;   // bounded staging for host downloads
+  uint64_t out_stage_bytes = 0;
+  uint64_t variants_added = 0;
+};
+
+extern "C" {
+
+int pl2gpu_abi_version(void) { return 1; }
+
+const char* pl2gpu_last_error(void) { return get_error(); }
+
+int pl2gpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr) {
+  *ctx_ptr = nullptr;
+  int n = 0;
+  PL2_CUDA_OK(cudaGetDeviceCount(&n));
+  if (device_idx < 0 || device_idx >= n) {
+    set_error("pl2gpu_ctx_create: device %d out of range (%d CUDA devices visible); there is no CPU fallback", device_idx, n);
+    return 1;
+  }
+  cudaDeviceProp prop;
+  PL2_CUDA_OK(cudaGetDeviceProperties(&prop, device_idx));
+  if (prop.major != 10) {
+    set_error("pl2gpu_ctx_create: device %d is sm_%d%d; this library contains sm_100a code only", device_idx, prop.major, prop.minor);
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(device_idx));
+  Pl2GpuCtx* ctx = new Pl2GpuCtx();
+  ctx->c.device = device_idx;
+  ctx->c.sm_count = prop.multiProcessorCount;
+  PL2_CUDA_OK(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+  PL2_CUDA_OK(cudaStreamCreateWithFlags(&ctx->c.copy_stream, cudaStreamNonBlocking));
+  PL2_CUDA_OK(cudaFuncSetAttribute(king_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+  PL2_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
+  *ctx_ptr = ctx;
+  return 0;
+}
+
+int pl2gpu_ctx_destroy(Pl2GpuCtx* ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->c.device);
+  if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
+  if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
+  delete ctx;
+  return 0;
+}
+
+int pl2gpu_ctx_synchronize(Pl2GpuCtx* ctx) {
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  PL2_CUDA_OK(cudaStreamSynchronize(ctx->c.stream));
+  return 0;
+}
+
+void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx) { return ctx ? static_cast<void*>(ctx->c.stream) : nullptr; }
+
+uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+// ------------------------------------------------------------------------------------------ KING
+
+uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add) {
+  const uint64_t tiles = CountTiles(row_start, row_end);
+  uint32_t cap = max_variants_per_add ? max_variants_per_add : kMaxStageVariants;
+  if (cap > kMaxStageVariants) cap = kMaxStageVariants;
+  cap = RoundUpU32(cap, kVariantPad);
+  const uint64_t npad = RoundUpU32(sample_ct, kSamplePad);
+  const uint64_t raw = static_cast<uint64_t>(cap) * (npad / 4);
+  const uint64_t planes = 3ull * (cap / 32) * npad * 4;
+  return tiles * kKingTileAccWords * 4 + raw + planes + (256ull << 20) + tiles * 8;
+}
+
+int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr) {
+  *job_ptr = nullptr;
+  if (!ctx) {
+    set_error("pl2gpu_king_begin: null context");
+    return 1;
+  }
+  if (sample_ct < 2 || row_end > sample_ct || row_start >= row_end) {
+    set_error("pl2gpu_king_begin: bad row range [%u,%u) for %u samples", row_start, row_end, sample_ct);
+    return 1;
+  }
+  if (algo == kPl2KingAlgoAuto) algo = kPl2KingAlgoTensor;
+  if (algo != kPl2KingAlgoPopcount && algo != kPl2KingAlgoTensor) {
+    set_error("pl2gpu_king_begin: unknown algo %d", algo);
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  Pl2KingJob* job = new Pl2KingJob();
+  job->ctx = ctx;
+  job->sample_ct = sample_ct;
+  job->row_start = row_start;
+  job->row_end = row_end;
+  job->algo = algo;
+  auto fail = [&]() {
+    pl2gpu_king_end(job);
+    return 1;
+  };
+  if (BuildTileList(row_start, row_end, &job->tiles)) return fail();
+  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage)) return fail();
+  const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * kKingTileAccWords * sizeof(int32_t);
+  if (cudaMalloc(&job->d_raw_acc, acc_bytes ? acc_bytes : 4) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_king_begin: insufficient device memory for %u pair tiles (%.1f GB of accumulators); narrow the row range", job->tiles.tile_ct, acc_bytes / 1e9);
+    return fail();
+  }
+  if (cudaMemsetAsync(job->d_raw_acc, 0, acc_bytes, ctx->c.stream) != cudaSuccess) {
+    set_error("pl2gpu_king_begin: cudaMemsetAsync failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail();
+  }
+  if (algo == kPl2KingAlgoPopcount) {
+    const uint64_t plane_bytes = 3ull * (job->stage.variant_cap / 32) * job->stage.sample_ct_padded * sizeof(uint32_t);
+    if (cudaMalloc(&job->d_planes, plane_bytes) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_king_begin: insufficient device memory for bit planes");
+      return fail();
+    }
+  }
+  job->out_stage_bytes = 256ull << 20;
+  if (cudaMalloc(&job->d_out_stage, job->out_stage_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_king_begin: insufficient device memory for output staging");
+    return fail();
+  }
+  *job_ptr = job;
+  return 0;
+}
+
+int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device) {
+  if (!job) {
+    set_error("pl2gpu_king_add_variants: null job");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint64_t min_stride = 8ull * DivUpU32(job->sample_ct, 32);
+  if (variant_stride_bytes < DivUpU32(job->sample_ct, 4)) {
+    set_error("pl2gpu_king_add_variants: variant stride %llu < %u bytes of genotype data (PgrGet rows are %llu bytes)", static_cast<unsigned long long>(variant_stride_bytes), DivUpU32(job->sample_ct, 4), static_cast<unsigned long long>(min_stride));
+    return 1;
+  }
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  uint32_t done = 0;
+  while (done < variant_ct) {
+    uint32_t cur = variant_ct - done;
+    if (cur > job->stage.variant_cap) cur = job->stage.variant_cap;
+    uint32_t padded = 0;
+    // The stage buffer is reused: make sure the previous chunk's kernels are ordered before the
+    // copy (same stream => implicit).
+    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    if (job->tiles.tile_ct) {
+      if (job->algo == kPl2KingAlgoPopcount) {
+        const uint32_t word_ct = padded / 32;
+        const uint64_t warps = static_cast<uint64_t>(job->stage.sample_ct_padded / 32) * word_ct;
+        split_transpose_kernel<<<static_cast<uint32_t>(DivUpU64(warps, 8)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->stage.sample_ct_padded, word_ct, job->d_planes);
+        c->launches++;
+        king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage.sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+        c->launches++;
+      } else {
+        king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+        c->launches++;
+      }
+      PL2_CUDA_OK(cudaGetLastError());
+    }
+    if (!src_is_device) {
+      // pageable/pinned host source: the async copy has consumed it once the stream reaches here
+      // only for pinned memory; be conservative and keep host semantics simple.
+      PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    done += cur;
+  }
+  job->variants_added += variant_ct;
+  return 0;
+}
+
+static int KingGet(Pl2KingJob* job, uint32_t r0, uint32_t r1, void* dst, int dst_is_device, bool kinship) {
+  if (!job) {
+    set_error("pl2gpu_king_get: null job");
+    return 1;
+  }
+  if (r0 < job->row_start || r1 > job->row_end || r0 > r1) {
+    set_error("pl2gpu_king_get: rows [%u,%u) outside the job's [%u,%u)", r0, r1, job->row_start, job->row_end);
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint64_t bytes_per_pair = kinship ? 8 : 20;
+  auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
+  uint8_t* out = static_cast<uint8_t*>(dst);
+  uint32_t cur0 = r0;
+  while (cur0 < r1) {
+    uint32_t cur1;
+    void* d_dst;
+    if (dst_is_device) {
+      cur1 = r1;
+      d_dst = out;
+    } else {
+      // largest row block whose pairs fit the staging buffer (at least one row)
+      cur1 = cur0 + 1;
+      while (cur1 < r1 && (tri(cur1 + 1) - tri(cur0)) * bytes_per_pair <= job->out_stage_bytes) ++cur1;
+      if ((tri(cur1) - tri(cur0)) * bytes_per_pair > job->out_stage_bytes) {
+        set_error("pl2gpu_king_get: a single row exceeds the staging buffer");
+        return 1;
+      }
+      d_dst = job->d_out_stage;
+    }
+    const uint64_t pairs = tri(cur1) - tri(cur0);
+    if (pairs) {
+      const uint32_t rt_a = cur0 / kTileRows - job->tiles.row_tile_first;
+      const uint32_t rt_b = (cur1 - 1) / kTileRows - job->tiles.row_tile_first;
+      const uint32_t tile_a = job->tiles.h_rowtile_offset[rt_a];
+      const uint32_t tile_b = job->tiles.h_rowtile_offset[rt_b + 1];
+      if (tile_b > tile_a) {
+        const uint32_t grid = (tile_b - tile_a) * 8;
+        if (kinship) {
+          king_finalize_kernel<true><<<grid, 256, 0, c->stream>>>(job->d_raw_acc + static_cast<uint64_t>(tile_a) * kKingTileAccWords, job->tiles.d_tile_rt + tile_a, job->tiles.d_tile_tc + tile_a, job->sample_ct, cur0, cur1, nullptr, static_cast<double*>(d_dst));
+        } else {
+          king_finalize_kernel<false><<<grid, 256, 0, c->stream>>>(job->d_raw_acc + static_cast<uint64_t>(tile_a) * kKingTileAccWords, job->tiles.d_tile_rt + tile_a, job->tiles.d_tile_tc + tile_a, job->sample_ct, cur0, cur1, static_cast<uint32_t*>(d_dst), nullptr);
+        }
+        c->launches++;
+        PL2_CUDA_OK(cudaGetLastError());
+      }
+      if (!dst_is_device) {
+        PL2_CUDA_OK(cudaMemcpyAsync(out, d_dst, pairs * bytes_per_pair, cudaMemcpyDeviceToHost, c->stream));
+        PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+        out += pairs * bytes_per_pair;
+      }
+    }
+    cur0 = cur1;
+  }
+  if (dst_is_device) {
+    // caller synchronises through pl2gpu_ctx_synchronize / its own stream ordering
+  }
+  return 0;
+}
+
+int pl2gpu_king_get_counts(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, uint32_t* dst, int dst_is_device) {
+  return KingGet(job, out_row_start, out_row_end, dst, dst_is_device, false);
+}
+
+int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, double* dst, int dst_is_device) {
+  return KingGet(job, out_row_start, out_row_end, dst, dst_is_device, true);
+}
+
+uint64_t pl2gpu_king_variants_added(Pl2KingJob* job) { return job ? job->variants_added : 0; }
+
+int pl2gpu_king_end(Pl2KingJob* job) {
+  if (!job) return 0;
+  if (job->ctx) {
+    cudaSetDevice(job->ctx->c.device);
+    cudaStreamSynchronize(job->ctx->c.stream);
+  }
+  FreeTileList(&job->tiles);
+  cudaFree(job->stage.d_raw);
+  cudaFree(job->d_planes);
+  cudaFree(job->d_raw_acc);
+  cudaFree(job->d_out_stage);
+  cudaGetLastError();
+  delete job;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ probe
+
+int pl2gpu_debug_umma(Pl2GpuCtx* ctx, const uint8_t* a_img, uint32_t a_bytes, const uint8_t* b_img, uint32_t b_bytes, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_step_bytes, uint32_t b_step_bytes, uint32_t k_steps, uint32_t idesc, uint32_t n, int32_t* d_out_host) {
+  if (!ctx) {
+    set_error("pl2gpu_debug_umma: null context");
+    return 1;
+  }
+  Ctx* c = &ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  UmmaProbeParams prm;
+  prm.a_bytes = a_bytes;
+  prm.b_bytes = b_bytes;
+  prm.b_smem_off = RoundUpU32(a_bytes, 1024);
+  if (prm.b_smem_off + b_bytes + 1024 > kProbeSmemBytes || n > 256 || (n & 15)) {
+    set_error("pl2gpu_debug_umma: images too large or bad n");
+    return 1;
+  }
+  prm.a_lbo = a_lbo;
+  prm.a_sbo = a_sbo;
+  prm.b_lbo = b_lbo;
+  prm.b_sbo = b_sbo;
+  prm.a_step_bytes = a_step_bytes;
+  prm.b_step_bytes = b_step_bytes;
+  prm.k_steps = k_steps;
+  prm.idesc = idesc;
+  prm.n = n;
+  uint8_t *d_a = nullptr, *d_b = nullptr;
+  int32_t* d_d = nullptr;
+  PL2_CUDA_OK(cudaMalloc(&d_a, a_bytes));
+  PL2_CUDA_OK(cudaMalloc(&d_b, b_bytes));
+  PL2_CUDA_OK(cudaMalloc(&d_d, 128ull * n * 4));
+  PL2_CUDA_OK(cudaMemcpyAsync(d_a, a_img, a_bytes, cudaMemcpyHostToDevice, c->stream));
+  PL2_CUDA_OK(cudaMemcpyAsync(d_b, b_img, b_bytes, cudaMemcpyHostToDevice, c->stream));
+  umma_probe_kernel<<<1, 128, kProbeSmemBytes, c->stream>>>(d_a, d_b, prm, d_d);
+  c->launches++;
+  PL2_CUDA_OK(cudaGetLastError());
+  PL2_CUDA_OK(cudaMemcpyAsync(d_out_host, d_d, 128ull * n * 4, cudaMemcpyDeviceToHost, c->stream));
+  PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  cudaFree(d_a);
+  cudaFree(d_b);
+  cudaFree(d_d);
+  return 0;
+}
+
+int pl2gpu_selftest_umma(Pl2GpuCtx* ctx, int verbose) {
+  // Production operand layout (geno_expand.cuh operand_offset), M=128, N=96, K=64 (two k-steps).
+  const uint32_t M = 128, N = 96, K = 64;
+  const uint32_t lbo_a = operand_lbo(M), lbo_b = operand_lbo(N);
+  std::vector<uint8_t> a(M * K), b(N * K);
+  std::vector<int8_t> av(M * K), bv(N * K);
+  uint32_t seed = 12345;
+  auto rnd = [&]() {
+    seed = seed * 1664525u + 1013904223u;
+    return static_cast<int8_t>((seed >> 24) % 7) - 3;
+  };
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t k = 0; k < K; ++k) {
+      const int8_t v = rnd();
+      av[m * K + k] = v;
+      a[operand_offset(k, m / 16, lbo_a) + (m % 16)] = static_cast<uint8_t>(v);
+    }
+  for (uint32_t n = 0; n < N; ++n)
+    for (uint32_t k = 0; k < K; ++k) {
+      const int8_t v = rnd();
+      bv[n * K + k] = v;
+      b[operand_offset(k, n / 16, lbo_b) + (n % 16)] = static_cast<uint8_t>(v);
+    }
+  std::vector<int32_t> d(128 * N);
+  const uint32_t idesc = make_idesc_i8(M, N, true, true);
+  PL2_TRY(pl2gpu_debug_umma(ctx, a.data(), M * K, b.data(), N * K, lbo_a, kCoreBytes, lbo_b, kCoreBytes, 4 * lbo_a, 4 * lbo_b, K / 32, idesc, N, d.data()));
+  uint32_t bad = 0;
+  for (uint32_t m = 0; m < M; ++m)
+    for (uint32_t n = 0; n < N; ++n) {
+      int32_t ref = 0;
+      for (uint32_t k = 0; k < K; ++k) ref += static_cast<int32_t>(av[m * K + k]) * bv[n * K + k];
+      if (ref != d[m * N + n]) {
+        if (verbose && bad < 8) fprintf(stderr, "selftest_umma mismatch m=%u n=%u got=%d want=%d\n", m, n, d[m * N + n], ref);
+        ++bad;
+      }
+    }
+  if (bad) {
+    set_error("pl2gpu_selftest_umma: %u of %u accumulator entries differ from the scalar reference", bad, M * N);
+    return 1;
+  }
+  return 0;
+}
+
+}  // extern "C"

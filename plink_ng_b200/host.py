@@ -1,0 +1,154 @@
+"""Thin host-side mirror of the reference's calling conventions for tests and bench.py.
+
+Names follow the reference: `parallel_bounds` is ParallelBounds (2.0/plink2_common.cc:4956),
+genotype blocks are "genovecs" in PgrGet layout (2.0/include/pgenlib_read.h:537), KING results are
+`king_counts[pair][5]` (2.0/plink2_matrix_calc.cc:864-868).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from . import capi
+from .capi import lib, check
+
+KING_ALGO_AUTO, KING_ALGO_POPCOUNT, KING_ALGO_TENSOR = 0, 1, 2
+
+
+def pack_genotypes(geno: np.ndarray) -> np.ndarray:
+    """[variants, samples] uint8 codes (0,1,2 = ALT dosage, 3 = missing) -> genovecs
+    [variants, ceil(samples/32)] uint64 in PgrGet layout (trailing entries zero)."""
+    geno = np.ascontiguousarray(geno, dtype=np.uint8)
+    m, n = geno.shape
+    n32 = (n + 31) // 32 * 32
+    pad = np.zeros((m, n32), dtype=np.uint8)
+    pad[:, :n] = geno & 3
+    q = pad.reshape(m, n32 // 4, 4)
+    by = (q[:, :, 0] | (q[:, :, 1] << 2) | (q[:, :, 2] << 4) | (q[:, :, 3] << 6)).astype(np.uint8)
+    return np.ascontiguousarray(by).view("<u8").reshape(m, n32 // 32)
+
+
+def unpack_genotypes(genovecs: np.ndarray, sample_ct: int) -> np.ndarray:
+    by = np.ascontiguousarray(genovecs).view(np.uint8).reshape(genovecs.shape[0], -1)
+    codes = np.stack([(by >> s) & 3 for s in (0, 2, 4, 6)], axis=-1).reshape(by.shape[0], -1)
+    return np.ascontiguousarray(codes[:, :sample_ct])
+
+
+def _triangle_divide(cur_prod_x2: int, modif: int) -> int:
+    # 2.0/plink2_common.cc:4936-4954
+    if cur_prod_x2 == 0:
+        return -modif if modif < 0 else 0
+    vv = int(math.sqrt(float(cur_prod_x2)))
+    while (vv - 1) * (vv + modif - 1) >= cur_prod_x2:
+        vv -= 1
+    while vv * (vv + modif) < cur_prod_x2:
+        vv += 1
+    return vv
+
+
+def parallel_bounds(ct: int, start: int, parallel_idx: int, parallel_tot: int):
+    """ParallelBounds (2.0/plink2_common.cc:4956-4961): equal-area row range of piece k of n."""
+    modif = 1 - start * 2
+    ct_tot = ct * (ct + modif)
+    return (
+        _triangle_divide((ct_tot * parallel_idx) // parallel_tot, modif),
+        _triangle_divide((ct_tot * (parallel_idx + 1)) // parallel_tot, modif),
+    )
+
+
+class GpuContext:
+    def __init__(self, device_idx: int = 0):
+        self._h = C.c_void_p()
+        check(lib.pl2gpu_ctx_create(device_idx, C.byref(self._h)), "pl2gpu_ctx_create")
+
+    @property
+    def handle(self):
+        return self._h
+
+    def synchronize(self):
+        check(lib.pl2gpu_ctx_synchronize(self._h), "pl2gpu_ctx_synchronize")
+
+    def launch_count(self) -> int:
+        return int(lib.pl2gpu_ctx_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(lib.pl2gpu_ctx_stream(self._h) or 0)
+
+    def selftest_umma(self, verbose: bool = True):
+        check(lib.pl2gpu_selftest_umma(self._h, 1 if verbose else 0), "pl2gpu_selftest_umma")
+
+    def close(self):
+        if self._h:
+            lib.pl2gpu_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def _pairs(r0: int, r1: int) -> int:
+    tri = lambda r: r * (r - 1) // 2 if r else 0  # noqa: E731
+    return tri(r1) - tri(r0)
+
+
+class KingJob:
+    """CalcKing's dense loop (2.0/plink2_matrix_calc.cc:2016-2117) for one row range."""
+
+    def __init__(self, ctx: GpuContext, sample_ct: int, row_start: int = 0, row_end: int = None, algo: int = KING_ALGO_AUTO):
+        self.ctx = ctx
+        self.sample_ct = sample_ct
+        self.row_start = row_start
+        self.row_end = sample_ct if row_end is None else row_end
+        self._h = C.c_void_p()
+        check(lib.pl2gpu_king_begin(ctx.handle, sample_ct, self.row_start, self.row_end, algo, C.byref(self._h)), "pl2gpu_king_begin")
+
+    def add_variants(self, genovecs: np.ndarray):
+        """genovecs: host uint64 [variants, ceil(sample_ct/32)] (PgrGet rows)."""
+        g = np.ascontiguousarray(genovecs)
+        assert g.dtype == np.uint64 and g.ndim == 2 and g.shape[1] * 32 >= self.sample_ct
+        check(lib.pl2gpu_king_add_variants(self._h, g.ctypes.data, g.strides[0], g.shape[0], 0), "pl2gpu_king_add_variants")
+
+    def add_variants_device(self, dev_ptr: int, stride_bytes: int, variant_ct: int):
+        check(lib.pl2gpu_king_add_variants(self._h, C.c_void_p(dev_ptr), stride_bytes, variant_ct, 1), "pl2gpu_king_add_variants")
+
+    def counts(self, row_start: int = None, row_end: int = None) -> np.ndarray:
+        r0 = self.row_start if row_start is None else row_start
+        r1 = self.row_end if row_end is None else row_end
+        out = np.empty((_pairs(r0, r1), 5), dtype=np.uint32)
+        check(lib.pl2gpu_king_get_counts(self._h, r0, r1, out.ctypes.data, 0), "pl2gpu_king_get_counts")
+        return out
+
+    def kinship(self, row_start: int = None, row_end: int = None) -> np.ndarray:
+        r0 = self.row_start if row_start is None else row_start
+        r1 = self.row_end if row_end is None else row_end
+        out = np.empty(_pairs(r0, r1), dtype=np.float64)
+        check(lib.pl2gpu_king_get_kinship(self._h, r0, r1, out.ctypes.data, 0), "pl2gpu_king_get_kinship")
+        return out
+
+    def counts_to_device(self, dev_ptr: int, row_start: int, row_end: int):
+        check(lib.pl2gpu_king_get_counts(self._h, row_start, row_end, C.c_void_p(dev_ptr), 1), "pl2gpu_king_get_counts")
+
+    def kinship_to_device(self, dev_ptr: int, row_start: int, row_end: int):
+        check(lib.pl2gpu_king_get_kinship(self._h, row_start, row_end, C.c_void_p(dev_ptr), 1), "pl2gpu_king_get_kinship")
+
+    def close(self):
+        if self._h:
+            lib.pl2gpu_king_end(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
+def king_counts(genovecs: np.ndarray, sample_ct: int, algo: int = KING_ALGO_AUTO, device: int = 0, batch: int = 65536) -> np.ndarray:
+    """All-pairs king_counts[pair][5] for one genotype block (convenience for tests)."""
+    with GpuContext(device) as ctx, KingJob(ctx, sample_ct, 0, sample_ct, algo) as job:
+        for s in range(0, genovecs.shape[0], batch):
+            job.add_variants(genovecs[s : s + batch])
+        return job.counts()

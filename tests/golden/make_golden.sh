@@ -1,0 +1,60 @@
+#!/usr/bin/env bash
+# Regenerates the golden fixtures in this directory by running the UNMODIFIED reference binary
+# (oracle/_ref/plink2 / plink2_lapack, built by oracle/build_ref.sh from /root/reference).
+# The reference ships no golden vectors for KING / GRM / --indep-pairwise, so
+# these outputs of the reference itself are what pins the oracle (oracle/plink_oracle.py) and,
+# through it, the CUDA path.  Run from the repo root: bash tests/golden/make_golden.sh
+set -euo pipefail
+cd "$(dirname "$0")"
+P=../../oracle/_ref/plink2
+PL=../../oracle/_ref/plink2_lapack
+T=$(mktemp -d)
+# --- set A: 100 samples x 1000 variants, 3% missing, HWE genotypes, ~half the variants in LD with
+# their predecessor (2.0/plink2_import.cc:16326-16460).  --dummy output depends on --threads.
+$P --dummy 100 1000 0.03 --seed 7 --threads 2 --make-bed --out $T/a > /dev/null
+cp $T/a.bed a.bed; cp $T/a.bim a.bim; cp $T/a.fam a.fam
+$P --bfile a --make-pgen --out $T/a_pgen --threads 2 > /dev/null        # mode 0x10 (difflist / LD-compressed records)
+cp $T/a_pgen.pgen a_mode10.pgen
+$P --bfile a --make-pgen format=2 --out $T/a_f2 --threads 2 > /dev/null  # mode 0x02 fixed width
+cp $T/a_f2.pgen a_mode02.pgen; cp $T/a_f2.pvar a.pvar; cp $T/a_f2.psam a.psam
+$P --bfile a --make-king-table counts cols=+ibs1,+ibs --make-king bin4 triangle --threads 2 --out $T/a_king > /dev/null
+gzip -9 -n -c $T/a_king.kin0 > a_king.kin0.gz; cp $T/a_king.king.bin a_king.king.bin
+$P --bfile a --make-king-table --threads 2 --out $T/a_kingp > /dev/null   # default proportion columns
+gzip -9 -n -c $T/a_kingp.kin0 > a_kingp.kin0.gz
+$P --bfile a --make-king square --threads 2 --out $T/a_kingsq > /dev/null
+gzip -9 -n -c $T/a_kingsq.king > a_kingsq.king.gz; cp $T/a_kingsq.king.id a_kingsq.king.id
+$P --bfile a --make-king-table counts --parallel 2 3 --threads 2 --out $T/a_kingpar > /dev/null
+gzip -9 -n -c $T/a_kingpar.kin0.2 > a_kingpar.kin0.2.gz
+$P --bfile a --king-cutoff 0.02 --threads 2 --out $T/a_cut > /dev/null
+cp $T/a_cut.king.cutoff.in.id a_cut.king.cutoff.in.id; cp $T/a_cut.king.cutoff.out.id a_cut.king.cutoff.out.id
+$P --bfile a --freq --threads 2 --out $T/a_freq > /dev/null
+cp $T/a_freq.afreq a.afreq
+$P --bfile a --make-grm-bin --threads 2 --out $T/a_grm > /dev/null
+cp $T/a_grm.grm.bin a_grm.grm.bin; cp $T/a_grm.grm.N.bin a_grm.grm.N.bin; cp $T/a_grm.grm.id a_grm.grm.id
+$P --bfile a --make-grm-bin meanimpute --threads 2 --out $T/a_grmmi > /dev/null
+cp $T/a_grmmi.grm.bin a_grmmi.grm.bin
+$P --bfile a --make-rel cov bin4 triangle --threads 2 --out $T/a_relcov > /dev/null
+cp $T/a_relcov.rel.bin a_relcov.rel.bin
+$P --bfile a --make-rel square --threads 2 --out $T/a_rel > /dev/null
+gzip -9 -n -c $T/a_rel.rel > a_rel.rel.gz
+$P --bfile a --indep-pairwise 50 5 0.2 --threads 2 --out $T/a_ld > /dev/null
+cp $T/a_ld.prune.in a_ld.prune.in; cp $T/a_ld.prune.out a_ld.prune.out
+$P --bfile a --indep-pairwise 100 1 0.1 --threads 2 --out $T/a_ld2 > /dev/null
+cp $T/a_ld2.prune.in a_ld2.prune.in
+$P --bfile a --indep-pairwise 20kb 0.3 --threads 2 --out $T/a_ldkb > /dev/null
+cp $T/a_ldkb.prune.in a_ldkb.prune.in
+if [ -x $PL ]; then
+  $PL --bfile a --pca 4 --threads 2 --out $T/a_pca > /dev/null
+  cp $T/a_pca.eigenval a_pca.eigenval; cp $T/a_pca.eigenvec a_pca.eigenvec
+  $PL --bfile a --pca 3 approx --seed 11 --threads 2 --out $T/a_pcaa > /dev/null
+  cp $T/a_pcaa.eigenval a_pcaa.eigenval; cp $T/a_pcaa.eigenvec a_pcaa.eigenvec
+fi
+# --- set T: the reference's own toy fixture (1.9/toy.ped + toy.map; BASELINE.json configs[0])
+if [ -f /root/reference/1.9/toy.ped ]; then
+  $P --ped /root/reference/1.9/toy.ped --map /root/reference/1.9/toy.map --make-bed --out $T/toy > /dev/null
+  cp $T/toy.bed toy.bed; cp $T/toy.bim toy.bim; cp $T/toy.fam toy.fam
+  $P --bfile toy --make-king square --make-king-table counts cols=+ibs1,+ibs --out $T/toy_king > /dev/null
+  cp $T/toy_king.king toy_king.king; cp $T/toy_king.kin0 toy_king.kin0
+fi
+rm -rf $T
+ls -la
