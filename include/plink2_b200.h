@@ -51,6 +51,11 @@ int pl2gpu_ctx_synchronize(Pl2GpuCtx* ctx);
 void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx);
+/* CUDA-event timing ON THE CONTEXT'S STREAM (the stream every kernel of this library is launched
+ * on): record event `slot` (0..15) now; elapsed = milliseconds between two recorded slots (blocks
+ * until the later one has completed). */
+int pl2gpu_ctx_event_record(Pl2GpuCtx* ctx, int slot);
+int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, float* ms);
 
 /* ---- KING-robust pair counts: replaces the CalcKingDenseThread -> IncrKing/IncrKingHomhom hot
  * loop (plink2_matrix_calc.cc:1255-1334, :1533-1552) together with the reader-thread

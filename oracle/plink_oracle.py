@@ -146,3 +146,241 @@ def read_kin0_counts(path: str):
     kin = np.array([float(r[col["KINSHIP"]]) for r in rows]) if "KINSHIP" in col else None
     ids = [(r[col["IID1"]], r[col["IID2"]]) for r in rows]
     return ids, ints, kin
+
+
+# -------------------------------------------------------------------------------- allele frequencies
+def genotype_counts(geno: np.ndarray):
+    """Per-variant (hom-REF, het, hom-ALT, missing) counts - GenoarrCountFreqsUnsafe
+    (2.0/include/pgenlib_misc.cc:702)."""
+    return tuple((geno == c).sum(axis=1).astype(np.int64) for c in range(4))
+
+
+def ref_allele_freqs(geno: np.ndarray) -> np.ndarray:
+    """ComputeAlleleFreqs (2.0/plink2_filter.cc:2113-2151), biallelic hard calls, no pseudocount:
+    ref_freq = ref_count * (1.0 / total_count) (multiply by reciprocal, :2144-2148); 0.5 when the
+    variant has no non-missing founder call (:2138-2142)."""
+    n0, n1, n2, _ = genotype_counts(geno)
+    ref_ct = (2 * n0 + n1).astype(np.float64)
+    tot = (2 * (n0 + n1 + n2)).astype(np.float64)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        f = ref_ct * (1.0 / tot)
+    return np.where(tot == 0, 0.5, f)
+
+
+def major_allele_freqs(ref_freq: np.ndarray) -> np.ndarray:
+    """GetMajIdx / GetAlleleFreq (2.0/plink2_common.h:559-595): REF is major iff ref_freq >= 0.5;
+    the ALT frequency is 1.0 - ref_freq."""
+    return np.where(ref_freq >= 0.5, ref_freq, np.maximum(1.0 - ref_freq, 0.0))
+
+
+# --------------------------------------------------------------------------------------------- GRM
+def centered_varmaj(geno: np.ndarray, ref_freq: np.ndarray, variance_standardize: bool = True) -> np.ndarray:
+    """ExpandCenteredVarmaj + PopulateRescaledDosage (2.0/plink2_matrix_calc.cc:3839-3886,
+    2.0/plink2_common.cc:323-341): per variant a 4-entry table {intercept, intercept+slope,
+    intercept+2*slope, 0.0(missing)} with slope = inv_stdev, intercept = -2*alt_freq*inv_stdev.
+    Zero-variance variants contribute all zeros (the consistency checks at :3844-3868 only decide
+    whether the reference errors out)."""
+    alt = 1.0 - ref_freq
+    if variance_standardize:
+        variance = 2 * ref_freq * alt
+        ok = variance > SMALL_EPSILON
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv_stdev = np.where(ok, 1.0 / np.sqrt(variance), 0.0)
+    else:
+        ok = np.ones_like(ref_freq, dtype=bool)
+        inv_stdev = np.ones_like(ref_freq)
+    slope = inv_stdev
+    intercept = -2 * alt * inv_stdev
+    table = np.stack([intercept, intercept + slope, intercept + 2 * slope, np.zeros_like(slope)], axis=1)
+    table[~ok] = 0.0
+    return np.take_along_axis(table, geno.astype(np.int64), axis=1)  # [variants, samples]
+
+
+def grm(geno: np.ndarray, ref_freq: np.ndarray = None, meanimpute: bool = False, cov: bool = False):
+    """CalcGrm (2.0/plink2_matrix_calc.cc:4555-4788): grm = Z^T Z in fp64, then each entry divided by
+    its own observation count (M - miss_i - miss_j + bothmiss_ij; diagonal M - miss_i), or multiplied
+    by 1/M with `meanimpute` or when no variant has a missing call (:4756-4788).
+    Returns (G [N,N] float64 full symmetric, obs_counts [N,N] int64 or None)."""
+    if ref_freq is None:
+        ref_freq = ref_allele_freqs(geno)
+    z = centered_varmaj(geno, ref_freq, not cov)
+    g = z.T @ z
+    m = geno.shape[0]
+    miss = (geno == 3)
+    if meanimpute or not miss.any():
+        return g * (1.0 / float(m)), None
+    # CalcMissingMatrix (:4404-4553): only variants with >= 1 missing call are scanned; totals identical
+    mf = miss.astype(np.float64)
+    missing_cts = miss.sum(axis=0).astype(np.int64)
+    both = np.rint(mf.T @ mf).astype(np.int64)
+    obs = m - missing_cts[:, None] - missing_cts[None, :] + both
+    np.fill_diagonal(obs, m - missing_cts)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return g / obs.astype(np.float64), obs
+
+
+def lower_triangle_with_diag(mat: np.ndarray) -> np.ndarray:
+    """Row-major lower triangle including the diagonal (.grm.bin order, :4963-4971)."""
+    n = mat.shape[0]
+    return np.concatenate([mat[j, : j + 1] for j in range(n)])
+
+
+# -------------------------------------------------------------------------------- --indep-pairwise
+def ld_pair_components(x: np.ndarray, nm: np.ndarray, a: int, bs: np.ndarray):
+    """ComputeIndepPairwiseR2Components (2.0/plink2_ld.cc:699-723) for `second` = a against every
+    `first` in bs: all six integers restricted to samples non-missing in both variants.
+    x in {+1 (code 0), 0 (het), -1 (code 2), 0 (missing)}; nm = non-missing indicator."""
+    xa, na = x[a], nm[a]
+    xb, nb = x[bs], nm[bs]
+    nm_ct = nb @ na
+    dot = xb @ xa
+    s_b = xb @ na
+    q_b = (xb * xb) @ na
+    s_a = nb @ xa
+    q_a = nb @ (xa * xa)
+    r = lambda v: np.rint(v).astype(np.int64)  # noqa: E731
+    return r(nm_ct), r(s_b), r(q_b), r(s_a), r(q_a), r(dot)
+
+
+def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int, step: int, r2_thresh: float) -> np.ndarray:
+    """IndepPairwiseThread, default (non --indep-order 1) branch (2.0/plink2_ld.cc:862-1109) for one
+    subcontig.  `geno` [L, founders]; returns removed[L] bool.  Window bookkeeping follows
+    LdPruneNextSubcontig (:605-633) and LdPruneNextWindow (:635-689); `bps` is None for
+    variant-count windows.  The major-allele inversion of PgrGetInv1 (:1357) does not change any
+    decision (cov^2 and both variances are invariant under negating a variable), so plain codes are
+    used."""
+    L = geno.shape[0]
+    thr = r2_thresh * (1 + SMALL_EPSILON)  # :1255
+    x = np.where(geno == 0, 1.0, np.where(geno == 2, -1.0, 0.0)).astype(np.float32)
+    nm = (geno != 3).astype(np.float32)
+    nm_ct_v = (geno != 3).sum(axis=1)
+    plus_v = (geno == 0).sum(axis=1)
+    minus_v = (geno == 2).sum(axis=1)
+    mono = ((plus_v == 0) & (minus_v == 0)) | (plus_v == nm_ct_v) | (minus_v == nm_ct_v)  # :902
+    removed = np.zeros(L, dtype=bool)
+    if L < 2:
+        return removed
+    start = 0
+    if bps is not None:
+        bp_thresh = int(bps[0]) + window
+        first_len = 1
+        idx = 0
+        while True:
+            idx += 1
+            if not (bps[idx] <= bp_thresh):
+                break
+            first_len += 1
+            if not (first_len < L):
+                break
+        next_end = first_len
+    else:
+        next_end = min(L, window)
+    win = []          # tvidx per window position
+    win_removed = []  # cur_window_removed bit per window position
+    winpos_split = 0
+    for cur in range(L):
+        win.append(cur)
+        if mono[cur]:
+            win_removed.append(True)
+            removed[cur] = True
+        else:
+            win_removed.append(False)
+        if cur + 1 != next_end:
+            continue
+        second_stop = winpos_split if winpos_split else 1
+        for second_winpos in range(len(win) - 1, second_stop - 1, -1):
+            a = win[second_winpos]
+            firsts = np.array(win[:second_winpos], dtype=np.int64)
+            if firsts.size == 0:
+                continue
+            nm_ct, s_b, q_b, s_a, q_a, dot = ld_pair_components(x, nm, a, firsts)
+            cov12 = (dot * nm_ct - s_b * s_a).astype(np.float64)
+            var1 = (q_b * nm_ct - s_b * s_b).astype(np.float64)  # first
+            var2 = (q_a * nm_ct - s_a * s_a).astype(np.float64)  # second
+            over = cov12 * cov12 > thr * var1 * var2
+            for first_winpos in range(second_winpos - 1, -1, -1):
+                if win_removed[first_winpos]:
+                    continue
+                if over[first_winpos]:
+                    b = win[first_winpos]
+                    if maj_freq[b] <= maj_freq[a] * (1 + SMALL_EPSILON):
+                        win_removed[second_winpos] = True
+                        removed[a] = True
+                        break
+                    win_removed[first_winpos] = True
+                    removed[b] = True
+        # LdPruneNextWindow
+        if next_end == L:
+            break
+        if bps is not None:
+            min_bp = int(bps[next_end]) - window
+            nstart = start
+            while True:
+                nstart += 1
+                sbp = int(bps[nstart])
+                if not (sbp < min_bp):
+                    break
+            end_thresh = sbp + window
+            e = next_end
+            while True:
+                e += 1
+                if e == L:
+                    break
+                if not (bps[e] <= end_thresh):
+                    break
+            start, next_end = nstart, e
+        else:
+            start += step
+            next_end = min(start + window, L)
+        keep = [k for k in range(len(win)) if (not win_removed[k]) and win[k] >= start]
+        win = [win[k] for k in keep]
+        win_removed = [False] * len(win)
+        winpos_split = len(win)
+    return removed
+
+
+def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, step: int, r2_thresh: float, window_is_bp: bool = False, ref_freq: np.ndarray = None) -> np.ndarray:
+    """LdPrune -> IndepPairwise (2.0/plink2_ld.cc:2530-2724): chr0 variants are dropped up front
+    (:2542, reported in neither list), every chromosome (bp windows: every run of variants whose
+    gaps are <= window, LdPruneSubcontigSplitAll :2165-2268) with >= 2 variants is an independent
+    job; variants in singleton subcontigs are never examined (kept).  Returns removed[M] bool
+    (chr0 variants: False)."""
+    m = geno.shape[0]
+    if ref_freq is None:
+        ref_freq = ref_allele_freqs(geno)
+    majf = major_allele_freqs(ref_freq)
+    removed = np.zeros(m, dtype=bool)
+    idx_all = np.arange(m)
+    for c in [c for c in dict.fromkeys(chrom.tolist()) if c not in ("0", 0)]:
+        idx = idx_all[chrom == c]
+        if idx.size < 2:
+            continue
+        groups = []
+        if window_is_bp:
+            # split where variant_bp - window > previous bp (:2199-2211)
+            cur = [idx[0]]
+            for k in idx[1:]:
+                if int(bps[k]) >= window and int(bps[k]) - window > int(bps[cur[-1]]):
+                    groups.append(cur)
+                    cur = []
+                cur.append(k)
+            groups.append(cur)
+        else:
+            groups = [list(idx)]
+        for gidx in groups:
+            if len(gidx) < 2:
+                continue
+            gidx = np.array(gidx)
+            removed[gidx] = ld_prune_subcontig(geno[gidx], majf[gidx], bps[gidx] if window_is_bp else None, window, step, r2_thresh)
+    return removed
+
+
+def read_bim(path: str):
+    chrom, ids, bps = [], [], []
+    with open(path) as f:
+        for ln in f:
+            t = ln.split()
+            chrom.append(t[0])
+            ids.append(t[1])
+            bps.append(int(t[3]))
+    return np.array(chrom), ids, np.array(bps, dtype=np.int64)

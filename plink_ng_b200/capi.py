@@ -34,6 +34,8 @@ SIGNATURES = {
     "pl2gpu_ctx_synchronize": (C.c_int, [vp]),
     "pl2gpu_ctx_stream": (vp, [vp]),
     "pl2gpu_ctx_launch_count": (C.c_uint64, [vp]),
+    "pl2gpu_ctx_event_record": (C.c_int, [vp, C.c_int]),
+    "pl2gpu_ctx_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "pl2gpu_king_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
     "pl2gpu_king_mem_required": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "pl2gpu_king_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int]),

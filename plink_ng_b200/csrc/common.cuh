@@ -53,6 +53,7 @@ struct Ctx {
   cudaStream_t copy_stream = nullptr;
   int sm_count = 0;
   uint64_t launches = 0;
+  cudaEvent_t events[16] = {};
 };
 
 struct TileList {

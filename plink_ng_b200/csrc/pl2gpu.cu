@@ -170,6 +170,8 @@ int pl2gpu_ctx_destroy(Pl2GpuCtx* ctx) {
   cudaSetDevice(ctx->c.device);
   if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
   if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
+  for (auto& e : ctx->c.events)
+    if (e) cudaEventDestroy(e);
   delete ctx;
   return 0;
 }
@@ -183,6 +185,28 @@ int pl2gpu_ctx_synchronize(Pl2GpuCtx* ctx) {
 void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx) { return ctx ? static_cast<void*>(ctx->c.stream) : nullptr; }
 
 uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int pl2gpu_ctx_event_record(Pl2GpuCtx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= 16) {
+    set_error("pl2gpu_ctx_event_record: bad arguments");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  if (!ctx->c.events[slot]) PL2_CUDA_OK(cudaEventCreate(&ctx->c.events[slot]));
+  PL2_CUDA_OK(cudaEventRecord(ctx->c.events[slot], ctx->c.stream));
+  return 0;
+}
+
+int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, float* ms) {
+  if (!ctx || slot_from < 0 || slot_from >= 16 || slot_to < 0 || slot_to >= 16 || !ctx->c.events[slot_from] || !ctx->c.events[slot_to]) {
+    set_error("pl2gpu_ctx_event_elapsed_ms: bad arguments");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  PL2_CUDA_OK(cudaEventSynchronize(ctx->c.events[slot_to]));
+  PL2_CUDA_OK(cudaEventElapsedTime(ms, ctx->c.events[slot_from], ctx->c.events[slot_to]));
+  return 0;
+}
 
 // ------------------------------------------------------------------------------------------ KING
 

@@ -71,6 +71,14 @@ class GpuContext:
     def launch_count(self) -> int:
         return int(lib.pl2gpu_ctx_launch_count(self._h))
 
+    def event_record(self, slot: int):
+        check(lib.pl2gpu_ctx_event_record(self._h, slot), "pl2gpu_ctx_event_record")
+
+    def event_elapsed_ms(self, slot_from: int, slot_to: int) -> float:
+        ms = C.c_float()
+        check(lib.pl2gpu_ctx_event_elapsed_ms(self._h, slot_from, slot_to, C.byref(ms)), "pl2gpu_ctx_event_elapsed_ms")
+        return float(ms.value)
+
     def stream(self) -> int:
         return int(lib.pl2gpu_ctx_stream(self._h) or 0)
 
