@@ -92,6 +92,51 @@ uint64_t pl2gpu_king_variants_added(Pl2KingJob* job);
 /* Idempotent; accepts NULL. */
 int pl2gpu_king_end(Pl2KingJob* job);
 
+/* ---- GRM: replaces ExpandCenteredVarmaj + the CalcGrmThread/CalcGrmPartThread dsyrk/dgemm
+ * accumulation (2.0/plink2_matrix_calc.cc:3839-3886, :4285-4327) and the CalcMissingMatrix pass
+ * (:4404-4553) for rows [row_start,row_end) of the lower triangle (diagonal included), one
+ * TriangleFill2 slab / `--parallel` piece.  Exact int8 tcgen05 accumulation of fixed-point
+ * (32-bit) per-variant genotype tables; see DESIGN.md for the error bound. ---- */
+typedef struct Pl2GrmJob Pl2GrmJob;
+enum {
+  kPl2GrmMeanimpute = 1, /* `meanimpute` modifier: divide by the variant count, not per-pair obs counts */
+  kPl2GrmCov = 2         /* `cov` modifier: no variance standardisation (inv_stdev = 1) */
+};
+int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int flags, Pl2GrmJob** job_ptr);
+/* ref_freqs: host double[variant_ct] REF allele frequencies (the caller's allele_freqs); NULL =
+ * compute them from this block's genotype counts as ComputeAlleleFreqs does (all samples founders).
+ * Returns 2 (kPglRetDegenerateData at the call site) when a zero-variance frequency meets a
+ * non-monomorphic variant, like ExpandCenteredVarmaj :3844-3868. */
+int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs);
+/* Normalised relationship values (CalcGrm :4769-4788) for rows [r0,r1) in the reference's in-memory
+ * layout dst_grm[(j - r0) * row_stride + i], i <= j (entries i > j are left untouched / zero);
+ * dst_obs (optional) receives the per-pair observation counts as float (.grm.N.bin payload). */
+int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_grm, float* dst_obs, uint64_t row_stride, int dst_is_device);
+uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job);
+int pl2gpu_grm_end(Pl2GrmJob* job);
+
+/* ---- per-variant genotype counts {hom-REF, het, hom-ALT, missing}: the hard-call part of the
+ * LoadAlleleAndGenoCounts pre-pass (2.0/plink2.cc:2280; GenoarrCountFreqsUnsafe,
+ * 2.0/include/pgenlib_misc.cc:702) that feeds ComputeAlleleFreqs (2.0/plink2_filter.cc:2113).
+ * counts_host: uint32 [variant_ct][4] (host memory). ---- */
+int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t sample_ct, uint32_t variant_ct, int src_is_device, uint32_t* counts_host);
+
+/* ---- --indep-pairwise pair decisions: replaces ComputeIndepPairwiseR2Components (DotprodWords /
+ * SumSsqWords / SumSsqNmWords, 2.0/plink2_ld.cc:699-723, :235, :317, :578) and the r^2 test
+ * (:1085-1090) for every pair that can share a window.  flags_host[v * band + (d - 1)], 1 <= d <= band,
+ * is 1 iff for second = v, first = v - d:  cov12^2 > prune_ld_thresh * var1 * var2  (exact int64
+ * sextuple -> fp64, unfused multiplies).  genovecs: founders only, PgrGet layout. ---- */
+int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, int src_is_device, uint32_t band, double prune_ld_thresh, uint8_t* flags_host);
+
+/* ---- function face of LdPrune -> IndepPairwise (2.0/plink2_ld.h:160, 2.0/plink2_ld.cc:2530, :1116)
+ * on an in-memory founder genotype block: variants in file order with chromosome codes (0 =
+ * unplaced, never examined), bp positions (needed iff window_is_bp), window/step/r^2 as parsed from
+ * `--indep-pairwise`, optional REF allele frequencies (NULL = compute from the block, as
+ * ComputeAlleleFreqs does) and optional --indep-preferred flags.  removed_out[v] = 0 kept
+ * (.prune.in), 1 removed (.prune.out), 2 unplaced.  The GPU evaluates the pair decisions; the greedy
+ * window walk (IndepPairwiseThread, :862-1109) runs on the calling host thread. ---- */
+int pl2_indep_pairwise(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int src_is_device, uint8_t* removed_out);
+
 /* ---- self-test of the tcgen05 operand path (descriptor/layout probe); returns 0 iff an int8
  * UMMA over library-written shared-memory tiles reproduces a scalar device-side reference. ---- */
 int pl2gpu_selftest_umma(Pl2GpuCtx* ctx, int verbose);

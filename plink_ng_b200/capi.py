@@ -43,6 +43,14 @@ SIGNATURES = {
     "pl2gpu_king_get_kinship": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
     "pl2gpu_king_variants_added": (C.c_uint64, [vp]),
     "pl2gpu_king_end": (C.c_int, [vp]),
+    "pl2gpu_grm_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
+    "pl2gpu_grm_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, vp]),
+    "pl2gpu_grm_get_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, C.c_int]),
+    "pl2gpu_grm_variants_added": (C.c_uint64, [vp]),
+    "pl2gpu_grm_end": (C.c_int, [vp]),
+    "pl2gpu_geno_counts": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, vp]),
+    "pl2gpu_ld_band_flags": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_double, vp]),
+    "pl2_indep_pairwise": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_double, C.c_int, vp, vp, C.c_int, vp]),
     "pl2gpu_selftest_umma": (C.c_int, [vp, C.c_int]),
     "pl2gpu_debug_umma": (
         C.c_int,

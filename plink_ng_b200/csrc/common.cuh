@@ -64,11 +64,36 @@ struct TileList {
   uint32_t* d_tile_rt = nullptr;       // [tile_ct] row-tile index (absolute)
   uint32_t* d_tile_tc = nullptr;       // [tile_ct] col-tile index
   uint32_t* d_rowtile_offset = nullptr;  // [row_tile_ct + 1] first tile of each row tile
+  uint32_t* d_tile_order = nullptr;      // [tile_ct] launch order: 12 x 12 tile blocks so co-resident CTAs share L2 lines
   std::vector<uint32_t> h_rowtile_offset;  // host copy of the same
 };
+
+uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag);
+int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl);
+void FreeTileList(TileList* tl);
+
+// ---- staged genotype block on the device (implemented in pl2gpu.cu) ----
+struct GenoStage {
+  uint8_t* d_raw = nullptr;  // [variant_cap][pitch]
+  uint32_t pitch = 0;        // bytes per variant row = sample_ct_padded / 4
+  uint32_t sample_ct = 0;
+  uint32_t sample_ct_padded = 0;
+  uint32_t variant_cap = 0;  // multiple of kVariantPad
+};
+constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
+constexpr uint32_t kMaxStageVariants = 65536;
+int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs);
+void StageFree(GenoStage* gs);
+// Copies variant_ct (<= variant_cap) rows starting at destination row dst_row and forces padding
+// samples / rows [dst_row + variant_ct, dst_row + padded) to "missing".
+int StageUpload(Ctx* ctx, GenoStage* gs, const void* src, uint64_t src_stride, uint32_t variant_ct, int src_is_device, uint32_t* padded_ct_ptr, uint32_t dst_row = 0, uint32_t pad_to = kVariantPad);
 
 static inline uint32_t DivUpU32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 static inline uint64_t DivUpU64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
 static inline uint32_t RoundUpU32(uint32_t a, uint32_t b) { return DivUpU32(a, b) * b; }
 
 }  // namespace pl2
+
+struct Pl2GpuCtx {
+  pl2::Ctx c;
+};

@@ -1,0 +1,250 @@
+// grm.cu - GRM job driver (kernel face of CalcGrm, 2.0/plink2_matrix_calc.cc:4555-5182).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/plink2_b200.h"
+#include "common.cuh"
+#include "grm_kernels.cuh"
+#include "ld_kernels.cuh"  // geno_counts_kernel
+
+using namespace pl2;
+
+namespace {
+constexpr double kSmallEpsilon = 1.0 / 17592186044416.0;  // 2^-44
+}
+
+struct Pl2GrmJob {
+  Pl2GpuCtx* ctx = nullptr;
+  uint32_t sample_ct = 0, row_start = 0, row_end = 0;
+  int flags = 0;
+  TileList tiles;
+  GenoStage stage;
+  double* d_acc_g = nullptr;
+  int32_t* d_acc_obs = nullptr;
+  uint32_t* d_tab = nullptr;
+  double* d_lvals = nullptr;
+  uint32_t* d_counts = nullptr;
+  void* d_out_stage = nullptr;
+  uint64_t out_stage_bytes = 0;
+  uint64_t variants_added = 0;
+  uint64_t variants_with_missing = 0;
+  std::vector<double> h_lvals;
+  std::vector<uint32_t> h_counts;
+};
+
+extern "C" {
+
+int pl2gpu_grm_end(Pl2GrmJob* job);
+
+int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int flags, Pl2GrmJob** job_ptr) {
+  *job_ptr = nullptr;
+  if (!ctx || !sample_ct || row_end > sample_ct || row_start >= row_end) {
+    set_error("pl2gpu_grm_begin: bad row range [%u,%u) for %u samples", row_start, row_end, sample_ct);
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  static bool attr_set = false;
+  if (!attr_set) {
+    PL2_CUDA_OK(cudaFuncSetAttribute(grm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrmSmemBytes));
+    attr_set = true;
+  }
+  Pl2GrmJob* job = new Pl2GrmJob();
+  job->ctx = ctx;
+  job->sample_ct = sample_ct;
+  job->row_start = row_start;
+  job->row_end = row_end;
+  job->flags = flags;
+  auto fail = [&]() {
+    pl2gpu_grm_end(job);
+    return 1;
+  };
+  if (BuildTileList(row_start, row_end, true, &job->tiles)) return fail();
+  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage)) return fail();
+  const uint64_t words = static_cast<uint64_t>(job->tiles.tile_ct) * kGrmTileWords;
+  job->out_stage_bytes = 256ull << 20;
+  if (cudaMalloc(&job->d_acc_g, words * 8 + 8) != cudaSuccess || cudaMalloc(&job->d_acc_obs, words * 4 + 4) != cudaSuccess ||
+      cudaMalloc(&job->d_tab, static_cast<uint64_t>(job->stage.variant_cap) * kGrmTabStride * 4) != cudaSuccess ||
+      cudaMalloc(&job->d_lvals, static_cast<uint64_t>(job->stage.variant_cap) * 6 * 8) != cudaSuccess ||
+      cudaMalloc(&job->d_counts, static_cast<uint64_t>(job->stage.variant_cap) * 16) != cudaSuccess || cudaMalloc(&job->d_out_stage, job->out_stage_bytes) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_grm_begin: insufficient device memory for %u pair tiles (%.1f GB of accumulators); narrow the row range", job->tiles.tile_ct, words * 12 / 1e9);
+    return fail();
+  }
+  if (cudaMemsetAsync(job->d_acc_g, 0, words * 8, ctx->c.stream) != cudaSuccess || cudaMemsetAsync(job->d_acc_obs, 0, words * 4, ctx->c.stream) != cudaSuccess) {
+    set_error("pl2gpu_grm_begin: memset failed");
+    return fail();
+  }
+  *job_ptr = job;
+  return 0;
+}
+
+int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs) {
+  if (!job) {
+    set_error("pl2gpu_grm_add_variants: null job");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const bool cov = (job->flags & kPl2GrmCov) != 0;
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  for (uint32_t done = 0; done < variant_ct;) {
+    const uint32_t cur = std::min(job->stage.variant_cap, variant_ct - done);
+    uint32_t padded = 0;
+    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    // genotype counts of the batch: missingness presence, the zero-variance consistency check
+    // (ExpandCenteredVarmaj :3844-3868) and, when the caller passes no frequencies, ComputeAlleleFreqs.
+    geno_counts_kernel<<<DivUpU32(cur, 8), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->stage.sample_ct, job->stage.sample_ct_padded, cur, job->d_counts);
+    c->launches++;
+    job->h_counts.resize(4ull * cur);
+    PL2_CUDA_OK(cudaMemcpyAsync(job->h_counts.data(), job->d_counts, 16ull * cur, cudaMemcpyDeviceToHost, c->stream));
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    job->h_lvals.assign(6ull * cur, 0.0);
+    double max_l = 0.0;
+    for (uint32_t v = 0; v < cur; ++v) {
+      const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2], n3 = job->h_counts[4ull * v + 3];
+      if (n3) job->variants_with_missing++;
+      double ref_freq;
+      if (ref_freqs) {
+        ref_freq = ref_freqs[done + v];
+      } else {
+        const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);
+        ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
+      }
+      const double alt_freq = 1.0 - ref_freq;
+      double inv_stdev;
+      if (!cov) {
+        const double variance = 2 * ref_freq * alt_freq;
+        if (!(variance > kSmallEpsilon)) {
+          // reference errors out unless the variant really is monomorphic for the expected allele
+          bool bad = n1 != 0;
+          if (variance != variance) {
+            bad = bad || n0 || n2;
+          } else if (ref_freq > 0.5) {
+            bad = bad || n2;
+          } else {
+            bad = bad || n0;
+          }
+          if (bad) {
+            set_error("pl2gpu_grm_add_variants: variant %llu has zero-variance allele frequency %g but non-monomorphic genotypes (kPglRetDegenerateData, plink2_matrix_calc.cc:3844-3868)", static_cast<unsigned long long>(job->variants_added + done + v), ref_freq);
+            return 2;
+          }
+          continue;  // all-zero column
+        }
+        inv_stdev = 1.0 / sqrt(variance);
+      } else {
+        inv_stdev = 1.0;
+      }
+      // PopulateRescaledDosage lookup table (plink2_common.cc:323-330)
+      const double slope = inv_stdev;
+      const double intercept = -2 * alt_freq * inv_stdev;
+      const double z[3] = {intercept, intercept + slope, intercept + 2 * slope};
+      double* lv = &job->h_lvals[6ull * v];
+      for (int g = 0; g < 3; ++g) {
+        lv[g] = slope * z[g];          // multiplies the other sample's dosage g
+        lv[3 + g] = intercept * z[g];  // multiplies the other sample's non-missing indicator
+        max_l = std::max(max_l, std::max(fabs(lv[g]), fabs(lv[3 + g])));
+      }
+    }
+    // fixed-point scale: |L| * 2^F < 2^30 so four balanced base-256 digits always suffice
+    int f_bits = 0;
+    if (max_l > 0.0) {
+      int e;
+      frexp(max_l, &e);  // max_l = m * 2^e, m in [0.5, 1)
+      f_bits = 30 - e;
+    }
+    const double scale = ldexp(1.0, f_bits), inv_scale = ldexp(1.0, -f_bits);
+    PL2_CUDA_OK(cudaMemcpyAsync(job->d_lvals, job->h_lvals.data(), 48ull * cur, cudaMemcpyHostToDevice, c->stream));
+    grm_tables_kernel<<<DivUpU32(padded, 128), 128, 0, c->stream>>>(job->d_lvals, cur, padded, scale, job->d_tab);
+    c->launches++;
+    if (job->tiles.tile_ct) {
+      grm_tc_kernel<<<job->tiles.tile_ct, kGrmThreads, kGrmSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->d_tab, inv_scale, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_acc_g, job->d_acc_obs);
+      c->launches++;
+    }
+    PL2_CUDA_OK(cudaGetLastError());
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));  // h_lvals / host source reuse
+    done += cur;
+  }
+  job->variants_added += variant_ct;
+  return 0;
+}
+
+int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_grm, float* dst_obs, uint64_t row_stride, int dst_is_device) {
+  if (!job) {
+    set_error("pl2gpu_grm_get_rows: null job");
+    return 1;
+  }
+  if (r0 < job->row_start || r1 > job->row_end || r0 > r1 || row_stride < r1) {
+    set_error("pl2gpu_grm_get_rows: rows [%u,%u) (stride %llu) outside the job's [%u,%u)", r0, r1, static_cast<unsigned long long>(row_stride), job->row_start, job->row_end);
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const bool meanimpute = (job->flags & kPl2GrmMeanimpute) != 0;
+  const int use_obs = (!meanimpute && job->variants_with_missing) ? 1 : 0;  // CalcGrm :4756-4768
+  const double recip = job->variants_added ? 1.0 / static_cast<double>(job->variants_added) : 0.0;
+  const uint64_t per_row = row_stride * (dst_obs ? 12 : 8);
+  uint32_t cur0 = r0;
+  while (cur0 < r1) {
+    uint32_t cur1;
+    double* d_g;
+    float* d_o = nullptr;
+    if (dst_is_device) {
+      cur1 = r1;
+      d_g = dst_grm + static_cast<uint64_t>(cur0 - r0) * row_stride;
+      if (dst_obs) d_o = dst_obs + static_cast<uint64_t>(cur0 - r0) * row_stride;
+    } else {
+      const uint64_t max_rows = job->out_stage_bytes / per_row;
+      if (!max_rows) {
+        set_error("pl2gpu_grm_get_rows: a single row exceeds the staging buffer");
+        return 1;
+      }
+      cur1 = static_cast<uint32_t>(std::min<uint64_t>(r1, cur0 + max_rows));
+      d_g = static_cast<double*>(job->d_out_stage);
+      if (dst_obs) d_o = reinterpret_cast<float*>(d_g + static_cast<uint64_t>(cur1 - cur0) * row_stride);
+      PL2_CUDA_OK(cudaMemsetAsync(job->d_out_stage, 0, static_cast<uint64_t>(cur1 - cur0) * per_row, c->stream));
+    }
+    const uint32_t rt_a = cur0 / kTileRows - job->tiles.row_tile_first;
+    const uint32_t rt_b = (cur1 - 1) / kTileRows - job->tiles.row_tile_first;
+    const uint32_t tile_a = job->tiles.h_rowtile_offset[rt_a];
+    const uint32_t tile_b = job->tiles.h_rowtile_offset[rt_b + 1];
+    if (tile_b > tile_a) {
+      grm_finalize_kernel<<<(tile_b - tile_a) * 8, 256, 0, c->stream>>>(job->d_acc_g + static_cast<uint64_t>(tile_a) * kGrmTileWords, job->d_acc_obs + static_cast<uint64_t>(tile_a) * kGrmTileWords, job->tiles.d_tile_rt + tile_a, job->tiles.d_tile_tc + tile_a,
+                                                                              job->sample_ct, cur0, cur1, row_stride, use_obs, recip, d_g, d_o);
+      c->launches++;
+      PL2_CUDA_OK(cudaGetLastError());
+    }
+    if (!dst_is_device) {
+      const uint64_t n = static_cast<uint64_t>(cur1 - cur0) * row_stride;
+      PL2_CUDA_OK(cudaMemcpyAsync(dst_grm + static_cast<uint64_t>(cur0 - r0) * row_stride, d_g, n * 8, cudaMemcpyDeviceToHost, c->stream));
+      if (dst_obs) PL2_CUDA_OK(cudaMemcpyAsync(dst_obs + static_cast<uint64_t>(cur0 - r0) * row_stride, d_o, n * 4, cudaMemcpyDeviceToHost, c->stream));
+      PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    }
+    cur0 = cur1;
+  }
+  return 0;
+}
+
+uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job) { return job ? job->variants_added : 0; }
+
+int pl2gpu_grm_end(Pl2GrmJob* job) {
+  if (!job) return 0;
+  if (job->ctx) {
+    cudaSetDevice(job->ctx->c.device);
+    cudaStreamSynchronize(job->ctx->c.stream);
+  }
+  FreeTileList(&job->tiles);
+  StageFree(&job->stage);
+  cudaFree(job->d_acc_g);
+  cudaFree(job->d_acc_obs);
+  cudaFree(job->d_tab);
+  cudaFree(job->d_lvals);
+  cudaFree(job->d_counts);
+  cudaFree(job->d_out_stage);
+  cudaGetLastError();
+  delete job;
+  return 0;
+}
+
+}  // extern "C"

@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "geno_expand.cuh"
 #include "umma.cuh"
+#include "cp_async.cuh"
 
 namespace pl2 {
 
@@ -84,15 +85,6 @@ __global__ void __launch_bounds__(256) split_transpose_kernel(const uint8_t* __r
 // cp.async double buffering.  Per pair and 32 variants: 5 LOP3 + 5 POPC + 5 IADD.
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kPopcKw = 8;  // 32-variant words per smem chunk
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
 
 __global__ void __launch_bounds__(256, 1)
 king_popc_kernel(const uint32_t* __restrict__ planes, uint32_t sample_ct_padded, uint32_t word_ct, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
@@ -210,7 +202,7 @@ king_popc_kernel(const uint32_t* __restrict__ planes, uint32_t sample_ct_padded,
 // ---------------------------------------------------------------------------------------------
 constexpr uint32_t kTcKc = 64;       // variants per pipeline stage (two K=32 UMMA steps)
 constexpr uint32_t kTcStages = 4;
-constexpr uint32_t kTcLookahead = 4; // register-prefetched stages of raw genotype words
+constexpr uint32_t kTcLookahead = 4; // register-prefetched stages (per producer group) of raw genotype rows
 constexpr uint32_t kTcSuperI = 3 * kTileRows;  // 384 "samples" (3 planes x 128)
 constexpr uint32_t kTcSuperJ = 3 * kTileCols;  // 288
 constexpr uint32_t kTcLboI = operand_lbo(kTcSuperI);  // 3072
@@ -220,14 +212,15 @@ constexpr uint32_t kTcStageBytesJ = kTcSuperJ * kTcKc;  // 18432
 constexpr uint32_t kTcStageBytes = kTcStageBytesI + kTcStageBytesJ;
 constexpr uint32_t kTcSmemBytes = kTcStages * kTcStageBytes + 1024;
 constexpr uint32_t kTcProducerThreads = 256;
+constexpr uint32_t kTcGroupThreads = 128;  // two producer groups alternate stages
 constexpr uint32_t kTcThreads = kTcProducerThreads + 32;
 
-struct KingTcTables {
-  uint32_t tab[3];
-};
+__device__ __forceinline__ void sts16(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
-king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_ct_padded /* multiple of kTcKc */, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
+king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_ct_padded /* multiple of kTcKc */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full[kTcStages];
   __shared__ __align__(8) uint64_t bar_empty[kTcStages];
@@ -237,7 +230,7 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5;
   const uint32_t lane = tid & 31;
-  const uint32_t tile = blockIdx.x;
+  const uint32_t tile = tile_order[blockIdx.x];
   const uint32_t i0 = tile_rt[tile] * kTileRows;
   const uint32_t j0 = tile_tc[tile] * kTileCols;
   const uint32_t stage_iters = variant_ct_padded / kTcKc;
@@ -245,7 +238,7 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kTcStages; ++s) {
-      mbar_init(&bar_full[s], kTcProducerThreads);
+      mbar_init(&bar_full[s], kTcGroupThreads);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_acc, 1);
@@ -261,64 +254,66 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
 
   if (warp < 8) {
     // ---------------- producers ----------------
-    const bool is_i = tid < 128;
-    const uint32_t half = (tid >> 6) & 1;
-    const uint32_t k = tid & 63;
-    const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + (is_i ? (i0 / 4 + 16 * half) : (j0 / 4 + 12 * half));
+    // Group g = warp / 4 owns stages it = 2 j + g.  Within a group, thread u < 64 expands the
+    // 128 row-side samples of variant k = u (one 32-byte sector), thread u >= 64 the 96 col-side
+    // samples of variant k = u - 64 (24 bytes): every global sector is requested exactly once.
+    const uint32_t group = tid >> 7;
+    const uint32_t u = tid & 127;
+    const bool is_i = u < 64;
+    const uint32_t k = u & 63;
+    const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + (is_i ? (i0 / 4) : (j0 / 4));
     const uint64_t stage_stride = static_cast<uint64_t>(kTcKc) * pitch;
     const uint32_t lbo = is_i ? kTcLboI : kTcLboJ;
     const uint32_t groups_per_plane = is_i ? 8u : 6u;
-    const uint32_t words = is_i ? 4u : 3u;
-    const uint32_t g0 = words * half;
-    const uint32_t side_off = is_i ? 0u : kTcStageBytesI;
-    const uint32_t dst_k = operand_offset(k, 0, lbo) + side_off;
+    const uint32_t dst_k = operand_offset(k, 0, lbo) + (is_i ? 0u : kTcStageBytesI);
 
-    auto load_words = [&](uint32_t it) -> uint4 {
-      uint4 w = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+    struct Row {
+      uint32_t w[8];
+    };
+    auto load_row = [&](uint32_t it) -> Row {
+      Row r;
+#pragma unroll
+      for (uint32_t q = 0; q < 8; ++q) r.w[q] = 0xFFFFFFFFu;
       if (it < stage_iters) {
         const uint8_t* p = src + it * stage_stride;
         if (is_i) {
-          w = __ldg(reinterpret_cast<const uint4*>(p));
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(p));
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+          r.w[0] = a.x; r.w[1] = a.y; r.w[2] = a.z; r.w[3] = a.w;
+          r.w[4] = b.x; r.w[5] = b.y; r.w[6] = b.z; r.w[7] = b.w;
         } else {
-          const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
-          w.x = __ldg(q);
-          w.y = __ldg(q + 1);
-          w.z = __ldg(q + 2);
+          const uint2 a = __ldg(reinterpret_cast<const uint2*>(p));
+          const uint2 b = __ldg(reinterpret_cast<const uint2*>(p) + 1);
+          const uint2 c = __ldg(reinterpret_cast<const uint2*>(p) + 2);
+          r.w[0] = a.x; r.w[1] = a.y; r.w[2] = b.x; r.w[3] = b.y; r.w[4] = c.x; r.w[5] = c.y;
         }
       }
-      return w;
+      return r;
     };
 
-    uint4 pre[kTcLookahead];
+    Row pre[kTcLookahead];
 #pragma unroll
-    for (uint32_t d = 0; d < kTcLookahead; ++d) pre[d] = load_words(d);
+    for (uint32_t d = 0; d < kTcLookahead; ++d) pre[d] = load_row(2 * d + group);
 
-    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTcLookahead) {
+    for (uint32_t j0s = 0; 2 * j0s + group < stage_iters; j0s += kTcLookahead) {
 #pragma unroll
       for (uint32_t d = 0; d < kTcLookahead; ++d) {
-        const uint32_t it = it0 + d;
+        const uint32_t it = 2 * (j0s + d) + group;
         if (it < stage_iters) {
           const uint32_t s = it % kTcStages;
           const uint32_t ph = (it / kTcStages) & 1;
-          const uint4 cur = pre[d];
-          pre[d] = load_words(it + kTcLookahead);
+          const Row cur = pre[d];
+          pre[d] = load_row(it + 2 * kTcLookahead);
           mbar_wait(&bar_empty[s], ph ^ 1);
           const uint32_t dst = smem_base + s * kTcStageBytes + dst_k;
-          const uint32_t wv[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-          for (uint32_t q = 0; q < 4; ++q) {
-            if (q < words) {
-              const Sel4 sel = make_selectors(wv[q]);
-              const uint32_t g = g0 + q;
-              const uint4 vt = expand16(kTabHet, sel);
-              const uint4 vh = expand16(kTabHom, sel);
-              const uint4 vs = expand16(kTabSgn, sel);
-              const uint32_t a0 = dst + g * kCoreBytes;
-              const uint32_t a1 = a0 + groups_per_plane * kCoreBytes;
-              const uint32_t a2 = a1 + groups_per_plane * kCoreBytes;
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a1), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a2), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
+          for (uint32_t q = 0; q < 8; ++q) {
+            if (q < groups_per_plane) {
+              const Sel4 sel = make_selectors(cur.w[q]);
+              const uint32_t a0 = dst + q * kCoreBytes;
+              sts16(a0, expand16(kTabHet, sel));
+              sts16(a0 + groups_per_plane * kCoreBytes, expand16(kTabHom, sel));
+              sts16(a0 + 2 * groups_per_plane * kCoreBytes, expand16(kTabSgn, sel));
             }
           }
           fence_proxy_async_smem();

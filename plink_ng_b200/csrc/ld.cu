@@ -1,0 +1,279 @@
+// ld.cu - --indep-pairwise: genotype-count pass, banded r^2 decision kernel driver, and the
+// host-side greedy window walk (function face of LdPrune/IndepPairwise, 2.0/plink2_ld.cc:2530, :1116).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "../../include/plink2_b200.h"
+#include "common.cuh"
+#include "ld_kernels.cuh"
+
+using namespace pl2;
+
+namespace {
+
+constexpr double kSmallEpsilon = 1.0 / 17592186044416.0;  // 2^-44, 2.0/include/plink2_base.h kSmallEpsilon
+constexpr uint32_t kLdChunkVariants = 16384;
+
+struct DevBuf {
+  void* p = nullptr;
+  ~DevBuf() { cudaFree(p); }
+  int alloc(uint64_t bytes) {
+    if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) {
+      cudaGetLastError();
+      p = nullptr;
+      set_error("insufficient device memory (%.2f GB requested)", bytes / 1e9);
+      return 1;
+    }
+    return 0;
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t sample_ct, uint32_t variant_ct, int src_is_device, uint32_t* counts_host) {
+  if (!ctx || !sample_ct) {
+    set_error("pl2gpu_geno_counts: bad arguments");
+    return 1;
+  }
+  Ctx* c = &ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  GenoStage st;
+  const uint32_t cap = std::min<uint32_t>(kMaxStageVariants, RoundUpU32(std::max(variant_ct, 1u), kVariantPad));
+  PL2_TRY(StageAlloc(sample_ct, cap, &st));
+  DevBuf d_counts;
+  if (d_counts.alloc(16ull * cap)) {
+    StageFree(&st);
+    return 1;
+  }
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  int rc = 0;
+  for (uint32_t done = 0; done < variant_ct && !rc; done += cap) {
+    const uint32_t cur = std::min(cap, variant_ct - done);
+    uint32_t padded;
+    rc = StageUpload(c, &st, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded);
+    if (rc) break;
+    geno_counts_kernel<<<DivUpU32(cur, 8), 256, 0, c->stream>>>(st.d_raw, st.pitch, st.sample_ct, st.sample_ct_padded, cur, static_cast<uint32_t*>(d_counts.p));
+    c->launches++;
+    if (cudaMemcpyAsync(counts_host + 4ull * done, d_counts.p, 16ull * cur, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_geno_counts: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+  }
+  StageFree(&st);
+  return rc;
+}
+
+int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, int src_is_device, uint32_t band, double prune_ld_thresh, uint8_t* flags_host) {
+  if (!ctx || !founder_ct || !band) {
+    set_error("pl2gpu_ld_band_flags: bad arguments");
+    return 1;
+  }
+  Ctx* c = &ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint32_t band_r = RoundUpU32(band, 64);
+  const uint32_t rows_cap = kLdChunkVariants + band_r;
+  GenoStage st;
+  PL2_TRY(StageAlloc(founder_ct, rows_cap, &st));
+  const uint32_t word_ct = st.sample_ct_padded / 32;
+  DevBuf d_planes, d_flags;
+  if (d_planes.alloc(3ull * word_ct * rows_cap * 4) || d_flags.alloc(static_cast<uint64_t>(kLdChunkVariants) * band)) {
+    StageFree(&st);
+    return 1;
+  }
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  int rc = 0;
+  for (uint32_t a0 = 0; a0 < variant_ct && !rc; a0 += kLdChunkVariants) {
+    const uint32_t a1 = std::min(variant_ct, a0 + kLdChunkVariants);
+    const uint32_t lo = (a0 > band_r) ? (a0 - band_r) : 0;
+    uint32_t padded;
+    rc = StageUpload(c, &st, src + static_cast<uint64_t>(lo) * variant_stride_bytes, variant_stride_bytes, a1 - lo, src_is_device, &padded, 0, 64);
+    if (rc) break;
+    const uint32_t vin = padded;  // multiple of 64
+    ld_split_kernel<<<dim3(vin / 32, DivUpU32(word_ct, 32)), 1024, 0, c->stream>>>(st.d_raw, st.pitch, word_ct, vin, static_cast<uint32_t*>(d_planes.p));
+    c->launches++;
+    ld_band_kernel<<<dim3(DivUpU32(a1 - a0, 64), band_r / 64 + 1), 256, 0, c->stream>>>(static_cast<const uint32_t*>(d_planes.p), word_ct, vin, lo, a0, a1, band, prune_ld_thresh, static_cast<uint8_t*>(d_flags.p));
+    c->launches++;
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(flags_host + static_cast<uint64_t>(a0) * band, d_flags.p, static_cast<uint64_t>(a1 - a0) * band, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+    }
+  }
+  StageFree(&st);
+  return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Function face.  `variant_ct` variants in file order (already restricted to the included set),
+// `chr_codes[v]` = chromosome index (0 = unplaced -> never examined, plink2_ld.cc:2542),
+// founders only.  removed_out[v]: 0 = kept (.prune.in), 1 = removed (.prune.out), 2 = unplaced.
+// ---------------------------------------------------------------------------------------------
+int pl2_indep_pairwise(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int src_is_device, uint8_t* removed_out) {
+  if (!ctx || !variant_ct || !removed_out || !chr_codes || (window_is_bp && !variant_bps)) {
+    set_error("pl2_indep_pairwise: bad arguments");
+    return 1;
+  }
+  if (window_size < 2 || !window_incr) {
+    set_error("pl2_indep_pairwise: window size must be >= 2 and step >= 1");
+    return 1;
+  }
+  // 1. genotype counts -> allele frequencies (ComputeAlleleFreqs, plink2_filter.cc:2113-2151),
+  //    major-allele frequencies (GetMajIdx/GetAlleleFreq, plink2_common.h:559-595) and the
+  //    load-time monomorphic rule (plink2_ld.cc:902).
+  std::vector<uint32_t> counts(4ull * variant_ct);
+  PL2_TRY(pl2gpu_geno_counts(ctx, genovecs, variant_stride_bytes, founder_ct, variant_ct, src_is_device, counts.data()));
+  std::vector<double> maj_freq(variant_ct);
+  std::vector<uint8_t> mono(variant_ct);
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    const uint32_t n0 = counts[4ull * v], n1 = counts[4ull * v + 1], n2 = counts[4ull * v + 2];
+    double ref_freq;
+    if (ref_freqs) {
+      ref_freq = ref_freqs[v];
+    } else {
+      const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);
+      ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
+    }
+    double mf;
+    if (ref_freq >= 0.5) {
+      mf = ref_freq;
+    } else {
+      mf = 1.0 - ref_freq;
+      if (mf < 0.0) mf = 0.0;
+    }
+    if (preferred && preferred[v]) mf -= 1.0;  // plink2_ld.cc:916-918
+    maj_freq[v] = mf;
+    const uint32_t nm = n0 + n1 + n2;
+    mono[v] = ((!n0 && !n2) || n0 == nm || n2 == nm) ? 1 : 0;
+  }
+  // 2. subcontigs (LdPruneSubcontigSplitAll, plink2_ld.cc:2165-2268) and the widest window
+  struct Sub {
+    uint32_t first, len;
+  };
+  std::vector<Sub> subs;
+  uint32_t window_max = 0;
+  for (uint32_t v = 0; v < variant_ct; ++v) removed_out[v] = chr_codes[v] ? 0 : 2;
+  for (uint32_t s = 0; s < variant_ct;) {
+    uint32_t e = s + 1;
+    while (e < variant_ct && chr_codes[e] == chr_codes[s]) ++e;
+    if (chr_codes[s] != 0 && e - s > 1) {
+      if (!window_is_bp) {
+        subs.push_back({s, e - s});
+        window_max = std::max(window_max, std::min(e - s, window_size));
+      } else {
+        uint32_t first = s;
+        for (uint32_t v = s + 1; v <= e; ++v) {
+          const bool split = (v == e) || (variant_bps[v] >= window_size && variant_bps[v] - window_size > variant_bps[v - 1]);
+          if (split) {
+            if (v - first > 1) subs.push_back({first, v - first});
+            first = v;
+          }
+        }
+      }
+    }
+    s = e;
+  }
+  if (window_is_bp) {
+    // widest window in variant count: for each variant, how many predecessors lie within window_size bp
+    for (const Sub& sc : subs) {
+      uint32_t lo = sc.first;
+      for (uint32_t v = sc.first; v < sc.first + sc.len; ++v) {
+        while (static_cast<uint64_t>(variant_bps[lo]) + window_size < variant_bps[v]) ++lo;
+        window_max = std::max(window_max, v - lo + 1);
+      }
+    }
+  }
+  if (subs.empty()) return 0;
+  const uint32_t band = std::max(1u, window_max - 1);
+  // 3. per-pair decisions on the GPU
+  std::vector<uint8_t> flags(static_cast<uint64_t>(variant_ct) * band);
+  const double thresh = r2_thresh * (1 + kSmallEpsilon);  // plink2_ld.cc:1255
+  PL2_TRY(pl2gpu_ld_band_flags(ctx, genovecs, variant_stride_bytes, founder_ct, variant_ct, src_is_device, band, thresh, flags.data()));
+  // 4. greedy window walk per subcontig (IndepPairwiseThread default branch, plink2_ld.cc:862-1109;
+  //    LdPruneNextSubcontig :605-633, LdPruneNextWindow :635-689)
+  std::vector<uint32_t> win;
+  std::vector<uint8_t> win_removed;
+  for (const Sub& sc : subs) {
+    const uint32_t base = sc.first, L = sc.len;
+    const uint32_t* bps = window_is_bp ? (variant_bps + base) : nullptr;
+    uint32_t start = 0, next_end;
+    if (bps) {
+      const uint64_t bp_thresh = static_cast<uint64_t>(bps[0]) + window_size;
+      uint32_t first_len = 1, idx = 0;
+      while (true) {
+        ++idx;
+        if (!(bps[idx] <= bp_thresh)) break;
+        if (!(++first_len < L)) break;
+      }
+      next_end = first_len;
+    } else {
+      next_end = std::min(L, window_size);
+    }
+    win.clear();
+    win_removed.clear();
+    uint32_t winpos_split = 0;
+    for (uint32_t cur = 0; cur < L; ++cur) {
+      win.push_back(cur);
+      if (mono[base + cur]) {
+        win_removed.push_back(1);
+        removed_out[base + cur] = 1;
+      } else {
+        win_removed.push_back(0);
+      }
+      if (cur + 1 != next_end) continue;
+      const uint32_t second_stop = winpos_split ? winpos_split : 1;
+      for (uint32_t second_winpos = static_cast<uint32_t>(win.size()); second_winpos != second_stop;) {
+        --second_winpos;
+        const uint32_t a = base + win[second_winpos];
+        const uint8_t* arow = flags.data() + static_cast<uint64_t>(a) * band;
+        for (uint32_t first_winpos = second_winpos; first_winpos;) {
+          --first_winpos;
+          if (win_removed[first_winpos]) continue;
+          const uint32_t b = base + win[first_winpos];
+          if (arow[a - b - 1]) {
+            if (maj_freq[b] <= maj_freq[a] * (1 + kSmallEpsilon)) {
+              win_removed[second_winpos] = 1;
+              removed_out[a] = 1;
+              break;
+            }
+            win_removed[first_winpos] = 1;
+            removed_out[b] = 1;
+          }
+        }
+      }
+      if (next_end == L) break;
+      if (bps) {
+        const uint32_t min_bp = bps[next_end] - window_size;  // >= 0: bps[next_end] lies beyond the window
+        uint32_t nstart = start, sbp;
+        do {
+          ++nstart;
+          sbp = bps[nstart];
+        } while (sbp < min_bp);
+        const uint64_t end_thresh = static_cast<uint64_t>(sbp) + window_size;
+        uint32_t e = next_end;
+        while (true) {
+          if (++e == L) break;
+          if (!(bps[e] <= end_thresh)) break;
+        }
+        start = nstart;
+        next_end = e;
+      } else {
+        start += window_incr;
+        next_end = std::min(start + window_size, L);
+      }
+      uint32_t w = 0;
+      for (uint32_t r = 0; r < win.size(); ++r) {
+        if (!win_removed[r] && win[r] >= start) win[w++] = win[r];
+      }
+      win.resize(w);
+      win_removed.assign(w, 0);
+      winpos_split = w;
+    }
+  }
+  return 0;
+}
+
+}  // extern "C"

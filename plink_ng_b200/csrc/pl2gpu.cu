@@ -1,5 +1,6 @@
 // pl2gpu.cu - C-ABI entry points (include/plink2_b200.h): context, staging, KING job driver.
 #include <cstdarg>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 
@@ -21,28 +22,29 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 // ---- tile list over the strict lower triangle restricted to rows [row_start,row_end) ----
-static uint32_t ColTilesForRowTile(uint32_t rt, uint32_t row_end) {
+static uint32_t ColTilesForRowTile(uint32_t rt, uint32_t row_end, bool include_diag) {
   uint32_t tile_row_end = (rt + 1) * kTileRows;
   if (tile_row_end > row_end) tile_row_end = row_end;
-  // columns 0 .. tile_row_end-2 are needed
-  if (tile_row_end < 2) return 0;
-  return DivUpU32(tile_row_end - 1, kTileCols);
+  // columns 0 .. tile_row_end-2 are needed (.. tile_row_end-1 with the diagonal)
+  const uint32_t cols = include_diag ? tile_row_end : (tile_row_end ? tile_row_end - 1 : 0);
+  if (!cols) return 0;
+  return DivUpU32(cols, kTileCols);
 }
 
-static uint64_t CountTiles(uint32_t row_start, uint32_t row_end) {
+uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag) {
   if (row_end <= row_start) return 0;
   uint64_t n = 0;
-  for (uint32_t rt = row_start / kTileRows; rt * kTileRows < row_end; ++rt) n += ColTilesForRowTile(rt, row_end);
+  for (uint32_t rt = row_start / kTileRows; rt * kTileRows < row_end; ++rt) n += ColTilesForRowTile(rt, row_end, include_diag);
   return n;
 }
 
-static int BuildTileList(uint32_t row_start, uint32_t row_end, TileList* tl) {
+int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl) {
   std::vector<uint32_t> rt_v, tc_v, off_v;
   tl->row_tile_first = row_start / kTileRows;
   uint32_t rt = tl->row_tile_first;
   for (; rt * kTileRows < row_end; ++rt) {
     off_v.push_back(static_cast<uint32_t>(rt_v.size()));
-    const uint32_t nct = ColTilesForRowTile(rt, row_end);
+    const uint32_t nct = ColTilesForRowTile(rt, row_end, include_diag);
     for (uint32_t tc = 0; tc < nct; ++tc) {
       rt_v.push_back(rt);
       tc_v.push_back(tc);
@@ -61,44 +63,73 @@ static int BuildTileList(uint32_t row_start, uint32_t row_end, TileList* tl) {
   }
   PL2_CUDA_OK(cudaMemcpy(tl->d_rowtile_offset, off_v.data(), off_v.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   tl->h_rowtile_offset = off_v;
+  // launch order: blocks of kBand x kBand tiles (~ one wave of 148 CTAs) so that the CTAs resident at
+  // the same time stream the same few row/column sample ranges and hit in L2
+  constexpr uint32_t kBand = 12;
+  std::vector<uint32_t> order;
+  order.reserve(rt_v.size());
+  const uint32_t n_rt = tl->row_tile_ct;
+  for (uint32_t rb = 0; rb < n_rt; rb += kBand) {
+    const uint32_t rb_end = std::min(n_rt, rb + kBand);
+    uint32_t max_cols = 0;
+    for (uint32_t r = rb; r < rb_end; ++r) max_cols = std::max(max_cols, off_v[r + 1] - off_v[r]);
+    for (uint32_t cb = 0; cb < max_cols; cb += kBand) {
+      for (uint32_t r = rb; r < rb_end; ++r) {
+        const uint32_t ncols = off_v[r + 1] - off_v[r];
+        for (uint32_t c = cb; c < std::min(ncols, cb + kBand); ++c) order.push_back(off_v[r] + c);
+      }
+    }
+  }
+  PL2_CUDA_OK(cudaMalloc(&tl->d_tile_order, nb));
+  if (!order.empty()) PL2_CUDA_OK(cudaMemcpy(tl->d_tile_order, order.data(), order.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
   return 0;
 }
 
-static void FreeTileList(TileList* tl) {
+void FreeTileList(TileList* tl) {
   cudaFree(tl->d_tile_rt);
   cudaFree(tl->d_tile_tc);
   cudaFree(tl->d_rowtile_offset);
+  cudaFree(tl->d_tile_order);
+  tl->d_tile_order = nullptr;
   tl->d_tile_rt = tl->d_tile_tc = tl->d_rowtile_offset = nullptr;
 }
 
 // ---- staged genotype block on the device ----
-struct GenoStage {
-  uint8_t* d_raw = nullptr;  // [variant_cap][pitch]
-  uint32_t pitch = 0;        // bytes per variant row = sample_ct_padded / 4
-  uint32_t sample_ct = 0;
-  uint32_t sample_ct_padded = 0;
-  uint32_t variant_cap = 0;  // multiple of kVariantPad
-};
-constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
-constexpr uint32_t kMaxStageVariants = 65536;
-
-static int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs) {
+int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs) {
   gs->sample_ct = sample_ct;
   gs->sample_ct_padded = RoundUpU32(sample_ct, kSamplePad);
   gs->pitch = gs->sample_ct_padded / 4;
   gs->variant_cap = RoundUpU32(variant_cap, kVariantPad);
-  PL2_CUDA_OK(cudaMalloc(&gs->d_raw, static_cast<uint64_t>(gs->variant_cap) * gs->pitch));
+  if (cudaMalloc(&gs->d_raw, static_cast<uint64_t>(gs->variant_cap) * gs->pitch) != cudaSuccess) {
+    cudaGetLastError();
+    gs->d_raw = nullptr;
+    set_error("insufficient device memory for a %u-variant x %u-sample genotype stage", gs->variant_cap, sample_ct);
+    return 1;
+  }
   return 0;
 }
 
-// Copies variant_ct (<= variant_cap) rows and pads; returns the padded variant count.
-static int StageUpload(Ctx* ctx, GenoStage* gs, const void* src, uint64_t src_stride, uint32_t variant_ct, int src_is_device, uint32_t* padded_ct_ptr) {
-  const uint32_t padded = RoundUpU32(variant_ct, kVariantPad);
+void StageFree(GenoStage* gs) {
+  cudaFree(gs->d_raw);
+  gs->d_raw = nullptr;
+}
+
+int StageUpload(Ctx* ctx, GenoStage* gs, const void* src, uint64_t src_stride, uint32_t variant_ct, int src_is_device, uint32_t* padded_ct_ptr, uint32_t dst_row, uint32_t pad_to) {
+  const uint32_t padded = RoundUpU32(variant_ct, pad_to);
+  if (dst_row + padded > gs->variant_cap) {
+    set_error("StageUpload: %u + %u rows exceed the stage capacity %u", dst_row, padded, gs->variant_cap);
+    return 1;
+  }
   const uint32_t width = DivUpU32(gs->sample_ct, 4);
-  PL2_CUDA_OK(cudaMemcpy2DAsync(gs->d_raw, gs->pitch, src, src_stride, width, variant_ct, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-  pad_genotypes_kernel<<<padded, 128, 0, ctx->stream>>>(gs->d_raw, gs->pitch, gs->sample_ct, variant_ct, padded);
-  ctx->launches++;
-  PL2_CUDA_OK(cudaGetLastError());
+  uint8_t* dst = gs->d_raw + static_cast<uint64_t>(dst_row) * gs->pitch;
+  if (variant_ct) {
+    PL2_CUDA_OK(cudaMemcpy2DAsync(dst, gs->pitch, src, src_stride, width, variant_ct, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (padded) {
+    pad_genotypes_kernel<<<padded, 128, 0, ctx->stream>>>(dst, gs->pitch, gs->sample_ct, variant_ct, padded);
+    ctx->launches++;
+    PL2_CUDA_OK(cudaGetLastError());
+  }
   *padded_ct_ptr = padded;
   return 0;
 }
@@ -106,10 +137,6 @@ static int StageUpload(Ctx* ctx, GenoStage* gs, const void* src, uint64_t src_st
 }  // namespace pl2
 
 using namespace pl2;
-
-struct Pl2GpuCtx {
-  Ctx c;
-};
 
 struct Pl2KingJob {
   Pl2GpuCtx* ctx = nullptr;
@@ -211,7 +238,7 @@ int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, floa
 // ------------------------------------------------------------------------------------------ KING
 
 uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add) {
-  const uint64_t tiles = CountTiles(row_start, row_end);
+  const uint64_t tiles = CountTiles(row_start, row_end, false);
   uint32_t cap = max_variants_per_add ? max_variants_per_add : kMaxStageVariants;
   if (cap > kMaxStageVariants) cap = kMaxStageVariants;
   cap = RoundUpU32(cap, kVariantPad);
@@ -247,7 +274,7 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     pl2gpu_king_end(job);
     return 1;
   };
-  if (BuildTileList(row_start, row_end, &job->tiles)) return fail();
+  if (BuildTileList(row_start, row_end, false, &job->tiles)) return fail();
   if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage)) return fail();
   const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * kKingTileAccWords * sizeof(int32_t);
   if (cudaMalloc(&job->d_raw_acc, acc_bytes ? acc_bytes : 4) != cudaSuccess) {
@@ -307,7 +334,7 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
         king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage.sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       } else {
-        king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+        king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       }
       PL2_CUDA_OK(cudaGetLastError());
@@ -401,7 +428,7 @@ int pl2gpu_king_end(Pl2KingJob* job) {
     cudaStreamSynchronize(job->ctx->c.stream);
   }
   FreeTileList(&job->tiles);
-  cudaFree(job->stage.d_raw);
+  StageFree(&job->stage);
   cudaFree(job->d_planes);
   cudaFree(job->d_raw_acc);
   cudaFree(job->d_out_stage);

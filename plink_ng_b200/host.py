@@ -160,3 +160,79 @@ def king_counts(genovecs: np.ndarray, sample_ct: int, algo: int = KING_ALGO_AUTO
         for s in range(0, genovecs.shape[0], batch):
             job.add_variants(genovecs[s : s + batch])
         return job.counts()
+
+
+def geno_counts(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int) -> np.ndarray:
+    """uint32 [variants, 4] = {hom-REF, het, hom-ALT, missing} (GenoarrCountFreqsUnsafe)."""
+    g = np.ascontiguousarray(genovecs)
+    out = np.empty((g.shape[0], 4), dtype=np.uint32)
+    check(lib.pl2gpu_geno_counts(ctx.handle, g.ctypes.data, g.strides[0], sample_ct, g.shape[0], 0, out.ctypes.data), "pl2gpu_geno_counts")
+    return out
+
+
+def ld_band_flags(ctx: GpuContext, genovecs: np.ndarray, founder_ct: int, band: int, prune_ld_thresh: float) -> np.ndarray:
+    g = np.ascontiguousarray(genovecs)
+    out = np.zeros((g.shape[0], band), dtype=np.uint8)
+    check(lib.pl2gpu_ld_band_flags(ctx.handle, g.ctypes.data, g.strides[0], founder_ct, g.shape[0], 0, band, prune_ld_thresh, out.ctypes.data), "pl2gpu_ld_band_flags")
+    return out
+
+
+def indep_pairwise(ctx: GpuContext, genovecs: np.ndarray, founder_ct: int, chr_codes, bps, window: int, step: int, r2: float, window_is_bp: bool = False, ref_freqs=None, preferred=None) -> np.ndarray:
+    """LdPrune/IndepPairwise (2.0/plink2_ld.cc:2530) on an in-memory block -> removed[variants] uint8."""
+    g = np.ascontiguousarray(genovecs)
+    m = g.shape[0]
+    chr_codes = np.ascontiguousarray(chr_codes, dtype=np.uint32)
+    bps_a = np.ascontiguousarray(bps, dtype=np.uint32) if bps is not None else None
+    rf = np.ascontiguousarray(ref_freqs, dtype=np.float64) if ref_freqs is not None else None
+    pf = np.ascontiguousarray(preferred, dtype=np.uint8) if preferred is not None else None
+    out = np.zeros(m, dtype=np.uint8)
+    check(
+        lib.pl2_indep_pairwise(ctx.handle, g.ctypes.data, g.strides[0], founder_ct, m, chr_codes.ctypes.data, bps_a.ctypes.data if bps_a is not None else None,
+                               window, step, r2, 1 if window_is_bp else 0, rf.ctypes.data if rf is not None else None, pf.ctypes.data if pf is not None else None, 0, out.ctypes.data),
+        "pl2_indep_pairwise",
+    )
+    return out
+
+
+GRM_MEANIMPUTE, GRM_COV = 1, 2
+
+
+class GrmJob:
+    """CalcGrm's accumulation loop (2.0/plink2_matrix_calc.cc:4711-4749) for one row range."""
+
+    def __init__(self, ctx: GpuContext, sample_ct: int, row_start: int = 0, row_end: int = None, flags: int = 0):
+        self.ctx = ctx
+        self.sample_ct = sample_ct
+        self.row_start = row_start
+        self.row_end = sample_ct if row_end is None else row_end
+        self._h = C.c_void_p()
+        check(lib.pl2gpu_grm_begin(ctx.handle, sample_ct, self.row_start, self.row_end, flags, C.byref(self._h)), "pl2gpu_grm_begin")
+
+    def add_variants(self, genovecs: np.ndarray, ref_freqs=None):
+        g = np.ascontiguousarray(genovecs)
+        rf = None if ref_freqs is None else np.ascontiguousarray(ref_freqs, dtype=np.float64)
+        rc = lib.pl2gpu_grm_add_variants(self._h, g.ctypes.data, g.strides[0], g.shape[0], 0, rf.ctypes.data if rf is not None else None)
+        check(rc, "pl2gpu_grm_add_variants")
+
+    def add_variants_device(self, dev_ptr: int, stride_bytes: int, variant_ct: int, ref_freqs=None):
+        rf = None if ref_freqs is None else np.ascontiguousarray(ref_freqs, dtype=np.float64)
+        check(lib.pl2gpu_grm_add_variants(self._h, C.c_void_p(dev_ptr), stride_bytes, variant_ct, 1, rf.ctypes.data if rf is not None else None), "pl2gpu_grm_add_variants")
+
+    def rows(self, r0: int = None, r1: int = None, with_obs: bool = False):
+        r0 = self.row_start if r0 is None else r0
+        r1 = self.row_end if r1 is None else r1
+        g = np.zeros((r1 - r0, r1), dtype=np.float64)
+        obs = np.zeros((r1 - r0, r1), dtype=np.float32) if with_obs else None
+        check(lib.pl2gpu_grm_get_rows(self._h, r0, r1, g.ctypes.data, obs.ctypes.data if with_obs else None, r1, 0), "pl2gpu_grm_get_rows")
+        return (g, obs) if with_obs else g
+
+    def close(self):
+        if self._h:
+            lib.pl2gpu_grm_end(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -11,14 +11,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def _declared():
     txt = open(os.path.join(ROOT, "include", "plink2_b200.h")).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(pl2gpu_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(pl2(?:gpu)?_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_symbols_exported():
     lib = os.path.join(ROOT, "plink_ng_b200", "libpl2gpu.so")
     assert os.path.exists(lib), "build first: python -c 'import __graft_entry__ as g; g.build()'"
     out = subprocess.run(["nm", "-D", "--defined-only", lib], capture_output=True, text=True, check=True).stdout
-    exported = set(re.findall(r"\bT (pl2gpu_[a-z0-9_]+)", out))
+    exported = set(re.findall(r"\bT (pl2(?:gpu)?_[a-z0-9_]+)", out))
     declared = _declared()
     assert len(declared) >= 15
     missing = [s for s in declared if s not in exported]

@@ -26,3 +26,17 @@ with p.GpuContext(0) as ctx:
             ctx.event_record(1)
             ms = ctx.event_elapsed_ms(0, 1) / reps
             print(f"{name:9s} N={n} M={m}: {ms:9.3f} ms/batch  {pairs * m / ms / 1e9:10.2f} G pair*SNP/ms->{pairs * m / (ms * 1e-3):.3e} pair*SNP/s  int8-equiv {5 * 2 * pairs * m / (ms * 1e-3) / 1e12:8.1f} TOP/s", flush=True)
+
+# GRM kernel timing (same shape)
+from plink_ng_b200.host import GrmJob
+rf = np.random.default_rng(0).uniform(0.05, 0.95, size=m)
+with p.GpuContext(0) as ctx, GrmJob(ctx, n) as job:
+    job.add_variants_device(g.data_ptr(), words * 8, m, ref_freqs=rf)
+    ctx.synchronize()
+    ctx.event_record(0)
+    for _ in range(reps):
+        job.add_variants_device(g.data_ptr(), words * 8, m, ref_freqs=rf)
+    ctx.event_record(1)
+    ms = ctx.event_elapsed_ms(0, 1) / reps
+    tri = n * (n + 1) // 2
+    print(f"grm       N={n} M={m}: {ms:9.3f} ms/batch  int8 {9 * 2 * tri * m / (ms * 1e-3) / 1e12:8.1f} TOP/s (9 products: 8 digit + obs)", flush=True)
