@@ -68,8 +68,8 @@ struct TileList {
   std::vector<uint32_t> h_rowtile_offset;  // host copy of the same
 };
 
-uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag);
-int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl);
+uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag, uint32_t tile_cols = kTileCols);
+int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl, uint32_t tile_cols = kTileCols);
 void FreeTileList(TileList* tl);
 
 // ---- staged genotype block on the device (implemented in pl2gpu.cu) ----
@@ -82,7 +82,7 @@ struct GenoStage {
 };
 constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
 constexpr uint32_t kMaxStageVariants = 65536;
-int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs);
+int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t sample_pad = kSamplePad);
 void StageFree(GenoStage* gs);
 // Copies variant_ct (<= variant_cap) rows starting at destination row dst_row and forces padding
 // samples / rows [dst_row + variant_ct, dst_row + padded) to "missing".

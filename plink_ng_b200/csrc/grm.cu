@@ -60,8 +60,8 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
     pl2gpu_grm_end(job);
     return 1;
   };
-  if (BuildTileList(row_start, row_end, true, &job->tiles)) return fail();
-  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage)) return fail();
+  if (BuildTileList(row_start, row_end, true, &job->tiles, kGrmTileCols)) return fail();
+  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, kGrmSamplePad)) return fail();
   const uint64_t words = static_cast<uint64_t>(job->tiles.tile_ct) * kGrmTileWords;
   job->out_stage_bytes = 256ull << 20;
   if (cudaMalloc(&job->d_acc_g, words * 8 + 8) != cudaSuccess || cudaMalloc(&job->d_acc_obs, words * 4 + 4) != cudaSuccess ||
@@ -147,12 +147,12 @@ int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t varia
         max_l = std::max(max_l, std::max(fabs(lv[g]), fabs(lv[3 + g])));
       }
     }
-    // fixed-point scale: |L| * 2^F < 2^30 so four balanced base-256 digits always suffice
+    // fixed-point scale: |L| * 2^F < 2^38 so five balanced base-256 digits always suffice
     int f_bits = 0;
     if (max_l > 0.0) {
       int e;
       frexp(max_l, &e);  // max_l = m * 2^e, m in [0.5, 1)
-      f_bits = 30 - e;
+      f_bits = static_cast<int>(kGrmFixedBits) - e;
     }
     const double scale = ldexp(1.0, f_bits), inv_scale = ldexp(1.0, -f_bits);
     PL2_CUDA_OK(cudaMemcpyAsync(job->d_lvals, job->h_lvals.data(), 48ull * cur, cudaMemcpyHostToDevice, c->stream));

@@ -22,29 +22,29 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_err; }
 
 // ---- tile list over the strict lower triangle restricted to rows [row_start,row_end) ----
-static uint32_t ColTilesForRowTile(uint32_t rt, uint32_t row_end, bool include_diag) {
+static uint32_t ColTilesForRowTile(uint32_t rt, uint32_t row_end, bool include_diag, uint32_t tile_cols) {
   uint32_t tile_row_end = (rt + 1) * kTileRows;
   if (tile_row_end > row_end) tile_row_end = row_end;
   // columns 0 .. tile_row_end-2 are needed (.. tile_row_end-1 with the diagonal)
   const uint32_t cols = include_diag ? tile_row_end : (tile_row_end ? tile_row_end - 1 : 0);
   if (!cols) return 0;
-  return DivUpU32(cols, kTileCols);
+  return DivUpU32(cols, tile_cols);
 }
 
-uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag) {
+uint64_t CountTiles(uint32_t row_start, uint32_t row_end, bool include_diag, uint32_t tile_cols) {
   if (row_end <= row_start) return 0;
   uint64_t n = 0;
-  for (uint32_t rt = row_start / kTileRows; rt * kTileRows < row_end; ++rt) n += ColTilesForRowTile(rt, row_end, include_diag);
+  for (uint32_t rt = row_start / kTileRows; rt * kTileRows < row_end; ++rt) n += ColTilesForRowTile(rt, row_end, include_diag, tile_cols);
   return n;
 }
 
-int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl) {
+int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileList* tl, uint32_t tile_cols) {
   std::vector<uint32_t> rt_v, tc_v, off_v;
   tl->row_tile_first = row_start / kTileRows;
   uint32_t rt = tl->row_tile_first;
   for (; rt * kTileRows < row_end; ++rt) {
     off_v.push_back(static_cast<uint32_t>(rt_v.size()));
-    const uint32_t nct = ColTilesForRowTile(rt, row_end, include_diag);
+    const uint32_t nct = ColTilesForRowTile(rt, row_end, include_diag, tile_cols);
     for (uint32_t tc = 0; tc < nct; ++tc) {
       rt_v.push_back(rt);
       tc_v.push_back(tc);
@@ -95,9 +95,9 @@ void FreeTileList(TileList* tl) {
 }
 
 // ---- staged genotype block on the device ----
-int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs) {
+int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t sample_pad) {
   gs->sample_ct = sample_ct;
-  gs->sample_ct_padded = RoundUpU32(sample_ct, kSamplePad);
+  gs->sample_ct_padded = RoundUpU32(sample_ct, sample_pad);
   gs->pitch = gs->sample_ct_padded / 4;
   gs->variant_cap = RoundUpU32(variant_cap, kVariantPad);
   if (cudaMalloc(&gs->d_raw, static_cast<uint64_t>(gs->variant_cap) * gs->pitch) != cudaSuccess) {

@@ -1,10 +1,10 @@
 """GPU parity: GRM through the C-ABI vs the fp64 oracle (which is pinned to the reference's
 .grm.bin / .grm.N.bin / .rel.bin in tests/test_oracle_golden.py).
 
-Tolerance (north_star: 1e-5 relative): |G - G_ref| <= 1e-5 * |G_ref| + 1e-8.  The absolute floor
-(1e-8 on a matrix whose diagonal is ~1) only matters for off-diagonal entries that cancel to
-~1e-3 or less; the int8 path's own error is the 2^-(F+1) rounding of the per-variant tables
-(32 significant bits), orders of magnitude below the fp32 precision of the reference's output files.
+Tolerance (north_star: 1e-5 relative): |G - G_ref| <= 1e-5 * |G_ref| + 1e-10.  The absolute floor
+(1e-10 on a matrix whose diagonal is ~1) only matters for off-diagonal entries that cancel below
+1e-5; the int8 path's own error is the 2^-(F+1) rounding of the per-variant tables (40 significant
+bits relative to the largest table entry), far below the fp32 precision of the reference's files.
 Observation counts are exact integers."""
 import os
 
@@ -15,7 +15,7 @@ from plink_ng_b200.host import GRM_COV, GRM_MEANIMPUTE, GrmJob, pack_genotypes, 
 from oracle import plink_oracle as orc
 
 pytestmark = pytest.mark.gpu
-RTOL, ATOL = 1e-5, 1e-8
+RTOL, ATOL = 1e-5, 1e-10
 
 
 def _geno(m, n, seed, miss=0.03, lo=0.02):
@@ -45,7 +45,7 @@ def test_grm_matches_oracle(gpu_ctx, n, m, flags):
         got, got_obs = job.rows(with_obs=True)
     a, b = _got_lower(got, 0, n), _lower(want, 0, n)
     assert np.all(np.abs(a - b) <= RTOL * np.abs(b) + ATOL), float(np.max(np.abs(a - b)))
-    assert float(np.max(np.abs(a - b))) < 5e-8  # what the int8 path actually delivers at these sizes
+    assert float(np.max(np.abs(a - b))) < 1e-9  # what the 40-bit int8 path actually delivers at these sizes
     if obs is not None:
         assert np.array_equal(_got_lower(got_obs, 0, n), _lower(obs, 0, n).astype(np.float32))
 
@@ -91,7 +91,8 @@ def test_grm_rare_variants_precision(gpu_ctx):
         job.add_variants(pack_genotypes(geno))
         got = job.rows()
     a, b = _got_lower(got, 0, n), _lower(want, 0, n)
-    assert np.all(np.abs(a - b) <= RTOL * np.abs(b) + ATOL), float(np.max(np.abs(a - b)))
+    # singleton weights are ~800x the common-variant ones, so the shared fixed-point scale costs ~10 bits
+    assert np.all(np.abs(a - b) <= RTOL * np.abs(b) + 2e-9), float(np.max(np.abs(a - b)))
 
 
 def test_grm_degenerate_frequency_is_an_error(gpu_ctx):
