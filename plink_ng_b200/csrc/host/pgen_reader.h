@@ -1,0 +1,57 @@
+// pgen_reader.h - the slice of the pgenlib reader surface the pairwise-genotype commands use
+// (2.0/include/pgenlib_read.h:442-747): open a .bed / .pgen, then PgrGet-style sequential or
+// random access to variant-major packed 2-bit hard calls, optionally restricted to a sample
+// subset.  Format per pgen_spec/pgen_spec.tex: storage modes 0x01 (.bed, :132-136), 0x02 (fixed
+// width, :137-139) and 0x10 (variable width, :144-145) with main-track record types 0 (raw), 1
+// (1-bit + difflist), 2/3 (LD-compressed), 4/6/7 (difflist against a constant) (:443-468).
+// Auxiliary tracks (multiallelic, phase, dosage; record-type bits 3-7) are not hard calls of a
+// biallelic variant: multiallelic records are rejected, phase/dosage tracks are ignored exactly as
+// PgrGet ignores them.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pl2host {
+
+class PgenReader {
+ public:
+  // raw_sample_ct is required for .bed (the file does not store it) and cross-checked otherwise.
+  // 0 = "unknown" for .pgen.  Returns false and sets *err on failure.
+  bool Open(const std::string& path, uint32_t raw_sample_ct, uint32_t raw_variant_ct, std::string* err);
+  void Close();
+  ~PgenReader() { Close(); }
+
+  uint32_t raw_sample_ct() const { return raw_sample_ct_; }
+  uint32_t raw_variant_ct() const { return raw_variant_ct_; }
+  // uint64 words per variant for n samples: ceil(n / 32)
+  static uint32_t WordsFor(uint32_t n) { return (n + 31) / 32; }
+
+  // PgrGet without subsetting: all raw samples of variant `vidx` into genovec[WordsFor(raw_sample_ct)].
+  // Codes 0 hom-REF, 1 het, 2 hom-ALT, 3 missing; trailing entries of the last word are zero.
+  bool Get(uint32_t vidx, uint64_t* genovec, std::string* err);
+  // PgrGet with a sample subset (sample_include bitset over raw samples, sample_ct set bits):
+  // subsetted genovec[WordsFor(sample_ct)] (CopyNyparrNonemptySubset semantics).
+  bool GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err);
+
+ private:
+  bool DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err);
+  bool ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err);
+  bool ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after);
+
+  int fd_ = -1;
+  const uint8_t* map_ = nullptr;
+  uint64_t map_len_ = 0;
+  uint8_t mode_ = 0;
+  uint32_t raw_sample_ct_ = 0;
+  uint32_t raw_variant_ct_ = 0;
+  uint64_t fixed_start_ = 0;      // modes 0x01/0x02: offset of record 0
+  uint32_t fixed_bpv_ = 0;
+  std::vector<uint8_t> vrtypes_;  // mode 0x10
+  std::vector<uint64_t> rec_off_; // mode 0x10: [raw_variant_ct + 1]
+  std::vector<uint64_t> ldbase_;  // last non-LD-compressed genovec
+  uint32_t ldbase_vidx_ = 0xFFFFFFFFu;
+  std::vector<uint64_t> scratch_;
+};
+
+}  // namespace pl2host

@@ -1,0 +1,291 @@
+#include "text_util.h"
+
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace pl2host {
+
+namespace {
+
+// Round-half-to-even with the reference's tolerance band: values within 5e-9 of a .5 tie are
+// treated as exact ties (kBankerRound8, plink2_string.cc:2232-2237).
+inline uint32_t RoundTol(double x) {
+  uint32_t r = static_cast<uint32_t>(static_cast<int32_t>(x));
+  const double bump = (r & 1) ? 0.500000005 : 0.499999995;
+  r += static_cast<uint32_t>(static_cast<int32_t>((x - static_cast<double>(r)) + bump));
+  return r;
+}
+
+// digits of `v` zero-padded to `width`, trailing zeros removed (at least one digit kept when
+// keep_one); returns new end
+inline char* PutFrac(uint32_t v, int width, char* p) {
+  char tmp[12];
+  for (int i = width - 1; i >= 0; --i) {
+    tmp[i] = static_cast<char>('0' + v % 10);
+    v /= 10;
+  }
+  int n = width;
+  while (n > 0 && tmp[n - 1] == '0') --n;
+  memcpy(p, tmp, n);
+  return p + n;
+}
+
+inline char* PutExp(uint32_t e, char sign, char* p) {
+  *p++ = 'e';
+  *p++ = sign;
+  if (e >= 100) {
+    *p++ = static_cast<char>('0' + e / 100);
+    e %= 100;
+  }
+  *p++ = static_cast<char>('0' + e / 10);
+  *p++ = static_cast<char>('0' + e % 10);
+  return p;
+}
+
+// one leading digit + up to 5 decimals from x in [0.99999949999999, 9.9999949999999)
+inline char* PutMantissa(double x, char* p) {
+  const uint32_t v = RoundTol(x * 100000);
+  *p++ = static_cast<char>('0' + v / 100000);
+  const uint32_t rem = v % 100000;
+  if (rem) {
+    *p++ = '.';
+    p = PutFrac(rem, 5, p);
+  }
+  return p;
+}
+
+}  // namespace
+
+char* u32toa(uint32_t x, char* buf) {
+  char tmp[12];
+  int n = 0;
+  do {
+    tmp[n++] = static_cast<char>('0' + x % 10);
+    x /= 10;
+  } while (x);
+  while (n) *buf++ = tmp[--n];
+  return buf;
+}
+
+char* i32toa(int32_t x, char* buf) {
+  if (x < 0) {
+    *buf++ = '-';
+    return u32toa(static_cast<uint32_t>(-static_cast<int64_t>(x)), buf);
+  }
+  return u32toa(static_cast<uint32_t>(x), buf);
+}
+
+char* dtoa_g(double x, char* p) {
+  if (x != x) {
+    memcpy(p, "nan", 3);
+    return p + 3;
+  }
+  if (x < 0) {
+    *p++ = '-';
+    x = -x;
+  }
+  if (x < 9.9999949999999e-5) {
+    // exponential notation, small: scale up by the binary decomposition of the exponent
+    uint32_t xp10 = 0;
+    if (x < 9.9999949999999e-16) {
+      if (x < 9.9999949999999e-128) {
+        if (x == 0.0) {
+          *p++ = '0';
+          return p;
+        }
+        if (x < 9.9999949999999e-256) {
+          x *= 1.0e256;
+          xp10 |= 256;
+        } else {
+          x *= 1.0e128;
+          xp10 |= 128;
+        }
+      }
+      if (x < 9.9999949999999e-64) {
+        x *= 1.0e64;
+        xp10 |= 64;
+      }
+      if (x < 9.9999949999999e-32) {
+        x *= 1.0e32;
+        xp10 |= 32;
+      }
+      if (x < 9.9999949999999e-16) {
+        x *= 1.0e16;
+        xp10 |= 16;
+      }
+    }
+    if (x < 9.9999949999999e-8) {
+      x *= 100000000;
+      xp10 |= 8;
+    }
+    if (x < 9.9999949999999e-4) {
+      x *= 10000;
+      xp10 |= 4;
+    }
+    if (x < 9.9999949999999e-2) {
+      x *= 100;
+      xp10 |= 2;
+    }
+    if (x < 9.9999949999999e-1) {
+      x *= 10;
+      ++xp10;
+    }
+    return PutExp(xp10, '-', PutMantissa(x, p));
+  }
+  if (x >= 999999.49999999) {
+    uint32_t xp10 = 0;
+    if (x >= 9.9999949999999e15) {
+      if (x >= 9.9999949999999e127) {
+        if (x > DBL_MAX) {
+          memcpy(p, "inf", 3);
+          return p + 3;
+        }
+        if (x >= 9.9999949999999e255) {
+          x *= 1.0e-256;
+          xp10 |= 256;
+        } else {
+          x *= 1.0e-128;
+          xp10 |= 128;
+        }
+      }
+      if (x >= 9.9999949999999e63) {
+        x *= 1.0e-64;
+        xp10 |= 64;
+      }
+      if (x >= 9.9999949999999e31) {
+        x *= 1.0e-32;
+        xp10 |= 32;
+      }
+      if (x >= 9.9999949999999e15) {
+        x *= 1.0e-16;
+        xp10 |= 16;
+      }
+    }
+    if (x >= 9.9999949999999e7) {
+      x *= 1.0e-8;
+      xp10 |= 8;
+    }
+    if (x >= 9.9999949999999e3) {
+      x *= 1.0e-4;
+      xp10 |= 4;
+    }
+    if (x >= 9.9999949999999e1) {
+      x *= 1.0e-2;
+      xp10 |= 2;
+    }
+    if (x >= 9.9999949999999e0) {
+      x *= 1.0e-1;
+      ++xp10;
+    }
+    return PutExp(xp10, '+', PutMantissa(x, p));
+  }
+  if (x >= 0.99999949999999) {
+    // k integer digits, 6 - k decimals
+    static const double kUpper[5] = {9.9999949999999, 99.999949999999, 999.99949999999, 9999.9949999999, 99999.949999999};
+    static const double kScale[6] = {100000, 10000, 1000, 100, 10, 1};
+    static const uint32_t kDiv[6] = {100000, 10000, 1000, 100, 10, 1};
+    int k = 0;
+    while (k < 5 && !(x < kUpper[k])) ++k;  // k + 1 integer digits
+    const uint32_t v = (k == 5) ? RoundTol(x) : RoundTol(x * kScale[k]);
+    p = u32toa(v / kDiv[k], p);
+    const uint32_t rem = v % kDiv[k];
+    if (rem) {
+      *p++ = '.';
+      p = PutFrac(rem, 5 - k, p);
+    }
+    return p;
+  }
+  // 0.0001 <= x < 1
+  *p++ = '0';
+  *p++ = '.';
+  if (x < 9.9999949999999e-3) {
+    x *= 100;
+    *p++ = '0';
+    *p++ = '0';
+  }
+  if (x < 9.9999949999999e-2) {
+    x *= 10;
+    *p++ = '0';
+  }
+  char* q = PutFrac(RoundTol(x * 1000000), 6, p);
+  if (q == p) *q++ = '0';
+  return q;
+}
+
+bool OutFile::Open(const std::string& path) {
+  f_ = fopen(path.c_str(), "wb");
+  buf_.resize(1 << 20);
+  pos_ = 0;
+  ok_ = f_ != nullptr;
+  return ok_;
+}
+
+void OutFile::Flush() {
+  if (f_ && pos_) {
+    if (fwrite(buf_.data(), 1, pos_, f_) != pos_) ok_ = false;
+  }
+  pos_ = 0;
+}
+
+bool OutFile::Close() {
+  if (f_) {
+    Flush();
+    if (fclose(f_)) ok_ = false;
+    f_ = nullptr;
+  }
+  return ok_;
+}
+
+char* OutFile::Reserve(size_t n) {
+  if (pos_ + n > buf_.size()) {
+    Flush();
+    if (n > buf_.size()) buf_.resize(n);
+  }
+  return buf_.data() + pos_;
+}
+
+void OutFile::Write(const void* p, size_t n) {
+  if (n >= buf_.size() / 2) {
+    Flush();
+    if (f_ && fwrite(p, 1, n, f_) != n) ok_ = false;
+    return;
+  }
+  char* d = Reserve(n);
+  memcpy(d, p, n);
+  pos_ += n;
+}
+
+void OutFile::Puts(const char* s) { Write(s, strlen(s)); }
+
+std::vector<std::string> SplitWs(const std::string& line) {
+  std::vector<std::string> out;
+  size_t i = 0, n = line.size();
+  while (i < n) {
+    while (i < n && (line[i] == ' ' || line[i] == '\t' || line[i] == '\r' || line[i] == '\n')) ++i;
+    if (i >= n) break;
+    size_t j = i;
+    while (j < n && !(line[j] == ' ' || line[j] == '\t' || line[j] == '\r' || line[j] == '\n')) ++j;
+    out.emplace_back(line, i, j - i);
+    i = j;
+  }
+  return out;
+}
+
+bool ReadLines(const std::string& path, std::vector<std::string>* lines, std::string* err) {
+  std::ifstream in(path);
+  if (!in) {
+    *err = "Failed to open " + path + ".";
+    return false;
+  }
+  std::string ln;
+  while (std::getline(in, ln)) {
+    if (!ln.empty() && ln.back() == '\r') ln.pop_back();
+    lines->push_back(ln);
+  }
+  return true;
+}
+
+}  // namespace pl2host
