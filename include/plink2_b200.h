@@ -51,6 +51,11 @@ int pl2gpu_ctx_synchronize(Pl2GpuCtx* ctx);
 void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx);
+/* Free / total device memory in bytes (pass planning, the analogue of bigstack_left()). */
+int pl2gpu_ctx_mem_info(Pl2GpuCtx* ctx, uint64_t* free_bytes, uint64_t* total_bytes);
+/* Page-locked host buffers for genotype blocks / results (async copies need them). */
+int pl2gpu_host_alloc(uint64_t bytes, void** ptr);
+int pl2gpu_host_free(void* ptr);
 /* CUDA-event timing ON THE CONTEXT'S STREAM (the stream every kernel of this library is launched
  * on): record event `slot` (0..15) now; elapsed = milliseconds between two recorded slots (blocks
  * until the later one has completed). */

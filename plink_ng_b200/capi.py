@@ -34,6 +34,9 @@ SIGNATURES = {
     "pl2gpu_ctx_synchronize": (C.c_int, [vp]),
     "pl2gpu_ctx_stream": (vp, [vp]),
     "pl2gpu_ctx_launch_count": (C.c_uint64, [vp]),
+    "pl2gpu_ctx_mem_info": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "pl2gpu_host_alloc": (C.c_int, [C.c_uint64, C.POINTER(vp)]),
+    "pl2gpu_host_free": (C.c_int, [vp]),
     "pl2gpu_ctx_event_record": (C.c_int, [vp, C.c_int]),
     "pl2gpu_ctx_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "pl2gpu_king_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),

@@ -1,0 +1,135 @@
+#include "dataset.h"
+
+#include <cstdlib>
+#include <cstring>
+
+#include "text_util.h"
+
+namespace pl2host {
+
+namespace {
+
+// human chromosome codes (the reference's default chr-set): 1-22, X=23, Y=24, XY=25, MT=26, 0 unplaced
+bool ParseChr(const std::string& tok, uint32_t* code) {
+  const char* s = tok.c_str();
+  if ((s[0] == 'c' || s[0] == 'C') && (s[1] == 'h' || s[1] == 'H') && (s[2] == 'r' || s[2] == 'R')) s += 3;
+  if (!*s) return false;
+  char* endp = nullptr;
+  const long v = strtol(s, &endp, 10);
+  if (endp != s && !*endp) {
+    if (v < 0 || v > 26) return false;
+    *code = static_cast<uint32_t>(v);
+    return true;
+  }
+  std::string u(s);
+  for (auto& c : u) c = static_cast<char>(toupper(c));
+  if (u == "X") *code = 23;
+  else if (u == "Y") *code = 24;
+  else if (u == "XY" || u == "PAR1" || u == "PAR2") *code = 25;
+  else if (u == "MT" || u == "M") *code = 26;
+  else return false;
+  return true;
+}
+
+}  // namespace
+
+bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
+  std::vector<std::string> lines;
+  if (!ReadLines(path, &lines, err)) return false;
+  size_t li = 0;
+  // .psam: optional '##' comment lines then a '#FID ...' / '#IID ...' header; .fam: no header, 6 columns
+  while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
+  int col_fid = -1, col_iid = -1, col_sid = -1, col_pat = -1, col_mat = -1;
+  if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
+    std::vector<std::string> hdr = SplitWs(lines[li].substr(1));
+    for (size_t c = 0; c < hdr.size(); ++c) {
+      if (hdr[c] == "FID") col_fid = static_cast<int>(c);
+      else if (hdr[c] == "IID") col_iid = static_cast<int>(c);
+      else if (hdr[c] == "SID") col_sid = static_cast<int>(c);
+      else if (hdr[c] == "PAT") col_pat = static_cast<int>(c);
+      else if (hdr[c] == "MAT") col_mat = static_cast<int>(c);
+    }
+    if (col_iid < 0 || (col_fid > 0)) {
+      *err = "Invalid .psam header line in " + path + " (#FID or #IID must come first).";
+      return false;
+    }
+    ++li;
+  } else {
+    col_fid = 0;
+    col_iid = 1;
+    col_pat = 2;
+    col_mat = 3;
+  }
+  out->fid_present = col_fid >= 0;
+  out->sid_present = col_sid >= 0;
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    std::vector<std::string> t = SplitWs(lines[li]);
+    if (t.empty()) continue;
+    const int need = std::max(std::max(col_iid, col_sid), std::max(col_pat, col_mat));
+    if (static_cast<int>(t.size()) <= need) {
+      *err = "Line " + std::to_string(li + 1) + " of " + path + " has fewer tokens than expected.";
+      return false;
+    }
+    out->fid.push_back(col_fid >= 0 ? t[col_fid] : "0");
+    out->iid.push_back(t[col_iid]);
+    out->sid.push_back(col_sid >= 0 ? t[col_sid] : "0");
+    const bool founder = (col_pat < 0 || t[col_pat] == "0") && (col_mat < 0 || t[col_mat] == "0");
+    out->is_founder.push_back(founder ? 1 : 0);
+  }
+  if (out->iid.empty()) {
+    *err = "No samples in " + path + ".";
+    return false;
+  }
+  return true;
+}
+
+bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
+  std::vector<std::string> lines;
+  if (!ReadLines(path, &lines, err)) return false;
+  size_t li = 0;
+  while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
+  int col_chr, col_pos, col_id;
+  if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
+    // .pvar header: #CHROM POS ID REF ALT ...
+    std::vector<std::string> hdr = SplitWs(lines[li].substr(1));
+    col_chr = col_pos = col_id = -1;
+    for (size_t c = 0; c < hdr.size(); ++c) {
+      if (hdr[c] == "CHROM") col_chr = static_cast<int>(c);
+      else if (hdr[c] == "POS") col_pos = static_cast<int>(c);
+      else if (hdr[c] == "ID") col_id = static_cast<int>(c);
+    }
+    if (col_chr != 0 || col_pos < 0 || col_id < 0) {
+      *err = "Invalid .pvar header line in " + path + ".";
+      return false;
+    }
+    ++li;
+  } else {
+    // .bim: CHROM ID CM POS A1 A2   (5-column variant without CM also accepted)
+    col_chr = 0;
+    col_id = 1;
+    col_pos = 3;
+  }
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    std::vector<std::string> t = SplitWs(lines[li]);
+    if (t.empty()) continue;
+    int cpos = col_pos;
+    if (col_pos == 3 && t.size() == 5) cpos = 2;
+    if (static_cast<int>(t.size()) <= std::max(cpos, col_id)) {
+      *err = "Line " + std::to_string(li + 1) + " of " + path + " has fewer tokens than expected.";
+      return false;
+    }
+    uint32_t code;
+    if (!ParseChr(t[col_chr], &code)) {
+      *err = "Invalid chromosome code '" + t[col_chr] + "' on line " + std::to_string(li + 1) + " of " + path + " (contigs outside the human chromosome set are not supported).";
+      return false;
+    }
+    out->chr_code.push_back(code);
+    out->bp.push_back(static_cast<uint32_t>(strtoul(t[cpos].c_str(), nullptr, 10)));
+    out->id.push_back(t[col_id]);
+  }
+  return true;
+}
+
+}  // namespace pl2host

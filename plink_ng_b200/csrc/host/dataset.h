@@ -1,0 +1,44 @@
+// dataset.h - minimal .psam/.fam + .pvar/.bim loaders and the genotype-block streamer used by the
+// command drivers.  Only what the pairwise-genotype commands read is kept: sample IDs (FID/IID/SID),
+// founder status, variant chromosome / bp / ID (2.0/plink2_psam.cc LoadPsam, 2.0/plink2_pvar.cc
+// LoadPvar; file rules pgen_spec/pgen_spec.tex:695-833).
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "pgen_reader.h"
+
+namespace pl2host {
+
+struct SampleInfo {
+  std::vector<std::string> fid, iid, sid;
+  std::vector<uint8_t> is_founder;
+  bool fid_present = false;  // kfSampleIdFidPresent (plink2_psam.cc:104-130, :279, :823)
+  bool sid_present = false;
+  uint32_t size() const { return static_cast<uint32_t>(iid.size()); }
+};
+
+struct VariantInfo {
+  std::vector<uint32_t> chr_code;  // 0 = unplaced, 1..22 autosomes, 23 X, 24 Y, 25 XY, 26 MT
+  std::vector<uint32_t> bp;
+  std::vector<std::string> id;
+  uint32_t size() const { return static_cast<uint32_t>(id.size()); }
+};
+
+bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err);
+bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err);
+
+inline bool IsAutosome(uint32_t chr_code) { return chr_code >= 1 && chr_code <= 22; }
+// CountNonAutosomalVariants(..., count_x=1, count_mt=1) semantics used by CalcKing/CalcGrm
+// (plink2_matrix_calc.cc:1704, :4654): X, Y, XY(PAR is kept by the reference; treated as
+// autosomal-like), MT excluded; unplaced (0) kept.
+inline bool KeptForRelationship(uint32_t chr_code) { return chr_code != 23 && chr_code != 24 && chr_code != 26; }
+
+struct Dataset {
+  SampleInfo samples;
+  VariantInfo variants;
+  PgenReader reader;
+};
+
+}  // namespace pl2host

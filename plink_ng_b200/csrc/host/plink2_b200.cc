@@ -1,0 +1,1236 @@
+// plink2_b200 - host program: the plink2 command-line face of the pairwise-genotype commands
+// (--make-king, --make-king-table, --king-cutoff, --make-grm-bin, --make-rel, --pca,
+// --indep-pairwise) on top of the C-ABI GPU library (include/plink2_b200.h).
+//
+// Mirrors, per command, the reference's driver functions: flag semantics from 2.0/plink2.cc
+// (:8462-8598 KING, :9099-9300 GRM, :7238-7312 --indep-pairwise, :10093 --parallel), execution
+// order of Plink2Core (:2523-2670, :2925-2930: KING -> GRM -> PCA -> LD prune), output files of
+// CalcKing / CalcGrm / LdPruneWrite.  File decoding, text formatting and the sequential graph /
+// window logic run here on the host; every pairwise accumulation runs on the GPU - there is no
+// CPU fallback and the program exits with kPglRetGpuFail-style status when the device is missing.
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "../../../include/plink2_b200.h"
+#include "dataset.h"
+#include "pca.h"
+#include "text_util.h"
+
+using namespace pl2host;
+
+namespace {
+
+// PglErr values used as process exit codes (2.0/include/plink2_base.h:358-387)
+enum { kRetSuccess = 0, kRetNomem = 2, kRetOpenFail = 3, kRetReadFail = 4, kRetWriteFail = 5, kRetMalformedInput = 6, kRetInconsistentInput = 7, kRetInvalidCmdline = 8, kRetDegenerateData = 13, kRetGpuFail = 16, kRetNotYetSupported = 63 };
+
+FILE* g_log = nullptr;
+void logprintf(const char* fmt, ...) {
+  char buf[4096];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  fputs(buf, stdout);
+  fflush(stdout);
+  if (g_log) fputs(buf, g_log);
+}
+
+struct Cmd {
+  std::string pgen, pvar, psam, out = "plink2";
+  uint32_t parallel_idx = 0, parallel_tot = 1;
+  uint32_t threads = 0;
+  uint64_t seed = 0;
+  bool seed_given = false;
+  int device = 0;
+  // KING
+  bool make_king = false, make_king_table = false;
+  enum Shape { kTri, kSq, kSq0 } king_shape = kTri, rel_shape = kTri;
+  enum Enc { kText, kBin, kBin4 } king_enc = kText, rel_enc = kText;
+  bool king_counts = false;
+  bool col_fid_maybe = true, col_fid = false, col_id = true, col_sid_maybe = true, col_sid = false, col_nsnp = true, col_hethet = true, col_ibs0 = true, col_ibs1 = false, col_hamming = false, col_kinship = true;
+  double king_table_filter = -DBL_MAX;
+  double king_cutoff = -1;
+  // GRM
+  bool make_grm_bin = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
+  // PCA
+  bool pca = false, pca_approx = false, pca_meanimpute = false;
+  uint32_t pc_ct = 10;
+  // LD
+  bool indep_pairwise = false, indep_kb = false, bad_ld = false;
+  uint32_t indep_window = 0, indep_step = 1;
+  double indep_r2 = 0;
+};
+
+bool ParseU32(const char* s, uint32_t* out) {
+  char* e;
+  const unsigned long v = strtoul(s, &e, 10);
+  if (e == s || *e || v > 0xFFFFFFFFul) return false;
+  *out = static_cast<uint32_t>(v);
+  return true;
+}
+bool ParseDouble(const char* s, double* out) {
+  char* e;
+  *out = strtod(s, &e);
+  return e != s && !*e;
+}
+
+int Usage(const char* msg) {
+  logprintf("Error: %s\n", msg);
+  return kRetInvalidCmdline;
+}
+
+// --make-king-table cols= (default maybefid,id,maybesid,nsnp,hethet,ibs0,kinship; plink2_matrix_calc.h:60)
+bool ParseKingCols(const std::string& spec, Cmd* c) {
+  std::vector<std::string> toks;
+  size_t i = 0;
+  while (i <= spec.size()) {
+    size_t j = spec.find(',', i);
+    if (j == std::string::npos) j = spec.size();
+    if (j > i) toks.push_back(spec.substr(i, j - i));
+    i = j + 1;
+  }
+  if (toks.empty()) return false;
+  const bool incremental = toks[0][0] == '+' || toks[0][0] == '-';
+  if (!incremental) c->col_fid_maybe = c->col_fid = c->col_id = c->col_sid_maybe = c->col_sid = c->col_nsnp = c->col_hethet = c->col_ibs0 = c->col_ibs1 = c->col_hamming = c->col_kinship = false;
+  for (std::string t : toks) {
+    bool val = true;
+    if (t[0] == '+' || t[0] == '-') {
+      if (!incremental) return false;
+      val = t[0] == '+';
+      t = t.substr(1);
+    } else if (incremental) {
+      return false;
+    }
+    if (t == "maybefid") c->col_fid_maybe = val;
+    else if (t == "fid") c->col_fid = val;
+    else if (t == "id") c->col_id = val;
+    else if (t == "maybesid") c->col_sid_maybe = val;
+    else if (t == "sid") c->col_sid = val;
+    else if (t == "nsnp") c->col_nsnp = val;
+    else if (t == "hethet") c->col_hethet = val;
+    else if (t == "ibs0") c->col_ibs0 = val;
+    else if (t == "ibs1") c->col_ibs1 = val;
+    else if (t == "ibs") c->col_hamming = val;
+    else if (t == "kinship") c->col_kinship = val;
+    else return false;
+  }
+  return true;
+}
+
+int ParseArgs(int argc, char** argv, Cmd* c) {
+  std::string bfile, pfile, bed, bim, fam;
+  for (int i = 1; i < argc;) {
+    const std::string flag = argv[i];
+    int j = i + 1;
+    while (j < argc && !(argv[j][0] == '-' && argv[j][1] == '-')) ++j;
+    const int nparam = j - i - 1;
+    char** prm = argv + i + 1;
+    auto need = [&](int lo, int hi) { return nparam >= lo && nparam <= hi; };
+    if (flag == "--bfile") {
+      if (!need(1, 1)) return Usage("--bfile requires a prefix.");
+      bfile = prm[0];
+    } else if (flag == "--pfile") {
+      if (!need(1, 1)) return Usage("--pfile requires a prefix.");
+      pfile = prm[0];
+    } else if (flag == "--bed" || flag == "--pgen") {
+      if (!need(1, 1)) return Usage("--bed/--pgen requires a filename.");
+      c->pgen = prm[0];
+    } else if (flag == "--bim" || flag == "--pvar") {
+      if (!need(1, 1)) return Usage("--bim/--pvar requires a filename.");
+      c->pvar = prm[0];
+    } else if (flag == "--fam" || flag == "--psam") {
+      if (!need(1, 1)) return Usage("--fam/--psam requires a filename.");
+      c->psam = prm[0];
+    } else if (flag == "--out") {
+      if (!need(1, 1)) return Usage("--out requires a prefix.");
+      c->out = prm[0];
+    } else if (flag == "--threads") {
+      if (!need(1, 1) || !ParseU32(prm[0], &c->threads)) return Usage("Invalid --threads argument.");
+    } else if (flag == "--memory") {
+      if (!need(1, 2)) return Usage("Invalid --memory argument.");  // host arena size: not used here
+    } else if (flag == "--seed") {
+      uint32_t s;
+      if (!need(1, 1) || !ParseU32(prm[0], &s)) return Usage("Invalid --seed argument.");
+      c->seed = s;
+      c->seed_given = true;
+    } else if (flag == "--gpu-device") {
+      uint32_t d;
+      if (!need(1, 1) || !ParseU32(prm[0], &d)) return Usage("Invalid --gpu-device argument.");
+      c->device = static_cast<int>(d);
+    } else if (flag == "--parallel") {
+      if (!need(2, 2) || !ParseU32(prm[0], &c->parallel_idx) || !ParseU32(prm[1], &c->parallel_tot) || !c->parallel_idx || c->parallel_idx > c->parallel_tot) return Usage("Invalid --parallel arguments.");
+      --c->parallel_idx;
+    } else if (flag == "--make-king") {
+      if (!need(0, 2)) return Usage("--make-king takes at most 2 arguments.");
+      c->make_king = true;
+      bool shape_set = false;
+      for (int k = 0; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "bin") c->king_enc = Cmd::kBin;
+        else if (m == "bin4") c->king_enc = Cmd::kBin4;
+        else if (m == "square") c->king_shape = Cmd::kSq, shape_set = true;
+        else if (m == "square0") c->king_shape = Cmd::kSq0, shape_set = true;
+        else if (m == "triangle") c->king_shape = Cmd::kTri, shape_set = true;
+        else if (m == "zs") return Usage("--make-king 'zs' output is not supported by plink2_b200.");
+        else return Usage(("Invalid --make-king argument '" + m + "'.").c_str());
+      }
+      if (!shape_set) c->king_shape = (c->king_enc == Cmd::kText) ? Cmd::kTri : Cmd::kSq;  // plink2.cc:8521-8526
+    } else if (flag == "--make-king-table") {
+      c->make_king_table = true;
+      for (int k = 0; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "counts") c->king_counts = true;
+        else if (m.compare(0, 5, "cols=") == 0) {
+          if (!ParseKingCols(m.substr(5), c)) return Usage(("Invalid --make-king-table cols= argument '" + m + "'.").c_str());
+        } else if (m == "zs" || m == "rel-check") return Usage("--make-king-table zs / rel-check are not supported by plink2_b200.");
+        else return Usage(("Invalid --make-king-table argument '" + m + "'.").c_str());
+      }
+    } else if (flag == "--king-table-filter") {
+      if (!need(1, 1) || !ParseDouble(prm[0], &c->king_table_filter)) return Usage("Invalid --king-table-filter argument.");
+    } else if (flag == "--king-cutoff") {
+      if (nparam == 2) return Usage("--king-cutoff with a precomputed matrix prefix is not supported by plink2_b200.");
+      if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
+    } else if (flag == "--make-grm-bin" || flag == "--make-rel") {
+      const bool is_rel = flag == "--make-rel";
+      (is_rel ? c->make_rel : c->make_grm_bin) = true;
+      bool shape_set = false;
+      for (int k = 0; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "cov") c->grm_cov = true;
+        else if (m == "meanimpute") c->grm_meanimpute = true;
+        else if (m == "id-header" && !is_rel) c->grm_id_header = true;
+        else if (is_rel && m == "bin") c->rel_enc = Cmd::kBin;
+        else if (is_rel && m == "bin4") c->rel_enc = Cmd::kBin4;
+        else if (is_rel && m == "square") c->rel_shape = Cmd::kSq, shape_set = true;
+        else if (is_rel && m == "square0") c->rel_shape = Cmd::kSq0, shape_set = true;
+        else if (is_rel && m == "triangle") c->rel_shape = Cmd::kTri, shape_set = true;
+        else return Usage(("Invalid " + flag + " argument '" + m + "'.").c_str());
+      }
+      if (is_rel && !shape_set) c->rel_shape = (c->rel_enc == Cmd::kText) ? Cmd::kTri : Cmd::kSq;
+    } else if (flag == "--pca") {
+      c->pca = true;
+      for (int k = 0; k < nparam; ++k) {
+        const std::string m = prm[k];
+        uint32_t v;
+        if (m == "approx") c->pca_approx = true;
+        else if (m == "meanimpute") c->pca_meanimpute = true;
+        else if (ParseU32(m.c_str(), &v)) c->pc_ct = v;
+        else return Usage(("Invalid or unsupported --pca argument '" + m + "'.").c_str());
+      }
+      if (c->pc_ct < 1 || c->pc_ct > 8000) return Usage("Invalid --pca PC count.");
+    } else if (flag == "--indep-pairwise") {
+      // <window size>['kb'] [step size (variant ct)] <r^2 threshold>   (plink2.cc:7238-7312)
+      if (!need(2, 4)) return Usage("--indep-pairwise requires 2-4 arguments.");
+      c->indep_pairwise = true;
+      std::vector<std::string> p(prm, prm + nparam);
+      std::string w = p[0];
+      size_t next = 1;
+      auto strip_kb = [&](std::string* s) {
+        if (s->size() > 2 && (s->substr(s->size() - 2) == "kb" || s->substr(s->size() - 2) == "KB" || s->substr(s->size() - 2) == "Kb")) {
+          s->resize(s->size() - 2);
+          return true;
+        }
+        return false;
+      };
+      if (strip_kb(&w)) {
+        c->indep_kb = true;
+      } else if (next < p.size() && (p[next] == "kb" || p[next] == "KB")) {
+        c->indep_kb = true;
+        ++next;
+      }
+      double wd;
+      if (!ParseDouble(w.c_str(), &wd) || wd < 0) return Usage("Invalid --indep-pairwise window size.");
+      if (c->indep_kb) {
+        wd *= 1000;
+        if (wd > 2147483646) wd = 2147483646;
+        c->indep_window = static_cast<uint32_t>(wd);
+      } else {
+        if (wd < 2 || wd != floor(wd)) return Usage("Invalid --indep-pairwise window size.");
+        c->indep_window = static_cast<uint32_t>(wd);
+      }
+      const size_t remaining = p.size() - next;
+      if (remaining == 2) {
+        if (!ParseU32(p[next].c_str(), &c->indep_step) || !c->indep_step) return Usage("Invalid --indep-pairwise step size.");
+        ++next;
+      } else if (remaining != 1) {
+        return Usage("Invalid --indep-pairwise argument sequence.");
+      }
+      if (c->indep_kb && c->indep_step != 1) return Usage("--indep-pairwise step size must be 1 when the window is in kilobase units.");
+      if (!c->indep_kb && c->indep_step > c->indep_window) return Usage("--indep-pairwise step size cannot exceed the window size.");
+      if (!ParseDouble(p[next].c_str(), &c->indep_r2) || c->indep_r2 < 0 || c->indep_r2 >= 1) return Usage("Invalid --indep-pairwise r^2 threshold.");
+    } else if (flag == "--bad-ld") {
+      c->bad_ld = true;
+    } else {
+      return Usage(("Unrecognized or unsupported flag '" + flag + "' (plink2_b200 implements the KING / GRM / PCA / --indep-pairwise path only).").c_str());
+    }
+    i = j;
+  }
+  if (!bfile.empty()) {
+    c->pgen = bfile + ".bed";
+    c->pvar = bfile + ".bim";
+    c->psam = bfile + ".fam";
+  } else if (!pfile.empty()) {
+    c->pgen = pfile + ".pgen";
+    c->pvar = pfile + ".pvar";
+    c->psam = pfile + ".psam";
+  }
+  if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_rel || c->pca || c->indep_pairwise)) return Usage("No command given.");
+  return 0;
+}
+
+// ParallelBounds / TriangleDivide (2.0/plink2_common.cc:4936-4961)
+uint32_t TriangleDivide(int64_t cur_prod_x2, int32_t modif) {
+  if (cur_prod_x2 == 0) return modif < 0 ? static_cast<uint32_t>(-modif) : 0;
+  int64_t vv = static_cast<int64_t>(sqrt(static_cast<double>(cur_prod_x2)));
+  while ((vv - 1) * (vv + modif - 1) >= cur_prod_x2) --vv;
+  while (vv * (vv + modif) < cur_prod_x2) ++vv;
+  return static_cast<uint32_t>(vv);
+}
+void ParallelBounds(uint32_t ct, int32_t start, uint32_t idx, uint32_t tot, uint32_t* b0, uint32_t* b1) {
+  const int32_t modif = 1 - start * 2;
+  const int64_t ct_tot = static_cast<int64_t>(ct) * (ct + modif);
+  *b0 = TriangleDivide((ct_tot * idx) / tot, modif);
+  *b1 = TriangleDivide((ct_tot * (idx + 1)) / tot, modif);
+}
+
+std::string PieceName(const std::string& base, const Cmd& c) { return c.parallel_tot == 1 ? base : base + "." + std::to_string(c.parallel_idx + 1); }
+
+// sample ID text "[FID\t]IID[\tSID]" (CollapsedSampleFmtidInit, plink2_common.cc)
+struct IdFmt {
+  bool fid, sid;
+};
+IdFmt KingIdFmt(const Cmd& c, const SampleInfo& s) { return {c.col_fid || (c.col_fid_maybe && s.fid_present), c.col_sid || (c.col_sid_maybe && s.sid_present)}; }
+std::string FmtId(const SampleInfo& s, uint32_t k, IdFmt f) {
+  std::string r;
+  if (f.fid) r += s.fid[k] + "\t";
+  r += s.iid[k];
+  if (f.sid) r += "\t" + s.sid[k];
+  return r;
+}
+
+// WriteSampleIds: "#FID\tIID[\tSID]" header unless no_header
+bool WriteIdFile(const std::string& path, const SampleInfo& s, const std::vector<uint32_t>& which, bool header) {
+  OutFile f;
+  if (!f.Open(path)) return false;
+  if (header) {
+    std::string h = "#";
+    if (s.fid_present) h += "FID\t";
+    h += "IID";
+    if (s.sid_present) h += "\tSID";
+    h += "\n";
+    f.Puts(h.c_str());
+  }
+  for (uint32_t k : which) {
+    std::string ln;
+    if (s.fid_present) ln += s.fid[k] + "\t";
+    ln += s.iid[k];
+    if (s.sid_present) ln += "\t" + s.sid[k];
+    ln += "\n";
+    f.Puts(ln.c_str());
+  }
+  return f.Close();
+}
+
+// ---- genotype block streaming: decode `idx` variants into a pinned host buffer ----
+struct BlockStreamer {
+  Dataset* ds;
+  const std::vector<uint32_t>* vidx;
+  const uint64_t* sample_include = nullptr;  // null = all samples
+  uint32_t sample_ct;
+  uint32_t words;
+  uint64_t* buf = nullptr;
+  uint32_t cap;
+  size_t pos = 0;
+  BlockStreamer(Dataset* d, const std::vector<uint32_t>* v, uint32_t n_samples, uint32_t batch) : ds(d), vidx(v), sample_ct(n_samples), words(PgenReader::WordsFor(n_samples)), cap(batch) {}
+  ~BlockStreamer() { pl2gpu_host_free(buf); }
+  bool Init() {
+    void* p = nullptr;
+    if (pl2gpu_host_alloc(static_cast<uint64_t>(cap) * words * 8, &p)) return false;
+    buf = static_cast<uint64_t*>(p);
+    return true;
+  }
+  // returns number of variants decoded (0 at end), -1 on error
+  int Next(std::string* err) {
+    uint32_t n = 0;
+    while (n < cap && pos < vidx->size()) {
+      uint64_t* dst = buf + static_cast<uint64_t>(n) * words;
+      const bool ok = sample_include ? ds->reader.GetSubset((*vidx)[pos], sample_include, sample_ct, dst, err) : ds->reader.Get((*vidx)[pos], dst, err);
+      if (!ok) return -1;
+      ++n;
+      ++pos;
+    }
+    return static_cast<int>(n);
+  }
+  void Rewind() { pos = 0; }
+};
+
+int GpuFail(const char* what) {
+  logprintf("Error: %s: %s\n", what, pl2gpu_last_error());
+  return kRetGpuFail;
+}
+
+// ------------------------------------------------------------------------------------------ KING
+// KinshipPruneDestructive (2.0/plink2_matrix_calc.cc:278-391): while edges remain, remove the
+// partner of the first degree-1 vertex if any, else the first maximum-degree vertex.
+void KinshipPrune(std::vector<uint64_t>* table_ptr, uint32_t n, std::vector<uint8_t>* removed) {
+  std::vector<uint64_t>& tab = *table_ptr;
+  const uint32_t wl = (n + 63) / 64;
+  std::vector<uint32_t> degree(n, 0);
+  std::vector<uint8_t> nz(n, 0);
+  removed->assign(n, 0);
+  uint32_t deg1 = 0, nz_ct = 0;
+  for (uint32_t i = 0; i < n; ++i) {
+    uint32_t d = 0;
+    for (uint32_t w = 0; w < wl; ++w) d += static_cast<uint32_t>(__builtin_popcountll(tab[static_cast<uint64_t>(i) * wl + w]));
+    if (d) {
+      degree[i] = d;
+      deg1 += d == 1;
+      nz[i] = 1;
+      ++nz_ct;
+    }
+  }
+  auto first_set = [&](const uint64_t* row, uint32_t from) {
+    for (uint32_t w = from / 64; w < wl; ++w) {
+      uint64_t x = row[w];
+      if (w == from / 64) x &= ~0ull << (from % 64);
+      if (x) return w * 64 + static_cast<uint32_t>(__builtin_ctzll(x));
+    }
+    return n;
+  };
+  while (nz_ct) {
+    uint32_t prune, cur_degree;
+    if (deg1) {
+      uint32_t u = 0;
+      while (!(nz[u] && degree[u] == 1)) ++u;
+      prune = first_set(&tab[static_cast<uint64_t>(u) * wl], 0);
+      cur_degree = degree[prune];
+    } else {
+      prune = 0;
+      cur_degree = 0;
+      bool first = true;
+      for (uint32_t u = 0; u < n; ++u) {
+        if (!nz[u]) continue;
+        if (first || degree[u] > cur_degree) {
+          cur_degree = degree[u];
+          prune = u;
+          first = false;
+        }
+      }
+    }
+    const uint64_t col_mask = ~(1ull << (prune % 64));
+    const uint64_t* row = &tab[static_cast<uint64_t>(prune) * wl];
+    uint32_t u = 0;
+    for (uint32_t p = 0; p < cur_degree; ++p, ++u) {
+      u = first_set(row, u);
+      const uint32_t nd = degree[u] - 1;
+      if (!nd) {
+        nz[u] = 0;
+        --deg1;
+        --nz_ct;
+      } else {
+        tab[static_cast<uint64_t>(u) * wl + prune / 64] &= col_mask;
+        deg1 += nd == 1;
+        degree[u] = nd;
+      }
+    }
+    if (degree[prune] == 1) --deg1;
+    (*removed)[prune] = 1;
+    nz[prune] = 0;
+    --nz_ct;
+  }
+}
+
+inline double KinshipFromCounts(const uint32_t* c) {  // ComputeKinship, :1566-1573
+  const int64_t ibs0 = c[0], hethet = c[1], het2hom1 = c[2], het1hom2 = c[3];
+  const int64_t smaller = hethet + std::min(het1hom2, het2hom1);
+  return 0.5 - static_cast<double>(4 * ibs0 + het1hom2 + het2hom1) / static_cast<double>(4 * smaller);
+}
+
+int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cutoff_removed) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  const char* flagname = c.make_king ? "--make-king" : (c.make_king_table ? "--make-king-table" : "--king-cutoff");
+  if (n < 2) {
+    logprintf("Error: %s requires at least 2 samples.\n", flagname);
+    return kRetDegenerateData;
+  }
+  std::vector<uint32_t> vidx;
+  uint32_t non_auto = 0;
+  for (uint32_t v = 0; v < ds->variants.size(); ++v) {
+    if (KeptForRelationship(ds->variants.chr_code[v])) vidx.push_back(v);
+    else ++non_auto;
+  }
+  if (non_auto) logprintf("Excluding %u variant%s on non-autosomes from KING-robust calculation.\n", non_auto, non_auto == 1 ? "" : "s");
+  if (vidx.empty()) {
+    logprintf("Error: No variants remaining for KING-robust calculation.\n");
+    return kRetDegenerateData;
+  }
+  uint32_t grand_r0, grand_r1;
+  ParallelBounds(n, 1, c.parallel_idx, c.parallel_tot, &grand_r0, &grand_r1);
+  const bool want_table = c.make_king_table;
+  const bool want_matrix = c.make_king;
+  const bool square_text_full = want_matrix && c.king_shape == Cmd::kSq;  // needs the mirrored upper triangle
+  if (square_text_full && c.parallel_tot != 1) {
+    logprintf("Error: --make-king square output cannot be combined with --parallel; use square0 or triangle.\n");
+    return kRetInvalidCmdline;
+  }
+  const uint32_t wl = (n + 63) / 64;
+  std::vector<uint64_t> kin_table;
+  if (c.king_cutoff >= 0) kin_table.assign(static_cast<uint64_t>(n) * wl, 0);
+
+  OutFile fmat, ftab;
+  std::string mat_name, tab_name;
+  if (want_matrix) {
+    mat_name = PieceName(c.out + (c.king_enc == Cmd::kText ? ".king" : ".king.bin"), c);
+    if (!fmat.Open(mat_name)) {
+      logprintf("Error: Failed to open %s for writing.\n", mat_name.c_str());
+      return kRetOpenFail;
+    }
+  }
+  const IdFmt idf = KingIdFmt(c, S);
+  std::vector<std::string> fmtids;
+  if (want_table) {
+    tab_name = PieceName(c.out + ".kin0", c);
+    if (!ftab.Open(tab_name)) {
+      logprintf("Error: Failed to open %s for writing.\n", tab_name.c_str());
+      return kRetOpenFail;
+    }
+    if (!c.parallel_idx) {  // AppendKingTableHeader, :1611-1652
+      std::string h = "#";
+      if (c.col_id) {
+        if (idf.fid) h += "FID1\t";
+        h += "IID1\t";
+        if (idf.sid) h += "SID1\t";
+        if (idf.fid) h += "FID2\t";
+        h += "IID2\t";
+        if (idf.sid) h += "SID2\t";
+      }
+      if (c.col_nsnp) h += "NSNP\t";
+      if (c.col_hethet) h += "HETHET\t";
+      if (c.col_ibs0) h += "IBS0\t";
+      if (c.col_ibs1) h += "HET1_HOM2\tHET2_HOM1\t";
+      if (c.col_hamming) h += "IBS\t";
+      if (c.col_kinship) h += "KINSHIP\t";
+      h.back() = '\n';
+      ftab.Puts(h.c_str());
+    }
+    fmtids.resize(n);
+    for (uint32_t k = 0; k < n; ++k) fmtids[k] = FmtId(S, k, idf);
+  }
+  std::vector<double> full_kin;  // lower triangle, only for `square` output
+  if (square_text_full) full_kin.resize(static_cast<uint64_t>(n) * (n - 1) / 2);
+
+  // pass planning (CountTrianglePasses / NextTrianglePass, :216-255): largest row block whose
+  // device accumulators fit
+  uint64_t free_b = 0, total_b = 0;
+  if (pl2gpu_ctx_mem_info(ctx, &free_b, &total_b)) return GpuFail("pl2gpu_ctx_mem_info");
+  const uint64_t budget = free_b - free_b / 10;
+  const uint32_t batch = 32768;
+  uint32_t pass_ct = 0;
+  for (uint32_t r = grand_r0; r < grand_r1; ++pass_ct) {
+    uint32_t lo = r + 1, hi = grand_r1;  // largest e in (r, grand_r1] that fits
+    if (pl2gpu_king_mem_required(n, r, r + 1, batch) > budget) {
+      logprintf("Error: Insufficient GPU memory for %s on %u samples.\n", flagname, n);
+      return kRetNomem;
+    }
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      if (pl2gpu_king_mem_required(n, r, mid, batch) <= budget) lo = mid;
+      else hi = mid - 1;
+    }
+    r = lo;
+  }
+  BlockStreamer bs(ds, &vidx, n, batch);
+  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  if (want_matrix && c.king_shape == Cmd::kSq0 && !c.parallel_idx) {
+    // square0 output starts with sample 0's row: the diagonal 0.5 followed by zeros (:2129-2132)
+    if (c.king_enc == Cmd::kText) {
+      std::string row0 = "0.5";
+      for (uint32_t i = 1; i < n; ++i) row0 += "\t0";
+      row0 += "\n";
+      fmat.Puts(row0.c_str());
+    } else if (c.king_enc == Cmd::kBin4) {
+      std::vector<float> row(n, 0.0f);
+      row[0] = 0.5f;
+      fmat.Write(row.data(), sizeof(float) * n);
+    } else {
+      std::vector<double> row(n, 0.0);
+      row[0] = 0.5;
+      fmat.Write(row.data(), sizeof(double) * n);
+    }
+  }
+  uint64_t filter_ct = 0;
+  uint32_t row_end = grand_r0;
+  for (uint32_t pass = 1; pass <= pass_ct; ++pass) {
+    const uint32_t row_start = row_end;
+    {
+      uint32_t lo = row_start + 1, hi = grand_r1;
+      while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo + 1) / 2;
+        if (pl2gpu_king_mem_required(n, row_start, mid, batch) <= budget) lo = mid;
+        else hi = mid - 1;
+      }
+      row_end = lo;
+    }
+    Pl2KingJob* job = nullptr;
+    if (pl2gpu_king_begin(ctx, n, row_start, row_end, kPl2KingAlgoAuto, &job)) return GpuFail("pl2gpu_king_begin");
+    bs.Rewind();
+    std::string err;
+    uint32_t done = 0;
+    for (;;) {
+      const int got = bs.Next(&err);
+      if (got < 0) {
+        logprintf("\nError: %s\n", err.c_str());
+        pl2gpu_king_end(job);
+        return kRetMalformedInput;
+      }
+      if (!got) break;
+      if (pl2gpu_king_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
+        pl2gpu_king_end(job);
+        return GpuFail("pl2gpu_king_add_variants");
+      }
+      done += static_cast<uint32_t>(got);
+      printf("\r%s pass %u/%u: %u variants complete.", flagname, pass, pass_ct, done);
+      fflush(stdout);
+    }
+    printf("\r%s pass %u/%u: Writing...                   ", flagname, pass, pass_ct);
+    fflush(stdout);
+    // results in row chunks of <= ~512 MB
+    const uint64_t max_pairs = (512ull << 20) / 20;
+    std::vector<uint32_t> counts;
+    std::vector<double> kin;
+    for (uint32_t c0 = row_start; c0 < row_end;) {
+      uint32_t c1 = c0 + 1;
+      auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
+      while (c1 < row_end && tri(c1 + 1) - tri(c0) <= max_pairs) ++c1;
+      const uint64_t pairs = tri(c1) - tri(c0);
+      if (want_table) {
+        counts.resize(pairs * 5);
+        if (pairs && pl2gpu_king_get_counts(job, c0, c1, counts.data(), 0)) {
+          pl2gpu_king_end(job);
+          return GpuFail("pl2gpu_king_get_counts");
+        }
+      }
+      if (want_matrix || c.king_cutoff >= 0 || !want_table) {
+        kin.resize(pairs);
+        if (pairs && pl2gpu_king_get_kinship(job, c0, c1, kin.data(), 0)) {
+          pl2gpu_king_end(job);
+          return GpuFail("pl2gpu_king_get_kinship");
+        }
+      }
+      uint64_t p = 0;
+      for (uint32_t j = c0; j < c1; ++j) {
+        const uint64_t row_p = p;
+        // --king-cutoff bit matrix (:2148-2151)
+        if (c.king_cutoff >= 0) {
+          for (uint32_t i = 0; i < j; ++i) {
+            if (kin[row_p + i] > c.king_cutoff) {
+              kin_table[static_cast<uint64_t>(j) * wl + i / 64] |= 1ull << (i % 64);
+              kin_table[static_cast<uint64_t>(i) * wl + j / 64] |= 1ull << (j % 64);
+            }
+          }
+        }
+        if (want_matrix) {
+          if (square_text_full) {
+            memcpy(&full_kin[tri(j)], &kin[row_p], sizeof(double) * j);
+          } else if (c.king_enc == Cmd::kText) {
+            // triangle: row j = kin(j,0..j-1); square0: + "0.5" + zeros (:2133-2184)
+            char* w = fmat.Reserve(static_cast<size_t>(n) * 16 + 64);
+            for (uint32_t i = 0; i < j; ++i) {
+              w = dtoa_g(kin[row_p + i], w);
+              *w++ = '\t';
+            }
+            if (c.king_shape == Cmd::kSq0) {
+              memcpy(w, "0.5", 3);
+              w += 3;
+              for (uint32_t i = j + 1; i < n; ++i) {
+                *w++ = '\t';
+                *w++ = '0';
+              }
+              *w++ = '\n';
+            } else {
+              if (j) w[-1] = '\n';
+              else *w++ = '\n';
+            }
+            fmat.Advance(w);
+          } else {
+            const bool f4 = c.king_enc == Cmd::kBin4;
+            const uint32_t row_len = (c.king_shape == Cmd::kTri) ? j : n;
+            if (f4) {
+              std::vector<float> rowf(row_len, 0.0f);
+              for (uint32_t i = 0; i < j; ++i) rowf[i] = static_cast<float>(kin[row_p + i]);
+              if (c.king_shape != Cmd::kTri) rowf[j] = 0.5f;
+              fmat.Write(rowf.data(), sizeof(float) * row_len);
+            } else {
+              std::vector<double> rowd(row_len, 0.0);
+              for (uint32_t i = 0; i < j; ++i) rowd[i] = kin[row_p + i];
+              if (c.king_shape != Cmd::kTri) rowd[j] = 0.5;
+              fmat.Write(rowd.data(), sizeof(double) * row_len);
+            }
+          }
+        }
+        if (want_table) {
+          for (uint32_t i = 0; i < j; ++i) {
+            const uint32_t* cc = &counts[(row_p + i) * 5];
+            const uint32_t ibs0 = cc[0], hethet = cc[1], het2hom1 = cc[2], het1hom2 = cc[3], homhom = cc[4];
+            const double kinship = KinshipFromCounts(cc);
+            if (c.king_table_filter != -DBL_MAX && kinship < c.king_table_filter) {
+              ++filter_ct;
+              continue;
+            }
+            char* w = ftab.Reserve(fmtids[j].size() + fmtids[i].size() + 160);
+            if (c.col_id) {
+              memcpy(w, fmtids[j].data(), fmtids[j].size());
+              w += fmtids[j].size();
+              *w++ = '\t';
+              memcpy(w, fmtids[i].data(), fmtids[i].size());
+              w += fmtids[i].size();
+              *w++ = '\t';
+            }
+            const uint32_t nonmiss = het1hom2 + het2hom1 + homhom + hethet;
+            double recip = 0.0;
+            if (c.col_nsnp) {
+              w = u32toa(nonmiss, w);
+              *w++ = '\t';
+            }
+            if (!c.king_counts) recip = 1.0 / static_cast<double>(nonmiss);
+            auto put = [&](uint32_t v) {
+              if (c.king_counts) w = u32toa(v, w);
+              else w = dtoa_g(recip * static_cast<double>(v), w);
+              *w++ = '\t';
+            };
+            if (c.col_hethet) put(hethet);
+            if (c.col_ibs0) put(ibs0);
+            if (c.col_ibs1) {
+              put(het1hom2);
+              put(het2hom1);
+            }
+            if (c.col_hamming) {
+              const uint32_t hamming = 2 * ibs0 + het1hom2 + het2hom1;
+              if (c.king_counts) w = u32toa(hamming, w);
+              else w = dtoa_g(recip * 0.5 * static_cast<double>(hamming), w);
+              *w++ = '\t';
+            }
+            if (c.col_kinship) {
+              w = dtoa_g(kinship, w);
+              *w++ = '\t';
+            }
+            w[-1] = '\n';
+            ftab.Advance(w);
+          }
+        }
+        p += j;
+      }
+      c0 = c1;
+    }
+    pl2gpu_king_end(job);
+  }
+  if (square_text_full) {
+    auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
+    auto at = [&](uint32_t a, uint32_t b) { return a > b ? full_kin[tri(a) + b] : full_kin[tri(b) + a]; };
+    for (uint32_t j = 0; j < n; ++j) {
+      if (c.king_enc == Cmd::kText) {
+        char* w = fmat.Reserve(static_cast<size_t>(n) * 16 + 64);
+        for (uint32_t i = 0; i < n; ++i) {
+          if (i == j) {
+            memcpy(w, "0.5", 3);
+            w += 3;
+          } else {
+            w = dtoa_g(at(j, i), w);
+          }
+          *w++ = '\t';
+        }
+        w[-1] = '\n';
+        fmat.Advance(w);
+      } else if (c.king_enc == Cmd::kBin4) {
+        std::vector<float> row(n);
+        for (uint32_t i = 0; i < n; ++i) row[i] = (i == j) ? 0.5f : static_cast<float>(at(j, i));
+        fmat.Write(row.data(), sizeof(float) * n);
+      } else {
+        std::vector<double> row(n);
+        for (uint32_t i = 0; i < n; ++i) row[i] = (i == j) ? 0.5 : at(j, i);
+        fmat.Write(row.data(), sizeof(double) * n);
+      }
+    }
+  }
+  printf("\r                                              \r");
+  logprintf("%s: %u variants processed.\n", flagname, static_cast<uint32_t>(vidx.size()));
+  if (want_matrix) {
+    if (!fmat.Close()) {
+      logprintf("Error: File write failure.\n");
+      return kRetWriteFail;
+    }
+    std::string idname = c.out + ".king.id";
+    if (!c.parallel_idx) {
+      std::vector<uint32_t> all(n);
+      for (uint32_t k = 0; k < n; ++k) all[k] = k;
+      if (!WriteIdFile(idname, S, all, true)) return kRetWriteFail;
+      logprintf("Results written to %s and %s .\n", mat_name.c_str(), idname.c_str());
+    } else {
+      logprintf("Results written to %s .\n", mat_name.c_str());
+    }
+  }
+  if (want_table) {
+    if (!ftab.Close()) {
+      logprintf("Error: File write failure.\n");
+      return kRetWriteFail;
+    }
+    logprintf("Results written to %s .\n", tab_name.c_str());
+    if (c.king_table_filter != -DBL_MAX) {
+      const uint64_t tot = (static_cast<uint64_t>(grand_r1) * (grand_r1 - 1) - static_cast<uint64_t>(grand_r0) * (grand_r0 - 1)) / 2;
+      logprintf("--king-table-filter: %llu relationship%s reported (%llu filtered out).\n", static_cast<unsigned long long>(tot - filter_ct), (tot - filter_ct == 1) ? "" : "s", static_cast<unsigned long long>(filter_ct));
+    }
+  }
+  if (c.king_cutoff >= 0) {
+    if (c.parallel_tot != 1) {
+      logprintf("Error: --king-cutoff cannot be used with --parallel.\n");
+      return kRetInvalidCmdline;
+    }
+    KinshipPrune(&kin_table, n, cutoff_removed);
+    std::vector<uint32_t> in, out;
+    for (uint32_t k = 0; k < n; ++k) ((*cutoff_removed)[k] ? out : in).push_back(k);
+    const std::string in_name = c.out + ".king.cutoff.in.id", out_name = c.out + ".king.cutoff.out.id";
+    if (!WriteIdFile(in_name, S, in, true) || !WriteIdFile(out_name, S, out, true)) return kRetWriteFail;
+    logprintf("--king-cutoff: Excluded sample ID%s written to %s , and %u remaining sample ID%s written to %s .\n", out.size() == 1 ? "" : "s", out_name.c_str(), static_cast<uint32_t>(in.size()), in.size() == 1 ? "" : "s", in_name.c_str());
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ GRM
+// ComputeAlleleFreqs over founders (plink2.cc:2301, plink2_filter.cc:2113-2151).  Returns false
+// when every sample is a founder (the library then derives the same numbers from each block).
+bool FounderRefFreqs(Dataset* ds, Pl2GpuCtx* ctx, const std::vector<uint32_t>& vidx, std::vector<double>* ref_freqs, int* rc) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  uint32_t founder_ct = 0;
+  for (uint32_t k = 0; k < n; ++k) founder_ct += S.is_founder[k];
+  *rc = 0;
+  if (founder_ct == n) return false;
+  ref_freqs->assign(vidx.size(), 0.5);
+  if (!founder_ct) return true;
+  std::vector<uint64_t> inc((n + 63) / 64, 0);
+  for (uint32_t k = 0; k < n; ++k)
+    if (S.is_founder[k]) inc[k / 64] |= 1ull << (k % 64);
+  BlockStreamer bs(ds, &vidx, founder_ct, 16384);
+  bs.sample_include = inc.data();
+  if (!bs.Init()) {
+    *rc = GpuFail("pl2gpu_host_alloc");
+    return true;
+  }
+  std::vector<uint32_t> counts(4ull * 16384);
+  std::string err;
+  size_t base = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("Error: %s\n", err.c_str());
+      *rc = kRetMalformedInput;
+      return true;
+    }
+    if (!got) break;
+    if (pl2gpu_geno_counts(ctx, bs.buf, static_cast<uint64_t>(bs.words) * 8, founder_ct, static_cast<uint32_t>(got), 0, counts.data())) {
+      *rc = GpuFail("pl2gpu_geno_counts");
+      return true;
+    }
+    for (int v = 0; v < got; ++v) {
+      const uint64_t n0 = counts[4ull * v], n1 = counts[4ull * v + 1], n2 = counts[4ull * v + 2];
+      const uint64_t tot = 2 * (n0 + n1 + n2);
+      (*ref_freqs)[base + v] = tot ? static_cast<double>(2 * n0 + n1) * (1.0 / static_cast<double>(tot)) : 0.5;
+    }
+    base += static_cast<size_t>(got);
+  }
+  return true;
+}
+
+int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJob** kept_job, std::vector<uint32_t>* used_vidx) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  std::vector<uint32_t>& vidx = *used_vidx;
+  vidx.clear();
+  uint32_t non_auto = 0;
+  for (uint32_t v = 0; v < ds->variants.size(); ++v) {
+    if (KeptForRelationship(ds->variants.chr_code[v])) vidx.push_back(v);
+    else ++non_auto;
+  }
+  if (non_auto) logprintf("Excluding %u variant%s on non-autosomes from GRM construction.\n", non_auto, non_auto == 1 ? "" : "s");
+  if (vidx.empty()) {
+    logprintf("Error: No variants remaining for GRM construction.\n");
+    return kRetDegenerateData;
+  }
+  uint32_t r0, r1;
+  ParallelBounds(n, 0, c.parallel_idx, c.parallel_tot, &r0, &r1);
+  std::vector<double> ref_freqs;
+  int rc = 0;
+  const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
+  if (rc) return rc;
+  const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
+  Pl2GrmJob* job = nullptr;
+  if (pl2gpu_grm_begin(ctx, n, r0, r1, flags, &job)) return GpuFail("pl2gpu_grm_begin");
+  BlockStreamer bs(ds, &vidx, n, 32768);
+  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  logprintf("Constructing GRM: ");
+  std::string err;
+  size_t base = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("\nError: %s\n", err.c_str());
+      pl2gpu_grm_end(job);
+      return kRetMalformedInput;
+    }
+    if (!got) break;
+    const int arc = pl2gpu_grm_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, have_freqs ? ref_freqs.data() + base : nullptr);
+    if (arc) {
+      logprintf("\nError: %s\n", pl2gpu_last_error());
+      pl2gpu_grm_end(job);
+      return arc == 2 ? kRetDegenerateData : kRetGpuFail;
+    }
+    base += static_cast<size_t>(got);
+    printf("\rConstructing GRM: %u%%", static_cast<uint32_t>(base * 100 / vidx.size()));
+    fflush(stdout);
+  }
+  printf("\r");
+  logprintf("Constructing GRM: done.\n");
+  // writers
+  const uint64_t stride = r1;
+  const uint64_t max_rows = std::max<uint64_t>(1, (384ull << 20) / (stride * 12));
+  std::vector<double> g;
+  std::vector<float> obs;
+  auto fetch = [&](uint32_t a, uint32_t b) -> bool {
+    g.assign(static_cast<uint64_t>(b - a) * stride, 0.0);
+    obs.assign(static_cast<uint64_t>(b - a) * stride, 0.0f);
+    return pl2gpu_grm_get_rows(job, a, b, g.data(), obs.data(), stride, 0) == 0;
+  };
+  if (c.make_grm_bin) {
+    const std::string gname = PieceName(c.out + ".grm.bin", c), nname = PieceName(c.out + ".grm.N.bin", c);
+    OutFile fg, fn;
+    if (!fg.Open(gname) || !fn.Open(nname)) return kRetOpenFail;
+    std::vector<float> rowf(r1);
+    for (uint32_t a = r0; a < r1;) {
+      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      if (!fetch(a, b)) {
+        pl2gpu_grm_end(job);
+        return GpuFail("pl2gpu_grm_get_rows");
+      }
+      for (uint32_t j = a; j < b; ++j) {
+        const double* gr = &g[static_cast<uint64_t>(j - a) * stride];
+        for (uint32_t i = 0; i <= j; ++i) rowf[i] = static_cast<float>(gr[i]);
+        fg.Write(rowf.data(), sizeof(float) * (j + 1));
+        fn.Write(&obs[static_cast<uint64_t>(j - a) * stride], sizeof(float) * (j + 1));
+      }
+      a = b;
+    }
+    if (!fg.Close() || !fn.Close()) return kRetWriteFail;
+    std::string msg = std::string("--make-grm-bin: GRM ") + (c.parallel_tot != 1 ? "component " : "") + "written to " + gname + " , observation counts to " + nname;
+    if (!c.parallel_idx) {
+      const std::string idname = c.out + ".grm.id";
+      std::vector<uint32_t> all(n);
+      for (uint32_t k = 0; k < n; ++k) all[k] = k;
+      if (!WriteIdFile(idname, S, all, c.grm_id_header)) return kRetWriteFail;
+      msg += " , and IDs to " + idname;
+    }
+    logprintf("%s .\n", msg.c_str());
+  }
+  if (c.make_rel) {
+    const std::string base_name = c.out + (c.rel_enc == Cmd::kText ? ".rel" : ".rel.bin");
+    const std::string rname = PieceName(base_name, c);
+    if (c.rel_shape == Cmd::kSq && c.parallel_tot != 1) {
+      logprintf("Error: --make-rel square output cannot be combined with --parallel; use square0 or triangle.\n");
+      return kRetInvalidCmdline;
+    }
+    OutFile fr;
+    if (!fr.Open(rname)) return kRetOpenFail;
+    std::vector<double> full;  // square: whole lower triangle incl. diagonal
+    auto tri1 = [](uint64_t r) { return r * (r + 1) / 2; };
+    if (c.rel_shape == Cmd::kSq) full.resize(tri1(n));
+    for (uint32_t a = r0; a < r1;) {
+      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      if (!fetch(a, b)) {
+        pl2gpu_grm_end(job);
+        return GpuFail("pl2gpu_grm_get_rows");
+      }
+      for (uint32_t j = a; j < b; ++j) {
+        const double* gr = &g[static_cast<uint64_t>(j - a) * stride];
+        if (c.rel_shape == Cmd::kSq) {
+          memcpy(&full[tri1(j)], gr, sizeof(double) * (j + 1));
+          continue;
+        }
+        if (c.rel_enc == Cmd::kText) {
+          char* w = fr.Reserve(static_cast<size_t>(n) * 16 + 64);
+          for (uint32_t i = 0; i <= j; ++i) {
+            w = dtoa_g(gr[i], w);
+            *w++ = '\t';
+          }
+          if (c.rel_shape == Cmd::kSq0) {
+            for (uint32_t i = j + 1; i < n; ++i) {
+              *w++ = '0';
+              *w++ = '\t';
+            }
+          }
+          w[-1] = '\n';
+          fr.Advance(w);
+        } else {
+          const uint32_t len = (c.rel_shape == Cmd::kTri) ? j + 1 : n;
+          if (c.rel_enc == Cmd::kBin4) {
+            std::vector<float> row(len, 0.0f);
+            for (uint32_t i = 0; i <= j; ++i) row[i] = static_cast<float>(gr[i]);
+            fr.Write(row.data(), sizeof(float) * len);
+          } else {
+            std::vector<double> row(len, 0.0);
+            memcpy(row.data(), gr, sizeof(double) * (j + 1));
+            fr.Write(row.data(), sizeof(double) * len);
+          }
+        }
+      }
+      a = b;
+    }
+    if (c.rel_shape == Cmd::kSq) {
+      auto at = [&](uint32_t x, uint32_t y) { return x >= y ? full[tri1(x) + y] : full[tri1(y) + x]; };
+      for (uint32_t j = 0; j < n; ++j) {
+        if (c.rel_enc == Cmd::kText) {
+          char* w = fr.Reserve(static_cast<size_t>(n) * 16 + 64);
+          for (uint32_t i = 0; i < n; ++i) {
+            w = dtoa_g(at(j, i), w);
+            *w++ = '\t';
+          }
+          w[-1] = '\n';
+          fr.Advance(w);
+        } else if (c.rel_enc == Cmd::kBin4) {
+          std::vector<float> row(n);
+          for (uint32_t i = 0; i < n; ++i) row[i] = static_cast<float>(at(j, i));
+          fr.Write(row.data(), sizeof(float) * n);
+        } else {
+          std::vector<double> row(n);
+          for (uint32_t i = 0; i < n; ++i) row[i] = at(j, i);
+          fr.Write(row.data(), sizeof(double) * n);
+        }
+      }
+    }
+    if (!fr.Close()) return kRetWriteFail;
+    std::string msg = "--make-rel: GRM " + std::string(c.parallel_tot != 1 ? "component " : "") + "written to " + rname;
+    if (!c.parallel_idx) {
+      const std::string idname = c.out + ".rel.id";
+      std::vector<uint32_t> all(n);
+      for (uint32_t k = 0; k < n; ++k) all[k] = k;
+      if (!WriteIdFile(idname, S, all, true)) return kRetWriteFail;
+      msg += " , and IDs to " + idname;
+    }
+    logprintf("%s .\n", msg.c_str());
+  }
+  if (keep_for_pca) *kept_job = job;
+  else pl2gpu_grm_end(job);
+  return 0;
+}
+
+// --------------------------------------------------------------------------------------- LD prune
+int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size();
+  // unique variant IDs (plink2_ld.cc:2590-2593)
+  {
+    std::vector<std::string> ids;
+    for (uint32_t v = 0; v < V.size(); ++v)
+      if (V.chr_code[v]) ids.push_back(V.id[v]);
+    std::sort(ids.begin(), ids.end());
+    for (size_t k = 1; k < ids.size(); ++k) {
+      if (ids[k] == ids[k - 1]) {
+        logprintf("Error: --indep-pairwise requires unique variant IDs ('%s' appears multiple times).\n", ids[k].c_str());
+        return kRetInconsistentInput;
+      }
+    }
+  }
+  for (uint32_t v = 0; v < V.size(); ++v) {
+    if (V.chr_code[v] > 22 && V.chr_code[v] != 25) {
+      logprintf("Error: --indep-pairwise on chrX/chrY/chrMT variants is not supported by plink2_b200 yet (restrict to autosomes first).\n");
+      return kRetNotYetSupported;
+    }
+  }
+  uint32_t founder_ct = 0;
+  std::vector<uint64_t> inc((n + 63) / 64, 0);
+  for (uint32_t k = 0; k < n; ++k) {
+    if (S.is_founder[k]) {
+      inc[k / 64] |= 1ull << (k % 64);
+      ++founder_ct;
+    }
+  }
+  if (founder_ct < 50 && !c.bad_ld) {  // plink2.cc:2065
+    logprintf("Error: This run estimates linkage disequilibrium between variants, but there are less than 50 founders in the current dataset.  LD estimates would be very noisy; use --bad-ld to override.\n");
+    return kRetDegenerateData;
+  }
+  const uint32_t m = V.size();
+  const uint32_t words = PgenReader::WordsFor(founder_ct);
+  std::vector<uint32_t> all(m);
+  for (uint32_t v = 0; v < m; ++v) all[v] = v;
+  BlockStreamer bs(ds, &all, founder_ct, 8192);
+  if (founder_ct != n) bs.sample_include = inc.data();
+  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  // the whole founder block is staged in host memory (M * ceil(F/32) * 8 bytes), then handed to the
+  // function-face entry point which windows it through the GPU
+  void* blk = nullptr;
+  if (pl2gpu_host_alloc(static_cast<uint64_t>(m) * words * 8, &blk)) return GpuFail("pl2gpu_host_alloc");
+  std::string err;
+  size_t base = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("Error: %s\n", err.c_str());
+      pl2gpu_host_free(blk);
+      return kRetMalformedInput;
+    }
+    if (!got) break;
+    memcpy(static_cast<uint64_t*>(blk) + base * words, bs.buf, static_cast<uint64_t>(got) * words * 8);
+    base += static_cast<size_t>(got);
+  }
+  std::vector<uint8_t> removed(m, 0);
+  const int rc = pl2_indep_pairwise(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, nullptr, 0, removed.data());
+  pl2gpu_host_free(blk);
+  if (rc) return GpuFail("pl2_indep_pairwise");
+  // LdPruneWrite (plink2_ld.cc:2464-2528)
+  const std::string in_name = c.out + ".prune.in", out_name = c.out + ".prune.out";
+  OutFile fin, fout;
+  if (!fin.Open(in_name) || !fout.Open(out_name)) return kRetOpenFail;
+  uint32_t removed_ct = 0, considered = 0;
+  for (uint32_t v = 0; v < m; ++v) {
+    if (removed[v] == 2) continue;
+    ++considered;
+    OutFile& f = removed[v] ? fout : fin;
+    removed_ct += removed[v];
+    f.Write(V.id[v].data(), V.id[v].size());
+    f.Puts("\n");
+  }
+  if (!fin.Close() || !fout.Close()) return kRetWriteFail;
+  logprintf("--indep-pairwise: %u/%u variant%s removed.\n", removed_ct, considered, considered == 1 ? "" : "s");
+  logprintf("Variant lists written to %s and %s .\n", in_name.c_str(), out_name.c_str());
+  return 0;
+}
+
+}  // namespace
+
+// Host-only debug hooks used by the CPU test-suite (no GPU involved):
+//   --debug-dtoa <in: raw doubles> <out: one dtoa_g line each>
+//   --debug-dump-geno <pgen> <psam/fam> <pvar/bim> <out: one byte per genotype, variant-major>
+int DebugHooks(int argc, char** argv) {
+  if (argc == 4 && !strcmp(argv[1], "--debug-dtoa")) {
+    FILE* in = fopen(argv[2], "rb");
+    OutFile out;
+    if (!in || !out.Open(argv[3])) return kRetOpenFail;
+    double x;
+    while (fread(&x, 8, 1, in) == 1) {
+      char* w = out.Reserve(64);
+      w = dtoa_g(x, w);
+      *w++ = '\n';
+      out.Advance(w);
+    }
+    fclose(in);
+    return out.Close() ? 0 : kRetWriteFail;
+  }
+  if (argc == 6 && !strcmp(argv[1], "--debug-dump-geno")) {
+    Dataset ds;
+    std::string err;
+    if (!LoadSamples(argv[3], &ds.samples, &err) || !LoadVariants(argv[4], &ds.variants, &err) || !ds.reader.Open(argv[2], ds.samples.size(), ds.variants.size(), &err)) {
+      fprintf(stderr, "Error: %s\n", err.c_str());
+      return kRetMalformedInput;
+    }
+    OutFile out;
+    if (!out.Open(argv[5])) return kRetOpenFail;
+    const uint32_t n = ds.samples.size();
+    std::vector<uint64_t> gv(PgenReader::WordsFor(n));
+    std::vector<uint8_t> row(n);
+    for (uint32_t v = 0; v < ds.variants.size(); ++v) {
+      if (!ds.reader.Get(v, gv.data(), &err)) {
+        fprintf(stderr, "Error: %s\n", err.c_str());
+        return kRetMalformedInput;
+      }
+      for (uint32_t k = 0; k < n; ++k) row[k] = (gv[k / 32] >> (2 * (k % 32))) & 3;
+      out.Write(row.data(), n);
+    }
+    return out.Close() ? 0 : kRetWriteFail;
+  }
+  return -1;
+}
+
+int main(int argc, char** argv) {
+  {
+    const int dbg = DebugHooks(argc, argv);
+    if (dbg >= 0) return dbg;
+  }
+  Cmd c;
+  // the log file name depends on --out, so scan for it first
+  for (int i = 1; i + 1 < argc; ++i)
+    if (!strcmp(argv[i], "--out")) c.out = argv[i + 1];
+  g_log = fopen((c.out + ".log").c_str(), "w");
+  logprintf("plink2_b200: B200-native KING / GRM / PCA / --indep-pairwise (plink2 command-line face)\n");
+  {
+    std::string opts = "Options in effect:\n";
+    for (int i = 1; i < argc; ++i) {
+      if (argv[i][0] == '-' && argv[i][1] == '-') opts += std::string(i > 1 ? "\n" : "") + "  " + argv[i];
+      else opts += std::string(" ") + argv[i];
+    }
+    logprintf("%s\n\n", opts.c_str());
+  }
+  int rc = ParseArgs(argc, argv, &c);
+  if (rc) return rc;
+  Dataset ds;
+  std::string err;
+  if (!LoadSamples(c.psam, &ds.samples, &err) || !LoadVariants(c.pvar, &ds.variants, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  if (!ds.reader.Open(c.pgen, ds.samples.size(), ds.variants.size(), &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetMalformedInput;
+  }
+  uint32_t founder_ct = 0;
+  for (uint8_t f : ds.samples.is_founder) founder_ct += f;
+  logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
+  logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
+  Pl2GpuCtx* ctx = nullptr;
+  if (pl2gpu_ctx_create(c.device, &ctx)) {
+    logprintf("Error: GPU initialisation failed: %s\n", pl2gpu_last_error());
+    return kRetGpuFail;
+  }
+  std::vector<uint8_t> cutoff_removed;
+  if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
+    rc = RunKing(c, &ds, ctx, &cutoff_removed);
+    if (rc) return rc;
+    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_rel || c.pca || c.indep_pairwise)) {
+      logprintf("Error: chaining --king-cutoff sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
+      return kRetNotYetSupported;
+    }
+  }
+  Pl2GrmJob* grm_job = nullptr;
+  std::vector<uint32_t> grm_vidx;
+  const bool exact_pca = c.pca && !c.pca_approx;
+  if (c.make_grm_bin || c.make_rel || exact_pca) {
+    if (exact_pca && c.parallel_tot != 1) {
+      logprintf("Error: --pca cannot be used with --parallel.\n");
+      return kRetInvalidCmdline;
+    }
+    rc = RunGrm(c, &ds, ctx, exact_pca, &grm_job, &grm_vidx);
+    if (rc) return rc;
+  }
+  if (c.pca) {
+    rc = RunPca(c.out, c.pc_ct, c.pca_approx, c.seed_given, c.seed, c.threads, &ds, ctx, grm_job);
+    if (grm_job) pl2gpu_grm_end(grm_job);
+    if (rc) return rc;
+  }
+  if (c.indep_pairwise) {
+    rc = RunLdPrune(c, &ds, ctx);
+    if (rc) return rc;
+  }
+  pl2gpu_ctx_destroy(ctx);
+  time_t now = time(nullptr);
+  logprintf("End time: %s", ctime(&now));
+  if (g_log) fclose(g_log);
+  return 0;
+}

@@ -213,6 +213,30 @@ void* pl2gpu_ctx_stream(Pl2GpuCtx* ctx) { return ctx ? static_cast<void*>(ctx->c
 
 uint64_t pl2gpu_ctx_launch_count(Pl2GpuCtx* ctx) { return ctx ? ctx->c.launches : 0; }
 
+int pl2gpu_ctx_mem_info(Pl2GpuCtx* ctx, uint64_t* free_bytes, uint64_t* total_bytes) {
+  if (!ctx) {
+    set_error("pl2gpu_ctx_mem_info: null context");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  size_t f = 0, t = 0;
+  PL2_CUDA_OK(cudaMemGetInfo(&f, &t));
+  if (free_bytes) *free_bytes = f;
+  if (total_bytes) *total_bytes = t;
+  return 0;
+}
+
+int pl2gpu_host_alloc(uint64_t bytes, void** ptr) {
+  *ptr = nullptr;
+  PL2_CUDA_OK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return 0;
+}
+
+int pl2gpu_host_free(void* ptr) {
+  if (ptr) PL2_CUDA_OK(cudaFreeHost(ptr));
+  return 0;
+}
+
 int pl2gpu_ctx_event_record(Pl2GpuCtx* ctx, int slot) {
   if (!ctx || slot < 0 || slot >= 16) {
     set_error("pl2gpu_ctx_event_record: bad arguments");

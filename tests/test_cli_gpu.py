@@ -1,0 +1,106 @@
+"""GPU: the plink2 command-line face.  plink2_b200 is run with the reference's own flags on the
+golden inputs and its output FILES are compared with the files the reference binary wrote
+(tests/golden/, see make_golden.sh): byte-identical for KING tables / matrices / ID lists /
+prune lists / observation counts, fp32-identical-or-1ulp for GRM payloads."""
+import gzip
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "plink_ng_b200", "plink2_b200")
+
+
+def run(golden_dir, tmp_path, *flags, inp="bfile"):
+    out = str(tmp_path / "o")
+    src = ["--bfile", os.path.join(golden_dir, "a")] if inp == "bfile" else ["--pgen", os.path.join(golden_dir, inp), "--pvar", os.path.join(golden_dir, "a.pvar"), "--psam", os.path.join(golden_dir, "a.psam")]
+    r = subprocess.run([BIN] + src + list(flags) + ["--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return out
+
+
+def gz(golden_dir, name):
+    return gzip.open(os.path.join(golden_dir, name), "rb").read()
+
+
+def test_make_king_table_counts_byte_identical(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--make-king-table", "counts", "cols=+ibs1,+ibs", "--make-king", "bin4", "triangle")
+    assert open(out + ".kin0", "rb").read() == gz(golden_dir, "a_king.kin0.gz")
+    assert open(out + ".king.bin", "rb").read() == open(os.path.join(golden_dir, "a_king.king.bin"), "rb").read()
+
+
+def test_make_king_table_proportions_byte_identical(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--make-king-table")
+    assert open(out + ".kin0", "rb").read() == gz(golden_dir, "a_kingp.kin0.gz")
+
+
+def test_make_king_square_text_and_ids(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--make-king", "square")
+    assert open(out + ".king", "rb").read() == gz(golden_dir, "a_kingsq.king.gz")
+    assert open(out + ".king.id", "rb").read() == open(os.path.join(golden_dir, "a_kingsq.king.id"), "rb").read()
+
+
+def test_make_king_table_parallel_piece(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--make-king-table", "counts", "--parallel", "2", "3")
+    assert open(out + ".kin0.2", "rb").read() == gz(golden_dir, "a_kingpar.kin0.2.gz")
+
+
+def test_king_cutoff_lists(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--king-cutoff", "0.02")
+    for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):
+        assert open(out + ext, "rb").read() == open(os.path.join(golden_dir, "a_cut" + ext), "rb").read(), ext
+
+
+@pytest.mark.parametrize("inp", ["bfile", "a_mode10.pgen", "a_mode02.pgen"])
+def test_make_grm_bin_files(golden_dir, tmp_path, inp):
+    out = run(golden_dir, tmp_path, "--make-grm-bin", inp=inp)
+    got = np.fromfile(out + ".grm.bin", dtype=np.float32)
+    ref = np.fromfile(os.path.join(golden_dir, "a_grm.grm.bin"), dtype=np.float32)
+    # fp64 values agree to ~1e-10; after the cast to fp32 at most the last bit can differ
+    assert np.all(np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)) <= 1)
+    assert (got != ref).mean() < 0.02
+    assert open(out + ".grm.N.bin", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.N.bin"), "rb").read()
+    if inp == "bfile":
+        assert open(out + ".grm.id", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.id"), "rb").read()
+
+
+def test_make_rel_variants(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--make-rel", "cov", "bin4", "triangle")
+    got = np.fromfile(out + ".rel.bin", dtype=np.float32)
+    ref = np.fromfile(os.path.join(golden_dir, "a_relcov.rel.bin"), dtype=np.float32)
+    assert np.all(np.abs(got.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)) <= 1)
+    out = run(golden_dir, tmp_path, "--make-rel", "square")
+    got_txt = open(out + ".rel").read().split("\n")
+    ref_txt = gz(golden_dir, "a_rel.rel.gz").decode().split("\n")
+    assert len(got_txt) == len(ref_txt)
+    diff = 0
+    for a, b in zip(got_txt, ref_txt):
+        if a != b:
+            fa, fb = np.array(a.split("\t"), dtype=float), np.array(b.split("\t"), dtype=float)
+            assert np.allclose(fa, fb, rtol=2e-6, atol=1e-12)
+            diff += int((np.array(a.split("\t")) != np.array(b.split("\t"))).sum())
+    assert diff <= 20  # 6-significant-digit text: only exact rounding ties may print differently
+
+
+@pytest.mark.parametrize("flags,name", [(("50", "5", "0.2"), "a_ld"), (("100", "1", "0.1"), "a_ld2"), (("20kb", "0.3"), "a_ldkb")])
+def test_indep_pairwise_lists_byte_identical(golden_dir, tmp_path, flags, name):
+    out = run(golden_dir, tmp_path, "--indep-pairwise", *flags)
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, name + ".prune.in"), "rb").read()
+    if name == "a_ld":
+        assert open(out + ".prune.out", "rb").read() == open(os.path.join(golden_dir, "a_ld.prune.out"), "rb").read()
+
+
+def test_toy_fixture_configs0(golden_dir, tmp_path):
+    out = str(tmp_path / "toy")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".king", "rb").read() == open(os.path.join(golden_dir, "toy_king.king"), "rb").read()
+    assert open(out + ".kin0", "rb").read() == open(os.path.join(golden_dir, "toy_king.kin0"), "rb").read()
+
+
+def test_unsupported_flag_fails_loudly(golden_dir, tmp_path):
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--glm", "--out", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode == 8 and "unsupported" in r.stdout
