@@ -118,6 +118,10 @@ int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t varia
  * dst_obs (optional) receives the per-pair observation counts as float (.grm.N.bin payload). */
 int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_grm, float* dst_obs, uint64_t row_stride, int dst_is_device);
 uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job);
+/* Exact --pca (CalcPca non-approx branch, plink2_matrix_calc.cc:5942-6040 -> ExtractEigvecs/dsyevr,
+ * plink2_matrix.cc:1089): top pc_ct eigenpairs of the finished GRM (job must cover all rows).
+ * eigvals_host[pc_ct] descending; eigvecs_host[pc][sample], unit norm, sign arbitrary. */
+int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, double* eigvecs_host);
 int pl2gpu_grm_end(Pl2GrmJob* job);
 
 /* ---- per-variant genotype counts {hom-REF, het, hom-ALT, missing}: the hard-call part of the

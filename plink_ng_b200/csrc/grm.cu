@@ -4,6 +4,8 @@
 #include <cstring>
 #include <vector>
 
+#include <cusolverDn.h>
+
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "grm_kernels.cuh"
@@ -227,6 +229,96 @@ int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_gr
 }
 
 uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job) { return job ? job->variants_added : 0; }
+
+// Exact --pca: top-k eigenpairs of the finished GRM (CalcPca non-approx branch,
+// plink2_matrix_calc.cc:5942-6040, which calls LAPACK dsyevr through ExtractEigvecs,
+// plink2_matrix.cc:1089-1104).  The dense symmetric eigensolver is a library call here as well
+// (cuSOLVER syevdx); it is not part of the pairwise hot path.
+int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, double* eigvecs_host) {
+  if (!job || !pc_ct) {
+    set_error("pl2gpu_grm_eigen_topk: bad arguments");
+    return 1;
+  }
+  const uint32_t n = job->sample_ct;
+  if (job->row_start != 0 || job->row_end != n) {
+    set_error("pl2gpu_grm_eigen_topk: needs the whole matrix (rows [0,%u)), job holds [%u,%u)", n, job->row_start, job->row_end);
+    return 1;
+  }
+  if (pc_ct > n) {
+    set_error("pl2gpu_grm_eigen_topk: %u PCs requested from %u samples", pc_ct, n);
+    return 1;
+  }
+  if (n > 46340) {  // same int32 n^2 limit as the reference's non-ILP64 LAPACK build (:5943-5948)
+    set_error("pl2gpu_grm_eigen_topk: exact PCA is limited to 46340 samples; use --pca approx");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  double* d_a = nullptr;
+  double* d_w = nullptr;
+  double* d_work = nullptr;
+  int* d_info = nullptr;
+  cusolverDnHandle_t h = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_a, static_cast<uint64_t>(n) * n * 8) != cudaSuccess || cudaMalloc(&d_w, static_cast<uint64_t>(n) * 8) != cudaSuccess || cudaMalloc(&d_info, 4) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_grm_eigen_topk: insufficient device memory for a dense %u x %u matrix", n, n);
+      break;
+    }
+    if (cudaMemsetAsync(d_a, 0, static_cast<uint64_t>(n) * n * 8, c->stream) != cudaSuccess) break;
+    // row-major lower triangle == column-major upper triangle
+    if (pl2gpu_grm_get_rows(job, 0, n, d_a, nullptr, n, 1)) break;
+    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS || cusolverDnSetStream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
+      set_error("pl2gpu_grm_eigen_topk: cusolverDnCreate failed");
+      break;
+    }
+    int lwork = 0, meig = 0;
+    const int il = static_cast<int>(n - pc_ct + 1), iu = static_cast<int>(n);
+    if (cusolverDnDsyevdx_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+      set_error("pl2gpu_grm_eigen_topk: syevdx workspace query failed");
+      break;
+    }
+    if (cudaMalloc(&d_work, static_cast<uint64_t>(lwork) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_grm_eigen_topk: insufficient device memory for the eigensolver workspace");
+      break;
+    }
+    const cusolverStatus_t st = cusolverDnDsyevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, d_work, lwork, d_info);
+    c->launches++;
+    int info = 0;
+    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    if (st != CUSOLVER_STATUS_SUCCESS || info != 0 || meig != static_cast<int>(pc_ct)) {
+      set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (status %d, info %d, %d eigenvalues); the GRM may contain missing values", static_cast<int>(st), info, meig);
+      break;
+    }
+    std::vector<double> w(pc_ct), v(static_cast<uint64_t>(pc_ct) * n);
+    if (cudaMemcpy(w.data(), d_w, 8ull * pc_ct, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(v.data(), d_a, 8ull * pc_ct * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    bool finite = true;
+    for (uint32_t k = 0; k < pc_ct; ++k) {  // ascending -> descending (:6024-6039)
+      eigvals_host[k] = w[pc_ct - 1 - k];
+      finite = finite && std::isfinite(eigvals_host[k]);
+      memcpy(eigvecs_host + static_cast<uint64_t>(k) * n, v.data() + static_cast<uint64_t>(pc_ct - 1 - k) * n, 8ull * n);
+    }
+    if (!finite) {
+      set_error("pl2gpu_grm_eigen_topk: GRM contains missing values (a sample pair has no jointly observed variant)");
+      break;
+    }
+    rc = 0;
+  } while (0);
+  if (h) cusolverDnDestroy(h);
+  cudaFree(d_a);
+  cudaFree(d_w);
+  cudaFree(d_work);
+  cudaFree(d_info);
+  return rc;
+}
 
 int pl2gpu_grm_end(Pl2GrmJob* job) {
   if (!job) return 0;

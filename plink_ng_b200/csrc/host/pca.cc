@@ -1,12 +1,79 @@
 #include "pca.h"
 
 #include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "text_util.h"
 
 namespace pl2host {
 
-int RunPca(const std::string&, uint32_t, bool, bool, uint64_t, uint32_t, Dataset*, Pl2GpuCtx*, Pl2GrmJob*) {
-  fprintf(stderr, "Error: --pca is not available in this build yet.\n");
-  return 63;
+namespace {
+
+// .eigenvec / .eigenval writers (plink2_matrix_calc.cc:6237-6290): "#[FID\t]IID[\tSID]\tPC1..PCk",
+// one line per sample; eigenvalues one per line, both through dtoa_g.
+bool WriteEigen(const std::string& out_prefix, const SampleInfo& S, uint32_t pc_ct, const double* eigvals, const double* eigvecs /* [pc][sample] */) {
+  const uint32_t n = S.size();
+  OutFile fv, fe;
+  if (!fv.Open(out_prefix + ".eigenvec") || !fe.Open(out_prefix + ".eigenval")) return false;
+  std::string h = "#";
+  if (S.fid_present) h += "FID\t";
+  h += "IID";
+  if (S.sid_present) h += "\tSID";
+  for (uint32_t k = 0; k < pc_ct; ++k) h += "\tPC" + std::to_string(k + 1);
+  h += "\n";
+  fv.Puts(h.c_str());
+  for (uint32_t s = 0; s < n; ++s) {
+    std::string id;
+    if (S.fid_present) id += S.fid[s] + "\t";
+    id += S.iid[s];
+    if (S.sid_present) id += "\t" + S.sid[s];
+    char* w = fv.Reserve(id.size() + 16 * pc_ct + 16);
+    memcpy(w, id.data(), id.size());
+    w += id.size();
+    for (uint32_t k = 0; k < pc_ct; ++k) {
+      *w++ = '\t';
+      w = dtoa_g(eigvecs[static_cast<uint64_t>(k) * n + s], w);
+    }
+    *w++ = '\n';
+    fv.Advance(w);
+  }
+  for (uint32_t k = 0; k < pc_ct; ++k) {
+    char* w = fe.Reserve(32);
+    w = dtoa_g(eigvals[k], w);
+    *w++ = '\n';
+    fe.Advance(w);
+  }
+  return fv.Close() && fe.Close();
+}
+
+}  // namespace
+
+int RunPca(const std::string& out_prefix, uint32_t pc_ct, bool approx, bool seed_given, uint64_t seed, uint32_t threads, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
+  (void)seed_given;
+  (void)seed;
+  (void)threads;
+  (void)ctx;
+  const uint32_t n = ds->samples.size();
+  if (approx) {
+    fprintf(stderr, "Error: \"--pca approx\" is not available in this build yet (exact --pca is).\n");
+    return 63;
+  }
+  if (pc_ct > n) pc_ct = n;  // the reference reduces the PC count with a warning (:5655-5661)
+  std::vector<double> eigvals(pc_ct), eigvecs(static_cast<uint64_t>(pc_ct) * n);
+  printf("Extracting eigenvalue%s and eigenvector%s... ", pc_ct == 1 ? "" : "s", pc_ct == 1 ? "" : "s");
+  fflush(stdout);
+  if (pl2gpu_grm_eigen_topk(grm_job, pc_ct, eigvals.data(), eigvecs.data())) {
+    printf("\nError: %s\n", pl2gpu_last_error());
+    return 16;
+  }
+  printf("done.\n");
+  if (!WriteEigen(out_prefix, ds->samples, pc_ct, eigvals.data(), eigvecs.data())) {
+    printf("Error: File write failure.\n");
+    return 5;
+  }
+  printf("--pca: Eigenvector%s written to %s.eigenvec , and eigenvalue%s written to %s.eigenval .\n", pc_ct == 1 ? "" : "s", out_prefix.c_str(), pc_ct == 1 ? "" : "s", out_prefix.c_str());
+  return 0;
 }
 
 }  // namespace pl2host

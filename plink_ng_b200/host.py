@@ -226,6 +226,13 @@ class GrmJob:
         check(lib.pl2gpu_grm_get_rows(self._h, r0, r1, g.ctypes.data, obs.ctypes.data if with_obs else None, r1, 0), "pl2gpu_grm_get_rows")
         return (g, obs) if with_obs else g
 
+    def eigen_topk(self, pc_ct: int):
+        """Exact --pca: (eigvals[pc_ct] descending, eigvecs[pc_ct, samples])."""
+        vals = np.empty(pc_ct, dtype=np.float64)
+        vecs = np.empty((pc_ct, self.sample_ct), dtype=np.float64)
+        check(lib.pl2gpu_grm_eigen_topk(self._h, pc_ct, vals.ctypes.data, vecs.ctypes.data), "pl2gpu_grm_eigen_topk")
+        return vals, vecs
+
     def close(self):
         if self._h:
             lib.pl2gpu_grm_end(self._h)

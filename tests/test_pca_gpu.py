@@ -1,0 +1,66 @@
+"""GPU parity: exact --pca (top-k eigenpairs of the GPU-built GRM) vs numpy eigh of the oracle GRM
+and vs the reference's .eigenval/.eigenvec (LAPACK-enabled oracle build), sign-flip tolerant like
+the reference's own comparer (2.0/Tests/TEST_PHASED_VCF/pca_compare.py:75-80)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from plink_ng_b200.host import GrmJob, pack_genotypes
+from oracle import plink_oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "plink_ng_b200", "plink2_b200")
+
+
+def _structured_geno(m, n, seed, pops=4, fst=0.08, miss=0.01):
+    """Balding-Nichols populations so the leading eigenvalues are well separated (SURVEY 8c caveat)."""
+    rng = np.random.default_rng(seed)
+    anc = rng.uniform(0.1, 0.9, size=m)
+    a = anc * (1 - fst) / fst
+    b = (1 - anc) * (1 - fst) / fst
+    pf = rng.beta(a[:, None], b[:, None], size=(m, pops))
+    lab = rng.integers(0, pops, size=n)
+    f = pf[:, lab]
+    g = (rng.random((m, n)) < f).astype(np.uint8) + (rng.random((m, n)) < f).astype(np.uint8)
+    g[rng.random((m, n)) < miss] = 3
+    return g
+
+
+def _align(vecs, ref):
+    s = np.sign(np.sum(vecs * ref, axis=1, keepdims=True))
+    s[s == 0] = 1
+    return vecs * s
+
+
+def test_exact_pca_matches_numpy_eigh(gpu_ctx):
+    n, m, k = 300, 4000, 5
+    geno = _structured_geno(m, n, seed=4)
+    want, _ = orc.grm(geno)
+    w, v = np.linalg.eigh(want)
+    w, v = w[::-1][:k], v[:, ::-1][:, :k].T
+    with GrmJob(gpu_ctx, n) as job:
+        job.add_variants(pack_genotypes(geno))
+        vals, vecs = job.eigen_topk(k)
+    assert np.allclose(vals, w, rtol=1e-8)
+    assert np.allclose(_align(vecs[:3], v[:3]), v[:3], atol=1e-5 * np.abs(v[:3]).max())  # 3 structure PCs: 1e-5 relative
+    assert np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-12)
+
+
+def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
+    out = str(tmp_path / "p")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--pca", "4", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref_val = np.loadtxt(os.path.join(golden_dir, "a_pca.eigenval"))
+    got_val = np.loadtxt(out + ".eigenval")
+    assert np.allclose(got_val, ref_val, rtol=3e-6)
+    ref = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(golden_dir, "a_pca.eigenvec"))]
+    got = [ln.rstrip("\n").split("\t") for ln in open(out + ".eigenvec")]
+    assert got[0] == ref[0] and [g[:2] for g in got] == [g[:2] for g in ref]
+    rv = np.array([x[2:] for x in ref[1:]], dtype=float).T
+    gv = np.array([x[2:] for x in got[1:]], dtype=float).T
+    # unstructured --dummy data: eigenvalue gaps ~1e-2, so eigenvectors are compared at the
+    # 6-significant-digit print precision amplified by 1/gap
+    assert np.allclose(_align(gv, rv), rv, atol=2e-4)
