@@ -195,7 +195,8 @@ def b200_arm(args):
     import torch.distributed as dist
 
     import plink_ng_b200 as p
-    from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KingJob, parallel_bounds
+    from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KingJob
+    from plink_ng_b200.sharding import assemble_block, pairs_in_rows, row_block, variant_slice
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -207,18 +208,17 @@ def b200_arm(args):
     n = args.samples
     mb = args.batch_variants
     row_bytes = (n + 31) // 32 * 8
-    r0, r1 = parallel_bounds(n, 1, rank, world)
-    my_pairs = (r1 * (r1 - 1) - r0 * (r0 - 1)) // 2
+    r0, r1 = row_block(n, rank, world)
+    my_pairs = pairs_in_rows(r0, r1)
     total_pairs = n * (n - 1) // 2
     algo = KING_ALGO_TENSOR if args.algo == "tensor" else KING_ALGO_POPCOUNT
 
     # this rank's slice of the step's variants; all_gather assembles the tile (north_star)
-    per = (mb + world - 1) // world
-    v0, v1 = min(mb, rank * per), min(mb, (rank + 1) * per)
+    per, v0, v1 = variant_slice(mb, rank, world)
     slice_dev = torch.zeros((per, row_bytes), dtype=torch.uint8, device=dev)
     if v1 > v0:
         slice_dev[: v1 - v0] = synth_genovecs(torch, n, v0, v1, dev)
-    full = torch.empty((per * world, row_bytes), dtype=torch.uint8, device=dev) if world > 1 else slice_dev
+    full = slice_dev  # world == 1; otherwise re-assembled by the all_gather of every step
     torch.cuda.synchronize()
 
     ctx = p.GpuContext(local_rank)
@@ -227,9 +227,9 @@ def b200_arm(args):
     ext_stream = torch.cuda.ExternalStream(ctx.stream(), device=dev)
 
     def step_resident():
+        nonlocal full
         with torch.cuda.stream(ext_stream):
-            if world > 1:
-                dist.all_gather_into_tensor(full.view(-1), slice_dev.view(-1))
+            full = assemble_block(dist, torch, slice_dev, per, world)
         job.add_variants_device(full.data_ptr(), row_bytes, mb)
 
     def barrier():

@@ -51,7 +51,8 @@ def test_exact_pca_matches_numpy_eigh(gpu_ctx):
 
 def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
     out = str(tmp_path / "p")
-    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--pca", "4", "--out", out], capture_output=True, text=True)
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--pca", "4", "--out", out], capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout + r.stderr
     ref_val = np.loadtxt(os.path.join(golden_dir, "a_pca.eigenval"))
     got_val = np.loadtxt(out + ".eigenval")
