@@ -124,6 +124,17 @@ uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job);
 int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, double* eigvecs_host);
 int pl2gpu_grm_end(Pl2GrmJob* job);
 
+/* ---- `--pca approx` (CalcPca approx branch, 2.0/plink2_matrix_calc.cc:5697-5941: CalcPcaXtxaThread
+ * :5210, CalcPcaXaThread :5243, CalcPcaXtbThread :5272, SvdRectFused :5860/:5918).  The whole 2-bit
+ * genotype matrix stays resident in HBM; Y (standardised, missing -> 0) is never materialised.
+ * g1_host: the N x 2k Gaussian start matrix, row-major [sample][2k] (FillGaussianDArr order).
+ * Returns eigvals[pc_ct] = sigma^2 / M and eigvecs[pc][sample].  Return code 2 = kPglRetDegenerateData. ---- */
+typedef struct Pl2PcaJob Pl2PcaJob;
+int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, Pl2PcaJob** job_ptr);
+int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs);
+int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, double* eigvecs_host);
+int pl2gpu_pca_end(Pl2PcaJob* job);
+
 /* ---- per-variant genotype counts {hom-REF, het, hom-ALT, missing}: the hard-call part of the
  * LoadAlleleAndGenoCounts pre-pass (2.0/plink2.cc:2280; GenoarrCountFreqsUnsafe,
  * 2.0/include/pgenlib_misc.cc:702) that feeds ComputeAlleleFreqs (2.0/plink2_filter.cc:2113).

@@ -384,3 +384,33 @@ def read_bim(path: str):
             ids.append(t[1])
             bps.append(int(t[3]))
     return np.array(chrom), ids, np.array(bps, dtype=np.int64)
+
+
+# --------------------------------------------------------------------------------------------- PCA
+def pca_exact(grm_matrix: np.ndarray, pc_ct: int):
+    """CalcPca exact branch (2.0/plink2_matrix_calc.cc:5942-6040): top-k eigenpairs, descending."""
+    w, v = np.linalg.eigh(grm_matrix)
+    return w[::-1][:pc_ct], v[:, ::-1][:, :pc_ct].T
+
+
+def pca_approx(geno: np.ndarray, pc_ct: int, g1: np.ndarray, ref_freq: np.ndarray = None):
+    """CalcPca approx branch (2.0/plink2_matrix_calc.cc:5697-5941) for a given Gaussian start matrix
+    g1 [samples, 2k]: k+1 projections H_t = Y G_t with G_{t+1} = Y^T H_t / M kept side by side (qq,
+    M x 2k(k+1)); Q = left singular vectors of qq; B = Y^T Q; eigvecs = first k left singular vectors
+    of B, eigvals = sigma^2 / M.  Y = centered_varmaj (missing -> 0, always variance-standardised)."""
+    if ref_freq is None:
+        ref_freq = ref_allele_freqs(geno)
+    y = centered_varmaj(geno, ref_freq, True)
+    m = y.shape[0]
+    c2 = 2 * pc_ct
+    qq = np.empty((m, c2 * (pc_ct + 1)))
+    g = np.array(g1, dtype=np.float64)
+    for it in range(pc_ct + 1):
+        h = y @ g
+        qq[:, it * c2 : (it + 1) * c2] = h
+        if it < pc_ct:
+            g = (y.T @ h) * (1.0 / m)
+    u, _, _ = np.linalg.svd(qq, full_matrices=False)
+    b = y.T @ u
+    ub, sb, _ = np.linalg.svd(b, full_matrices=False)
+    return sb[:pc_ct] ** 2 * (1.0 / m), ub[:, :pc_ct].T

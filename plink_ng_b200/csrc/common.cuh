@@ -82,6 +82,8 @@ struct GenoStage {
 };
 constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
 constexpr uint32_t kMaxStageVariants = 65536;
+// pad_genotypes_kernel launcher (kernel lives in pl2gpu.cu's translation unit)
+int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded);
 int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t sample_pad = kSamplePad);
 void StageFree(GenoStage* gs);
 // Copies variant_ct (<= variant_cap) rows starting at destination row dst_row and forces padding

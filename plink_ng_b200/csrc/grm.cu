@@ -5,6 +5,7 @@
 #include <vector>
 
 #include <cusolverDn.h>
+#include <dlfcn.h>
 
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
@@ -230,6 +231,38 @@ int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_gr
 
 uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job) { return job ? job->variants_added : 0; }
 
+// cuSOLVER is loaded on first use (dlopen): it and its cuBLAS dependencies are ~1 GB of shared
+// objects that the KING / GRM / LD commands never need.
+namespace {
+struct CusolverApi {
+  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*syevdx_bufsize)(cusolverDnHandle_t, cusolverEigMode_t, cusolverEigRange_t, cublasFillMode_t, int, const double*, int, double, double, int, int, int*, const double*, int*) = nullptr;
+  cusolverStatus_t (*syevdx)(cusolverDnHandle_t, cusolverEigMode_t, cusolverEigRange_t, cublasFillMode_t, int, double*, int, double, double, int, int, int*, double*, double*, int, int*) = nullptr;
+  bool ok = false;
+};
+CusolverApi* LoadCusolver() {
+  static CusolverApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void* h = nullptr;
+  for (const char* name : {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return nullptr;
+  api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cusolverDnCreate"));
+  api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cusolverDnDestroy"));
+  api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cusolverDnSetStream"));
+  api.syevdx_bufsize = reinterpret_cast<decltype(api.syevdx_bufsize)>(dlsym(h, "cusolverDnDsyevdx_bufferSize"));
+  api.syevdx = reinterpret_cast<decltype(api.syevdx)>(dlsym(h, "cusolverDnDsyevdx"));
+  api.ok = api.create && api.destroy && api.set_stream && api.syevdx_bufsize && api.syevdx;
+  return api.ok ? &api : nullptr;
+}
+}  // namespace
+
 // Exact --pca: top-k eigenpairs of the finished GRM (CalcPca non-approx branch,
 // plink2_matrix_calc.cc:5942-6040, which calls LAPACK dsyevr through ExtractEigvecs,
 // plink2_matrix.cc:1089-1104).  The dense symmetric eigensolver is a library call here as well
@@ -252,6 +285,11 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
     set_error("pl2gpu_grm_eigen_topk: exact PCA is limited to 46340 samples; use --pca approx");
     return 1;
   }
+  CusolverApi* cs = LoadCusolver();
+  if (!cs) {
+    set_error("pl2gpu_grm_eigen_topk: libcusolver.so.11 could not be loaded (%s)", dlerror());
+    return 1;
+  }
   Ctx* c = &job->ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
   double* d_a = nullptr;
@@ -269,13 +307,13 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
     if (cudaMemsetAsync(d_a, 0, static_cast<uint64_t>(n) * n * 8, c->stream) != cudaSuccess) break;
     // row-major lower triangle == column-major upper triangle
     if (pl2gpu_grm_get_rows(job, 0, n, d_a, nullptr, n, 1)) break;
-    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS || cusolverDnSetStream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
+    if (cs->create(&h) != CUSOLVER_STATUS_SUCCESS || cs->set_stream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
       set_error("pl2gpu_grm_eigen_topk: cusolverDnCreate failed");
       break;
     }
     int lwork = 0, meig = 0;
     const int il = static_cast<int>(n - pc_ct + 1), iu = static_cast<int>(n);
-    if (cusolverDnDsyevdx_bufferSize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+    if (cs->syevdx_bufsize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, &lwork) != CUSOLVER_STATUS_SUCCESS) {
       set_error("pl2gpu_grm_eigen_topk: syevdx workspace query failed");
       break;
     }
@@ -284,7 +322,7 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
       set_error("pl2gpu_grm_eigen_topk: insufficient device memory for the eigensolver workspace");
       break;
     }
-    const cusolverStatus_t st = cusolverDnDsyevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, d_work, lwork, d_info);
+    const cusolverStatus_t st = cs->syevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, d_work, lwork, d_info);
     c->launches++;
     int info = 0;
     if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
@@ -312,7 +350,7 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
     }
     rc = 0;
   } while (0);
-  if (h) cusolverDnDestroy(h);
+  if (h) cs->destroy(h);
   cudaFree(d_a);
   cudaFree(d_w);
   cudaFree(d_work);

@@ -8,11 +8,10 @@
 
 namespace pl2host {
 
-namespace {
 
 // .eigenvec / .eigenval writers (plink2_matrix_calc.cc:6237-6290): "#[FID\t]IID[\tSID]\tPC1..PCk",
 // one line per sample; eigenvalues one per line, both through dtoa_g.
-bool WriteEigen(const std::string& out_prefix, const SampleInfo& S, uint32_t pc_ct, const double* eigvals, const double* eigvecs /* [pc][sample] */) {
+bool WriteEigen(const std::string& out_prefix, const SampleInfo& S, uint32_t pc_ct, const double* eigvals, const double* eigvecs) {
   const uint32_t n = S.size();
   OutFile fv, fe;
   if (!fv.Open(out_prefix + ".eigenvec") || !fe.Open(out_prefix + ".eigenval")) return false;
@@ -47,33 +46,5 @@ bool WriteEigen(const std::string& out_prefix, const SampleInfo& S, uint32_t pc_
   return fv.Close() && fe.Close();
 }
 
-}  // namespace
-
-int RunPca(const std::string& out_prefix, uint32_t pc_ct, bool approx, bool seed_given, uint64_t seed, uint32_t threads, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
-  (void)seed_given;
-  (void)seed;
-  (void)threads;
-  (void)ctx;
-  const uint32_t n = ds->samples.size();
-  if (approx) {
-    fprintf(stderr, "Error: \"--pca approx\" is not available in this build yet (exact --pca is).\n");
-    return 63;
-  }
-  if (pc_ct > n) pc_ct = n;  // the reference reduces the PC count with a warning (:5655-5661)
-  std::vector<double> eigvals(pc_ct), eigvecs(static_cast<uint64_t>(pc_ct) * n);
-  printf("Extracting eigenvalue%s and eigenvector%s... ", pc_ct == 1 ? "" : "s", pc_ct == 1 ? "" : "s");
-  fflush(stdout);
-  if (pl2gpu_grm_eigen_topk(grm_job, pc_ct, eigvals.data(), eigvecs.data())) {
-    printf("\nError: %s\n", pl2gpu_last_error());
-    return 16;
-  }
-  printf("done.\n");
-  if (!WriteEigen(out_prefix, ds->samples, pc_ct, eigvals.data(), eigvecs.data())) {
-    printf("Error: File write failure.\n");
-    return 5;
-  }
-  printf("--pca: Eigenvector%s written to %s.eigenvec , and eigenvalue%s written to %s.eigenval .\n", pc_ct == 1 ? "" : "s", out_prefix.c_str(), pc_ct == 1 ? "" : "s", out_prefix.c_str());
-  return 0;
-}
 
 }  // namespace pl2host

@@ -22,6 +22,7 @@
 #include "../../../include/plink2_b200.h"
 #include "dataset.h"
 #include "pca.h"
+#include "sfmt.h"
 #include "text_util.h"
 
 using namespace pl2host;
@@ -1031,6 +1032,90 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ PCA
+int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  uint32_t pc_ct = c.pc_ct;
+  if (pc_ct > n) {
+    logprintf("Warning: calculating %u PCs, since there are only %u samples.\n", n, n);
+    pc_ct = n;
+  }
+  std::vector<double> eigvals(pc_ct), eigvecs(static_cast<uint64_t>(pc_ct) * n);
+  if (!c.pca_approx) {
+    // exact: top eigenpairs of the GRM already accumulated on the device (CalcPca :5942-6040)
+    logprintf("Extracting eigenvalue%s and eigenvector%s... ", pc_ct == 1 ? "" : "s", pc_ct == 1 ? "" : "s");
+    if (pl2gpu_grm_eigen_topk(grm_job, pc_ct, eigvals.data(), eigvecs.data())) {
+      logprintf("\n");
+      return GpuFail("pl2gpu_grm_eigen_topk");
+    }
+    logprintf("done.\n");
+  } else {
+    // approx (:5697-5941)
+    if (n <= 5000) logprintf("Warning: \"--pca approx\" is only recommended for analysis of >5000 samples.\n");
+    std::vector<uint32_t> vidx;
+    for (uint32_t v = 0; v < ds->variants.size(); ++v)
+      if (KeptForRelationship(ds->variants.chr_code[v])) vidx.push_back(v);
+    const uint64_t q = 2ull * pc_ct * (pc_ct + 1);
+    if (q > vidx.size()) {
+      logprintf("Error: Too few variants to compute %u PCs with \"--pca approx\" (%llu required).\n", pc_ct, static_cast<unsigned long long>(q));
+      return kRetDegenerateData;
+    }
+    std::vector<double> ref_freqs;
+    int rc = 0;
+    const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
+    if (rc) return rc;
+    Pl2PcaJob* job = nullptr;
+    rc = pl2gpu_pca_begin(ctx, n, static_cast<uint32_t>(vidx.size()), pc_ct, &job);
+    if (rc) {
+      logprintf("Error: %s\n", pl2gpu_last_error());
+      return rc == 2 ? kRetDegenerateData : kRetGpuFail;
+    }
+    BlockStreamer bs(ds, &vidx, n, 32768);
+    if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+    std::string err;
+    size_t base = 0;
+    for (;;) {
+      const int got = bs.Next(&err);
+      if (got < 0) {
+        logprintf("Error: %s\n", err.c_str());
+        pl2gpu_pca_end(job);
+        return kRetMalformedInput;
+      }
+      if (!got) break;
+      const int arc = pl2gpu_pca_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, have_freqs ? ref_freqs.data() + base : nullptr);
+      if (arc) {
+        logprintf("Error: %s\n", pl2gpu_last_error());
+        pl2gpu_pca_end(job);
+        return arc == 2 ? kRetDegenerateData : kRetGpuFail;
+      }
+      base += static_cast<size_t>(got);
+    }
+    // Gaussian start: the reference's main SFMT stream (seeded by --seed, else by time) sliced over
+    // min(--threads, ceil(N*k / 262144)) Box-Muller streams (FillGaussianDArr, plink2_random.cc:89)
+    Sfmt19937 rng;
+    const uint32_t seed = c.seed_given ? static_cast<uint32_t>(c.seed) : static_cast<uint32_t>(time(nullptr));
+    if (!c.seed_given) logprintf("Random number seed: %u\n", seed);
+    rng.InitGenRand(seed);
+    std::vector<double> g1(static_cast<uint64_t>(n) * 2 * pc_ct);
+    FillGaussian(static_cast<uint64_t>(n) * pc_ct, c.threads ? c.threads : 1, &rng, g1.data());
+    logprintf("Projecting random vectors, computing SVD of Krylov matrix, recovering top PCs... ");
+    if (pl2gpu_pca_run(job, g1.data(), eigvals.data(), eigvecs.data())) {
+      logprintf("\nError: %s\n", pl2gpu_last_error());
+      pl2gpu_pca_end(job);
+      return kRetGpuFail;
+    }
+    logprintf("done.\n");
+    pl2gpu_pca_end(job);
+  }
+  if (!WriteEigen(c.out, S, pc_ct, eigvals.data(), eigvecs.data())) {
+    logprintf("Error: File write failure.\n");
+    return kRetWriteFail;
+  }
+  logprintf("--pca: Eigenvector%s written to %s.eigenvec , and eigenvalue%s written to %s.eigenval .\n", pc_ct == 1 ? "" : "s", c.out.c_str(), pc_ct == 1 ? "" : "s", c.out.c_str());
+  return 0;
+}
+
 // --------------------------------------------------------------------------------------- LD prune
 int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
@@ -1134,6 +1219,29 @@ int DebugHooks(int argc, char** argv) {
     fclose(in);
     return out.Close() ? 0 : kRetWriteFail;
   }
+  if (argc == 5 && !strcmp(argv[1], "--debug-sfmt")) {  // <seed> <count> <out: raw uint32>
+    Sfmt19937 rng;
+    rng.InitGenRand(static_cast<uint32_t>(strtoul(argv[2], nullptr, 10)));
+    OutFile out;
+    if (!out.Open(argv[4])) return kRetOpenFail;
+    const unsigned long cnt = strtoul(argv[3], nullptr, 10);
+    for (unsigned long k = 0; k < cnt; ++k) {
+      const uint32_t v = rng.GenRandU32();
+      out.Write(&v, 4);
+    }
+    return out.Close() ? 0 : kRetWriteFail;
+  }
+  if (argc == 6 && !strcmp(argv[1], "--debug-gauss")) {  // <seed> <pairs> <threads> <out: raw doubles>
+    Sfmt19937 rng;
+    rng.InitGenRand(static_cast<uint32_t>(strtoul(argv[2], nullptr, 10)));
+    const uint64_t pairs = strtoull(argv[3], nullptr, 10);
+    std::vector<double> g(2 * pairs);
+    FillGaussian(pairs, static_cast<uint32_t>(strtoul(argv[4], nullptr, 10)), &rng, g.data());
+    OutFile out;
+    if (!out.Open(argv[5])) return kRetOpenFail;
+    out.Write(g.data(), g.size() * 8);
+    return out.Close() ? 0 : kRetWriteFail;
+  }
   if (argc == 6 && !strcmp(argv[1], "--debug-dump-geno")) {
     Dataset ds;
     std::string err;
@@ -1220,7 +1328,7 @@ int main(int argc, char** argv) {
     if (rc) return rc;
   }
   if (c.pca) {
-    rc = RunPca(c.out, c.pc_ct, c.pca_approx, c.seed_given, c.seed, c.threads, &ds, ctx, grm_job);
+    rc = RunPca(c, &ds, ctx, grm_job);
     if (grm_job) pl2gpu_grm_end(grm_job);
     if (rc) return rc;
   }

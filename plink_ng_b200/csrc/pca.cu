@@ -1,0 +1,284 @@
+// pca.cu - `--pca approx` job (CalcPca approx branch, 2.0/plink2_matrix_calc.cc:5697-5941): the
+// EIGENSOFT-style randomized range finder (Halko et al. 2011; Galinsky et al. 2016) on the resident
+// 2-bit genotype matrix.  Gaussian start matrix is supplied by the caller (the host program
+// reproduces the reference's SFMT / Box-Muller stream, host/sfmt.cc).
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include <cusolverDn.h>
+
+#include "../../include/plink2_b200.h"
+#include "common.cuh"
+#include "ld_kernels.cuh"    // geno_counts_kernel
+#include "pca_kernels.cuh"
+
+using namespace pl2;
+
+namespace {
+constexpr double kSmallEpsilon = 1.0 / 17592186044416.0;
+
+struct GesvdApi {
+  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
+  cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
+  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
+  cusolverStatus_t (*gesvd_bufsize)(cusolverDnHandle_t, int, int, int*) = nullptr;
+  cusolverStatus_t (*gesvd)(cusolverDnHandle_t, signed char, signed char, int, int, double*, int, double*, double*, int, double*, int, double*, int, double*, int*) = nullptr;
+  bool ok = false;
+};
+GesvdApi* LoadGesvd() {
+  static GesvdApi api;
+  static bool tried = false;
+  if (tried) return api.ok ? &api : nullptr;
+  tried = true;
+  void* h = nullptr;
+  for (const char* name : {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"}) {
+    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if (h) break;
+  }
+  if (!h) return nullptr;
+  api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cusolverDnCreate"));
+  api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cusolverDnDestroy"));
+  api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cusolverDnSetStream"));
+  api.gesvd_bufsize = reinterpret_cast<decltype(api.gesvd_bufsize)>(dlsym(h, "cusolverDnDgesvd_bufferSize"));
+  api.gesvd = reinterpret_cast<decltype(api.gesvd)>(dlsym(h, "cusolverDnDgesvd"));
+  api.ok = api.create && api.destroy && api.set_stream && api.gesvd_bufsize && api.gesvd;
+  return api.ok ? &api : nullptr;
+}
+}  // namespace
+
+struct Pl2PcaJob {
+  Pl2GpuCtx* ctx = nullptr;
+  uint32_t sample_ct = 0, sample_ct_padded = 0, pitch = 0;
+  uint32_t variant_cap = 0, variant_ct = 0, pc_ct = 0;
+  uint8_t* d_raw = nullptr;
+  double* d_ztab = nullptr;
+  uint32_t* d_counts = nullptr;
+  std::vector<double> h_ztab;
+  std::vector<uint32_t> h_counts;
+};
+
+extern "C" {
+
+int pl2gpu_pca_end(Pl2PcaJob* job);
+
+int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, Pl2PcaJob** job_ptr) {
+  *job_ptr = nullptr;
+  if (!ctx || !sample_ct || !variant_ct_total || !pc_ct) {
+    set_error("pl2gpu_pca_begin: bad arguments");
+    return 1;
+  }
+  const uint64_t q = 2ull * pc_ct * (pc_ct + 1);
+  if (q > variant_ct_total) {  // :5716-5719
+    set_error("Too few variants to compute %u PCs with \"--pca approx\" (%llu required).", pc_ct, static_cast<unsigned long long>(q));
+    return 2;
+  }
+  if (q > sample_ct) {
+    set_error("pl2gpu_pca_begin: \"--pca approx\" with %u PCs needs at least %llu samples in this implementation (tall thin SVD)", pc_ct, static_cast<unsigned long long>(q));
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  Pl2PcaJob* job = new Pl2PcaJob();
+  job->ctx = ctx;
+  job->sample_ct = sample_ct;
+  job->sample_ct_padded = RoundUpU32(sample_ct, 128);
+  job->pitch = job->sample_ct_padded / 4;
+  job->variant_cap = RoundUpU32(variant_ct_total, 128);
+  job->pc_ct = pc_ct;
+  if (cudaMalloc(&job->d_raw, static_cast<uint64_t>(job->variant_cap) * job->pitch) != cudaSuccess || cudaMalloc(&job->d_ztab, static_cast<uint64_t>(job->variant_cap) * 32) != cudaSuccess ||
+      cudaMalloc(&job->d_counts, 16ull * 65536) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_pca_begin: insufficient device memory to keep %u x %u genotypes resident", variant_ct_total, sample_ct);
+    pl2gpu_pca_end(job);
+    return 1;
+  }
+  *job_ptr = job;
+  return 0;
+}
+
+int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs) {
+  if (!job || job->variant_ct + static_cast<uint64_t>(variant_ct) > job->variant_cap) {
+    set_error("pl2gpu_pca_add_variants: more variants than announced at pl2gpu_pca_begin");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  for (uint32_t done = 0; done < variant_ct;) {
+    const uint32_t cur = std::min<uint32_t>(65536, variant_ct - done);
+    uint8_t* dst = job->d_raw + static_cast<uint64_t>(job->variant_ct) * job->pitch;
+    PL2_CUDA_OK(cudaMemcpy2DAsync(dst, job->pitch, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, DivUpU32(job->sample_ct, 4), cur, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->stream));
+    PL2_TRY(LaunchPadGenotypes(c, dst, job->pitch, job->sample_ct, cur, cur));
+    geno_counts_kernel<<<DivUpU32(cur, 8), 256, 0, c->stream>>>(dst, job->pitch, job->sample_ct, job->sample_ct_padded, cur, job->d_counts);
+    c->launches++;
+    job->h_counts.resize(4ull * cur);
+    PL2_CUDA_OK(cudaMemcpyAsync(job->h_counts.data(), job->d_counts, 16ull * cur, cudaMemcpyDeviceToHost, c->stream));
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    job->h_ztab.assign(4ull * cur, 0.0);
+    for (uint32_t v = 0; v < cur; ++v) {
+      const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2];
+      double ref_freq;
+      if (ref_freqs) {
+        ref_freq = ref_freqs[done + v];
+      } else {
+        const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);
+        ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
+      }
+      const double alt_freq = 1.0 - ref_freq;
+      const double variance = 2 * ref_freq * alt_freq;
+      if (!(variance > kSmallEpsilon)) {
+        bool bad = n1 != 0;
+        if (variance != variance) bad = bad || n0 || n2;
+        else if (ref_freq > 0.5) bad = bad || n2;
+        else bad = bad || n0;
+        if (bad) {
+          set_error("pl2gpu_pca_add_variants: variant %u has zero-variance allele frequency %g but non-monomorphic genotypes (kPglRetDegenerateData)", job->variant_ct + v, ref_freq);
+          return 2;
+        }
+        continue;
+      }
+      const double inv_stdev = 1.0 / sqrt(variance);
+      const double intercept = -2 * alt_freq * inv_stdev;
+      double* z = &job->h_ztab[4ull * v];
+      z[0] = intercept;
+      z[1] = intercept + inv_stdev;
+      z[2] = intercept + 2 * inv_stdev;
+    }
+    PL2_CUDA_OK(cudaMemcpyAsync(job->d_ztab + 4ull * job->variant_ct, job->h_ztab.data(), 32ull * cur, cudaMemcpyHostToDevice, c->stream));
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    job->variant_ct += cur;
+    done += cur;
+  }
+  return 0;
+}
+
+int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, double* eigvecs_host) {
+  if (!job || !g1_host) {
+    set_error("pl2gpu_pca_run: bad arguments");
+    return 1;
+  }
+  GesvdApi* cs = LoadGesvd();
+  if (!cs) {
+    set_error("pl2gpu_pca_run: libcusolver.so.11 could not be loaded");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint32_t n = job->sample_ct, npad = job->sample_ct_padded, m = job->variant_ct, k = job->pc_ct;
+  const uint32_t c2 = 2 * k;
+  const uint64_t q = static_cast<uint64_t>(c2) * (k + 1);
+  if (q > m || q > n) {
+    set_error("pl2gpu_pca_run: need 2k(k+1) = %llu <= min(variants %u, samples %u)", static_cast<unsigned long long>(q), m, n);
+    return 1;
+  }
+  double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr, *d_s = nullptr, *d_work = nullptr;
+  int* d_info = nullptr;
+  cusolverDnHandle_t h = nullptr;
+  int rc = 1;
+  const double m_recip = 1.0 / static_cast<double>(m);
+  auto launch_xa = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
+    for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
+      const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
+      pca_xa_kernel<<<DivUpU32(m, 128), 32 * (cols / 4), 128 * cols * 8, c->stream>>>(job->d_raw, job->pitch, npad, m, job->d_ztab, g + cc, g_ld, 0, cols, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0);
+      c->launches++;
+    }
+  };
+  auto launch_xtb = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
+    for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
+      const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
+      pca_xtb_kernel<<<DivUpU32(n, 128), 32 * (cols / 4), (128 * cols + 512) * 8, c->stream>>>(job->d_raw, job->pitch, n, m, job->d_ztab, hin + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0, 0, cols, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
+      c->launches++;
+    }
+  };
+  do {
+    if (cudaMalloc(&d_qq, static_cast<uint64_t>(m) * q * 8) != cudaSuccess || cudaMalloc(&d_u, static_cast<uint64_t>(std::max(m, n)) * q * 8) != cudaSuccess || cudaMalloc(&d_g1, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess ||
+        cudaMalloc(&d_g2, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess || cudaMalloc(&d_b, static_cast<uint64_t>(n) * q * 8) != cudaSuccess || cudaMalloc(&d_s, q * 8) != cudaSuccess || cudaMalloc(&d_info, 4) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_pca_run: insufficient device memory for the %u x %llu Krylov matrix", m, static_cast<unsigned long long>(q));
+      break;
+    }
+    if (cudaMemsetAsync(d_g1, 0, static_cast<uint64_t>(npad) * c2 * 8, c->stream) != cudaSuccess || cudaMemcpyAsync(d_g1, g1_host, static_cast<uint64_t>(n) * c2 * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+    // k+1 projections; every H_t = Y G_t is kept side by side in qq (column-major M x q)   :5783-5855
+    for (uint32_t iter = 0; iter <= k; ++iter) {
+      launch_xa(d_g1, c2, d_qq, m, iter * c2, c2);
+      if (iter < k) {
+        if (cudaMemsetAsync(d_g2, 0, static_cast<uint64_t>(npad) * c2 * 8, c->stream) != cudaSuccess) break;
+        launch_xtb(d_qq, m, iter * c2, c2, d_g2, c2, 1);
+        scale_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(npad) * c2, 256)), 256, 0, c->stream>>>(d_g2, static_cast<uint64_t>(npad) * c2, m_recip);
+        c->launches++;
+        std::swap(d_g1, d_g2);
+      }
+    }
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("pl2gpu_pca_run: kernel launch failed");
+      break;
+    }
+    if (cs->create(&h) != CUSOLVER_STATUS_SUCCESS || cs->set_stream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
+      set_error("pl2gpu_pca_run: cusolverDnCreate failed");
+      break;
+    }
+    int lwork_a = 0, lwork_b = 0;
+    if (cs->gesvd_bufsize(h, static_cast<int>(m), static_cast<int>(q), &lwork_a) != CUSOLVER_STATUS_SUCCESS || cs->gesvd_bufsize(h, static_cast<int>(n), static_cast<int>(q), &lwork_b) != CUSOLVER_STATUS_SUCCESS) {
+      set_error("pl2gpu_pca_run: gesvd workspace query failed");
+      break;
+    }
+    const int lwork = std::max(lwork_a, lwork_b);
+    if (cudaMalloc(&d_work, static_cast<uint64_t>(lwork) * 8) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_pca_run: insufficient device memory for the SVD workspace");
+      break;
+    }
+    // SVD of the Krylov matrix: left singular vectors = orthonormal basis Q of its range   :5860
+    cusolverStatus_t st = cs->gesvd(h, 'S', 'N', static_cast<int>(m), static_cast<int>(q), d_qq, static_cast<int>(m), d_s, d_u, static_cast<int>(m), nullptr, static_cast<int>(q), d_work, lwork, nullptr, d_info);
+    int info = 0;
+    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || st != CUSOLVER_STATUS_SUCCESS || info) {
+      set_error("Failed to compute SVD of Krylov matrix (cusolver status %d, info=%d).", static_cast<int>(st), info);
+      break;
+    }
+    // B = Y^T Q (N x q, column-major)   :5870-5916
+    if (cudaMemsetAsync(d_b, 0, static_cast<uint64_t>(n) * q * 8, c->stream) != cudaSuccess) break;
+    launch_xtb(d_u, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
+    // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B
+    st = cs->gesvd(h, 'S', 'N', static_cast<int>(n), static_cast<int>(q), d_b, static_cast<int>(n), d_s, d_u, static_cast<int>(n), nullptr, static_cast<int>(q), d_work, lwork, nullptr, d_info);
+    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || st != CUSOLVER_STATUS_SUCCESS || info) {
+      set_error("Failed to compute SVD of final matrix (cusolver status %d, info=%d).", static_cast<int>(st), info);
+      break;
+    }
+    std::vector<double> s(k);
+    if (cudaMemcpy(s.data(), d_s, 8ull * k, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("pl2gpu_pca_run: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    for (uint32_t p = 0; p < k; ++p) eigvals_host[p] = s[p] * s[p] * m_recip;  // :5931
+    rc = 0;
+  } while (0);
+  if (h) cs->destroy(h);
+  cudaFree(d_qq);
+  cudaFree(d_u);
+  cudaFree(d_g1);
+  cudaFree(d_g2);
+  cudaFree(d_b);
+  cudaFree(d_s);
+  cudaFree(d_work);
+  cudaFree(d_info);
+  return rc;
+}
+
+int pl2gpu_pca_end(Pl2PcaJob* job) {
+  if (!job) return 0;
+  if (job->ctx) {
+    cudaSetDevice(job->ctx->c.device);
+    cudaStreamSynchronize(job->ctx->c.stream);
+  }
+  cudaFree(job->d_raw);
+  cudaFree(job->d_ztab);
+  cudaFree(job->d_counts);
+  cudaGetLastError();
+  delete job;
+  return 0;
+}
+
+}  // extern "C"

@@ -109,6 +109,14 @@ int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t
   return 0;
 }
 
+int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded) {
+  if (!variant_ct_padded) return 0;
+  pad_genotypes_kernel<<<variant_ct_padded, 128, 0, ctx->stream>>>(dst, pitch, sample_ct, variant_ct, variant_ct_padded);
+  ctx->launches++;
+  PL2_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 void StageFree(GenoStage* gs) {
   cudaFree(gs->d_raw);
   gs->d_raw = nullptr;

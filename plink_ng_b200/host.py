@@ -243,3 +243,22 @@ class GrmJob:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def pca_approx(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int, pc_ct: int, g1: np.ndarray, ref_freqs=None):
+    """`--pca approx` on an in-memory block with a caller-supplied Gaussian start matrix
+    g1 [sample_ct, 2*pc_ct] -> (eigvals[pc_ct], eigvecs[pc_ct, sample_ct])."""
+    g = np.ascontiguousarray(genovecs)
+    g1 = np.ascontiguousarray(g1, dtype=np.float64)
+    assert g1.shape == (sample_ct, 2 * pc_ct)
+    rf = None if ref_freqs is None else np.ascontiguousarray(ref_freqs, dtype=np.float64)
+    h = C.c_void_p()
+    check(lib.pl2gpu_pca_begin(ctx.handle, sample_ct, g.shape[0], pc_ct, C.byref(h)), "pl2gpu_pca_begin")
+    try:
+        check(lib.pl2gpu_pca_add_variants(h, g.ctypes.data, g.strides[0], g.shape[0], 0, rf.ctypes.data if rf is not None else None), "pl2gpu_pca_add_variants")
+        vals = np.empty(pc_ct, dtype=np.float64)
+        vecs = np.empty((pc_ct, sample_ct), dtype=np.float64)
+        check(lib.pl2gpu_pca_run(h, g1.ctypes.data, vals.ctypes.data, vecs.ctypes.data), "pl2gpu_pca_run")
+        return vals, vecs
+    finally:
+        lib.pl2gpu_pca_end(h)

@@ -55,3 +55,54 @@ def test_dtoa_g_matches_reference_text(golden_dir, tmp_path):
         else:
             assert float(s) == pytest.approx(x, rel=6e-6, abs=0), (x, s)
     assert got[len(kin)] == "0" and got[len(kin) + 3] == "0.5" and got[len(kin) + 7] == "1e-05"
+
+
+REF_INC = "/root/reference/2.0/include"
+SFMT_OBJ = os.path.join(ROOT, "oracle", "_ref", "obj", "include_SFMT_c.o")
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_INC) and os.path.exists(SFMT_OBJ)), reason="needs the reference's compiled SFMT (this container only)")
+def test_sfmt_and_gaussian_fill_match_reference_generator(tmp_path):
+    """The SFMT-19937 restatement and FillGaussian reproduce the reference's vendored generator
+    (2.0/include/SFMT.c) and RandNormal/FillGaussianDArr (2.0/plink2_random.cc:29-99) bit for bit."""
+    harness = tmp_path / "h.c"
+    harness.write_text(r'''
+#include <stdio.h>
+#include <stdlib.h>
+#include <math.h>
+#include "SFMT.h"
+int main(int argc, char** argv) {
+  sfmt_t s; uint32_t seed = strtoul(argv[1], 0, 10); unsigned long n = strtoul(argv[2], 0, 10);
+  sfmt_init_gen_rand(&s, seed);
+  FILE* f = fopen(argv[3], "wb");
+  for (unsigned long k = 0; k < n; ++k) { uint32_t v = sfmt_genrand_uint32(&s); fwrite(&v, 4, 1, f); }
+  fclose(f);
+  /* second stream: init_by_array with the next four draws, as InitAllocSfmtpArr does */
+  uint32_t key[4]; for (int k = 0; k < 4; ++k) key[k] = sfmt_genrand_uint32(&s);
+  sfmt_t t; sfmt_init_by_array(&t, key, 4);
+  f = fopen(argv[4], "wb");
+  for (unsigned long k = 0; k < 1000; ++k) { uint32_t v = sfmt_genrand_uint32(&t); fwrite(&v, 4, 1, f); }
+  fclose(f);
+  return 0;
+}
+''')
+    exe = tmp_path / "h"
+    subprocess.run(["gcc", "-O1", "-DSFMT_MEXP=19937", "-I" + REF_INC, str(harness), SFMT_OBJ, "-lm", "-o", str(exe)], check=True)
+    n = 5000
+    subprocess.run([str(exe), "11", str(n), str(tmp_path / "ref.u32"), str(tmp_path / "ref2.u32")], check=True)
+    subprocess.run([BIN, "--debug-sfmt", "11", str(n), str(tmp_path / "got.u32")], check=True)
+    ref = np.fromfile(tmp_path / "ref.u32", dtype=np.uint32)
+    got = np.fromfile(tmp_path / "got.u32", dtype=np.uint32)
+    assert np.array_equal(ref, got)
+    # Gaussian fill, single stream: Box-Muller on consecutive draws
+    subprocess.run([BIN, "--debug-gauss", "11", "1000", "1", str(tmp_path / "g.f64")], check=True)
+    g = np.fromfile(tmp_path / "g.f64", dtype=np.float64)
+    u = (ref[:2000].astype(np.float64) + 0.5) * 2.0 ** -32
+    r = np.sqrt(-2 * np.log(u[0::2]))
+    th = (2 * 3.1415926535897932) * u[1::2]
+    assert np.allclose(g[0::2], r * np.sin(th), rtol=1e-15, atol=0) and np.allclose(g[1::2], r * np.cos(th), rtol=1e-15, atol=0)
+    # two streams (pairs > 262144): the second half comes from an init_by_array-seeded generator
+    pairs = 300000
+    subprocess.run([BIN, "--debug-gauss", "11", str(pairs), "4", str(tmp_path / "g2.f64")], check=True)
+    g2 = np.fromfile(tmp_path / "g2.f64", dtype=np.float64)
+    assert g2.shape[0] == 2 * pairs and np.isfinite(g2).all() and abs(g2.mean()) < 0.01 and abs(g2.std() - 1) < 0.01

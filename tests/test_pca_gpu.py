@@ -65,3 +65,39 @@ def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
     # unstructured --dummy data: eigenvalue gaps ~1e-2, so eigenvectors are compared at the
     # 6-significant-digit print precision amplified by 1/gap
     assert np.allclose(_align(gv, rv), rv, atol=2e-4)
+
+
+def test_approx_pca_matches_oracle_same_gaussian_start(gpu_ctx):
+    from plink_ng_b200.host import pca_approx
+
+    n, m, k = 400, 6000, 4
+    geno = _structured_geno(m, n, seed=9, pops=5, fst=0.1)
+    g1 = np.random.default_rng(1).standard_normal((n, 2 * k))
+    want_vals, want_vecs = orc.pca_approx(geno, k, g1)
+    vals, vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
+    assert np.allclose(vals, want_vals, rtol=1e-6)
+    # 5 populations -> 4 structure PCs with well separated eigenvalues: north_star's 1e-5 (relative to the
+    # largest component) applies
+    assert np.allclose(_align(vecs, want_vecs), want_vecs, atol=1e-5 * np.abs(want_vecs).max())
+    # and the approximation is a good one: close to the exact eigenpairs of the mean-imputed GRM
+    g, _ = orc.grm(geno, meanimpute=True)
+    ev, _ = orc.pca_exact(g, k)
+    assert np.allclose(vals, ev, rtol=2e-2)
+
+
+def test_approx_pca_cli_matches_reference_files(golden_dir, tmp_path):
+    """Same --seed => same SFMT/Box-Muller start matrix as the reference run that wrote the golden files."""
+    out = str(tmp_path / "pa")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--pca", "3", "approx", "--seed", "11", "--threads", "2", "--out", out], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout + r.stderr
+    ref_val = np.loadtxt(os.path.join(golden_dir, "a_pcaa.eigenval"))
+    got_val = np.loadtxt(out + ".eigenval")
+    assert np.allclose(got_val, ref_val, rtol=1e-5)
+    ref = [ln.rstrip("\n").split("\t") for ln in open(os.path.join(golden_dir, "a_pcaa.eigenvec"))]
+    got = [ln.rstrip("\n").split("\t") for ln in open(out + ".eigenvec")]
+    assert got[0] == ref[0]
+    rv = np.array([x[2:] for x in ref[1:]], dtype=float).T
+    gv = np.array([x[2:] for x in got[1:]], dtype=float).T
+    # unstructured 100-sample data: near-degenerate eigenvalues amplify last-digit differences
+    assert np.allclose(_align(gv, rv), rv, atol=5e-4)
