@@ -182,14 +182,14 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   auto launch_xa = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
     for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
       const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
-      pca_xa_kernel<<<DivUpU32(m, 128), 32 * (cols / 4), 128 * cols * 8, c->stream>>>(job->d_raw, job->pitch, npad, m, job->d_ztab, g + cc, g_ld, 0, cols, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0);
+      pca_xa_kernel<<<DivUpU32(m, 128), 32 * DivUpU32(cols, 4), (128 * cols + 4) * 8, c->stream>>>(job->d_raw, job->pitch, npad, m, job->d_ztab, g + cc, g_ld, 0, cols, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0);
       c->launches++;
     }
   };
   auto launch_xtb = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
     for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
       const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
-      pca_xtb_kernel<<<DivUpU32(n, 128), 32 * (cols / 4), (128 * cols + 512) * 8, c->stream>>>(job->d_raw, job->pitch, n, m, job->d_ztab, hin + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0, 0, cols, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
+      pca_xtb_kernel<<<DivUpU32(n, 128), 32 * DivUpU32(cols, 4), (128 * cols + 512) * 8, c->stream>>>(job->d_raw, job->pitch, n, m, job->d_ztab, hin + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0, 0, cols, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
       c->launches++;
     }
   };

@@ -16,7 +16,8 @@ namespace pl2 {
 constexpr uint32_t kPcaColsMax = 40;   // columns per launch (multiple of 4; 128 x 40 doubles of smem)
 
 // H (column-major, ld = h_ld) [v_global][c] for the variants of this batch.
-// grid.x = variant tiles of 128; block = 32 lanes x (C/4) warps; each thread 4 variants x 4 columns.
+// grid.x = variant tiles of 128; block = 32 lanes x ceil(C/4) warps; each thread 4 variants x 4 columns
+// (C even; a trailing half quad reads two slack doubles and is masked on store).
 static __global__ void pca_xa_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t sample_ct_padded, uint32_t variant_ct, const double* __restrict__ ztab /* [variant][4] */, const double* __restrict__ g /* row-major [sample][g_ld] */, uint32_t g_ld, uint32_t col0, uint32_t cols,
                                      double* __restrict__ h, uint64_t h_ld, uint64_t v_global0) {
   extern __shared__ __align__(16) double s_g[];  // [128 samples][cols]

@@ -70,13 +70,13 @@ def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
 def test_approx_pca_matches_oracle_same_gaussian_start(gpu_ctx):
     from plink_ng_b200.host import pca_approx
 
-    n, m, k = 400, 6000, 4
-    geno = _structured_geno(m, n, seed=9, pops=5, fst=0.1)
+    n, m, k = 400, 6000, 5  # 2k = 10 columns: exercises the half column quad
+    geno = _structured_geno(m, n, seed=9, pops=6, fst=0.1)
     g1 = np.random.default_rng(1).standard_normal((n, 2 * k))
     want_vals, want_vecs = orc.pca_approx(geno, k, g1)
     vals, vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
     assert np.allclose(vals, want_vals, rtol=1e-6)
-    # 5 populations -> 4 structure PCs with well separated eigenvalues: north_star's 1e-5 (relative to the
+    # 6 populations -> 5 structure PCs with well separated eigenvalues: north_star's 1e-5 (relative to the
     # largest component) applies
     assert np.allclose(_align(vecs, want_vecs), want_vecs, atol=1e-5 * np.abs(want_vecs).max())
     # and the approximation is a good one: close to the exact eigenpairs of the mean-imputed GRM
