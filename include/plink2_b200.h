@@ -73,7 +73,8 @@ typedef struct Pl2KingJob Pl2KingJob;
 enum {
   kPl2KingAlgoAuto = 0,
   kPl2KingAlgoPopcount = 1, /* bit-plane AND/XOR + __popc over smem tiles */
-  kPl2KingAlgoTensor = 2    /* exact int8 tcgen05 contraction over {0,+-1} indicator planes */
+  kPl2KingAlgoTensor = 2,   /* exact int8 tcgen05 contraction over {0,+-1} indicator planes (both operands via smem) */
+  kPl2KingAlgoTensorTS = 3  /* same contraction, row-side operand expanded straight into tensor memory */
 };
 
 /* Rows [row_start, row_end) of the strict lower triangle over sample_ct samples (row = larger

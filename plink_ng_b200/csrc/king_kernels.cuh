@@ -393,21 +393,21 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
 // pair order: for j in rows: for i in [0, j)  (:1545-1547).
 // One CTA per (tile, 16-row sub-block): coalesced tile reads -> smem -> row-contiguous writes.
 // ---------------------------------------------------------------------------------------------
-template <bool kKinship>
+template <bool kKinship, uint32_t kCols>
 __global__ void __launch_bounds__(256)
 king_finalize_kernel(const int32_t* __restrict__ raw_acc, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, uint32_t sample_ct, uint32_t out_row_start, uint32_t out_row_end, uint32_t* __restrict__ out_counts, double* __restrict__ out_kinship) {
-  __shared__ int32_t s_acc[16][kKingTileAccCols + 1];
+  __shared__ int32_t s_acc[16][(5 * kCols) + 1];
   const uint32_t tile = blockIdx.x >> 3;
   const uint32_t sub = blockIdx.x & 7;
   const uint32_t rt = tile_rt[tile];
   const uint32_t tc = tile_tc[tile];
   const uint32_t row_base = rt * kTileRows + sub * 16;
   if (row_base >= out_row_end || row_base + 16 <= out_row_start) return;
-  const uint32_t col_base = tc * kTileCols;
+  const uint32_t col_base = tc * kCols;
   if (col_base + 1 > row_base + 15) return;  // no strict-lower-triangle pair in this block
-  const int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kKingTileAccWords + sub * 16;
+  const int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * (5 * kCols * kTileRows) + sub * 16;
   const uint32_t r = threadIdx.x & 15;
-  for (uint32_t cidx = threadIdx.x >> 4; cidx < kKingTileAccCols; cidx += 16) {
+  for (uint32_t cidx = threadIdx.x >> 4; cidx < (5 * kCols); cidx += 16) {
     s_acc[r][cidx] = acc_tile[static_cast<uint64_t>(cidx) * kTileRows + r];
   }
   __syncthreads();
@@ -417,35 +417,35 @@ king_finalize_kernel(const int32_t* __restrict__ raw_acc, const uint32_t* __rest
     if (j < out_row_start || j >= out_row_end || j >= sample_ct) continue;
     const uint64_t pair_row = static_cast<uint64_t>(j) * (j - 1) / 2 - tri_base;  // j >= 1 whenever any i < j exists
     if (kKinship) {
-      for (uint32_t cl = threadIdx.x; cl < kTileCols; cl += 256) {
+      for (uint32_t cl = threadIdx.x; cl < kCols; cl += 256) {
         const uint32_t i = col_base + cl;
         if (i >= j) continue;
         const int32_t tt = s_acc[rr][cl];
-        const int32_t th = s_acc[rr][kTileCols + cl];
-        const int32_t ht = s_acc[rr][2 * kTileCols + cl];
-        const int32_t hh = s_acc[rr][3 * kTileCols + cl];
-        const int32_t ss = s_acc[rr][4 * kTileCols + cl];
+        const int32_t th = s_acc[rr][kCols + cl];
+        const int32_t ht = s_acc[rr][2 * kCols + cl];
+        const int32_t hh = s_acc[rr][3 * kCols + cl];
+        const int32_t ss = s_acc[rr][4 * kCols + cl];
         const int64_t ibs0 = (hh - ss) >> 1;
         const int64_t het2hom1 = th, het1hom2 = ht;
         const int64_t smaller_het = tt + (het1hom2 < het2hom1 ? het1hom2 : het2hom1);
         out_kinship[pair_row + i] = 0.5 - static_cast<double>(4 * ibs0 + het1hom2 + het2hom1) / static_cast<double>(4 * smaller_het);
       }
     } else {
-      for (uint32_t idx = threadIdx.x; idx < kTileCols * 5; idx += 256) {
+      for (uint32_t idx = threadIdx.x; idx < kCols * 5; idx += 256) {
         const uint32_t cl = idx / 5, q = idx % 5;
         const uint32_t i = col_base + cl;
         if (i >= j) continue;
         uint32_t val;
         if (q == 0) {
-          val = static_cast<uint32_t>((s_acc[rr][3 * kTileCols + cl] - s_acc[rr][4 * kTileCols + cl]) >> 1);  // IBS0
+          val = static_cast<uint32_t>((s_acc[rr][3 * kCols + cl] - s_acc[rr][4 * kCols + cl]) >> 1);  // IBS0
         } else if (q == 1) {
           val = static_cast<uint32_t>(s_acc[rr][cl]);  // HETHET = TT
         } else if (q == 2) {
-          val = static_cast<uint32_t>(s_acc[rr][kTileCols + cl]);  // HET2HOM1 = TH
+          val = static_cast<uint32_t>(s_acc[rr][kCols + cl]);  // HET2HOM1 = TH
         } else if (q == 3) {
-          val = static_cast<uint32_t>(s_acc[rr][2 * kTileCols + cl]);  // HET1HOM2 = HT
+          val = static_cast<uint32_t>(s_acc[rr][2 * kCols + cl]);  // HET1HOM2 = HT
         } else {
-          val = static_cast<uint32_t>(s_acc[rr][3 * kTileCols + cl]);  // HOMHOM = HH
+          val = static_cast<uint32_t>(s_acc[rr][3 * kCols + cl]);  // HOMHOM = HH
         }
         out_counts[(pair_row + i) * 5 + q] = val;
       }

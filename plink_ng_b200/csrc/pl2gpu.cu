@@ -7,6 +7,7 @@
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "king_kernels.cuh"
+#include "king_ts_kernel.cuh"
 #include "umma_probe.cuh"
 
 namespace pl2 {
@@ -153,6 +154,8 @@ struct Pl2KingJob {
   TileList tiles;
   GenoStage stage;
   uint32_t* d_planes = nullptr;  // popcount path only
+  uint8_t* d_raw_t = nullptr;    // TS path only: sample-major copy of the staged block
+  uint32_t tile_cols = kTileCols;
   int32_t* d_raw_acc = nullptr;
   void* d_out_stage = nullptr;   // bounded staging for host downloads
   uint64_t out_stage_bytes = 0;
@@ -196,6 +199,8 @@ int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr) {
   PL2_CUDA_OK(cudaStreamCreateWithFlags(&ctx->c.copy_stream, cudaStreamNonBlocking));
   PL2_CUDA_OK(cudaFuncSetAttribute(king_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   PL2_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
+  PL2_CUDA_OK(cudaFuncSetAttribute(umma_probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
+  PL2_CUDA_OK(cudaFuncSetAttribute(king_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTsSmemBytes));
   *ctx_ptr = ctx;
   return 0;
 }
@@ -291,7 +296,7 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     return 1;
   }
   if (algo == kPl2KingAlgoAuto) algo = kPl2KingAlgoTensor;
-  if (algo != kPl2KingAlgoPopcount && algo != kPl2KingAlgoTensor) {
+  if (algo != kPl2KingAlgoPopcount && algo != kPl2KingAlgoTensor && algo != kPl2KingAlgoTensorTS) {
     set_error("pl2gpu_king_begin: unknown algo %d", algo);
     return 1;
   }
@@ -306,9 +311,16 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     pl2gpu_king_end(job);
     return 1;
   };
-  if (BuildTileList(row_start, row_end, false, &job->tiles)) return fail();
-  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage)) return fail();
-  const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * kKingTileAccWords * sizeof(int32_t);
+  const bool ts = algo == kPl2KingAlgoTensorTS;
+  job->tile_cols = ts ? kTsCols : kTileCols;
+  if (BuildTileList(row_start, row_end, false, &job->tiles, job->tile_cols)) return fail();
+  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, ts ? kTsSamplePad : kSamplePad)) return fail();
+  if (ts && cudaMalloc(&job->d_raw_t, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_king_begin: insufficient device memory for the sample-major genotype copy");
+    return fail();
+  }
+  const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * (5ull * job->tile_cols * kTileRows) * sizeof(int32_t);
   if (cudaMalloc(&job->d_raw_acc, acc_bytes ? acc_bytes : 4) != cudaSuccess) {
     cudaGetLastError();
     set_error("pl2gpu_king_begin: insufficient device memory for %u pair tiles (%.1f GB of accumulators); narrow the row range", job->tiles.tile_ct, acc_bytes / 1e9);
@@ -364,6 +376,12 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
         split_transpose_kernel<<<static_cast<uint32_t>(DivUpU64(warps, 8)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->stage.sample_ct_padded, word_ct, job->d_planes);
         c->launches++;
         king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage.sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+        c->launches++;
+      } else if (job->algo == kPl2KingAlgoTensorTS) {
+        const uint32_t pitch_t = padded / 4;
+        geno_transpose_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->d_raw_t, pitch_t);
+        c->launches++;
+        king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->d_raw_t, pitch_t, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       } else {
         king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
@@ -421,10 +439,15 @@ static int KingGet(Pl2KingJob* job, uint32_t r0, uint32_t r1, void* dst, int dst
       const uint32_t tile_b = job->tiles.h_rowtile_offset[rt_b + 1];
       if (tile_b > tile_a) {
         const uint32_t grid = (tile_b - tile_a) * 8;
-        if (kinship) {
-          king_finalize_kernel<true><<<grid, 256, 0, c->stream>>>(job->d_raw_acc + static_cast<uint64_t>(tile_a) * kKingTileAccWords, job->tiles.d_tile_rt + tile_a, job->tiles.d_tile_tc + tile_a, job->sample_ct, cur0, cur1, nullptr, static_cast<double*>(d_dst));
+        const int32_t* acc0 = job->d_raw_acc + static_cast<uint64_t>(tile_a) * (5ull * job->tile_cols * kTileRows);
+        const uint32_t* trt = job->tiles.d_tile_rt + tile_a;
+        const uint32_t* ttc = job->tiles.d_tile_tc + tile_a;
+        if (job->tile_cols == kTsCols) {
+          if (kinship) king_finalize_kernel<true, kTsCols><<<grid, 256, 0, c->stream>>>(acc0, trt, ttc, job->sample_ct, cur0, cur1, nullptr, static_cast<double*>(d_dst));
+          else king_finalize_kernel<false, kTsCols><<<grid, 256, 0, c->stream>>>(acc0, trt, ttc, job->sample_ct, cur0, cur1, static_cast<uint32_t*>(d_dst), nullptr);
         } else {
-          king_finalize_kernel<false><<<grid, 256, 0, c->stream>>>(job->d_raw_acc + static_cast<uint64_t>(tile_a) * kKingTileAccWords, job->tiles.d_tile_rt + tile_a, job->tiles.d_tile_tc + tile_a, job->sample_ct, cur0, cur1, static_cast<uint32_t*>(d_dst), nullptr);
+          if (kinship) king_finalize_kernel<true, kTileCols><<<grid, 256, 0, c->stream>>>(acc0, trt, ttc, job->sample_ct, cur0, cur1, nullptr, static_cast<double*>(d_dst));
+          else king_finalize_kernel<false, kTileCols><<<grid, 256, 0, c->stream>>>(acc0, trt, ttc, job->sample_ct, cur0, cur1, static_cast<uint32_t*>(d_dst), nullptr);
         }
         c->launches++;
         PL2_CUDA_OK(cudaGetLastError());
@@ -462,6 +485,7 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   FreeTileList(&job->tiles);
   StageFree(&job->stage);
   cudaFree(job->d_planes);
+  cudaFree(job->d_raw_t);
   cudaFree(job->d_raw_acc);
   cudaFree(job->d_out_stage);
   cudaGetLastError();
@@ -552,6 +576,50 @@ int pl2gpu_selftest_umma(Pl2GpuCtx* ctx, int verbose) {
   if (bad) {
     set_error("pl2gpu_selftest_umma: %u of %u accumulator entries differ from the scalar reference", bad, M * N);
     return 1;
+  }
+  // TS form: same B image, A rows written to tensor memory with tcgen05.st (K-major, 4 K-bytes per column)
+  {
+    Ctx* c = &ctx->c;
+    std::vector<uint8_t> a_rows(M * K);
+    for (uint32_t m = 0; m < M; ++m)
+      for (uint32_t k = 0; k < K; ++k) a_rows[m * K + k] = static_cast<uint8_t>(av[m * K + k]);
+    UmmaProbeParams prm{};
+    prm.b_bytes = N * K;
+    prm.b_lbo = lbo_b;
+    prm.b_sbo = kCoreBytes;
+    prm.b_step_bytes = 4 * lbo_b;
+    prm.k_steps = K / 32;
+    prm.idesc = make_idesc_i8(M, N, false, true);
+    prm.n = N;
+    uint8_t *d_a = nullptr, *d_b = nullptr;
+    int32_t* d_d = nullptr;
+    PL2_CUDA_OK(cudaMalloc(&d_a, M * K));
+    PL2_CUDA_OK(cudaMalloc(&d_b, N * K));
+    PL2_CUDA_OK(cudaMalloc(&d_d, 128ull * N * 4));
+    PL2_CUDA_OK(cudaMemcpyAsync(d_a, a_rows.data(), M * K, cudaMemcpyHostToDevice, c->stream));
+    PL2_CUDA_OK(cudaMemcpyAsync(d_b, b.data(), N * K, cudaMemcpyHostToDevice, c->stream));
+    umma_probe_ts_kernel<<<1, 128, kProbeSmemBytes, c->stream>>>(d_a, d_b, prm, d_d);
+    c->launches++;
+    PL2_CUDA_OK(cudaGetLastError());
+    PL2_CUDA_OK(cudaMemcpyAsync(d.data(), d_d, 128ull * N * 4, cudaMemcpyDeviceToHost, c->stream));
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaFree(d_d);
+    bad = 0;
+    for (uint32_t m = 0; m < M; ++m)
+      for (uint32_t n = 0; n < N; ++n) {
+        int32_t ref = 0;
+        for (uint32_t k = 0; k < K; ++k) ref += static_cast<int32_t>(av[m * K + k]) * bv[n * K + k];
+        if (ref != d[m * N + n]) {
+          if (verbose && bad < 8) fprintf(stderr, "selftest_umma(TS) mismatch m=%u n=%u got=%d want=%d\n", m, n, d[m * N + n], ref);
+          ++bad;
+        }
+      }
+    if (bad) {
+      set_error("pl2gpu_selftest_umma: TS form: %u of %u accumulator entries differ from the scalar reference", bad, M * N);
+      return 3;
+    }
   }
   return 0;
 }

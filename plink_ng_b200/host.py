@@ -12,7 +12,7 @@ import numpy as np
 from . import capi
 from .capi import lib, check
 
-KING_ALGO_AUTO, KING_ALGO_POPCOUNT, KING_ALGO_TENSOR = 0, 1, 2
+KING_ALGO_AUTO, KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS = 0, 1, 2, 3
 
 
 def pack_genotypes(geno: np.ndarray) -> np.ndarray:

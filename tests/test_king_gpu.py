@@ -6,12 +6,12 @@ import numpy as np
 import pytest
 
 import plink_ng_b200 as p
-from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KingJob, pack_genotypes, parallel_bounds
+from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS, KingJob, pack_genotypes, parallel_bounds
 from oracle import plink_oracle as orc
 
 pytestmark = pytest.mark.gpu
 
-ALGOS = [pytest.param(KING_ALGO_POPCOUNT, id="popcount"), pytest.param(KING_ALGO_TENSOR, id="tensor")]
+ALGOS = [pytest.param(KING_ALGO_POPCOUNT, id="popcount"), pytest.param(KING_ALGO_TENSOR, id="tensor"), pytest.param(KING_ALGO_TENSOR_TS, id="tensor_ts")]
 
 
 def _random_geno(m, n, seed, miss=0.03):
@@ -66,11 +66,11 @@ def test_king_tensor_equals_popcount_medium(gpu_ctx):
     n, m = 1500, 20000
     gv = pack_genotypes(_random_geno(m, n, seed=3, miss=0.01))
     res = []
-    for algo in (KING_ALGO_POPCOUNT, KING_ALGO_TENSOR):
+    for algo in (KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS):
         with KingJob(gpu_ctx, n, 0, n, algo) as job:
             job.add_variants(gv)
             res.append(job.counts())
-    assert np.array_equal(res[0], res[1])
+    assert np.array_equal(res[0], res[1]) and np.array_equal(res[0], res[2])
     # size-independent property: every pair's five categories partition the jointly non-missing variants
     c = res[1].astype(np.int64)
     nsnp = c[:, 1] + c[:, 2] + c[:, 3] + c[:, 4]
