@@ -110,11 +110,12 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
 
   if (warp < 8) {
     // ---------------- producers ----------------
-    // thread = (variant k = tid % 64, role = tid / 64).  role 0: the 128 row-side samples (one
-    // 32-byte sector) -> planes g, m.  roles 1..3: the 80 col-side samples (20 bytes) -> digit planes
-    // {0..3}, {4..7}, {8,9,10} through the per-variant tables.
-    const uint32_t k = tid & 63;
-    const uint32_t role = tid >> 6;
+    // thread = (variant k = 8 * warp + lane % 8, role = lane / 8).  role 0: the 128 row-side samples
+    // (one 32-byte sector) -> planes g, m.  roles 1..3: the 80 col-side samples (20 bytes) -> digit
+    // planes {0..3}, {4..7}, {8,9,10} through the per-variant tables.  The three col-side roles of a
+    // variant sit in the same warp, so their identical genotype loads coalesce into one request.
+    const uint32_t k = 8 * warp + (lane & 7);
+    const uint32_t role = lane >> 3;
     const bool is_i = role == 0;
     const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + (is_i ? (i0 / 4) : (j0 / 4));
     const uint64_t stage_stride = static_cast<uint64_t>(kGrmKc) * pitch;

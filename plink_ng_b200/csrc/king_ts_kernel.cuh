@@ -28,8 +28,6 @@ constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1984: +64
 constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 15872
 constexpr uint32_t kTsSmemBytes = kTsStagesJ * kTsStageBytesJ + 1024;
 constexpr uint32_t kTsThreads = 288;
-constexpr uint32_t kTsLookaheadI = 8;          // k-steps of row-side words held in registers
-constexpr uint32_t kTsLookaheadJ = 3;          // stages of col-side words held in registers
 
 // ---- 2-bit matrix transpose: raw[variant][pitch] -> rawT[sample][pitch_t] (pitch_t = variants/4 bytes).
 // One CTA = 64 variants x 64 samples through a shared-memory byte tile.
@@ -70,7 +68,6 @@ king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* _
   const uint32_t i0 = tile_rt[tile] * kTileRows;
   const uint32_t j0 = tile_tc[tile] * kTsCols;
   const uint32_t stage_iters = variant_ct_padded / kTsKcJ;
-  const uint32_t kstep_ct = 2 * stage_iters;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
   if (tid == 0) {
@@ -91,103 +88,111 @@ king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* _
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp < 4) {
-    // ---------------- row-side producers: thread = TMEM lane = sample i0 + tid ----------------
-    const uint8_t* src = raw_t + static_cast<uint64_t>(i0 + tid) * pitch_t;
-    const uint32_t taddr_lane = tmem_base + ((32u * warp) << 16) + kTsAccCols;
-    auto load_ks = [&](uint32_t ks) -> uint2 { return (ks < kstep_ct) ? __ldg(reinterpret_cast<const uint2*>(src + 8ull * ks)) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu); };
-    uint2 pre[kTsLookaheadI];
-#pragma unroll
-    for (uint32_t d = 0; d < kTsLookaheadI; ++d) pre[d] = load_ks(d);
-    for (uint32_t ks0 = 0; ks0 < kstep_ct; ks0 += kTsLookaheadI) {
-#pragma unroll
-      for (uint32_t d = 0; d < kTsLookaheadI; ++d) {
-        const uint32_t ks = ks0 + d;
-        if (ks < kstep_ct) {
-          const uint2 cur = pre[d];
-          pre[d] = load_ks(ks + kTsLookaheadI);
-          const uint32_t slot = ks % kTsASlots;
-          const uint32_t ph = (ks / kTsASlots) & 1;
-          const Sel4 s0 = make_selectors(cur.x);
-          const Sel4 s1 = make_selectors(cur.y);
-          mbar_wait(&bar_empty_a[slot], ph ^ 1);
-          tc_fence_after_sync();
-          const uint32_t ta = taddr_lane + slot * kTsASlotCols;
-          {
-            const uint4 a = expand16(kTabHet, s0), b = expand16(kTabHet, s1);
-            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            tmem_st8(ta, v);
-          }
-          {
-            const uint4 a = expand16(kTabHom, s0), b = expand16(kTabHom, s1);
-            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            tmem_st8(ta + 8, v);
-          }
-          {
-            const uint4 a = expand16(kTabSgn, s0), b = expand16(kTabSgn, s1);
-            const uint32_t v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            tmem_st8(ta + 16, v);
-          }
-          tmem_st_wait();
-          tc_fence_before_sync();
-          mbar_arrive(&bar_full_a[slot]);
-        }
-      }
-    }
-  } else if (warp < 8) {
-    // ---------------- col-side producers: thread = (variant k of the stage, half of the 20-byte row) ----
-    const uint32_t t = tid - 128;
+  if (warp < 8) {
+    // ---------------- producers ----------------
+    // Two groups of four warps (group = warp / 4).  Group g expands the ROW side of k-steps ks = 2 it + g
+    // straight into tensor memory (thread = TMEM lane = sample i0 + 32 (warp % 4) + lane) and the COLUMN
+    // side of the shared-memory stages it with it % 2 == g (thread = variant k of the stage, half of its
+    // 20-byte row).  The tcgen05.st of one k-step is overlapped with the column-side work and with the
+    // expansion of the group's next k-step; tcgen05.wait::st + arrive come last.
+    const uint32_t grp = warp >> 2;
+    const uint32_t lq = warp & 3;
+    const uint32_t row = 32 * lq + lane;
+    const uint8_t* src_i = raw_t + static_cast<uint64_t>(i0 + row) * pitch_t;
+    const uint32_t taddr_lane = tmem_base + ((32u * lq) << 16) + kTsAccCols;
+    const uint32_t t = row;                        // 0..127 inside the group
     const uint32_t k = t & 63;
-    const uint32_t half = t >> 6;                 // 0: words 0..2, 1: words 3..4
+    const uint32_t half = t >> 6;                  // 0: words 0..2, 1: words 3..4
     const uint32_t w0 = half ? 3u : 0u;
     const uint32_t wn = half ? 2u : 3u;
-    const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + j0 / 4 + 4 * w0;
+    const uint8_t* src_j = raw + static_cast<uint64_t>(k) * pitch + j0 / 4 + 4 * w0;
     const uint64_t stage_stride = static_cast<uint64_t>(kTsKcJ) * pitch;
-    // K rows are stored in the PRMT position order of the row side (geno_expand.cuh): variant k of a
-    // 16-variant group sits at row SampleToPos(k % 16)
+    // K rows of the column side are stored in the PRMT position order of the row side
+    // (geno_expand.cuh): variant k of a 16-variant group sits at row SampleToPos(k % 16)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
     const uint32_t dst_k = (kpos >> 3) * kTsLboJ + (kpos & 7) * 16 + w0 * kCoreBytes;
-    struct Row {
+
+    auto load_i = [&](uint32_t it) -> uint2 {  // row-side words of k-step 2 it + grp
+      const uint32_t ks = 2 * it + grp;
+      return (it < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 8ull * ks)) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    };
+    struct RowJ {
       uint32_t w[3];
     };
-    auto load_row = [&](uint32_t it) -> Row {
-      Row r;
+    auto load_j = [&](uint32_t it) -> RowJ {  // column-side words of stage it
+      RowJ r;
       r.w[0] = r.w[1] = r.w[2] = 0xFFFFFFFFu;
       if (it < stage_iters) {
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src + it * stage_stride);
+        const uint32_t* p = reinterpret_cast<const uint32_t*>(src_j + it * stage_stride);
         r.w[0] = __ldg(p);
         r.w[1] = __ldg(p + 1);
         if (wn == 3) r.w[2] = __ldg(p + 2);
       }
       return r;
     };
-    Row pre[kTsLookaheadJ];
+    struct ExpI {
+      uint32_t v[3][8];
+    };
+    auto expand_i = [&](const uint2& w) -> ExpI {
+      ExpI e;
+      const Sel4 s0 = make_selectors(w.x), s1 = make_selectors(w.y);
+      const uint32_t tabs[3] = {kTabHet, kTabHom, kTabSgn};
 #pragma unroll
-    for (uint32_t d = 0; d < kTsLookaheadJ; ++d) pre[d] = load_row(d);
-    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTsLookaheadJ) {
+      for (int p = 0; p < 3; ++p) {
+        const uint4 a = expand16(tabs[p], s0), b = expand16(tabs[p], s1);
+        e.v[p][0] = a.x; e.v[p][1] = a.y; e.v[p][2] = a.z; e.v[p][3] = a.w;
+        e.v[p][4] = b.x; e.v[p][5] = b.y; e.v[p][6] = b.z; e.v[p][7] = b.w;
+      }
+      return e;
+    };
+
+    constexpr uint32_t kLa = 4;  // iterations of lookahead (row side: 4 k-steps of this group; column side: 2 stages)
+    uint2 pre_i[kLa];
+    RowJ pre_j[kLa / 2];
 #pragma unroll
-      for (uint32_t d = 0; d < kTsLookaheadJ; ++d) {
+    for (uint32_t d = 0; d < kLa; ++d) pre_i[d] = load_i(d);
+#pragma unroll
+    for (uint32_t d = 0; d < kLa / 2; ++d) pre_j[d] = load_j(2 * d + grp);
+    ExpI cur = expand_i(pre_i[0]);
+    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kLa) {
+#pragma unroll
+      for (uint32_t d = 0; d < kLa; ++d) {
         const uint32_t it = it0 + d;
         if (it < stage_iters) {
-          const Row cur = pre[d];
-          pre[d] = load_row(it + kTsLookaheadJ);
-          const uint32_t sb = it % kTsStagesJ;
-          const uint32_t ph = (it / kTsStagesJ) & 1;
-          mbar_wait(&bar_empty_b[sb], ph ^ 1);
-          const uint32_t dst = smem_base + sb * kTsStageBytesJ + dst_k;
+          const uint32_t ks = 2 * it + grp;
+          const uint32_t slot = ks % kTsASlots;
+          pre_i[d] = load_i(it + kLa);
+          mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
+          tc_fence_after_sync();
+          const uint32_t ta = taddr_lane + slot * kTsASlotCols;
+          tmem_st8(ta, cur.v[0]);
+          tmem_st8(ta + 8, cur.v[1]);
+          tmem_st8(ta + 16, cur.v[2]);
+          if ((d & 1) == grp) {  // this group's turn on the column side (it0 is a multiple of 4)
+            const RowJ rj = pre_j[d >> 1];
+            pre_j[d >> 1] = load_j(it + kLa);
+            const uint32_t sb = it % kTsStagesJ;
+            mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
+            const uint32_t dst = smem_base + sb * kTsStageBytesJ + dst_k;
 #pragma unroll
-          for (uint32_t q = 0; q < 3; ++q) {
-            if (q < wn) {
-              const Sel4 sel = make_selectors(cur.w[q]);
-              const uint4 vt = expand16(kTabHet, sel), vh = expand16(kTabHom, sel), vs = expand16(kTabSgn, sel);
-              const uint32_t a0 = dst + q * kCoreBytes;
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
-              asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
+            for (uint32_t q = 0; q < 3; ++q) {
+              if (q < wn) {
+                const Sel4 sel = make_selectors(rj.w[q]);
+                const uint4 vt = expand16(kTabHet, sel), vh = expand16(kTabHom, sel), vs = expand16(kTabSgn, sel);
+                const uint32_t a0 = dst + q * kCoreBytes;
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
+                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
+              }
             }
+            fence_proxy_async_smem();
+            mbar_arrive(&bar_full_b[sb]);
           }
-          fence_proxy_async_smem();
-          mbar_arrive(&bar_full_b[sb]);
+          const ExpI nxt = expand_i(pre_i[(d + 1) % kLa]);  // words of iteration it + 1 (already resident)
+          tmem_st_wait();
+          tc_fence_before_sync();
+          mbar_arrive(&bar_full_a[slot]);
+          cur = nxt;
         }
       }
     }
