@@ -86,7 +86,7 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t warp = tid >> 5;
+  const uint32_t warp = uniform_warp_idx();
   const uint32_t lane = tid & 31;
   const uint32_t tile = tile_order[blockIdx.x];
   const uint32_t i0 = tile_rt[tile] * kTileRows;
@@ -96,7 +96,7 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kGrmStages; ++s) {
-      mbar_init(&bar_full[s], kGrmProducerThreads);
+      mbar_init(&bar_full[s], kGrmProducerThreads / 32);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_acc, 1);
@@ -110,12 +110,11 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
 
   if (warp < 8) {
     // ---------------- producers ----------------
-    // thread = (variant k = 8 * warp + lane % 8, role = lane / 8).  role 0: the 128 row-side samples
-    // (one 32-byte sector) -> planes g, m.  roles 1..3: the 80 col-side samples (20 bytes) -> digit
-    // planes {0..3}, {4..7}, {8,9,10} through the per-variant tables.  The three col-side roles of a
-    // variant sit in the same warp, so their identical genotype loads coalesce into one request.
-    const uint32_t k = 8 * warp + (lane & 7);
-    const uint32_t role = lane >> 3;
+    // thread = (variant k = tid % 64, role = tid / 64).  role 0: the 128 row-side samples (one
+    // 32-byte sector) -> planes g, m.  roles 1..3: the 80 col-side samples (20 bytes) -> digit planes
+    // {0..3}, {4..7}, {8,9,10} through the per-variant tables.
+    const uint32_t k = tid & 63;
+    const uint32_t role = tid >> 6;
     const bool is_i = role == 0;
     const uint8_t* src = raw + static_cast<uint64_t>(k) * pitch + (is_i ? (i0 / 4) : (j0 / 4));
     const uint64_t stage_stride = static_cast<uint64_t>(kGrmKc) * pitch;
@@ -184,7 +183,7 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
             }
           }
           fence_proxy_async_smem();
-          mbar_arrive(&bar_full[s]);
+          mbar_arrive_warp(&bar_full[s], lane);
         }
       }
     }
@@ -222,35 +221,41 @@ grm_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant_
     }
     tc_fence_before_sync();
   } else {
-    if (lane == 0) {
-      constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kGrmTileCols, true, true);
-      constexpr uint32_t idesc_n80 = make_idesc_i8(128, kGrmTileCols, true, true);
-      constexpr uint32_t kPlaneBytes = kGrmGroupsJ * kCoreBytes;  // J plane step inside a k-group
-      for (uint32_t it = 0; it < stage_iters; ++it) {
-        const uint32_t s = it % kGrmStages;
-        const uint32_t ph = (it / kGrmStages) & 1;
-        mbar_wait(&bar_full[s], ph);
-        tc_fence_after_sync();
+    // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
+    constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kGrmTileCols, true, true);
+    constexpr uint32_t idesc_n80 = make_idesc_i8(128, kGrmTileCols, true, true);
+    constexpr uint32_t kPlaneStep = (kGrmGroupsJ * kCoreBytes) >> 4;  // J plane step inside a k-group (descriptor units)
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t desc_i = make_smem_desc(smem_base, kGrmLboI, kCoreBytes);
+    const uint64_t desc_j = make_smem_desc(smem_base + kGrmStageBytesI, kGrmLboJ, kCoreBytes);
+    uint32_t s = 0, ph = 0;
+    for (uint32_t it = 0; it < stage_iters; ++it) {
+      mbar_wait(&bar_full[s], ph);
+      tc_fence_after_sync();
+      if (elect_one_sync()) {
 #pragma unroll
         for (uint32_t kk = 0; kk < kGrmKc / 32; ++kk) {
-          const uint32_t si = smem_base + s * kGrmStageBytes + kk * 4 * kGrmLboI;
-          const uint32_t sj = smem_base + s * kGrmStageBytes + kGrmStageBytesI + kk * 4 * kGrmLboJ;
           const uint32_t acc = (it | kk) ? 1u : 0u;
-          const uint64_t a_g = make_smem_desc(si, kGrmLboI, kCoreBytes);
-          const uint64_t a_m = make_smem_desc(si + 8 * kCoreBytes, kGrmLboI, kCoreBytes);
-          auto bj = [&](uint32_t plane) { return make_smem_desc(sj + plane * kPlaneBytes, kGrmLboJ, kCoreBytes); };
-          umma_i8_ss(tmem_base + 0, a_g, bj(0), idesc_n160, acc);                    // g x [d1_0 d1_1]
-          umma_i8_ss(tmem_base + 2 * kGrmTileCols, a_g, bj(2), idesc_n160, acc);     // g x [d1_2 d1_3]
-          umma_i8_ss(tmem_base + 4 * kGrmTileCols, a_g, bj(4), idesc_n80, acc);      // g x d1_4
-          umma_i8_ss(tmem_base + 0, a_m, bj(5), idesc_n160, 1u);                     // m x [d2_0 d2_1]
-          umma_i8_ss(tmem_base + 2 * kGrmTileCols, a_m, bj(7), idesc_n160, 1u);      // m x [d2_2 d2_3]
-          umma_i8_ss(tmem_base + 4 * kGrmTileCols, a_m, bj(9), idesc_n80, 1u);       // m x d2_4
-          umma_i8_ss(tmem_base + 5 * kGrmTileCols, a_m, bj(10), idesc_n80, acc);     // m x m = obs
+          const uint64_t a_g = desc_i + ((s * kGrmStageBytes + kk * 4 * kGrmLboI) >> 4);
+          const uint64_t a_m = a_g + ((8 * kCoreBytes) >> 4);
+          const uint64_t bj = desc_j + ((s * kGrmStageBytes + kk * 4 * kGrmLboJ) >> 4);
+          umma_i8_ss(tmem_u + 0, a_g, bj, idesc_n160, acc);                                       // g x [d1_0 d1_1]
+          umma_i8_ss(tmem_u + 2 * kGrmTileCols, a_g, bj + 2 * kPlaneStep, idesc_n160, acc);       // g x [d1_2 d1_3]
+          umma_i8_ss(tmem_u + 4 * kGrmTileCols, a_g, bj + 4 * kPlaneStep, idesc_n80, acc);        // g x d1_4
+          umma_i8_ss(tmem_u + 0, a_m, bj + 5 * kPlaneStep, idesc_n160, 1u);                       // m x [d2_0 d2_1]
+          umma_i8_ss(tmem_u + 2 * kGrmTileCols, a_m, bj + 7 * kPlaneStep, idesc_n160, 1u);        // m x [d2_2 d2_3]
+          umma_i8_ss(tmem_u + 4 * kGrmTileCols, a_m, bj + 9 * kPlaneStep, idesc_n80, 1u);         // m x d2_4
+          umma_i8_ss(tmem_u + 5 * kGrmTileCols, a_m, bj + 10 * kPlaneStep, idesc_n80, acc);       // m x m = obs
         }
         umma_commit(&bar_empty[s]);
       }
-      umma_commit(&bar_acc);
+      __syncwarp();
+      if (++s == kGrmStages) {
+        s = 0;
+        ph ^= 1;
+      }
     }
+    if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
   }
   __syncthreads();

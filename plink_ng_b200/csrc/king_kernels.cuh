@@ -228,7 +228,7 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t warp = tid >> 5;
+  const uint32_t warp = uniform_warp_idx();
   const uint32_t lane = tid & 31;
   const uint32_t tile = tile_order[blockIdx.x];
   const uint32_t i0 = tile_rt[tile] * kTileRows;
@@ -238,7 +238,7 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kTcStages; ++s) {
-      mbar_init(&bar_full[s], kTcGroupThreads);
+      mbar_init(&bar_full[s], kTcGroupThreads / 32);
       mbar_init(&bar_empty[s], 1);
     }
     mbar_init(&bar_acc, 1);
@@ -317,7 +317,7 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
             }
           }
           fence_proxy_async_smem();
-          mbar_arrive(&bar_full[s]);
+          mbar_arrive_warp(&bar_full[s], lane);
         }
       }
     }
@@ -348,35 +348,34 @@ king_tc_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t variant
     }
     tc_fence_before_sync();
   } else {
-    // ---------------- UMMA issuer (warp 8, one lane) ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_n192 = make_idesc_i8(128, 192, true, true);
-      constexpr uint32_t idesc_n96 = make_idesc_i8(128, 96, true, true);
-      for (uint32_t it = 0; it < stage_iters; ++it) {
-        const uint32_t s = it % kTcStages;
-        const uint32_t ph = (it / kTcStages) & 1;
+    // ---------------- UMMA issuer (warp 8): whole warp loops, one elected lane issues (umma.cuh) ----------------
+    constexpr uint32_t idesc_n192 = make_idesc_i8(128, 192, true, true);
+    constexpr uint32_t idesc_n96 = make_idesc_i8(128, 96, true, true);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t desc_i = make_smem_desc(smem_base, kTcLboI, kCoreBytes);
+    const uint64_t desc_j = make_smem_desc(smem_base + kTcStageBytesI, kTcLboJ, kCoreBytes);
+    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTcStages) {  // stage_iters is a multiple of kTcStages (variant pad 256)
+      const uint32_t ph = (it0 / kTcStages) & 1;
+#pragma unroll
+      for (uint32_t s = 0; s < kTcStages; ++s) {
         mbar_wait(&bar_full[s], ph);
         tc_fence_after_sync();
-        const uint32_t si = smem_base + s * kTcStageBytes;
-        const uint32_t sj = si + kTcStageBytesI;
+        if (elect_one_sync()) {
 #pragma unroll
-        for (uint32_t kk = 0; kk < kTcKc / 32; ++kk) {
-          const uint32_t acc = (it | kk) ? 1u : 0u;
-          const uint32_t ai = si + kk * 4 * kTcLboI;
-          const uint32_t bj = sj + kk * 4 * kTcLboJ;
-          const uint64_t a_t = make_smem_desc(ai, kTcLboI, kCoreBytes);
-          const uint64_t a_h = make_smem_desc(ai + 8 * kCoreBytes, kTcLboI, kCoreBytes);
-          const uint64_t a_s = make_smem_desc(ai + 16 * kCoreBytes, kTcLboI, kCoreBytes);
-          const uint64_t b_th = make_smem_desc(bj, kTcLboJ, kCoreBytes);
-          const uint64_t b_s = make_smem_desc(bj + 12 * kCoreBytes, kTcLboJ, kCoreBytes);
-          umma_i8_ss(tmem_base + 0, a_t, b_th, idesc_n192, acc);
-          umma_i8_ss(tmem_base + 192, a_h, b_th, idesc_n192, acc);
-          umma_i8_ss(tmem_base + 384, a_s, b_s, idesc_n96, acc);
+          for (uint32_t kk = 0; kk < kTcKc / 32; ++kk) {
+            const uint32_t acc = (it0 | s | kk) ? 1u : 0u;
+            const uint64_t a_t = desc_i + ((s * kTcStageBytes + kk * 4 * kTcLboI) >> 4);
+            const uint64_t b_th = desc_j + ((s * kTcStageBytes + kk * 4 * kTcLboJ) >> 4);
+            umma_i8_ss(tmem_u + 0, a_t, b_th, idesc_n192, acc);
+            umma_i8_ss(tmem_u + 192, a_t + ((8 * kCoreBytes) >> 4), b_th, idesc_n192, acc);
+            umma_i8_ss(tmem_u + 384, a_t + ((16 * kCoreBytes) >> 4), b_th + ((12 * kCoreBytes) >> 4), idesc_n96, acc);
+          }
+          umma_commit(&bar_empty[s]);
         }
-        umma_commit(&bar_empty[s]);
+        __syncwarp();
       }
-      umma_commit(&bar_acc);
     }
+    if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
   }
   __syncthreads();

@@ -27,11 +27,17 @@ constexpr uint32_t kTsStagesJ = 4;
 constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1984: +64 keeps the K-permuted rows bank-conflict free
 constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 15872
 constexpr uint32_t kTsSmemBytes = kTsStagesJ * kTsStageBytesJ + 1024;
-constexpr uint32_t kTsThreads = 288;
+constexpr uint32_t kTsRowWarps = 8;
+constexpr uint32_t kTsColWarps = 10;           // 5 words x 64 variants per stage
+constexpr uint32_t kTsThreads = 32 * (kTsRowWarps + kTsColWarps + 1);  // + the UMMA issuer warp
 
-// ---- 2-bit matrix transpose: raw[variant][pitch] -> rawT[sample][pitch_t] (pitch_t = variants/4 bytes).
+// ---- operand re-tiling of the staged block raw[variant][pitch] (2-bit, variant-major) -------------
+// Both copies make every producer load of king_ts_kernel a contiguous run of bytes (the first TS
+// version read 8 bytes per lane from 32 different rows: 336 L1 wavefronts per k-step, LSU-bound).
+//
+// Row side:  raw_i[row tile rt][k-step ks][row 0..127][8 bytes]   8 bytes = 32 variants of one sample
 // One CTA = 64 variants x 64 samples through a shared-memory byte tile.
-static __global__ void __launch_bounds__(256) geno_transpose_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint8_t* __restrict__ raw_t, uint32_t pitch_t) {
+static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t kstep_ct, uint8_t* __restrict__ raw_i) {
   __shared__ uint8_t tile[64][68];
   const uint32_t v0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
   const uint32_t t = threadIdx.x;
@@ -43,16 +49,28 @@ static __global__ void __launch_bounds__(256) geno_transpose_kernel(const uint8_
   }
   __syncthreads();
   {
-    const uint32_t s = t >> 2, vw = t & 3;
+    const uint32_t sl = t >> 2, vw = t & 3;
     uint32_t w = 0;
 #pragma unroll
-    for (uint32_t j = 0; j < 16; ++j) w |= static_cast<uint32_t>(tile[16 * vw + j][s]) << (2 * j);
-    *reinterpret_cast<uint32_t*>(raw_t + static_cast<uint64_t>(s0 + s) * pitch_t + v0 / 4 + 4 * vw) = w;
+    for (uint32_t j = 0; j < 16; ++j) w |= static_cast<uint32_t>(tile[16 * vw + j][sl]) << (2 * j);
+    const uint32_t s = s0 + sl, v = v0 + 16 * vw;
+    *reinterpret_cast<uint32_t*>(raw_i + (static_cast<uint64_t>(s >> 7) * kstep_ct + (v >> 5)) * 1024 + (s & 127) * 8 + 4 * ((v >> 4) & 1)) = w;
+  }
+}
+
+// Column side:  raw_j[column tile ct][stage][variant 0..63][20 bytes]   20 bytes = the tile's 80 samples
+static __global__ void __launch_bounds__(256) geno_tile_cols_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t stage_ct, uint32_t coltile_ct, uint8_t* __restrict__ raw_j) {
+  const uint32_t stage = blockIdx.x, ct0 = blockIdx.y * 16;
+  for (uint32_t idx = threadIdx.x; idx < 16 * kTsKcJ * 5; idx += 256) {
+    const uint32_t w = idx % 5, k = (idx / 5) % kTsKcJ, ct = ct0 + idx / (5 * kTsKcJ);
+    if (ct >= coltile_ct) break;
+    const uint32_t val = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(stage * kTsKcJ + k) * pitch + 20 * ct + 4 * w);
+    *reinterpret_cast<uint32_t*>(raw_j + ((static_cast<uint64_t>(ct) * stage_ct + stage) * kTsKcJ + k) * 20 + 4 * w) = val;
   }
 }
 
 __global__ void __launch_bounds__(kTsThreads, 1)
-king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* __restrict__ raw_t, uint32_t pitch_t, uint32_t variant_ct_padded /* multiple of 64 */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
+king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw_i, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full_a[kTsASlots];
   __shared__ __align__(8) uint64_t bar_empty_a[kTsASlots];
@@ -62,73 +80,44 @@ king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* _
   __shared__ uint32_t tmem_base_slot;
 
   const uint32_t tid = threadIdx.x;
-  const uint32_t warp = tid >> 5;
+  const uint32_t warp = uniform_warp_idx();
   const uint32_t lane = tid & 31;
   const uint32_t tile = tile_order[blockIdx.x];
-  const uint32_t i0 = tile_rt[tile] * kTileRows;
-  const uint32_t j0 = tile_tc[tile] * kTsCols;
+  const uint32_t rt = tile_rt[tile];
+  const uint32_t ct = tile_tc[tile];
   const uint32_t stage_iters = variant_ct_padded / kTsKcJ;
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
 
   if (tid == 0) {
     for (uint32_t s = 0; s < kTsASlots; ++s) {
-      mbar_init(&bar_full_a[s], 128);
+      mbar_init(&bar_full_a[s], 4);             // one arrival per row-side warp of the owning group
       mbar_init(&bar_empty_a[s], 1);
     }
     for (uint32_t s = 0; s < kTsStagesJ; ++s) {
-      mbar_init(&bar_full_b[s], 128);
+      mbar_init(&bar_full_b[s], kTsColWarps);
       mbar_init(&bar_empty_b[s], 1);
     }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
   }
-  if (warp == 8) tmem_alloc<512>(&tmem_base_slot);
+  if (warp == kTsRowWarps + kTsColWarps) tmem_alloc<512>(&tmem_base_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
-  if (warp < 8) {
-    // ---------------- producers ----------------
-    // Two groups of four warps (group = warp / 4).  Group g expands the ROW side of k-steps ks = 2 it + g
-    // straight into tensor memory (thread = TMEM lane = sample i0 + 32 (warp % 4) + lane) and the COLUMN
-    // side of the shared-memory stages it with it % 2 == g (thread = variant k of the stage, half of its
-    // 20-byte row).  The tcgen05.st of one k-step is overlapped with the column-side work and with the
-    // expansion of the group's next k-step; tcgen05.wait::st + arrive come last.
+  if (warp < kTsRowWarps) {
+    // ---------------- row-side producers: 2-bit words -> registers -> tensor memory ----------------
+    // Two groups of four warps (group = warp / 4); group g owns k-steps ks = 2 n + g and the A slots
+    // ks % 4 in {g, g + 2}.  Thread = TMEM lane = sample 128 rt + 32 (warp % 4) + lane.  The words of
+    // the next k-step are expanded while the UMMAs of the previous ones run.
     const uint32_t grp = warp >> 2;
     const uint32_t lq = warp & 3;
     const uint32_t row = 32 * lq + lane;
-    const uint8_t* src_i = raw_t + static_cast<uint64_t>(i0 + row) * pitch_t;
+    const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt) * (2 * stage_iters) * 1024 + row * 8;
     const uint32_t taddr_lane = tmem_base + ((32u * lq) << 16) + kTsAccCols;
-    const uint32_t t = row;                        // 0..127 inside the group
-    const uint32_t k = t & 63;
-    const uint32_t half = t >> 6;                  // 0: words 0..2, 1: words 3..4
-    const uint32_t w0 = half ? 3u : 0u;
-    const uint32_t wn = half ? 2u : 3u;
-    const uint8_t* src_j = raw + static_cast<uint64_t>(k) * pitch + j0 / 4 + 4 * w0;
-    const uint64_t stage_stride = static_cast<uint64_t>(kTsKcJ) * pitch;
-    // K rows of the column side are stored in the PRMT position order of the row side
-    // (geno_expand.cuh): variant k of a 16-variant group sits at row SampleToPos(k % 16)
-    const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
-    const uint32_t dst_k = (kpos >> 3) * kTsLboJ + (kpos & 7) * 16 + w0 * kCoreBytes;
-
-    auto load_i = [&](uint32_t it) -> uint2 {  // row-side words of k-step 2 it + grp
-      const uint32_t ks = 2 * it + grp;
-      return (it < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 8ull * ks)) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    };
-    struct RowJ {
-      uint32_t w[3];
-    };
-    auto load_j = [&](uint32_t it) -> RowJ {  // column-side words of stage it
-      RowJ r;
-      r.w[0] = r.w[1] = r.w[2] = 0xFFFFFFFFu;
-      if (it < stage_iters) {
-        const uint32_t* p = reinterpret_cast<const uint32_t*>(src_j + it * stage_stride);
-        r.w[0] = __ldg(p);
-        r.w[1] = __ldg(p + 1);
-        if (wn == 3) r.w[2] = __ldg(p + 2);
-      }
-      return r;
+    auto load_i = [&](uint32_t n) -> uint2 {
+      return (n < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 1024ull * (2 * n + grp))) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
     };
     struct ExpI {
       uint32_t v[3][8];
@@ -145,89 +134,105 @@ king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* _
       }
       return e;
     };
-
-    constexpr uint32_t kLa = 4;  // iterations of lookahead (row side: 4 k-steps of this group; column side: 2 stages)
+    constexpr uint32_t kLa = 4;
     uint2 pre_i[kLa];
-    RowJ pre_j[kLa / 2];
 #pragma unroll
     for (uint32_t d = 0; d < kLa; ++d) pre_i[d] = load_i(d);
-#pragma unroll
-    for (uint32_t d = 0; d < kLa / 2; ++d) pre_j[d] = load_j(2 * d + grp);
     ExpI cur = expand_i(pre_i[0]);
+    for (uint32_t n0 = 0; n0 < stage_iters; n0 += kLa) {  // stage_iters is a multiple of 4
+#pragma unroll
+      for (uint32_t d = 0; d < kLa; ++d) {
+        const uint32_t n = n0 + d;
+        const uint32_t ks = 2 * n + grp;
+        const uint32_t slot = ks % kTsASlots;
+        pre_i[d] = load_i(n + kLa);
+        mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t ta = taddr_lane + slot * kTsASlotCols;
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st8(ta + 16, cur.v[2]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[slot], lane);
+        cur = expand_i(pre_i[(d + 1) % kLa]);
+      }
+    }
+  } else if (warp < kTsRowWarps + kTsColWarps) {
+    // ---------------- column-side producers: 2-bit words -> int8 planes in shared memory ----------------
+    // Thread = (word w of the 20-byte row, variant k of the 64-variant stage).
+    const uint32_t t = tid - 32 * kTsRowWarps;     // 0..319
+    const uint32_t k = t & 63;
+    const uint32_t w = t >> 6;
+    const uint8_t* src_j = raw_j + static_cast<uint64_t>(ct) * stage_iters * (kTsKcJ * 20) + k * 20 + 4 * w;
+    // K rows are stored in the PRMT position order of the row side (geno_expand.cuh): variant k of a
+    // 16-variant group sits at row SampleToPos(k % 16)
+    const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
+    const uint32_t dst_k = (kpos >> 3) * kTsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
+    auto load_j = [&](uint32_t it) -> uint32_t {
+      return (it < stage_iters) ? __ldg(reinterpret_cast<const uint32_t*>(src_j + static_cast<uint64_t>(it) * (kTsKcJ * 20))) : 0xFFFFFFFFu;
+    };
+    constexpr uint32_t kLa = 4;
+    uint32_t pre_j[kLa];
+#pragma unroll
+    for (uint32_t d = 0; d < kLa; ++d) pre_j[d] = load_j(d);
     for (uint32_t it0 = 0; it0 < stage_iters; it0 += kLa) {
 #pragma unroll
       for (uint32_t d = 0; d < kLa; ++d) {
         const uint32_t it = it0 + d;
-        if (it < stage_iters) {
-          const uint32_t ks = 2 * it + grp;
-          const uint32_t slot = ks % kTsASlots;
-          pre_i[d] = load_i(it + kLa);
-          mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
-          tc_fence_after_sync();
-          const uint32_t ta = taddr_lane + slot * kTsASlotCols;
-          tmem_st8(ta, cur.v[0]);
-          tmem_st8(ta + 8, cur.v[1]);
-          tmem_st8(ta + 16, cur.v[2]);
-          if ((d & 1) == grp) {  // this group's turn on the column side (it0 is a multiple of 4)
-            const RowJ rj = pre_j[d >> 1];
-            pre_j[d >> 1] = load_j(it + kLa);
-            const uint32_t sb = it % kTsStagesJ;
-            mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
-            const uint32_t dst = smem_base + sb * kTsStageBytesJ + dst_k;
-#pragma unroll
-            for (uint32_t q = 0; q < 3; ++q) {
-              if (q < wn) {
-                const Sel4 sel = make_selectors(rj.w[q]);
-                const uint4 vt = expand16(kTabHet, sel), vh = expand16(kTabHom, sel), vs = expand16(kTabSgn, sel);
-                const uint32_t a0 = dst + q * kCoreBytes;
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
-                asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
-              }
-            }
-            fence_proxy_async_smem();
-            mbar_arrive(&bar_full_b[sb]);
-          }
-          const ExpI nxt = expand_i(pre_i[(d + 1) % kLa]);  // words of iteration it + 1 (already resident)
-          tmem_st_wait();
-          tc_fence_before_sync();
-          mbar_arrive(&bar_full_a[slot]);
-          cur = nxt;
-        }
+        const Sel4 sel = make_selectors(pre_j[d]);
+        pre_j[d] = load_j(it + kLa);
+        const uint4 vt = expand16(kTabHet, sel), vh = expand16(kTabHom, sel), vs = expand16(kTabSgn, sel);
+        const uint32_t sb = d % kTsStagesJ;
+        mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
+        const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
+        fence_proxy_async_smem();
+        mbar_arrive_warp(&bar_full_b[sb], lane);
       }
     }
   } else {
-    // ---------------- UMMA issuer ----------------
-    if (lane == 0) {
-      constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kTsCols, false, true);
-      constexpr uint32_t idesc_n80 = make_idesc_i8(128, kTsCols, false, true);
-      for (uint32_t it = 0; it < stage_iters; ++it) {
-        const uint32_t sb = it % kTsStagesJ;
-        mbar_wait(&bar_full_b[sb], (it / kTsStagesJ) & 1);
+    // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
+    // One outer iteration = the 4 shared-memory stages = 8 k-steps = two rounds of the 4 A slots, so
+    // every slot index, A parity and descriptor offset is a compile-time constant.
+    static_assert(kTsStagesJ == 4 && kTsASlots == 4, "issuer unrolling assumes 4 stages / 4 slots");
+    constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kTsCols, false, true);
+    constexpr uint32_t idesc_n80 = make_idesc_i8(128, kTsCols, false, true);
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t desc0 = make_smem_desc(smem_base, kTsLboJ, kCoreBytes);
+    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTsStagesJ) {
+      const uint32_t ph_b = (it0 / kTsStagesJ) & 1;
+#pragma unroll
+      for (uint32_t sb = 0; sb < kTsStagesJ; ++sb) {
+        mbar_wait(&bar_full_b[sb], ph_b);
 #pragma unroll
         for (uint32_t kk = 0; kk < 2; ++kk) {
-          const uint32_t ks = 2 * it + kk;
-          const uint32_t slot = ks % kTsASlots;
-          mbar_wait(&bar_full_a[slot], (ks / kTsASlots) & 1);
+          const uint32_t kq = 2 * sb + kk;            // k-step inside the outer iteration
+          const uint32_t slot = kq % kTsASlots;
+          mbar_wait(&bar_full_a[slot], (kq / kTsASlots) & 1);
           tc_fence_after_sync();
-          const uint32_t acc = ks ? 1u : 0u;
-          const uint32_t bj = smem_base + sb * kTsStageBytesJ + kk * 4 * kTsLboJ;
-          const uint64_t b_th = make_smem_desc(bj, kTsLboJ, kCoreBytes);
-          const uint64_t b_s = make_smem_desc(bj + 2 * kTsGroupsJ * kCoreBytes, kTsLboJ, kCoreBytes);
-          const uint32_t ta = tmem_base + kTsAccCols + slot * kTsASlotCols;
-          umma_i8_ts(tmem_base + 0, ta, b_th, idesc_n160, acc);
-          umma_i8_ts(tmem_base + 2 * kTsCols, ta + 8, b_th, idesc_n160, acc);
-          umma_i8_ts(tmem_base + 4 * kTsCols, ta + 16, b_s, idesc_n80, acc);
-          umma_commit(&bar_empty_a[slot]);
+          if (elect_one_sync()) {
+            const uint32_t acc = (it0 | kq) ? 1u : 0u;
+            const uint64_t b_th = desc0 + ((sb * kTsStageBytesJ + kk * 4 * kTsLboJ) >> 4);
+            const uint64_t b_s = b_th + ((2 * kTsGroupsJ * kCoreBytes) >> 4);
+            const uint32_t ta = tmem_u + kTsAccCols + slot * kTsASlotCols;
+            umma_i8_ts(tmem_u + 0, ta, b_th, idesc_n160, acc);
+            umma_i8_ts(tmem_u + 2 * kTsCols, ta + 8, b_th, idesc_n160, acc);
+            umma_i8_ts(tmem_u + 4 * kTsCols, ta + 16, b_s, idesc_n80, acc);
+            umma_commit(&bar_empty_a[slot]);
+            if (kk == 1) umma_commit(&bar_empty_b[sb]);
+          }
+          __syncwarp();
         }
-        umma_commit(&bar_empty_b[sb]);
       }
-      umma_commit(&bar_acc);
     }
+    if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
   }
 
-  if (warp < 8) {
+  if (warp < kTsRowWarps) {
     // ---------------- epilogue: TMEM -> raw accumulators (+=) ----------------
     mbar_wait(&bar_acc, 0);
     tc_fence_after_sync();
@@ -252,7 +257,7 @@ king_ts_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, const uint8_t* _
     tc_fence_before_sync();
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTsRowWarps + kTsColWarps) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);
   }

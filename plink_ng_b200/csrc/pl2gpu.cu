@@ -154,7 +154,8 @@ struct Pl2KingJob {
   TileList tiles;
   GenoStage stage;
   uint32_t* d_planes = nullptr;  // popcount path only
-  uint8_t* d_raw_t = nullptr;    // TS path only: sample-major copy of the staged block
+  uint8_t* d_raw_t = nullptr;    // TS path only: row-side re-tiled copy of the staged block (king_ts_kernel.cuh)
+  uint8_t* d_raw_j = nullptr;    // TS path only: column-side re-tiled copy
   uint32_t tile_cols = kTileCols;
   int32_t* d_raw_acc = nullptr;
   void* d_out_stage = nullptr;   // bounded staging for host downloads
@@ -315,9 +316,10 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
   job->tile_cols = ts ? kTsCols : kTileCols;
   if (BuildTileList(row_start, row_end, false, &job->tiles, job->tile_cols)) return fail();
   if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, ts ? kTsSamplePad : kSamplePad)) return fail();
-  if (ts && cudaMalloc(&job->d_raw_t, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess) {
+  if (ts && (cudaMalloc(&job->d_raw_t, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
+             cudaMalloc(&job->d_raw_j, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess)) {
     cudaGetLastError();
-    set_error("pl2gpu_king_begin: insufficient device memory for the sample-major genotype copy");
+    set_error("pl2gpu_king_begin: insufficient device memory for the re-tiled genotype copies");
     return fail();
   }
   const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * (5ull * job->tile_cols * kTileRows) * sizeof(int32_t);
@@ -378,10 +380,12 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
         king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage.sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       } else if (job->algo == kPl2KingAlgoTensorTS) {
-        const uint32_t pitch_t = padded / 4;
-        geno_transpose_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->d_raw_t, pitch_t);
+        const uint32_t coltile_ct = job->stage.sample_ct_padded / kTsCols;
+        geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, job->d_raw_t);
         c->launches++;
-        king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->d_raw_t, pitch_t, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+        geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);
+        c->launches++;
+        king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->d_raw_j, job->d_raw_t, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       } else {
         king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
@@ -486,6 +490,7 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   StageFree(&job->stage);
   cudaFree(job->d_planes);
   cudaFree(job->d_raw_t);
+  cudaFree(job->d_raw_j);
   cudaFree(job->d_raw_acc);
   cudaFree(job->d_out_stage);
   cudaGetLastError();
@@ -538,6 +543,25 @@ int pl2gpu_debug_umma(Pl2GpuCtx* ctx, const uint8_t* a_img, uint32_t a_bytes, co
 }
 
 int pl2gpu_selftest_umma(Pl2GpuCtx* ctx, int verbose) {
+  if (getenv("PL2_UMMA_BENCH")) {  // diagnostic: tcgen05.mma issue / execution rate (umma_probe.cuh)
+    Ctx* c = &ctx->c;
+    long long* d_out = nullptr;
+    PL2_CUDA_OK(cudaMalloc(&d_out, 64));
+    PL2_CUDA_OK(cudaFuncSetAttribute(umma_issue_bench_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
+    const uint32_t reps = 512;
+    for (uint32_t mode = 0; mode < 4; ++mode)
+      for (uint32_t issuers = 1; issuers <= 2; ++issuers)
+        for (uint32_t n : {80u, 160u, 224u})
+          for (uint32_t ce : {0u, 1u}) {
+            if (n * issuers > 448) continue;
+            umma_issue_bench_kernel<<<1, 128, kProbeSmemBytes, c->stream>>>(n, reps, mode, issuers, ce, d_out);
+            long long h[8] = {0};
+            PL2_CUDA_OK(cudaMemcpyAsync(h, d_out, 64, cudaMemcpyDeviceToHost, c->stream));
+            PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+            printf("umma_bench style=%s mode=%s issuers=%u n=%3u commit_every=%u: issue %.1f clk/mma, complete %.1f clk/mma (floor %.0f)\n", (mode >> 1) ? "elect" : "lane0", (mode & 1) ? "TS" : "SS", issuers, n, ce, double(h[0]) / reps, double(h[1]) / reps, n / 2.0 * issuers);
+          }
+    cudaFree(d_out);
+  }
   // Production operand layout (geno_expand.cuh operand_offset), M=128, N=96, K=64 (two k-steps).
   const uint32_t M = 128, N = 96, K = 64;
   const uint32_t lbo_a = operand_lbo(M), lbo_b = operand_lbo(N);

@@ -22,6 +22,14 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP (barrier count = producer warps): mbarrier.arrive is a shared-memory atomic,
+// and one per thread (288 per k-step in the first TS kernel) serialises on the barrier word.  Each
+// lane orders its own writes first (fence.proxy.async / tcgen05.wait::st + fence), __syncwarp makes
+// them cumulative with lane 0's release-arrive.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, uint32_t lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -128,5 +136,30 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8])
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+
+// ---- single-thread issue without waterfall loops -------------------------------------------------
+// tcgen05.mma / tcgen05.commit are warp-level uniform-datapath instructions in SASS (UTCIMMA, UTCBAR).
+// ptxas emits them straight-line only when (a) the surrounding control flow is provably warp-uniform
+// and (b) every operand is provably uniform; otherwise EACH one is wrapped in a VOTEU / ELECT /
+// R2UR.BROADCAST / BRA.U.ANY waterfall loop that costs 110-190 clk per UMMA on the issuing thread
+// (umma_issue_bench_kernel: 186 clk/UMMA under `if (lane == 0)`, i.e. more than the 40-96 clk the
+// tensor pipe needs for our N = 80..192 shapes).  Recipe, as in CUTLASS' sm100 kernels:
+//   * take the warp index with uniform_warp_idx() (a __shfl_sync from lane 0 is provably uniform),
+//   * broadcast values read from memory (the TMEM base) with uniform_u32(),
+//   * run the issuer loop on the WHOLE warp and guard the tcgen05 block with `if (elect_one_sync())`.
+__device__ __forceinline__ uint32_t uniform_u32(uint32_t v) { return __shfl_sync(0xFFFFFFFFu, v, 0); }
+__device__ __forceinline__ uint32_t uniform_warp_idx() { return __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0); }
+__device__ __forceinline__ uint32_t elect_one_sync() {
+  uint32_t pred = 0, laneid = 0;
+  asm volatile(
+      "{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\t"
+      "elect.sync %%rx|%%px, %2;\n\t"
+      "@%%px mov.s32 %1, 1;\n\t"
+      "mov.s32 %0, %%rx;\n\t}"
+      : "+r"(laneid), "+r"(pred)
+      : "r"(0xFFFFFFFFu));
+  return pred;
+}
 
 }  // namespace pl2

@@ -127,4 +127,72 @@ umma_probe_ts_kernel(const uint8_t* __restrict__ a_rows, const uint8_t* __restri
   }
 }
 
+
+// Issue-rate microbenchmark (diagnostic, printed by pl2gpu_selftest_umma when PL2_UMMA_BENCH is set):
+// `issuers` warps each issue `reps` back-to-back int8 UMMAs of width n into their own accumulator
+// columns from garbage shared memory / tensor memory, then commit.  Reports clocks per UMMA for the
+// issue loop alone and up to completion.  mode 0 = SS, 1 = TS.
+__global__ void __launch_bounds__(128, 1)
+umma_issue_bench_kernel(uint32_t n, uint32_t reps, uint32_t mode, uint32_t issuers, uint32_t commit_every, long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_done[4];
+  __shared__ uint32_t tmem_base_slot;
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+  if (tid == 0) {
+    for (int i = 0; i < 4; ++i) mbar_init(&bar_done[i], 1);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_base_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+  if (warp < issuers) {
+    const uint32_t style = mode >> 1;  // 0: `if (lane == 0)` region, 1: whole warp + elect.sync
+    const uint32_t ts = mode & 1;
+    const uint32_t idesc = make_idesc_i8(128, n, ts == 0, true);
+    const uint32_t d = tmem_base + warp * (448 / issuers);
+    const uint64_t da = make_smem_desc(smem_base, 2048, 128), db = make_smem_desc(smem_base + 32768, 2048, 128);
+    long long t0 = 0, t1 = 0, t2 = 0;
+    if (style == 0) {
+      if (lane == 0) {
+        t0 = clock64();
+        for (uint32_t r = 0; r < reps; ++r) {
+          if (ts == 0) umma_i8_ss(d, da, db, idesc, r ? 1u : 0u);
+          else umma_i8_ts(d, tmem_base + 480, db, idesc, r ? 1u : 0u);
+          if (commit_every) umma_commit(&bar_done[2 + warp]);  // never waited on
+        }
+        t1 = clock64();
+        umma_commit(&bar_done[warp]);
+      }
+    } else {
+      t0 = clock64();
+      for (uint32_t r = 0; r < reps; ++r) {
+        if (elect_one_sync()) {
+          if (ts == 0) umma_i8_ss(d, da, db, idesc, r ? 1u : 0u);
+          else umma_i8_ts(d, tmem_base + 480, db, idesc, r ? 1u : 0u);
+          if (commit_every) umma_commit(&bar_done[2 + warp]);
+        }
+        __syncwarp();
+      }
+      t1 = clock64();
+      if (elect_one_sync()) umma_commit(&bar_done[warp]);
+      __syncwarp();
+    }
+    mbar_wait(&bar_done[warp], 0);
+    t2 = clock64();
+    if (lane == 0) {
+      out[2 * warp] = t1 - t0;
+      out[2 * warp + 1] = t2 - t0;
+    }
+  }
+  tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 }  // namespace pl2

@@ -16,7 +16,7 @@ g = torch.randint(0, 256, (m, words * 8), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 pairs = n * (n - 1) // 2
 with p.GpuContext(0) as ctx:
-    for name, algo in (("tensor", KING_ALGO_TENSOR), ("tensor_ts", KING_ALGO_TENSOR_TS), ("popcount", KING_ALGO_POPCOUNT))[: (2 if os.environ.get("SKIP_POPC") else 3)]:
+    for name, algo in (("tensor", KING_ALGO_TENSOR), ("tensor_ts", KING_ALGO_TENSOR_TS), ("popcount", KING_ALGO_POPCOUNT))[: (2 if os.environ.get("SKIP_POPC") else 3)][(1 if os.environ.get("SKIP_GRM") else 0):]:
         with KingJob(ctx, n, 0, n, algo) as job:
             job.add_variants_device(g.data_ptr(), words * 8, m)  # warm-up
             ctx.synchronize()
@@ -28,6 +28,8 @@ with p.GpuContext(0) as ctx:
             print(f"{name:9s} N={n} M={m}: {ms:9.3f} ms/batch  {pairs * m / ms / 1e9:10.2f} G pair*SNP/ms->{pairs * m / (ms * 1e-3):.3e} pair*SNP/s  int8-equiv {5 * 2 * pairs * m / (ms * 1e-3) / 1e12:8.1f} TOP/s", flush=True)
 
 # GRM kernel timing (same shape)
+if os.environ.get("SKIP_GRM"):
+    raise SystemExit(0)
 from plink_ng_b200.host import GrmJob
 rf = np.random.default_rng(0).uniform(0.05, 0.95, size=m)
 with p.GpuContext(0) as ctx, GrmJob(ctx, n) as job:
