@@ -11,7 +11,8 @@ counts accumulate in HBM across steps exactly as in a full run (16 steps of 65,5
   e2e     = same metric through the C-ABI with HOST buffers: every step copies the step's genotype
             batch from pinned host memory and reads back 1/steps_per_job of the fp64 kinship matrix.
   roofline= int8 tensor pipe: 5 products x 2 ops x pairs x variants / kernel time (CUDA events on the
-            library's stream) vs 2 x the measured bf16 cuBLAS rate in MEASURED_PEAKS.json.
+            library's stream) vs the nominal dense int8 rate (4.5 POP/s); fractions of 2 x the measured
+            bf16 cuBLAS rates of MEASURED_PEAKS.json are reported beside it.
   cpu_baseline / --impl reference = the UNMODIFIED reference binary (oracle/_ref/plink2,
             --make-king-table, all host threads) on a bounded sample of the same workload.
 
@@ -47,7 +48,7 @@ def parse_args():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--samples", type=int, default=FULL_N)
     ap.add_argument("--batch-variants", type=int, default=65536)
-    ap.add_argument("--algo", default="tensor", choices=["tensor", "popcount"])
+    ap.add_argument("--algo", default="tensor_ts", choices=["tensor_ts", "tensor", "popcount"])
     ap.add_argument("--cpu-samples", type=int, default=16384)
     ap.add_argument("--cpu-variants", type=int, default=65536)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -195,7 +196,7 @@ def b200_arm(args):
     import torch.distributed as dist
 
     import plink_ng_b200 as p
-    from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KingJob
+    from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS, KingJob
     from plink_ng_b200.sharding import assemble_block, pairs_in_rows, row_block, variant_slice
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -211,7 +212,7 @@ def b200_arm(args):
     r0, r1 = row_block(n, rank, world)
     my_pairs = pairs_in_rows(r0, r1)
     total_pairs = n * (n - 1) // 2
-    algo = KING_ALGO_TENSOR if args.algo == "tensor" else KING_ALGO_POPCOUNT
+    algo = {"tensor_ts": KING_ALGO_TENSOR_TS, "tensor": KING_ALGO_TENSOR, "popcount": KING_ALGO_POPCOUNT}[args.algo]
 
     # this rank's slice of the step's variants; all_gather assembles the tile (north_star)
     per, v0, v1 = variant_slice(mb, rank, world)
@@ -319,13 +320,22 @@ def b200_arm(args):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
-    peak_src = "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8:bf16 = 2:1 on tcgen05)" if peaks else "2 x fallback 1.4 PF sustained bf16"
+    # int8 tensor peak.  MEASURED_PEAKS.json holds no int8 figure, only cuBLAS bf16 (burst / sustained, the
+    # latter power-capped at ~1.37 GHz).  tcgen05 kind::i8 retires 8192 MAC/clk/SM (128 x N x 32 in N/2 clk,
+    # B300_MICROARCH.md "tcgen05 floor"): 148 SMs x 16384 op/clk x 1.965 GHz = 4.77 POP/s, NVIDIA's dense
+    # int8/fp8 nominal is 4.5 POP/s.  `peak` is the nominal 4500; the bf16-derived figures are given beside it.
+    bf16_burst = peaks.get("bf16_tflops") or 1590.0
+    bf16_sust = peaks.get("bf16_tflops_sustained") or 1400.0
+    peak = 4500.0
+    peak_src = ("nominal dense int8 4.5 POP/s (no measured int8 peak exists; 2 x measured bf16 would be "
+                f"{2 * bf16_burst:.0f} burst / {2 * bf16_sust:.0f} sustained TOP/s, which this kernel exceeds because cuBLAS bf16 is power-capped)")
     ops = 5 * 2 * my_pairs * mb  # algorithmic: 5 indicator products per pair and variant
     achieved = ops / (kern_ms * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": 2 * bf16, "unit": "TOP/s (int8)", "frac": achieved / (2 * bf16), "traffic": None,
-                "kernel": "king_tc_kernel" if algo == KING_ALGO_TENSOR else "king_popc_kernel", "kernel_ms": kern_ms, "peak_source": peak_src,
-                "algorithmic_ops_per_launch": ops}
+    kname = {KING_ALGO_TENSOR_TS: "king_ts_kernel", KING_ALGO_TENSOR: "king_tc_kernel", KING_ALGO_POPCOUNT: "king_popc_kernel"}[algo]
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": None,
+                "kernel": kname, "kernel_ms": kern_ms, "peak_source": peak_src, "frac_of_2x_bf16_burst": achieved / (2 * bf16_burst),
+                "frac_of_2x_bf16_sustained": achieved / (2 * bf16_sust), "algorithmic_ops_per_launch": ops,
+                "kernel_ms_note": "one add_variants call = pad + two re-tiling launches (~2%) + the tensor kernel, CUDA events on the library's stream"}
     if algo == KING_ALGO_POPCOUNT:
         roofline["note"] = "popcount kernel: int8-equivalent ops shown for comparability; its own limiter is the POPC pipe"
 
@@ -343,7 +353,7 @@ def b200_arm(args):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "s8 (exact int32 accumulate)" if algo == KING_ALGO_TENSOR else "u32 popcount",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32 popcount" if algo == KING_ALGO_POPCOUNT else "s8 (exact int32 accumulate)",
         "data": "synthetic",
         "config": {"workload": f"--make-king, {n} samples x {FULL_M} SNPs in steps of {mb} variants", "samples": n, "variants_per_step": mb, "steps_per_full_job": FULL_M // mb,
                    "parallelism": f"row-block x{world} (ParallelBounds), 1 all_gather/step" if world > 1 else "single GPU", "algo": args.algo,

@@ -276,14 +276,21 @@ int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, floa
 // ------------------------------------------------------------------------------------------ KING
 
 uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add) {
-  const uint64_t tiles = CountTiles(row_start, row_end, false);
+  // Upper bound over the algorithms (the caller does not pass one): accumulators + staged block and
+  // its per-algorithm re-layouts + tile lists + slack.
   uint32_t cap = max_variants_per_add ? max_variants_per_add : kMaxStageVariants;
   if (cap > kMaxStageVariants) cap = kMaxStageVariants;
   cap = RoundUpU32(cap, kVariantPad);
+  const uint64_t slack = 256ull << 20;
+  // SS tensor / popcount: 128 x 96 tiles, raw block + 3 bit planes (popcount only)
+  const uint64_t tiles = CountTiles(row_start, row_end, false);
   const uint64_t npad = RoundUpU32(sample_ct, kSamplePad);
-  const uint64_t raw = static_cast<uint64_t>(cap) * (npad / 4);
-  const uint64_t planes = 3ull * (cap / 32) * npad * 4;
-  return tiles * kKingTileAccWords * 4 + raw + planes + (256ull << 20) + tiles * 8;
+  const uint64_t need_ss = tiles * kKingTileAccWords * 4 + static_cast<uint64_t>(cap) * (npad / 4) + 3ull * (cap / 32) * npad * 4 + tiles * 12;
+  // TS tensor (the default): 128 x 80 tiles, raw block + row-side and column-side re-tiled copies
+  const uint64_t tiles_ts = CountTiles(row_start, row_end, false, kTsCols);
+  const uint64_t npad_ts = RoundUpU32(sample_ct, kTsSamplePad);
+  const uint64_t need_ts = tiles_ts * kTsTileAccWords * 4 + 3ull * cap * (npad_ts / 4) + tiles_ts * 12;
+  return (need_ss > need_ts ? need_ss : need_ts) + slack;
 }
 
 int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr) {
@@ -296,7 +303,7 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     set_error("pl2gpu_king_begin: bad row range [%u,%u) for %u samples", row_start, row_end, sample_ct);
     return 1;
   }
-  if (algo == kPl2KingAlgoAuto) algo = kPl2KingAlgoTensor;
+  if (algo == kPl2KingAlgoAuto) algo = kPl2KingAlgoTensorTS;
   if (algo != kPl2KingAlgoPopcount && algo != kPl2KingAlgoTensor && algo != kPl2KingAlgoTensorTS) {
     set_error("pl2gpu_king_begin: unknown algo %d", algo);
     return 1;

@@ -16,7 +16,7 @@ g = torch.randint(0, 256, (m, words * 8), dtype=torch.uint8, device="cuda")
 torch.cuda.synchronize()
 pairs = n * (n - 1) // 2
 with p.GpuContext(0) as ctx:
-    for name, algo in (("tensor", KING_ALGO_TENSOR), ("tensor_ts", KING_ALGO_TENSOR_TS), ("popcount", KING_ALGO_POPCOUNT))[: (2 if os.environ.get("SKIP_POPC") else 3)][(1 if os.environ.get("SKIP_GRM") else 0):]:
+    for name, algo in (("tensor", KING_ALGO_TENSOR), ("tensor_ts", KING_ALGO_TENSOR_TS), ("popcount", KING_ALGO_POPCOUNT))[: (2 if os.environ.get("SKIP_POPC") else 3)][(1 if os.environ.get("SKIP_SS") else 0):]:
         with KingJob(ctx, n, 0, n, algo) as job:
             job.add_variants_device(g.data_ptr(), words * 8, m)  # warm-up
             ctx.synchronize()
