@@ -1,0 +1,51 @@
+// geno_tile.cuh - operand re-tiling for the "TS" tensor kernels (king_ts_kernel.cuh, grm_ts_kernel.cuh):
+// 128-row x 80-column pair tiles, row operand expanded into tensor memory, column operand into
+// shared memory.  Kernels are static (header is included by several translation units).
+#pragma once
+#include "common.cuh"
+
+namespace pl2 {
+
+constexpr uint32_t kTsCols = 80;
+constexpr uint32_t kTsSamplePad = 640;  // lcm(128, 80)
+constexpr uint32_t kTsKcJ = 64;         // variants per shared-memory stage (two k-steps)
+
+// ---- operand re-tiling of the staged block raw[variant][pitch] (2-bit, variant-major) -------------
+// Both copies make every producer load of king_ts_kernel a contiguous run of bytes (the first TS
+// version read 8 bytes per lane from 32 different rows: 336 L1 wavefronts per k-step, LSU-bound).
+//
+// Row side:  raw_i[row tile rt][k-step ks][row 0..127][8 bytes]   8 bytes = 32 variants of one sample
+// One CTA = 64 variants x 64 samples through a shared-memory byte tile.
+static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t kstep_ct, uint8_t* __restrict__ raw_i) {
+  __shared__ uint8_t tile[64][68];
+  const uint32_t v0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
+  const uint32_t t = threadIdx.x;
+  {
+    const uint32_t v = t >> 2, sw = t & 3;
+    const uint32_t w = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(v0 + v) * pitch + s0 / 4 + 4 * sw);
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) tile[v][16 * sw + j] = static_cast<uint8_t>((w >> (2 * j)) & 3u);
+  }
+  __syncthreads();
+  {
+    const uint32_t sl = t >> 2, vw = t & 3;
+    uint32_t w = 0;
+#pragma unroll
+    for (uint32_t j = 0; j < 16; ++j) w |= static_cast<uint32_t>(tile[16 * vw + j][sl]) << (2 * j);
+    const uint32_t s = s0 + sl, v = v0 + 16 * vw;
+    *reinterpret_cast<uint32_t*>(raw_i + (static_cast<uint64_t>(s >> 7) * kstep_ct + (v >> 5)) * 1024 + (s & 127) * 8 + 4 * ((v >> 4) & 1)) = w;
+  }
+}
+
+// Column side:  raw_j[column tile ct][stage][variant 0..63][20 bytes]   20 bytes = the tile's 80 samples
+static __global__ void __launch_bounds__(256) geno_tile_cols_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t stage_ct, uint32_t coltile_ct, uint8_t* __restrict__ raw_j) {
+  const uint32_t stage = blockIdx.x, ct0 = blockIdx.y * 16;
+  for (uint32_t idx = threadIdx.x; idx < 16 * kTsKcJ * 5; idx += 256) {
+    const uint32_t w = idx % 5, k = (idx / 5) % kTsKcJ, ct = ct0 + idx / (5 * kTsKcJ);
+    if (ct >= coltile_ct) break;
+    const uint32_t val = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(stage * kTsKcJ + k) * pitch + 20 * ct + 4 * w);
+    *reinterpret_cast<uint32_t*>(raw_j + ((static_cast<uint64_t>(ct) * stage_ct + stage) * kTsKcJ + k) * 20 + 4 * w) = val;
+  }
+}
+
+}  // namespace pl2

@@ -1,0 +1,263 @@
+// grm_ts_kernel.cuh - GRM contraction, "TS" form: the row-side operand (planes g, m) is expanded from
+// the sample-major re-tiled copy straight into tensor memory, only the column side (10 digit planes
+// + m) goes through shared memory.  Same math, tables and accumulator semantics as grm_kernels.cuh
+// (which documents the fixed-point digit decomposition); that SS form moved 56 KB of operands through
+// shared memory per 440 tensor clocks (127 B/clk of the 128 B/clk available) and sat at 45 % of the
+// tensor pipe.
+//
+// Tile = 128 rows x 80 cols.  TMEM columns: [0,400) digit accumulators D_0..D_4, [400,480) obs counts,
+// [480,512) two A slots of 16 columns (planes g, m; 8 columns = 32 K-bytes per lane).
+// Per 32 variants (6 UMMAs, 440 tensor clk):  m x [d2_0 d2_1], m x [d2_2 d2_3], m x [d2_4 | m] (N = 160,
+// lands on D_4 and obs), g x [d1_0 d1_1], g x [d1_2 d1_3], g x d1_4.  The m products are issued first so
+// that on the very first k-step they zero-initialise every accumulator (accumulate = 0) and the g
+// products always accumulate.
+#pragma once
+#include "common.cuh"
+#include "geno_expand.cuh"
+#include "geno_tile.cuh"
+#include "grm_kernels.cuh"
+#include "umma.cuh"
+
+namespace pl2 {
+
+static_assert(kGrmTileCols == kTsCols && kGrmSamplePad == kTsSamplePad && kGrmKc == kTsKcJ, "GRM TS kernel shares the KING TS tiling");
+constexpr uint32_t kGtsAccCols = (kGrmLimbs + 1) * kGrmTileCols;          // 480
+constexpr uint32_t kGtsASlots = 2;
+constexpr uint32_t kGtsASlotCols = 16;
+constexpr uint32_t kGtsStagesJ = 3;
+constexpr uint32_t kGtsLboJ = kGrmPlanesJ * kGrmGroupsJ * kCoreBytes + 64;  // 7104: +64 keeps the K-permuted rows bank-conflict free
+constexpr uint32_t kGtsStageBytesJ = (kGrmKc / 8) * kGtsLboJ;               // 56832
+constexpr uint32_t kGtsSmemBytes = kGtsStagesJ * kGtsStageBytesJ + 1024;
+constexpr uint32_t kGtsRowWarps = 8;
+constexpr uint32_t kGtsColWarps = 10;                                       // 5 words x 64 variants per stage
+constexpr uint32_t kGtsThreads = 32 * (kGtsRowWarps + kGtsColWarps + 1);
+static_assert(kGtsSmemBytes <= 232448, "GRM TS pipeline exceeds the 227 KB shared-memory opt-in limit");
+static_assert(kGtsAccCols + kGtsASlots * kGtsASlotCols <= 512, "GRM TS accumulators + A slots exceed TMEM");
+
+__global__ void __launch_bounds__(kGtsThreads, 1)
+grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw_i, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tab, double inv_scale, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, double* __restrict__ acc_g, int32_t* __restrict__ acc_obs) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ __align__(8) uint64_t bar_full_a[kGtsASlots];
+  __shared__ __align__(8) uint64_t bar_empty_a[kGtsASlots];
+  __shared__ __align__(8) uint64_t bar_full_b[kGtsStagesJ];
+  __shared__ __align__(8) uint64_t bar_empty_b[kGtsStagesJ];
+  __shared__ __align__(8) uint64_t bar_acc;
+  __shared__ uint32_t tmem_base_slot;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = uniform_warp_idx();
+  const uint32_t lane = tid & 31;
+  const uint32_t tile = tile_order[blockIdx.x];
+  const uint32_t rt = tile_rt[tile];
+  const uint32_t ct = tile_tc[tile];
+  const uint32_t stage_iters = variant_ct_padded / kGrmKc;
+  const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < kGtsASlots; ++s) {
+      mbar_init(&bar_full_a[s], 4);  // one arrival per row-side warp of the owning group
+      mbar_init(&bar_empty_a[s], 1);
+    }
+    for (uint32_t s = 0; s < kGtsStagesJ; ++s) {
+      mbar_init(&bar_full_b[s], kGtsColWarps);
+      mbar_init(&bar_empty_b[s], 1);
+    }
+    mbar_init(&bar_acc, 1);
+    mbar_fence_init();
+  }
+  if (warp == kGtsRowWarps + kGtsColWarps) tmem_alloc<512>(&tmem_base_slot);
+  tc_fence_before_sync();
+  __syncthreads();
+  tc_fence_after_sync();
+  const uint32_t tmem_base = tmem_base_slot;
+
+  if (warp < kGtsRowWarps) {
+    // ---------------- row-side producers: 2-bit words -> registers -> tensor memory ----------------
+    // Group g = warp / 4 owns k-steps ks = 2 n + g and A slot g.  Thread = TMEM lane = sample.
+    const uint32_t grp = warp >> 2;
+    const uint32_t lq = warp & 3;
+    const uint32_t row = 32 * lq + lane;
+    const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt) * (2 * stage_iters) * 1024 + row * 8;
+    const uint32_t ta = tmem_base + ((32u * lq) << 16) + kGtsAccCols + grp * kGtsASlotCols;
+    auto load_i = [&](uint32_t n) -> uint2 {
+      return (n < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 1024ull * (2 * n + grp))) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
+    };
+    struct ExpI {
+      uint32_t v[2][8];
+    };
+    auto expand_i = [&](const uint2& w) -> ExpI {
+      ExpI e;
+      const Sel4 s0 = make_selectors(w.x), s1 = make_selectors(w.y);
+      const uint32_t tabs[2] = {kTabDosage, kTabNonmiss};
+#pragma unroll
+      for (int p = 0; p < 2; ++p) {
+        const uint4 a = expand16(tabs[p], s0), b = expand16(tabs[p], s1);
+        e.v[p][0] = a.x; e.v[p][1] = a.y; e.v[p][2] = a.z; e.v[p][3] = a.w;
+        e.v[p][4] = b.x; e.v[p][5] = b.y; e.v[p][6] = b.z; e.v[p][7] = b.w;
+      }
+      return e;
+    };
+    constexpr uint32_t kLa = 4;
+    uint2 pre_i[kLa];
+#pragma unroll
+    for (uint32_t d = 0; d < kLa; ++d) pre_i[d] = load_i(d);
+    ExpI cur = expand_i(pre_i[0]);
+    for (uint32_t n0 = 0; n0 < stage_iters; n0 += kLa) {  // stage_iters is a multiple of 4 (variant pad 256)
+#pragma unroll
+      for (uint32_t d = 0; d < kLa; ++d) {
+        const uint32_t n = n0 + d;
+        pre_i[d] = load_i(n + kLa);
+        mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
+        tc_fence_after_sync();
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[grp], lane);
+        cur = expand_i(pre_i[(d + 1) % kLa]);
+      }
+    }
+  } else if (warp < kGtsRowWarps + kGtsColWarps) {
+    // ---------------- column-side producers: 2-bit words -> 11 int8 planes in shared memory ----------------
+    // Thread = (word w of the 20-byte row, variant k of the 64-variant stage); the per-variant digit
+    // tables come from grm_tables_kernel.
+    const uint32_t t = tid - 32 * kGtsRowWarps;  // 0..319
+    const uint32_t k = t & 63;
+    const uint32_t w = t >> 6;
+    const uint8_t* src_j = raw_j + static_cast<uint64_t>(ct) * stage_iters * (kGrmKc * 20) + k * 20 + 4 * w;
+    const uint32_t* tab_k = tab + static_cast<uint64_t>(k) * kGrmTabStride;
+    const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);  // K rows in the PRMT position order of the row side
+    const uint32_t dst_k = (kpos >> 3) * kGtsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
+    struct RowJ {
+      uint32_t w;
+      uint4 t0, t1, t2;  // tables of planes 0..3, 4..7, 8..10
+    };
+    auto load_j = [&](uint32_t it) -> RowJ {
+      RowJ r;
+      r.w = 0xFFFFFFFFu;
+      r.t0 = r.t1 = r.t2 = make_uint4(0, 0, 0, 0);
+      if (it < stage_iters) {
+        r.w = __ldg(reinterpret_cast<const uint32_t*>(src_j + static_cast<uint64_t>(it) * (kGrmKc * 20)));
+        const uint4* tp = reinterpret_cast<const uint4*>(tab_k + static_cast<uint64_t>(it) * kGrmKc * kGrmTabStride);
+        r.t0 = __ldg(tp);
+        r.t1 = __ldg(tp + 1);
+        r.t2 = __ldg(tp + 2);
+      }
+      return r;
+    };
+    auto sts16 = [](uint32_t addr, const uint4& v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
+    constexpr uint32_t kLa = 2;
+    constexpr uint32_t kPlane = kGrmGroupsJ * kCoreBytes;  // 640 bytes between planes inside a k-group
+    RowJ pre_j[kLa];
+#pragma unroll
+    for (uint32_t d = 0; d < kLa; ++d) pre_j[d] = load_j(d);
+    uint32_t sb = 0, ph = 0;
+    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kLa) {
+#pragma unroll
+      for (uint32_t d = 0; d < kLa; ++d) {
+        const uint32_t it = it0 + d;
+        const RowJ cur = pre_j[d];
+        pre_j[d] = load_j(it + kLa);
+        const Sel4 sel = make_selectors(cur.w);
+        mbar_wait(&bar_empty_b[sb], ph ^ 1);
+        const uint32_t a0 = smem_base + sb * kGtsStageBytesJ + dst_k;
+        sts16(a0 + 0 * kPlane, expand16(cur.t0.x, sel));
+        sts16(a0 + 1 * kPlane, expand16(cur.t0.y, sel));
+        sts16(a0 + 2 * kPlane, expand16(cur.t0.z, sel));
+        sts16(a0 + 3 * kPlane, expand16(cur.t0.w, sel));
+        sts16(a0 + 4 * kPlane, expand16(cur.t1.x, sel));
+        sts16(a0 + 5 * kPlane, expand16(cur.t1.y, sel));
+        sts16(a0 + 6 * kPlane, expand16(cur.t1.z, sel));
+        sts16(a0 + 7 * kPlane, expand16(cur.t1.w, sel));
+        sts16(a0 + 8 * kPlane, expand16(cur.t2.x, sel));
+        sts16(a0 + 9 * kPlane, expand16(cur.t2.y, sel));
+        sts16(a0 + 10 * kPlane, expand16(cur.t2.z, sel));
+        fence_proxy_async_smem();
+        mbar_arrive_warp(&bar_full_b[sb], lane);
+        if (++sb == kGtsStagesJ) {
+          sb = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else {
+    // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
+    constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kGrmTileCols, false, true);
+    constexpr uint32_t idesc_n80 = make_idesc_i8(128, kGrmTileCols, false, true);
+    constexpr uint32_t kPlaneStep = (kGrmGroupsJ * kCoreBytes) >> 4;  // plane step in descriptor units
+    const uint32_t tmem_u = uniform_u32(tmem_base);
+    const uint64_t desc0 = make_smem_desc(smem_base, kGtsLboJ, kCoreBytes);
+    uint32_t sb = 0, ph = 0;
+    for (uint32_t it = 0; it < stage_iters; ++it) {
+      mbar_wait(&bar_full_b[sb], ph);
+#pragma unroll
+      for (uint32_t kk = 0; kk < 2; ++kk) {
+        // k-step ks = 2 it + kk lives in A slot kk, round it
+        mbar_wait(&bar_full_a[kk], it & 1);
+        tc_fence_after_sync();
+        if (elect_one_sync()) {
+          const uint32_t acc = (it | kk) ? 1u : 0u;  // 0 only on the very first k-step
+          const uint64_t bj = desc0 + ((sb * kGtsStageBytesJ + kk * 4 * kGtsLboJ) >> 4);
+          const uint32_t a_g = tmem_u + kGtsAccCols + kk * kGtsASlotCols;
+          const uint32_t a_m = a_g + 8;
+          umma_i8_ts(tmem_u + 0, a_m, bj + 5 * kPlaneStep, idesc_n160, acc);                    // m x [d2_0 d2_1]
+          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_m, bj + 7 * kPlaneStep, idesc_n160, acc);     // m x [d2_2 d2_3]
+          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_m, bj + 9 * kPlaneStep, idesc_n160, acc);     // m x [d2_4 | m] -> D_4, obs
+          umma_i8_ts(tmem_u + 0, a_g, bj, idesc_n160, 1u);                                        // g x [d1_0 d1_1]
+          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_g, bj + 2 * kPlaneStep, idesc_n160, 1u);        // g x [d1_2 d1_3]
+          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_g, bj + 4 * kPlaneStep, idesc_n80, 1u);         // g x d1_4
+          umma_commit(&bar_empty_a[kk]);
+          if (kk == 1) umma_commit(&bar_empty_b[sb]);
+        }
+        __syncwarp();
+      }
+      if (++sb == kGtsStagesJ) {
+        sb = 0;
+        ph ^= 1;
+      }
+    }
+    if (elect_one_sync()) umma_commit(&bar_acc);
+    __syncwarp();
+  }
+
+  if (warp < kGtsRowWarps) {
+    // ---------------- epilogue: digits -> fp64, += into the HBM accumulators ----------------
+    mbar_wait(&bar_acc, 0);
+    tc_fence_after_sync();
+    const uint32_t lane_grp = warp & 3;
+    const uint32_t rsample = 32 * lane_grp + lane;  // rows are in natural sample order here
+    double* g_tile = acc_g + static_cast<uint64_t>(tile) * kGrmTileWords + rsample;
+    int32_t* o_tile = acc_obs + static_cast<uint64_t>(tile) * kGrmTileWords + rsample;
+    const uint32_t taddr = tmem_base + ((32u * lane_grp) << 16);
+    // 5 column groups of 16: warps 0-3 take groups {0,2,4}, warps 4-7 take {1,3}
+#pragma unroll 1
+    for (uint32_t grp = warp >> 2; grp < kGrmGroupsJ; grp += 2) {
+      const uint32_t c0 = grp * 16;
+      uint32_t d0[16], d1[16], d2[16], d3[16], d4[16], nn[16];
+      tmem_ld16(taddr + c0, d0);
+      tmem_ld16(taddr + kGrmTileCols + c0, d1);
+      tmem_ld16(taddr + 2 * kGrmTileCols + c0, d2);
+      tmem_ld16(taddr + 3 * kGrmTileCols + c0, d3);
+      tmem_ld16(taddr + 4 * kGrmTileCols + c0, d4);
+      tmem_ld16(taddr + 5 * kGrmTileCols + c0, nn);
+      tmem_ld_wait();
+#pragma unroll
+      for (uint32_t c = 0; c < 16; ++c) {
+        const uint32_t csample = c0 + PosToSample(c);
+        const long long tot = static_cast<long long>(static_cast<int32_t>(d0[c])) + (static_cast<long long>(static_cast<int32_t>(d1[c])) << 8) +
+                              (static_cast<long long>(static_cast<int32_t>(d2[c])) << 16) + (static_cast<long long>(static_cast<int32_t>(d3[c])) << 24) +
+                              (static_cast<long long>(static_cast<int32_t>(d4[c])) << 32);
+        g_tile[static_cast<uint64_t>(csample) * kTileRows] += static_cast<double>(tot) * inv_scale;
+        o_tile[static_cast<uint64_t>(csample) * kTileRows] += static_cast<int32_t>(nn[c]);
+      }
+    }
+    tc_fence_before_sync();
+  }
+  __syncthreads();
+  if (warp == kGtsRowWarps + kGtsColWarps) {
+    tc_fence_after_sync();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace pl2
