@@ -120,14 +120,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- reference CPU arm
-def run_reference_sample(n, m, threads, workdir, keep_input=None):
+def run_reference_sample(n, m, threads, workdir, keep_input=None, binary=None):
     """Times the unmodified reference binary on an n x m synthetic .bed: `--make-king-table` with a
     table filter so the text output stays small (the N^2 M/64 popcount loop is unaffected).
     Returns (seconds, pair_snp_per_s)."""
     import numpy as np
     import torch
 
-    plink2 = os.path.join(ROOT, "oracle", "_ref", "plink2")
+    plink2 = binary or os.path.join(ROOT, "oracle", "_ref", "plink2")
     if not os.path.exists(plink2):
         raise FileNotFoundError(f"{plink2} missing (oracle/build_ref.sh builds it where /root/reference exists)")
     prefix = keep_input or os.path.join(workdir, f"cpu_{n}_{m}")
@@ -153,7 +153,7 @@ def run_reference_sample(n, m, threads, workdir, keep_input=None):
         with open(prefix + ".fam", "w") as f:
             f.write("".join(f"0\tper{k}\t0\t0\t2\t-9\n" for k in range(n)))
     t0 = time.perf_counter()
-    r = subprocess.run([plink2, "--bfile", prefix, "--make-king-table", "--king-table-filter", "0.35", "--threads", str(threads), "--memory", "64000", "--out", prefix + "_out"], capture_output=True, text=True)
+    r = subprocess.run([plink2, "--bfile", prefix, "--make-king-table", "--king-table-filter", "0.35", "--threads", str(threads), "--memory", "64000", "--out", prefix + ("_out" if binary is None else "_b200")], capture_output=True, text=True)
     dt = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError("reference binary failed: " + r.stdout[-500:] + r.stderr[-500:])
@@ -340,6 +340,7 @@ def b200_arm(args):
         roofline["note"] = "popcount kernel: int8-equivalent ops shown for comparability; its own limiter is the POPC pipe"
 
     cpu_baseline = None
+    cli = None
     if world == 1 and not args.no_cpu_baseline:
         try:
             tmp = tempfile.mkdtemp(prefix="pl2cpu_")
@@ -347,6 +348,16 @@ def b200_arm(args):
             dt, rate = run_reference_sample(args.cpu_samples, args.cpu_variants, threads, tmp)
             cpu_baseline = {"value": rate / 1e6, "unit": UNIT, "cores": threads, "kind": "reference", "seconds": dt,
                             "sample": f"{args.cpu_samples} samples x {args.cpu_variants} variants, one whole `plink2 --make-king-table --threads {threads}` run (incl. .bed load) of oracle/_ref/plink2"}
+            # the same command line through OUR host program (the drop-in face), same files, outputs compared byte for byte
+            try:
+                ours = os.path.join(ROOT, "plink_ng_b200", "plink2_b200")
+                dt2, rate2 = run_reference_sample(args.cpu_samples, args.cpu_variants, threads, tmp, binary=ours)
+                pre = os.path.join(tmp, f"cpu_{args.cpu_samples}_{args.cpu_variants}")
+                same = open(pre + "_out.kin0", "rb").read() == open(pre + "_b200.kin0", "rb").read()
+                cli = {"seconds": dt2, "value": rate2 / 1e6, "unit": UNIT, "speedup_vs_reference_run": dt / dt2, "kin0_identical_to_reference": same,
+                       "command": "plink2_b200 --bfile <same> --make-king-table --king-table-filter 0.35 (process start to exit: CUDA init, .bed load, H2D, kernels, table write)"}
+            except Exception as ex:
+                cli = {"error": str(ex)[-300:]}
             shutil.rmtree(tmp, ignore_errors=True)
         except Exception as ex:  # the baseline is reported, never silently faked
             cpu_baseline = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"unavailable: {ex}"}
@@ -358,7 +369,7 @@ def b200_arm(args):
         "config": {"workload": f"--make-king, {n} samples x {FULL_M} SNPs in steps of {mb} variants", "samples": n, "variants_per_step": mb, "steps_per_full_job": FULL_M // mb,
                    "parallelism": f"row-block x{world} (ParallelBounds), 1 all_gather/step" if world > 1 else "single GPU", "algo": args.algo,
                    "l2_policy": "inputs (1.6 GB batch + accumulators) exceed L2; no flush needed", "pair_snp_per_s": total_pairs * mb / (step_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps},
-        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "cli_same_files": cli, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

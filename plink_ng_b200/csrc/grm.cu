@@ -4,13 +4,12 @@
 #include <cstring>
 #include <vector>
 
-#include <cusolverDn.h>
-#include <dlfcn.h>
 
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "grm_kernels.cuh"
 #include "grm_ts_kernel.cuh"
+#include "jacobi.cuh"
 #include "ld_kernels.cuh"  // geno_counts_kernel
 
 using namespace pl2;
@@ -247,42 +246,41 @@ int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_gr
 
 uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job) { return job ? job->variants_added : 0; }
 
-// cuSOLVER is loaded on first use (dlopen): it and its cuBLAS dependencies are ~1 GB of shared
-// objects that the KING / GRM / LD commands never need.
+}  // extern "C" (reopened below)
+
+// ---- dense symmetric helpers for the exact-PCA eigensolve (jacobi.cuh) ----
 namespace {
-struct CusolverApi {
-  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
-  cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
-  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
-  cusolverStatus_t (*syevdx_bufsize)(cusolverDnHandle_t, cusolverEigMode_t, cusolverEigRange_t, cublasFillMode_t, int, const double*, int, double, double, int, int, int*, const double*, int*) = nullptr;
-  cusolverStatus_t (*syevdx)(cusolverDnHandle_t, cusolverEigMode_t, cusolverEigRange_t, cublasFillMode_t, int, double*, int, double, double, int, int, int*, double*, double*, int, int*) = nullptr;
-  bool ok = false;
-};
-CusolverApi* LoadCusolver() {
-  static CusolverApi api;
-  static bool tried = false;
-  if (tried) return api.ok ? &api : nullptr;
-  tried = true;
-  void* h = nullptr;
-  for (const char* name : {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"}) {
-    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-    if (h) break;
+// get_rows fills the row-major lower triangle (= column-major upper); mirror it.
+__global__ void symmetrize_kernel(double* __restrict__ a, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+  if (i < n && i > j) a[static_cast<uint64_t>(j) * n + i] = a[static_cast<uint64_t>(i) * n + j];
+}
+// per column: Gershgorin excess sum_{i != j} |a_ij| - a_jj, or NaN when the column holds a non-finite entry
+__global__ void gershgorin_kernel(const double* __restrict__ a, uint32_t n, double* __restrict__ excess) {
+  __shared__ double red[8];
+  const uint32_t j = blockIdx.x;
+  double sum = 0.0;
+  for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+    const double v = a[static_cast<uint64_t>(j) * n + i];
+    sum += (i == j) ? -v : fabs(v);  // NaN / inf propagate
   }
-  if (!h) return nullptr;
-  api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cusolverDnCreate"));
-  api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cusolverDnDestroy"));
-  api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cusolverDnSetStream"));
-  api.syevdx_bufsize = reinterpret_cast<decltype(api.syevdx_bufsize)>(dlsym(h, "cusolverDnDsyevdx_bufferSize"));
-  api.syevdx = reinterpret_cast<decltype(api.syevdx)>(dlsym(h, "cusolverDnDsyevdx"));
-  api.ok = api.create && api.destroy && api.set_stream && api.syevdx_bufsize && api.syevdx;
-  return api.ok ? &api : nullptr;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (uint32_t w = 0; w < blockDim.x / 32; ++w) t += red[w];
+    excess[j] = t;
+  }
+}
+__global__ void add_diagonal_kernel(double* __restrict__ a, uint32_t n, double mu) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[static_cast<uint64_t>(i) * n + i] += mu;
 }
 }  // namespace
 
-// Exact --pca: top-k eigenpairs of the finished GRM (CalcPca non-approx branch,
-// plink2_matrix_calc.cc:5942-6040, which calls LAPACK dsyevr through ExtractEigvecs,
-// plink2_matrix.cc:1089-1104).  The dense symmetric eigensolver is a library call here as well
-// (cuSOLVER syevdx); it is not part of the pairwise hot path.
+extern "C" {
+
 int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, double* eigvecs_host) {
   if (!job || !pc_ct) {
     set_error("pl2gpu_grm_eigen_topk: bad arguments");
@@ -301,76 +299,60 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
     set_error("pl2gpu_grm_eigen_topk: exact PCA is limited to 46340 samples; use --pca approx");
     return 1;
   }
-  CusolverApi* cs = LoadCusolver();
-  if (!cs) {
-    set_error("pl2gpu_grm_eigen_topk: libcusolver.so.11 could not be loaded (%s)", dlerror());
-    return 1;
-  }
   Ctx* c = &job->ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
-  double* d_a = nullptr;
-  double* d_w = nullptr;
-  double* d_work = nullptr;
-  int* d_info = nullptr;
-  cusolverDnHandle_t h = nullptr;
+  // Top eigenpairs of the symmetric GRM by one-sided Jacobi on the shifted matrix G + mu I (mu = the
+  // Gershgorin bound that makes it positive semi-definite, so singular values = eigenvalues + mu in
+  // the same order and the unit columns of (G + mu I) V are the eigenvectors).  Replaces dsyevr (:5943-6039).
+  double *d_a = nullptr, *d_u = nullptr, *d_ex = nullptr;
   int rc = 1;
   do {
-    if (cudaMalloc(&d_a, static_cast<uint64_t>(n) * n * 8) != cudaSuccess || cudaMalloc(&d_w, static_cast<uint64_t>(n) * 8) != cudaSuccess || cudaMalloc(&d_info, 4) != cudaSuccess) {
+    if (cudaMalloc(&d_a, static_cast<uint64_t>(n) * n * 8) != cudaSuccess || cudaMalloc(&d_u, static_cast<uint64_t>(n) * pc_ct * 8) != cudaSuccess || cudaMalloc(&d_ex, 8ull * n) != cudaSuccess) {
       cudaGetLastError();
       set_error("pl2gpu_grm_eigen_topk: insufficient device memory for a dense %u x %u matrix", n, n);
       break;
     }
     if (cudaMemsetAsync(d_a, 0, static_cast<uint64_t>(n) * n * 8, c->stream) != cudaSuccess) break;
-    // row-major lower triangle == column-major upper triangle
-    if (pl2gpu_grm_get_rows(job, 0, n, d_a, nullptr, n, 1)) break;
-    if (cs->create(&h) != CUSOLVER_STATUS_SUCCESS || cs->set_stream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
-      set_error("pl2gpu_grm_eigen_topk: cusolverDnCreate failed");
-      break;
-    }
-    int lwork = 0, meig = 0;
-    const int il = static_cast<int>(n - pc_ct + 1), iu = static_cast<int>(n);
-    if (cs->syevdx_bufsize(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, &lwork) != CUSOLVER_STATUS_SUCCESS) {
-      set_error("pl2gpu_grm_eigen_topk: syevdx workspace query failed");
-      break;
-    }
-    if (cudaMalloc(&d_work, static_cast<uint64_t>(lwork) * 8) != cudaSuccess) {
-      cudaGetLastError();
-      set_error("pl2gpu_grm_eigen_topk: insufficient device memory for the eigensolver workspace");
-      break;
-    }
-    const cusolverStatus_t st = cs->syevdx(h, CUSOLVER_EIG_MODE_VECTOR, CUSOLVER_EIG_RANGE_I, CUBLAS_FILL_MODE_UPPER, static_cast<int>(n), d_a, static_cast<int>(n), 0.0, 0.0, il, iu, &meig, d_w, d_work, lwork, d_info);
-    c->launches++;
-    int info = 0;
-    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    if (pl2gpu_grm_get_rows(job, 0, n, d_a, nullptr, n, 1)) break;  // row-major lower triangle == column-major upper
+    symmetrize_kernel<<<dim3(DivUpU32(n, 256), n), 256, 0, c->stream>>>(d_a, n);
+    gershgorin_kernel<<<n, 256, 0, c->stream>>>(d_a, n, d_ex);
+    c->launches += 2;
+    std::vector<double> ex(n);
+    if (cudaMemcpyAsync(ex.data(), d_ex, 8ull * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
       set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }
-    if (st != CUSOLVER_STATUS_SUCCESS || info != 0 || meig != static_cast<int>(pc_ct)) {
-      set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (status %d, info %d, %d eigenvalues); the GRM may contain missing values", static_cast<int>(st), info, meig);
-      break;
-    }
-    std::vector<double> w(pc_ct), v(static_cast<uint64_t>(pc_ct) * n);
-    if (cudaMemcpy(w.data(), d_w, 8ull * pc_ct, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(v.data(), d_a, 8ull * pc_ct * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
-      set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
-      break;
-    }
+    double mu = 0.0;
     bool finite = true;
-    for (uint32_t k = 0; k < pc_ct; ++k) {  // ascending -> descending (:6024-6039)
-      eigvals_host[k] = w[pc_ct - 1 - k];
-      finite = finite && std::isfinite(eigvals_host[k]);
-      memcpy(eigvecs_host + static_cast<uint64_t>(k) * n, v.data() + static_cast<uint64_t>(pc_ct - 1 - k) * n, 8ull * n);
+    for (uint32_t j = 0; j < n; ++j) {
+      finite = finite && std::isfinite(ex[j]);
+      mu = std::max(mu, ex[j]);
     }
     if (!finite) {
       set_error("pl2gpu_grm_eigen_topk: GRM contains missing values (a sample pair has no jointly observed variant)");
       break;
     }
+    if (mu > 0.0) {
+      add_diagonal_kernel<<<DivUpU32(n, 256), 256, 0, c->stream>>>(d_a, n, mu);
+      c->launches++;
+    }
+    std::vector<double> sigma(pc_ct);
+    const char* err = nullptr;
+    uint32_t sweeps = 0;
+    if (JacobiSvd(c, d_a, n, n, n, pc_ct, sigma.data(), d_u, n, &sweeps, &err)) {
+      set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (%s)", err ? err : "?");
+      break;
+    }
+    if (cudaMemcpy(eigvecs_host, d_u, 8ull * pc_ct * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    for (uint32_t k = 0; k < pc_ct; ++k) eigvals_host[k] = sigma[k] - mu;  // descending (:6024-6039)
     rc = 0;
   } while (0);
-  if (h) cs->destroy(h);
   cudaFree(d_a);
-  cudaFree(d_w);
-  cudaFree(d_work);
-  cudaFree(d_info);
+  cudaFree(d_u);
+  cudaFree(d_ex);
   return rc;
 }
 

@@ -2,52 +2,22 @@
 // EIGENSOFT-style randomized range finder (Halko et al. 2011; Galinsky et al. 2016) on the resident
 // 2-bit genotype matrix.  Gaussian start matrix is supplied by the caller (the host program
 // reproduces the reference's SFMT / Box-Muller stream, host/sfmt.cc).
-#include <dlfcn.h>
-
 #include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
 
-#include <cusolverDn.h>
-
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "ld_kernels.cuh"    // geno_counts_kernel
 #include "pca_kernels.cuh"
+#include "jacobi.cuh"
 
 using namespace pl2;
 
 namespace {
 constexpr double kSmallEpsilon = 1.0 / 17592186044416.0;
 
-struct GesvdApi {
-  cusolverStatus_t (*create)(cusolverDnHandle_t*) = nullptr;
-  cusolverStatus_t (*destroy)(cusolverDnHandle_t) = nullptr;
-  cusolverStatus_t (*set_stream)(cusolverDnHandle_t, cudaStream_t) = nullptr;
-  cusolverStatus_t (*gesvd_bufsize)(cusolverDnHandle_t, int, int, int*) = nullptr;
-  cusolverStatus_t (*gesvd)(cusolverDnHandle_t, signed char, signed char, int, int, double*, int, double*, double*, int, double*, int, double*, int, double*, int*) = nullptr;
-  bool ok = false;
-};
-GesvdApi* LoadGesvd() {
-  static GesvdApi api;
-  static bool tried = false;
-  if (tried) return api.ok ? &api : nullptr;
-  tried = true;
-  void* h = nullptr;
-  for (const char* name : {"libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"}) {
-    h = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
-    if (h) break;
-  }
-  if (!h) return nullptr;
-  api.create = reinterpret_cast<decltype(api.create)>(dlsym(h, "cusolverDnCreate"));
-  api.destroy = reinterpret_cast<decltype(api.destroy)>(dlsym(h, "cusolverDnDestroy"));
-  api.set_stream = reinterpret_cast<decltype(api.set_stream)>(dlsym(h, "cusolverDnSetStream"));
-  api.gesvd_bufsize = reinterpret_cast<decltype(api.gesvd_bufsize)>(dlsym(h, "cusolverDnDgesvd_bufferSize"));
-  api.gesvd = reinterpret_cast<decltype(api.gesvd)>(dlsym(h, "cusolverDnDgesvd"));
-  api.ok = api.create && api.destroy && api.set_stream && api.gesvd_bufsize && api.gesvd;
-  return api.ok ? &api : nullptr;
-}
 }  // namespace
 
 struct Pl2PcaJob {
@@ -160,11 +130,6 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     set_error("pl2gpu_pca_run: bad arguments");
     return 1;
   }
-  GesvdApi* cs = LoadGesvd();
-  if (!cs) {
-    set_error("pl2gpu_pca_run: libcusolver.so.11 could not be loaded");
-    return 1;
-  }
   Ctx* c = &job->ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
   const uint32_t n = job->sample_ct, npad = job->sample_ct_padded, m = job->variant_ct, k = job->pc_ct;
@@ -174,9 +139,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     set_error("pl2gpu_pca_run: need 2k(k+1) = %llu <= min(variants %u, samples %u)", static_cast<unsigned long long>(q), m, n);
     return 1;
   }
-  double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr, *d_s = nullptr, *d_work = nullptr;
-  int* d_info = nullptr;
-  cusolverDnHandle_t h = nullptr;
+  double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr;
   int rc = 1;
   const double m_recip = 1.0 / static_cast<double>(m);
   auto launch_xa = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
@@ -195,7 +158,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   };
   do {
     if (cudaMalloc(&d_qq, static_cast<uint64_t>(m) * q * 8) != cudaSuccess || cudaMalloc(&d_u, static_cast<uint64_t>(std::max(m, n)) * q * 8) != cudaSuccess || cudaMalloc(&d_g1, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess ||
-        cudaMalloc(&d_g2, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess || cudaMalloc(&d_b, static_cast<uint64_t>(n) * q * 8) != cudaSuccess || cudaMalloc(&d_s, q * 8) != cudaSuccess || cudaMalloc(&d_info, 4) != cudaSuccess) {
+        cudaMalloc(&d_g2, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess || cudaMalloc(&d_b, static_cast<uint64_t>(n) * q * 8) != cudaSuccess ) {
       cudaGetLastError();
       set_error("pl2gpu_pca_run: insufficient device memory for the %u x %llu Krylov matrix", m, static_cast<unsigned long long>(q));
       break;
@@ -216,54 +179,34 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       set_error("pl2gpu_pca_run: kernel launch failed");
       break;
     }
-    if (cs->create(&h) != CUSOLVER_STATUS_SUCCESS || cs->set_stream(h, c->stream) != CUSOLVER_STATUS_SUCCESS) {
-      set_error("pl2gpu_pca_run: cusolverDnCreate failed");
-      break;
-    }
-    int lwork_a = 0, lwork_b = 0;
-    if (cs->gesvd_bufsize(h, static_cast<int>(m), static_cast<int>(q), &lwork_a) != CUSOLVER_STATUS_SUCCESS || cs->gesvd_bufsize(h, static_cast<int>(n), static_cast<int>(q), &lwork_b) != CUSOLVER_STATUS_SUCCESS) {
-      set_error("pl2gpu_pca_run: gesvd workspace query failed");
-      break;
-    }
-    const int lwork = std::max(lwork_a, lwork_b);
-    if (cudaMalloc(&d_work, static_cast<uint64_t>(lwork) * 8) != cudaSuccess) {
-      cudaGetLastError();
-      set_error("pl2gpu_pca_run: insufficient device memory for the SVD workspace");
-      break;
-    }
     // SVD of the Krylov matrix: left singular vectors = orthonormal basis Q of its range   :5860
-    cusolverStatus_t st = cs->gesvd(h, 'S', 'N', static_cast<int>(m), static_cast<int>(q), d_qq, static_cast<int>(m), d_s, d_u, static_cast<int>(m), nullptr, static_cast<int>(q), d_work, lwork, nullptr, d_info);
-    int info = 0;
-    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || st != CUSOLVER_STATUS_SUCCESS || info) {
-      set_error("Failed to compute SVD of Krylov matrix (cusolver status %d, info=%d).", static_cast<int>(st), info);
+    // (one-sided Jacobi, jacobi.cuh; the reference calls dgesvd)
+    std::vector<double> s(q);
+    const char* err = nullptr;
+    if (JacobiSvd(c, d_qq, m, m, static_cast<uint32_t>(q), static_cast<uint32_t>(q), s.data(), d_u, m, nullptr, &err)) {
+      set_error("Failed to compute SVD of Krylov matrix (%s).", err ? err : "?");
       break;
     }
     // B = Y^T Q (N x q, column-major)   :5870-5916
     if (cudaMemsetAsync(d_b, 0, static_cast<uint64_t>(n) * q * 8, c->stream) != cudaSuccess) break;
     launch_xtb(d_u, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
-    // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B
-    st = cs->gesvd(h, 'S', 'N', static_cast<int>(n), static_cast<int>(q), d_b, static_cast<int>(n), d_s, d_u, static_cast<int>(n), nullptr, static_cast<int>(q), d_work, lwork, nullptr, d_info);
-    if (cudaMemcpyAsync(&info, d_info, 4, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess || st != CUSOLVER_STATUS_SUCCESS || info) {
-      set_error("Failed to compute SVD of final matrix (cusolver status %d, info=%d).", static_cast<int>(st), info);
+    // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B   :5920
+    if (JacobiSvd(c, d_b, n, n, static_cast<uint32_t>(q), k, s.data(), d_u, n, nullptr, &err)) {
+      set_error("Failed to compute SVD of final matrix (%s).", err ? err : "?");
       break;
     }
-    std::vector<double> s(k);
-    if (cudaMemcpy(s.data(), d_s, 8ull * k, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
       set_error("pl2gpu_pca_run: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }
     for (uint32_t p = 0; p < k; ++p) eigvals_host[p] = s[p] * s[p] * m_recip;  // :5931
     rc = 0;
   } while (0);
-  if (h) cs->destroy(h);
   cudaFree(d_qq);
   cudaFree(d_u);
   cudaFree(d_g1);
   cudaFree(d_g2);
   cudaFree(d_b);
-  cudaFree(d_s);
-  cudaFree(d_work);
-  cudaFree(d_info);
   return rc;
 }
 
