@@ -29,7 +29,6 @@ struct Pl2GrmJob {
   uint32_t* d_tab = nullptr;
   uint8_t* d_raw_i = nullptr;  // row-side re-tiled copy of the staged block (geno_tile.cuh)
   uint8_t* d_raw_j = nullptr;  // column-side re-tiled copy
-  bool ss_form = false;        // PL2_GRM_SS=1: the older smem x smem kernel (cross-check only)
   double* d_lvals = nullptr;
   uint32_t* d_counts = nullptr;
   void* d_out_stage = nullptr;
@@ -53,7 +52,6 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
   PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
   static bool attr_set = false;
   if (!attr_set) {
-    PL2_CUDA_OK(cudaFuncSetAttribute(grm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGrmSmemBytes));
     PL2_CUDA_OK(cudaFuncSetAttribute(grm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGtsSmemBytes));
     attr_set = true;
   }
@@ -63,7 +61,6 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
   job->row_start = row_start;
   job->row_end = row_end;
   job->flags = flags;
-  job->ss_form = getenv("PL2_GRM_SS") != nullptr;
   auto fail = [&]() {
     pl2gpu_grm_end(job);
     return 1;
@@ -73,7 +70,7 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
   const uint64_t words = static_cast<uint64_t>(job->tiles.tile_ct) * kGrmTileWords;
   job->out_stage_bytes = 256ull << 20;
   if (cudaMalloc(&job->d_acc_g, words * 8 + 8) != cudaSuccess || cudaMalloc(&job->d_acc_obs, words * 4 + 4) != cudaSuccess ||
-      cudaMalloc(&job->d_tab, static_cast<uint64_t>(job->stage.variant_cap) * kGrmTabStride * 4) != cudaSuccess ||
+      cudaMalloc(&job->d_tab, static_cast<uint64_t>(job->stage.variant_cap) * kGrmTabPlanes * 4) != cudaSuccess ||
       cudaMalloc(&job->d_raw_i, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
       cudaMalloc(&job->d_raw_j, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
       cudaMalloc(&job->d_lvals, static_cast<uint64_t>(job->stage.variant_cap) * 6 * 8) != cudaSuccess ||
@@ -169,10 +166,7 @@ int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t varia
     grm_tables_kernel<<<DivUpU32(padded, 128), 128, 0, c->stream>>>(job->d_lvals, cur, padded, scale, job->d_tab);
     c->launches++;
     if (job->tiles.tile_ct) {
-      if (job->ss_form) {
-        grm_tc_kernel<<<job->tiles.tile_ct, kGrmThreads, kGrmSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->d_tab, inv_scale, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_acc_g, job->d_acc_obs);
-        c->launches++;
-      } else {
+      {
         const uint32_t coltile_ct = job->stage.sample_ct_padded / kTsCols;
         geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, job->d_raw_i);
         geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);

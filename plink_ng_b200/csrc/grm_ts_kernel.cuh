@@ -125,23 +125,23 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     const uint32_t k = t & 63;
     const uint32_t w = t >> 6;
     const uint8_t* src_j = raw_j + static_cast<uint64_t>(ct) * stage_iters * (kGrmKc * 20) + k * 20 + 4 * w;
-    const uint32_t* tab_k = tab + static_cast<uint64_t>(k) * kGrmTabStride;
+    const uint32_t* tab_k = tab + k;  // tab[stage][plane][64 variants] (grm_tab_index)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);  // K rows in the PRMT position order of the row side
     const uint32_t dst_k = (kpos >> 3) * kGtsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
     struct RowJ {
       uint32_t w;
-      uint4 t0, t1, t2;  // tables of planes 0..3, 4..7, 8..10
+      uint32_t t[kGrmPlanesJ];  // tables of planes 0..10
     };
     auto load_j = [&](uint32_t it) -> RowJ {
       RowJ r;
       r.w = 0xFFFFFFFFu;
-      r.t0 = r.t1 = r.t2 = make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (uint32_t p = 0; p < kGrmPlanesJ; ++p) r.t[p] = 0;
       if (it < stage_iters) {
         r.w = __ldg(reinterpret_cast<const uint32_t*>(src_j + static_cast<uint64_t>(it) * (kGrmKc * 20)));
-        const uint4* tp = reinterpret_cast<const uint4*>(tab_k + static_cast<uint64_t>(it) * kGrmKc * kGrmTabStride);
-        r.t0 = __ldg(tp);
-        r.t1 = __ldg(tp + 1);
-        r.t2 = __ldg(tp + 2);
+        const uint32_t* tp = tab_k + static_cast<uint64_t>(it) * (kGrmTabPlanes * 64);
+#pragma unroll
+        for (uint32_t p = 0; p < kGrmPlanesJ; ++p) r.t[p] = __ldg(tp + p * 64);
       }
       return r;
     };
@@ -161,17 +161,8 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
         const Sel4 sel = make_selectors(cur.w);
         mbar_wait(&bar_empty_b[sb], ph ^ 1);
         const uint32_t a0 = smem_base + sb * kGtsStageBytesJ + dst_k;
-        sts16(a0 + 0 * kPlane, expand16(cur.t0.x, sel));
-        sts16(a0 + 1 * kPlane, expand16(cur.t0.y, sel));
-        sts16(a0 + 2 * kPlane, expand16(cur.t0.z, sel));
-        sts16(a0 + 3 * kPlane, expand16(cur.t0.w, sel));
-        sts16(a0 + 4 * kPlane, expand16(cur.t1.x, sel));
-        sts16(a0 + 5 * kPlane, expand16(cur.t1.y, sel));
-        sts16(a0 + 6 * kPlane, expand16(cur.t1.z, sel));
-        sts16(a0 + 7 * kPlane, expand16(cur.t1.w, sel));
-        sts16(a0 + 8 * kPlane, expand16(cur.t2.x, sel));
-        sts16(a0 + 9 * kPlane, expand16(cur.t2.y, sel));
-        sts16(a0 + 10 * kPlane, expand16(cur.t2.z, sel));
+#pragma unroll
+        for (uint32_t p = 0; p < kGrmPlanesJ; ++p) sts16(a0 + p * kPlane, expand16(cur.t[p], sel));
         fence_proxy_async_smem();
         mbar_arrive_warp(&bar_full_b[sb], lane);
         if (++sb == kGtsStagesJ) {

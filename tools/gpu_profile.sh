@@ -13,7 +13,7 @@ tail -3 gpurun_out/launches_tensor.csv
 echo "== ncu full: king_ts_kernel"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:king_ts_kernel -s 1 -c 1 -f -o gpurun_out/prof_king_ts python bench.py $SMALL > gpurun_out/ncu_full_ts.log 2>&1; tail -2 gpurun_out/ncu_full_ts.log
 if [ -n "$PROFILE_GRM" ]; then
-echo "== ncu full: grm_tc_kernel"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:grm_tc_kernel -s 1 -c 1 -f -o gpurun_out/prof_grm_tc python tools/quick_king_bench.py 16384 65536 1 > gpurun_out/ncu_full_grm.log 2>&1; tail -4 gpurun_out/ncu_full_grm.log
+echo "== ncu full: grm_ts_kernel"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:grm_ts_kernel -s 1 -c 1 -f -o gpurun_out/prof_grm_ts python tools/quick_king_bench.py 16384 65536 1 > gpurun_out/ncu_full_grm.log 2>&1; tail -4 gpurun_out/ncu_full_grm.log
 fi
 ls -la gpurun_out
