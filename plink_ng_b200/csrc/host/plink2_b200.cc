@@ -60,7 +60,7 @@ struct Cmd {
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
   // GRM
-  bool make_grm_bin = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
+  bool make_grm_bin = false, make_grm_list = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
   // PCA
   bool pca = false, pca_approx = false, pca_meanimpute = false;
   uint32_t pc_ct = 10;
@@ -199,15 +199,17 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--king-cutoff") {
       if (nparam == 2) return Usage("--king-cutoff with a precomputed matrix prefix is not supported by plink2_b200.");
       if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
-    } else if (flag == "--make-grm-bin" || flag == "--make-rel") {
+    } else if (flag == "--make-grm-bin" || flag == "--make-grm-list" || flag == "--make-rel") {
       const bool is_rel = flag == "--make-rel";
-      (is_rel ? c->make_rel : c->make_grm_bin) = true;
+      (is_rel ? c->make_rel : (flag == "--make-grm-list" ? c->make_grm_list : c->make_grm_bin)) = true;
+      if (c->make_grm_bin && c->make_grm_list) return Usage("--make-grm-list cannot be used with --make-grm-bin.");
       bool shape_set = false;
       for (int k = 0; k < nparam; ++k) {
         const std::string m = prm[k];
         if (m == "cov") c->grm_cov = true;
         else if (m == "meanimpute") c->grm_meanimpute = true;
         else if (m == "id-header" && !is_rel) c->grm_id_header = true;
+        else if (m == "zs" && flag == "--make-grm-list") return Usage("--make-grm-list 'zs' output is not supported by plink2_b200.");
         else if (is_rel && m == "bin") c->rel_enc = Cmd::kBin;
         else if (is_rel && m == "bin4") c->rel_enc = Cmd::kBin4;
         else if (is_rel && m == "square") c->rel_shape = Cmd::kSq, shape_set = true;
@@ -284,7 +286,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     c->psam = pfile + ".psam";
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_rel || c->pca || c->indep_pairwise)) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_rel || c->pca || c->indep_pairwise)) return Usage("No command given.");
   return 0;
 }
 
@@ -873,7 +875,7 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   int rc = 0;
   const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
   if (rc) return rc;
-  const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
+  const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_grm_list && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
   Pl2GrmJob* job = nullptr;
   if (pl2gpu_grm_begin(ctx, n, r0, r1, flags, &job)) return GpuFail("pl2gpu_grm_begin");
   BlockStreamer bs(ds, &vidx, n, 32768);
@@ -932,6 +934,48 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     }
     if (!fg.Close() || !fn.Close()) return kRetWriteFail;
     std::string msg = std::string("--make-grm-bin: GRM ") + (c.parallel_tot != 1 ? "component " : "") + "written to " + gname + " , observation counts to " + nname;
+    if (!c.parallel_idx) {
+      const std::string idname = c.out + ".grm.id";
+      std::vector<uint32_t> all(n);
+      for (uint32_t k = 0; k < n; ++k) all[k] = k;
+      if (!WriteIdFile(idname, S, all, c.grm_id_header)) return kRetWriteFail;
+      msg += " , and IDs to " + idname;
+    }
+    logprintf("%s .\n", msg.c_str());
+  }
+  if (c.make_grm_list) {
+    // `.grm`: one line per pair i <= j, "j+1 <tab> i+1 <tab> observation count <tab> value" (2.0/plink2_matrix_calc.cc:5082-5106)
+    const std::string gname = PieceName(c.out + ".grm", c);
+    OutFile fg;
+    if (!fg.Open(gname)) return kRetOpenFail;
+    std::string line;
+    char num[64];
+    for (uint32_t a = r0; a < r1;) {
+      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      if (!fetch(a, b)) {
+        pl2gpu_grm_end(job);
+        return GpuFail("pl2gpu_grm_get_rows");
+      }
+      for (uint32_t j = a; j < b; ++j) {
+        const double* gr = &g[static_cast<uint64_t>(j - a) * stride];
+        const float* orow = &obs[static_cast<uint64_t>(j - a) * stride];
+        line.clear();
+        for (uint32_t i = 0; i <= j; ++i) {
+          line.append(num, u32toa(j + 1, num) - num);
+          line.push_back('\t');
+          line.append(num, u32toa(i + 1, num) - num);
+          line.push_back('\t');
+          line.append(num, u32toa(static_cast<uint32_t>(orow[i]), num) - num);
+          line.push_back('\t');
+          line.append(num, dtoa_g(gr[i], num) - num);
+          line.push_back('\n');
+        }
+        fg.Write(line.data(), line.size());
+      }
+      a = b;
+    }
+    if (!fg.Close()) return kRetWriteFail;
+    std::string msg = std::string("--make-grm-list: GRM ") + (c.parallel_tot != 1 ? "component " : "") + "written to " + gname;
     if (!c.parallel_idx) {
       const std::string idname = c.out + ".grm.id";
       std::vector<uint32_t> all(n);
@@ -1311,7 +1355,7 @@ int main(int argc, char** argv) {
   if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
     if (rc) return rc;
-    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_rel || c.pca || c.indep_pairwise)) {
+    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_grm_list || c.make_rel || c.pca || c.indep_pairwise)) {
       logprintf("Error: chaining --king-cutoff sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
       return kRetNotYetSupported;
     }
@@ -1319,7 +1363,7 @@ int main(int argc, char** argv) {
   Pl2GrmJob* grm_job = nullptr;
   std::vector<uint32_t> grm_vidx;
   const bool exact_pca = c.pca && !c.pca_approx;
-  if (c.make_grm_bin || c.make_rel || exact_pca) {
+  if (c.make_grm_bin || c.make_grm_list || c.make_rel || exact_pca) {
     if (exact_pca && c.parallel_tot != 1) {
       logprintf("Error: --pca cannot be used with --parallel.\n");
       return kRetInvalidCmdline;

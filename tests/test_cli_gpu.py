@@ -69,6 +69,23 @@ def test_make_grm_bin_files(golden_dir, tmp_path, inp):
         assert open(out + ".grm.id", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.id"), "rb").read()
 
 
+def test_make_grm_list_text(golden_dir, tmp_path):
+    """`.grm`: sample indices and observation counts byte-identical, values at dtoa_g's 6 significant digits."""
+    out = run(golden_dir, tmp_path, "--make-grm-list")
+    got = open(out + ".grm").read().split("\n")
+    ref = gz(golden_dir, "a_grml.grm.gz").decode().split("\n")
+    assert len(got) == len(ref) == 100 * 101 // 2 + 1
+    differing = 0
+    for a, b in zip(got, ref):
+        if a != b:
+            fa, fb = a.split("\t"), b.split("\t")
+            assert fa[:3] == fb[:3]
+            assert abs(float(fa[3]) - float(fb[3])) <= 1.2e-5 * abs(float(fb[3])) + 5e-10
+            differing += 1
+    assert differing < 0.01 * len(ref)
+    assert open(out + ".grm.id", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.id"), "rb").read()
+
+
 def test_make_rel_variants(golden_dir, tmp_path):
     out = run(golden_dir, tmp_path, "--make-rel", "cov", "bin4", "triangle")
     got = np.fromfile(out + ".rel.bin", dtype=np.float32)
