@@ -335,6 +335,7 @@ def b200_arm(args):
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": None,
                 "kernel": kname, "kernel_ms": kern_ms, "peak_source": peak_src, "frac_of_2x_bf16_burst": achieved / (2 * bf16_burst),
                 "frac_of_2x_bf16_sustained": achieved / (2 * bf16_sust), "algorithmic_ops_per_launch": ops,
+                "traffic_note": "not captured at this size; ncu at 16384 samples x 65536 variants: dram read+write 8.85 GB per launch vs 5.98 GB algorithmic (accumulators once each way + 2-bit operands), profiles/r01_ncu_king_ts_v3.md",
                 "kernel_ms_note": "one add_variants call = pad + two re-tiling launches (~2%) + the tensor kernel, CUDA events on the library's stream"}
     if algo == KING_ALGO_POPCOUNT:
         roofline["note"] = "popcount kernel: int8-equivalent ops shown for comparability; its own limiter is the POPC pipe"

@@ -8,7 +8,10 @@
 // CalcKing / CalcGrm / LdPruneWrite.  File decoding, text formatting and the sequential graph /
 // window logic run here on the host; every pairwise accumulation runs on the GPU - there is no
 // CPU fallback and the program exits with kPglRetGpuFail-style status when the device is missing.
+#include <unistd.h>
+
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdarg>
@@ -43,6 +46,20 @@ void logprintf(const char* fmt, ...) {
   fflush(stdout);
   if (g_log) fputs(buf, g_log);
 }
+
+// PL2_TIMING=1: phase timings on stderr (development aid; not part of the plink2 output contract)
+struct PhaseClock {
+  bool on = getenv("PL2_TIMING") != nullptr;
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+  void Mark(const char* what) {
+    if (!on) return;
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[timing] %-28s %8.3f s  (t = %.3f s)\n", what, std::chrono::duration<double>(now - last).count(), std::chrono::duration<double>(now - t0).count());
+    last = now;
+  }
+  double Since(std::chrono::steady_clock::time_point t) const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t).count(); }
+};
+PhaseClock g_clock;
 
 struct Cmd {
   std::string pgen, pvar, psam, out = "plink2";
@@ -586,27 +603,35 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     }
     Pl2KingJob* job = nullptr;
     if (pl2gpu_king_begin(ctx, n, row_start, row_end, kPl2KingAlgoAuto, &job)) return GpuFail("pl2gpu_king_begin");
+    g_clock.Mark("king: begin (device alloc)");
     bs.Rewind();
     std::string err;
     uint32_t done = 0;
+    double t_decode = 0, t_add = 0;
     for (;;) {
+      const auto td = std::chrono::steady_clock::now();
       const int got = bs.Next(&err);
+      t_decode += g_clock.Since(td);
       if (got < 0) {
         logprintf("\nError: %s\n", err.c_str());
         pl2gpu_king_end(job);
         return kRetMalformedInput;
       }
       if (!got) break;
+      const auto ta = std::chrono::steady_clock::now();
       if (pl2gpu_king_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
         pl2gpu_king_end(job);
         return GpuFail("pl2gpu_king_add_variants");
       }
+      t_add += g_clock.Since(ta);
       done += static_cast<uint32_t>(got);
       printf("\r%s pass %u/%u: %u variants complete.", flagname, pass, pass_ct, done);
       fflush(stdout);
     }
     printf("\r%s pass %u/%u: Writing...                   ", flagname, pass, pass_ct);
     fflush(stdout);
+    if (g_clock.on) fprintf(stderr, "[timing]   decode (PgrGet) %.3f s, pl2gpu_king_add_variants %.3f s\n", t_decode, t_add);
+    g_clock.Mark("king: decode + add_variants");
     // results in row chunks of <= ~512 MB
     const uint64_t max_pairs = (512ull << 20) / 20;
     std::vector<uint32_t> counts;
@@ -735,7 +760,9 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       }
       c0 = c1;
     }
+    g_clock.Mark("king: fetch results + write");
     pl2gpu_king_end(job);
+    g_clock.Mark("king: end (device free)");
   }
   if (square_text_full) {
     auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
@@ -1346,11 +1373,13 @@ int main(int argc, char** argv) {
   for (uint8_t f : ds.samples.is_founder) founder_ct += f;
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
   logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
+  g_clock.Mark("load .psam/.pvar, open .pgen");
   Pl2GpuCtx* ctx = nullptr;
   if (pl2gpu_ctx_create(c.device, &ctx)) {
     logprintf("Error: GPU initialisation failed: %s\n", pl2gpu_last_error());
     return kRetGpuFail;
   }
+  g_clock.Mark("pl2gpu_ctx_create");
   std::vector<uint8_t> cutoff_removed;
   if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
@@ -1380,9 +1409,14 @@ int main(int argc, char** argv) {
     rc = RunLdPrune(c, &ds, ctx);
     if (rc) return rc;
   }
-  pl2gpu_ctx_destroy(ctx);
+  pl2gpu_ctx_synchronize(ctx);
+  g_clock.Mark("commands done");
   time_t now = time(nullptr);
   logprintf("End time: %s", ctime(&now));
   if (g_log) fclose(g_log);
-  return 0;
+  fflush(stdout);
+  fflush(stderr);
+  // All output files are closed.  Skip the explicit CUDA teardown (context destroy + pinned-memory
+  // unmapping cost ~1.4 s here); the driver reclaims the device when the process exits.
+  _exit(0);
 }
