@@ -98,6 +98,18 @@ uint64_t pl2gpu_king_variants_added(Pl2KingJob* job);
 /* Idempotent; accepts NULL. */
 int pl2gpu_king_end(Pl2KingJob* job);
 
+/* ---- KING counts for an explicit pair list: replaces IncrKingSubset / IncrKingSubsetHomhom
+ * (2.0/plink2_matrix_calc.cc:2495-2741) driven by CalcKingTableSubset (:3224), i.e.
+ * `--make-king-table --king-table-subset`.  pairs[2 p], pairs[2 p + 1] = sample indices of pair p
+ * (host memory, copied at begin); counts come back as uint32 [pair][5] in the same
+ * {IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM} order, where - as in the reference's subset path - "1" is
+ * the FIRST sample of the listed pair and "2" the second. ---- */
+typedef struct Pl2KingPairJob Pl2KingPairJob;
+int pl2gpu_king_pairs_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, const uint32_t* pairs_host, uint64_t pair_ct, Pl2KingPairJob** job_ptr);
+int pl2gpu_king_pairs_add_variants(Pl2KingPairJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device);
+int pl2gpu_king_pairs_get_counts(Pl2KingPairJob* job, uint64_t pair_start, uint64_t pair_end, uint32_t* dst, int dst_is_device);
+int pl2gpu_king_pairs_end(Pl2KingPairJob* job);
+
 /* ---- GRM: replaces ExpandCenteredVarmaj + the CalcGrmThread/CalcGrmPartThread dsyrk/dgemm
  * accumulation (2.0/plink2_matrix_calc.cc:3839-3886, :4285-4327) and the CalcMissingMatrix pass
  * (:4404-4553) for rows [row_start,row_end) of the lower triangle (diagonal included), one

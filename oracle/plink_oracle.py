@@ -90,6 +90,20 @@ def king_counts(geno: np.ndarray, row_start: int = 0, row_end: int = None) -> np
     return np.concatenate(rows, axis=0).astype(np.uint32)
 
 
+def king_counts_pairs(geno: np.ndarray, pairs: np.ndarray) -> np.ndarray:
+    """IncrKingSubsetHomhom (2.0/plink2_matrix_calc.cc:2533-2575): the same five sums for an explicit list
+    of (first, second) sample pairs, "1" = first listed.  uint32 [pair][5] = {IBS0, HETHET, HET2HOM1,
+    HET1HOM2, HOMHOM}."""
+    hom, r2h = split_hom_ref2het(geno)
+    het = r2h & ~hom
+    out = np.zeros((len(pairs), 5), dtype=np.uint32)
+    for p, (a, b) in enumerate(np.asarray(pairs, dtype=np.int64)):
+        hom1, hom2, het1, het2 = hom[:, a], hom[:, b], het[:, a], het[:, b]
+        hh = hom1 & hom2
+        out[p] = (np.count_nonzero((r2h[:, a] ^ r2h[:, b]) & hh), np.count_nonzero(het1 & het2), np.count_nonzero(hom1 & het2), np.count_nonzero(hom2 & het1), np.count_nonzero(hh))
+    return out
+
+
 def king_counts_bruteforce(geno: np.ndarray) -> np.ndarray:
     """Pure-Python loop over pairs and variants (tiny inputs only): the literal per-genotype table
     behind IncrKingHomhom, used to cross-check the vectorised restatement."""

@@ -46,6 +46,10 @@ SIGNATURES = {
     "pl2gpu_king_get_kinship": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
     "pl2gpu_king_variants_added": (C.c_uint64, [vp]),
     "pl2gpu_king_end": (C.c_int, [vp]),
+    "pl2gpu_king_pairs_begin": (C.c_int, [vp, C.c_uint32, vp, C.c_uint64, C.POINTER(vp)]),
+    "pl2gpu_king_pairs_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int]),
+    "pl2gpu_king_pairs_get_counts": (C.c_int, [vp, C.c_uint64, C.c_uint64, vp, C.c_int]),
+    "pl2gpu_king_pairs_end": (C.c_int, [vp]),
     "pl2gpu_grm_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
     "pl2gpu_grm_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, vp]),
     "pl2gpu_grm_get_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, C.c_int]),

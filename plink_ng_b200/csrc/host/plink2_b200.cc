@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <unordered_map>
 #include <chrono>
 #include <cfloat>
 #include <cmath>
@@ -77,6 +78,8 @@ struct Cmd {
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
   // GRM
+  std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
+  double king_table_subset_thresh = -DBL_MAX;
   bool make_grm_bin = false, make_grm_list = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
   // PCA
   bool pca = false, pca_approx = false, pca_meanimpute = false;
@@ -213,6 +216,10 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     } else if (flag == "--king-table-filter") {
       if (!need(1, 1) || !ParseDouble(prm[0], &c->king_table_filter)) return Usage("Invalid --king-table-filter argument.");
+    } else if (flag == "--king-table-subset") {
+      if (!need(1, 2)) return Usage("--king-table-subset requires a filename and an optional kinship threshold.");
+      c->king_table_subset = prm[0];
+      if (nparam == 2 && !ParseDouble(prm[1], &c->king_table_subset_thresh)) return Usage("Invalid --king-table-subset threshold.");
     } else if (flag == "--king-cutoff") {
       if (nparam == 2) return Usage("--king-cutoff with a precomputed matrix prefix is not supported by plink2_b200.");
       if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
@@ -475,6 +482,267 @@ inline double KinshipFromCounts(const uint32_t* c) {  // ComputeKinship, :1566-1
   return 0.5 - static_cast<double>(4 * ibs0 + het1hom2 + het2hom1) / static_cast<double>(4 * smaller);
 }
 
+// AppendKingTableHeader (:1611-1652)
+std::string KingTableHeader(const Cmd& c, const IdFmt& idf) {
+  std::string h = "#";
+  if (c.col_id) {
+    if (idf.fid) h += "FID1\t";
+    h += "IID1\t";
+    if (idf.sid) h += "SID1\t";
+    if (idf.fid) h += "FID2\t";
+    h += "IID2\t";
+    if (idf.sid) h += "SID2\t";
+  }
+  if (c.col_nsnp) h += "NSNP\t";
+  if (c.col_hethet) h += "HETHET\t";
+  if (c.col_ibs0) h += "IBS0\t";
+  if (c.col_ibs1) h += "HET1_HOM2\tHET2_HOM1\t";
+  if (c.col_hamming) h += "IBS\t";
+  if (c.col_kinship) h += "KINSHIP\t";
+  h.back() = '\n';
+  return h;
+}
+
+// One .kin0 line (:2285-2364 / :3705-3760): cc = {IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM}.
+void WriteKingTableRow(const Cmd& c, const std::string& id1, const std::string& id2, const uint32_t* cc, double kinship, OutFile* ftab) {
+  const uint32_t ibs0 = cc[0], hethet = cc[1], het2hom1 = cc[2], het1hom2 = cc[3], homhom = cc[4];
+  char* w = ftab->Reserve(id1.size() + id2.size() + 160);
+  if (c.col_id) {
+    memcpy(w, id1.data(), id1.size());
+    w += id1.size();
+    *w++ = '\t';
+    memcpy(w, id2.data(), id2.size());
+    w += id2.size();
+    *w++ = '\t';
+  }
+  const uint32_t nonmiss = het1hom2 + het2hom1 + homhom + hethet;
+  double recip = 0.0;
+  if (c.col_nsnp) {
+    w = u32toa(nonmiss, w);
+    *w++ = '\t';
+  }
+  if (!c.king_counts) recip = 1.0 / static_cast<double>(nonmiss);
+  auto put = [&](uint32_t v) {
+    if (c.king_counts) w = u32toa(v, w);
+    else w = dtoa_g(recip * static_cast<double>(v), w);
+    *w++ = '\t';
+  };
+  if (c.col_hethet) put(hethet);
+  if (c.col_ibs0) put(ibs0);
+  if (c.col_ibs1) {
+    put(het1hom2);
+    put(het2hom1);
+  }
+  if (c.col_hamming) {
+    const uint32_t hamming = 2 * ibs0 + het1hom2 + het2hom1;
+    if (c.king_counts) w = u32toa(hamming, w);
+    else w = dtoa_g(recip * 0.5 * static_cast<double>(hamming), w);
+    *w++ = '\t';
+  }
+  if (c.col_kinship) {
+    w = dtoa_g(kinship, w);
+    *w++ = '\t';
+  }
+  w[-1] = '\n';
+  ftab->Advance(w);
+}
+
+// `--make-king-table --king-table-subset <file> [thresh]` (CalcKingTableSubset, :3224; KingTableSubsetLoad,
+// :2774): KING-robust for the pairs listed in a .kin0-style file, in file order, ID1 = first listed sample.
+int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  if (c.parallel_tot != 1) {
+    logprintf("Error: --king-table-subset with --parallel is not supported by plink2_b200 yet.\n");
+    return kRetNotYetSupported;
+  }
+  if (n < 2) {
+    logprintf("Error: --make-king-table requires at least 2 samples.\n");
+    return kRetDegenerateData;
+  }
+  std::vector<uint32_t> vidx;
+  uint32_t non_auto = 0;
+  for (uint32_t v = 0; v < ds->variants.size(); ++v) {
+    if (KeptForRelationship(ds->variants.chr_code[v])) vidx.push_back(v);
+    else ++non_auto;
+  }
+  if (non_auto) logprintf("Excluding %u variant%s on non-autosomes from KING-robust calculation.\n", non_auto, non_auto == 1 ? "" : "s");
+  if (vidx.empty()) {
+    logprintf("Error: No variants remaining for KING-robust calculation.\n");
+    return kRetDegenerateData;
+  }
+  // ---- header (:3391-3452): [#FID1|FID] (ID1|IID1) [SID1] [FID2] (ID2|IID2) [SID2] ... [KINSHIP|Kinship]
+  std::vector<std::string> lines;
+  std::string rerr;
+  if (!ReadLines(c.king_table_subset, &lines, &rerr)) {
+    logprintf("Error: %s\n", rerr.c_str());
+    return kRetOpenFail;
+  }
+  if (lines.empty()) {
+    logprintf("Error: Empty --king-table-subset file.\n");
+    return kRetMalformedInput;
+  }
+  std::vector<std::string> hd = SplitWs(lines[0]);
+  auto bad_header = [&]() {
+    logprintf("Error: Invalid header line in --king-table-subset file.\n");
+    return kRetMalformedInput;
+  };
+  if (hd.empty()) return bad_header();
+  size_t t = 0;
+  bool fid_present = hd[0] == "#FID1" || hd[0] == "FID";
+  std::string tok0 = hd[0];
+  if (fid_present) {
+    ++t;
+    if (t >= hd.size()) return bad_header();
+    tok0 = hd[t];
+  } else {
+    if (tok0.empty() || tok0[0] != '#') return bad_header();
+    tok0 = tok0.substr(1);
+  }
+  if (tok0 != "ID1" && tok0 != "IID1") return bad_header();
+  ++t;
+  bool sid_cols = false;
+  if (t < hd.size() && hd[t] == "SID1") {
+    sid_cols = true;
+    ++t;
+  }
+  if (fid_present) {
+    if (t >= hd.size() || hd[t] != "FID2") return bad_header();
+    ++t;
+  }
+  if (t >= hd.size() || (hd[t] != "ID2" && hd[t] != "IID2")) return bad_header();
+  ++t;
+  if (sid_cols) {
+    if (t >= hd.size() || hd[t] != "SID2") return bad_header();
+    ++t;
+  }
+  const size_t id_tokens = t;  // tokens of a data line before the first non-ID column
+  size_t kinship_col = 0;
+  double thresh = c.king_table_subset_thresh;
+  if (thresh != -DBL_MAX) {
+    thresh *= 1.0 - 1.0 / 17592186044416.0;  // kSmallEpsilon = 2^-44 (:3441)
+    size_t k = t;
+    for (; k < hd.size(); ++k)
+      if (hd[k] == "KINSHIP" || hd[k] == "Kinship") break;
+    if (k == hd.size()) {
+      logprintf("Error: No kinship-coefficient column in --king-table-subset file.\n");
+      return kRetInconsistentInput;
+    }
+    kinship_col = k;
+  }
+  // ---- sample lookup: FID<tab>IID when the file has FID columns, IID alone otherwise
+  std::unordered_map<std::string, uint32_t> lookup;
+  lookup.reserve(static_cast<size_t>(n) * 2);
+  for (uint32_t k = 0; k < n; ++k) {
+    const std::string key = fid_present ? (S.fid[k] + "\t" + S.iid[k]) : S.iid[k];
+    if (!lookup.emplace(key, k).second && !fid_present) {
+      logprintf("Error: Duplicate sample ID '%s' (the --king-table-subset file has no FID columns).\n", key.c_str());
+      return kRetInconsistentInput;
+    }
+  }
+  std::vector<uint32_t> pairs;
+  for (size_t li = 1; li < lines.size(); ++li) {
+    const std::vector<std::string> f = SplitWs(lines[li]);
+    if (f.empty()) continue;
+    if (f.size() < id_tokens) {
+      logprintf("Error: Line %zu of --king-table-subset file has fewer tokens than expected.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    size_t q = 0;
+    std::string k1 = fid_present ? (f[q] + "\t" + f[q + 1]) : f[q];
+    q += fid_present ? 2 : 1;
+    if (sid_cols) ++q;
+    std::string k2 = fid_present ? (f[q] + "\t" + f[q + 1]) : f[q];
+    const auto i1 = lookup.find(k1), i2 = lookup.find(k2);
+    if (i1 == lookup.end() || i2 == lookup.end()) continue;  // not loaded: skipped silently, as in the reference
+    if (i1->second == i2->second) {
+      logprintf("Error: Identical sample IDs on line %zu of --king-table-subset file.\n", li + 1);
+      return kRetInconsistentInput;
+    }
+    if (thresh != -DBL_MAX) {
+      if (f.size() <= kinship_col) {
+        logprintf("Error: Line %zu of --king-table-subset file has fewer tokens than expected.\n", li + 1);
+        return kRetMalformedInput;
+      }
+      double kv;
+      if (!ParseDouble(f[kinship_col].c_str(), &kv)) continue;  // e.g. "nan": not a number -> line skipped
+      if (kv < thresh) continue;
+    }
+    pairs.push_back(i1->second);
+    pairs.push_back(i2->second);
+  }
+  const uint64_t pair_ct = pairs.size() / 2;
+  if (!pair_ct) {
+    logprintf("Error: No valid pairs in --king-table-subset file.\n");
+    return kRetInconsistentInput;
+  }
+  logprintf("--king-table-subset: %llu pair%s loaded.\n", static_cast<unsigned long long>(pair_ct), pair_ct == 1 ? "" : "s");
+  const IdFmt idf = KingIdFmt(c, S);
+  const std::string tab_name = c.out + ".kin0";
+  OutFile ftab;
+  if (!ftab.Open(tab_name)) {
+    logprintf("Error: Failed to open %s for writing.\n", tab_name.c_str());
+    return kRetOpenFail;
+  }
+  ftab.Puts(KingTableHeader(c, idf).c_str());
+  Pl2KingPairJob* job = nullptr;
+  if (pl2gpu_king_pairs_begin(ctx, n, pairs.data(), pair_ct, &job)) return GpuFail("pl2gpu_king_pairs_begin");
+  BlockStreamer bs(ds, &vidx, n, 32768);
+  if (!bs.Init()) {
+    pl2gpu_king_pairs_end(job);
+    return GpuFail("pl2gpu_host_alloc");
+  }
+  std::string err;
+  uint32_t done = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("\nError: %s\n", err.c_str());
+      pl2gpu_king_pairs_end(job);
+      return kRetMalformedInput;
+    }
+    if (!got) break;
+    if (pl2gpu_king_pairs_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
+      pl2gpu_king_pairs_end(job);
+      return GpuFail("pl2gpu_king_pairs_add_variants");
+    }
+    done += static_cast<uint32_t>(got);
+    printf("\r--make-king-table pass 1: %u variants complete.", done);
+    fflush(stdout);
+  }
+  printf("\r--make-king-table pass 1: Writing...                   ");
+  fflush(stdout);
+  std::vector<uint32_t> counts;
+  uint64_t filter_ct = 0;
+  const uint64_t chunk = 8ull << 20;
+  for (uint64_t p0 = 0; p0 < pair_ct; p0 += chunk) {
+    const uint64_t p1 = std::min(pair_ct, p0 + chunk);
+    counts.resize((p1 - p0) * 5);
+    if (pl2gpu_king_pairs_get_counts(job, p0, p1, counts.data(), 0)) {
+      pl2gpu_king_pairs_end(job);
+      return GpuFail("pl2gpu_king_pairs_get_counts");
+    }
+    for (uint64_t p = p0; p < p1; ++p) {
+      const uint32_t* cc = &counts[(p - p0) * 5];
+      const double kinship = KinshipFromCounts(cc);
+      if (c.king_table_filter != -DBL_MAX && kinship < c.king_table_filter) {
+        ++filter_ct;
+        continue;
+      }
+      WriteKingTableRow(c, FmtId(S, pairs[2 * p], idf), FmtId(S, pairs[2 * p + 1], idf), cc, kinship, &ftab);
+    }
+  }
+  pl2gpu_king_pairs_end(job);
+  if (!ftab.Close()) return kRetWriteFail;
+  printf("\r");
+  logprintf("--make-king-table: %u variant%s processed.\n", static_cast<uint32_t>(vidx.size()), vidx.size() == 1 ? "" : "s");
+  logprintf("Results written to %s .\n", tab_name.c_str());
+  if (c.king_table_filter != -DBL_MAX) {
+    logprintf("--king-table-filter: %llu relationship%s reported (%llu filtered out).\n", static_cast<unsigned long long>(pair_ct - filter_ct), (pair_ct - filter_ct == 1) ? "" : "s", static_cast<unsigned long long>(filter_ct));
+  }
+  return 0;
+}
+
 int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cutoff_removed) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
@@ -524,25 +792,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       logprintf("Error: Failed to open %s for writing.\n", tab_name.c_str());
       return kRetOpenFail;
     }
-    if (!c.parallel_idx) {  // AppendKingTableHeader, :1611-1652
-      std::string h = "#";
-      if (c.col_id) {
-        if (idf.fid) h += "FID1\t";
-        h += "IID1\t";
-        if (idf.sid) h += "SID1\t";
-        if (idf.fid) h += "FID2\t";
-        h += "IID2\t";
-        if (idf.sid) h += "SID2\t";
-      }
-      if (c.col_nsnp) h += "NSNP\t";
-      if (c.col_hethet) h += "HETHET\t";
-      if (c.col_ibs0) h += "IBS0\t";
-      if (c.col_ibs1) h += "HET1_HOM2\tHET2_HOM1\t";
-      if (c.col_hamming) h += "IBS\t";
-      if (c.col_kinship) h += "KINSHIP\t";
-      h.back() = '\n';
-      ftab.Puts(h.c_str());
-    }
+    if (!c.parallel_idx) ftab.Puts(KingTableHeader(c, idf).c_str());
     fmtids.resize(n);
     for (uint32_t k = 0; k < n; ++k) fmtids[k] = FmtId(S, k, idf);
   }
@@ -709,51 +959,12 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
         if (want_table) {
           for (uint32_t i = 0; i < j; ++i) {
             const uint32_t* cc = &counts[(row_p + i) * 5];
-            const uint32_t ibs0 = cc[0], hethet = cc[1], het2hom1 = cc[2], het1hom2 = cc[3], homhom = cc[4];
             const double kinship = KinshipFromCounts(cc);
             if (c.king_table_filter != -DBL_MAX && kinship < c.king_table_filter) {
               ++filter_ct;
               continue;
             }
-            char* w = ftab.Reserve(fmtids[j].size() + fmtids[i].size() + 160);
-            if (c.col_id) {
-              memcpy(w, fmtids[j].data(), fmtids[j].size());
-              w += fmtids[j].size();
-              *w++ = '\t';
-              memcpy(w, fmtids[i].data(), fmtids[i].size());
-              w += fmtids[i].size();
-              *w++ = '\t';
-            }
-            const uint32_t nonmiss = het1hom2 + het2hom1 + homhom + hethet;
-            double recip = 0.0;
-            if (c.col_nsnp) {
-              w = u32toa(nonmiss, w);
-              *w++ = '\t';
-            }
-            if (!c.king_counts) recip = 1.0 / static_cast<double>(nonmiss);
-            auto put = [&](uint32_t v) {
-              if (c.king_counts) w = u32toa(v, w);
-              else w = dtoa_g(recip * static_cast<double>(v), w);
-              *w++ = '\t';
-            };
-            if (c.col_hethet) put(hethet);
-            if (c.col_ibs0) put(ibs0);
-            if (c.col_ibs1) {
-              put(het1hom2);
-              put(het2hom1);
-            }
-            if (c.col_hamming) {
-              const uint32_t hamming = 2 * ibs0 + het1hom2 + het2hom1;
-              if (c.king_counts) w = u32toa(hamming, w);
-              else w = dtoa_g(recip * 0.5 * static_cast<double>(hamming), w);
-              *w++ = '\t';
-            }
-            if (c.col_kinship) {
-              w = dtoa_g(kinship, w);
-              *w++ = '\t';
-            }
-            w[-1] = '\n';
-            ftab.Advance(w);
+            WriteKingTableRow(c, fmtids[j], fmtids[i], cc, kinship, &ftab);
           }
         }
         p += j;
@@ -1381,7 +1592,14 @@ int main(int argc, char** argv) {
   }
   g_clock.Mark("pl2gpu_ctx_create");
   std::vector<uint8_t> cutoff_removed;
-  if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
+  if (!c.king_table_subset.empty()) {
+    if (!c.make_king_table || c.make_king || c.king_cutoff >= 0) {
+      logprintf("Error: --king-table-subset must be used with --make-king-table (and without --make-king / --king-cutoff).\n");
+      return kRetInvalidCmdline;
+    }
+    rc = RunKingSubset(c, &ds, ctx);
+    if (rc) return rc;
+  } else if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
     if (rc) return rc;
     if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_grm_list || c.make_rel || c.pca || c.indep_pairwise)) {

@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "king_kernels.cuh"
 #include "king_ts_kernel.cuh"
+#include "king_pairs_kernel.cuh"
 #include "umma_probe.cuh"
 
 namespace pl2 {
@@ -500,6 +501,117 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   cudaFree(job->d_raw_j);
   cudaFree(job->d_raw_acc);
   cudaFree(job->d_out_stage);
+  cudaGetLastError();
+  delete job;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ pair list
+
+struct Pl2KingPairJob {
+  Pl2GpuCtx* ctx = nullptr;
+  uint32_t sample_ct = 0;
+  uint64_t pair_ct = 0;
+  GenoStage stage;
+  uint8_t* d_raw_t = nullptr;   // sample-major 2-bit copy of the staged block
+  uint32_t* d_pairs = nullptr;  // [pair][2]
+  uint32_t* d_counts = nullptr; // [pair][5]
+};
+
+int pl2gpu_king_pairs_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, const uint32_t* pairs_host, uint64_t pair_ct, Pl2KingPairJob** job_ptr) {
+  if (job_ptr) *job_ptr = nullptr;
+  if (!ctx || !job_ptr || !sample_ct || (pair_ct && !pairs_host)) {
+    set_error("pl2gpu_king_pairs_begin: bad arguments");
+    return 1;
+  }
+  for (uint64_t p = 0; p < 2 * pair_ct; ++p) {
+    if (pairs_host[p] >= sample_ct) {
+      set_error("pl2gpu_king_pairs_begin: pair %llu names sample %u of %u", static_cast<unsigned long long>(p / 2), pairs_host[p], sample_ct);
+      return 1;
+    }
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  Pl2KingPairJob* job = new Pl2KingPairJob();
+  job->ctx = ctx;
+  job->sample_ct = sample_ct;
+  job->pair_ct = pair_ct;
+  auto fail = [&]() {
+    pl2gpu_king_pairs_end(job);
+    return 1;
+  };
+  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, 64)) return fail();
+  const uint64_t n_alloc = pair_ct ? pair_ct : 1;
+  if (cudaMalloc(&job->d_raw_t, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess || cudaMalloc(&job->d_pairs, n_alloc * 8) != cudaSuccess ||
+      cudaMalloc(&job->d_counts, n_alloc * 20) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_king_pairs_begin: insufficient device memory for %llu pairs", static_cast<unsigned long long>(pair_ct));
+    return fail();
+  }
+  if (cudaMemcpyAsync(job->d_pairs, pairs_host, pair_ct * 8, cudaMemcpyHostToDevice, ctx->c.stream) != cudaSuccess || cudaMemsetAsync(job->d_counts, 0, n_alloc * 20, ctx->c.stream) != cudaSuccess ||
+      cudaStreamSynchronize(ctx->c.stream) != cudaSuccess) {
+    set_error("pl2gpu_king_pairs_begin: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail();
+  }
+  *job_ptr = job;
+  return 0;
+}
+
+int pl2gpu_king_pairs_add_variants(Pl2KingPairJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device) {
+  if (!job || (!genovecs && variant_ct)) {
+    set_error("pl2gpu_king_pairs_add_variants: bad arguments");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint64_t min_stride = static_cast<uint64_t>(DivUpU32(job->sample_ct, 4));
+  if (variant_stride_bytes < min_stride) {
+    set_error("pl2gpu_king_pairs_add_variants: variant stride %llu < %llu bytes of genotype data", static_cast<unsigned long long>(variant_stride_bytes), static_cast<unsigned long long>(min_stride));
+    return 1;
+  }
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  uint32_t done = 0;
+  while (done < variant_ct) {
+    uint32_t cur = variant_ct - done;
+    if (cur > job->stage.variant_cap) cur = job->stage.variant_cap;
+    uint32_t padded = 0;
+    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    if (job->pair_ct) {
+      const uint32_t pitch_t = padded / 4;
+      geno_transpose_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->d_raw_t, pitch_t);
+      king_pairs_kernel<<<static_cast<uint32_t>(DivUpU64(job->pair_ct, 8)), 256, 0, c->stream>>>(job->d_raw_t, pitch_t, padded / 32, job->d_pairs, job->pair_ct, job->d_counts);
+      c->launches += 2;
+      PL2_CUDA_OK(cudaGetLastError());
+    }
+    if (!src_is_device) PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+    done += cur;
+  }
+  return 0;
+}
+
+int pl2gpu_king_pairs_get_counts(Pl2KingPairJob* job, uint64_t pair_start, uint64_t pair_end, uint32_t* dst, int dst_is_device) {
+  if (!job || pair_start > pair_end || pair_end > job->pair_ct || (!dst && pair_end > pair_start)) {
+    set_error("pl2gpu_king_pairs_get_counts: bad arguments");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  if (pair_end > pair_start) {
+    PL2_CUDA_OK(cudaMemcpyAsync(dst, job->d_counts + 5 * pair_start, (pair_end - pair_start) * 20, dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+  }
+  PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pl2gpu_king_pairs_end(Pl2KingPairJob* job) {
+  if (!job) return 0;
+  if (job->ctx) {
+    cudaSetDevice(job->ctx->c.device);
+    cudaStreamSynchronize(job->ctx->c.stream);
+  }
+  StageFree(&job->stage);
+  cudaFree(job->d_raw_t);
+  cudaFree(job->d_pairs);
+  cudaFree(job->d_counts);
   cudaGetLastError();
   delete job;
   return 0;

@@ -154,6 +154,37 @@ class KingJob:
         self.close()
 
 
+class KingPairJob:
+    """KING counts for an explicit pair list (`--king-table-subset`; CalcKingTableSubset,
+    2.0/plink2_matrix_calc.cc:3224).  pairs: int array [P, 2] of sample indices (first, second)."""
+
+    def __init__(self, ctx: GpuContext, sample_ct: int, pairs: np.ndarray):
+        self.pairs = np.ascontiguousarray(pairs, dtype=np.uint32).reshape(-1, 2)
+        self.sample_ct = sample_ct
+        self._h = C.c_void_p()
+        check(lib.pl2gpu_king_pairs_begin(ctx.handle, sample_ct, self.pairs.ctypes.data, len(self.pairs), C.byref(self._h)), "pl2gpu_king_pairs_begin")
+
+    def add_variants(self, genovecs: np.ndarray):
+        g = np.ascontiguousarray(genovecs)
+        check(lib.pl2gpu_king_pairs_add_variants(self._h, g.ctypes.data, g.strides[0], g.shape[0], 0), "pl2gpu_king_pairs_add_variants")
+
+    def counts(self) -> np.ndarray:
+        out = np.empty((len(self.pairs), 5), dtype=np.uint32)
+        check(lib.pl2gpu_king_pairs_get_counts(self._h, 0, len(self.pairs), out.ctypes.data, 0), "pl2gpu_king_pairs_get_counts")
+        return out
+
+    def close(self):
+        if self._h:
+            lib.pl2gpu_king_pairs_end(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+
 def king_counts(genovecs: np.ndarray, sample_ct: int, algo: int = KING_ALGO_AUTO, device: int = 0, batch: int = 65536) -> np.ndarray:
     """All-pairs king_counts[pair][5] for one genotype block (convenience for tests)."""
     with GpuContext(device) as ctx, KingJob(ctx, sample_ct, 0, sample_ct, algo) as job:

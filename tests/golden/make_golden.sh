@@ -25,6 +25,14 @@ $P --bfile a --make-king square --threads 2 --out $T/a_kingsq > /dev/null
 gzip -9 -n -c $T/a_kingsq.king > a_kingsq.king.gz; cp $T/a_kingsq.king.id a_kingsq.king.id
 $P --bfile a --make-king-table counts --parallel 2 3 --threads 2 --out $T/a_kingpar > /dev/null
 gzip -9 -n -c $T/a_kingpar.kin0.2 > a_kingpar.kin0.2.gz
+# pair-list KING (--king-table-subset): (1) the proportion table above as the pair list with a kinship threshold,
+# (2) a hand-written IID-only list with swapped orientation, an unknown ID and ibs1 columns
+zcat a_kingp.kin0.gz > $T/in.kin0
+$P --bfile a --make-king-table counts --king-table-subset $T/in.kin0 -0.05 --threads 2 --out $T/a_sub > /dev/null
+gzip -9 -n -c $T/a_sub.kin0 > a_kingsub.kin0.gz
+printf '#IID1\tIID2\tKINSHIP\nper7\tper3\t0.1\nper2\tper90\t0.2\nnosuch\tper1\t0.3\nper50\tper49\t-0.4\n' > a_sub2.txt
+$P --bfile a --make-king-table counts cols=+ibs1 --king-table-subset a_sub2.txt --threads 2 --out $T/a_sub2 > /dev/null
+cp $T/a_sub2.kin0 a_kingsub2.kin0
 $P --bfile a --king-cutoff 0.02 --threads 2 --out $T/a_cut > /dev/null
 cp $T/a_cut.king.cutoff.in.id a_cut.king.cutoff.in.id; cp $T/a_cut.king.cutoff.out.id a_cut.king.cutoff.out.id
 $P --bfile a --freq --threads 2 --out $T/a_freq > /dev/null

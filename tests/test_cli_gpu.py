@@ -49,6 +49,17 @@ def test_make_king_table_parallel_piece(golden_dir, tmp_path):
     assert open(out + ".kin0.2", "rb").read() == gz(golden_dir, "a_kingpar.kin0.2.gz")
 
 
+def test_king_table_subset_byte_identical(golden_dir, tmp_path):
+    """--king-table-subset (pair-list kernel): the reference's own .kin0 as the pair list + kinship threshold, and a
+    hand-written IID-only list with swapped orientation and an unknown ID."""
+    sub = tmp_path / "in.kin0"
+    sub.write_bytes(gz(golden_dir, "a_kingp.kin0.gz"))
+    out = run(golden_dir, tmp_path, "--make-king-table", "counts", "--king-table-subset", str(sub), "-0.05")
+    assert open(out + ".kin0", "rb").read() == gz(golden_dir, "a_kingsub.kin0.gz")
+    out = run(golden_dir, tmp_path, "--make-king-table", "counts", "cols=+ibs1", "--king-table-subset", os.path.join(golden_dir, "a_sub2.txt"))
+    assert open(out + ".kin0", "rb").read() == open(os.path.join(golden_dir, "a_kingsub2.kin0"), "rb").read()
+
+
 def test_king_cutoff_lists(golden_dir, tmp_path):
     out = run(golden_dir, tmp_path, "--king-cutoff", "0.02")
     for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):

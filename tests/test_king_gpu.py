@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import plink_ng_b200 as p
-from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS, KingJob, pack_genotypes, parallel_bounds
+from plink_ng_b200.host import KING_ALGO_POPCOUNT, KING_ALGO_TENSOR, KING_ALGO_TENSOR_TS, KingJob, KingPairJob, pack_genotypes, parallel_bounds
 from oracle import plink_oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -75,6 +75,50 @@ def test_king_tensor_equals_popcount_medium(gpu_ctx):
     c = res[1].astype(np.int64)
     nsnp = c[:, 1] + c[:, 2] + c[:, 3] + c[:, 4]
     assert nsnp.max() <= m and (c[:, 0] <= c[:, 4]).all()
+
+
+@pytest.mark.parametrize("n,m,pair_ct", [(2, 5, 1), (97, 300, 50), (385, 1300, 2000), (1000, 70000, 300)])
+def test_king_pair_list_matches_oracle(gpu_ctx, n, m, pair_ct):
+    """--king-table-subset kernel: listed (first, second) pairs in any order / orientation, "1" = first listed."""
+    geno = _random_geno(m, n, seed=n + m)
+    rng = np.random.default_rng(pair_ct)
+    first = rng.integers(0, n, size=pair_ct)
+    second = (first + rng.integers(1, n, size=pair_ct)) % n
+    pairs = np.stack([first, second], axis=1).astype(np.uint32)
+    with KingPairJob(gpu_ctx, n, pairs) as job:
+        gv = pack_genotypes(geno)
+        half = max(1, m // 2)
+        job.add_variants(gv[:half])  # two batches accumulate
+        if m > half:
+            job.add_variants(gv[half:])
+        got = job.counts()
+    want = orc.king_counts_pairs(geno, pairs)
+    assert np.array_equal(got, want)
+
+
+def test_king_large_block_marginal_identities(gpu_ctx):
+    """Size-independent check at a size the pairwise oracle cannot reach (2e8 pairs): summed over all pairs, every
+    KING count is a per-variant closed form of the genotype counts n0 (hom-REF), n1 (het), n2 (hom-ALT):
+      sum HETHET = sum_v C(n1, 2)            sum IBS0   = sum_v n0 n2
+      sum (HET1_HOM2 + HET2_HOM1) = sum_v n1 (n0 + n2)      sum HOMHOM = sum_v C(n0 + n2, 2)
+    (a checksum of checksums over the whole N x N result of the default TS tensor kernel, several batches)."""
+    n, m = 20000, 8192
+    rng = np.random.default_rng(77)
+    tot = np.zeros(5, dtype=object)
+    want = np.zeros(4, dtype=object)
+    with KingJob(gpu_ctx, n) as job:
+        for b0 in range(0, m, 2048):
+            freq = rng.uniform(0.05, 0.95, size=(2048, 1))
+            g = (rng.random((2048, n)) < freq).astype(np.uint8) + (rng.random((2048, n)) < freq).astype(np.uint8)
+            g[rng.random((2048, n)) < 0.02] = 3
+            job.add_variants(pack_genotypes(g))
+            n0, n1, n2 = [(g == c).sum(axis=1).astype(np.int64) for c in (0, 1, 2)]
+            hom = n0 + n2
+            want += np.array([int((n1 * (n1 - 1) // 2).sum()), int((n0 * n2).sum()), int((n1 * hom).sum()), int((hom * (hom - 1) // 2).sum())], dtype=object)
+        for r0 in range(0, n, 2500):
+            c = job.counts(r0, min(n, r0 + 2500)).astype(np.int64)  # {IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM}
+            tot += np.array([int(x) for x in c.sum(axis=0)], dtype=object)
+    assert int(tot[1]) == want[0] and int(tot[0]) == want[1] and int(tot[2]) + int(tot[3]) == want[2] and int(tot[4]) == want[3]
 
 
 @pytest.mark.parametrize("algo", ALGOS)
