@@ -43,6 +43,14 @@ constexpr uint32_t kTabDosage = 0x00020100u;  // g: ALT dosage 0/1/2, missing ->
 constexpr uint32_t kTabNonmiss = 0x00010101u; // m: non-missing indicator
 constexpr uint32_t kTabMiss = 0x01000000u;    // mu: missing indicator
 
+// A plane table as a PER-THREAD register.  PRMT needs its table operand in a vector register; a
+// compile-time constant gets hoisted into a uniform register and re-materialised with one extra
+// IMAD.U32 in front of EVERY PRMT (164 of them in king_ts_kernel, ~25 % of its issue slots).  OR-ing in
+// `thread_zero` - a value that is 0 at run time but that ptxas can prove neither constant nor
+// warp-uniform (callers pass threadIdx.x * (a kernel argument >> 31)) - keeps each table in one
+// vector register for the whole kernel.
+__device__ __forceinline__ uint32_t table_reg(uint32_t table, uint32_t thread_zero) { return table | thread_zero; }
+
 // MN-major, no-swizzle UMMA operand tile ("interleave" canonical layout,
 // cute/atom/mma_traits_sm100.hpp:171): 16 consecutive samples of one variant are one 16-byte row
 // of an 8-row core matrix (8 consecutive variants, 128 contiguous bytes); core matrices step by

@@ -66,6 +66,9 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
 
+  const uint32_t thread_zero = tid * (variant_ct_padded >> 31);  // 0 (a batch never has 2^31 variants)
+  const uint32_t tab_t = table_reg(kTabHet, thread_zero), tab_h = table_reg(kTabHom, thread_zero), tab_s = table_reg(kTabSgn, thread_zero);
+
   if (warp < kTsRowWarps) {
     // ---------------- row-side producers: 2-bit words -> registers -> tensor memory ----------------
     // Two groups of four warps (group = warp / 4); group g owns k-steps ks = 2 n + g and the A slots
@@ -85,7 +88,7 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
     auto expand_i = [&](const uint2& w) -> ExpI {
       ExpI e;
       const Sel4 s0 = make_selectors(w.x), s1 = make_selectors(w.y);
-      const uint32_t tabs[3] = {kTabHet, kTabHom, kTabSgn};
+      const uint32_t tabs[3] = {tab_t, tab_h, tab_s};
 #pragma unroll
       for (int p = 0; p < 3; ++p) {
         const uint4 a = expand16(tabs[p], s0), b = expand16(tabs[p], s1);
@@ -142,7 +145,7 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
         const uint32_t it = it0 + d;
         const Sel4 sel = make_selectors(pre_j[d]);
         pre_j[d] = load_j(it + kLa);
-        const uint4 vt = expand16(kTabHet, sel), vh = expand16(kTabHom, sel), vs = expand16(kTabSgn, sel);
+        const uint4 vt = expand16(tab_t, sel), vh = expand16(tab_h, sel), vs = expand16(tab_s, sel);
         const uint32_t sb = d % kTsStagesJ;
         mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
         const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
