@@ -162,6 +162,9 @@ struct Pl2KingJob {
   void* d_out_stage = nullptr;   // bounded staging for host downloads
   uint64_t out_stage_bytes = 0;
   uint64_t variants_added = 0;
+  // TS path, host sources: H2D of batch k+1 on the copy stream overlaps the tensor kernel of batch k
+  cudaEvent_t ev_copied = nullptr;      // the staged block has arrived (copy stream)
+  cudaEvent_t ev_stage_free = nullptr;  // the staged block has been re-tiled and may be overwritten (compute stream)
 };
 
 extern "C" {
@@ -321,6 +324,10 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     return 1;
   };
   const bool ts = algo == kPl2KingAlgoTensorTS;
+  if (cudaEventCreateWithFlags(&job->ev_copied, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&job->ev_stage_free, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("pl2gpu_king_begin: cudaEventCreate failed");
+    return fail();
+  }
   job->tile_cols = ts ? kTsCols : kTileCols;
   if (BuildTileList(row_start, row_end, false, &job->tiles, job->tile_cols)) return fail();
   if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, ts ? kTsSamplePad : kSamplePad)) return fail();
@@ -378,7 +385,20 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
     uint32_t padded = 0;
     // The stage buffer is reused: make sure the previous chunk's kernels are ordered before the
     // copy (same stream => implicit).
-    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    const bool overlap_h2d = !src_is_device && job->algo == kPl2KingAlgoTensorTS && job->tiles.tile_ct;
+    if (overlap_h2d) {
+      // The TS kernel reads only the re-tiled copies, so the raw stage is free as soon as the previous
+      // batch's re-tiling kernels are done: copy on the copy stream while the previous tensor kernel runs.
+      padded = RoundUpU32(cur, kVariantPad);
+      const uint32_t width = DivUpU32(job->stage.sample_ct, 4);
+      PL2_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, job->ev_stage_free, 0));
+      PL2_CUDA_OK(cudaMemcpy2DAsync(job->stage.d_raw, job->stage.pitch, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, width, cur, cudaMemcpyHostToDevice, c->copy_stream));
+      PL2_CUDA_OK(cudaEventRecord(job->ev_copied, c->copy_stream));
+      PL2_CUDA_OK(cudaStreamWaitEvent(c->stream, job->ev_copied, 0));
+      PL2_TRY(LaunchPadGenotypes(c, job->stage.d_raw, job->stage.pitch, job->stage.sample_ct, cur, padded));
+    } else {
+      PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    }
     if (job->tiles.tile_ct) {
       if (job->algo == kPl2KingAlgoPopcount) {
         const uint32_t word_ct = padded / 32;
@@ -393,6 +413,7 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
         c->launches++;
         geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);
         c->launches++;
+        PL2_CUDA_OK(cudaEventRecord(job->ev_stage_free, c->stream));
         king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->d_raw_j, job->d_raw_t, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
         c->launches++;
       } else {
@@ -401,9 +422,10 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
       }
       PL2_CUDA_OK(cudaGetLastError());
     }
-    if (!src_is_device) {
-      // pageable/pinned host source: the async copy has consumed it once the stream reaches here
-      // only for pinned memory; be conservative and keep host semantics simple.
+    if (overlap_h2d) {
+      PL2_CUDA_OK(cudaEventSynchronize(job->ev_copied));  // the caller may reuse its buffer; the kernels keep running
+    } else if (!src_is_device) {
+      // host source on the compute stream: it has been consumed once the stream reaches here
       PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
     }
     done += cur;
@@ -494,6 +516,9 @@ int pl2gpu_king_end(Pl2KingJob* job) {
     cudaSetDevice(job->ctx->c.device);
     cudaStreamSynchronize(job->ctx->c.stream);
   }
+  if (job->ctx && job->ctx->c.copy_stream) cudaStreamSynchronize(job->ctx->c.copy_stream);
+  if (job->ev_copied) cudaEventDestroy(job->ev_copied);
+  if (job->ev_stage_free) cudaEventDestroy(job->ev_stage_free);
   FreeTileList(&job->tiles);
   StageFree(&job->stage);
   cudaFree(job->d_planes);
