@@ -353,7 +353,7 @@ def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int,
     return removed
 
 
-def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, step: int, r2_thresh: float, window_is_bp: bool = False, ref_freq: np.ndarray = None) -> np.ndarray:
+def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, step: int, r2_thresh: float, window_is_bp: bool = False, ref_freq: np.ndarray = None, preferred: np.ndarray = None) -> np.ndarray:
     """LdPrune -> IndepPairwise (2.0/plink2_ld.cc:2530-2724): chr0 variants are dropped up front
     (:2542, reported in neither list), every chromosome (bp windows: every run of variants whose
     gaps are <= window, LdPruneSubcontigSplitAll :2165-2268) with >= 2 variants is an independent
@@ -363,6 +363,8 @@ def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, 
     if ref_freq is None:
         ref_freq = ref_allele_freqs(geno)
     majf = major_allele_freqs(ref_freq)
+    if preferred is not None:  # --indep-preferred: listed variants win every victim comparison (:916-918)
+        majf = np.where(np.asarray(preferred, dtype=bool), majf - 1.0, majf)
     removed = np.zeros(m, dtype=bool)
     idx_all = np.arange(m)
     for c in [c for c in dict.fromkeys(chrom.tolist()) if c not in ("0", 0)]:

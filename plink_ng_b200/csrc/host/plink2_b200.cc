@@ -78,6 +78,7 @@ struct Cmd {
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
   // GRM
+  std::string indep_preferred;            // --indep-preferred <file of variant IDs>
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
   bool make_grm_bin = false, make_grm_list = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
@@ -253,6 +254,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else return Usage(("Invalid or unsupported --pca argument '" + m + "'.").c_str());
       }
       if (c->pc_ct < 1 || c->pc_ct > 8000) return Usage("Invalid --pca PC count.");
+    } else if (flag == "--indep-preferred") {
+      if (!need(1, 1)) return Usage("--indep-preferred requires a filename.");
+      c->indep_preferred = prm[0];
     } else if (flag == "--indep-pairwise") {
       // <window size>['kb'] [step size (variant ct)] <r^2 threshold>   (plink2.cc:7238-7312)
       if (!need(2, 4)) return Usage("--indep-pairwise requires 2-4 arguments.");
@@ -310,6 +314,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     c->psam = pfile + ".psam";
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
+  if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
   if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_rel || c->pca || c->indep_pairwise)) return Usage("No command given.");
   return 0;
 }
@@ -1458,8 +1463,36 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     memcpy(static_cast<uint64_t*>(blk) + base * words, bs.buf, static_cast<uint64_t>(got) * words * 8);
     base += static_cast<size_t>(got);
   }
+  // --indep-preferred (plink2_ld.cc:2577-2597, NondupIdLoad): variants whose ID is listed keep priority in
+  // the pairwise victim choice (:916-918)
+  std::vector<uint8_t> preferred;
+  if (!c.indep_preferred.empty()) {
+    std::vector<std::string> plines;
+    std::string perr;
+    if (!ReadLines(c.indep_preferred, &plines, &perr)) {
+      pl2gpu_host_free(blk);
+      logprintf("Error: %s\n", perr.c_str());
+      return kRetOpenFail;
+    }
+    std::unordered_map<std::string, uint32_t> by_id;
+    by_id.reserve(static_cast<size_t>(m) * 2);
+    for (uint32_t v = 0; v < m; ++v)
+      if (V.chr_code[v]) by_id.emplace(V.id[v], v);
+    preferred.assign(m, 0);
+    uint32_t pref_ct = 0;
+    for (const std::string& ln : plines) {
+      for (const std::string& tok : SplitWs(ln)) {
+        const auto it = by_id.find(tok);
+        if (it != by_id.end() && !preferred[it->second]) {
+          preferred[it->second] = 1;
+          ++pref_ct;
+        }
+      }
+    }
+    logprintf("--indep-preferred: %u variant%s loaded.\n", pref_ct, pref_ct == 1 ? "" : "s");
+  }
   std::vector<uint8_t> removed(m, 0);
-  const int rc = pl2_indep_pairwise(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, nullptr, 0, removed.data());
+  const int rc = pl2_indep_pairwise(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, preferred.empty() ? nullptr : preferred.data(), 0, removed.data());
   pl2gpu_host_free(blk);
   if (rc) return GpuFail("pl2_indep_pairwise");
   // LdPruneWrite (plink2_ld.cc:2464-2528)

@@ -52,6 +52,9 @@ cp $T/a_ld.prune.in a_ld.prune.in; cp $T/a_ld.prune.out a_ld.prune.out
 $P --bfile a --indep-pairwise 100 1 0.1 --threads 2 --out $T/a_ld2 > /dev/null
 cp $T/a_ld2.prune.in a_ld2.prune.in
 $P --bfile a --indep-pairwise 20kb 0.3 --threads 2 --out $T/a_ldkb > /dev/null
+awk 'NR%7==3{print $2}' a.bim > a_pref.txt
+$P --bfile a --indep-pairwise 50 5 0.1 --indep-preferred a_pref.txt --threads 2 --out $T/a_ldp > /dev/null
+cp $T/a_ldp.prune.in a_ldpref.prune.in
 cp $T/a_ldkb.prune.in a_ldkb.prune.in
 if [ -x $PL ]; then
   $PL --bfile a --pca 4 --threads 2 --out $T/a_pca > /dev/null

@@ -123,6 +123,11 @@ def test_indep_pairwise_lists_byte_identical(golden_dir, tmp_path, flags, name):
         assert open(out + ".prune.out", "rb").read() == open(os.path.join(golden_dir, "a_ld.prune.out"), "rb").read()
 
 
+def test_indep_preferred_list_byte_identical(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--indep-pairwise", "50", "5", "0.1", "--indep-preferred", os.path.join(golden_dir, "a_pref.txt"))
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldpref.prune.in"), "rb").read()
+
+
 def test_toy_fixture_configs0(golden_dir, tmp_path):
     out = str(tmp_path / "toy")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True, env=ENV)
