@@ -94,6 +94,12 @@ int pl2gpu_king_get_counts(Pl2KingJob* job, uint32_t out_row_start, uint32_t out
 /* Same pairs, KING-robust kinship as fp64 (ComputeKinship, plink2_matrix_calc.cc:1566-1573, with
  * zero singleton terms): 0.5 - (4*IBS0 + HET1HOM2 + HET2HOM1) / (4*(HETHET + min(HET1HOM2, HET2HOM1))). */
 int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, double* dst, int dst_is_device);
+/* `--king-table-filter` evaluated on the device: the pairs of rows [r0,r1) whose kinship is NOT below
+ * min_kinship (the reference's test, 2.0/plink2_matrix_calc.cc:2296-2300), sorted in table order
+ * (row j ascending, then i).  Host outputs: pairs[k][2] = {j (larger index), i}, counts[k][5], kinship[k].
+ * *n_found = number of qualifying pairs; when it exceeds max_out the outputs are incomplete and the
+ * call should be repeated with larger buffers. */
+int pl2gpu_king_get_filtered(Pl2KingJob* job, uint32_t r0, uint32_t r1, double min_kinship, uint64_t max_out, uint32_t* pairs_out, uint32_t* counts_out, double* kinship_out, uint64_t* n_found);
 uint64_t pl2gpu_king_variants_added(Pl2KingJob* job);
 /* Idempotent; accepts NULL. */
 int pl2gpu_king_end(Pl2KingJob* job);

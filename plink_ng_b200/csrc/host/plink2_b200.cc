@@ -887,11 +887,33 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     fflush(stdout);
     if (g_clock.on) fprintf(stderr, "[timing]   decode (PgrGet) %.3f s, pl2gpu_king_add_variants %.3f s\n", t_decode, t_add);
     g_clock.Mark("king: decode + add_variants");
+    // --make-king-table with --king-table-filter and nothing else to produce: filter on the device and
+    // fetch only the surviving rows (the unfiltered table is 20 bytes x N^2/2)
+    const bool device_filter = want_table && !want_matrix && c.king_cutoff < 0 && c.king_table_filter != -DBL_MAX;
+    if (device_filter) {
+      std::vector<uint32_t> fp, fc;
+      std::vector<double> fk;
+      uint64_t cap = 1ull << 22, found = 0;
+      for (;;) {
+        fp.resize(cap * 2);
+        fc.resize(cap * 5);
+        fk.resize(cap);
+        if (pl2gpu_king_get_filtered(job, row_start, row_end, c.king_table_filter, cap, fp.data(), fc.data(), fk.data(), &found)) {
+          pl2gpu_king_end(job);
+          return GpuFail("pl2gpu_king_get_filtered");
+        }
+        if (found <= cap) break;
+        cap = found;
+      }
+      for (uint64_t q = 0; q < found; ++q) WriteKingTableRow(c, fmtids[fp[2 * q]], fmtids[fp[2 * q + 1]], &fc[5 * q], fk[q], &ftab);
+      auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
+      filter_ct += tri(row_end) - tri(row_start) - found;
+    }
     // results in row chunks of <= ~512 MB
     const uint64_t max_pairs = (512ull << 20) / 20;
     std::vector<uint32_t> counts;
     std::vector<double> kin;
-    for (uint32_t c0 = row_start; c0 < row_end;) {
+    for (uint32_t c0 = row_start; c0 < row_end && !device_filter;) {
       uint32_t c1 = c0 + 1;
       auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
       while (c1 < row_end && tri(c1 + 1) - tri(c0) <= max_pairs) ++c1;

@@ -452,4 +452,47 @@ king_finalize_kernel(const int32_t* __restrict__ raw_acc, const uint32_t* __rest
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// `--king-table-filter` on the device: append only the pairs of rows [row_start, row_end) whose
+// kinship is not below `min_kinship` (NaN is kept, as the reference's `kinship < filter` test does,
+// 2.0/plink2_matrix_calc.cc:2296-2300).  At 100k samples the unfiltered table is 5e9 pairs = 100 GB of
+// counts; relationship screening keeps a few thousand of them.  One CTA per tile, thread = tile row.
+// Slots are handed out with an atomic counter, so the output order is arbitrary (the host sorts).
+// ---------------------------------------------------------------------------------------------
+template <uint32_t kCols>
+__global__ void __launch_bounds__(kTileRows)
+king_filter_kernel(const int32_t* __restrict__ raw_acc, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, double min_kinship, unsigned long long max_out,
+                   unsigned long long* __restrict__ found, uint32_t* __restrict__ out_pairs, uint32_t* __restrict__ out_counts, double* __restrict__ out_kinship) {
+  const uint32_t tile = blockIdx.x;
+  const uint32_t j = tile_rt[tile] * kTileRows + threadIdx.x;
+  const uint32_t col_base = tile_tc[tile] * kCols;
+  if (j < row_start || j >= row_end || j >= sample_ct) return;
+  const int32_t* acc = raw_acc + static_cast<uint64_t>(tile) * (5 * kCols * kTileRows) + threadIdx.x;
+  for (uint32_t cl = 0; cl < kCols; ++cl) {
+    const uint32_t i = col_base + cl;
+    if (i >= j) break;
+    const int32_t tt = acc[static_cast<uint64_t>(cl) * kTileRows];
+    const int32_t th = acc[static_cast<uint64_t>(kCols + cl) * kTileRows];
+    const int32_t ht = acc[static_cast<uint64_t>(2 * kCols + cl) * kTileRows];
+    const int32_t hh = acc[static_cast<uint64_t>(3 * kCols + cl) * kTileRows];
+    const int32_t ss = acc[static_cast<uint64_t>(4 * kCols + cl) * kTileRows];
+    const int64_t ibs0 = (hh - ss) >> 1;
+    const int64_t het2hom1 = th, het1hom2 = ht;
+    const int64_t smaller_het = tt + (het1hom2 < het2hom1 ? het1hom2 : het2hom1);
+    const double kinship = 0.5 - static_cast<double>(4 * ibs0 + het1hom2 + het2hom1) / static_cast<double>(4 * smaller_het);
+    if (kinship < min_kinship) continue;
+    const unsigned long long slot = atomicAdd(found, 1ull);
+    if (slot >= max_out) continue;
+    out_pairs[2 * slot] = j;
+    out_pairs[2 * slot + 1] = i;
+    uint32_t* c = out_counts + 5 * slot;
+    c[0] = static_cast<uint32_t>(ibs0);
+    c[1] = static_cast<uint32_t>(tt);
+    c[2] = static_cast<uint32_t>(th);
+    c[3] = static_cast<uint32_t>(ht);
+    c[4] = static_cast<uint32_t>(hh);
+    out_kinship[slot] = kinship;
+  }
+}
+
 }  // namespace pl2

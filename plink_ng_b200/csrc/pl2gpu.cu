@@ -508,6 +508,71 @@ int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t ou
   return KingGet(job, out_row_start, out_row_end, dst, dst_is_device, true);
 }
 
+int pl2gpu_king_get_filtered(Pl2KingJob* job, uint32_t r0, uint32_t r1, double min_kinship, uint64_t max_out, uint32_t* pairs_out, uint32_t* counts_out, double* kinship_out, uint64_t* n_found) {
+  if (!job || !n_found || (max_out && (!pairs_out || !counts_out || !kinship_out))) {
+    set_error("pl2gpu_king_get_filtered: bad arguments");
+    return 1;
+  }
+  if (r0 < job->row_start || r1 > job->row_end || r0 > r1) {
+    set_error("pl2gpu_king_get_filtered: rows [%u,%u) outside the job's [%u,%u)", r0, r1, job->row_start, job->row_end);
+    return 1;
+  }
+  *n_found = 0;
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  if (!job->tiles.tile_ct || r0 == r1) return 0;
+  unsigned long long* d_found = nullptr;
+  uint32_t *d_pairs = nullptr, *d_counts = nullptr;
+  double* d_kin = nullptr;
+  const uint64_t cap = max_out ? max_out : 1;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_found, 8) != cudaSuccess || cudaMalloc(&d_pairs, cap * 8) != cudaSuccess || cudaMalloc(&d_counts, cap * 20) != cudaSuccess || cudaMalloc(&d_kin, cap * 8) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_king_get_filtered: insufficient device memory for %llu result slots", static_cast<unsigned long long>(max_out));
+      break;
+    }
+    if (cudaMemsetAsync(d_found, 0, 8, c->stream) != cudaSuccess) break;
+    if (job->tile_cols == kTsCols) {
+      king_filter_kernel<kTsCols><<<job->tiles.tile_ct, kTileRows, 0, c->stream>>>(job->d_raw_acc, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->sample_ct, r0, r1, min_kinship, max_out, d_found, d_pairs, d_counts, d_kin);
+    } else {
+      king_filter_kernel<kTileCols><<<job->tiles.tile_ct, kTileRows, 0, c->stream>>>(job->d_raw_acc, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->sample_ct, r0, r1, min_kinship, max_out, d_found, d_pairs, d_counts, d_kin);
+    }
+    c->launches++;
+    unsigned long long found = 0;
+    if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(&found, d_found, 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_king_get_filtered: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    *n_found = found;
+    const uint64_t k = found < max_out ? found : max_out;
+    if (k) {
+      std::vector<uint32_t> hp(2 * k), hc(5 * k);
+      std::vector<double> hk(k);
+      if (cudaMemcpy(hp.data(), d_pairs, k * 8, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(hc.data(), d_counts, k * 20, cudaMemcpyDeviceToHost) != cudaSuccess || cudaMemcpy(hk.data(), d_kin, k * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_error("pl2gpu_king_get_filtered: %s", cudaGetErrorString(cudaGetLastError()));
+        break;
+      }
+      std::vector<uint64_t> order(k);
+      for (uint64_t q = 0; q < k; ++q) order[q] = q;
+      std::sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) { return hp[2 * a] != hp[2 * b] ? hp[2 * a] < hp[2 * b] : hp[2 * a + 1] < hp[2 * b + 1]; });
+      for (uint64_t q = 0; q < k; ++q) {
+        const uint64_t src = order[q];
+        pairs_out[2 * q] = hp[2 * src];
+        pairs_out[2 * q + 1] = hp[2 * src + 1];
+        memcpy(counts_out + 5 * q, &hc[5 * src], 20);
+        kinship_out[q] = hk[src];
+      }
+    }
+    rc = 0;
+  } while (0);
+  cudaFree(d_found);
+  cudaFree(d_pairs);
+  cudaFree(d_counts);
+  cudaFree(d_kin);
+  return rc;
+}
+
 uint64_t pl2gpu_king_variants_added(Pl2KingJob* job) { return job ? job->variants_added : 0; }
 
 int pl2gpu_king_end(Pl2KingJob* job) {

@@ -136,6 +136,22 @@ class KingJob:
         check(lib.pl2gpu_king_get_kinship(self._h, r0, r1, out.ctypes.data, 0), "pl2gpu_king_get_kinship")
         return out
 
+    def filtered(self, min_kinship: float, max_out: int = 1 << 20, row_start: int = None, row_end: int = None):
+        """--king-table-filter on the device: (pairs [k,2] = (j, i), counts [k,5], kinship [k]) in table order,
+        only pairs whose kinship is not below min_kinship.  Grows the buffers and retries on overflow."""
+        r0 = self.row_start if row_start is None else row_start
+        r1 = self.row_end if row_end is None else row_end
+        while True:
+            pairs = np.empty((max_out, 2), dtype=np.uint32)
+            counts = np.empty((max_out, 5), dtype=np.uint32)
+            kin = np.empty(max_out, dtype=np.float64)
+            found = C.c_uint64(0)
+            check(lib.pl2gpu_king_get_filtered(self._h, r0, r1, min_kinship, max_out, pairs.ctypes.data, counts.ctypes.data, kin.ctypes.data, C.byref(found)), "pl2gpu_king_get_filtered")
+            if found.value <= max_out:
+                k = found.value
+                return pairs[:k], counts[:k], kin[:k]
+            max_out = int(found.value)
+
     def counts_to_device(self, dev_ptr: int, row_start: int, row_end: int):
         check(lib.pl2gpu_king_get_counts(self._h, row_start, row_end, C.c_void_p(dev_ptr), 1), "pl2gpu_king_get_counts")
 

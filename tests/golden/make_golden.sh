@@ -25,6 +25,8 @@ $P --bfile a --make-king square --threads 2 --out $T/a_kingsq > /dev/null
 gzip -9 -n -c $T/a_kingsq.king > a_kingsq.king.gz; cp $T/a_kingsq.king.id a_kingsq.king.id
 $P --bfile a --make-king-table counts --parallel 2 3 --threads 2 --out $T/a_kingpar > /dev/null
 gzip -9 -n -c $T/a_kingpar.kin0.2 > a_kingpar.kin0.2.gz
+$P --bfile a --make-king-table counts --king-table-filter 0.02 --threads 2 --out $T/a_kf > /dev/null
+cp $T/a_kf.kin0 a_kingfilt.kin0
 # pair-list KING (--king-table-subset): (1) the proportion table above as the pair list with a kinship threshold,
 # (2) a hand-written IID-only list with swapped orientation, an unknown ID and ibs1 columns
 zcat a_kingp.kin0.gz > $T/in.kin0

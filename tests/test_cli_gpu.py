@@ -49,6 +49,14 @@ def test_make_king_table_parallel_piece(golden_dir, tmp_path):
     assert open(out + ".kin0.2", "rb").read() == gz(golden_dir, "a_kingpar.kin0.2.gz")
 
 
+def test_king_table_filter_byte_identical(golden_dir, tmp_path):
+    """--king-table-filter runs on the device (pl2gpu_king_get_filtered); same rows, same order, same log count."""
+    out = run(golden_dir, tmp_path, "--make-king-table", "counts", "--king-table-filter", "0.02")
+    assert open(out + ".kin0", "rb").read() == open(os.path.join(golden_dir, "a_kingfilt.kin0"), "rb").read()
+    log = open(out + ".log").read()
+    assert "--king-table-filter: 662 relationships reported (4288 filtered out)." in log
+
+
 def test_king_table_subset_byte_identical(golden_dir, tmp_path):
     """--king-table-subset (pair-list kernel): the reference's own .kin0 as the pair list + kinship threshold, and a
     hand-written IID-only list with swapped orientation and an unknown ID."""

@@ -96,6 +96,28 @@ def test_king_pair_list_matches_oracle(gpu_ctx, n, m, pair_ct):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("algo", ALGOS)
+def test_king_filter_on_device_matches_host_filter(gpu_ctx, algo):
+    """pl2gpu_king_get_filtered == filtering the full table on the host (same fp64 kinship, table order, NaN kept),
+    including the buffer-overflow retry and a row sub-range."""
+    n, m = 333, 900
+    geno = _random_geno(m, n, seed=21)
+    geno[:, 5] = 0  # a sample without heterozygous calls -> 0/0 kinship with another such sample
+    geno[:, 9] = 2
+    with KingJob(gpu_ctx, n, 0, n, algo) as job:
+        job.add_variants(pack_genotypes(geno))
+        counts, kin = job.counts(), job.kinship()
+        ii = np.array([(j, i) for j in range(1, n) for i in range(j)], dtype=np.uint32)
+        for thr, r0, r1, cap in ((0.02, 0, n, 1 << 16), (-0.1, 0, n, 7), (0.0, 100, 250, 1 << 16)):
+            tri = lambda r: r * (r - 1) // 2  # noqa: E731
+            sl = slice(tri(r0), tri(r1))
+            keep = ~(kin[sl] < thr)
+            p, c, k = job.filtered(thr, cap, r0, r1)
+            assert np.array_equal(p, ii[sl][keep]) and np.array_equal(c, counts[sl][keep])
+            assert np.array_equal(k, kin[sl][keep], equal_nan=True)
+            assert np.isnan(k).any() or thr != -0.1
+
+
 def test_king_large_block_marginal_identities(gpu_ctx):
     """Size-independent check at a size the pairwise oracle cannot reach (2e8 pairs): summed over all pairs, every
     KING count is a per-variant closed form of the genotype counts n0 (hom-REF), n1 (het), n2 (hom-ALT):
