@@ -77,6 +77,8 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     const uint32_t grp = warp >> 2;
     const uint32_t lq = warp & 3;
     const uint32_t row = 32 * lq + lane;
+    const uint32_t thread_zero = tid * (variant_ct_padded >> 31);  // 0; keeps the tables in vector registers (geno_expand.cuh)
+    const uint32_t tab_g = table_reg(kTabDosage, thread_zero), tab_m = table_reg(kTabNonmiss, thread_zero);
     const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt) * (2 * stage_iters) * 1024 + row * 8;
     const uint32_t ta = tmem_base + ((32u * lq) << 16) + kGtsAccCols + grp * kGtsASlotCols;
     auto load_i = [&](uint32_t n) -> uint2 {
@@ -88,7 +90,7 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     auto expand_i = [&](const uint2& w) -> ExpI {
       ExpI e;
       const Sel4 s0 = make_selectors(w.x), s1 = make_selectors(w.y);
-      const uint32_t tabs[2] = {kTabDosage, kTabNonmiss};
+      const uint32_t tabs[2] = {tab_g, tab_m};
 #pragma unroll
       for (int p = 0; p < 2; ++p) {
         const uint4 a = expand16(tabs[p], s0), b = expand16(tabs[p], s1);

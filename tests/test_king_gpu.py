@@ -102,8 +102,8 @@ def test_king_filter_on_device_matches_host_filter(gpu_ctx, algo):
     including the buffer-overflow retry and a row sub-range."""
     n, m = 333, 900
     geno = _random_geno(m, n, seed=21)
-    geno[:, 5] = 0  # a sample without heterozygous calls -> 0/0 kinship with another such sample
-    geno[:, 9] = 2
+    geno[:, 5] = 0  # two all-hom-REF samples: no het, no opposite homozygotes -> 0/0 = NaN kinship for the pair (9, 5)
+    geno[:, 9] = 0
     with KingJob(gpu_ctx, n, 0, n, algo) as job:
         job.add_variants(pack_genotypes(geno))
         counts, kin = job.counts(), job.kinship()
