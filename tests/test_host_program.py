@@ -106,3 +106,29 @@ int main(int argc, char** argv) {
     subprocess.run([BIN, "--debug-gauss", "11", str(pairs), "4", str(tmp_path / "g2.f64")], check=True)
     g2 = np.fromfile(tmp_path / "g2.f64", dtype=np.float64)
     assert g2.shape[0] == 2 * pairs and np.isfinite(g2).all() and abs(g2.mean()) < 0.01 and abs(g2.std() - 1) < 0.01
+
+
+@pytest.mark.parametrize("flags,fragment", [
+    (("--glm",), "unsupported"),
+    (("--make-grm-bin", "--make-grm-list"), "--make-grm-list cannot be used with --make-grm-bin"),
+    (("--make-grm-list", "zs"), "not supported"),
+    (("--indep-preferred", "x.txt"), "--indep-preferred must be used with --indep-pairwise"),
+    (("--make-king-table", "--king-table-subset"), "--king-table-subset requires"),
+    (("--pca", "0"), "Invalid --pca PC count"),
+    (("--indep-pairwise", "50"), "--indep-pairwise requires 2-4 arguments"),
+])
+def test_command_line_errors_exit_8_before_touching_the_gpu(golden_dir, tmp_path, flags, fragment):
+    """kPglRetInvalidCmdline = 8, as the reference; the command line is validated before any CUDA call, so this
+    runs on a machine without a GPU."""
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), *flags, "--out", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode == 8, r.stdout + r.stderr
+    assert fragment in r.stdout + r.stderr
+
+
+def test_no_gpu_means_loud_failure_not_a_cpu_fallback(golden_dir, tmp_path):
+    """Without a visible device the program must stop with kPglRetGpuFail-style code 16 - there is no CPU path."""
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--make-king-table", "--out", str(tmp_path / "x")], capture_output=True, text=True, env=env)
+    assert r.returncode == 16, r.stdout + r.stderr
+    assert "GPU" in r.stdout
+    assert not os.path.exists(str(tmp_path / "x") + ".kin0")
