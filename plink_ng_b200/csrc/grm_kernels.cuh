@@ -33,20 +33,7 @@ constexpr uint32_t kGrmPlanesJ = 2 * kGrmLimbs + 1;
 constexpr uint32_t kGrmGroupsJ = kGrmTileCols / 16;  // 16-sample groups per J plane
 constexpr uint32_t kGrmTabPlanes = 12;          // uint32 tables per variant (11 used)
 constexpr uint32_t kGrmKc = 64;                 // variants per stage = two UMMA k-steps
-constexpr uint32_t kGrmStages = 3;
-constexpr uint32_t kGrmLookahead = 3;
-constexpr uint32_t kGrmSuperI = 2 * kTileRows;            // g, m
-constexpr uint32_t kGrmSuperJ = kGrmPlanesJ * kGrmTileCols;  // 880
-constexpr uint32_t kGrmLboI = operand_lbo(kGrmSuperI);    // 2048
-constexpr uint32_t kGrmLboJ = operand_lbo(kGrmSuperJ);    // 7040
-constexpr uint32_t kGrmStageBytesI = kGrmSuperI * kGrmKc;
-constexpr uint32_t kGrmStageBytesJ = kGrmSuperJ * kGrmKc;
-constexpr uint32_t kGrmStageBytes = kGrmStageBytesI + kGrmStageBytesJ;
-constexpr uint32_t kGrmSmemBytes = kGrmStages * kGrmStageBytes + 1024;
-constexpr uint32_t kGrmProducerThreads = 256;
-constexpr uint32_t kGrmThreads = kGrmProducerThreads + 32;
 constexpr uint32_t kGrmTileWords = kTileRows * kGrmTileCols;  // per-tile accumulator entries
-static_assert(kGrmSmemBytes <= 232448, "GRM pipeline exceeds the 227 KB shared-memory opt-in limit");
 static_assert((kGrmLimbs + 1) * kGrmTileCols <= 512, "GRM accumulators exceed TMEM");
 
 // ---- per-variant digit tables, byte c of a table = digit of that plane for genotype code c.
