@@ -89,7 +89,8 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
   if (!ReadLines(path, &lines, err)) return false;
   size_t li = 0;
   while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
-  int col_chr, col_pos, col_id;
+  int col_chr, col_pos, col_id, col_ref = -1, col_alt = -1;
+  bool is_bim = false;
   if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
     // .pvar header: #CHROM POS ID REF ALT ...
     std::vector<std::string> hdr = SplitWs(lines[li].substr(1));
@@ -98,6 +99,8 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
       if (hdr[c] == "CHROM") col_chr = static_cast<int>(c);
       else if (hdr[c] == "POS") col_pos = static_cast<int>(c);
       else if (hdr[c] == "ID") col_id = static_cast<int>(c);
+      else if (hdr[c] == "REF") col_ref = static_cast<int>(c);
+      else if (hdr[c] == "ALT") col_alt = static_cast<int>(c);
     }
     if (col_chr != 0 || col_pos < 0 || col_id < 0) {
       *err = "Invalid .pvar header line in " + path + ".";
@@ -109,13 +112,20 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     col_chr = 0;
     col_id = 1;
     col_pos = 3;
+    col_alt = 4;
+    col_ref = 5;
+    is_bim = true;
   }
   for (; li < lines.size(); ++li) {
     if (lines[li].empty()) continue;
     std::vector<std::string> t = SplitWs(lines[li]);
     if (t.empty()) continue;
-    int cpos = col_pos;
-    if (col_pos == 3 && t.size() == 5) cpos = 2;
+    int cpos = col_pos, cref = col_ref, calt = col_alt;
+    if (is_bim && t.size() == 5) {
+      cpos = 2;
+      calt = 3;
+      cref = 4;
+    }
     if (static_cast<int>(t.size()) <= std::max(cpos, col_id)) {
       *err = "Line " + std::to_string(li + 1) + " of " + path + " has fewer tokens than expected.";
       return false;
@@ -128,6 +138,9 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     out->chr_code.push_back(code);
     out->bp.push_back(static_cast<uint32_t>(strtoul(t[cpos].c_str(), nullptr, 10)));
     out->id.push_back(t[col_id]);
+    out->chr_name.push_back(t[col_chr]);
+    out->ref.push_back(cref >= 0 && cref < static_cast<int>(t.size()) ? t[cref] : std::string("."));
+    out->alt.push_back(calt >= 0 && calt < static_cast<int>(t.size()) ? t[calt] : std::string("."));
   }
   return true;
 }

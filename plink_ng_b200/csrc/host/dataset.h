@@ -23,6 +23,8 @@ struct VariantInfo {
   std::vector<uint32_t> chr_code;  // 0 = unplaced, 1..22 autosomes, 23 X, 24 Y, 25 XY, 26 MT
   std::vector<uint32_t> bp;
   std::vector<std::string> id;
+  std::vector<std::string> chr_name, ref, alt;  // as written in the file (.bim: REF = column 6, ALT = column 5)
+  bool provisional_ref = false;                 // .bim input: REF alleles are provisional (PROVISIONAL_REF? = Y)
   uint32_t size() const { return static_cast<uint32_t>(id.size()); }
 };
 

@@ -101,6 +101,7 @@ bool PgenReader::Open(const std::string& path, uint32_t raw_sample_ct, uint32_t 
       return false;
     }
     const uint8_t fb = map_[11];
+    nonref_mode_ = fb >> 6;
     if (mode_ == 0x02) {
       fixed_bpv_ = (raw_sample_ct_ + 3) / 4;
       fixed_start_ = 12;

@@ -24,6 +24,9 @@ class PgenReader {
 
   uint32_t raw_sample_ct() const { return raw_sample_ct_; }
   uint32_t raw_variant_ct() const { return raw_variant_ct_; }
+  // header bits 6-7 (pgenlib_read.cc:874): 1 = every REF allele trusted, 2 = all provisional (always for .bed,
+  // :790), 3 = per-variant flags stored, 0 = not recorded
+  uint32_t nonref_flags_storage() const { return mode_ == 0x01 ? 2u : nonref_mode_; }
   // uint64 words per variant for n samples: ceil(n / 32)
   static uint32_t WordsFor(uint32_t n) { return (n + 31) / 32; }
 
@@ -43,6 +46,7 @@ class PgenReader {
   const uint8_t* map_ = nullptr;
   uint64_t map_len_ = 0;
   uint8_t mode_ = 0;
+  uint32_t nonref_mode_ = 0;
   uint32_t raw_sample_ct_ = 0;
   uint32_t raw_variant_ct_ = 0;
   uint64_t fixed_start_ = 0;      // modes 0x01/0x02: offset of record 0

@@ -78,6 +78,7 @@ struct Cmd {
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
   // GRM
+  bool freq = false;                      // --freq
   std::string indep_preferred;            // --indep-preferred <file of variant IDs>
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
@@ -254,6 +255,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else return Usage(("Invalid or unsupported --pca argument '" + m + "'.").c_str());
       }
       if (c->pc_ct < 1 || c->pc_ct > 8000) return Usage("Invalid --pca PC count.");
+    } else if (flag == "--freq") {
+      if (nparam) return Usage("--freq modifiers (counts, zs, cols=, bins) are not supported by plink2_b200.");
+      c->freq = true;
     } else if (flag == "--indep-preferred") {
       if (!need(1, 1)) return Usage("--indep-preferred requires a filename.");
       c->indep_preferred = prm[0];
@@ -315,7 +319,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
   if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_rel || c->pca || c->indep_pairwise)) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_rel || c->pca || c->indep_pairwise || c->freq)) return Usage("No command given.");
   return 0;
 }
 
@@ -1426,6 +1430,88 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
 }
 
 // --------------------------------------------------------------------------------------- LD prune
+// `--freq` (WriteAlleleFreqs, 2.0/plink2_misc.cc:3573; counts from the LoadAlleleAndGenoCounts pass,
+// 2.0/plink2.cc:2280): founder ALT allele frequencies of biallelic hard calls -> <out>.afreq.
+int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  for (uint32_t v = 0; v < m; ++v) {
+    if (V.chr_code[v] > 22 && V.chr_code[v] != 25) {
+      logprintf("Error: --freq on chrX/chrY/chrMT variants (sex-dependent ploidy) is not supported by plink2_b200 yet.\n");
+      return kRetNotYetSupported;
+    }
+  }
+  uint32_t founder_ct = 0;
+  std::vector<uint64_t> inc((n + 63) / 64, 0);
+  for (uint32_t k = 0; k < n; ++k) {
+    if (S.is_founder[k]) {
+      inc[k / 64] |= 1ull << (k % 64);
+      ++founder_ct;
+    }
+  }
+  if (!founder_ct) {
+    logprintf("Error: No founders for --freq.\n");
+    return kRetDegenerateData;
+  }
+  if (ds->reader.nonref_flags_storage() == 3) {
+    logprintf("Error: --freq on a .pgen with per-variant provisional-REF flags is not supported by plink2_b200 yet.\n");
+    return kRetNotYetSupported;
+  }
+  std::vector<uint32_t> all(m);
+  for (uint32_t v = 0; v < m; ++v) all[v] = v;
+  BlockStreamer bs(ds, &all, founder_ct, 16384);
+  if (founder_ct != n) bs.sample_include = inc.data();
+  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  const std::string name = c.out + ".afreq";
+  OutFile f;
+  if (!f.Open(name)) return kRetOpenFail;
+  f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
+  std::vector<uint32_t> counts;
+  std::string err;
+  size_t base = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("Error: %s\n", err.c_str());
+      return kRetMalformedInput;
+    }
+    if (!got) break;
+    counts.resize(4ull * got);
+    if (pl2gpu_geno_counts(ctx, bs.buf, static_cast<uint64_t>(bs.words) * 8, founder_ct, static_cast<uint32_t>(got), 0, counts.data())) return GpuFail("pl2gpu_geno_counts");
+    for (int k = 0; k < got; ++k) {
+      const uint32_t v = static_cast<uint32_t>(base) + k;
+      const uint64_t n0 = counts[4ull * k], n1 = counts[4ull * k + 1], n2 = counts[4ull * k + 2];
+      // allele "ddosages" in 1/32768 units, as the reference accumulates them (:3746-3772, :3833)
+      const uint64_t alt_dd = (n1 + 2 * n2) * 32768ull, tot_dd = 2 * (n0 + n1 + n2) * 32768ull;
+      const double recip = tot_dd ? 1.0 / static_cast<double>(tot_dd) : 0.0;
+      char* w = f.Reserve(V.chr_name[v].size() + V.id[v].size() + V.ref[v].size() + V.alt[v].size() + 96);
+      auto puts = [&](const std::string& t) {
+        memcpy(w, t.data(), t.size());
+        w += t.size();
+        *w++ = '\t';
+      };
+      puts(V.chr_name[v]);
+      puts(V.id[v]);
+      puts(V.ref[v]);
+      puts(V.alt[v]);
+      if (V.provisional_ref) {
+        *w++ = 'Y';
+        *w++ = '\t';
+      }
+      w = dtoa_g(static_cast<double>(alt_dd) * recip, w);
+      *w++ = '\t';
+      w = u32toa(static_cast<uint32_t>(tot_dd / 32768ull), w);
+      *w++ = '\n';
+      f.Advance(w);
+    }
+    base += static_cast<size_t>(got);
+  }
+  if (!f.Close()) return kRetWriteFail;
+  logprintf("--freq: Allele frequencies (founders only) written to %s .\n", name.c_str());
+  return 0;
+}
+
 int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
@@ -1635,6 +1721,7 @@ int main(int argc, char** argv) {
     logprintf("Error: %s\n", err.c_str());
     return kRetMalformedInput;
   }
+  ds.variants.provisional_ref = ds.reader.nonref_flags_storage() == 2;
   uint32_t founder_ct = 0;
   for (uint8_t f : ds.samples.is_founder) founder_ct += f;
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
@@ -1646,6 +1733,10 @@ int main(int argc, char** argv) {
     return kRetGpuFail;
   }
   g_clock.Mark("pl2gpu_ctx_create");
+  if (c.freq) {
+    rc = RunFreq(c, &ds, ctx);
+    if (rc) return rc;
+  }
   std::vector<uint8_t> cutoff_removed;
   if (!c.king_table_subset.empty()) {
     if (!c.make_king_table || c.make_king || c.king_cutoff >= 0) {

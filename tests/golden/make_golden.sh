@@ -39,6 +39,8 @@ $P --bfile a --king-cutoff 0.02 --threads 2 --out $T/a_cut > /dev/null
 cp $T/a_cut.king.cutoff.in.id a_cut.king.cutoff.in.id; cp $T/a_cut.king.cutoff.out.id a_cut.king.cutoff.out.id
 $P --bfile a --freq --threads 2 --out $T/a_freq > /dev/null
 cp $T/a_freq.afreq a.afreq
+$P --pgen a_mode02.pgen --pvar a.pvar --psam a.psam --freq --threads 2 --out $T/a_pf > /dev/null   # REF not provisional: no PROVISIONAL_REF? column
+cp $T/a_pf.afreq a_pvar.afreq
 $P --bfile a --make-grm-bin --threads 2 --out $T/a_grm > /dev/null
 cp $T/a_grm.grm.bin a_grm.grm.bin; cp $T/a_grm.grm.N.bin a_grm.grm.N.bin; cp $T/a_grm.grm.id a_grm.grm.id
 $P --bfile a --make-grm-bin meanimpute --threads 2 --out $T/a_grmmi > /dev/null

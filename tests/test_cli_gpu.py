@@ -131,6 +131,13 @@ def test_indep_pairwise_lists_byte_identical(golden_dir, tmp_path, flags, name):
         assert open(out + ".prune.out", "rb").read() == open(os.path.join(golden_dir, "a_ld.prune.out"), "rb").read()
 
 
+@pytest.mark.parametrize("inp,name", [("bfile", "a.afreq"), ("pfile02", "a_pvar.afreq")])
+def test_freq_byte_identical(golden_dir, tmp_path, inp, name):
+    """--freq: genotype counts on the device (pl2gpu_geno_counts), .afreq text as the reference writes it."""
+    out = run(golden_dir, tmp_path, "--freq", inp=inp)
+    assert open(out + ".afreq", "rb").read() == open(os.path.join(golden_dir, name), "rb").read()
+
+
 def test_indep_preferred_list_byte_identical(golden_dir, tmp_path):
     out = run(golden_dir, tmp_path, "--indep-pairwise", "50", "5", "0.1", "--indep-preferred", os.path.join(golden_dir, "a_pref.txt"))
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldpref.prune.in"), "rb").read()
