@@ -131,7 +131,7 @@ def test_indep_pairwise_lists_byte_identical(golden_dir, tmp_path, flags, name):
         assert open(out + ".prune.out", "rb").read() == open(os.path.join(golden_dir, "a_ld.prune.out"), "rb").read()
 
 
-@pytest.mark.parametrize("inp,name", [("bfile", "a.afreq"), ("pfile02", "a_pvar.afreq")])
+@pytest.mark.parametrize("inp,name", [("bfile", "a.afreq"), ("a_mode02.pgen", "a_pvar.afreq"), ("a_mode10.pgen", "a_pvar.afreq")])
 def test_freq_byte_identical(golden_dir, tmp_path, inp, name):
     """--freq: genotype counts on the device (pl2gpu_geno_counts), .afreq text as the reference writes it."""
     out = run(golden_dir, tmp_path, "--freq", inp=inp)
