@@ -11,6 +11,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+    # built artefacts are not in git: build them once if this is a fresh checkout
+    pkg = os.path.join(ROOT, "plink_ng_b200")
+    if not (os.path.exists(os.path.join(pkg, "libpl2gpu.so")) and os.path.exists(os.path.join(pkg, "plink2_b200"))):
+        import subprocess
+
+        subprocess.run(["make", "-C", os.path.join(pkg, "csrc")], check=True, stdout=subprocess.DEVNULL)
 
 
 @pytest.fixture(scope="session")
