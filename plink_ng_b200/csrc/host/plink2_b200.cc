@@ -82,6 +82,8 @@ struct Cmd {
   std::string indep_preferred;            // --indep-preferred <file of variant IDs>
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
+  bool make_grm_sparse = false;            // --make-grm-sparse <cutoff>
+  double grm_sparse_cutoff = -DBL_MAX;
   bool make_grm_bin = false, make_grm_list = false, make_rel = false, grm_cov = false, grm_meanimpute = false, grm_id_header = false;
   // PCA
   bool pca = false, pca_approx = false, pca_meanimpute = false;
@@ -225,7 +227,25 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--king-cutoff") {
       if (nparam == 2) return Usage("--king-cutoff with a precomputed matrix prefix is not supported by plink2_b200.");
       if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
+    } else if (flag == "--make-grm-sparse") {
+      // <cutoff> ['cov'] ['meanimpute'] ['id-header']   (plink2.cc:9178-9226)
+      if (!need(1, 5)) return Usage("--make-grm-sparse requires a relationship cutoff.");
+      if (c->make_grm_bin) return Usage("--make-grm-sparse cannot be used with --make-grm-bin.");
+      if (c->make_grm_list) return Usage("--make-grm-sparse cannot be used with --make-grm-list.");
+      double dxx;
+      if (!ParseDouble(prm[0], &dxx)) return Usage((std::string("Invalid --make-grm-sparse threshold '") + prm[0] + "'.").c_str());
+      c->grm_sparse_cutoff = dxx * (1.0 - 1.0 / 17592186044416.0);
+      c->make_grm_sparse = true;
+      for (int k = 1; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "cov") c->grm_cov = true;
+        else if (m == "meanimpute") c->grm_meanimpute = true;
+        else if (m == "id-header" || m == "idheader") c->grm_id_header = true;
+        else if (m == "zs") return Usage("--make-grm-sparse 'zs' output is not supported by plink2_b200.");
+        else return Usage(("Invalid --make-grm-sparse argument '" + m + "'.").c_str());
+      }
     } else if (flag == "--make-grm-bin" || flag == "--make-grm-list" || flag == "--make-rel") {
+      if (c->make_grm_sparse) return Usage((flag + " cannot be used with --make-grm-sparse.").c_str());
       const bool is_rel = flag == "--make-rel";
       (is_rel ? c->make_rel : (flag == "--make-grm-list" ? c->make_grm_list : c->make_grm_bin)) = true;
       if (c->make_grm_bin && c->make_grm_list) return Usage("--make-grm-list cannot be used with --make-grm-bin.");
@@ -319,7 +339,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
   if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_rel || c->pca || c->indep_pairwise || c->freq)) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq)) return Usage("No command given.");
   return 0;
 }
 
@@ -1144,7 +1164,7 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   int rc = 0;
   const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
   if (rc) return rc;
-  const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_grm_list && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
+  const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_grm_list && !c.make_grm_sparse && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
   Pl2GrmJob* job = nullptr;
   if (pl2gpu_grm_begin(ctx, n, r0, r1, flags, &job)) return GpuFail("pl2gpu_grm_begin");
   BlockStreamer bs(ds, &vidx, n, 32768);
@@ -1245,6 +1265,45 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     }
     if (!fg.Close()) return kRetWriteFail;
     std::string msg = std::string("--make-grm-list: GRM ") + (c.parallel_tot != 1 ? "component " : "") + "written to " + gname;
+    if (!c.parallel_idx) {
+      const std::string idname = c.out + ".grm.id";
+      std::vector<uint32_t> all(n);
+      for (uint32_t k = 0; k < n; ++k) all[k] = k;
+      if (!WriteIdFile(idname, S, all, c.grm_id_header)) return kRetWriteFail;
+      msg += " , and IDs to " + idname;
+    }
+    logprintf("%s .\n", msg.c_str());
+  }
+  if (c.make_grm_sparse) {
+    // `.grm.sp` (GCTA sparse GRM): "j <tab> i <tab> value" (0-based, 8 significant digits) for every i <= j whose
+    // value is not below the cutoff (2.0/plink2_matrix_calc.cc:5064-5081)
+    const std::string gname = PieceName(c.out + ".grm.sp", c);
+    OutFile fg;
+    if (!fg.Open(gname)) return kRetOpenFail;
+    for (uint32_t a = r0; a < r1;) {
+      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      if (!fetch(a, b)) {
+        pl2gpu_grm_end(job);
+        return GpuFail("pl2gpu_grm_get_rows");
+      }
+      for (uint32_t j = a; j < b; ++j) {
+        const double* gr = &g[static_cast<uint64_t>(j - a) * stride];
+        for (uint32_t i = 0; i <= j; ++i) {
+          if (gr[i] < c.grm_sparse_cutoff) continue;
+          char* w = fg.Reserve(64);
+          w = u32toa(j, w);
+          *w++ = '\t';
+          w = u32toa(i, w);
+          *w++ = '\t';
+          w = dtoa_g_p8(gr[i], w);
+          *w++ = '\n';
+          fg.Advance(w);
+        }
+      }
+      a = b;
+    }
+    if (!fg.Close()) return kRetWriteFail;
+    std::string msg = std::string("--make-grm-sparse: GRM ") + (c.parallel_tot != 1 ? "component " : "") + "written to " + gname;
     if (!c.parallel_idx) {
       const std::string idname = c.out + ".grm.id";
       std::vector<uint32_t> all(n);
@@ -1628,14 +1687,15 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
 //   --debug-dtoa <in: raw doubles> <out: one dtoa_g line each>
 //   --debug-dump-geno <pgen> <psam/fam> <pvar/bim> <out: one byte per genotype, variant-major>
 int DebugHooks(int argc, char** argv) {
-  if (argc == 4 && !strcmp(argv[1], "--debug-dtoa")) {
+  if (argc == 4 && (!strcmp(argv[1], "--debug-dtoa") || !strcmp(argv[1], "--debug-dtoa-p8"))) {
+    const bool p8 = argv[1][12] != 0;
     FILE* in = fopen(argv[2], "rb");
     OutFile out;
     if (!in || !out.Open(argv[3])) return kRetOpenFail;
     double x;
     while (fread(&x, 8, 1, in) == 1) {
       char* w = out.Reserve(64);
-      w = dtoa_g(x, w);
+      w = p8 ? dtoa_g_p8(x, w) : dtoa_g(x, w);
       *w++ = '\n';
       out.Advance(w);
     }
@@ -1748,7 +1808,7 @@ int main(int argc, char** argv) {
   } else if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
     if (rc) return rc;
-    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_grm_list || c.make_rel || c.pca || c.indep_pairwise)) {
+    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise)) {
       logprintf("Error: chaining --king-cutoff sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
       return kRetNotYetSupported;
     }
@@ -1756,7 +1816,7 @@ int main(int argc, char** argv) {
   Pl2GrmJob* grm_job = nullptr;
   std::vector<uint32_t> grm_vidx;
   const bool exact_pca = c.pca && !c.pca_approx;
-  if (c.make_grm_bin || c.make_grm_list || c.make_rel || exact_pca) {
+  if (c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || exact_pca) {
     if (exact_pca && c.parallel_tot != 1) {
       logprintf("Error: --pca cannot be used with --parallel.\n");
       return kRetInvalidCmdline;

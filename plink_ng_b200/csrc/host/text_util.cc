@@ -215,6 +215,165 @@ char* dtoa_g(double x, char* p) {
   return q;
 }
 
+// dtoa_g_p8: the 8-significant-digit sibling (reference contract: 2.0/include/plink2_string.cc:2641-2790; used
+// by --make-grm-sparse, :5073).  Same shape as dtoa_g with the bounds moved to 9.9999999499999e-k, the
+// mantissa carried as round(x * 10^(8 - integer digits)) and ties decided inside a +-5e-7 band (kBankerRound6).
+namespace {
+inline uint32_t RoundTol6(double x) {
+  uint32_t r = static_cast<uint32_t>(static_cast<int32_t>(x));
+  const double bump = (r & 1) ? 0.5000005 : 0.4999995;
+  r += static_cast<uint32_t>(static_cast<int32_t>((x - static_cast<double>(r)) + bump));
+  return r;
+}
+inline char* PutMantissa8(double x, char* p) {  // one leading digit + up to 7 decimals
+  const uint32_t v = RoundTol6(x * 10000000);
+  *p++ = static_cast<char>('0' + v / 10000000);
+  const uint32_t rem = v % 10000000;
+  if (rem) {
+    *p++ = '.';
+    p = PutFrac(rem, 7, p);
+  }
+  return p;
+}
+}  // namespace
+
+char* dtoa_g_p8(double x, char* p) {
+  if (x != x) {
+    memcpy(p, "nan", 3);
+    return p + 3;
+  }
+  char* const start = p;
+  if (x < 0) {
+    *p++ = '-';
+    x = -x;
+  }
+  if (x < 9.9999999499999e-5) {
+    uint32_t xp10 = 0;
+    if (x < 9.9999999499999e-16) {
+      if (x < 9.9999999499999e-128) {
+        if (x == 0.0) {
+          *start = '0';  // the sign of -0 is dropped, as in the reference
+          return start + 1;
+        }
+        if (x < 9.9999999499999e-256) {
+          x *= 1.0e256;
+          xp10 |= 256;
+        } else {
+          x *= 1.0e128;
+          xp10 |= 128;
+        }
+      }
+      if (x < 9.9999999499999e-64) {
+        x *= 1.0e64;
+        xp10 |= 64;
+      }
+      if (x < 9.9999999499999e-32) {
+        x *= 1.0e32;
+        xp10 |= 32;
+      }
+      if (x < 9.9999999499999e-16) {
+        x *= 1.0e16;
+        xp10 |= 16;
+      }
+    }
+    if (x < 9.9999999499999e-8) {
+      x *= 100000000;
+      xp10 |= 8;
+    }
+    if (x < 9.9999999499999e-4) {
+      x *= 10000;
+      xp10 |= 4;
+    }
+    if (x < 9.9999999499999e-2) {
+      x *= 100;
+      xp10 |= 2;
+    }
+    if (x < 9.9999999499999e-1) {
+      x *= 10;
+      ++xp10;
+    }
+    return PutExp(xp10, '-', PutMantissa8(x, p));
+  }
+  if (x >= 99999999.499999) {
+    uint32_t xp10 = 0;
+    if (x >= 9.9999999499999e15) {
+      if (x >= 9.9999999499999e127) {
+        if (x > DBL_MAX) {  // the reference prints " inf" (with the blank) for +infinity
+          memcpy(start, (p == start) ? " inf" : "-inf", 4);
+          return start + 4;
+        }
+        if (x >= 9.9999999499999e255) {
+          x *= 1.0e-256;
+          xp10 |= 256;
+        } else {
+          x *= 1.0e-128;
+          xp10 |= 128;
+        }
+      }
+      if (x >= 9.9999999499999e63) {
+        x *= 1.0e-64;
+        xp10 |= 64;
+      }
+      if (x >= 9.9999999499999e31) {
+        x *= 1.0e-32;
+        xp10 |= 32;
+      }
+      if (x >= 9.9999999499999e15) {
+        x *= 1.0e-16;
+        xp10 |= 16;
+      }
+    }
+    if (x >= 9.9999999499999e7) {
+      x *= 1.0e-8;
+      xp10 |= 8;
+    }
+    if (x >= 9.9999999499999e3) {
+      x *= 1.0e-4;
+      xp10 |= 4;
+    }
+    if (x >= 9.9999999499999e1) {
+      x *= 1.0e-2;
+      xp10 |= 2;
+    }
+    if (x >= 9.9999999499999e0) {
+      x *= 1.0e-1;
+      ++xp10;
+    }
+    return PutExp(xp10, '+', PutMantissa8(x, p));
+  }
+  if (x >= 0.99999999499999) {
+    // k + 1 integer digits, 7 - k decimals
+    static const double kUpper[7] = {9.9999999499999, 99.999999499999, 999.99999499999, 9999.9999499999, 99999.999499999, 999999.99499999, 9999999.9499999};
+    static const double kScale[8] = {10000000, 1000000, 100000, 10000, 1000, 100, 10, 1};
+    static const uint32_t kDiv[8] = {10000000, 1000000, 100000, 10000, 1000, 100, 10, 1};
+    int k = 0;
+    while (k < 7 && !(x < kUpper[k])) ++k;
+    const uint32_t v = (k == 7) ? RoundTol6(x) : RoundTol6(x * kScale[k]);
+    p = u32toa(v / kDiv[k], p);
+    const uint32_t rem = v % kDiv[k];
+    if (rem) {
+      *p++ = '.';
+      p = PutFrac(rem, 7 - k, p);
+    }
+    return p;
+  }
+  // 0.0001 <= x < 1
+  *p++ = '0';
+  *p++ = '.';
+  if (x < 9.9999999499999e-3) {
+    x *= 100;
+    *p++ = '0';
+    *p++ = '0';
+  }
+  if (x < 9.9999999499999e-2) {
+    x *= 10;
+    *p++ = '0';
+  }
+  char* q = PutFrac(RoundTol6(x * 100000000), 8, p);
+  if (q == p) *q++ = '0';
+  return q;
+}
+
 bool OutFile::Open(const std::string& path) {
   f_ = fopen(path.c_str(), "wb");
   buf_.resize(1 << 20);

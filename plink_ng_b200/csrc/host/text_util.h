@@ -15,6 +15,8 @@ namespace pl2host {
 
 // Appends the decimal text of `x`; returns the new end pointer.  `buf` needs >= 16 free bytes.
 char* dtoa_g(double x, char* buf);
+// 8 significant digits (the reference's dtoa_g_p8, plink2_string.cc:2641); `buf` needs >= 24 free bytes.
+char* dtoa_g_p8(double x, char* buf);
 char* u32toa(uint32_t x, char* buf);
 char* i32toa(int32_t x, char* buf);
 

@@ -46,6 +46,8 @@ cp $T/a_grm.grm.bin a_grm.grm.bin; cp $T/a_grm.grm.N.bin a_grm.grm.N.bin; cp $T/
 $P --bfile a --make-grm-bin meanimpute --threads 2 --out $T/a_grmmi > /dev/null
 $P --bfile a --make-grm-list --threads 2 --out $T/a_grml > /dev/null
 gzip -9 -n -c $T/a_grml.grm > a_grml.grm.gz
+$P --bfile a --make-grm-sparse 0.02 --threads 2 --out $T/a_sp > /dev/null
+cp $T/a_sp.grm.sp a_grmsp.grm.sp
 cp $T/a_grmmi.grm.bin a_grmmi.grm.bin
 $P --bfile a --make-rel cov bin4 triangle --threads 2 --out $T/a_relcov > /dev/null
 cp $T/a_relcov.rel.bin a_relcov.rel.bin

@@ -105,6 +105,24 @@ def test_make_grm_list_text(golden_dir, tmp_path):
     assert open(out + ".grm.id", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.id"), "rb").read()
 
 
+def test_make_grm_sparse_text(golden_dir, tmp_path):
+    """`.grm.sp`: same (row, column) entries as the reference except values within 1e-9 of the cutoff, values at
+    dtoa_g_p8's 8 significant digits (our GRM is within ~1e-10 of the reference's fp64)."""
+    out = run(golden_dir, tmp_path, "--make-grm-sparse", "0.02")
+    got = {tuple(ln.split("\t")[:2]): ln.split("\t")[2] for ln in open(out + ".grm.sp").read().split("\n") if ln}
+    ref = {tuple(ln.split("\t")[:2]): ln.split("\t")[2] for ln in open(os.path.join(golden_dir, "a_grmsp.grm.sp")).read().split("\n") if ln}
+    for key in set(got) ^ set(ref):
+        v = float(got.get(key, ref.get(key)))
+        assert abs(v - 0.02) < 1e-8, key
+    differing = 0
+    for key in set(got) & set(ref):
+        if got[key] != ref[key]:
+            assert abs(float(got[key]) - float(ref[key])) <= 2e-9 + 1.5e-8 * abs(float(ref[key]))
+            differing += 1
+    assert len(ref) == 1380 and differing < 0.05 * len(ref)
+    assert open(out + ".grm.id", "rb").read() == open(os.path.join(golden_dir, "a_grm.grm.id"), "rb").read()
+
+
 def test_make_rel_variants(golden_dir, tmp_path):
     out = run(golden_dir, tmp_path, "--make-rel", "cov", "bin4", "triangle")
     got = np.fromfile(out + ".rel.bin", dtype=np.float32)

@@ -59,6 +59,43 @@ def test_dtoa_g_matches_reference_text(golden_dir, tmp_path):
 
 REF_INC = "/root/reference/2.0/include"
 SFMT_OBJ = os.path.join(ROOT, "oracle", "_ref", "obj", "include_SFMT_c.o")
+STRING_OBJS = [os.path.join(ROOT, "oracle", "_ref", "obj", "include_plink2_%s_cc.o" % x) for x in ("string", "base", "bits", "float", "simd")]
+
+
+@pytest.mark.skipif(not (os.path.isdir(REF_INC) and all(os.path.exists(o) for o in STRING_OBJS)), reason="needs the reference's compiled plink2_string.cc (this container only)")
+def test_dtoa_g_p8_matches_reference_function(tmp_path):
+    """The 8-digit formatter behind --make-grm-sparse, byte for byte against the reference's own dtoa_g_p8
+    (2.0/include/plink2_string.cc:2641) on 85,000 doubles: all magnitude ranges, exact .5 ties at every digit
+    position and values a few 1e-7 either side of them, zeros, infinities, NaN."""
+    harness = tmp_path / "h.cc"
+    harness.write_text(r"""
+#include <cstdio>
+#include "plink2_string.h"
+int main(int argc, char** argv) {
+  FILE* in = fopen(argv[1], "rb"); FILE* out = fopen(argv[2], "w");
+  double x; char buf[64];
+  while (fread(&x, 8, 1, in) == 1) { char* e = plink2::dtoa_g_p8(x, buf); *e = 0; fprintf(out, "%s\n", buf); }
+  fclose(in); fclose(out); return 0;
+}
+""")
+    exe = tmp_path / "h"
+    subprocess.run(["g++", "-O1", "-std=c++11", "-mavx2", "-mbmi", "-mbmi2", "-mfma", "-mlzcnt", "-w", "-I" + REF_INC, "-I/root/reference/2.0/simde", str(harness)] + STRING_OBJS + ["-o", str(exe)], check=True)
+    rng = np.random.default_rng(5)
+    fixed = [0.0, -0.0, 1.0, -1.0, 0.5, 0.1, 0.01, 0.001, 0.0001, 1e-5, 123456.789, 12345678.9, 99999999.4, 99999999.5, 1e8, 1.5e8, 9.9999999e-5, 2 / 3, 1 / 3, np.pi, 1e300,
+             -2.5e-300, np.inf, -np.inf, np.nan, 0.99999999, 0.999999995, 0.05, 0.025, 0.0125]
+    rnd = np.concatenate([
+        rng.uniform(-1, 1, 20000), 10 ** rng.uniform(-12, 12, 20000) * rng.choice([-1, 1], 20000), rng.uniform(0, 0.2, 20000),
+        (rng.integers(1, 10 ** 8, 20000) + 0.5) / 10.0 ** rng.integers(0, 9, 20000),
+        (rng.integers(1, 10 ** 8, 5000) + 0.5 + rng.choice([-1e-7, 1e-7, 3e-7, -3e-7], 5000)) / 10.0 ** rng.integers(0, 9, 5000)])
+    vals = np.concatenate([np.array(fixed), rnd]).astype("<f8")
+    vals.tofile(tmp_path / "in.bin")
+    subprocess.run([str(exe), str(tmp_path / "in.bin"), str(tmp_path / "ref.txt")], check=True)
+    subprocess.run([BIN, "--debug-dtoa-p8", str(tmp_path / "in.bin"), str(tmp_path / "got.txt")], check=True)
+    ref = open(tmp_path / "ref.txt").read().split("\n")
+    got = open(tmp_path / "got.txt").read().split("\n")
+    assert len(ref) == len(got) == len(vals) + 1
+    assert ref == got
+    assert ref[10] == "123456.79" and ref[17] == "0.66666667" and ref[22] == " inf"
 
 
 @pytest.mark.skipif(not (os.path.isdir(REF_INC) and os.path.exists(SFMT_OBJ)), reason="needs the reference's compiled SFMT (this container only)")
@@ -116,6 +153,8 @@ int main(int argc, char** argv) {
     (("--make-king-table", "--king-table-subset"), "--king-table-subset requires"),
     (("--pca", "0"), "Invalid --pca PC count"),
     (("--indep-pairwise", "50"), "--indep-pairwise requires 2-4 arguments"),
+    (("--make-grm-sparse", "0.05", "--make-grm-bin"), "cannot be used with --make-grm-sparse"),
+    (("--make-grm-sparse", "abc"), "Invalid --make-grm-sparse threshold"),
 ])
 def test_command_line_errors_exit_8_before_touching_the_gpu(golden_dir, tmp_path, flags, fragment):
     """kPglRetInvalidCmdline = 8, as the reference; the command line is validated before any CUDA call, so this
