@@ -27,6 +27,21 @@ def test_reader_decodes_all_storage_modes(golden_dir, tmp_path, pgen, psam, pvar
     assert np.array_equal(got.reshape(want.shape), want)
 
 
+def test_reader_on_structure_rich_fixture(golden_dir, tmp_path):
+    """Set B (37 samples - not a multiple of 4 -, 400 variants): rare-ALT and rare-REF variants (difflists on either
+    base), monomorphic and all-missing variants, 40 % missingness, near-copies of the previous variant
+    (LD-compressed records), written by the reference's --make-pgen: our reader must reproduce the .bed exactly,
+    full and through a founder-style sample subset."""
+    want = orc.read_bed(os.path.join(golden_dir, "b.bed"), 37)
+    assert want.shape == (400, 37)
+    for pgen, psam, pvar in (("b.bed", "b.fam", "b.bim"), ("b_mode10.pgen", "b.psam", "b.pvar")):
+        got = _dump(os.path.join(golden_dir, pgen), os.path.join(golden_dir, psam), os.path.join(golden_dir, pvar), tmp_path)
+        assert np.array_equal(got.reshape(400, 37), want), pgen
+    # the compressed file really exercises the non-trivial record types
+    raw = open(os.path.join(golden_dir, "b_mode10.pgen"), "rb").read()
+    assert raw[2] == 0x10 and len(raw) < 0.6 * (3 + 400 * 10)
+
+
 def test_mode10_fixture_really_uses_compressed_records(golden_dir):
     raw = open(os.path.join(golden_dir, "a_mode10.pgen"), "rb").read()
     assert raw[:3] == b"\x6c\x1b\x10"
