@@ -77,3 +77,35 @@ if [ -f /root/reference/1.9/toy.ped ]; then
 fi
 rm -rf $T
 ls -la
+
+# --- set B: structure-rich reader fixture (37 samples, 400 variants): rare-ALT / rare-REF variants (difflists on
+# either base), monomorphic and all-missing variants, 40 % missingness, near-copies of the previous variant
+# (LD-compressed records).  The .bed is synthesised here, the .pgen is written by the reference.
+python3 - <<'PY'
+import numpy as np
+rng = np.random.default_rng(99)
+n, m = 37, 400
+g = np.zeros((m, n), dtype=np.uint8)
+for v in range(m):
+    kind = v % 8
+    f = {0: 0.5, 1: 0.01, 2: 0.01, 3: 0.99, 4: 0.0}.get(kind, None)
+    if f is None:
+        f = rng.uniform(0.02, 0.98)
+    g[v] = (rng.random(n) < f).astype(np.uint8) + (rng.random(n) < f)
+    if kind == 5:
+        g[v][rng.random(n) < 0.4] = 3
+    if kind == 6 and v > 0:
+        g[v] = g[v - 1]
+        g[v][rng.integers(0, n, 2)] = rng.integers(0, 4, 2)
+    if kind == 7:
+        g[v] = 3
+remap = np.array([3, 2, 0, 1], dtype=np.uint8)  # PgrGet code -> .bed code
+b = remap[g]
+b = np.concatenate([b, np.zeros((m, (-n) % 4), dtype=np.uint8)], axis=1).reshape(m, -1, 4)
+by = (b[..., 0] | (b[..., 1] << 2) | (b[..., 2] << 4) | (b[..., 3] << 6)).astype(np.uint8)
+open("b.bed", "wb").write(bytes([0x6C, 0x1B, 1]) + by.tobytes())
+open("b.bim", "w").write("".join(f"{1 + v // 200}\tv{v}\t0\t{100 + v}\tA\tC\n" for v in range(m)))
+open("b.fam", "w").write("".join(f"f{k}\ti{k}\t0\t0\t{1 + k % 2}\t-9\n" for k in range(n)))
+PY
+$P --bfile b --make-pgen --out $T/b --threads 1 > /dev/null
+cp $T/b.pgen b_mode10.pgen; cp $T/b.pvar b.pvar; cp $T/b.psam b.psam
