@@ -62,6 +62,20 @@ int pl2gpu_host_free(void* ptr);
 int pl2gpu_ctx_event_record(Pl2GpuCtx* ctx, int slot);
 int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, float* ms);
 
+/* ---- multi-GPU: one context (= one GPU, one rank) per process or host thread; NCCL over NVLink, loaded with
+ * dlopen on first use.  The N x N outputs are row-block partitioned exactly like the reference's `--parallel`
+ * pieces (ParallelBounds, 2.0/plink2_common.cc:4956-4961); the only data exchange is one all-gather of each
+ * genotype column tile (pl2gpu_king_add_variants_sharded) and, for `--pca approx`, one all-reduce of the
+ * N x 2k pass matrix per pass (the sum over per-thread g2_bb_part_bufs, 2.0/plink2_matrix_calc.cc:5838-5847).
+ * Rank 0 creates the id, every rank passes the same bytes to pl2gpu_comm_init (collective call). ---- */
+#define PL2GPU_COMM_ID_BYTES 128
+int pl2gpu_comm_unique_id(uint8_t* id_out /* [PL2GPU_COMM_ID_BYTES] */);
+int pl2gpu_comm_init(Pl2GpuCtx* ctx, int rank, int world, const uint8_t* id);
+/* Idempotent; also called by pl2gpu_ctx_destroy. */
+int pl2gpu_comm_destroy(Pl2GpuCtx* ctx);
+/* In-place sum over all ranks of a device fp64 buffer, on the context's stream. */
+int pl2gpu_comm_allreduce_sum_f64(Pl2GpuCtx* ctx, double* device_buf, uint64_t count);
+
 /* ---- KING-robust pair counts: replaces the CalcKingDenseThread -> IncrKing/IncrKingHomhom hot
  * loop (plink2_matrix_calc.cc:1255-1334, :1533-1552) together with the reader-thread
  * SplitHomRef2hetUnsafeW + TransposeBitblock staging (:2055-2099).  The sparse pre-scan
@@ -82,12 +96,26 @@ enum {
  * for those rows are allocated here; fails with "insufficient device memory" if they do not fit
  * (the caller then narrows the row range - the reference's CountTrianglePasses multipass). */
 int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr);
-/* Bytes of device memory pl2gpu_king_begin would need for that row range (for pass planning). */
+/* Same, with the capacity of the staged genotype block chosen by the caller: every add_variants call is
+ * processed in chunks of at most max_variants_per_add variants (0 = 65,536; at most 2^20; rounded up to a
+ * multiple of 256).  Larger chunks amortise the per-tile accumulator read-modify-write over more variants. */
+int pl2gpu_king_begin_ex(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, uint32_t max_variants_per_add, Pl2KingJob** job_ptr);
+/* Bytes of device memory pl2gpu_king_begin_ex would need for that row range and chunk size (for pass planning,
+ * the analogue of CountTrianglePasses, 2.0/plink2_matrix_calc.cc:216-255). */
 uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add);
 /* Accumulate `variant_ct` more variants.  `genovecs` is host memory unless src_is_device != 0;
  * consecutive variants are `variant_stride_bytes` apart (>= 8*ceil(sample_ct/32), multiple of 8).
- * Asynchronous with respect to the host when the source is device memory or pinned host memory. */
+ * src_is_device: 0 = host memory (the call returns once the buffer has been consumed; the kernels keep
+ * running), 1 = device memory written by work the caller ordered on the context's stream, 2 = device memory
+ * that is already complete (lets the copy of batch k+1 overlap the tensor kernel of batch k).  A device
+ * source must stay unmodified until work queued on the context's stream after this call has started. */
 int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device);
+/* Multi-GPU form (context with a communicator; collective call): every rank passes ITS `slice_variant_ct`
+ * variants (same count on every rank - the last slice of a file is topped up by the caller with all-missing
+ * rows, which count nothing); one in-place NCCL all-gather on the prep stream assembles the
+ * world * slice_variant_ct-variant column tile on every GPU, overlapped with the previous batch's tensor
+ * kernel.  Rank r's variants are rows [r * slice, (r + 1) * slice) of the batch. */
+int pl2gpu_king_add_variants_sharded(Pl2KingJob* job, const void* slice, uint64_t variant_stride_bytes, uint32_t slice_variant_ct, int src_is_device);
 /* Copy out uint32 counts[pair][5] for rows [out_row_start, out_row_end) (a sub-range of the job's
  * rows) in the reference's pair order.  dst is host memory unless dst_is_device != 0. */
 int pl2gpu_king_get_counts(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, uint32_t* dst, int dst_is_device);
@@ -175,6 +203,12 @@ int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_
  * (.prune.in), 1 removed (.prune.out), 2 unplaced.  The GPU evaluates the pair decisions; the greedy
  * window walk (IndepPairwiseThread, :862-1109) runs on the calling host thread. ---- */
 int pl2_indep_pairwise(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int src_is_device, uint8_t* removed_out);
+
+/* ---- measured int8 tensor peak: every SM issues back-to-back tcgen05.mma kind::i8 (M = 128, N = n_cols,
+ * K = 32; form 0 = both operands in shared memory, 1 = A operand in tensor memory as the KING/GRM kernels use
+ * it) for at least min_seconds; *tops_out = 2*128*n_cols*32 ops x UMMAs / elapsed (CUDA events), in TOP/s.
+ * This is the roofline denominator bench.py reports against. ---- */
+int pl2gpu_int8_peak(Pl2GpuCtx* ctx, uint32_t n_cols, int form, double min_seconds, double* tops_out, double* seconds_out);
 
 /* ---- self-test of the tcgen05 operand path (descriptor/layout probe); returns 0 iff an int8
  * UMMA over library-written shared-memory tiles reproduces a scalar device-side reference. ---- */

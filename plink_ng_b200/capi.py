@@ -39,7 +39,13 @@ SIGNATURES = {
     "pl2gpu_host_free": (C.c_int, [vp]),
     "pl2gpu_ctx_event_record": (C.c_int, [vp, C.c_int]),
     "pl2gpu_ctx_event_elapsed_ms": (C.c_int, [vp, C.c_int, C.c_int, C.POINTER(C.c_float)]),
+    "pl2gpu_comm_unique_id": (C.c_int, [vp]),
+    "pl2gpu_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "pl2gpu_comm_destroy": (C.c_int, [vp]),
+    "pl2gpu_comm_allreduce_sum_f64": (C.c_int, [vp, vp, C.c_uint64]),
     "pl2gpu_king_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
+    "pl2gpu_king_begin_ex": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(vp)]),
+    "pl2gpu_king_add_variants_sharded": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int]),
     "pl2gpu_king_mem_required": (C.c_uint64, [C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "pl2gpu_king_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int]),
     "pl2gpu_king_get_counts": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, C.c_int]),
@@ -64,6 +70,7 @@ SIGNATURES = {
     "pl2gpu_geno_counts": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, vp]),
     "pl2gpu_ld_band_flags": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_double, vp]),
     "pl2_indep_pairwise": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, C.c_uint32, C.c_double, C.c_int, vp, vp, C.c_int, vp]),
+    "pl2gpu_int8_peak": (C.c_int, [vp, C.c_uint32, C.c_int, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pl2gpu_selftest_umma": (C.c_int, [vp, C.c_int]),
     "pl2gpu_debug_umma": (
         C.c_int,

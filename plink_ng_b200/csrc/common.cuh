@@ -1,6 +1,7 @@
 // common.cuh - shared declarations of the pl2gpu library (internal; the public face is
 // include/plink2_b200.h).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -49,12 +50,24 @@ __host__ __device__ constexpr uint32_t SampleToPos(uint32_t s) { return (s & 1) 
 
 struct Ctx {
   int device = -1;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;
+  cudaStream_t stream = nullptr;       // compute stream: every tensor / popcount / finalize kernel
+  cudaStream_t copy_stream = nullptr;  // high-priority prep stream: H2D / D2D copies, all-gathers, padding, re-tiling
   int sm_count = 0;
   uint64_t launches = 0;
   cudaEvent_t events[16] = {};
+  // optional NCCL communicator (one rank per context; pl2gpu_comm_init), loaded lazily with dlopen
+  void* comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 };
+
+// NCCL plumbing (pl2gpu.cu): in-place all-gather of `bytes_per_rank` bytes per rank over buf (rank r's part
+// already sits at buf + r * bytes_per_rank), and an in-place fp64 sum all-reduce, both enqueued on `stream`.
+int CommAllGatherInPlace(Ctx* ctx, void* buf, uint64_t bytes_per_rank, cudaStream_t stream);
+int CommAllReduceSumF64(Ctx* ctx, double* buf, uint64_t count, cudaStream_t stream);
+
+// 2-D uint8 tensor map over a staged block raw[rows][pitch] with box {box_bytes, box_rows} (no swizzle,
+// zero fill) for cp.async.bulk.tensor loads; cuTensorMapEncodeTiled is fetched through the runtime.
+int MakeRawTensorMap(CUtensorMap* out, void* base, uint32_t pitch, uint32_t rows, uint32_t box_bytes, uint32_t box_rows);
 
 struct TileList {
   // tiles of the strict lower triangle restricted to rows [row_start, row_end)
@@ -81,9 +94,10 @@ struct GenoStage {
   uint32_t variant_cap = 0;  // multiple of kVariantPad
 };
 constexpr uint32_t kVariantPad = 256;      // lcm(popcount chunk 8*32, tensor stage 64)
-constexpr uint32_t kMaxStageVariants = 65536;
-// pad_genotypes_kernel launcher (kernel lives in pl2gpu.cu's translation unit)
-int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded);
+constexpr uint32_t kMaxStageVariants = 65536;        // default capacity of a staged block
+constexpr uint32_t kMaxStageVariantsEx = 1u << 20;   // largest capacity pl2gpu_king_begin_ex accepts
+// pad_genotypes_kernel launcher (kernel lives in pl2gpu.cu's translation unit); stream = nullptr: the compute stream
+int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded, cudaStream_t stream = nullptr);
 int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t sample_pad = kSamplePad);
 void StageFree(GenoStage* gs);
 // Copies variant_ct (<= variant_cap) rows starting at destination row dst_row and forces padding

@@ -9,6 +9,7 @@ namespace pl2 {
 constexpr uint32_t kTsCols = 80;
 constexpr uint32_t kTsSamplePad = 640;  // lcm(128, 80)
 constexpr uint32_t kTsKcJ = 64;         // variants per shared-memory stage (two k-steps)
+constexpr uint32_t kTsRawBoxBytes = 32; // inner extent of the TMA box over the raw block (>= 20 bytes = 80 samples, multiple of 16)
 
 // ---- operand re-tiling of the staged block raw[variant][pitch] (2-bit, variant-major) -------------
 // Both copies make every producer load of king_ts_kernel a contiguous run of bytes (the first TS
@@ -16,9 +17,11 @@ constexpr uint32_t kTsKcJ = 64;         // variants per shared-memory stage (two
 //
 // Row side:  raw_i[row tile rt][k-step ks][row 0..127][8 bytes]   8 bytes = 32 variants of one sample
 // One CTA = 64 variants x 64 samples through a shared-memory byte tile.
-static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t kstep_ct, uint8_t* __restrict__ raw_i) {
+// Only samples [s_base, s_base + 64 * gridDim.y) are written (a job re-tiles its own row tiles only);
+// row tile s_base / 128 is stored at index 0.
+static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t kstep_ct, uint32_t s_base, uint8_t* __restrict__ raw_i) {
   __shared__ uint8_t tile[64][68];
-  const uint32_t v0 = blockIdx.x * 64, s0 = blockIdx.y * 64;
+  const uint32_t v0 = blockIdx.x * 64, s0 = s_base + blockIdx.y * 64;
   const uint32_t t = threadIdx.x;
   {
     const uint32_t v = t >> 2, sw = t & 3;
@@ -33,7 +36,7 @@ static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_
 #pragma unroll
     for (uint32_t j = 0; j < 16; ++j) w |= static_cast<uint32_t>(tile[16 * vw + j][sl]) << (2 * j);
     const uint32_t s = s0 + sl, v = v0 + 16 * vw;
-    *reinterpret_cast<uint32_t*>(raw_i + (static_cast<uint64_t>(s >> 7) * kstep_ct + (v >> 5)) * 1024 + (s & 127) * 8 + 4 * ((v >> 4) & 1)) = w;
+    *reinterpret_cast<uint32_t*>(raw_i + (static_cast<uint64_t>((s - s_base) >> 7) * kstep_ct + (v >> 5)) * 1024 + (s & 127) * 8 + 4 * ((v >> 4) & 1)) = w;
   }
 }
 

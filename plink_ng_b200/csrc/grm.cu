@@ -168,7 +168,7 @@ int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t varia
     if (job->tiles.tile_ct) {
       {
         const uint32_t coltile_ct = job->stage.sample_ct_padded / kTsCols;
-        geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, job->d_raw_i);
+        geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, 0, job->d_raw_i);
         geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);
         grm_ts_kernel<<<job->tiles.tile_ct, kGtsThreads, kGtsSmemBytes, c->stream>>>(job->d_raw_j, job->d_raw_i, padded, job->d_tab, inv_scale, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_acc_g, job->d_acc_obs);
         c->launches += 3;

@@ -69,6 +69,7 @@ struct Cmd {
   uint64_t seed = 0;
   bool seed_given = false;
   int device = 0;
+  uint64_t gpu_memory_mib = 0;  // --gpu-memory / PL2_GPU_MEM_MIB: cap on the device memory a job may plan with (0 = what is free)
   // KING
   bool make_king = false, make_king_table = false;
   enum Shape { kTri, kSq, kSq0 } king_shape = kTri, rel_shape = kTri;
@@ -186,6 +187,12 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (!need(1, 1) || !ParseU32(prm[0], &s)) return Usage("Invalid --seed argument.");
       c->seed = s;
       c->seed_given = true;
+    } else if (flag == "--gpu-memory") {
+      // device-side analogue of --memory: the N x N accumulators are planned against this many MiB, which
+      // forces the reference's multipass behaviour (CountTrianglePasses, plink2_matrix_calc.cc:216-255)
+      uint32_t mib;
+      if (!need(1, 1) || !ParseU32(prm[0], &mib) || !mib) return Usage("Invalid --gpu-memory argument.");
+      c->gpu_memory_mib = mib;
     } else if (flag == "--gpu-device") {
       uint32_t d;
       if (!need(1, 1) || !ParseU32(prm[0], &d)) return Usage("Invalid --gpu-device argument.");
@@ -336,6 +343,11 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     c->pgen = pfile + ".pgen";
     c->pvar = pfile + ".pvar";
     c->psam = pfile + ".psam";
+  }
+  if (!c->gpu_memory_mib) {
+    const char* e = getenv("PL2_GPU_MEM_MIB");
+    uint32_t mib;
+    if (e && ParseU32(e, &mib)) c->gpu_memory_mib = mib;
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
   if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
@@ -832,8 +844,12 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   // device accumulators fit
   uint64_t free_b = 0, total_b = 0;
   if (pl2gpu_ctx_mem_info(ctx, &free_b, &total_b)) return GpuFail("pl2gpu_ctx_mem_info");
-  const uint64_t budget = free_b - free_b / 10;
-  const uint32_t batch = 32768;
+  uint64_t budget = free_b - free_b / 10;
+  if (c.gpu_memory_mib && (c.gpu_memory_mib << 20) < budget) budget = c.gpu_memory_mib << 20;
+  // variants per staged block: the full 65,536 unless the cap is so small that the two staged blocks would
+  // eat most of it (then halve until they fit in a quarter of the budget)
+  uint32_t batch = 65536;
+  while (batch > 2048 && 4ull * batch * ((n + 639) / 640 * 160) > budget / 4) batch /= 2;
   uint32_t pass_ct = 0;
   for (uint32_t r = grand_r0; r < grand_r1; ++pass_ct) {
     uint32_t lo = r + 1, hi = grand_r1;  // largest e in (r, grand_r1] that fits
@@ -848,6 +864,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     }
     r = lo;
   }
+  if (pass_ct > 1) logprintf("%s: %u passes over the variants (device accumulators planned against %llu MiB).\n", flagname, pass_ct, static_cast<unsigned long long>(budget >> 20));
   BlockStreamer bs(ds, &vidx, n, batch);
   if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
   if (want_matrix && c.king_shape == Cmd::kSq0 && !c.parallel_idx) {
@@ -881,7 +898,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       row_end = lo;
     }
     Pl2KingJob* job = nullptr;
-    if (pl2gpu_king_begin(ctx, n, row_start, row_end, kPl2KingAlgoAuto, &job)) return GpuFail("pl2gpu_king_begin");
+    if (pl2gpu_king_begin_ex(ctx, n, row_start, row_end, kPl2KingAlgoAuto, batch, &job)) return GpuFail("pl2gpu_king_begin_ex");
     g_clock.Mark("king: begin (device alloc)");
     bs.Rewind();
     std::string err;

@@ -8,7 +8,18 @@
 // Tile = 128 rows x 80 cols.  TMEM columns: [0,400) accumulators TT|TH, HT|HH, SS (int32),
 // [400,496) four A slots of 24 columns (planes T, H, S; 8 columns = 32 K-bytes per lane).
 // Same products and the same raw accumulator semantics as king_tc_kernel (tile width 80).
+//
+// Operand staging (round 2): one producer warp feeds two shared-memory rings with the TMA unit,
+//   * column side: the RAW variant-major 2-bit block is read in place through a 2-D tensor map
+//     (cp.async.bulk.tensor, SASS UTMALDG): box = 64 variants x 32 bytes at byte column 20 * ct (the
+//     tile's 80 samples are the first 20 bytes of each box row) - no column re-tiling pass, no copy;
+//   * row side: 1 KB bulk copies (UBLKCP) of the sample-major k-steps written by
+//     geno_tile_rows_kernel (the bit transpose CalcKing also needs, TransposeBitblock
+//     2.0/include/plink2_bits.cc:2065), restricted to the job's own row tiles.
+// The expansion warps read their words from shared memory (LDS) instead of issuing global loads.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "geno_expand.cuh"
 #include "geno_tile.cuh"
@@ -24,18 +35,31 @@ constexpr uint32_t kTsASlotCols = 24;
 constexpr uint32_t kTsStagesJ = 4;
 constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1984: +64 keeps the K-permuted rows bank-conflict free
 constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 15872
-constexpr uint32_t kTsSmemBytes = kTsStagesJ * kTsStageBytesJ + 1024;
+constexpr uint32_t kTsRawJSlots = 8;                                // TMA ring: raw column boxes (64 variants x 32 B)
+constexpr uint32_t kTsRawJBytes = kTsKcJ * kTsRawBoxBytes;          // 2048
+constexpr uint32_t kTsRawISlots = 16;                               // bulk-copy ring: row-side k-steps (128 samples x 8 B)
+constexpr uint32_t kTsRawIBytes = kTileRows * 8;                    // 1024
+constexpr uint32_t kTsSmemOffRawJ = kTsStagesJ * kTsStageBytesJ;    // 63488 (multiple of 1024)
+constexpr uint32_t kTsSmemOffRawI = kTsSmemOffRawJ + kTsRawJSlots * kTsRawJBytes;
+constexpr uint32_t kTsSmemBytes = kTsSmemOffRawI + kTsRawISlots * kTsRawIBytes + 1024;
 constexpr uint32_t kTsRowWarps = 8;
 constexpr uint32_t kTsColWarps = 10;           // 5 words x 64 variants per stage
-constexpr uint32_t kTsThreads = 32 * (kTsRowWarps + kTsColWarps + 1);  // + the UMMA issuer warp
+constexpr uint32_t kTsIssuerWarp = kTsRowWarps + kTsColWarps;
+constexpr uint32_t kTsLoaderWarp = kTsIssuerWarp + 1;
+constexpr uint32_t kTsThreads = 32 * (kTsRowWarps + kTsColWarps + 2);  // + the UMMA issuer warp + the TMA producer warp
+static_assert(kTsSmemOffRawJ % 1024 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(kTsThreads, 1)
-king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw_i, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
+king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __restrict__ raw_i, uint32_t row_tile_first, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full_a[kTsASlots];
   __shared__ __align__(8) uint64_t bar_empty_a[kTsASlots];
   __shared__ __align__(8) uint64_t bar_full_b[kTsStagesJ];
   __shared__ __align__(8) uint64_t bar_empty_b[kTsStagesJ];
+  __shared__ __align__(8) uint64_t bar_full_rj[kTsRawJSlots];
+  __shared__ __align__(8) uint64_t bar_empty_rj[kTsRawJSlots];
+  __shared__ __align__(8) uint64_t bar_full_ri[kTsRawISlots];
+  __shared__ __align__(8) uint64_t bar_empty_ri[kTsRawISlots];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
 
@@ -57,10 +81,18 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
       mbar_init(&bar_full_b[s], kTsColWarps);
       mbar_init(&bar_empty_b[s], 1);
     }
+    for (uint32_t s = 0; s < kTsRawJSlots; ++s) {
+      mbar_init(&bar_full_rj[s], 1);            // the producer's expect_tx arrival
+      mbar_init(&bar_empty_rj[s], kTsColWarps);
+    }
+    for (uint32_t s = 0; s < kTsRawISlots; ++s) {
+      mbar_init(&bar_full_ri[s], 1);
+      mbar_init(&bar_empty_ri[s], 4);           // the four lane-quarter warps of the owning group
+    }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
   }
-  if (warp == kTsRowWarps + kTsColWarps) tmem_alloc<512>(&tmem_base_slot);
+  if (warp == kTsIssuerWarp) tmem_alloc<512>(&tmem_base_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -77,11 +109,8 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
     const uint32_t grp = warp >> 2;
     const uint32_t lq = warp & 3;
     const uint32_t row = 32 * lq + lane;
-    const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt) * (2 * stage_iters) * 1024 + row * 8;
+    const uint32_t ring_i = smem_base + kTsSmemOffRawI + row * 8;
     const uint32_t taddr_lane = tmem_base + ((32u * lq) << 16) + kTsAccCols;
-    auto load_i = [&](uint32_t n) -> uint2 {
-      return (n < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 1024ull * (2 * n + grp))) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    };
     struct ExpI {
       uint32_t v[3][8];
     };
@@ -97,66 +126,72 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
       }
       return e;
     };
-    constexpr uint32_t kLa = 4;
-    uint2 pre_i[kLa];
-#pragma unroll
-    for (uint32_t d = 0; d < kLa; ++d) pre_i[d] = load_i(d);
-    ExpI cur = expand_i(pre_i[0]);
-    for (uint32_t n0 = 0; n0 < stage_iters; n0 += kLa) {  // stage_iters is a multiple of 4
-#pragma unroll
-      for (uint32_t d = 0; d < kLa; ++d) {
-        const uint32_t n = n0 + d;
-        const uint32_t ks = 2 * n + grp;
-        const uint32_t slot = ks % kTsASlots;
-        pre_i[d] = load_i(n + kLa);
-        mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t ta = taddr_lane + slot * kTsASlotCols;
-        tmem_st8(ta, cur.v[0]);
-        tmem_st8(ta + 8, cur.v[1]);
-        tmem_st8(ta + 16, cur.v[2]);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&bar_full_a[slot], lane);
-        cur = expand_i(pre_i[(d + 1) % kLa]);
-      }
+    // fetch k-step ks = 2 n + grp from the ring, release the slot once every lane has expanded its word
+    auto fetch = [&](uint32_t n) -> ExpI {
+      const uint32_t ks = 2 * n + grp;
+      const uint32_t si = ks % kTsRawISlots;
+      mbar_wait(&bar_full_ri[si], (ks / kTsRawISlots) & 1);
+      const uint2 w = lds64(ring_i + si * kTsRawIBytes);
+      const ExpI e = expand_i(w);
+      mbar_arrive_warp(&bar_empty_ri[si], lane);
+      return e;
+    };
+    ExpI cur = fetch(0);
+    for (uint32_t n = 0; n < stage_iters; ++n) {
+      const uint32_t ks = 2 * n + grp;
+      const uint32_t slot = ks % kTsASlots;
+      mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint32_t ta = taddr_lane + slot * kTsASlotCols;
+      tmem_st8(ta, cur.v[0]);
+      tmem_st8(ta + 8, cur.v[1]);
+      tmem_st8(ta + 16, cur.v[2]);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive_warp(&bar_full_a[slot], lane);
+      if (n + 1 < stage_iters) cur = fetch(n + 1);
     }
-  } else if (warp < kTsRowWarps + kTsColWarps) {
+  } else if (warp < kTsIssuerWarp) {
     // ---------------- column-side producers: 2-bit words -> int8 planes in shared memory ----------------
-    // Thread = (word w of the 20-byte row, variant k of the 64-variant stage).
+    // Thread = (word w of the 20-byte tile row, variant k of the 64-variant stage).  A quarter-warp is
+    // one (8-variant group, word) combination: conflict-free st.shared.v4 (the 8 K rows of a phase land in
+    // 8 different 16-byte bank groups) and 2-way ld.shared.b32 from the 32-byte-pitch TMA box.
     const uint32_t t = tid - 32 * kTsRowWarps;     // 0..319
-    const uint32_t k = t & 63;
-    const uint32_t w = t >> 6;
-    const uint8_t* src_j = raw_j + static_cast<uint64_t>(ct) * stage_iters * (kTsKcJ * 20) + k * 20 + 4 * w;
+    const uint32_t combo = t >> 3;                 // 0..39 = (k group of 8) * 5 + word
+    const uint32_t k = 8 * (combo / 5) + (t & 7);
+    const uint32_t w = combo % 5;
+    const uint32_t ring_j = smem_base + kTsSmemOffRawJ + k * kTsRawBoxBytes + 4 * w;
     // K rows are stored in the PRMT position order of the row side (geno_expand.cuh): variant k of a
     // 16-variant group sits at row SampleToPos(k % 16)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
     const uint32_t dst_k = (kpos >> 3) * kTsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
-    auto load_j = [&](uint32_t it) -> uint32_t {
-      return (it < stage_iters) ? __ldg(reinterpret_cast<const uint32_t*>(src_j + static_cast<uint64_t>(it) * (kTsKcJ * 20))) : 0xFFFFFFFFu;
+    struct ExpJ {
+      uint4 vt, vh, vs;
     };
-    constexpr uint32_t kLa = 4;
-    uint32_t pre_j[kLa];
-#pragma unroll
-    for (uint32_t d = 0; d < kLa; ++d) pre_j[d] = load_j(d);
-    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kLa) {
-#pragma unroll
-      for (uint32_t d = 0; d < kLa; ++d) {
-        const uint32_t it = it0 + d;
-        const Sel4 sel = make_selectors(pre_j[d]);
-        pre_j[d] = load_j(it + kLa);
-        const uint4 vt = expand16(tab_t, sel), vh = expand16(tab_h, sel), vs = expand16(tab_s, sel);
-        const uint32_t sb = d % kTsStagesJ;
-        mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
-        const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(vt.x), "r"(vt.y), "r"(vt.z), "r"(vt.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(vh.x), "r"(vh.y), "r"(vh.z), "r"(vh.w) : "memory");
-        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(vs.x), "r"(vs.y), "r"(vs.z), "r"(vs.w) : "memory");
-        fence_proxy_async_smem();
-        mbar_arrive_warp(&bar_full_b[sb], lane);
-      }
+    auto fetch = [&](uint32_t it) -> ExpJ {
+      const uint32_t sj = it % kTsRawJSlots;
+      mbar_wait(&bar_full_rj[sj], (it / kTsRawJSlots) & 1);
+      const Sel4 sel = make_selectors(lds32(ring_j + sj * kTsRawJBytes));
+      ExpJ e;
+      e.vt = expand16(tab_t, sel);
+      e.vh = expand16(tab_h, sel);
+      e.vs = expand16(tab_s, sel);
+      mbar_arrive_warp(&bar_empty_rj[sj], lane);
+      return e;
+    };
+    ExpJ cur = fetch(0);
+    for (uint32_t it = 0; it < stage_iters; ++it) {
+      const uint32_t sb = it % kTsStagesJ;
+      mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
+      const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(cur.vt.x), "r"(cur.vt.y), "r"(cur.vt.z), "r"(cur.vt.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(cur.vh.x), "r"(cur.vh.y), "r"(cur.vh.z), "r"(cur.vh.w) : "memory");
+      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(cur.vs.x), "r"(cur.vs.y), "r"(cur.vs.z), "r"(cur.vs.w) : "memory");
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&bar_full_b[sb], lane);
+      if (it + 1 < stage_iters) cur = fetch(it + 1);
     }
-  } else {
+  } else if (warp == kTsIssuerWarp) {
     // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
     // One outer iteration = the 4 shared-memory stages = 8 k-steps = two rounds of the 4 A slots, so
     // every slot index, A parity and descriptor offset is a compile-time constant.
@@ -193,6 +228,29 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
     }
     if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
+  } else {
+    // ---------------- TMA producer: one elected lane keeps both raw rings full ----------------
+    if (elect_one_sync()) {
+      prefetch_tensormap(&tmap_raw);
+      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * kTsRawIBytes;
+      const uint32_t ring_j = smem_base + kTsSmemOffRawJ, ring_i = smem_base + kTsSmemOffRawI;
+      const int32_t c0 = static_cast<int32_t>(ct * (kTsCols / 4));
+      for (uint32_t it = 0; it < stage_iters; ++it) {
+#pragma unroll
+        for (uint32_t kk = 0; kk < 2; ++kk) {
+          const uint32_t ks = 2 * it + kk;
+          const uint32_t si = ks % kTsRawISlots;
+          mbar_wait(&bar_empty_ri[si], ((ks / kTsRawISlots) & 1) ^ 1);
+          mbar_expect_tx(&bar_full_ri[si], kTsRawIBytes);
+          bulk_load_1d(ring_i + si * kTsRawIBytes, src_i + static_cast<uint64_t>(ks) * kTsRawIBytes, kTsRawIBytes, &bar_full_ri[si]);
+        }
+        const uint32_t sj = it % kTsRawJSlots;
+        mbar_wait(&bar_empty_rj[sj], ((it / kTsRawJSlots) & 1) ^ 1);
+        mbar_expect_tx(&bar_full_rj[sj], kTsRawJBytes);
+        tma_load_2d(ring_j + sj * kTsRawJBytes, &tmap_raw, c0, static_cast<int32_t>(it * kTsKcJ), &bar_full_rj[sj]);
+      }
+    }
+    __syncwarp();
   }
 
   if (warp < kTsRowWarps) {
@@ -220,7 +278,7 @@ king_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ ra
     tc_fence_before_sync();
   }
   __syncthreads();
-  if (warp == kTsRowWarps + kTsColWarps) {
+  if (warp == kTsIssuerWarp) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);
   }

@@ -1,7 +1,11 @@
 // pl2gpu.cu - C-ABI entry points (include/plink2_b200.h): context, staging, KING job driver.
-#include <cstdarg>
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include <algorithm>
+#include <cstdarg>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "../../include/plink2_b200.h"
@@ -96,6 +100,94 @@ void FreeTileList(TileList* tl) {
   tl->d_tile_rt = tl->d_tile_tc = tl->d_rowtile_offset = nullptr;
 }
 
+// ---- TMA tensor maps ----
+int MakeRawTensorMap(CUtensorMap* out, void* base, uint32_t pitch, uint32_t rows, uint32_t box_bytes, uint32_t box_rows) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      cudaGetLastError();
+      set_error("cuTensorMapEncodeTiled is not available from this driver");
+      return 1;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  const cuuint64_t dims[2] = {pitch, rows};
+  const cuuint64_t strides[1] = {pitch};  // bytes, dimension 1
+  const cuuint32_t box[2] = {box_bytes, box_rows};
+  const cuuint32_t elem_strides[2] = {1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, base, dims, strides, box, elem_strides, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) for a %u x %u-byte block", static_cast<int>(r), rows, pitch);
+    return 1;
+  }
+  return 0;
+}
+
+// ---- NCCL, loaded on first use: the library has no link-time dependency on it, and inside a process that
+// already carries an NCCL (torch.distributed) the same copy is shared ----
+namespace {
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi g_nccl;
+std::once_flag g_nccl_once;
+
+void LoadNccl() {
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return;
+  g_nccl.GetUniqueId = reinterpret_cast<decltype(g_nccl.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
+  g_nccl.CommInitRank = reinterpret_cast<decltype(g_nccl.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+  g_nccl.CommDestroy = reinterpret_cast<decltype(g_nccl.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
+  g_nccl.AllGather = reinterpret_cast<decltype(g_nccl.AllGather)>(dlsym(h, "ncclAllGather"));
+  g_nccl.AllReduce = reinterpret_cast<decltype(g_nccl.AllReduce)>(dlsym(h, "ncclAllReduce"));
+  g_nccl.GetErrorString = reinterpret_cast<decltype(g_nccl.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
+  g_nccl.ok = g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.CommDestroy && g_nccl.AllGather && g_nccl.AllReduce && g_nccl.GetErrorString;
+}
+bool HaveNccl() {
+  std::call_once(g_nccl_once, LoadNccl);
+  if (!g_nccl.ok) set_error("NCCL (libnccl.so.2) could not be loaded: %s", dlerror() ? dlerror() : "symbols missing");
+  return g_nccl.ok;
+}
+}  // namespace
+
+#define PL2_NCCL_OK(expr)                                                                              \
+  do {                                                                                                 \
+    ncclResult_t r__ = (expr);                                                                         \
+    if (r__ != ncclSuccess) {                                                                          \
+      pl2::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__, g_nccl.GetErrorString(r__)); \
+      return 1;                                                                                        \
+    }                                                                                                  \
+  } while (0)
+
+int CommAllGatherInPlace(Ctx* ctx, void* buf, uint64_t bytes_per_rank, cudaStream_t stream) {
+  if (!ctx->comm) {
+    set_error("no communicator attached to the context");
+    return 1;
+  }
+  const uint8_t* mine = static_cast<const uint8_t*>(buf) + static_cast<uint64_t>(ctx->comm_rank) * bytes_per_rank;
+  PL2_NCCL_OK(g_nccl.AllGather(mine, buf, bytes_per_rank, ncclUint8, static_cast<ncclComm_t>(ctx->comm), stream));
+  return 0;
+}
+
+int CommAllReduceSumF64(Ctx* ctx, double* buf, uint64_t count, cudaStream_t stream) {
+  if (!ctx->comm) {
+    set_error("no communicator attached to the context");
+    return 1;
+  }
+  PL2_NCCL_OK(g_nccl.AllReduce(buf, buf, count, ncclDouble, ncclSum, static_cast<ncclComm_t>(ctx->comm), stream));
+  return 0;
+}
+
 // ---- staged genotype block on the device ----
 int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t sample_pad) {
   gs->sample_ct = sample_ct;
@@ -111,9 +203,9 @@ int StageAlloc(uint32_t sample_ct, uint32_t variant_cap, GenoStage* gs, uint32_t
   return 0;
 }
 
-int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded) {
+int LaunchPadGenotypes(Ctx* ctx, uint8_t* dst, uint32_t pitch, uint32_t sample_ct, uint32_t variant_ct, uint32_t variant_ct_padded, cudaStream_t stream) {
   if (!variant_ct_padded) return 0;
-  pad_genotypes_kernel<<<variant_ct_padded, 128, 0, ctx->stream>>>(dst, pitch, sample_ct, variant_ct, variant_ct_padded);
+  pad_genotypes_kernel<<<variant_ct_padded, 128, 0, stream ? stream : ctx->stream>>>(dst, pitch, sample_ct, variant_ct, variant_ct_padded);
   ctx->launches++;
   PL2_CUDA_OK(cudaGetLastError());
   return 0;
@@ -153,23 +245,29 @@ struct Pl2KingJob {
   uint32_t sample_ct = 0, row_start = 0, row_end = 0;
   int algo = kPl2KingAlgoTensor;
   TileList tiles;
-  GenoStage stage;
+  // TS path: two staged blocks + two row-side re-tiled copies, so that the copy / all-gather, padding and
+  // row re-tiling of batch k+1 (prep stream) overlap the tensor kernel of batch k (compute stream).
+  // The other algorithms use buffer 0 on the compute stream only.
+  GenoStage stage[2];
+  uint8_t* d_raw_t[2] = {nullptr, nullptr};  // TS path: row-side re-tiled copy of the job's own row tiles (geno_tile.cuh)
+  CUtensorMap tmap[2];                       // TS path: 2-D tensor maps over stage[b].d_raw for the column-side TMA loads
+  cudaEvent_t ev_prep_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
+  bool kernel_pending[2] = {false, false};
+  uint32_t buf_idx = 0;
   uint32_t* d_planes = nullptr;  // popcount path only
-  uint8_t* d_raw_t = nullptr;    // TS path only: row-side re-tiled copy of the staged block (king_ts_kernel.cuh)
-  uint8_t* d_raw_j = nullptr;    // TS path only: column-side re-tiled copy
   uint32_t tile_cols = kTileCols;
   int32_t* d_raw_acc = nullptr;
   void* d_out_stage = nullptr;   // bounded staging for host downloads
   uint64_t out_stage_bytes = 0;
   uint64_t variants_added = 0;
-  // TS path, host sources: H2D of batch k+1 on the copy stream overlaps the tensor kernel of batch k
-  cudaEvent_t ev_copied = nullptr;      // the staged block has arrived (copy stream)
-  cudaEvent_t ev_stage_free = nullptr;  // the staged block has been re-tiled and may be overwritten (compute stream)
+  cudaEvent_t ev_copied = nullptr;     // the caller's buffer has been consumed (prep stream)
+  cudaEvent_t ev_src_ready = nullptr;  // device sources ordered on the compute stream
 };
 
 extern "C" {
 
-int pl2gpu_abi_version(void) { return 1; }
+int pl2gpu_abi_version(void) { return 2; }
 
 const char* pl2gpu_last_error(void) { return get_error(); }
 
@@ -201,7 +299,13 @@ int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr) {
   ctx->c.device = device_idx;
   ctx->c.sm_count = prop.multiProcessorCount;
   PL2_CUDA_OK(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
-  PL2_CUDA_OK(cudaStreamCreateWithFlags(&ctx->c.copy_stream, cudaStreamNonBlocking));
+  {
+    // the prep stream outranks the compute stream: its short copy / pad / re-tile / all-gather kernels must get
+    // SM slots while a long tensor kernel keeps every SM busy
+    int prio_lo = 0, prio_hi = 0;
+    PL2_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    PL2_CUDA_OK(cudaStreamCreateWithPriority(&ctx->c.copy_stream, cudaStreamNonBlocking, prio_hi));
+  }
   PL2_CUDA_OK(cudaFuncSetAttribute(king_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
   PL2_CUDA_OK(cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
   PL2_CUDA_OK(cudaFuncSetAttribute(umma_probe_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
@@ -213,6 +317,7 @@ int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr) {
 int pl2gpu_ctx_destroy(Pl2GpuCtx* ctx) {
   if (!ctx) return 0;
   cudaSetDevice(ctx->c.device);
+  pl2gpu_comm_destroy(ctx);
   if (ctx->c.stream) cudaStreamDestroy(ctx->c.stream);
   if (ctx->c.copy_stream) cudaStreamDestroy(ctx->c.copy_stream);
   for (auto& e : ctx->c.events)
@@ -277,27 +382,94 @@ int pl2gpu_ctx_event_elapsed_ms(Pl2GpuCtx* ctx, int slot_from, int slot_to, floa
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------ communicator
+
+int pl2gpu_comm_unique_id(uint8_t* id_out) {
+  if (!id_out || !HaveNccl()) {
+    if (!id_out) set_error("pl2gpu_comm_unique_id: null output");
+    return 1;
+  }
+  static_assert(sizeof(ncclUniqueId) == PL2GPU_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId id;
+  PL2_NCCL_OK(g_nccl.GetUniqueId(&id));
+  memcpy(id_out, &id, sizeof(id));
+  return 0;
+}
+
+int pl2gpu_comm_init(Pl2GpuCtx* ctx, int rank, int world, const uint8_t* id) {
+  if (!ctx || !id || world < 1 || rank < 0 || rank >= world) {
+    set_error("pl2gpu_comm_init: bad arguments");
+    return 1;
+  }
+  if (ctx->c.comm) {
+    set_error("pl2gpu_comm_init: the context already has a communicator");
+    return 1;
+  }
+  if (!HaveNccl()) return 1;
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  ncclUniqueId uid;
+  memcpy(&uid, id, sizeof(uid));
+  ncclComm_t comm = nullptr;
+  PL2_NCCL_OK(g_nccl.CommInitRank(&comm, world, uid, rank));
+  ctx->c.comm = comm;
+  ctx->c.comm_rank = rank;
+  ctx->c.comm_world = world;
+  return 0;
+}
+
+int pl2gpu_comm_destroy(Pl2GpuCtx* ctx) {
+  if (!ctx || !ctx->c.comm) return 0;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  cudaStreamSynchronize(ctx->c.copy_stream);
+  g_nccl.CommDestroy(static_cast<ncclComm_t>(ctx->c.comm));
+  ctx->c.comm = nullptr;
+  ctx->c.comm_rank = 0;
+  ctx->c.comm_world = 1;
+  return 0;
+}
+
+int pl2gpu_comm_allreduce_sum_f64(Pl2GpuCtx* ctx, double* device_buf, uint64_t count) {
+  if (!ctx || !device_buf) {
+    set_error("pl2gpu_comm_allreduce_sum_f64: bad arguments");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  return CommAllReduceSumF64(&ctx->c, device_buf, count, ctx->c.stream);
+}
+
 // ------------------------------------------------------------------------------------------ KING
 
-uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add) {
-  // Upper bound over the algorithms (the caller does not pass one): accumulators + staged block and
-  // its per-algorithm re-layouts + tile lists + slack.
+static uint32_t ClampStageCap(uint32_t max_variants_per_add) {
   uint32_t cap = max_variants_per_add ? max_variants_per_add : kMaxStageVariants;
-  if (cap > kMaxStageVariants) cap = kMaxStageVariants;
-  cap = RoundUpU32(cap, kVariantPad);
-  const uint64_t slack = 256ull << 20;
+  if (cap > kMaxStageVariantsEx) cap = kMaxStageVariantsEx;
+  return RoundUpU32(cap, kVariantPad);
+}
+constexpr uint64_t kKingOutStageBytes = 256ull << 20;
+
+uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t max_variants_per_add) {
+  // Upper bound over the algorithms (the caller does not pass one) of exactly what pl2gpu_king_begin_ex
+  // allocates for the same max_variants_per_add: accumulators + staged block(s) and their per-algorithm
+  // re-layouts + tile lists + the output staging buffer, plus slack for allocator granularity.
+  const uint64_t cap = ClampStageCap(max_variants_per_add);
+  const uint64_t slack = 128ull << 20;
   // SS tensor / popcount: 128 x 96 tiles, raw block + 3 bit planes (popcount only)
   const uint64_t tiles = CountTiles(row_start, row_end, false);
   const uint64_t npad = RoundUpU32(sample_ct, kSamplePad);
-  const uint64_t need_ss = tiles * kKingTileAccWords * 4 + static_cast<uint64_t>(cap) * (npad / 4) + 3ull * (cap / 32) * npad * 4 + tiles * 12;
-  // TS tensor (the default): 128 x 80 tiles, raw block + row-side and column-side re-tiled copies
+  const uint64_t need_ss = tiles * kKingTileAccWords * 4 + cap * (npad / 4) + 3ull * (cap / 32) * npad * 4 + tiles * 16;
+  // TS tensor (the default): 128 x 80 tiles, two raw blocks + two row-side re-tiled copies of the job's row tiles
   const uint64_t tiles_ts = CountTiles(row_start, row_end, false, kTsCols);
   const uint64_t npad_ts = RoundUpU32(sample_ct, kTsSamplePad);
-  const uint64_t need_ts = tiles_ts * kTsTileAccWords * 4 + 3ull * cap * (npad_ts / 4) + tiles_ts * 12;
-  return (need_ss > need_ts ? need_ss : need_ts) + slack;
+  const uint64_t row_tiles = row_end > row_start ? (DivUpU32(row_end, kTileRows) - row_start / kTileRows) : 0;
+  const uint64_t need_ts = tiles_ts * kTsTileAccWords * 4 + 2 * cap * (npad_ts / 4) + 2 * row_tiles * kTileRows * (cap / 4) + tiles_ts * 16;
+  return (need_ss > need_ts ? need_ss : need_ts) + kKingOutStageBytes + slack;
 }
 
 int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr) {
+  return pl2gpu_king_begin_ex(ctx, sample_ct, row_start, row_end, algo, 0, job_ptr);
+}
+
+int pl2gpu_king_begin_ex(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, uint32_t max_variants_per_add, Pl2KingJob** job_ptr) {
   *job_ptr = nullptr;
   if (!ctx) {
     set_error("pl2gpu_king_begin: null context");
@@ -324,18 +496,28 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     return 1;
   };
   const bool ts = algo == kPl2KingAlgoTensorTS;
-  if (cudaEventCreateWithFlags(&job->ev_copied, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&job->ev_stage_free, cudaEventDisableTiming) != cudaSuccess) {
+  const uint32_t cap = ClampStageCap(max_variants_per_add);
+  bool ev_ok = cudaEventCreateWithFlags(&job->ev_copied, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&job->ev_src_ready, cudaEventDisableTiming) == cudaSuccess;
+  for (int b = 0; b < 2 && ev_ok; ++b) {
+    ev_ok = cudaEventCreateWithFlags(&job->ev_prep_done[b], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&job->ev_kernel_done[b], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ev_ok) {
     set_error("pl2gpu_king_begin: cudaEventCreate failed");
     return fail();
   }
   job->tile_cols = ts ? kTsCols : kTileCols;
   if (BuildTileList(row_start, row_end, false, &job->tiles, job->tile_cols)) return fail();
-  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, ts ? kTsSamplePad : kSamplePad)) return fail();
-  if (ts && (cudaMalloc(&job->d_raw_t, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
-             cudaMalloc(&job->d_raw_j, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess)) {
-    cudaGetLastError();
-    set_error("pl2gpu_king_begin: insufficient device memory for the re-tiled genotype copies");
-    return fail();
+  for (int b = 0; b < (ts ? 2 : 1); ++b) {
+    if (StageAlloc(sample_ct, cap, &job->stage[b], ts ? kTsSamplePad : kSamplePad)) return fail();
+    if (ts) {
+      const uint64_t raw_t_bytes = static_cast<uint64_t>(job->tiles.row_tile_ct) * kTileRows * (job->stage[b].variant_cap / 4);
+      if (cudaMalloc(&job->d_raw_t[b], raw_t_bytes ? raw_t_bytes : 16) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pl2gpu_king_begin: insufficient device memory for the row-side re-tiled genotype copy");
+        return fail();
+      }
+      if (MakeRawTensorMap(&job->tmap[b], job->stage[b].d_raw, job->stage[b].pitch, job->stage[b].variant_cap, kTsRawBoxBytes, kTsKcJ)) return fail();
+    }
   }
   const uint64_t acc_bytes = static_cast<uint64_t>(job->tiles.tile_ct) * (5ull * job->tile_cols * kTileRows) * sizeof(int32_t);
   if (cudaMalloc(&job->d_raw_acc, acc_bytes ? acc_bytes : 4) != cudaSuccess) {
@@ -348,20 +530,46 @@ int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, ui
     return fail();
   }
   if (algo == kPl2KingAlgoPopcount) {
-    const uint64_t plane_bytes = 3ull * (job->stage.variant_cap / 32) * job->stage.sample_ct_padded * sizeof(uint32_t);
+    const uint64_t plane_bytes = 3ull * (job->stage[0].variant_cap / 32) * job->stage[0].sample_ct_padded * sizeof(uint32_t);
     if (cudaMalloc(&job->d_planes, plane_bytes) != cudaSuccess) {
       cudaGetLastError();
       set_error("pl2gpu_king_begin: insufficient device memory for bit planes");
       return fail();
     }
   }
-  job->out_stage_bytes = 256ull << 20;
+  job->out_stage_bytes = kKingOutStageBytes;
   if (cudaMalloc(&job->d_out_stage, job->out_stage_bytes) != cudaSuccess) {
     cudaGetLastError();
     set_error("pl2gpu_king_begin: insufficient device memory for output staging");
     return fail();
   }
   *job_ptr = job;
+  return 0;
+}
+
+// TS path: the staged block stage[b] holds `cur` variants (rows [0, cur)); pad it, re-tile the job's row
+// tiles and queue the tensor kernel.  Everything up to the kernel runs on the prep stream.
+static int KingTsPrepAndLaunch(Pl2KingJob* job, uint32_t b, uint32_t cur, bool pad_valid_rows) {
+  Ctx* c = &job->ctx->c;
+  cudaStream_t prep = c->copy_stream;
+  GenoStage& st = job->stage[b];
+  const uint32_t padded = RoundUpU32(cur, kVariantPad);
+  // pad_valid_rows == false: the valid rows were already padded slice by slice (sharded add); only the tail rows remain
+  if (pad_valid_rows) {
+    PL2_TRY(LaunchPadGenotypes(c, st.d_raw, st.pitch, st.sample_ct, cur, padded, prep));
+  } else if (padded > cur) {
+    PL2_TRY(LaunchPadGenotypes(c, st.d_raw + static_cast<uint64_t>(cur) * st.pitch, st.pitch, st.sample_ct, 0, padded - cur, prep));
+  }
+  geno_tile_rows_kernel<<<dim3(padded / 64, job->tiles.row_tile_ct * (kTileRows / 64)), 256, 0, prep>>>(st.d_raw, st.pitch, padded / 32, job->tiles.row_tile_first * kTileRows, job->d_raw_t[b]);
+  c->launches++;
+  PL2_CUDA_OK(cudaGetLastError());
+  PL2_CUDA_OK(cudaEventRecord(job->ev_prep_done[b], prep));
+  PL2_CUDA_OK(cudaStreamWaitEvent(c->stream, job->ev_prep_done[b], 0));
+  king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->tmap[b], job->d_raw_t[b], job->tiles.row_tile_first, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+  c->launches++;
+  PL2_CUDA_OK(cudaGetLastError());
+  PL2_CUDA_OK(cudaEventRecord(job->ev_kernel_done[b], c->stream));
+  job->kernel_pending[b] = true;
   return 0;
 }
 
@@ -378,59 +586,95 @@ int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t var
     return 1;
   }
   const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  const bool ts = job->algo == kPl2KingAlgoTensorTS;
   uint32_t done = 0;
   while (done < variant_ct) {
     uint32_t cur = variant_ct - done;
-    if (cur > job->stage.variant_cap) cur = job->stage.variant_cap;
-    uint32_t padded = 0;
-    // The stage buffer is reused: make sure the previous chunk's kernels are ordered before the
-    // copy (same stream => implicit).
-    const bool overlap_h2d = !src_is_device && job->algo == kPl2KingAlgoTensorTS && job->tiles.tile_ct;
-    if (overlap_h2d) {
-      // The TS kernel reads only the re-tiled copies, so the raw stage is free as soon as the previous
-      // batch's re-tiling kernels are done: copy on the copy stream while the previous tensor kernel runs.
-      padded = RoundUpU32(cur, kVariantPad);
-      const uint32_t width = DivUpU32(job->stage.sample_ct, 4);
-      PL2_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, job->ev_stage_free, 0));
-      PL2_CUDA_OK(cudaMemcpy2DAsync(job->stage.d_raw, job->stage.pitch, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, width, cur, cudaMemcpyHostToDevice, c->copy_stream));
-      PL2_CUDA_OK(cudaEventRecord(job->ev_copied, c->copy_stream));
-      PL2_CUDA_OK(cudaStreamWaitEvent(c->stream, job->ev_copied, 0));
-      PL2_TRY(LaunchPadGenotypes(c, job->stage.d_raw, job->stage.pitch, job->stage.sample_ct, cur, padded));
-    } else {
-      PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
-    }
-    if (job->tiles.tile_ct) {
-      if (job->algo == kPl2KingAlgoPopcount) {
-        const uint32_t word_ct = padded / 32;
-        const uint64_t warps = static_cast<uint64_t>(job->stage.sample_ct_padded / 32) * word_ct;
-        split_transpose_kernel<<<static_cast<uint32_t>(DivUpU64(warps, 8)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->stage.sample_ct_padded, word_ct, job->d_planes);
-        c->launches++;
-        king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage.sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
-        c->launches++;
-      } else if (job->algo == kPl2KingAlgoTensorTS) {
-        const uint32_t coltile_ct = job->stage.sample_ct_padded / kTsCols;
-        geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, job->d_raw_t);
-        c->launches++;
-        geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);
-        c->launches++;
-        PL2_CUDA_OK(cudaEventRecord(job->ev_stage_free, c->stream));
-        king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->d_raw_j, job->d_raw_t, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
-        c->launches++;
-      } else {
-        king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
-        c->launches++;
+    if (cur > job->stage[0].variant_cap) cur = job->stage[0].variant_cap;
+    const uint8_t* src_cur = src + static_cast<uint64_t>(done) * variant_stride_bytes;
+    if (ts && job->tiles.tile_ct) {
+      // Double-buffered: copy + pad + row re-tiling on the prep stream while the previous batch's tensor
+      // kernel (which reads the OTHER staged block through its tensor map) is still running.
+      const uint32_t b = job->buf_idx;
+      job->buf_idx ^= 1;
+      GenoStage& st = job->stage[b];
+      cudaStream_t prep = c->copy_stream;
+      if (job->kernel_pending[b]) PL2_CUDA_OK(cudaStreamWaitEvent(prep, job->ev_kernel_done[b], 0));
+      if (src_is_device == 1) {
+        // device source produced by work the caller ordered on the context's stream
+        PL2_CUDA_OK(cudaEventRecord(job->ev_src_ready, c->stream));
+        PL2_CUDA_OK(cudaStreamWaitEvent(prep, job->ev_src_ready, 0));
       }
-      PL2_CUDA_OK(cudaGetLastError());
-    }
-    if (overlap_h2d) {
-      PL2_CUDA_OK(cudaEventSynchronize(job->ev_copied));  // the caller may reuse its buffer; the kernels keep running
-    } else if (!src_is_device) {
+      PL2_CUDA_OK(cudaMemcpy2DAsync(st.d_raw, st.pitch, src_cur, variant_stride_bytes, DivUpU32(st.sample_ct, 4), cur, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, prep));
+      PL2_CUDA_OK(cudaEventRecord(job->ev_copied, prep));
+      PL2_TRY(KingTsPrepAndLaunch(job, b, cur, true));
+      if (!src_is_device) PL2_CUDA_OK(cudaEventSynchronize(job->ev_copied));  // the caller may reuse its buffer; the kernels keep running
+    } else {
+      uint32_t padded = 0;
+      PL2_TRY(StageUpload(c, &job->stage[0], src_cur, variant_stride_bytes, cur, src_is_device, &padded));
+      if (job->tiles.tile_ct) {
+        if (job->algo == kPl2KingAlgoPopcount) {
+          const uint32_t word_ct = padded / 32;
+          const uint64_t warps = static_cast<uint64_t>(job->stage[0].sample_ct_padded / 32) * word_ct;
+          split_transpose_kernel<<<static_cast<uint32_t>(DivUpU64(warps, 8)), 256, 0, c->stream>>>(job->stage[0].d_raw, job->stage[0].pitch, job->stage[0].sample_ct_padded, word_ct, job->d_planes);
+          c->launches++;
+          king_popc_kernel<<<job->tiles.tile_ct * 2, 256, 0, c->stream>>>(job->d_planes, job->stage[0].sample_ct_padded, word_ct, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+          c->launches++;
+        } else {
+          king_tc_kernel<<<job->tiles.tile_ct, kTcThreads, kTcSmemBytes, c->stream>>>(job->stage[0].d_raw, job->stage[0].pitch, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
+          c->launches++;
+        }
+        PL2_CUDA_OK(cudaGetLastError());
+      }
       // host source on the compute stream: it has been consumed once the stream reaches here
-      PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+      if (!src_is_device) PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
     }
     done += cur;
   }
   job->variants_added += variant_ct;
+  return 0;
+}
+
+int pl2gpu_king_add_variants_sharded(Pl2KingJob* job, const void* slice, uint64_t variant_stride_bytes, uint32_t slice_variant_ct, int src_is_device) {
+  if (!job || !job->ctx->c.comm) {
+    set_error("pl2gpu_king_add_variants_sharded: %s", job ? "no communicator attached to the context (pl2gpu_comm_init)" : "null job");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  if (job->algo != kPl2KingAlgoTensorTS) {
+    set_error("pl2gpu_king_add_variants_sharded: only the default (TS tensor) algorithm is sharded");
+    return 1;
+  }
+  const uint64_t total64 = static_cast<uint64_t>(slice_variant_ct) * c->comm_world;
+  if (!slice_variant_ct || total64 > job->stage[0].variant_cap) {
+    set_error("pl2gpu_king_add_variants_sharded: %u variants x %d ranks exceed the stage capacity %u", slice_variant_ct, c->comm_world, job->stage[0].variant_cap);
+    return 1;
+  }
+  if (variant_stride_bytes < DivUpU32(job->sample_ct, 4)) {
+    set_error("pl2gpu_king_add_variants_sharded: variant stride too small");
+    return 1;
+  }
+  const uint32_t total = static_cast<uint32_t>(total64);
+  const uint32_t b = job->buf_idx;
+  job->buf_idx ^= 1;
+  GenoStage& st = job->stage[b];
+  cudaStream_t prep = c->copy_stream;
+  if (job->kernel_pending[b]) PL2_CUDA_OK(cudaStreamWaitEvent(prep, job->ev_kernel_done[b], 0));
+  if (src_is_device == 1) {
+    PL2_CUDA_OK(cudaEventRecord(job->ev_src_ready, c->stream));
+    PL2_CUDA_OK(cudaStreamWaitEvent(prep, job->ev_src_ready, 0));
+  }
+  // this rank's variants land at rows [rank * slice, (rank + 1) * slice) of the staged block, are padded
+  // there, and ONE in-place all-gather of the genotype column tile makes the block complete on every GPU
+  uint8_t* mine = st.d_raw + static_cast<uint64_t>(c->comm_rank) * slice_variant_ct * st.pitch;
+  PL2_CUDA_OK(cudaMemcpy2DAsync(mine, st.pitch, slice, variant_stride_bytes, DivUpU32(st.sample_ct, 4), slice_variant_ct, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, prep));
+  PL2_CUDA_OK(cudaEventRecord(job->ev_copied, prep));
+  PL2_TRY(LaunchPadGenotypes(c, mine, st.pitch, st.sample_ct, slice_variant_ct, slice_variant_ct, prep));
+  PL2_TRY(CommAllGatherInPlace(c, st.d_raw, static_cast<uint64_t>(slice_variant_ct) * st.pitch, prep));
+  PL2_TRY(KingTsPrepAndLaunch(job, b, total, false));
+  if (!src_is_device) PL2_CUDA_OK(cudaEventSynchronize(job->ev_copied));
+  job->variants_added += total;
   return 0;
 }
 
@@ -580,15 +824,18 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   if (job->ctx) {
     cudaSetDevice(job->ctx->c.device);
     cudaStreamSynchronize(job->ctx->c.stream);
+    if (job->ctx->c.copy_stream) cudaStreamSynchronize(job->ctx->c.copy_stream);
   }
-  if (job->ctx && job->ctx->c.copy_stream) cudaStreamSynchronize(job->ctx->c.copy_stream);
   if (job->ev_copied) cudaEventDestroy(job->ev_copied);
-  if (job->ev_stage_free) cudaEventDestroy(job->ev_stage_free);
+  if (job->ev_src_ready) cudaEventDestroy(job->ev_src_ready);
   FreeTileList(&job->tiles);
-  StageFree(&job->stage);
+  for (int b = 0; b < 2; ++b) {
+    if (job->ev_prep_done[b]) cudaEventDestroy(job->ev_prep_done[b]);
+    if (job->ev_kernel_done[b]) cudaEventDestroy(job->ev_kernel_done[b]);
+    StageFree(&job->stage[b]);
+    cudaFree(job->d_raw_t[b]);
+  }
   cudaFree(job->d_planes);
-  cudaFree(job->d_raw_t);
-  cudaFree(job->d_raw_j);
   cudaFree(job->d_raw_acc);
   cudaFree(job->d_out_stage);
   cudaGetLastError();
@@ -708,6 +955,46 @@ int pl2gpu_king_pairs_end(Pl2KingPairJob* job) {
 }
 
 // ------------------------------------------------------------------------------------------ probe
+
+int pl2gpu_int8_peak(Pl2GpuCtx* ctx, uint32_t n_cols, int form, double min_seconds, double* tops_out, double* seconds_out) {
+  if (!ctx || !tops_out || n_cols < 16 || n_cols > 240 || (n_cols & 15) || (form != 0 && form != 1)) {
+    set_error("pl2gpu_int8_peak: bad arguments (n_cols must be a multiple of 16 in [16,240])");
+    return 1;
+  }
+  Ctx* c = &ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  PL2_CUDA_OK(cudaFuncSetAttribute(umma_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kProbeSmemBytes));
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PL2_CUDA_OK(cudaEventCreate(&e0));
+  PL2_CUDA_OK(cudaEventCreate(&e1));
+  const uint32_t blocks = 4096;  // x 64 UMMAs: ~15-35 ms per launch
+  const double ops_per_launch = 2.0 * 128 * n_cols * 32 * 64.0 * blocks * c->sm_count;
+  umma_peak_kernel<<<c->sm_count, 128, kProbeSmemBytes, c->stream>>>(n_cols, blocks, static_cast<uint32_t>(form));  // warm-up
+  c->launches++;
+  PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  double total_s = 0, total_ops = 0;
+  uint32_t per_batch = 8;
+  while (total_s < min_seconds) {
+    PL2_CUDA_OK(cudaEventRecord(e0, c->stream));
+    for (uint32_t k = 0; k < per_batch; ++k) umma_peak_kernel<<<c->sm_count, 128, kProbeSmemBytes, c->stream>>>(n_cols, blocks, static_cast<uint32_t>(form));
+    c->launches += per_batch;
+    PL2_CUDA_OK(cudaEventRecord(e1, c->stream));
+    PL2_CUDA_OK(cudaEventSynchronize(e1));
+    PL2_CUDA_OK(cudaGetLastError());
+    float ms = 0;
+    PL2_CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+    total_s += ms * 1e-3;
+    total_ops += ops_per_launch * per_batch;
+    if (min_seconds <= 0) break;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tops_out = total_ops / total_s / 1e12;
+  if (seconds_out) *seconds_out = total_s;
+  return 0;
+}
+
+
 
 int pl2gpu_debug_umma(Pl2GpuCtx* ctx, const uint8_t* a_img, uint32_t a_bytes, const uint8_t* b_img, uint32_t b_bytes, uint32_t a_lbo, uint32_t a_sbo, uint32_t b_lbo, uint32_t b_sbo, uint32_t a_step_bytes, uint32_t b_step_bytes, uint32_t k_steps, uint32_t idesc, uint32_t n, int32_t* d_out_host) {
   if (!ctx) {

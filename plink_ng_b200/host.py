@@ -82,6 +82,17 @@ class GpuContext:
     def stream(self) -> int:
         return int(lib.pl2gpu_ctx_stream(self._h) or 0)
 
+    def int8_peak(self, n_cols: int = 160, form: int = 1, min_seconds: float = 2.0):
+        """Measured chip-wide tcgen05 kind::i8 rate (TOP/s, seconds): the roofline denominator."""
+        tops, secs = C.c_double(), C.c_double()
+        check(lib.pl2gpu_int8_peak(self._h, n_cols, form, min_seconds, C.byref(tops), C.byref(secs)), "pl2gpu_int8_peak")
+        return float(tops.value), float(secs.value)
+
+    def comm_init(self, rank: int, world: int, unique_id: bytes):
+        """Attach an NCCL communicator (collective over all ranks; rank 0 makes the id with comm_unique_id())."""
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        check(lib.pl2gpu_comm_init(self._h, rank, world, buf), "pl2gpu_comm_init")
+
     def selftest_umma(self, verbose: bool = True):
         check(lib.pl2gpu_selftest_umma(self._h, 1 if verbose else 0), "pl2gpu_selftest_umma")
 
@@ -97,6 +108,12 @@ class GpuContext:
         self.close()
 
 
+def comm_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    check(lib.pl2gpu_comm_unique_id(buf), "pl2gpu_comm_unique_id")
+    return bytes(buf)
+
+
 def _pairs(r0: int, r1: int) -> int:
     tri = lambda r: r * (r - 1) // 2 if r else 0  # noqa: E731
     return tri(r1) - tri(r0)
@@ -105,13 +122,13 @@ def _pairs(r0: int, r1: int) -> int:
 class KingJob:
     """CalcKing's dense loop (2.0/plink2_matrix_calc.cc:2016-2117) for one row range."""
 
-    def __init__(self, ctx: GpuContext, sample_ct: int, row_start: int = 0, row_end: int = None, algo: int = KING_ALGO_AUTO):
+    def __init__(self, ctx: GpuContext, sample_ct: int, row_start: int = 0, row_end: int = None, algo: int = KING_ALGO_AUTO, max_variants_per_add: int = 0):
         self.ctx = ctx
         self.sample_ct = sample_ct
         self.row_start = row_start
         self.row_end = sample_ct if row_end is None else row_end
         self._h = C.c_void_p()
-        check(lib.pl2gpu_king_begin(ctx.handle, sample_ct, self.row_start, self.row_end, algo, C.byref(self._h)), "pl2gpu_king_begin")
+        check(lib.pl2gpu_king_begin_ex(ctx.handle, sample_ct, self.row_start, self.row_end, algo, max_variants_per_add, C.byref(self._h)), "pl2gpu_king_begin_ex")
 
     def add_variants(self, genovecs: np.ndarray):
         """genovecs: host uint64 [variants, ceil(sample_ct/32)] (PgrGet rows)."""
@@ -119,8 +136,13 @@ class KingJob:
         assert g.dtype == np.uint64 and g.ndim == 2 and g.shape[1] * 32 >= self.sample_ct
         check(lib.pl2gpu_king_add_variants(self._h, g.ctypes.data, g.strides[0], g.shape[0], 0), "pl2gpu_king_add_variants")
 
-    def add_variants_device(self, dev_ptr: int, stride_bytes: int, variant_ct: int):
-        check(lib.pl2gpu_king_add_variants(self._h, C.c_void_p(dev_ptr), stride_bytes, variant_ct, 1), "pl2gpu_king_add_variants")
+    def add_variants_device(self, dev_ptr: int, stride_bytes: int, variant_ct: int, complete: bool = False):
+        """complete=True: the device buffer is not being written by pending work (src_is_device = 2)."""
+        check(lib.pl2gpu_king_add_variants(self._h, C.c_void_p(dev_ptr), stride_bytes, variant_ct, 2 if complete else 1), "pl2gpu_king_add_variants")
+
+    def add_variants_sharded(self, ptr: int, stride_bytes: int, slice_variant_ct: int, src_is_device: int):
+        """Collective: this rank's slice of the batch; the library all-gathers the column tile (NCCL)."""
+        check(lib.pl2gpu_king_add_variants_sharded(self._h, C.c_void_p(ptr), stride_bytes, slice_variant_ct, src_is_device), "pl2gpu_king_add_variants_sharded")
 
     def counts(self, row_start: int = None, row_end: int = None) -> np.ndarray:
         r0 = self.row_start if row_start is None else row_start
