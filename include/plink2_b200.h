@@ -129,6 +129,9 @@ int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t ou
  * call should be repeated with larger buffers. */
 int pl2gpu_king_get_filtered(Pl2KingJob* job, uint32_t r0, uint32_t r1, double min_kinship, uint64_t max_out, uint32_t* pairs_out, uint32_t* counts_out, double* kinship_out, uint64_t* n_found);
 uint64_t pl2gpu_king_variants_added(Pl2KingJob* job);
+/* Device time of the most recent pair-count tensor kernel launch (CUDA events recorded around that launch on
+ * the context's stream; blocks until it has finished).  bench.py's roofline uses it. */
+int pl2gpu_king_last_kernel_ms(Pl2KingJob* job, float* ms);
 /* Idempotent; accepts NULL. */
 int pl2gpu_king_end(Pl2KingJob* job);
 

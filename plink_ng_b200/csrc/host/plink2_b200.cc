@@ -351,6 +351,18 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
   if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
+  if (c->pca) {
+    // 2.0/plink2.cc:10207-10232
+    if (c->pca_approx) {
+      if (c->pc_ct > 100) return Usage("--pca approx does not support more than 100 PCs.");
+    } else {
+      if (c->parallel_tot != 1) return Usage("Non-approximate --pca cannot be used with --parallel.");
+      if (c->make_rel || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse) {
+        if (c->grm_meanimpute != c->pca_meanimpute) return Usage("--make-rel/--make-grm-{bin,list,sparse} meanimpute setting must match\n--pca meanimpute setting.");
+        if (c->grm_cov) return Usage("--make-rel/--make-grm-{bin,list,sparse} cannot be used to compute a\ncovariance matrix in the same run as non-approximate --pca.");
+      }
+    }
+  }
   if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq)) return Usage("No command given.");
   return 0;
 }

@@ -252,7 +252,9 @@ struct Pl2KingJob {
   uint8_t* d_raw_t[2] = {nullptr, nullptr};  // TS path: row-side re-tiled copy of the job's own row tiles (geno_tile.cuh)
   CUtensorMap tmap[2];                       // TS path: 2-D tensor maps over stage[b].d_raw for the column-side TMA loads
   cudaEvent_t ev_prep_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_kernel_start[2] = {nullptr, nullptr};  // timing-enabled pair around the tensor kernel (pl2gpu_king_last_kernel_ms)
   cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
+  int last_buf = -1;
   bool kernel_pending[2] = {false, false};
   uint32_t buf_idx = 0;
   uint32_t* d_planes = nullptr;  // popcount path only
@@ -499,7 +501,7 @@ int pl2gpu_king_begin_ex(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start,
   const uint32_t cap = ClampStageCap(max_variants_per_add);
   bool ev_ok = cudaEventCreateWithFlags(&job->ev_copied, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&job->ev_src_ready, cudaEventDisableTiming) == cudaSuccess;
   for (int b = 0; b < 2 && ev_ok; ++b) {
-    ev_ok = cudaEventCreateWithFlags(&job->ev_prep_done[b], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&job->ev_kernel_done[b], cudaEventDisableTiming) == cudaSuccess;
+    ev_ok = cudaEventCreateWithFlags(&job->ev_prep_done[b], cudaEventDisableTiming) == cudaSuccess && cudaEventCreate(&job->ev_kernel_start[b]) == cudaSuccess && cudaEventCreate(&job->ev_kernel_done[b]) == cudaSuccess;
   }
   if (!ev_ok) {
     set_error("pl2gpu_king_begin: cudaEventCreate failed");
@@ -565,11 +567,13 @@ static int KingTsPrepAndLaunch(Pl2KingJob* job, uint32_t b, uint32_t cur, bool p
   PL2_CUDA_OK(cudaGetLastError());
   PL2_CUDA_OK(cudaEventRecord(job->ev_prep_done[b], prep));
   PL2_CUDA_OK(cudaStreamWaitEvent(c->stream, job->ev_prep_done[b], 0));
+  PL2_CUDA_OK(cudaEventRecord(job->ev_kernel_start[b], c->stream));
   king_ts_kernel<<<job->tiles.tile_ct, kTsThreads, kTsSmemBytes, c->stream>>>(job->tmap[b], job->d_raw_t[b], job->tiles.row_tile_first, padded, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_raw_acc);
   c->launches++;
   PL2_CUDA_OK(cudaGetLastError());
   PL2_CUDA_OK(cudaEventRecord(job->ev_kernel_done[b], c->stream));
   job->kernel_pending[b] = true;
+  job->last_buf = static_cast<int>(b);
   return 0;
 }
 
@@ -819,6 +823,17 @@ int pl2gpu_king_get_filtered(Pl2KingJob* job, uint32_t r0, uint32_t r1, double m
 
 uint64_t pl2gpu_king_variants_added(Pl2KingJob* job) { return job ? job->variants_added : 0; }
 
+int pl2gpu_king_last_kernel_ms(Pl2KingJob* job, float* ms) {
+  if (!job || !ms || job->last_buf < 0) {
+    set_error("pl2gpu_king_last_kernel_ms: no tensor-kernel launch has been recorded (TS algorithm only)");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(job->ctx->c.device));
+  PL2_CUDA_OK(cudaEventSynchronize(job->ev_kernel_done[job->last_buf]));
+  PL2_CUDA_OK(cudaEventElapsedTime(ms, job->ev_kernel_start[job->last_buf], job->ev_kernel_done[job->last_buf]));
+  return 0;
+}
+
 int pl2gpu_king_end(Pl2KingJob* job) {
   if (!job) return 0;
   if (job->ctx) {
@@ -831,6 +846,7 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   FreeTileList(&job->tiles);
   for (int b = 0; b < 2; ++b) {
     if (job->ev_prep_done[b]) cudaEventDestroy(job->ev_prep_done[b]);
+    if (job->ev_kernel_start[b]) cudaEventDestroy(job->ev_kernel_start[b]);
     if (job->ev_kernel_done[b]) cudaEventDestroy(job->ev_kernel_done[b]);
     StageFree(&job->stage[b]);
     cudaFree(job->d_raw_t[b]);

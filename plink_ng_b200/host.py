@@ -144,6 +144,11 @@ class KingJob:
         """Collective: this rank's slice of the batch; the library all-gathers the column tile (NCCL)."""
         check(lib.pl2gpu_king_add_variants_sharded(self._h, C.c_void_p(ptr), stride_bytes, slice_variant_ct, src_is_device), "pl2gpu_king_add_variants_sharded")
 
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        check(lib.pl2gpu_king_last_kernel_ms(self._h, C.byref(ms)), "pl2gpu_king_last_kernel_ms")
+        return float(ms.value)
+
     def counts(self, row_start: int = None, row_end: int = None) -> np.ndarray:
         r0 = self.row_start if row_start is None else row_start
         r1 = self.row_end if row_end is None else row_end

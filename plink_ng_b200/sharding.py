@@ -13,6 +13,32 @@ def row_block(sample_ct: int, rank: int, world: int, include_diag: bool = False)
     return parallel_bounds(sample_ct, 0 if include_diag else 1, rank, world)
 
 
+def row_block_tiles(sample_ct: int, rank: int, world: int, tile_rows: int = 128, tile_cols: int = 80, include_diag: bool = False):
+    """Tile-aligned variant of row_block for the multi-GPU product path: boundaries are multiples of the
+    128-row pair tile and balance the number of 128 x 80 pair tiles per rank (what the tensor kernel's time is
+    proportional to), so no rank computes a partial row tile twice.  Pieces still concatenate to the full
+    triangle in row order, like the reference's --parallel pieces."""
+    first = 0 if include_diag else 1
+    row_tiles = (sample_ct + tile_rows - 1) // tile_rows
+    cum = [0]
+    for rt in range(row_tiles):
+        row_end = min(sample_ct, (rt + 1) * tile_rows)
+        cols = row_end if include_diag else row_end - 1
+        cum.append(cum[-1] + (cols + tile_cols - 1) // tile_cols)
+    total = cum[-1]
+
+    def bound(k):
+        if k == 0:
+            return first
+        if k == world:
+            return sample_ct
+        target = total * k / world
+        rt = min(range(row_tiles + 1), key=lambda t: abs(cum[t] - target))
+        return max(first, min(sample_ct, rt * tile_rows))
+
+    return bound(rank), bound(rank + 1)
+
+
 def variant_slice(variant_ct: int, rank: int, world: int):
     """(per_rank, v0, v1): every rank contributes `per_rank` rows to the gather (the last ones padded);
     rank holds variants [v0, v1) of the step."""

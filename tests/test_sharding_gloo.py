@@ -67,3 +67,19 @@ def test_row_blocks_many_world_sizes():
             g = [row_block(n, r, world, include_diag=True) for r in range(world)]
             assert g[0][0] == 0 and g[-1][1] == n
             assert sum(pairs_in_rows(a, b, True) for a, b in g) == n * (n + 1) // 2
+
+
+def test_tile_aligned_row_blocks_cover_triangle_and_balance():
+    """row_block_tiles (the multi-GPU product split): contiguous, tile-aligned, complete, and balanced in pair tiles."""
+    from plink_ng_b200.sharding import pairs_in_rows, row_block_tiles
+
+    for n in (300, 4096, 100000):
+        for world in (1, 2, 4, 8):
+            blocks = [row_block_tiles(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 1 and blocks[-1][1] == n
+            assert all(blocks[k][1] == blocks[k + 1][0] for k in range(world - 1))
+            assert all(b[1] % 128 == 0 or b[1] in (1, n) for b in blocks[:-1])
+            assert sum(pairs_in_rows(a, b) for a, b in blocks) == n * (n - 1) // 2
+            if n == 100000:
+                areas = [pairs_in_rows(a, b) for a, b in blocks]
+                assert max(areas) / (sum(areas) / world) < 1.01
