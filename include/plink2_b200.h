@@ -163,6 +163,11 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
  * Returns 2 (kPglRetDegenerateData at the call site) when a zero-variance frequency meets a
  * non-monomorphic variant, like ExpandCenteredVarmaj :3844-3868. */
 int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs);
+/* Multi-GPU form (context with a communicator; collective call), as pl2gpu_king_add_variants_sharded: every rank
+ * passes its slice_variant_ct rows, the library all-gathers the world * slice_variant_ct-row column tile; the
+ * first batch_variant_ct rows of the gathered tile are the batch's variants (the rest is filler and ignored).
+ * ref_freqs: host double[batch_variant_ct] for the WHOLE batch (same on every rank) or NULL. */
+int pl2gpu_grm_add_variants_sharded(Pl2GrmJob* job, const void* slice, uint64_t variant_stride_bytes, uint32_t slice_variant_ct, uint32_t batch_variant_ct, int src_is_device, const double* ref_freqs);
 /* Normalised relationship values (CalcGrm :4769-4788) for rows [r0,r1) in the reference's in-memory
  * layout dst_grm[(j - r0) * row_stride + i], i <= j (entries i > j are left untouched / zero);
  * dst_obs (optional) receives the per-pair observation counts as float (.grm.N.bin payload). */

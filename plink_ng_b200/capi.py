@@ -60,6 +60,7 @@ SIGNATURES = {
     "pl2gpu_king_pairs_end": (C.c_int, [vp]),
     "pl2gpu_grm_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(vp)]),
     "pl2gpu_grm_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, vp]),
+    "pl2gpu_grm_add_variants_sharded": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, vp]),
     "pl2gpu_grm_get_rows": (C.c_int, [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint64, C.c_int]),
     "pl2gpu_grm_variants_added": (C.c_uint64, [vp]),
     "pl2gpu_grm_eigen_topk": (C.c_int, [vp, C.c_uint32, vp, vp]),

@@ -23,20 +23,27 @@ struct Pl2GrmJob {
   uint32_t sample_ct = 0, row_start = 0, row_end = 0;
   int flags = 0;
   TileList tiles;
-  GenoStage stage;
+  // Double-buffered like the KING job (pl2gpu.cu): copy / all-gather, padding, genotype counts, digit tables and
+  // row re-tiling of batch k+1 run on the prep stream while the tensor kernel of batch k runs.
+  GenoStage stage[2];
+  uint8_t* d_raw_i[2] = {nullptr, nullptr};  // row-side re-tiled copy of the job's own row tiles (geno_tile.cuh)
+  CUtensorMap tmap[2];                       // tensor maps over stage[b].d_raw for the column-side TMA loads
+  uint32_t* d_tab[2] = {nullptr, nullptr};
+  double* d_lvals[2] = {nullptr, nullptr};
+  uint32_t* d_counts[2] = {nullptr, nullptr};
+  double* h_lvals[2] = {nullptr, nullptr};     // pinned
+  uint32_t* h_counts[2] = {nullptr, nullptr};  // pinned
+  cudaEvent_t ev_prep_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_kernel_done[2] = {nullptr, nullptr};
+  cudaEvent_t ev_src_ready = nullptr;
+  bool kernel_pending[2] = {false, false};
+  uint32_t buf_idx = 0;
   double* d_acc_g = nullptr;
   int32_t* d_acc_obs = nullptr;
-  uint32_t* d_tab = nullptr;
-  uint8_t* d_raw_i = nullptr;  // row-side re-tiled copy of the staged block (geno_tile.cuh)
-  uint8_t* d_raw_j = nullptr;  // column-side re-tiled copy
-  double* d_lvals = nullptr;
-  uint32_t* d_counts = nullptr;
   void* d_out_stage = nullptr;
   uint64_t out_stage_bytes = 0;
   uint64_t variants_added = 0;
   uint64_t variants_with_missing = 0;
-  std::vector<double> h_lvals;
-  std::vector<uint32_t> h_counts;
 };
 
 extern "C" {
@@ -50,11 +57,7 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
     return 1;
   }
   PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
-  static bool attr_set = false;
-  if (!attr_set) {
-    PL2_CUDA_OK(cudaFuncSetAttribute(grm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGtsSmemBytes));
-    attr_set = true;
-  }
+  PL2_CUDA_OK(cudaFuncSetAttribute(grm_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGtsSmemBytes));
   Pl2GrmJob* job = new Pl2GrmJob();
   job->ctx = ctx;
   job->sample_ct = sample_ct;
@@ -66,15 +69,21 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
     return 1;
   };
   if (BuildTileList(row_start, row_end, true, &job->tiles, kGrmTileCols)) return fail();
-  if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage, kGrmSamplePad)) return fail();
   const uint64_t words = static_cast<uint64_t>(job->tiles.tile_ct) * kGrmTileWords;
   job->out_stage_bytes = 256ull << 20;
-  if (cudaMalloc(&job->d_acc_g, words * 8 + 8) != cudaSuccess || cudaMalloc(&job->d_acc_obs, words * 4 + 4) != cudaSuccess ||
-      cudaMalloc(&job->d_tab, static_cast<uint64_t>(job->stage.variant_cap) * kGrmTabPlanes * 4) != cudaSuccess ||
-      cudaMalloc(&job->d_raw_i, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
-      cudaMalloc(&job->d_raw_j, static_cast<uint64_t>(job->stage.sample_ct_padded) * (job->stage.variant_cap / 4)) != cudaSuccess ||
-      cudaMalloc(&job->d_lvals, static_cast<uint64_t>(job->stage.variant_cap) * 6 * 8) != cudaSuccess ||
-      cudaMalloc(&job->d_counts, static_cast<uint64_t>(job->stage.variant_cap) * 16) != cudaSuccess || cudaMalloc(&job->d_out_stage, job->out_stage_bytes) != cudaSuccess) {
+  bool ok = cudaEventCreateWithFlags(&job->ev_src_ready, cudaEventDisableTiming) == cudaSuccess;
+  for (int b = 0; b < 2 && ok; ++b) {
+    if (StageAlloc(sample_ct, kMaxStageVariants, &job->stage[b], kGrmSamplePad)) return fail();
+    const uint64_t cap = job->stage[b].variant_cap;
+    const uint64_t raw_i_bytes = static_cast<uint64_t>(job->tiles.row_tile_ct) * kTileRows * (cap / 4);
+    ok = cudaMalloc(&job->d_raw_i[b], raw_i_bytes ? raw_i_bytes : 16) == cudaSuccess && cudaMalloc(&job->d_tab[b], cap * kGrmTabPlanes * 4) == cudaSuccess &&
+         cudaMalloc(&job->d_lvals[b], cap * 6 * 8) == cudaSuccess && cudaMalloc(&job->d_counts[b], cap * 16) == cudaSuccess &&
+         cudaHostAlloc(reinterpret_cast<void**>(&job->h_lvals[b]), cap * 6 * 8, cudaHostAllocDefault) == cudaSuccess &&
+         cudaHostAlloc(reinterpret_cast<void**>(&job->h_counts[b]), cap * 16, cudaHostAllocDefault) == cudaSuccess &&
+         cudaEventCreateWithFlags(&job->ev_prep_done[b], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&job->ev_kernel_done[b], cudaEventDisableTiming) == cudaSuccess;
+    if (ok && MakeRawTensorMap(&job->tmap[b], job->stage[b].d_raw, job->stage[b].pitch, job->stage[b].variant_cap, kTsRawBoxBytes, kGrmKc)) return fail();
+  }
+  if (!ok || cudaMalloc(&job->d_acc_g, words * 8 + 8) != cudaSuccess || cudaMalloc(&job->d_acc_obs, words * 4 + 4) != cudaSuccess || cudaMalloc(&job->d_out_stage, job->out_stage_bytes) != cudaSuccess) {
     cudaGetLastError();
     set_error("pl2gpu_grm_begin: insufficient device memory for %u pair tiles (%.1f GB of accumulators); narrow the row range", job->tiles.tile_ct, words * 12 / 1e9);
     return fail();
@@ -87,6 +96,114 @@ int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uin
   return 0;
 }
 
+// One staged batch: stage[b] rows [0, cur) hold the (already sample-padded when !pad_valid_rows) genotypes.
+// Counts -> per-variant lookup values (host, a few microseconds per thousand variants) -> fixed-point digit
+// tables, row re-tiling, tensor kernel.  ref_freqs: this batch's REF frequencies or nullptr.
+static int GrmPrepAndLaunch(Pl2GrmJob* job, uint32_t b, uint32_t cur, bool pad_valid_rows, const double* ref_freqs) {
+  Ctx* c = &job->ctx->c;
+  cudaStream_t prep = c->copy_stream;
+  GenoStage& st = job->stage[b];
+  const bool cov = (job->flags & kPl2GrmCov) != 0;
+  const uint32_t padded = RoundUpU32(cur, kVariantPad);
+  if (pad_valid_rows) {
+    PL2_TRY(LaunchPadGenotypes(c, st.d_raw, st.pitch, st.sample_ct, cur, padded, prep));
+  } else if (padded > cur) {
+    PL2_TRY(LaunchPadGenotypes(c, st.d_raw + static_cast<uint64_t>(cur) * st.pitch, st.pitch, st.sample_ct, 0, padded - cur, prep));
+  }
+  // genotype counts of the batch: missingness presence, the zero-variance consistency check
+  // (ExpandCenteredVarmaj :3844-3868) and, when the caller passes no frequencies, ComputeAlleleFreqs.
+  geno_counts_kernel<<<DivUpU32(cur, 8), 256, 0, prep>>>(st.d_raw, st.pitch, st.sample_ct, st.sample_ct_padded, cur, job->d_counts[b]);
+  c->launches++;
+  uint32_t* h_counts = job->h_counts[b];
+  double* h_lvals = job->h_lvals[b];
+  PL2_CUDA_OK(cudaMemcpyAsync(h_counts, job->d_counts[b], 16ull * cur, cudaMemcpyDeviceToHost, prep));
+  PL2_CUDA_OK(cudaStreamSynchronize(prep));  // the prep stream only: the previous batch's tensor kernel keeps running
+  memset(h_lvals, 0, 48ull * cur);
+  double max_l = 0.0;
+  for (uint32_t v = 0; v < cur; ++v) {
+    const uint32_t n0 = h_counts[4ull * v], n1 = h_counts[4ull * v + 1], n2 = h_counts[4ull * v + 2], n3 = h_counts[4ull * v + 3];
+    if (n3) job->variants_with_missing++;
+    double ref_freq;
+    if (ref_freqs) {
+      ref_freq = ref_freqs[v];
+    } else {
+      const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);
+      ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
+    }
+    const double alt_freq = 1.0 - ref_freq;
+    double inv_stdev;
+    if (!cov) {
+      const double variance = 2 * ref_freq * alt_freq;
+      if (!(variance > kSmallEpsilon)) {
+        // reference errors out unless the variant really is monomorphic for the expected allele
+        bool bad = n1 != 0;
+        if (variance != variance) {
+          bad = bad || n0 || n2;
+        } else if (ref_freq > 0.5) {
+          bad = bad || n2;
+        } else {
+          bad = bad || n0;
+        }
+        if (bad) {
+          set_error("pl2gpu_grm_add_variants: variant %llu has zero-variance allele frequency %g but non-monomorphic genotypes (kPglRetDegenerateData, plink2_matrix_calc.cc:3844-3868)", static_cast<unsigned long long>(job->variants_added + v), ref_freq);
+          return 2;
+        }
+        continue;  // all-zero column
+      }
+      inv_stdev = 1.0 / sqrt(variance);
+    } else {
+      inv_stdev = 1.0;
+    }
+    // PopulateRescaledDosage lookup table (plink2_common.cc:323-330)
+    const double slope = inv_stdev;
+    const double intercept = -2 * alt_freq * inv_stdev;
+    const double z[3] = {intercept, intercept + slope, intercept + 2 * slope};
+    double* lv = &h_lvals[6ull * v];
+    for (int g = 0; g < 3; ++g) {
+      lv[g] = slope * z[g];          // multiplies the other sample's dosage g
+      lv[3 + g] = intercept * z[g];  // multiplies the other sample's non-missing indicator
+      max_l = std::max(max_l, std::max(fabs(lv[g]), fabs(lv[3 + g])));
+    }
+  }
+  // fixed-point scale: |L| * 2^F < 2^38 so five balanced base-256 digits always suffice
+  int f_bits = 0;
+  if (max_l > 0.0) {
+    int e;
+    frexp(max_l, &e);  // max_l = m * 2^e, m in [0.5, 1)
+    f_bits = static_cast<int>(kGrmFixedBits) - e;
+  }
+  const double scale = ldexp(1.0, f_bits), inv_scale = ldexp(1.0, -f_bits);
+  PL2_CUDA_OK(cudaMemcpyAsync(job->d_lvals[b], h_lvals, 48ull * cur, cudaMemcpyHostToDevice, prep));
+  grm_tables_kernel<<<DivUpU32(padded, 128), 128, 0, prep>>>(job->d_lvals[b], cur, padded, scale, job->d_tab[b]);
+  c->launches++;
+  if (job->tiles.tile_ct) {
+    geno_tile_rows_kernel<<<dim3(padded / 64, job->tiles.row_tile_ct * (kTileRows / 64)), 256, 0, prep>>>(st.d_raw, st.pitch, padded / 32, job->tiles.row_tile_first * kTileRows, job->d_raw_i[b]);
+    c->launches++;
+    PL2_CUDA_OK(cudaGetLastError());
+    PL2_CUDA_OK(cudaEventRecord(job->ev_prep_done[b], prep));
+    PL2_CUDA_OK(cudaStreamWaitEvent(c->stream, job->ev_prep_done[b], 0));
+    grm_ts_kernel<<<job->tiles.tile_ct, kGtsThreads, kGtsSmemBytes, c->stream>>>(job->tmap[b], job->d_raw_i[b], job->tiles.row_tile_first, padded, job->d_tab[b], inv_scale, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_acc_g, job->d_acc_obs);
+    c->launches++;
+    PL2_CUDA_OK(cudaGetLastError());
+    PL2_CUDA_OK(cudaEventRecord(job->ev_kernel_done[b], c->stream));
+    job->kernel_pending[b] = true;
+  }
+  return 0;
+}
+
+static int GrmAcquireBuffer(Pl2GrmJob* job, int src_is_device, uint32_t* b_out) {
+  Ctx* c = &job->ctx->c;
+  const uint32_t b = job->buf_idx;
+  job->buf_idx ^= 1;
+  if (job->kernel_pending[b]) PL2_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, job->ev_kernel_done[b], 0));
+  if (src_is_device == 1) {
+    PL2_CUDA_OK(cudaEventRecord(job->ev_src_ready, c->stream));
+    PL2_CUDA_OK(cudaStreamWaitEvent(c->copy_stream, job->ev_src_ready, 0));
+  }
+  *b_out = b;
+  return 0;
+}
+
 int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs) {
   if (!job) {
     set_error("pl2gpu_grm_add_variants: null job");
@@ -94,91 +211,56 @@ int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t varia
   }
   Ctx* c = &job->ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
-  const bool cov = (job->flags & kPl2GrmCov) != 0;
+  if (variant_stride_bytes < DivUpU32(job->sample_ct, 4)) {
+    set_error("pl2gpu_grm_add_variants: variant stride too small");
+    return 1;
+  }
   const uint8_t* src = static_cast<const uint8_t*>(genovecs);
   for (uint32_t done = 0; done < variant_ct;) {
-    const uint32_t cur = std::min(job->stage.variant_cap, variant_ct - done);
-    uint32_t padded = 0;
-    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
-    // genotype counts of the batch: missingness presence, the zero-variance consistency check
-    // (ExpandCenteredVarmaj :3844-3868) and, when the caller passes no frequencies, ComputeAlleleFreqs.
-    geno_counts_kernel<<<DivUpU32(cur, 8), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, job->stage.sample_ct, job->stage.sample_ct_padded, cur, job->d_counts);
-    c->launches++;
-    job->h_counts.resize(4ull * cur);
-    PL2_CUDA_OK(cudaMemcpyAsync(job->h_counts.data(), job->d_counts, 16ull * cur, cudaMemcpyDeviceToHost, c->stream));
-    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
-    job->h_lvals.assign(6ull * cur, 0.0);
-    double max_l = 0.0;
-    for (uint32_t v = 0; v < cur; ++v) {
-      const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2], n3 = job->h_counts[4ull * v + 3];
-      if (n3) job->variants_with_missing++;
-      double ref_freq;
-      if (ref_freqs) {
-        ref_freq = ref_freqs[done + v];
-      } else {
-        const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);
-        ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
-      }
-      const double alt_freq = 1.0 - ref_freq;
-      double inv_stdev;
-      if (!cov) {
-        const double variance = 2 * ref_freq * alt_freq;
-        if (!(variance > kSmallEpsilon)) {
-          // reference errors out unless the variant really is monomorphic for the expected allele
-          bool bad = n1 != 0;
-          if (variance != variance) {
-            bad = bad || n0 || n2;
-          } else if (ref_freq > 0.5) {
-            bad = bad || n2;
-          } else {
-            bad = bad || n0;
-          }
-          if (bad) {
-            set_error("pl2gpu_grm_add_variants: variant %llu has zero-variance allele frequency %g but non-monomorphic genotypes (kPglRetDegenerateData, plink2_matrix_calc.cc:3844-3868)", static_cast<unsigned long long>(job->variants_added + done + v), ref_freq);
-            return 2;
-          }
-          continue;  // all-zero column
-        }
-        inv_stdev = 1.0 / sqrt(variance);
-      } else {
-        inv_stdev = 1.0;
-      }
-      // PopulateRescaledDosage lookup table (plink2_common.cc:323-330)
-      const double slope = inv_stdev;
-      const double intercept = -2 * alt_freq * inv_stdev;
-      const double z[3] = {intercept, intercept + slope, intercept + 2 * slope};
-      double* lv = &job->h_lvals[6ull * v];
-      for (int g = 0; g < 3; ++g) {
-        lv[g] = slope * z[g];          // multiplies the other sample's dosage g
-        lv[3 + g] = intercept * z[g];  // multiplies the other sample's non-missing indicator
-        max_l = std::max(max_l, std::max(fabs(lv[g]), fabs(lv[3 + g])));
-      }
-    }
-    // fixed-point scale: |L| * 2^F < 2^38 so five balanced base-256 digits always suffice
-    int f_bits = 0;
-    if (max_l > 0.0) {
-      int e;
-      frexp(max_l, &e);  // max_l = m * 2^e, m in [0.5, 1)
-      f_bits = static_cast<int>(kGrmFixedBits) - e;
-    }
-    const double scale = ldexp(1.0, f_bits), inv_scale = ldexp(1.0, -f_bits);
-    PL2_CUDA_OK(cudaMemcpyAsync(job->d_lvals, job->h_lvals.data(), 48ull * cur, cudaMemcpyHostToDevice, c->stream));
-    grm_tables_kernel<<<DivUpU32(padded, 128), 128, 0, c->stream>>>(job->d_lvals, cur, padded, scale, job->d_tab);
-    c->launches++;
-    if (job->tiles.tile_ct) {
-      {
-        const uint32_t coltile_ct = job->stage.sample_ct_padded / kTsCols;
-        geno_tile_rows_kernel<<<dim3(padded / 64, job->stage.sample_ct_padded / 64), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / 32, 0, job->d_raw_i);
-        geno_tile_cols_kernel<<<dim3(padded / kTsKcJ, DivUpU32(coltile_ct, 16)), 256, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, padded / kTsKcJ, coltile_ct, job->d_raw_j);
-        grm_ts_kernel<<<job->tiles.tile_ct, kGtsThreads, kGtsSmemBytes, c->stream>>>(job->d_raw_j, job->d_raw_i, padded, job->d_tab, inv_scale, job->tiles.d_tile_order, job->tiles.d_tile_rt, job->tiles.d_tile_tc, job->d_acc_g, job->d_acc_obs);
-        c->launches += 3;
-      }
-    }
-    PL2_CUDA_OK(cudaGetLastError());
-    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));  // h_lvals / host source reuse
+    const uint32_t cur = std::min(job->stage[0].variant_cap, variant_ct - done);
+    uint32_t b;
+    PL2_TRY(GrmAcquireBuffer(job, src_is_device, &b));
+    GenoStage& st = job->stage[b];
+    PL2_CUDA_OK(cudaMemcpy2DAsync(st.d_raw, st.pitch, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, DivUpU32(st.sample_ct, 4), cur, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream));
+    // GrmPrepAndLaunch synchronises the prep stream (it needs the counts on the host), so a host source has been
+    // consumed when it returns; the tensor kernel keeps running
+    const int rc = GrmPrepAndLaunch(job, b, cur, true, ref_freqs ? ref_freqs + done : nullptr);
+    if (rc) return rc;
+    job->variants_added += cur;
     done += cur;
   }
-  job->variants_added += variant_ct;
+  return 0;
+}
+
+int pl2gpu_grm_add_variants_sharded(Pl2GrmJob* job, const void* slice, uint64_t variant_stride_bytes, uint32_t slice_variant_ct, uint32_t batch_variant_ct, int src_is_device, const double* ref_freqs) {
+  if (!job || !job->ctx->c.comm) {
+    set_error("pl2gpu_grm_add_variants_sharded: %s", job ? "no communicator attached to the context (pl2gpu_comm_init)" : "null job");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint64_t total64 = static_cast<uint64_t>(slice_variant_ct) * c->comm_world;
+  if (!slice_variant_ct || total64 > job->stage[0].variant_cap || !batch_variant_ct || batch_variant_ct > total64) {
+    set_error("pl2gpu_grm_add_variants_sharded: bad slice (%u variants x %d ranks, batch %u, stage capacity %u)", slice_variant_ct, c->comm_world, batch_variant_ct, job->stage[0].variant_cap);
+    return 1;
+  }
+  if (variant_stride_bytes < DivUpU32(job->sample_ct, 4)) {
+    set_error("pl2gpu_grm_add_variants_sharded: variant stride too small");
+    return 1;
+  }
+  uint32_t b;
+  PL2_TRY(GrmAcquireBuffer(job, src_is_device, &b));
+  GenoStage& st = job->stage[b];
+  cudaStream_t prep = c->copy_stream;
+  uint8_t* mine = st.d_raw + static_cast<uint64_t>(c->comm_rank) * slice_variant_ct * st.pitch;
+  PL2_CUDA_OK(cudaMemcpy2DAsync(mine, st.pitch, slice, variant_stride_bytes, DivUpU32(st.sample_ct, 4), slice_variant_ct, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, prep));
+  PL2_TRY(LaunchPadGenotypes(c, mine, st.pitch, st.sample_ct, slice_variant_ct, slice_variant_ct, prep));
+  PL2_TRY(CommAllGatherInPlace(c, st.d_raw, static_cast<uint64_t>(slice_variant_ct) * st.pitch, prep));
+  // only the first batch_variant_ct rows of the gathered tile are real variants (the last slice of a file is
+  // topped up with filler rows); the rest is overwritten with "missing" by the tail padding
+  const int rc = GrmPrepAndLaunch(job, b, batch_variant_ct, false, ref_freqs);
+  if (rc) return rc;
+  job->variants_added += batch_variant_ct;
   return 0;
 }
 
@@ -355,16 +437,23 @@ int pl2gpu_grm_end(Pl2GrmJob* job) {
   if (job->ctx) {
     cudaSetDevice(job->ctx->c.device);
     cudaStreamSynchronize(job->ctx->c.stream);
+    cudaStreamSynchronize(job->ctx->c.copy_stream);
   }
   FreeTileList(&job->tiles);
-  StageFree(&job->stage);
+  for (int b = 0; b < 2; ++b) {
+    StageFree(&job->stage[b]);
+    cudaFree(job->d_raw_i[b]);
+    cudaFree(job->d_tab[b]);
+    cudaFree(job->d_lvals[b]);
+    cudaFree(job->d_counts[b]);
+    if (job->h_lvals[b]) cudaFreeHost(job->h_lvals[b]);
+    if (job->h_counts[b]) cudaFreeHost(job->h_counts[b]);
+    if (job->ev_prep_done[b]) cudaEventDestroy(job->ev_prep_done[b]);
+    if (job->ev_kernel_done[b]) cudaEventDestroy(job->ev_kernel_done[b]);
+  }
+  if (job->ev_src_ready) cudaEventDestroy(job->ev_src_ready);
   cudaFree(job->d_acc_g);
   cudaFree(job->d_acc_obs);
-  cudaFree(job->d_tab);
-  cudaFree(job->d_raw_i);
-  cudaFree(job->d_raw_j);
-  cudaFree(job->d_lvals);
-  cudaFree(job->d_counts);
   cudaFree(job->d_out_stage);
   cudaGetLastError();
   delete job;

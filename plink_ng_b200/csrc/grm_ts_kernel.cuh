@@ -12,6 +12,8 @@
 // that on the very first k-step they zero-initialise every accumulator (accumulate = 0) and the g
 // products always accumulate.
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 #include "geno_expand.cuh"
 #include "geno_tile.cuh"
@@ -27,20 +29,38 @@ constexpr uint32_t kGtsASlotCols = 16;
 constexpr uint32_t kGtsStagesJ = 3;
 constexpr uint32_t kGtsLboJ = kGrmPlanesJ * kGrmGroupsJ * kCoreBytes + 64;  // 7104: +64 keeps the K-permuted rows bank-conflict free
 constexpr uint32_t kGtsStageBytesJ = (kGrmKc / 8) * kGtsLboJ;               // 56832
-constexpr uint32_t kGtsSmemBytes = kGtsStagesJ * kGtsStageBytesJ + 1024;
+// Operand staging as in king_ts_kernel.cuh: one producer warp keeps three shared-memory rings full with the TMA
+// unit - raw column boxes read in place from the variant-major block through a tensor map (UTMALDG), row-side
+// k-steps of the sample-major copy, and the per-variant digit tables (both UBLKCP).
+constexpr uint32_t kGtsRawJSlots = 4;
+constexpr uint32_t kGtsRawJBytes = kGrmKc * kTsRawBoxBytes;                 // 2048
+constexpr uint32_t kGtsRawISlots = 8;
+constexpr uint32_t kGtsRawIBytes = kTileRows * 8;                           // 1024
+constexpr uint32_t kGtsTabSlots = 4;
+constexpr uint32_t kGtsTabBytes = kGrmTabPlanes * kGrmKc * 4;               // 3072
+constexpr uint32_t kGtsSmemOffRawJ = kGtsStagesJ * kGtsStageBytesJ;         // 170496 (multiple of 128)
+constexpr uint32_t kGtsSmemOffRawI = kGtsSmemOffRawJ + kGtsRawJSlots * kGtsRawJBytes;
+constexpr uint32_t kGtsSmemOffTab = kGtsSmemOffRawI + kGtsRawISlots * kGtsRawIBytes;
+constexpr uint32_t kGtsSmemBytes = kGtsSmemOffTab + kGtsTabSlots * kGtsTabBytes + 1024;
 constexpr uint32_t kGtsRowWarps = 8;
 constexpr uint32_t kGtsColWarps = 10;                                       // 5 words x 64 variants per stage
-constexpr uint32_t kGtsThreads = 32 * (kGtsRowWarps + kGtsColWarps + 1);
+constexpr uint32_t kGtsIssuerWarp = kGtsRowWarps + kGtsColWarps;
+constexpr uint32_t kGtsThreads = 32 * (kGtsRowWarps + kGtsColWarps + 2);    // + UMMA issuer + TMA producer
+static_assert(kGtsSmemOffRawJ % 128 == 0, "TMA destination alignment (128 bytes without swizzle)");
 static_assert(kGtsSmemBytes <= 232448, "GRM TS pipeline exceeds the 227 KB shared-memory opt-in limit");
 static_assert(kGtsAccCols + kGtsASlots * kGtsASlotCols <= 512, "GRM TS accumulators + A slots exceed TMEM");
 
 __global__ void __launch_bounds__(kGtsThreads, 1)
-grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw_i, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tab, double inv_scale, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, double* __restrict__ acc_g, int32_t* __restrict__ acc_obs) {
+grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __restrict__ raw_i, uint32_t row_tile_first, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tab, double inv_scale, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, double* __restrict__ acc_g, int32_t* __restrict__ acc_obs) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full_a[kGtsASlots];
   __shared__ __align__(8) uint64_t bar_empty_a[kGtsASlots];
   __shared__ __align__(8) uint64_t bar_full_b[kGtsStagesJ];
   __shared__ __align__(8) uint64_t bar_empty_b[kGtsStagesJ];
+  __shared__ __align__(8) uint64_t bar_full_rj[kGtsRawJSlots];   // raw column box + its table slot (same ring index)
+  __shared__ __align__(8) uint64_t bar_empty_rj[kGtsRawJSlots];
+  __shared__ __align__(8) uint64_t bar_full_ri[kGtsRawISlots];
+  __shared__ __align__(8) uint64_t bar_empty_ri[kGtsRawISlots];
   __shared__ __align__(8) uint64_t bar_acc;
   __shared__ uint32_t tmem_base_slot;
 
@@ -62,10 +82,18 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
       mbar_init(&bar_full_b[s], kGtsColWarps);
       mbar_init(&bar_empty_b[s], 1);
     }
+    for (uint32_t s = 0; s < kGtsRawJSlots; ++s) {
+      mbar_init(&bar_full_rj[s], 1);
+      mbar_init(&bar_empty_rj[s], kGtsColWarps);
+    }
+    for (uint32_t s = 0; s < kGtsRawISlots; ++s) {
+      mbar_init(&bar_full_ri[s], 1);
+      mbar_init(&bar_empty_ri[s], 4);
+    }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
   }
-  if (warp == kGtsRowWarps + kGtsColWarps) tmem_alloc<512>(&tmem_base_slot);
+  if (warp == kGtsIssuerWarp) tmem_alloc<512>(&tmem_base_slot);
   tc_fence_before_sync();
   __syncthreads();
   tc_fence_after_sync();
@@ -79,11 +107,8 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     const uint32_t row = 32 * lq + lane;
     const uint32_t thread_zero = tid * (variant_ct_padded >> 31);  // 0; keeps the tables in vector registers (geno_expand.cuh)
     const uint32_t tab_g = table_reg(kTabDosage, thread_zero), tab_m = table_reg(kTabNonmiss, thread_zero);
-    const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt) * (2 * stage_iters) * 1024 + row * 8;
+    const uint32_t ring_i = smem_base + kGtsSmemOffRawI + row * 8;
     const uint32_t ta = tmem_base + ((32u * lq) << 16) + kGtsAccCols + grp * kGtsASlotCols;
-    auto load_i = [&](uint32_t n) -> uint2 {
-      return (n < stage_iters) ? __ldg(reinterpret_cast<const uint2*>(src_i + 1024ull * (2 * n + grp))) : make_uint2(0xFFFFFFFFu, 0xFFFFFFFFu);
-    };
     struct ExpI {
       uint32_t v[2][8];
     };
@@ -99,81 +124,71 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
       }
       return e;
     };
-    constexpr uint32_t kLa = 4;
-    uint2 pre_i[kLa];
-#pragma unroll
-    for (uint32_t d = 0; d < kLa; ++d) pre_i[d] = load_i(d);
-    ExpI cur = expand_i(pre_i[0]);
-    for (uint32_t n0 = 0; n0 < stage_iters; n0 += kLa) {  // stage_iters is a multiple of 4 (variant pad 256)
-#pragma unroll
-      for (uint32_t d = 0; d < kLa; ++d) {
-        const uint32_t n = n0 + d;
-        pre_i[d] = load_i(n + kLa);
-        mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
-        tc_fence_after_sync();
-        tmem_st8(ta, cur.v[0]);
-        tmem_st8(ta + 8, cur.v[1]);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&bar_full_a[grp], lane);
-        cur = expand_i(pre_i[(d + 1) % kLa]);
-      }
+    auto fetch = [&](uint32_t n) -> ExpI {
+      const uint32_t ks = 2 * n + grp;
+      const uint32_t si = ks % kGtsRawISlots;
+      mbar_wait(&bar_full_ri[si], (ks / kGtsRawISlots) & 1);
+      const ExpI e = expand_i(lds64(ring_i + si * kGtsRawIBytes));
+      mbar_arrive_warp(&bar_empty_ri[si], lane);
+      return e;
+    };
+    ExpI cur = fetch(0);
+    for (uint32_t n = 0; n < stage_iters; ++n) {
+      mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
+      tc_fence_after_sync();
+      tmem_st8(ta, cur.v[0]);
+      tmem_st8(ta + 8, cur.v[1]);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive_warp(&bar_full_a[grp], lane);
+      if (n + 1 < stage_iters) cur = fetch(n + 1);
     }
   } else if (warp < kGtsRowWarps + kGtsColWarps) {
     // ---------------- column-side producers: 2-bit words -> 11 int8 planes in shared memory ----------------
     // Thread = (word w of the 20-byte row, variant k of the 64-variant stage); the per-variant digit
     // tables come from grm_tables_kernel.
     const uint32_t t = tid - 32 * kGtsRowWarps;  // 0..319
-    const uint32_t k = t & 63;
-    const uint32_t w = t >> 6;
-    const uint8_t* src_j = raw_j + static_cast<uint64_t>(ct) * stage_iters * (kGrmKc * 20) + k * 20 + 4 * w;
-    const uint32_t* tab_k = tab + k;  // tab[stage][plane][64 variants] (grm_tab_index)
+    const uint32_t combo = t >> 3;               // (k group of 8) * 5 + word: see king_ts_kernel.cuh
+    const uint32_t k = 8 * (combo / 5) + (t & 7);
+    const uint32_t w = combo % 5;
+    const uint32_t ring_j = smem_base + kGtsSmemOffRawJ + k * kTsRawBoxBytes + ((ct * (kGrmTileCols / 4)) & 15u) + 4 * w;  // box starts 16-byte aligned
+    const uint32_t ring_t = smem_base + kGtsSmemOffTab + 4 * k;  // tab[slot][plane][64 variants] (grm_tab_index)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);  // K rows in the PRMT position order of the row side
     const uint32_t dst_k = (kpos >> 3) * kGtsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
     struct RowJ {
       uint32_t w;
       uint32_t t[kGrmPlanesJ];  // tables of planes 0..10
     };
-    auto load_j = [&](uint32_t it) -> RowJ {
+    auto fetch = [&](uint32_t it) -> RowJ {
+      const uint32_t sj = it % kGtsRawJSlots;
+      mbar_wait(&bar_full_rj[sj], (it / kGtsRawJSlots) & 1);
       RowJ r;
-      r.w = 0xFFFFFFFFu;
+      r.w = lds32(ring_j + sj * kGtsRawJBytes);
 #pragma unroll
-      for (uint32_t p = 0; p < kGrmPlanesJ; ++p) r.t[p] = 0;
-      if (it < stage_iters) {
-        r.w = __ldg(reinterpret_cast<const uint32_t*>(src_j + static_cast<uint64_t>(it) * (kGrmKc * 20)));
-        const uint32_t* tp = tab_k + static_cast<uint64_t>(it) * (kGrmTabPlanes * 64);
-#pragma unroll
-        for (uint32_t p = 0; p < kGrmPlanesJ; ++p) r.t[p] = __ldg(tp + p * 64);
-      }
+      for (uint32_t p = 0; p < kGrmPlanesJ; ++p) r.t[p] = lds32(ring_t + sj * kGtsTabBytes + p * (kGrmKc * 4));
       return r;
     };
     auto sts16 = [](uint32_t addr, const uint4& v) { asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory"); };
-    constexpr uint32_t kLa = 2;
     constexpr uint32_t kPlane = kGrmGroupsJ * kCoreBytes;  // 640 bytes between planes inside a k-group
-    RowJ pre_j[kLa];
-#pragma unroll
-    for (uint32_t d = 0; d < kLa; ++d) pre_j[d] = load_j(d);
+    RowJ cur = fetch(0);
     uint32_t sb = 0, ph = 0;
-    for (uint32_t it0 = 0; it0 < stage_iters; it0 += kLa) {
+    for (uint32_t it = 0; it < stage_iters; ++it) {
+      const Sel4 sel = make_selectors(cur.w);
+      mbar_wait(&bar_empty_b[sb], ph ^ 1);
+      const uint32_t a0 = smem_base + sb * kGtsStageBytesJ + dst_k;
 #pragma unroll
-      for (uint32_t d = 0; d < kLa; ++d) {
-        const uint32_t it = it0 + d;
-        const RowJ cur = pre_j[d];
-        pre_j[d] = load_j(it + kLa);
-        const Sel4 sel = make_selectors(cur.w);
-        mbar_wait(&bar_empty_b[sb], ph ^ 1);
-        const uint32_t a0 = smem_base + sb * kGtsStageBytesJ + dst_k;
-#pragma unroll
-        for (uint32_t p = 0; p < kGrmPlanesJ; ++p) sts16(a0 + p * kPlane, expand16(cur.t[p], sel));
-        fence_proxy_async_smem();
-        mbar_arrive_warp(&bar_full_b[sb], lane);
-        if (++sb == kGtsStagesJ) {
-          sb = 0;
-          ph ^= 1;
-        }
+      for (uint32_t p = 0; p < kGrmPlanesJ; ++p) sts16(a0 + p * kPlane, expand16(cur.t[p], sel));
+      // every lane has consumed its ring words (they fed the PRMTs above): release the raw / table slot
+      mbar_arrive_warp(&bar_empty_rj[it % kGtsRawJSlots], lane);
+      fence_proxy_async_smem();
+      mbar_arrive_warp(&bar_full_b[sb], lane);
+      if (it + 1 < stage_iters) cur = fetch(it + 1);
+      if (++sb == kGtsStagesJ) {
+        sb = 0;
+        ph ^= 1;
       }
     }
-  } else {
+  } else if (warp == kGtsIssuerWarp) {
     // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
     constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kGrmTileCols, false, true);
     constexpr uint32_t idesc_n80 = make_idesc_i8(128, kGrmTileCols, false, true);
@@ -211,6 +226,29 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     }
     if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
+  } else {
+    // ---------------- TMA producer: one elected lane keeps the raw / table rings full ----------------
+    if (elect_one_sync()) {
+      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * kGtsRawIBytes;
+      const uint32_t ring_j = smem_base + kGtsSmemOffRawJ, ring_i = smem_base + kGtsSmemOffRawI, ring_t = smem_base + kGtsSmemOffTab;
+      const int32_t c0 = static_cast<int32_t>((ct * (kGrmTileCols / 4)) & ~15u);
+      for (uint32_t it = 0; it < stage_iters; ++it) {
+#pragma unroll
+        for (uint32_t kk = 0; kk < 2; ++kk) {
+          const uint32_t ks = 2 * it + kk;
+          const uint32_t si = ks % kGtsRawISlots;
+          mbar_wait(&bar_empty_ri[si], ((ks / kGtsRawISlots) & 1) ^ 1);
+          mbar_expect_tx(&bar_full_ri[si], kGtsRawIBytes);
+          bulk_load_1d(ring_i + si * kGtsRawIBytes, src_i + static_cast<uint64_t>(ks) * kGtsRawIBytes, kGtsRawIBytes, &bar_full_ri[si]);
+        }
+        const uint32_t sj = it % kGtsRawJSlots;
+        mbar_wait(&bar_empty_rj[sj], ((it / kGtsRawJSlots) & 1) ^ 1);
+        mbar_expect_tx(&bar_full_rj[sj], kGtsRawJBytes + kGtsTabBytes);
+        tma_load_2d(ring_j + sj * kGtsRawJBytes, &tmap_raw, c0, static_cast<int32_t>(it * kGrmKc), &bar_full_rj[sj]);
+        bulk_load_1d(ring_t + sj * kGtsTabBytes, tab + static_cast<uint64_t>(it) * (kGrmTabPlanes * kGrmKc), kGtsTabBytes, &bar_full_rj[sj]);
+      }
+    }
+    __syncwarp();
   }
 
   if (warp < kGtsRowWarps) {
@@ -247,7 +285,7 @@ grm_ts_kernel(const uint8_t* __restrict__ raw_j, const uint8_t* __restrict__ raw
     tc_fence_before_sync();
   }
   __syncthreads();
-  if (warp == kGtsRowWarps + kGtsColWarps) {
+  if (warp == kGtsIssuerWarp) {
     tc_fence_after_sync();
     tmem_dealloc<512>(tmem_base);
   }

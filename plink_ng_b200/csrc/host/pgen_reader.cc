@@ -322,8 +322,12 @@ bool PgenReader::DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err) {
       if (!ParseDifflistAndApply(rec, end, true, dst, 0, err, &after)) return false;
       break;
     }
+    case 5:
+      // all hom-REF, zero-length record (2.0/include/pgenlib_read.cc:2741-2743, :2996-3000)
+      for (uint32_t w = 0; w < words; ++w) dst[w] = 0;
+      break;
     default:
-      *err = "reserved .pgen variant record type 5";
+      *err = "invalid .pgen variant record type";
       return false;
   }
   ZeroTrailing(dst, n);

@@ -1520,6 +1520,20 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
 // --------------------------------------------------------------------------------------- LD prune
 // `--freq` (WriteAlleleFreqs, 2.0/plink2_misc.cc:3573; counts from the LoadAlleleAndGenoCounts pass,
 // 2.0/plink2.cc:2280): founder ALT allele frequencies of biallelic hard calls -> <out>.afreq.
+// Chromosome as the reference prints it under its default output encoding (kfChrOutputMT; chrtoa /
+// ChrNameStd, 2.0/plink2_common.cc:2150-2227): bare number for autosomes, X / Y / XY / MT, PAR1 / PAR2 kept.
+std::string ChrNameOut(uint32_t code, const std::string& as_read) {
+  if (code <= 22) return std::to_string(code);
+  if (code == 23) return "X";
+  if (code == 24) return "Y";
+  if (code == 26) return "MT";
+  std::string u = as_read;
+  if (u.size() > 3 && (u[0] == 'c' || u[0] == 'C') && (u[1] == 'h' || u[1] == 'H') && (u[2] == 'r' || u[2] == 'R')) u = u.substr(3);
+  for (auto& ch : u) ch = static_cast<char>(toupper(ch));
+  if (u == "PAR1" || u == "PAR2") return u;
+  return "XY";
+}
+
 int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
@@ -1579,7 +1593,7 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
         w += t.size();
         *w++ = '\t';
       };
-      puts(V.chr_name[v]);
+      puts(ChrNameOut(V.chr_code[v], V.chr_name[v]));
       puts(V.id[v]);
       puts(V.ref[v]);
       puts(V.alt[v]);

@@ -87,98 +87,45 @@ char* dtoa_g(double x, char* p) {
     *p++ = '-';
     x = -x;
   }
+  // Exponential notation (|x| < 1e-4 or >= 1e6, after rounding to 6 digits): bring x into [1, 10) by the binary
+  // decomposition of its decimal exponent, largest power first.  The comparison bounds and the multiply order
+  // are part of the output contract (a different scaling order rounds differently in the last printed digit).
+  struct Pow10Step {
+    uint32_t e;
+    double below, up;    // x < below  -> x *= up   (small side)
+    double from, down;   // x >= from  -> x *= down (large side)
+  };
+  static const Pow10Step kSteps[9] = {
+      {256, 9.9999949999999e-256, 1.0e256, 9.9999949999999e255, 1.0e-256}, {128, 9.9999949999999e-128, 1.0e128, 9.9999949999999e127, 1.0e-128},
+      {64, 9.9999949999999e-64, 1.0e64, 9.9999949999999e63, 1.0e-64},      {32, 9.9999949999999e-32, 1.0e32, 9.9999949999999e31, 1.0e-32},
+      {16, 9.9999949999999e-16, 1.0e16, 9.9999949999999e15, 1.0e-16},      {8, 9.9999949999999e-8, 100000000, 9.9999949999999e7, 1.0e-8},
+      {4, 9.9999949999999e-4, 10000, 9.9999949999999e3, 1.0e-4},           {2, 9.9999949999999e-2, 100, 9.9999949999999e1, 1.0e-2},
+      {1, 9.9999949999999e-1, 10, 9.9999949999999e0, 1.0e-1}};
   if (x < 9.9999949999999e-5) {
-    // exponential notation, small: scale up by the binary decomposition of the exponent
+    if (x == 0.0) {
+      *p++ = '0';
+      return p;
+    }
     uint32_t xp10 = 0;
-    if (x < 9.9999949999999e-16) {
-      if (x < 9.9999949999999e-128) {
-        if (x == 0.0) {
-          *p++ = '0';
-          return p;
-        }
-        if (x < 9.9999949999999e-256) {
-          x *= 1.0e256;
-          xp10 |= 256;
-        } else {
-          x *= 1.0e128;
-          xp10 |= 128;
-        }
+    for (const Pow10Step& st : kSteps) {
+      if (x < st.below) {
+        x *= st.up;
+        xp10 += st.e;
       }
-      if (x < 9.9999949999999e-64) {
-        x *= 1.0e64;
-        xp10 |= 64;
-      }
-      if (x < 9.9999949999999e-32) {
-        x *= 1.0e32;
-        xp10 |= 32;
-      }
-      if (x < 9.9999949999999e-16) {
-        x *= 1.0e16;
-        xp10 |= 16;
-      }
-    }
-    if (x < 9.9999949999999e-8) {
-      x *= 100000000;
-      xp10 |= 8;
-    }
-    if (x < 9.9999949999999e-4) {
-      x *= 10000;
-      xp10 |= 4;
-    }
-    if (x < 9.9999949999999e-2) {
-      x *= 100;
-      xp10 |= 2;
-    }
-    if (x < 9.9999949999999e-1) {
-      x *= 10;
-      ++xp10;
     }
     return PutExp(xp10, '-', PutMantissa(x, p));
   }
   if (x >= 999999.49999999) {
+    if (x > DBL_MAX) {
+      memcpy(p, "inf", 3);
+      return p + 3;
+    }
     uint32_t xp10 = 0;
-    if (x >= 9.9999949999999e15) {
-      if (x >= 9.9999949999999e127) {
-        if (x > DBL_MAX) {
-          memcpy(p, "inf", 3);
-          return p + 3;
-        }
-        if (x >= 9.9999949999999e255) {
-          x *= 1.0e-256;
-          xp10 |= 256;
-        } else {
-          x *= 1.0e-128;
-          xp10 |= 128;
-        }
+    for (const Pow10Step& st : kSteps) {
+      if (x >= st.from) {
+        x *= st.down;
+        xp10 += st.e;
       }
-      if (x >= 9.9999949999999e63) {
-        x *= 1.0e-64;
-        xp10 |= 64;
-      }
-      if (x >= 9.9999949999999e31) {
-        x *= 1.0e-32;
-        xp10 |= 32;
-      }
-      if (x >= 9.9999949999999e15) {
-        x *= 1.0e-16;
-        xp10 |= 16;
-      }
-    }
-    if (x >= 9.9999949999999e7) {
-      x *= 1.0e-8;
-      xp10 |= 8;
-    }
-    if (x >= 9.9999949999999e3) {
-      x *= 1.0e-4;
-      xp10 |= 4;
-    }
-    if (x >= 9.9999949999999e1) {
-      x *= 1.0e-2;
-      xp10 |= 2;
-    }
-    if (x >= 9.9999949999999e0) {
-      x *= 1.0e-1;
-      ++xp10;
     }
     return PutExp(xp10, '+', PutMantissa(x, p));
   }
@@ -247,97 +194,42 @@ char* dtoa_g_p8(double x, char* p) {
     *p++ = '-';
     x = -x;
   }
+  // same exponent decomposition as dtoa_g, with the 8-digit rounding bounds
+  struct Pow10Step {
+    uint32_t e;
+    double below, up, from, down;
+  };
+  static const Pow10Step kSteps[9] = {
+      {256, 9.9999999499999e-256, 1.0e256, 9.9999999499999e255, 1.0e-256}, {128, 9.9999999499999e-128, 1.0e128, 9.9999999499999e127, 1.0e-128},
+      {64, 9.9999999499999e-64, 1.0e64, 9.9999999499999e63, 1.0e-64},      {32, 9.9999999499999e-32, 1.0e32, 9.9999999499999e31, 1.0e-32},
+      {16, 9.9999999499999e-16, 1.0e16, 9.9999999499999e15, 1.0e-16},      {8, 9.9999999499999e-8, 100000000, 9.9999999499999e7, 1.0e-8},
+      {4, 9.9999999499999e-4, 10000, 9.9999999499999e3, 1.0e-4},           {2, 9.9999999499999e-2, 100, 9.9999999499999e1, 1.0e-2},
+      {1, 9.9999999499999e-1, 10, 9.9999999499999e0, 1.0e-1}};
   if (x < 9.9999999499999e-5) {
+    if (x == 0.0) {
+      *start = '0';  // the sign of -0 is dropped, as in the reference
+      return start + 1;
+    }
     uint32_t xp10 = 0;
-    if (x < 9.9999999499999e-16) {
-      if (x < 9.9999999499999e-128) {
-        if (x == 0.0) {
-          *start = '0';  // the sign of -0 is dropped, as in the reference
-          return start + 1;
-        }
-        if (x < 9.9999999499999e-256) {
-          x *= 1.0e256;
-          xp10 |= 256;
-        } else {
-          x *= 1.0e128;
-          xp10 |= 128;
-        }
+    for (const Pow10Step& st : kSteps) {
+      if (x < st.below) {
+        x *= st.up;
+        xp10 += st.e;
       }
-      if (x < 9.9999999499999e-64) {
-        x *= 1.0e64;
-        xp10 |= 64;
-      }
-      if (x < 9.9999999499999e-32) {
-        x *= 1.0e32;
-        xp10 |= 32;
-      }
-      if (x < 9.9999999499999e-16) {
-        x *= 1.0e16;
-        xp10 |= 16;
-      }
-    }
-    if (x < 9.9999999499999e-8) {
-      x *= 100000000;
-      xp10 |= 8;
-    }
-    if (x < 9.9999999499999e-4) {
-      x *= 10000;
-      xp10 |= 4;
-    }
-    if (x < 9.9999999499999e-2) {
-      x *= 100;
-      xp10 |= 2;
-    }
-    if (x < 9.9999999499999e-1) {
-      x *= 10;
-      ++xp10;
     }
     return PutExp(xp10, '-', PutMantissa8(x, p));
   }
   if (x >= 99999999.499999) {
+    if (x > DBL_MAX) {  // the reference prints " inf" (with the blank) for +infinity
+      memcpy(start, (p == start) ? " inf" : "-inf", 4);
+      return start + 4;
+    }
     uint32_t xp10 = 0;
-    if (x >= 9.9999999499999e15) {
-      if (x >= 9.9999999499999e127) {
-        if (x > DBL_MAX) {  // the reference prints " inf" (with the blank) for +infinity
-          memcpy(start, (p == start) ? " inf" : "-inf", 4);
-          return start + 4;
-        }
-        if (x >= 9.9999999499999e255) {
-          x *= 1.0e-256;
-          xp10 |= 256;
-        } else {
-          x *= 1.0e-128;
-          xp10 |= 128;
-        }
+    for (const Pow10Step& st : kSteps) {
+      if (x >= st.from) {
+        x *= st.down;
+        xp10 += st.e;
       }
-      if (x >= 9.9999999499999e63) {
-        x *= 1.0e-64;
-        xp10 |= 64;
-      }
-      if (x >= 9.9999999499999e31) {
-        x *= 1.0e-32;
-        xp10 |= 32;
-      }
-      if (x >= 9.9999999499999e15) {
-        x *= 1.0e-16;
-        xp10 |= 16;
-      }
-    }
-    if (x >= 9.9999999499999e7) {
-      x *= 1.0e-8;
-      xp10 |= 8;
-    }
-    if (x >= 9.9999999499999e3) {
-      x *= 1.0e-4;
-      xp10 |= 4;
-    }
-    if (x >= 9.9999999499999e1) {
-      x *= 1.0e-2;
-      xp10 |= 2;
-    }
-    if (x >= 9.9999999499999e0) {
-      x *= 1.0e-1;
-      ++xp10;
     }
     return PutExp(xp10, '+', PutMantissa8(x, p));
   }

@@ -160,7 +160,8 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     const uint32_t combo = t >> 3;                 // 0..39 = (k group of 8) * 5 + word
     const uint32_t k = 8 * (combo / 5) + (t & 7);
     const uint32_t w = combo % 5;
-    const uint32_t ring_j = smem_base + kTsSmemOffRawJ + k * kTsRawBoxBytes + 4 * w;
+    // the box starts at the 16-byte boundary at or below byte column 20 * ct (TMA-friendly start address)
+    const uint32_t ring_j = smem_base + kTsSmemOffRawJ + k * kTsRawBoxBytes + ((ct * (kTsCols / 4)) & 15u) + 4 * w;
     // K rows are stored in the PRMT position order of the row side (geno_expand.cuh): variant k of a
     // 16-variant group sits at row SampleToPos(k % 16)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
@@ -231,10 +232,9 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
   } else {
     // ---------------- TMA producer: one elected lane keeps both raw rings full ----------------
     if (elect_one_sync()) {
-      prefetch_tensormap(&tmap_raw);
       const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * kTsRawIBytes;
       const uint32_t ring_j = smem_base + kTsSmemOffRawJ, ring_i = smem_base + kTsSmemOffRawI;
-      const int32_t c0 = static_cast<int32_t>(ct * (kTsCols / 4));
+      const int32_t c0 = static_cast<int32_t>((ct * (kTsCols / 4)) & ~15u);  // 20 bytes at offset 0/4/8/12 of a 32-byte box
       for (uint32_t it = 0; it < stage_iters; ++it) {
 #pragma unroll
         for (uint32_t kk = 0; kk < 2; ++kk) {

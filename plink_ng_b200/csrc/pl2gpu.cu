@@ -983,8 +983,8 @@ int pl2gpu_int8_peak(Pl2GpuCtx* ctx, uint32_t n_cols, int form, double min_secon
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   PL2_CUDA_OK(cudaEventCreate(&e0));
   PL2_CUDA_OK(cudaEventCreate(&e1));
-  const uint32_t blocks = 4096;  // x 64 UMMAs: ~15-35 ms per launch
-  const double ops_per_launch = 2.0 * 128 * n_cols * 32 * 64.0 * blocks * c->sm_count;
+  const uint32_t blocks = 4096;  // x 32 UMMAs x 2 issuer warps: ~15-35 ms per launch
+  const double ops_per_launch = 2.0 * 128 * n_cols * 32 * 32.0 * 2 * blocks * c->sm_count;
   umma_peak_kernel<<<c->sm_count, 128, kProbeSmemBytes, c->stream>>>(n_cols, blocks, static_cast<uint32_t>(form));  // warm-up
   c->launches++;
   PL2_CUDA_OK(cudaStreamSynchronize(c->stream));

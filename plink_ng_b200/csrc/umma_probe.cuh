@@ -195,20 +195,22 @@ umma_issue_bench_kernel(uint32_t n, uint32_t reps, uint32_t mode, uint32_t issue
   }
 }
 
-// Chip-wide int8 tensor peak (pl2gpu_int8_peak): one CTA per SM, one issuer warp, `blocks` rounds of 64
-// back-to-back UMMAs (M = 128, N = n, K = 32) alternating between two accumulator ranges, a commit + wait per
-// round so the queue stays bounded.  Operands are whatever shared / tensor memory holds (the tensor pipe's
-// timing does not depend on the data).  ts = 1: A operand from tensor memory (the production kernels' form).
+// Chip-wide int8 tensor peak (pl2gpu_int8_peak): one CTA per SM, TWO issuer warps with their own accumulator
+// columns ([0,240) and [240,480)) so the tensor pipe always has an independent UMMA queued (a single issuer
+// accumulating into one range measures the issue/dependency latency instead: 96.6 clk per N = 160 UMMA).
+// Each issuer runs `blocks` rounds of 32 back-to-back UMMAs (M = 128, N = n, K = 32), one commit per round,
+// waiting for the round before the previous one so the queue stays bounded.  Operands are whatever shared /
+// tensor memory holds (timing does not depend on the data).  ts = 1: A operand from tensor memory.
 __global__ void __launch_bounds__(128, 1)
 umma_peak_kernel(uint32_t n, uint32_t blocks, uint32_t ts) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ __align__(8) uint64_t bar_done[2];
+  __shared__ __align__(8) uint64_t bar_done[2][2];
   __shared__ uint32_t tmem_base_slot;
   const uint32_t warp = uniform_warp_idx();
   const uint32_t smem_base = (smem_u32(smem) + 1023u) & ~1023u;
   if (threadIdx.x == 0) {
-    mbar_init(&bar_done[0], 1);
-    mbar_init(&bar_done[1], 1);
+    for (int i = 0; i < 2; ++i)
+      for (int j = 0; j < 2; ++j) mbar_init(&bar_done[i][j], 1);
     mbar_fence_init();
   }
   if (warp == 0) tmem_alloc<512>(&tmem_base_slot);
@@ -216,29 +218,29 @@ umma_peak_kernel(uint32_t n, uint32_t blocks, uint32_t ts) {
   __syncthreads();
   tc_fence_after_sync();
   const uint32_t tmem_base = tmem_base_slot;
-  if (warp == 0) {
+  if (warp < 2) {
     const uint32_t tmem_u = uniform_u32(tmem_base);
     const uint32_t idesc = make_idesc_i8(128, n, ts == 0, true);
     const uint64_t da = make_smem_desc(smem_base, 2048, 128), db = make_smem_desc(smem_base + 32768, 2048, 128);
+    const uint32_t d = tmem_u + warp * 240;
     for (uint32_t blk = 0; blk < blocks; ++blk) {
       const uint32_t half = blk & 1;
-      // the round issued two iterations ago used the same accumulator half: wait for it before re-using the barrier
-      if (blk >= 2) mbar_wait(&bar_done[half], ((blk >> 1) - 1) & 1);
+      if (blk >= 2) mbar_wait(&bar_done[warp][half], ((blk >> 1) - 1) & 1);
       if (elect_one_sync()) {
-        const uint32_t d = tmem_u + half * 240;
+        if (ts == 0) {
 #pragma unroll 8
-        for (uint32_t r = 0; r < 64; ++r) {
-          if (ts == 0) umma_i8_ss(d, da, db, idesc, 1u);
-          else umma_i8_ts(d, tmem_u + 480, db, idesc, 1u);
+          for (uint32_t r = 0; r < 32; ++r) umma_i8_ss(d, da, db, idesc, 1u);
+        } else {
+#pragma unroll 8
+          for (uint32_t r = 0; r < 32; ++r) umma_i8_ts(d, tmem_u + 480, db, idesc, 1u);
         }
-        umma_commit(&bar_done[half]);
+        umma_commit(&bar_done[warp][half]);
       }
       __syncwarp();
     }
-    // drain both halves
     for (uint32_t half = 0; half < 2; ++half) {
       const uint32_t rounds = (blocks + 1 - half) / 2;  // commits made on this half
-      if (rounds) mbar_wait(&bar_done[half], (rounds - 1) & 1);
+      if (rounds) mbar_wait(&bar_done[warp][half], (rounds - 1) & 1);
     }
   }
   tc_fence_before_sync();
