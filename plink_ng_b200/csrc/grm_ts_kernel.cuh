@@ -34,8 +34,8 @@ constexpr uint32_t kGtsStageBytesJ = (kGrmKc / 8) * kGtsLboJ;               // 5
 // k-steps of the sample-major copy, and the per-variant digit tables (both UBLKCP).
 constexpr uint32_t kGtsRawJSlots = 4;
 constexpr uint32_t kGtsRawJBytes = kGrmKc * kTsRawBoxBytes;                 // 2048
-constexpr uint32_t kGtsRawISlots = 8;
-constexpr uint32_t kGtsRawIBytes = kTileRows * 8;                           // 1024
+constexpr uint32_t kGtsRawISlots = 2;                                       // four row-side k-steps per 4 KB copy
+constexpr uint32_t kGtsRawIBytes = 4 * kTileRows * 8;                       // 4096
 constexpr uint32_t kGtsTabSlots = 4;
 constexpr uint32_t kGtsTabBytes = kGrmTabPlanes * kGrmKc * 4;               // 3072
 constexpr uint32_t kGtsSmemOffRawJ = kGtsStagesJ * kGtsStageBytesJ;         // 170496 (multiple of 128)
@@ -88,7 +88,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
     }
     for (uint32_t s = 0; s < kGtsRawISlots; ++s) {
       mbar_init(&bar_full_ri[s], 1);
-      mbar_init(&bar_empty_ri[s], 4);
+      mbar_init(&bar_empty_ri[s], kGtsRowWarps);
     }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
@@ -124,24 +124,40 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
       }
       return e;
     };
-    auto fetch = [&](uint32_t n) -> ExpI {
-      const uint32_t ks = 2 * n + grp;
-      const uint32_t si = ks % kGtsRawISlots;
-      mbar_wait(&bar_full_ri[si], (ks / kGtsRawISlots) & 1);
-      const ExpI e = expand_i(lds64(ring_i + si * kGtsRawIBytes));
-      mbar_arrive_warp(&bar_empty_ri[si], lane);
-      return e;
+    // ring slot = k-steps 4 q .. 4 q + 3; this group needs 4 q + grp and 4 q + grp + 2 (see king_ts_kernel.cuh)
+    struct Words {
+      uint2 w[2];
     };
-    ExpI cur = fetch(0);
-    for (uint32_t n = 0; n < stage_iters; ++n) {
-      mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
-      tc_fence_after_sync();
-      tmem_st8(ta, cur.v[0]);
-      tmem_st8(ta + 8, cur.v[1]);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive_warp(&bar_full_a[grp], lane);
-      if (n + 1 < stage_iters) cur = fetch(n + 1);
+    auto load_slot = [&](uint32_t q) -> Words {
+      const uint32_t si = q % kGtsRawISlots;
+      mbar_wait(&bar_full_ri[si], (q / kGtsRawISlots) & 1);
+      Words r;
+      r.w[0] = lds64(ring_i + si * kGtsRawIBytes + grp * (kTileRows * 8));
+      r.w[1] = lds64(ring_i + si * kGtsRawIBytes + (grp + 2) * (kTileRows * 8));
+      mbar_release_warp(&bar_empty_ri[si], lane, r.w[0].x ^ r.w[0].y ^ r.w[1].x ^ r.w[1].y);
+      return r;
+    };
+    const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4 (variant pad 256)
+    Words words = load_slot(0);
+    ExpI cur = expand_i(words.w[0]);
+    for (uint32_t q = 0; q < slot_iters; ++q) {
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t n = 2 * q + h;  // k-step 2 n + grp
+        mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
+        tc_fence_after_sync();
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[grp], lane);
+        if (h == 0) {
+          cur = expand_i(words.w[1]);
+        } else if (q + 1 < slot_iters) {
+          words = load_slot(q + 1);
+          cur = expand_i(words.w[0]);
+        }
+      }
     }
   } else if (warp < kGtsRowWarps + kGtsColWarps) {
     // ---------------- column-side producers: 2-bit words -> 11 int8 planes in shared memory ----------------
@@ -179,7 +195,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
 #pragma unroll
       for (uint32_t p = 0; p < kGrmPlanesJ; ++p) sts16(a0 + p * kPlane, expand16(cur.t[p], sel));
       // every lane has consumed its ring words (they fed the PRMTs above): release the raw / table slot
-      mbar_arrive_warp(&bar_empty_rj[it % kGtsRawJSlots], lane);
+      mbar_release_warp(&bar_empty_rj[it % kGtsRawJSlots], lane, cur.w ^ cur.t[0]);
       fence_proxy_async_smem();
       mbar_arrive_warp(&bar_full_b[sb], lane);
       if (it + 1 < stage_iters) cur = fetch(it + 1);
@@ -229,17 +245,15 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
   } else {
     // ---------------- TMA producer: one elected lane keeps the raw / table rings full ----------------
     if (elect_one_sync()) {
-      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * kGtsRawIBytes;
+      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * (kTileRows * 8);
       const uint32_t ring_j = smem_base + kGtsSmemOffRawJ, ring_i = smem_base + kGtsSmemOffRawI, ring_t = smem_base + kGtsSmemOffTab;
       const int32_t c0 = static_cast<int32_t>((ct * (kGrmTileCols / 4)) & ~15u);
       for (uint32_t it = 0; it < stage_iters; ++it) {
-#pragma unroll
-        for (uint32_t kk = 0; kk < 2; ++kk) {
-          const uint32_t ks = 2 * it + kk;
-          const uint32_t si = ks % kGtsRawISlots;
-          mbar_wait(&bar_empty_ri[si], ((ks / kGtsRawISlots) & 1) ^ 1);
+        if (!(it & 1)) {
+          const uint32_t q = it >> 1, si = q % kGtsRawISlots;
+          mbar_wait(&bar_empty_ri[si], ((q / kGtsRawISlots) & 1) ^ 1);
           mbar_expect_tx(&bar_full_ri[si], kGtsRawIBytes);
-          bulk_load_1d(ring_i + si * kGtsRawIBytes, src_i + static_cast<uint64_t>(ks) * kGtsRawIBytes, kGtsRawIBytes, &bar_full_ri[si]);
+          bulk_load_1d(ring_i + si * kGtsRawIBytes, src_i + static_cast<uint64_t>(q) * kGtsRawIBytes, kGtsRawIBytes, &bar_full_ri[si]);
         }
         const uint32_t sj = it % kGtsRawJSlots;
         mbar_wait(&bar_empty_rj[sj], ((it / kGtsRawJSlots) & 1) ^ 1);

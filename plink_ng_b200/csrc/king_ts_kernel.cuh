@@ -35,10 +35,13 @@ constexpr uint32_t kTsASlotCols = 24;
 constexpr uint32_t kTsStagesJ = 4;
 constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1984: +64 keeps the K-permuted rows bank-conflict free
 constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 15872
-constexpr uint32_t kTsRawJSlots = 8;                                // TMA ring: raw column boxes (64 variants x 32 B)
-constexpr uint32_t kTsRawJBytes = kTsKcJ * kTsRawBoxBytes;          // 2048
-constexpr uint32_t kTsRawISlots = 16;                               // bulk-copy ring: row-side k-steps (128 samples x 8 B)
-constexpr uint32_t kTsRawIBytes = kTileRows * 8;                    // 1024
+// Both rings move 4 KB per copy (= 4 k-steps): the single producer lane spends ~3 mbarrier / TMA operations per
+// copy, and at one copy per k-step (first version: 34.2 ms vs 24.4 ms per 16,384 x 65,536 batch) it, not the
+// tensor pipe, set the pace.
+constexpr uint32_t kTsRawJSlots = 4;                                // TMA ring: raw column boxes (128 variants x 32 B = two stages)
+constexpr uint32_t kTsRawJBytes = 2 * kTsKcJ * kTsRawBoxBytes;      // 4096
+constexpr uint32_t kTsRawISlots = 4;                                // bulk-copy ring: four row-side k-steps (128 samples x 8 B each)
+constexpr uint32_t kTsRawIBytes = 4 * kTileRows * 8;                // 4096
 constexpr uint32_t kTsSmemOffRawJ = kTsStagesJ * kTsStageBytesJ;    // 63488 (multiple of 1024)
 constexpr uint32_t kTsSmemOffRawI = kTsSmemOffRawJ + kTsRawJSlots * kTsRawJBytes;
 constexpr uint32_t kTsSmemBytes = kTsSmemOffRawI + kTsRawISlots * kTsRawIBytes + 1024;
@@ -87,7 +90,7 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     }
     for (uint32_t s = 0; s < kTsRawISlots; ++s) {
       mbar_init(&bar_full_ri[s], 1);
-      mbar_init(&bar_empty_ri[s], 4);           // the four lane-quarter warps of the owning group
+      mbar_init(&bar_empty_ri[s], kTsRowWarps); // every row warp reads two of the slot's four k-steps
     }
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
@@ -126,30 +129,44 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
       }
       return e;
     };
-    // fetch k-step ks = 2 n + grp from the ring, release the slot once every lane has expanded its word
-    auto fetch = [&](uint32_t n) -> ExpI {
-      const uint32_t ks = 2 * n + grp;
-      const uint32_t si = ks % kTsRawISlots;
-      mbar_wait(&bar_full_ri[si], (ks / kTsRawISlots) & 1);
-      const uint2 w = lds64(ring_i + si * kTsRawIBytes);
-      const ExpI e = expand_i(w);
-      mbar_arrive_warp(&bar_empty_ri[si], lane);
-      return e;
+    // One ring slot = k-steps 4 q .. 4 q + 3; this group needs 4 q + grp and 4 q + grp + 2.  Both words are read
+    // (and the slot released) up front, expanded one k-step ahead of the tensor-memory store.
+    struct Words {
+      uint2 w[2];
     };
-    ExpI cur = fetch(0);
-    for (uint32_t n = 0; n < stage_iters; ++n) {
-      const uint32_t ks = 2 * n + grp;
-      const uint32_t slot = ks % kTsASlots;
-      mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
-      tc_fence_after_sync();
-      const uint32_t ta = taddr_lane + slot * kTsASlotCols;
-      tmem_st8(ta, cur.v[0]);
-      tmem_st8(ta + 8, cur.v[1]);
-      tmem_st8(ta + 16, cur.v[2]);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive_warp(&bar_full_a[slot], lane);
-      if (n + 1 < stage_iters) cur = fetch(n + 1);
+    auto load_slot = [&](uint32_t q) -> Words {
+      const uint32_t si = q % kTsRawISlots;
+      mbar_wait(&bar_full_ri[si], (q / kTsRawISlots) & 1);
+      Words r;
+      r.w[0] = lds64(ring_i + si * kTsRawIBytes + grp * (kTileRows * 8));
+      r.w[1] = lds64(ring_i + si * kTsRawIBytes + (grp + 2) * (kTileRows * 8));
+      mbar_release_warp(&bar_empty_ri[si], lane, r.w[0].x ^ r.w[0].y ^ r.w[1].x ^ r.w[1].y);
+      return r;
+    };
+    const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4
+    Words words = load_slot(0);
+    ExpI cur = expand_i(words.w[0]);
+    for (uint32_t q = 0; q < slot_iters; ++q) {
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t ks = 4 * q + grp + 2 * h;
+        const uint32_t slot = ks % kTsASlots;
+        mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t ta = taddr_lane + slot * kTsASlotCols;
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st8(ta + 16, cur.v[2]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[slot], lane);
+        if (h == 0) {
+          cur = expand_i(words.w[1]);
+        } else if (q + 1 < slot_iters) {
+          words = load_slot(q + 1);
+          cur = expand_i(words.w[0]);
+        }
+      }
     }
   } else if (warp < kTsIssuerWarp) {
     // ---------------- column-side producers: 2-bit words -> int8 planes in shared memory ----------------
@@ -169,28 +186,46 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     struct ExpJ {
       uint4 vt, vh, vs;
     };
-    auto fetch = [&](uint32_t it) -> ExpJ {
-      const uint32_t sj = it % kTsRawJSlots;
-      mbar_wait(&bar_full_rj[sj], (it / kTsRawJSlots) & 1);
-      const Sel4 sel = make_selectors(lds32(ring_j + sj * kTsRawJBytes));
+    auto expand_j = [&](uint32_t word) -> ExpJ {
+      const Sel4 sel = make_selectors(word);
       ExpJ e;
       e.vt = expand16(tab_t, sel);
       e.vh = expand16(tab_h, sel);
       e.vs = expand16(tab_s, sel);
-      mbar_arrive_warp(&bar_empty_rj[sj], lane);
       return e;
     };
-    ExpJ cur = fetch(0);
-    for (uint32_t it = 0; it < stage_iters; ++it) {
-      const uint32_t sb = it % kTsStagesJ;
-      mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
-      const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(cur.vt.x), "r"(cur.vt.y), "r"(cur.vt.z), "r"(cur.vt.w) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(cur.vh.x), "r"(cur.vh.y), "r"(cur.vh.z), "r"(cur.vh.w) : "memory");
-      asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(cur.vs.x), "r"(cur.vs.y), "r"(cur.vs.z), "r"(cur.vs.w) : "memory");
-      fence_proxy_async_smem();
-      mbar_arrive_warp(&bar_full_b[sb], lane);
-      if (it + 1 < stage_iters) cur = fetch(it + 1);
+    // One ring slot = 128 variants = stages 2 q and 2 q + 1; variant k of either stage is this thread's.
+    auto load_slot = [&](uint32_t q) -> uint2 {
+      const uint32_t sj = q % kTsRawJSlots;
+      mbar_wait(&bar_full_rj[sj], (q / kTsRawJSlots) & 1);
+      uint2 r;
+      r.x = lds32(ring_j + sj * kTsRawJBytes);
+      r.y = lds32(ring_j + sj * kTsRawJBytes + kTsKcJ * kTsRawBoxBytes);
+      mbar_release_warp(&bar_empty_rj[sj], lane, r.x ^ r.y);
+      return r;
+    };
+    const uint32_t slot_iters = stage_iters / 2;
+    uint2 words = load_slot(0);
+    ExpJ cur = expand_j(words.x);
+    for (uint32_t q = 0; q < slot_iters; ++q) {
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t it = 2 * q + h;
+        const uint32_t sb = it % kTsStagesJ;
+        mbar_wait(&bar_empty_b[sb], ((it / kTsStagesJ) & 1) ^ 1);
+        const uint32_t a0 = smem_base + sb * kTsStageBytesJ + dst_k;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(cur.vt.x), "r"(cur.vt.y), "r"(cur.vt.z), "r"(cur.vt.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kTsGroupsJ * kCoreBytes), "r"(cur.vh.x), "r"(cur.vh.y), "r"(cur.vh.z), "r"(cur.vh.w) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kTsGroupsJ * kCoreBytes), "r"(cur.vs.x), "r"(cur.vs.y), "r"(cur.vs.z), "r"(cur.vs.w) : "memory");
+        fence_proxy_async_smem();
+        mbar_arrive_warp(&bar_full_b[sb], lane);
+        if (h == 0) {
+          cur = expand_j(words.y);
+        } else if (q + 1 < slot_iters) {
+          words = load_slot(q + 1);
+          cur = expand_j(words.x);
+        }
+      }
     }
   } else if (warp == kTsIssuerWarp) {
     // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
@@ -232,22 +267,18 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
   } else {
     // ---------------- TMA producer: one elected lane keeps both raw rings full ----------------
     if (elect_one_sync()) {
-      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * kTsRawIBytes;
+      const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * (kTileRows * 8);
       const uint32_t ring_j = smem_base + kTsSmemOffRawJ, ring_i = smem_base + kTsSmemOffRawI;
       const int32_t c0 = static_cast<int32_t>((ct * (kTsCols / 4)) & ~15u);  // 20 bytes at offset 0/4/8/12 of a 32-byte box
-      for (uint32_t it = 0; it < stage_iters; ++it) {
-#pragma unroll
-        for (uint32_t kk = 0; kk < 2; ++kk) {
-          const uint32_t ks = 2 * it + kk;
-          const uint32_t si = ks % kTsRawISlots;
-          mbar_wait(&bar_empty_ri[si], ((ks / kTsRawISlots) & 1) ^ 1);
-          mbar_expect_tx(&bar_full_ri[si], kTsRawIBytes);
-          bulk_load_1d(ring_i + si * kTsRawIBytes, src_i + static_cast<uint64_t>(ks) * kTsRawIBytes, kTsRawIBytes, &bar_full_ri[si]);
-        }
-        const uint32_t sj = it % kTsRawJSlots;
-        mbar_wait(&bar_empty_rj[sj], ((it / kTsRawJSlots) & 1) ^ 1);
+      for (uint32_t q = 0; q < stage_iters / 2; ++q) {
+        const uint32_t si = q % kTsRawISlots;
+        mbar_wait(&bar_empty_ri[si], ((q / kTsRawISlots) & 1) ^ 1);
+        mbar_expect_tx(&bar_full_ri[si], kTsRawIBytes);
+        bulk_load_1d(ring_i + si * kTsRawIBytes, src_i + static_cast<uint64_t>(q) * kTsRawIBytes, kTsRawIBytes, &bar_full_ri[si]);
+        const uint32_t sj = q % kTsRawJSlots;
+        mbar_wait(&bar_empty_rj[sj], ((q / kTsRawJSlots) & 1) ^ 1);
         mbar_expect_tx(&bar_full_rj[sj], kTsRawJBytes);
-        tma_load_2d(ring_j + sj * kTsRawJBytes, &tmap_raw, c0, static_cast<int32_t>(it * kTsKcJ), &bar_full_rj[sj]);
+        tma_load_2d(ring_j + sj * kTsRawJBytes, &tmap_raw, c0, static_cast<int32_t>(q * 2 * kTsKcJ), &bar_full_rj[sj]);
       }
     }
     __syncwarp();

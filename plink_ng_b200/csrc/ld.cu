@@ -8,6 +8,7 @@
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "ld_kernels.cuh"
+#include "ld_ts_kernel.cuh"
 
 using namespace pl2;
 
@@ -74,36 +75,99 @@ int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_
   }
   Ctx* c = &ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
+  // PL2_LD_ALGO=popcount selects the bit-plane popcount kernel (ld_kernels.cuh), kept as an independent cross-check
+  // of the default tensor kernel (ld_ts_kernel.cuh); both produce the same exact integer sums.
+  const char* algo_env = getenv("PL2_LD_ALGO");
+  const bool use_popc = algo_env && !strcmp(algo_env, "popcount");
   const uint32_t band_r = RoundUpU32(band, 64);
   const uint32_t rows_cap = kLdChunkVariants + band_r;
-  GenoStage st;
-  PL2_TRY(StageAlloc(founder_ct, rows_cap, &st));
-  const uint32_t word_ct = st.sample_ct_padded / 32;
-  DevBuf d_planes, d_flags;
-  if (d_planes.alloc(3ull * word_ct * rows_cap * 4) || d_flags.alloc(static_cast<uint64_t>(kLdChunkVariants) * band)) {
-    StageFree(&st);
-    return 1;
+  // two staged chunks: the copy of chunk k+1 (prep stream) overlaps the pair kernel of chunk k; flags come back
+  // through two pinned-size device buffers in the same rhythm
+  GenoStage st[2];
+  DevBuf d_planes, d_flags[2];
+  CUtensorMap tmap_a[2], tmap_b[2];
+  cudaEvent_t ev_copied[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+  int rc = 0;
+  for (int b = 0; b < 2 && !rc; ++b) {
+    rc = StageAlloc(founder_ct, rows_cap, &st[b], use_popc ? kSamplePad : 64) || d_flags[b].alloc(static_cast<uint64_t>(kLdChunkVariants) * band);
+    if (!rc && !use_popc) rc = MakeRawTensorMap(&tmap_a[b], st[b].d_raw, st[b].pitch, st[b].variant_cap, kLdtBoxBytes, kLdtRows) || MakeRawTensorMap(&tmap_b[b], st[b].d_raw, st[b].pitch, st[b].variant_cap, kLdtBoxBytes, kLdtCols);
+    if (!rc && (cudaEventCreateWithFlags(&ev_copied[b], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ev_done[b], cudaEventDisableTiming) != cudaSuccess)) {
+      set_error("pl2gpu_ld_band_flags: cudaEventCreate failed");
+      rc = 1;
+    }
+  }
+  const uint32_t word_ct = st[0].sample_ct_padded / 32;
+  if (!rc && use_popc) rc = d_planes.alloc(3ull * word_ct * rows_cap * 4);
+  if (!rc && !use_popc && cudaFuncSetAttribute(ld_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLdtSmemBytes) != cudaSuccess) {
+    set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
+    rc = 1;
   }
   const uint8_t* src = static_cast<const uint8_t*>(genovecs);
-  int rc = 0;
-  for (uint32_t a0 = 0; a0 < variant_ct && !rc; a0 += kLdChunkVariants) {
+  struct Pending {
+    uint32_t a0 = 0, a1 = 0;
+    bool live = false;
+  } pend[2];
+  auto drain = [&](int b) -> int {  // flags of the chunk that used buffer b -> host
+    if (!pend[b].live) return 0;
+    pend[b].live = false;
+    if (cudaMemcpyAsync(flags_host + static_cast<uint64_t>(pend[b].a0) * band, d_flags[b].p, static_cast<uint64_t>(pend[b].a1 - pend[b].a0) * band, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
+        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
+      return 1;
+    }
+    return 0;
+  };
+  uint32_t chunk_idx = 0;
+  for (uint32_t a0 = 0; a0 < variant_ct && !rc; a0 += kLdChunkVariants, ++chunk_idx) {
+    const int b = chunk_idx & 1;
     const uint32_t a1 = std::min(variant_ct, a0 + kLdChunkVariants);
     const uint32_t lo = (a0 > band_r) ? (a0 - band_r) : 0;
-    uint32_t padded;
-    rc = StageUpload(c, &st, src + static_cast<uint64_t>(lo) * variant_stride_bytes, variant_stride_bytes, a1 - lo, src_is_device, &padded, 0, 64);
+    rc = drain(b);  // buffer b is free again (its kernel has finished, its flags are on the host)
     if (rc) break;
-    const uint32_t vin = padded;  // multiple of 64
-    ld_split_kernel<<<dim3(vin / 32, DivUpU32(word_ct, 32)), 1024, 0, c->stream>>>(st.d_raw, st.pitch, word_ct, vin, static_cast<uint32_t*>(d_planes.p));
-    c->launches++;
-    ld_band_kernel<<<dim3(DivUpU32(a1 - a0, 64), band_r / 64 + 1), 256, 0, c->stream>>>(static_cast<const uint32_t*>(d_planes.p), word_ct, vin, lo, a0, a1, band, prune_ld_thresh, static_cast<uint8_t*>(d_flags.p));
-    c->launches++;
-    if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(flags_host + static_cast<uint64_t>(a0) * band, d_flags.p, static_cast<uint64_t>(a1 - a0) * band, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess ||
-        cudaStreamSynchronize(c->stream) != cudaSuccess) {
+    const uint32_t rows = a1 - lo, padded = RoundUpU32(rows, 64);
+    if (cudaMemcpy2DAsync(st[b].d_raw, st[b].pitch, src + static_cast<uint64_t>(lo) * variant_stride_bytes, variant_stride_bytes, DivUpU32(founder_ct, 4), rows, src_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) {
+      set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+      break;
+    }
+    rc = LaunchPadGenotypes(c, st[b].d_raw, st[b].pitch, st[b].sample_ct, rows, padded, c->copy_stream);
+    if (rc) break;
+    cudaEventRecord(ev_copied[b], c->copy_stream);
+    cudaStreamWaitEvent(c->stream, ev_copied[b], 0);
+    if (use_popc) {
+      ld_split_kernel<<<dim3(padded / 32, DivUpU32(word_ct, 32)), 1024, 0, c->stream>>>(st[b].d_raw, st[b].pitch, word_ct, padded, static_cast<uint32_t*>(d_planes.p));
+      c->launches++;
+      ld_band_kernel<<<dim3(DivUpU32(a1 - a0, 64), band_r / 64 + 1), 256, 0, c->stream>>>(static_cast<const uint32_t*>(d_planes.p), word_ct, padded, lo, a0, a1, band, prune_ld_thresh, static_cast<uint8_t*>(d_flags[b].p));
+      c->launches++;
+    } else {
+      ld_ts_kernel<<<dim3(DivUpU32(a1 - a0, kLdtRows), band_r / kLdtCols + 2), kLdtThreads, kLdtSmemBytes, c->stream>>>(tmap_a[b], tmap_b[b], st[b].sample_ct_padded, lo, a0, a1, band, prune_ld_thresh, static_cast<uint8_t*>(d_flags[b].p));
+      c->launches++;
+    }
+    if (cudaGetLastError() != cudaSuccess) {
+      set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = 1;
+      break;
+    }
+    pend[b].a0 = a0;
+    pend[b].a1 = a1;
+    pend[b].live = true;
+    // a host source may be reused by the caller only after the copy; chunks overlap by band_r rows, so wait here
+    if (!src_is_device && cudaEventSynchronize(ev_copied[b]) != cudaSuccess) {
       set_error("pl2gpu_ld_band_flags: %s", cudaGetErrorString(cudaGetLastError()));
       rc = 1;
     }
   }
-  StageFree(&st);
+  for (int b = 0; b < 2; ++b) {
+    const int other = (chunk_idx + b) & 1;  // oldest pending first
+    if (!rc) rc = drain(other);
+  }
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  for (int b = 0; b < 2; ++b) {
+    StageFree(&st[b]);
+    if (ev_copied[b]) cudaEventDestroy(ev_copied[b]);
+    if (ev_done[b]) cudaEventDestroy(ev_done[b]);
+  }
   return rc;
 }
 

@@ -30,6 +30,12 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, uint32_t lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
 }
+// Warp-level release of a shared-memory ring slot the lanes have READ: `dep` is any value computed from the
+// loaded words - making it an operand of the arrive pins the arrive behind the loads' completion.
+__device__ __forceinline__ void mbar_release_warp(uint64_t* bar, uint32_t lane, uint32_t dep) {
+  __syncwarp();
+  if (lane == 0) asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t// after %1\n\t}" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
+}
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -138,6 +144,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&v)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 

@@ -14,5 +14,6 @@ if grep -q "king ts == popcount: True" gpurun_out/min_king.log; then
   echo "== smoke"; timeout 300 python __graft_entry__.py smoke 2>&1 | tail -5 | tee gpurun_out/smoke.log
   echo "== int8 peak"; timeout 120 python tools/int8_peak.py 2>&1 | tail -2 | tee gpurun_out/int8_peak.json
   echo "== quick bench"; SKIP_POPC=1 SKIP_SS=1 timeout 300 python tools/quick_king_bench.py 16384 65536 2>&1 | tail -4 | tee gpurun_out/quick_bench.log
+  echo "== ld bench"; timeout 300 python tools/ld_bench.py 2>&1 | tail -6 | tee gpurun_out/ld_bench.log
   echo "== pytest"; ( time timeout 1800 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -25 ) 2>&1 | tee gpurun_out/pytest_gpu.log
 fi
