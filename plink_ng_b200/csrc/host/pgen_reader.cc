@@ -6,7 +6,9 @@
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <cstring>
+#include <thread>
 
 namespace pl2host {
 
@@ -167,13 +169,13 @@ bool PgenReader::Open(const std::string& path, uint32_t raw_sample_ct, uint32_t 
     return false;
   }
   const uint32_t words = WordsFor(raw_sample_ct_);
-  ldbase_.assign(words, 0);
-  scratch_.assign(words, 0);
-  ldbase_vidx_ = 0xFFFFFFFFu;
+  state_.ldbase.assign(words, 0);
+  state_.scratch.assign(words, 0);
+  state_.ldbase_vidx = 0xFFFFFFFFu;
   return true;
 }
 
-bool PgenReader::ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err) {
+bool PgenReader::ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err) const {
   if (vidx >= raw_variant_ct_) {
     *err = "variant index out of range";
     return false;
@@ -194,7 +196,7 @@ bool PgenReader::ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* l
 
 // Difflist (pgen_spec.tex:354-400).  with_values: patch (sample, 2-bit value) pairs; otherwise
 // set every listed sample to fixed_value.
-bool PgenReader::ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after) {
+bool PgenReader::ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after) const {
   uint32_t len;
   if (!GetVarint(&p, end, &len)) goto malformed;
   if (!len) {
@@ -233,7 +235,7 @@ malformed:
   return false;
 }
 
-bool PgenReader::DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err) {
+bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err) const {
   const uint8_t* rec;
   uint32_t len;
   if (!ReadRecordBytes(vidx, &rec, &len, err)) return false;
@@ -303,11 +305,11 @@ bool PgenReader::DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err) {
         }
         --b;
       } while ((vrtypes_[b] & 6) == 2);
-      if (ldbase_vidx_ != b) {
-        if (!DecodeRecord(b, ldbase_.data(), err)) return false;
-        ldbase_vidx_ = b;
+      if (st->ldbase_vidx != b) {
+        if (!DecodeRecord(st, b, st->ldbase.data(), err)) return false;
+        st->ldbase_vidx = b;
       }
-      memcpy(dst, ldbase_.data(), words * 8ull);
+      memcpy(dst, st->ldbase.data(), words * 8ull);
       if (!ParseDifflistAndApply(rec, end, true, dst, 0, err, &after)) return false;
       if (t == 3) {
         for (uint32_t w = 0; w < words; ++w) dst[w] ^= ((~dst[w]) & 0x5555555555555555ull) << 1;  // swap 0 <-> 2
@@ -331,18 +333,61 @@ bool PgenReader::DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err) {
       return false;
   }
   ZeroTrailing(dst, n);
-  if (t != 2 && t != 3 && dst != ldbase_.data()) {
-    memcpy(ldbase_.data(), dst, words * 8ull);
-    ldbase_vidx_ = vidx;
+  if (t != 2 && t != 3 && dst != st->ldbase.data()) {
+    memcpy(st->ldbase.data(), dst, words * 8ull);
+    st->ldbase_vidx = vidx;
   }
   return true;
 }
 
-bool PgenReader::Get(uint32_t vidx, uint64_t* genovec, std::string* err) { return DecodeRecord(vidx, genovec, err); }
+bool PgenReader::Get(uint32_t vidx, uint64_t* genovec, std::string* err) { return DecodeRecord(&state_, vidx, genovec, err); }
 
 bool PgenReader::GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) {
-  if (sample_ct == raw_sample_ct_) return DecodeRecord(vidx, genovec, err);
-  if (!DecodeRecord(vidx, scratch_.data(), err)) return false;
+  return GetSubsetWith(&state_, vidx, sample_include, sample_ct, genovec, err);
+}
+
+bool PgenReader::GetBlock(const uint32_t* vidx, uint32_t count, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* dst, uint64_t stride_words, uint32_t thread_ct, std::string* err) {
+  if (!count) return true;
+  thread_ct = std::max(1u, std::min(thread_ct, (count + 255) / 256));  // at least 256 variants per worker
+  if (thread_ct == 1) {
+    for (uint32_t k = 0; k < count; ++k) {
+      uint64_t* row = dst + static_cast<uint64_t>(k) * stride_words;
+      if (!(sample_include ? GetSubsetWith(&state_, vidx[k], sample_include, sample_ct, row, err) : DecodeRecord(&state_, vidx[k], row, err))) return false;
+    }
+    return true;
+  }
+  std::vector<std::string> errs(thread_ct);
+  std::vector<uint8_t> failed(thread_ct, 0);
+  std::vector<std::thread> workers;
+  const uint32_t words = WordsFor(raw_sample_ct_);
+  for (uint32_t t = 0; t < thread_ct; ++t) {
+    const uint32_t k0 = static_cast<uint32_t>(static_cast<uint64_t>(count) * t / thread_ct), k1 = static_cast<uint32_t>(static_cast<uint64_t>(count) * (t + 1) / thread_ct);
+    workers.emplace_back([=, &errs, &failed]() {
+      DecodeState st;
+      st.ldbase.assign(words, 0);
+      st.scratch.assign(words, 0);
+      for (uint32_t k = k0; k < k1; ++k) {
+        uint64_t* row = dst + static_cast<uint64_t>(k) * stride_words;
+        if (!(sample_include ? GetSubsetWith(&st, vidx[k], sample_include, sample_ct, row, &errs[t]) : DecodeRecord(&st, vidx[k], row, &errs[t]))) {
+          failed[t] = 1;
+          return;
+        }
+      }
+    });
+  }
+  for (auto& w : workers) w.join();
+  for (uint32_t t = 0; t < thread_ct; ++t) {
+    if (failed[t]) {
+      *err = errs[t];
+      return false;
+    }
+  }
+  return true;
+}
+
+bool PgenReader::GetSubsetWith(DecodeState* st, uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) const {
+  if (sample_ct == raw_sample_ct_) return DecodeRecord(st, vidx, genovec, err);
+  if (!DecodeRecord(st, vidx, st->scratch.data(), err)) return false;
   // CopyNyparrNonemptySubset: gather the 2-bit entries of included samples
   const uint32_t out_words = WordsFor(sample_ct);
   for (uint32_t w = 0; w < out_words; ++w) genovec[w] = 0;
@@ -353,7 +398,7 @@ bool PgenReader::GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32
     const uint32_t inc = static_cast<uint32_t>(sample_include[w >> 1] >> (32 * (w & 1)));
     if (!inc) continue;
     const uint64_t mask2 = _pdep_u64(inc, 0x5555555555555555ull) * 3;
-    const uint64_t packed = _pext_u64(scratch_[w], mask2);
+    const uint64_t packed = _pext_u64(st->scratch[w], mask2);
     const uint32_t cnt = static_cast<uint32_t>(__builtin_popcount(inc));
     const uint32_t sh = 2 * (out_pos & 31);
     genovec[out_pos >> 5] |= packed << sh;

@@ -36,11 +36,22 @@ class PgenReader {
   // PgrGet with a sample subset (sample_include bitset over raw samples, sample_ct set bits):
   // subsetted genovec[WordsFor(sample_ct)] (CopyNyparrNonemptySubset semantics).
   bool GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err);
+  // Multi-threaded block read (the role of PgenMtLoadInit + the per-thread PgenReaders of the reference's block
+  // readers, 2.0/plink2_common.cc:3926): variants vidx[0..count) -> dst[k * stride_words], decoded by
+  // `thread_ct` workers over contiguous sub-ranges (each with its own LD-base cache).  sample_include = nullptr:
+  // all raw samples.  Returns false (first error) if any record fails.
+  bool GetBlock(const uint32_t* vidx, uint32_t count, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* dst, uint64_t stride_words, uint32_t thread_ct, std::string* err);
 
  private:
-  bool DecodeRecord(uint32_t vidx, uint64_t* dst, std::string* err);
-  bool ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err);
-  bool ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after);
+  // per-decoder mutable state: the last non-LD-compressed genovec (LD base) and a subsetting scratch row
+  struct DecodeState {
+    std::vector<uint64_t> ldbase, scratch;
+    uint32_t ldbase_vidx = 0xFFFFFFFFu;
+  };
+  bool DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err) const;
+  bool GetSubsetWith(DecodeState* st, uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) const;
+  bool ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err) const;
+  bool ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after) const;
 
   int fd_ = -1;
   const uint8_t* map_ = nullptr;
@@ -53,9 +64,7 @@ class PgenReader {
   uint32_t fixed_bpv_ = 0;
   std::vector<uint8_t> vrtypes_;  // mode 0x10
   std::vector<uint64_t> rec_off_; // mode 0x10: [raw_variant_ct + 1]
-  std::vector<uint64_t> ldbase_;  // last non-LD-compressed genovec
-  uint32_t ldbase_vidx_ = 0xFFFFFFFFu;
-  std::vector<uint64_t> scratch_;
+  DecodeState state_;             // used by Get / GetSubset (single-threaded callers)
 };
 
 }  // namespace pl2host

@@ -8,6 +8,7 @@
 // CalcKing / CalcGrm / LdPruneWrite.  File decoding, text formatting and the sequential graph /
 // window logic run here on the host; every pairwise accumulation runs on the GPU - there is no
 // CPU fallback and the program exits with kPglRetGpuFail-style status when the device is missing.
+#include <sched.h>
 #include <unistd.h>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <cstring>
 #include <ctime>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/plink2_b200.h"
@@ -421,6 +423,25 @@ bool WriteIdFile(const std::string& path, const SampleInfo& s, const std::vector
 }
 
 // ---- genotype block streaming: decode `idx` variants into a pinned host buffer ----
+// host threads for genotype decoding: --threads if given, else min(affinity mask, cgroup CPU quota), at most 64
+uint32_t g_decode_threads = 1;
+uint32_t EffectiveHostThreads(uint32_t requested) {
+  if (requested) return std::min<uint32_t>(requested, 256);
+  uint32_t n = std::max(1u, std::thread::hardware_concurrency());
+  cpu_set_t set;
+  if (!sched_getaffinity(0, sizeof(set), &set)) n = std::max(1, CPU_COUNT(&set));
+  if (FILE* f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+    char q[64];
+    unsigned long long period = 0;
+    if (fscanf(f, "%63s %llu", q, &period) == 2 && strcmp(q, "max") && period) {
+      const unsigned long long quota = strtoull(q, nullptr, 10);
+      if (quota) n = std::min<uint32_t>(n, static_cast<uint32_t>((quota + period - 1) / period));
+    }
+    fclose(f);
+  }
+  return std::max(1u, std::min(n, 64u));
+}
+
 struct BlockStreamer {
   Dataset* ds;
   const std::vector<uint32_t>* vidx;
@@ -438,16 +459,13 @@ struct BlockStreamer {
     buf = static_cast<uint64_t*>(p);
     return true;
   }
-  // returns number of variants decoded (0 at end), -1 on error
+  // returns number of variants decoded (0 at end), -1 on error.  Decoding is spread over the host threads this
+  // process may use (--threads, else affinity mask / cgroup quota), like the reference's multithreaded block reads.
   int Next(std::string* err) {
-    uint32_t n = 0;
-    while (n < cap && pos < vidx->size()) {
-      uint64_t* dst = buf + static_cast<uint64_t>(n) * words;
-      const bool ok = sample_include ? ds->reader.GetSubset((*vidx)[pos], sample_include, sample_ct, dst, err) : ds->reader.Get((*vidx)[pos], dst, err);
-      if (!ok) return -1;
-      ++n;
-      ++pos;
-    }
+    const uint32_t n = static_cast<uint32_t>(std::min<size_t>(cap, vidx->size() - pos));
+    if (!n) return 0;
+    if (!ds->reader.GetBlock(vidx->data() + pos, n, sample_include, sample_ct, buf, words, g_decode_threads, err)) return -1;
+    pos += n;
     return static_cast<int>(n);
   }
   void Rewind() { pos = 0; }
@@ -1830,6 +1848,7 @@ int main(int argc, char** argv) {
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
   logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
   g_clock.Mark("load .psam/.pvar, open .pgen");
+  g_decode_threads = EffectiveHostThreads(c.threads);
   Pl2GpuCtx* ctx = nullptr;
   if (pl2gpu_ctx_create(c.device, &ctx)) {
     logprintf("Error: GPU initialisation failed: %s\n", pl2gpu_last_error());

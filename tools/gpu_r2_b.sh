@@ -15,5 +15,13 @@ if grep -q "king ts == popcount: True" gpurun_out/min_king.log; then
   echo "== int8 peak"; timeout 120 python tools/int8_peak.py 2>&1 | tail -2 | tee gpurun_out/int8_peak.json
   echo "== quick bench"; SKIP_POPC=1 SKIP_SS=1 timeout 300 python tools/quick_king_bench.py 16384 65536 2>&1 | tail -4 | tee gpurun_out/quick_bench.log
   echo "== ld bench"; timeout 300 python tools/ld_bench.py 2>&1 | tail -6 | tee gpurun_out/ld_bench.log
-  echo "== pytest"; ( time timeout 1800 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -25 ) 2>&1 | tee gpurun_out/pytest_gpu.log
+  echo "== debug cli"; timeout 300 python tools/debug_king_cli.py 3000 4096 --gpu-memory 640 2>&1 | tail -20 | tee gpurun_out/debug_cli.log
+  timeout 300 python tools/debug_king_cli.py 3000 4096 2>&1 | tail -12 | tee -a gpurun_out/debug_cli.log
+  echo "== pytest"; ( time timeout 1800 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_full.log 2>&1; tail -25 gpurun_out/pytest_full.log ) 2>&1 | tee gpurun_out/pytest_gpu.log
+  grep -n "differs from" -A6 gpurun_out/pytest_full.log | head -40
+fi
+if grep -q "king ts == popcount: True" gpurun_out/min_king.log; then
+  echo "== bench default"; ( time timeout 900 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err ) 2>&1 | tail -3; tail -c 3000 gpurun_out/bench_default.json; tail -5 gpurun_out/bench_default.err
+  echo "== ncu full: king_ts_kernel"
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:king_ts_kernel -s 1 -c 1 -f -o gpurun_out/prof_king_ts env SKIP_POPC=1 SKIP_SS=1 SKIP_GRM=1 python tools/quick_king_bench.py 16384 65536 1 > gpurun_out/ncu_full_king.log 2>&1; tail -3 gpurun_out/ncu_full_king.log
 fi
