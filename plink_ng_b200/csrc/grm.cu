@@ -52,7 +52,7 @@ int pl2gpu_grm_end(Pl2GrmJob* job);
 
 int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int flags, Pl2GrmJob** job_ptr) {
   *job_ptr = nullptr;
-  if (!ctx || !sample_ct || row_end > sample_ct || row_start >= row_end) {
+  if (!ctx || !sample_ct || row_end > sample_ct || row_start > row_end) {  // empty range: a rank that only takes part in the all-gathers
     set_error("pl2gpu_grm_begin: bad row range [%u,%u) for %u samples", row_start, row_end, sample_ct);
     return 1;
   }

@@ -134,8 +134,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
       Words r;
       r.w[0] = lds64(ring_i + si * kGtsRawIBytes + grp * (kTileRows * 8));
       r.w[1] = lds64(ring_i + si * kGtsRawIBytes + (grp + 2) * (kTileRows * 8));
-      mbar_release_warp(&bar_empty_ri[si], lane, r.w[0].x ^ r.w[0].y ^ r.w[1].x ^ r.w[1].y);
-      return r;
+      return r;  // released after both words went through tcgen05.st (king_ts_kernel.cuh explains why)
     };
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4 (variant pad 256)
     Words words = load_slot(0);
@@ -153,9 +152,12 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
         mbar_arrive_warp(&bar_full_a[grp], lane);
         if (h == 0) {
           cur = expand_i(words.w[1]);
-        } else if (q + 1 < slot_iters) {
-          words = load_slot(q + 1);
-          cur = expand_i(words.w[0]);
+        } else {
+          mbar_arrive_warp(&bar_empty_ri[q % kGtsRawISlots], lane);
+          if (q + 1 < slot_iters) {
+            words = load_slot(q + 1);
+            cur = expand_i(words.w[0]);
+          }
         }
       }
     }
@@ -195,7 +197,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
 #pragma unroll
       for (uint32_t p = 0; p < kGrmPlanesJ; ++p) sts16(a0 + p * kPlane, expand16(cur.t[p], sel));
       // every lane has consumed its ring words (they fed the PRMTs above): release the raw / table slot
-      mbar_release_warp(&bar_empty_rj[it % kGtsRawJSlots], lane, cur.w ^ cur.t[0]);
+      mbar_arrive_warp(&bar_empty_rj[it % kGtsRawJSlots], lane);
       fence_proxy_async_smem();
       mbar_arrive_warp(&bar_full_b[sb], lane);
       if (it + 1 < stage_iters) cur = fetch(it + 1);

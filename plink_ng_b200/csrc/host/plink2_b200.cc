@@ -71,6 +71,7 @@ struct Cmd {
   uint64_t seed = 0;
   bool seed_given = false;
   int device = 0;
+  uint32_t gpus = 1;            // --gpus: row-block split of the N x N jobs over this many devices (NCCL all-gather of each column tile)
   uint64_t gpu_memory_mib = 0;  // --gpu-memory / PL2_GPU_MEM_MIB: cap on the device memory a job may plan with (0 = what is free)
   // KING
   bool make_king = false, make_king_table = false;
@@ -189,6 +190,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (!need(1, 1) || !ParseU32(prm[0], &s)) return Usage("Invalid --seed argument.");
       c->seed = s;
       c->seed_given = true;
+    } else if (flag == "--gpus") {
+      if (!need(1, 1) || !ParseU32(prm[0], &c->gpus) || !c->gpus || c->gpus > 64) return Usage("Invalid --gpus argument.");
     } else if (flag == "--gpu-memory") {
       // device-side analogue of --memory: the N x N accumulators are planned against this many MiB, which
       // forces the reference's multipass behaviour (CountTrianglePasses, plink2_matrix_calc.cc:216-255)
@@ -451,11 +454,12 @@ struct BlockStreamer {
   uint64_t* buf = nullptr;
   uint32_t cap;
   size_t pos = 0;
-  BlockStreamer(Dataset* d, const std::vector<uint32_t>* v, uint32_t n_samples, uint32_t batch) : ds(d), vidx(v), sample_ct(n_samples), words(PgenReader::WordsFor(n_samples)), cap(batch) {}
+  uint32_t spare = 0;  // extra rows behind the block (filler for sharded uploads)
+  BlockStreamer(Dataset* d, const std::vector<uint32_t>* v, uint32_t n_samples, uint32_t batch, uint32_t spare_rows = 0) : ds(d), vidx(v), sample_ct(n_samples), words(PgenReader::WordsFor(n_samples)), cap(batch), spare(spare_rows) {}
   ~BlockStreamer() { pl2gpu_host_free(buf); }
   bool Init() {
     void* p = nullptr;
-    if (pl2gpu_host_alloc(static_cast<uint64_t>(cap) * words * 8, &p)) return false;
+    if (pl2gpu_host_alloc(static_cast<uint64_t>(cap + spare) * words * 8, &p)) return false;
     buf = static_cast<uint64_t*>(p);
     return true;
   }
@@ -474,6 +478,91 @@ struct BlockStreamer {
 int GpuFail(const char* what) {
   logprintf("Error: %s: %s\n", what, pl2gpu_last_error());
   return kRetGpuFail;
+}
+
+// ------------------------------------------------------------------------------------------ multi-GPU team
+// One context per device, one NCCL rank per context, all driven from this process (one host thread per rank for
+// the collective calls).  ctx[0] is the caller's context.
+struct GpuTeam {
+  std::vector<Pl2GpuCtx*> ctx;
+  ~GpuTeam() {
+    if (ctx.size() > 1) pl2gpu_comm_destroy(ctx[0]);
+    for (size_t g = 1; g < ctx.size(); ++g) pl2gpu_ctx_destroy(ctx[g]);
+  }
+  uint32_t size() const { return static_cast<uint32_t>(ctx.size()); }
+};
+
+// f(rank) on `g` host threads (rank 0 on the calling thread); returns the first nonzero return code and its
+// pl2gpu_last_error() text (thread-local in the library, so it is captured inside the worker).
+template <class F>
+int ForEachRank(uint32_t g, F&& f, std::string* errtext) {
+  std::vector<int> rc(g, 0);
+  std::vector<std::string> msg(g);
+  auto run = [&](uint32_t r) {
+    rc[r] = f(r);
+    if (rc[r]) msg[r] = pl2gpu_last_error();
+  };
+  std::vector<std::thread> th;
+  for (uint32_t r = 1; r < g; ++r) th.emplace_back(run, r);
+  run(0);
+  for (auto& t : th) t.join();
+  for (uint32_t r = 0; r < g; ++r) {
+    if (rc[r]) {
+      if (errtext) *errtext = msg[r];
+      return rc[r];
+    }
+  }
+  return 0;
+}
+
+// Contexts on devices first_device .. first_device + gpus - 1 joined in one communicator.  Returns 0, or a
+// kRet* code after logging.
+int TeamInit(Pl2GpuCtx* first, int first_device, uint32_t gpus, GpuTeam* team) {
+  team->ctx.assign(1, first);
+  if (gpus <= 1) return 0;
+  if (pl2gpu_device_count() < first_device + static_cast<int>(gpus)) {
+    logprintf("Error: --gpus %u needs devices %d..%d, but only %d CUDA device(s) are visible.\n", gpus, first_device, first_device + static_cast<int>(gpus) - 1, pl2gpu_device_count());
+    return kRetGpuFail;
+  }
+  for (uint32_t g = 1; g < gpus; ++g) {
+    Pl2GpuCtx* cx = nullptr;
+    if (pl2gpu_ctx_create(first_device + static_cast<int>(g), &cx)) return GpuFail("pl2gpu_ctx_create");
+    team->ctx.push_back(cx);
+  }
+  uint8_t id[PL2GPU_COMM_ID_BYTES];
+  if (pl2gpu_comm_unique_id(id)) return GpuFail("pl2gpu_comm_unique_id");
+  std::string err;
+  if (ForEachRank(gpus, [&](uint32_t r) { return pl2gpu_comm_init(team->ctx[r], static_cast<int>(r), static_cast<int>(gpus), id); }, &err)) {
+    logprintf("Error: pl2gpu_comm_init: %s\n", err.c_str());
+    return kRetGpuFail;
+  }
+  return 0;
+}
+
+// Rows [r0, r1) of the lower triangle cut into `parts` contiguous blocks whose interior boundaries are multiples
+// of the 128-row pair tile and which hold (nearly) the same number of 128 x 80 pair tiles - the unit the tensor
+// kernels' time is proportional to.  Blocks may be empty when the range holds fewer row tiles than parts.
+std::vector<uint32_t> TileAlignedBounds(uint32_t r0, uint32_t r1, uint32_t parts, bool include_diag) {
+  std::vector<uint32_t> b(parts + 1, r1);
+  b[0] = r0;
+  if (parts <= 1 || r1 <= r0) return b;
+  const uint32_t rt0 = r0 / 128, rt1 = (r1 + 127) / 128;
+  std::vector<uint64_t> cum(1, 0);
+  for (uint32_t rt = rt0; rt < rt1; ++rt) {
+    const uint32_t row_end = std::min(r1, (rt + 1) * 128);
+    const uint32_t cols = include_diag ? row_end : row_end - 1;
+    cum.push_back(cum.back() + (cols + 79) / 80);
+  }
+  for (uint32_t k = 1; k < parts; ++k) {
+    const double target = static_cast<double>(cum.back()) * k / parts;
+    uint32_t best = 0;
+    for (uint32_t t = 1; t < cum.size(); ++t) {
+      if (fabs(static_cast<double>(cum[t]) - target) < fabs(static_cast<double>(cum[best]) - target)) best = t;
+    }
+    uint32_t row = std::min(r1, std::max(r0, (rt0 + best) * 128));
+    b[k] = std::max(row, b[k - 1]);
+  }
+  return b;
 }
 
 // ------------------------------------------------------------------------------------------ KING
@@ -870,32 +959,56 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   std::vector<double> full_kin;  // lower triangle, only for `square` output
   if (square_text_full) full_kin.resize(static_cast<uint64_t>(n) * (n - 1) / 2);
 
+  // multi-GPU team (--gpus): every pass's row block is cut into one tile-aligned slab per device
+  GpuTeam team;
+  {
+    // not worth splitting tiny triangles: keep at least four 128-row tiles per device
+    const uint32_t gpus_eff = std::max(1u, std::min(c.gpus, (grand_r1 - grand_r0) / 512));
+    if (gpus_eff < c.gpus) logprintf("Note: --gpus %u reduced to %u for %u rows.\n", c.gpus, gpus_eff, grand_r1 - grand_r0);
+    const int trc = TeamInit(ctx, c.device, gpus_eff, &team);
+    if (trc) return trc;
+  }
+  const uint32_t G = team.size();
   // pass planning (CountTrianglePasses / NextTrianglePass, :216-255): largest row block whose
-  // device accumulators fit
-  uint64_t free_b = 0, total_b = 0;
-  if (pl2gpu_ctx_mem_info(ctx, &free_b, &total_b)) return GpuFail("pl2gpu_ctx_mem_info");
+  // device accumulators fit (on every device of the team)
+  uint64_t free_b = ~0ull;
+  for (uint32_t g = 0; g < G; ++g) {
+    uint64_t f = 0, t = 0;
+    if (pl2gpu_ctx_mem_info(team.ctx[g], &f, &t)) return GpuFail("pl2gpu_ctx_mem_info");
+    free_b = std::min(free_b, f);
+  }
   uint64_t budget = free_b - free_b / 10;
   if (c.gpu_memory_mib && (c.gpu_memory_mib << 20) < budget) budget = c.gpu_memory_mib << 20;
   // variants per staged block: the full 65,536 unless the cap is so small that the two staged blocks would
   // eat most of it (then halve until they fit in a quarter of the budget)
   uint32_t batch = 65536;
   while (batch > 2048 && 4ull * batch * ((n + 639) / 640 * 160) > budget / 4) batch /= 2;
+  auto pass_fits = [&](uint32_t a, uint32_t b) {
+    const std::vector<uint32_t> sb = TileAlignedBounds(a, b, G, false);
+    for (uint32_t g = 0; g < G; ++g) {
+      if (sb[g + 1] > sb[g] && pl2gpu_king_mem_required(n, sb[g], sb[g + 1], batch) > budget) return false;
+    }
+    return true;
+  };
+  auto next_pass_end = [&](uint32_t r) {  // largest e in (r, grand_r1] that fits
+    uint32_t lo = r + 1, hi = grand_r1;
+    while (lo < hi) {
+      const uint32_t mid = lo + (hi - lo + 1) / 2;
+      if (pass_fits(r, mid)) lo = mid;
+      else hi = mid - 1;
+    }
+    return lo;
+  };
   uint32_t pass_ct = 0;
   for (uint32_t r = grand_r0; r < grand_r1; ++pass_ct) {
-    uint32_t lo = r + 1, hi = grand_r1;  // largest e in (r, grand_r1] that fits
     if (pl2gpu_king_mem_required(n, r, r + 1, batch) > budget) {
       logprintf("Error: Insufficient GPU memory for %s on %u samples.\n", flagname, n);
       return kRetNomem;
     }
-    while (lo < hi) {
-      const uint32_t mid = lo + (hi - lo + 1) / 2;
-      if (pl2gpu_king_mem_required(n, r, mid, batch) <= budget) lo = mid;
-      else hi = mid - 1;
-    }
-    r = lo;
+    r = next_pass_end(r);
   }
   if (pass_ct > 1) logprintf("%s: %u passes over the variants (device accumulators planned against %llu MiB).\n", flagname, pass_ct, static_cast<unsigned long long>(budget >> 20));
-  BlockStreamer bs(ds, &vidx, n, batch);
+  BlockStreamer bs(ds, &vidx, n, batch, G);  // G spare rows: a sharded batch is topped up to a multiple of G
   if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
   if (want_matrix && c.king_shape == Cmd::kSq0 && !c.parallel_idx) {
     // square0 output starts with sample 0's row: the diagonal 0.5 followed by zeros (:2129-2132)
@@ -915,20 +1028,31 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     }
   }
   uint64_t filter_ct = 0;
-  uint32_t row_end = grand_r0;
-  for (uint32_t pass = 1; pass <= pass_ct; ++pass) {
-    const uint32_t row_start = row_end;
-    {
-      uint32_t lo = row_start + 1, hi = grand_r1;
-      while (lo < hi) {
-        const uint32_t mid = lo + (hi - lo + 1) / 2;
-        if (pl2gpu_king_mem_required(n, row_start, mid, batch) <= budget) lo = mid;
-        else hi = mid - 1;
-      }
-      row_end = lo;
-    }
+  struct Slab {
     Pl2KingJob* job = nullptr;
-    if (pl2gpu_king_begin_ex(ctx, n, row_start, row_end, kPl2KingAlgoAuto, batch, &job)) return GpuFail("pl2gpu_king_begin_ex");
+    uint32_t r0 = 0, r1 = 0;
+  };
+  uint32_t pass_r1 = grand_r0;
+  for (uint32_t pass = 1; pass <= pass_ct; ++pass) {
+    const uint32_t pass_r0 = pass_r1;
+    pass_r1 = next_pass_end(pass_r0);
+    const std::vector<uint32_t> sbounds = TileAlignedBounds(pass_r0, pass_r1, G, false);
+    std::vector<Slab> slabs(G);
+    auto end_jobs = [&]() {
+      for (Slab& sl : slabs) {
+        pl2gpu_king_end(sl.job);
+        sl.job = nullptr;
+      }
+    };
+    for (uint32_t g = 0; g < G; ++g) {
+      slabs[g].r0 = sbounds[g];
+      slabs[g].r1 = sbounds[g + 1];
+      // an empty slab still takes part in the all-gathers (rank g of the communicator)
+      if (pl2gpu_king_begin_ex(team.ctx[g], n, slabs[g].r0, slabs[g].r1, kPl2KingAlgoAuto, batch, &slabs[g].job)) {
+        end_jobs();
+        return GpuFail("pl2gpu_king_begin_ex");
+      }
+    }
     g_clock.Mark("king: begin (device alloc)");
     bs.Rewind();
     std::string err;
@@ -940,14 +1064,27 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       t_decode += g_clock.Since(td);
       if (got < 0) {
         logprintf("\nError: %s\n", err.c_str());
-        pl2gpu_king_end(job);
+        end_jobs();
         return kRetMalformedInput;
       }
       if (!got) break;
       const auto ta = std::chrono::steady_clock::now();
-      if (pl2gpu_king_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
-        pl2gpu_king_end(job);
-        return GpuFail("pl2gpu_king_add_variants");
+      if (G == 1) {
+        if (pl2gpu_king_add_variants(slabs[0].job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
+          end_jobs();
+          return GpuFail("pl2gpu_king_add_variants");
+        }
+      } else {
+        // device g uploads rows [g * per, (g + 1) * per) of the decoded block; NCCL all-gathers the column tile.
+        // Filler rows that top the block up to per * G are all-missing and count nothing.
+        const uint32_t per = (static_cast<uint32_t>(got) + G - 1) / G;
+        memset(bs.buf + static_cast<uint64_t>(got) * bs.words, 0xFF, static_cast<uint64_t>(per * G - static_cast<uint32_t>(got)) * bs.words * 8);
+        std::string gerr;
+        if (ForEachRank(G, [&](uint32_t g) { return pl2gpu_king_add_variants_sharded(slabs[g].job, bs.buf + static_cast<uint64_t>(g) * per * bs.words, static_cast<uint64_t>(bs.words) * 8, per, 0); }, &gerr)) {
+          logprintf("\nError: pl2gpu_king_add_variants_sharded: %s\n", gerr.c_str());
+          end_jobs();
+          return kRetGpuFail;
+        }
       }
       t_add += g_clock.Since(ta);
       done += static_cast<uint32_t>(got);
@@ -958,6 +1095,10 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     fflush(stdout);
     if (g_clock.on) fprintf(stderr, "[timing]   decode (PgrGet) %.3f s, pl2gpu_king_add_variants %.3f s\n", t_decode, t_add);
     g_clock.Mark("king: decode + add_variants");
+    for (Slab& sl : slabs) {
+    Pl2KingJob* const job = sl.job;
+    const uint32_t row_start = sl.r0, row_end = sl.r1;
+    if (row_start >= row_end) continue;
     // --make-king-table with --king-table-filter and nothing else to produce: filter on the device and
     // fetch only the surviving rows (the unfiltered table is 20 bytes x N^2/2)
     const bool device_filter = want_table && !want_matrix && c.king_cutoff < 0 && c.king_table_filter != -DBL_MAX;
@@ -970,7 +1111,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
         fc.resize(cap * 5);
         fk.resize(cap);
         if (pl2gpu_king_get_filtered(job, row_start, row_end, c.king_table_filter, cap, fp.data(), fc.data(), fk.data(), &found)) {
-          pl2gpu_king_end(job);
+          end_jobs();
           return GpuFail("pl2gpu_king_get_filtered");
         }
         if (found <= cap) break;
@@ -992,14 +1133,14 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       if (want_table) {
         counts.resize(pairs * 5);
         if (pairs && pl2gpu_king_get_counts(job, c0, c1, counts.data(), 0)) {
-          pl2gpu_king_end(job);
+          end_jobs();
           return GpuFail("pl2gpu_king_get_counts");
         }
       }
       if (want_matrix || c.king_cutoff >= 0 || !want_table) {
         kin.resize(pairs);
         if (pairs && pl2gpu_king_get_kinship(job, c0, c1, kin.data(), 0)) {
-          pl2gpu_king_end(job);
+          end_jobs();
           return GpuFail("pl2gpu_king_get_kinship");
         }
       }
@@ -1069,8 +1210,9 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       }
       c0 = c1;
     }
+    }  // slabs
     g_clock.Mark("king: fetch results + write");
-    pl2gpu_king_end(job);
+    end_jobs();
     g_clock.Mark("king: end (device free)");
   }
   if (square_text_full) {
@@ -1212,9 +1354,32 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
   if (rc) return rc;
   const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_grm_list && !c.make_grm_sparse && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
-  Pl2GrmJob* job = nullptr;
-  if (pl2gpu_grm_begin(ctx, n, r0, r1, flags, &job)) return GpuFail("pl2gpu_grm_begin");
-  BlockStreamer bs(ds, &vidx, n, 32768);
+  // multi-GPU team (--gpus): rows [r0, r1) in one tile-aligned slab per device (CalcGrm's own row split is
+  // TriangleFill2 over threads, 2.0/plink2_matrix_calc.cc:4596); exact --pca needs the whole matrix on one device
+  GpuTeam team;
+  {
+    uint32_t gpus_eff = std::max(1u, std::min(c.gpus, (r1 - r0) / 512));
+    if (keep_for_pca) gpus_eff = 1;
+    if (gpus_eff < c.gpus) logprintf("Note: GRM computed on %u GPU%s (--gpus %u%s).\n", gpus_eff, gpus_eff == 1 ? "" : "s", c.gpus, keep_for_pca ? "; non-approximate --pca keeps the matrix on one device" : "");
+    const int trc = TeamInit(ctx, c.device, gpus_eff, &team);
+    if (trc) return trc;
+  }
+  const uint32_t G = team.size();
+  const std::vector<uint32_t> sbounds = TileAlignedBounds(r0, r1, G, true);
+  std::vector<Pl2GrmJob*> jobs(G, nullptr);
+  auto end_jobs = [&]() {
+    for (auto& j : jobs) {
+      pl2gpu_grm_end(j);
+      j = nullptr;
+    }
+  };
+  for (uint32_t g = 0; g < G; ++g) {
+    if (pl2gpu_grm_begin(team.ctx[g], n, sbounds[g], sbounds[g + 1], flags, &jobs[g])) {
+      end_jobs();
+      return GpuFail("pl2gpu_grm_begin");
+    }
+  }
+  BlockStreamer bs(ds, &vidx, n, 32768, G);
   if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
   logprintf("Constructing GRM: ");
   std::string err;
@@ -1223,14 +1388,24 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     const int got = bs.Next(&err);
     if (got < 0) {
       logprintf("\nError: %s\n", err.c_str());
-      pl2gpu_grm_end(job);
+      end_jobs();
       return kRetMalformedInput;
     }
     if (!got) break;
-    const int arc = pl2gpu_grm_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, have_freqs ? ref_freqs.data() + base : nullptr);
+    int arc;
+    std::string gerr;
+    const double* batch_freqs = have_freqs ? ref_freqs.data() + base : nullptr;
+    if (G == 1) {
+      arc = pl2gpu_grm_add_variants(jobs[0], bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, batch_freqs);
+      if (arc) gerr = pl2gpu_last_error();
+    } else {
+      const uint32_t per = (static_cast<uint32_t>(got) + G - 1) / G;
+      memset(bs.buf + static_cast<uint64_t>(got) * bs.words, 0xFF, static_cast<uint64_t>(per * G - static_cast<uint32_t>(got)) * bs.words * 8);
+      arc = ForEachRank(G, [&](uint32_t g) { return pl2gpu_grm_add_variants_sharded(jobs[g], bs.buf + static_cast<uint64_t>(g) * per * bs.words, static_cast<uint64_t>(bs.words) * 8, per, static_cast<uint32_t>(got), 0, batch_freqs); }, &gerr);
+    }
     if (arc) {
-      logprintf("\nError: %s\n", pl2gpu_last_error());
-      pl2gpu_grm_end(job);
+      logprintf("\nError: %s\n", gerr.c_str());
+      end_jobs();
       return arc == 2 ? kRetDegenerateData : kRetGpuFail;
     }
     base += static_cast<size_t>(got);
@@ -1244,10 +1419,17 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   const uint64_t max_rows = std::max<uint64_t>(1, (384ull << 20) / (stride * 12));
   std::vector<double> g;
   std::vector<float> obs;
+  auto slab_of = [&](uint32_t row) {
+    uint32_t sg = 0;
+    while (sg + 1 < G && row >= sbounds[sg + 1]) ++sg;
+    return sg;
+  };
+  // row chunks handed to the writers never straddle two devices' slabs
+  auto chunk_end = [&](uint32_t a) { return static_cast<uint32_t>(std::min<uint64_t>(std::min<uint64_t>(r1, a + max_rows), sbounds[slab_of(a) + 1])); };
   auto fetch = [&](uint32_t a, uint32_t b) -> bool {
     g.assign(static_cast<uint64_t>(b - a) * stride, 0.0);
     obs.assign(static_cast<uint64_t>(b - a) * stride, 0.0f);
-    return pl2gpu_grm_get_rows(job, a, b, g.data(), obs.data(), stride, 0) == 0;
+    return pl2gpu_grm_get_rows(jobs[slab_of(a)], a, b, g.data(), obs.data(), stride, 0) == 0;
   };
   if (c.make_grm_bin) {
     const std::string gname = PieceName(c.out + ".grm.bin", c), nname = PieceName(c.out + ".grm.N.bin", c);
@@ -1255,9 +1437,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     if (!fg.Open(gname) || !fn.Open(nname)) return kRetOpenFail;
     std::vector<float> rowf(r1);
     for (uint32_t a = r0; a < r1;) {
-      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      const uint32_t b = chunk_end(a);
       if (!fetch(a, b)) {
-        pl2gpu_grm_end(job);
+        end_jobs();
         return GpuFail("pl2gpu_grm_get_rows");
       }
       for (uint32_t j = a; j < b; ++j) {
@@ -1287,9 +1469,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     std::string line;
     char num[64];
     for (uint32_t a = r0; a < r1;) {
-      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      const uint32_t b = chunk_end(a);
       if (!fetch(a, b)) {
-        pl2gpu_grm_end(job);
+        end_jobs();
         return GpuFail("pl2gpu_grm_get_rows");
       }
       for (uint32_t j = a; j < b; ++j) {
@@ -1328,9 +1510,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     OutFile fg;
     if (!fg.Open(gname)) return kRetOpenFail;
     for (uint32_t a = r0; a < r1;) {
-      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      const uint32_t b = chunk_end(a);
       if (!fetch(a, b)) {
-        pl2gpu_grm_end(job);
+        end_jobs();
         return GpuFail("pl2gpu_grm_get_rows");
       }
       for (uint32_t j = a; j < b; ++j) {
@@ -1373,9 +1555,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     auto tri1 = [](uint64_t r) { return r * (r + 1) / 2; };
     if (c.rel_shape == Cmd::kSq) full.resize(tri1(n));
     for (uint32_t a = r0; a < r1;) {
-      const uint32_t b = static_cast<uint32_t>(std::min<uint64_t>(r1, a + max_rows));
+      const uint32_t b = chunk_end(a);
       if (!fetch(a, b)) {
-        pl2gpu_grm_end(job);
+        end_jobs();
         return GpuFail("pl2gpu_grm_get_rows");
       }
       for (uint32_t j = a; j < b; ++j) {
@@ -1446,8 +1628,8 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
     }
     logprintf("%s .\n", msg.c_str());
   }
-  if (keep_for_pca) *kept_job = job;
-  else pl2gpu_grm_end(job);
+  if (keep_for_pca) *kept_job = jobs[0];  // G == 1 in that case
+  else end_jobs();
   return 0;
 }
 

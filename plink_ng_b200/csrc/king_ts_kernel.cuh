@@ -95,11 +95,18 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     mbar_init(&bar_acc, 1);
     mbar_fence_init();
   }
+  __syncthreads();  // barriers initialised
+  // Tensor memory is needed by the row warps and the issuer only.  The allocation blocks while the previous CTA on
+  // this SM still holds its 512 columns (two CTAs fit an SM otherwise), so the TMA producer and the column warps do
+  // NOT wait for it: rings and B stages of this tile fill up behind the previous tile's epilogue.
+  uint32_t tmem_base = 0;
   if (warp == kTsIssuerWarp) tmem_alloc<512>(&tmem_base_slot);
-  tc_fence_before_sync();
-  __syncthreads();
-  tc_fence_after_sync();
-  const uint32_t tmem_base = tmem_base_slot;
+  if (warp < kTsRowWarps || warp == kTsIssuerWarp) {
+    tc_fence_before_sync();
+    named_bar_sync<1, 32 * (kTsRowWarps + 1)>();
+    tc_fence_after_sync();
+    tmem_base = tmem_base_slot;
+  }
 
   const uint32_t thread_zero = tid * (variant_ct_padded >> 31);  // 0 (a batch never has 2^31 variants)
   const uint32_t tab_t = table_reg(kTabHet, thread_zero), tab_h = table_reg(kTabHom, thread_zero), tab_s = table_reg(kTabSgn, thread_zero);
@@ -140,8 +147,7 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
       Words r;
       r.w[0] = lds64(ring_i + si * kTsRawIBytes + grp * (kTileRows * 8));
       r.w[1] = lds64(ring_i + si * kTsRawIBytes + (grp + 2) * (kTileRows * 8));
-      mbar_release_warp(&bar_empty_ri[si], lane, r.w[0].x ^ r.w[0].y ^ r.w[1].x ^ r.w[1].y);
-      return r;
+      return r;  // the slot is released only after both words have gone through tcgen05.st (see below)
     };
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4
     Words words = load_slot(0);
@@ -162,9 +168,16 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
         mbar_arrive_warp(&bar_full_a[slot], lane);
         if (h == 0) {
           cur = expand_i(words.w[1]);
-        } else if (q + 1 < slot_iters) {
-          words = load_slot(q + 1);
-          cur = expand_i(words.w[0]);
+        } else {
+          // Release the ring slot HERE: the warp-collective tcgen05.st above could only issue once every lane's
+          // expanded registers - hence both ld.shared results - were complete.  (Releasing right after the loads
+          // is a race: the arrive can overtake a queued ld.shared, the producer refills the slot, and half a
+          // warp reads the next revolution's words - seen as 16-sample groups with slightly wrong counts.)
+          mbar_arrive_warp(&bar_empty_ri[q % kTsRawISlots], lane);
+          if (q + 1 < slot_iters) {
+            words = load_slot(q + 1);
+            cur = expand_i(words.w[0]);
+          }
         }
       }
     }
@@ -201,8 +214,7 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
       uint2 r;
       r.x = lds32(ring_j + sj * kTsRawJBytes);
       r.y = lds32(ring_j + sj * kTsRawJBytes + kTsKcJ * kTsRawBoxBytes);
-      mbar_release_warp(&bar_empty_rj[sj], lane, r.x ^ r.y);
-      return r;
+      return r;  // released after the second word has been stored (st.shared needs the loaded value)
     };
     const uint32_t slot_iters = stage_iters / 2;
     uint2 words = load_slot(0);
@@ -221,9 +233,12 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
         mbar_arrive_warp(&bar_full_b[sb], lane);
         if (h == 0) {
           cur = expand_j(words.y);
-        } else if (q + 1 < slot_iters) {
-          words = load_slot(q + 1);
-          cur = expand_j(words.x);
+        } else {
+          mbar_arrive_warp(&bar_empty_rj[q % kTsRawJSlots], lane);  // both words consumed by the st.shared above
+          if (q + 1 < slot_iters) {
+            words = load_slot(q + 1);
+            cur = expand_j(words.x);
+          }
         }
       }
     }
@@ -285,34 +300,54 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
   }
 
   if (warp < kTsRowWarps) {
-    // ---------------- epilogue: TMEM -> raw accumulators (+=) ----------------
+    // ---------------- epilogue: TMEM -> shared memory -> bulk reduce-add into the HBM accumulators ----------------
+    // The accumulators of a tile are one contiguous int32 [5 x 80 columns][128 rows] block.  Instead of a
+    // load-add-store per element from registers (latency-bound: ~16 KB in flight per SM, ~45 us per tile, i.e. >10 %
+    // of the tile), each accumulator plane (80 columns = 40 KB) is staged in shared memory - the operand stages and
+    // rings are idle now - and handed to the TMA unit as ONE cp.reduce.async.bulk .add.s32: the addition happens at
+    // the L2, nothing is read back, and tensor memory is released as soon as the last tcgen05.ld has returned.
     mbar_wait(&bar_acc, 0);
     tc_fence_after_sync();
-    const uint32_t lane_grp = warp & 3;
-    const uint32_t rsample = 32 * lane_grp + lane;  // rows are in natural sample order here
-    int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kTsTileAccWords + rsample;
-    const uint32_t chunk_begin = (warp < 4) ? 0u : 13u, chunk_end = (warp < 4) ? 13u : 25u;
+    constexpr uint32_t kPlaneBytes = kTsCols * kTileRows * 4;  // 40960
+    static_assert(2 * kPlaneBytes <= kTsSmemBytes - 1024, "two staging planes must fit the dynamic shared memory");
+    const uint32_t lq = warp & 3, half = warp >> 2;
+    const uint32_t rsample = 32 * lq + lane;  // rows are in natural sample order here
+    int32_t* acc_tile = raw_acc + static_cast<uint64_t>(tile) * kTsTileAccWords;
 #pragma unroll 1
-    for (uint32_t chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((32u * lane_grp) << 16) + 16 * chunk, v);
-      tmem_ld_wait();
-      const uint32_t q = chunk / kTsGroupsJ;
-      const uint32_t cgrp = chunk % kTsGroupsJ;
-      int32_t* base = acc_tile + static_cast<uint64_t>(q * kTsCols + cgrp * 16) * kTileRows;
+    for (uint32_t q = 0; q < 5; ++q) {  // accumulator planes TT, TH, HT, HH, SS
+      const uint32_t stage = smem_base + (q & 1) * kPlaneBytes + rsample * 4;
+      if (q >= 2) {
+        // plane q - 2 used this staging buffer: its bulk reduction must have finished READING shared memory
+        if (tid == 0) bulk_wait_group_read<1>();
+        named_bar_sync<2, 32 * kTsRowWarps>();
+      }
+      // 5 chunks of 16 columns per plane and lane quarter: half 0 takes chunks 0, 2, 4, half 1 takes 1, 3
+#pragma unroll 1
+      for (uint32_t cgrp = half; cgrp < kTsGroupsJ; cgrp += 2) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((32u * lq) << 16) + 16 * (q * kTsGroupsJ + cgrp), v);
+        tmem_ld_wait();
 #pragma unroll
-      for (uint32_t c = 0; c < 16; ++c) {
-        int32_t* p = base + PosToSample(c) * kTileRows;
-        *p += static_cast<int32_t>(v[c]);
+        for (uint32_t c = 0; c < 16; ++c) sts32(stage + (cgrp * 16 + PosToSample(c)) * (kTileRows * 4), v[c]);
+      }
+      fence_proxy_async_smem();
+      if (q == 4) tc_fence_before_sync();  // last tcgen05.ld of this warp is complete
+      named_bar_sync<2, 32 * kTsRowWarps>();
+      if (tid == 0) {
+        bulk_reduce_add_s32(acc_tile + static_cast<uint64_t>(q) * (kTsCols * kTileRows), smem_base + (q & 1) * kPlaneBytes, kPlaneBytes);
+        bulk_commit_group();
       }
     }
-    tc_fence_before_sync();
   }
-  __syncthreads();
-  if (warp == kTsIssuerWarp) {
-    tc_fence_after_sync();
-    tmem_dealloc<512>(tmem_base);
+  if (warp < kTsRowWarps || warp == kTsIssuerWarp) {
+    // all tensor-memory reads are done: hand the columns to the next CTA before the reductions have drained
+    named_bar_sync<1, 32 * (kTsRowWarps + 1)>();
+    if (warp == kTsIssuerWarp) {
+      tc_fence_after_sync();
+      tmem_dealloc<512>(tmem_base);
+    }
   }
+  if (tid == 0) bulk_wait_group_read<0>();  // shared memory must outlive the reductions' reads
 }
 
 }  // namespace pl2

@@ -50,7 +50,7 @@ constexpr uint32_t kLdtSmemBytes = kLdtSmemOffRawB + kLdtRawBSlots * kLdtRawBByt
 constexpr uint32_t kLdtRowWarps = 8;
 constexpr uint32_t kLdtColWarps = 8;               // 64 variants x 4 words per stage = 256 threads
 constexpr uint32_t kLdtIssuerWarp = kLdtRowWarps + kLdtColWarps;
-constexpr uint32_t kLdtThreads = 32 * (kLdtRowWarps + kLdtColWarps + 2);
+constexpr uint32_t kLdtThreads = 32 * (kLdtRowWarps + kLdtColWarps + 3);  // + UMMA issuer + one TMA producer warp per operand ring
 static_assert(kLdtAccCols + kLdtASlots * kLdtASlotCols <= 512, "LD accumulators + A slots exceed TMEM");
 
 // variants_in_chunk: rows of the staged block (multiple of 64, >= every row a box touches is zero-filled by TMA
@@ -140,8 +140,7 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         e.v[p][0] = a.x; e.v[p][1] = a.y; e.v[p][2] = a.z; e.v[p][3] = a.w;
         e.v[p][4] = b.x; e.v[p][5] = b.y; e.v[p][6] = b.z; e.v[p][7] = b.w;
       }
-      mbar_arrive_warp(&bar_empty_ra[sa], lane);
-      return e;
+      return e;  // the ring slot is released after the tcgen05.st of these registers (see king_ts_kernel.cuh)
     };
     ExpI cur = fetch(0);
     for (uint32_t n = 0; n < stage_iters; ++n) {
@@ -156,6 +155,7 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive_warp(&bar_full_a[slot], lane);
+      mbar_arrive_warp(&bar_empty_ra[n % kLdtRawASlots], lane);  // box n consumed: its words went through tcgen05.st
       if (n + 1 < stage_iters) cur = fetch(n + 1);
     }
   } else if (warp < kLdtIssuerWarp) {
@@ -178,8 +178,7 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       e.v_hom = expand16(tab_hom, sel);
       e.v_nm = expand16(tab_nm, sel);
       e.v_x = expand16(tab_x, sel);
-      mbar_arrive_warp(&bar_empty_rb[sb], lane);
-      return e;
+      return e;  // slot released after the st.shared of these registers
     };
     ExpJ cur = fetch(0);
     for (uint32_t it = 0; it < stage_iters; ++it) {
@@ -189,6 +188,7 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0), "r"(cur.v_hom.x), "r"(cur.v_hom.y), "r"(cur.v_hom.z), "r"(cur.v_hom.w) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + kLdtPlaneBytes), "r"(cur.v_nm.x), "r"(cur.v_nm.y), "r"(cur.v_nm.z), "r"(cur.v_nm.w) : "memory");
       asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a0 + 2 * kLdtPlaneBytes), "r"(cur.v_x.x), "r"(cur.v_x.y), "r"(cur.v_x.z), "r"(cur.v_x.w) : "memory");
+      mbar_arrive_warp(&bar_empty_rb[it % kLdtRawBSlots], lane);
       fence_proxy_async_smem();
       mbar_arrive_warp(&bar_full_b[sb], lane);
       if (it + 1 < stage_iters) cur = fetch(it + 1);
@@ -227,19 +227,27 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     if (elect_one_sync()) umma_commit(&bar_acc);
     __syncwarp();
   } else {
-    // ---------------- TMA producer ----------------
+    // ---------------- TMA producers: one elected lane per operand ring (a single lane feeding both rings spends
+    // ~6 mbarrier / TMA operations per 384-clk stage and becomes the limiter, cf. king_ts_kernel.cuh) ----------------
     if (elect_one_sync()) {
-      const uint32_t ring_a = smem_base + kLdtSmemOffRawA, ring_b = smem_base + kLdtSmemOffRawB;
-      const int32_t row_a = static_cast<int32_t>(a_start - chunk_lo), row_b = static_cast<int32_t>(b_start - chunk_lo);
-      for (uint32_t it = 0; it < stage_iters; ++it) {
-        const uint32_t sa = it % kLdtRawASlots;
-        mbar_wait(&bar_empty_ra[sa], ((it / kLdtRawASlots) & 1) ^ 1);
-        mbar_expect_tx(&bar_full_ra[sa], kLdtRawABytes);
-        tma_load_2d(ring_a + sa * kLdtRawABytes, &tmap_a, static_cast<int32_t>(it * kLdtBoxBytes), row_a, &bar_full_ra[sa]);
-        const uint32_t sb = it % kLdtRawBSlots;
-        mbar_wait(&bar_empty_rb[sb], ((it / kLdtRawBSlots) & 1) ^ 1);
-        mbar_expect_tx(&bar_full_rb[sb], kLdtRawBBytes);
-        tma_load_2d(ring_b + sb * kLdtRawBBytes, &tmap_b, static_cast<int32_t>(it * kLdtBoxBytes), row_b, &bar_full_rb[sb]);
+      if (warp == kLdtIssuerWarp + 1) {
+        const uint32_t ring_a = smem_base + kLdtSmemOffRawA;
+        const int32_t row_a = static_cast<int32_t>(a_start - chunk_lo);
+        for (uint32_t it = 0; it < stage_iters; ++it) {
+          const uint32_t sa = it % kLdtRawASlots;
+          mbar_wait(&bar_empty_ra[sa], ((it / kLdtRawASlots) & 1) ^ 1);
+          mbar_expect_tx(&bar_full_ra[sa], kLdtRawABytes);
+          tma_load_2d(ring_a + sa * kLdtRawABytes, &tmap_a, static_cast<int32_t>(it * kLdtBoxBytes), row_a, &bar_full_ra[sa]);
+        }
+      } else {
+        const uint32_t ring_b = smem_base + kLdtSmemOffRawB;
+        const int32_t row_b = static_cast<int32_t>(b_start - chunk_lo);
+        for (uint32_t it = 0; it < stage_iters; ++it) {
+          const uint32_t sb = it % kLdtRawBSlots;
+          mbar_wait(&bar_empty_rb[sb], ((it / kLdtRawBSlots) & 1) ^ 1);
+          mbar_expect_tx(&bar_full_rb[sb], kLdtRawBBytes);
+          tma_load_2d(ring_b + sb * kLdtRawBBytes, &tmap_b, static_cast<int32_t>(it * kLdtBoxBytes), row_b, &bar_full_rb[sb]);
+        }
       }
     }
     __syncwarp();

@@ -48,7 +48,8 @@ int BuildTileList(uint32_t row_start, uint32_t row_end, bool include_diag, TileL
   std::vector<uint32_t> rt_v, tc_v, off_v;
   tl->row_tile_first = row_start / kTileRows;
   uint32_t rt = tl->row_tile_first;
-  for (; rt * kTileRows < row_end; ++rt) {
+  // an empty row range (a rank of a multi-GPU team that owns no rows) has no tiles at all
+  for (; row_end > row_start && rt * kTileRows < row_end; ++rt) {
     off_v.push_back(static_cast<uint32_t>(rt_v.size()));
     const uint32_t nct = ColTilesForRowTile(rt, row_end, include_diag, tile_cols);
     for (uint32_t tc = 0; tc < nct; ++tc) {
@@ -477,7 +478,7 @@ int pl2gpu_king_begin_ex(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start,
     set_error("pl2gpu_king_begin: null context");
     return 1;
   }
-  if (sample_ct < 2 || row_end > sample_ct || row_start >= row_end) {
+  if (sample_ct < 2 || row_end > sample_ct || row_start > row_end) {  // row_start == row_end: a rank that only takes part in the all-gathers
     set_error("pl2gpu_king_begin: bad row range [%u,%u) for %u samples", row_start, row_end, sample_ct);
     return 1;
   }
@@ -561,6 +562,11 @@ static int KingTsPrepAndLaunch(Pl2KingJob* job, uint32_t b, uint32_t cur, bool p
     PL2_TRY(LaunchPadGenotypes(c, st.d_raw, st.pitch, st.sample_ct, cur, padded, prep));
   } else if (padded > cur) {
     PL2_TRY(LaunchPadGenotypes(c, st.d_raw + static_cast<uint64_t>(cur) * st.pitch, st.pitch, st.sample_ct, 0, padded - cur, prep));
+  }
+  if (!job->tiles.tile_ct) {  // nothing to count on this rank: only order later reuse of the buffer behind the gather
+    PL2_CUDA_OK(cudaEventRecord(job->ev_kernel_done[b], prep));
+    job->kernel_pending[b] = true;
+    return 0;
   }
   geno_tile_rows_kernel<<<dim3(padded / 64, job->tiles.row_tile_ct * (kTileRows / 64)), 256, 0, prep>>>(st.d_raw, st.pitch, padded / 32, job->tiles.row_tile_first * kTileRows, job->d_raw_t[b]);
   c->launches++;

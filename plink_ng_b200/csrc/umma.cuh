@@ -30,12 +30,9 @@ __device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar, uint32_t lane) {
   __syncwarp();
   if (lane == 0) mbar_arrive(bar);
 }
-// Warp-level release of a shared-memory ring slot the lanes have READ: `dep` is any value computed from the
-// loaded words - making it an operand of the arrive pins the arrive behind the loads' completion.
-__device__ __forceinline__ void mbar_release_warp(uint64_t* bar, uint32_t lane, uint32_t dep) {
-  __syncwarp();
-  if (lane == 0) asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t// after %1\n\t}" ::"r"(smem_u32(bar)), "r"(dep) : "memory");
-}
+// NOTE on releasing a shared-memory ring slot the lanes have READ with ld.shared: arrive only after an instruction
+// that consumed the loaded registers has issued (st.shared / tcgen05.st of values derived from them).  An arrive
+// placed right after the loads can overtake them in the memory pipeline.
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -66,6 +63,26 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const void* tenso
 __device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// Asynchronous bulk reduction shared -> global through the TMA unit (SASS UBLKRED): global[i] += smem[i] on
+// 32-bit signed integers / fp64, performed at the L2 without the SM ever reading the old values.  Issued by one
+// thread; completion of the shared-memory READS is tracked by that thread's bulk async-groups.
+__device__ __forceinline__ void bulk_reduce_add_s32(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.s32 [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f64(void* dst_global, uint32_t src_smem, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f64 [%0], [%1], %2;" ::"l"(dst_global), "r"(src_smem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_group_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+// named barrier among a subset of the CTA's warps (id 1..15; thread count a multiple of 32)
+template <uint32_t kId, uint32_t kThreads>
+__device__ __forceinline__ void named_bar_sync() {
+  asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kThreads) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const void* tensor_map) { asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;

@@ -10,7 +10,7 @@ pre = os.path.join(d, "d")
 subprocess.run([REF, "--dummy", str(n), str(m), "0.02", "--seed", "9", "--threads", "4", "--make-bed", "--out", pre], check=True, capture_output=True)
 flags = ["--make-king", "bin", "triangle", "--make-king-table", "counts", "--king-table-filter", "-0.05"]
 subprocess.run([REF, "--bfile", pre] + flags + ["--threads", "16", "--out", pre + "_ref"], check=True, capture_output=True)
-for rep in range(3):
+for rep in range(int(os.environ.get('REPS', '3'))):
     r = subprocess.run([BIN, "--bfile", pre] + flags + extra + ["--out", pre + "_b"], capture_output=True, text=True)
     print("rc", r.returncode, [ln for ln in r.stdout.split("\n") if "passes" in ln or "Error" in ln])
     a = np.fromfile(pre + "_ref.king.bin", dtype=np.float64)
