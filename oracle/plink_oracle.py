@@ -150,6 +150,31 @@ def king_table_columns(counts: np.ndarray):
     return nsnp, hethet, ibs0, het1hom2, het2hom1, hamming
 
 
+def king_sparse_nsnp_extra(geno: np.ndarray, row_end: int = None) -> np.ndarray:
+    """What the reference's rare-variant pre-scan adds to NSNP beyond the dense count, per pair in king_counts
+    order.  CalcKingSparseThread (2.0/plink2_matrix_calc.cc:904-1250) pre-scans a variant when hom-REF (else
+    hom-ALT) covers all but row_end // 33 of the pass's samples (KingMaxSparseCt :1654, AVX2 build; test order
+    :985-1001).  Its pair corrections reproduce dense counting except for (other homozygote, missing) pairs,
+    which get HOMHOM + 1 (:1086-1096, :1129-1139): the table's NSNP = HET1_HOM2 + HET2_HOM1 + HOMHOM + HETHET
+    (:2315-2318) is then one higher per such variant.  Verified against the reference binary on the
+    4,096 x 65,536 --dummy set (179 of 254,515 table rows differ from the dense count, all explained by this)."""
+    m, n = geno.shape
+    s_ct = n if row_end is None else row_end
+    g = geno[:, :s_ct]
+    n0, n2 = (g == 0).sum(axis=1), (g == 2).sum(axis=1)
+    min_common = s_ct - s_ct // 33
+    c0 = n0 >= min_common
+    c2 = (~c0) & (n2 >= min_common)
+    sp = np.flatnonzero(c0 | c2)
+    gs = g[sp]
+    other = np.where(c0[sp][:, None], gs == 2, gs == 0).astype(np.int64)
+    miss = (gs == 3).astype(np.int64)
+    om = other.T @ miss
+    om = om + om.T  # [a, b]: pre-scanned variants where one of a, b is the other homozygote and its partner is missing
+    rows = [om[j, :j] for j in range(1, s_ct)]
+    return np.concatenate(rows) if rows else np.zeros(0, dtype=np.int64)
+
+
 def read_kin0_counts(path: str):
     """Parse a reference `.kin0` written with `counts cols=+ibs1,+ibs` into (ids, int columns, kinship)."""
     with open(path) as f:

@@ -1,15 +1,19 @@
 // geno_tile.cuh - operand re-tiling for the "TS" tensor kernels (king_ts_kernel.cuh, grm_ts_kernel.cuh):
-// 128-row x 80-column pair tiles, row operand expanded into tensor memory, column operand into
+// 128-row x 64-column pair tiles, row operand expanded into tensor memory, column operand into
 // shared memory.  Kernels are static (header is included by several translation units).
 #pragma once
 #include "common.cuh"
 
 namespace pl2 {
 
-constexpr uint32_t kTsCols = 80;
-constexpr uint32_t kTsSamplePad = 640;  // lcm(128, 80)
+// 128 x 64 pair tiles: 5 (KING) / 6 (GRM) int32 accumulators take 320 / 384 of the 512 tensor-memory columns and
+// leave room for EIGHT row-operand slots.  With 80-column tiles only 4 (KING) / 2 (GRM) slots fit, and the slot
+// hand-off (tcgen05.commit -> mbarrier -> tcgen05.st -> mbarrier -> next UMMA, ~750 clk) is then longer than the
+// 3 (1) queued k-steps: the issuer was waiting for row slots 2.2 times per k-step (profiles/r02_ncu_king_ts.md).
+constexpr uint32_t kTsCols = 64;
+constexpr uint32_t kTsSamplePad = 128;  // lcm(128, 64)
 constexpr uint32_t kTsKcJ = 64;         // variants per shared-memory stage (two k-steps)
-constexpr uint32_t kTsRawBoxBytes = 32; // inner extent of the TMA box over the raw block (>= 20 bytes = 80 samples, multiple of 16)
+constexpr uint32_t kTsRawBoxBytes = 16; // inner extent of the TMA box over the raw block: the tile's 64 samples
 
 // ---- operand re-tiling of the staged block raw[variant][pitch] (2-bit, variant-major) -------------
 // Both copies make every producer load of king_ts_kernel a contiguous run of bytes (the first TS
@@ -37,17 +41,6 @@ static __global__ void __launch_bounds__(256) geno_tile_rows_kernel(const uint8_
     for (uint32_t j = 0; j < 16; ++j) w |= static_cast<uint32_t>(tile[16 * vw + j][sl]) << (2 * j);
     const uint32_t s = s0 + sl, v = v0 + 16 * vw;
     *reinterpret_cast<uint32_t*>(raw_i + (static_cast<uint64_t>((s - s_base) >> 7) * kstep_ct + (v >> 5)) * 1024 + (s & 127) * 8 + 4 * ((v >> 4) & 1)) = w;
-  }
-}
-
-// Column side:  raw_j[column tile ct][stage][variant 0..63][20 bytes]   20 bytes = the tile's 80 samples
-static __global__ void __launch_bounds__(256) geno_tile_cols_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t stage_ct, uint32_t coltile_ct, uint8_t* __restrict__ raw_j) {
-  const uint32_t stage = blockIdx.x, ct0 = blockIdx.y * 16;
-  for (uint32_t idx = threadIdx.x; idx < 16 * kTsKcJ * 5; idx += 256) {
-    const uint32_t w = idx % 5, k = (idx / 5) % kTsKcJ, ct = ct0 + idx / (5 * kTsKcJ);
-    if (ct >= coltile_ct) break;
-    const uint32_t val = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(stage * kTsKcJ + k) * pitch + 20 * ct + 4 * w);
-    *reinterpret_cast<uint32_t*>(raw_j + ((static_cast<uint64_t>(ct) * stage_ct + stage) * kTsKcJ + k) * 20 + 4 * w) = val;
   }
 }
 

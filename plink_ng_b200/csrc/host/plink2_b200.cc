@@ -540,7 +540,7 @@ int TeamInit(Pl2GpuCtx* first, int first_device, uint32_t gpus, GpuTeam* team) {
 }
 
 // Rows [r0, r1) of the lower triangle cut into `parts` contiguous blocks whose interior boundaries are multiples
-// of the 128-row pair tile and which hold (nearly) the same number of 128 x 80 pair tiles - the unit the tensor
+// of the 128-row pair tile and which hold (nearly) the same number of 128 x 64 pair tiles - the unit the tensor
 // kernels' time is proportional to.  Blocks may be empty when the range holds fewer row tiles than parts.
 std::vector<uint32_t> TileAlignedBounds(uint32_t r0, uint32_t r1, uint32_t parts, bool include_diag) {
   std::vector<uint32_t> b(parts + 1, r1);
@@ -551,7 +551,7 @@ std::vector<uint32_t> TileAlignedBounds(uint32_t r0, uint32_t r1, uint32_t parts
   for (uint32_t rt = rt0; rt < rt1; ++rt) {
     const uint32_t row_end = std::min(r1, (rt + 1) * 128);
     const uint32_t cols = include_diag ? row_end : row_end - 1;
-    cum.push_back(cum.back() + (cols + 79) / 80);
+    cum.push_back(cum.back() + (cols + 63) / 64);
   }
   for (uint32_t k = 1; k < parts; ++k) {
     const double target = static_cast<double>(cum.back()) * k / parts;
@@ -664,7 +664,80 @@ std::string KingTableHeader(const Cmd& c, const IdFmt& idf) {
 }
 
 // One .kin0 line (:2285-2364 / :3705-3760): cc = {IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM}.
-void WriteKingTableRow(const Cmd& c, const std::string& id1, const std::string& id2, const uint32_t* cc, double kinship, OutFile* ftab) {
+// The reference's rare-variant pre-scan (CalcKingSparseThread, 2.0/plink2_matrix_calc.cc:904-1250; a variant is
+// pre-scanned when its commonest genotype among hom-REF / hom-ALT covers all but row_end/33 of the pass's samples,
+// KingMaxSparseCt :1654) reproduces dense counting in every pair case but one: where one sample carries the OTHER
+// homozygote and its partner is missing, both branches add 1 to HOMHOM (:1086-1096, :1129-1139) although the pair
+// is not jointly observed.  NSNP = HET1_HOM2 + HET2_HOM1 + HOMHOM + HETHET (:2315-2318) - and every proportion
+// column, which divides by it - therefore comes out one higher per such variant than the dense count this
+// program's kernels produce (178 of 251,594 rows at 4,096 x 65,536 --dummy data).  The .kin0 writer adds the same
+// amount so that the table stays byte-identical; counts, kinship and the matrices are unaffected.
+struct SparseNsnpFix {
+  std::unordered_map<uint64_t, uint32_t> extra;  // (larger index << 32 | smaller index) -> pre-scanned variants with the (other-hom, missing) pattern
+  void Scan(const uint64_t* buf, uint32_t variant_ct, uint32_t words, uint32_t s_ct, uint32_t r0, uint32_t r1, uint32_t threads) {
+    if (s_ct < 66) return;  // max_sparse_ct = s_ct / 33 < 2: a pre-scanned variant cannot hold both rare genotypes
+    threads = std::max(1u, std::min(threads, (variant_ct + 1023) / 1024));
+    std::vector<std::vector<uint64_t>> found(threads);
+    auto work = [&](uint32_t t) {
+      const uint32_t v0 = static_cast<uint32_t>(static_cast<uint64_t>(variant_ct) * t / threads), v1 = static_cast<uint32_t>(static_cast<uint64_t>(variant_ct) * (t + 1) / threads);
+      const uint32_t full_words = s_ct / 32, rem = s_ct % 32;
+      const uint32_t min_common = s_ct - s_ct / 33;
+      std::vector<uint32_t> oth, mis;
+      for (uint32_t v = v0; v < v1; ++v) {
+        const uint64_t* row = buf + static_cast<uint64_t>(v) * words;
+        uint32_t n1 = 0, n2 = 0, n3 = 0;
+        for (uint32_t w = 0; w < full_words + (rem ? 1 : 0); ++w) {
+          uint64_t x = row[w];
+          if (w == full_words) x &= (1ull << (2 * rem)) - 1;
+          const uint64_t lo = x & 0x5555555555555555ull, hi = (x >> 1) & 0x5555555555555555ull;
+          n1 += static_cast<uint32_t>(__builtin_popcountll(lo & ~hi));
+          n2 += static_cast<uint32_t>(__builtin_popcountll(hi & ~lo));
+          n3 += static_cast<uint32_t>(__builtin_popcountll(lo & hi));
+        }
+        const uint32_t n0 = s_ct - n1 - n2 - n3;
+        uint32_t other_code;
+        if (n0 >= min_common) other_code = 2;
+        else if (n2 >= min_common) other_code = 0;
+        else continue;
+        if (!n3 || !(other_code == 2 ? n2 : n0)) continue;
+        oth.clear();
+        mis.clear();
+        for (uint32_t w = 0; w < full_words + (rem ? 1 : 0); ++w) {
+          uint64_t x = row[w];
+          const uint32_t lim = (w == full_words) ? rem : 32;
+          const uint64_t lo = x & 0x5555555555555555ull, hi = (x >> 1) & 0x5555555555555555ull;
+          uint64_t m_bits = lo & hi, o_bits = (other_code == 2) ? (hi & ~lo) : (~(lo | hi) & 0x5555555555555555ull);
+          if (lim < 32) {
+            const uint64_t keep = (1ull << (2 * lim)) - 1;
+            m_bits &= keep;
+            o_bits &= keep;
+          }
+          for (; m_bits; m_bits &= m_bits - 1) mis.push_back(32 * w + static_cast<uint32_t>(__builtin_ctzll(m_bits)) / 2);
+          for (; o_bits; o_bits &= o_bits - 1) oth.push_back(32 * w + static_cast<uint32_t>(__builtin_ctzll(o_bits)) / 2);
+        }
+        for (uint32_t o : oth) {
+          for (uint32_t m : mis) {
+            const uint32_t hi_s = std::max(o, m), lo_s = std::min(o, m);
+            if (hi_s >= r0 && hi_s < r1) found[t].push_back((static_cast<uint64_t>(hi_s) << 32) | lo_s);
+          }
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < threads; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (auto& f : found)
+      for (uint64_t k : f) ++extra[k];
+  }
+  uint32_t Get(uint32_t hi_s, uint32_t lo_s) const {
+    if (extra.empty()) return 0;
+    const auto it = extra.find((static_cast<uint64_t>(hi_s) << 32) | lo_s);
+    return it == extra.end() ? 0 : it->second;
+  }
+};
+
+void WriteKingTableRow(const Cmd& c, const std::string& id1, const std::string& id2, const uint32_t* cc, double kinship, OutFile* ftab, uint32_t nsnp_extra = 0) {
   const uint32_t ibs0 = cc[0], hethet = cc[1], het2hom1 = cc[2], het1hom2 = cc[3], homhom = cc[4];
   char* w = ftab->Reserve(id1.size() + id2.size() + 160);
   if (c.col_id) {
@@ -675,7 +748,7 @@ void WriteKingTableRow(const Cmd& c, const std::string& id1, const std::string& 
     w += id2.size();
     *w++ = '\t';
   }
-  const uint32_t nonmiss = het1hom2 + het2hom1 + homhom + hethet;
+  const uint32_t nonmiss = het1hom2 + het2hom1 + homhom + hethet + nsnp_extra;
   double recip = 0.0;
   if (c.col_nsnp) {
     w = u32toa(nonmiss, w);
@@ -982,7 +1055,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   // variants per staged block: the full 65,536 unless the cap is so small that the two staged blocks would
   // eat most of it (then halve until they fit in a quarter of the budget)
   uint32_t batch = 65536;
-  while (batch > 2048 && 4ull * batch * ((n + 639) / 640 * 160) > budget / 4) batch /= 2;
+  while (batch > 2048 && 4ull * batch * ((n + 127) / 128 * 32) > budget / 4) batch /= 2;
   auto pass_fits = [&](uint32_t a, uint32_t b) {
     const std::vector<uint32_t> sb = TileAlignedBounds(a, b, G, false);
     for (uint32_t g = 0; g < G; ++g) {
@@ -1032,6 +1105,9 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
     Pl2KingJob* job = nullptr;
     uint32_t r0 = 0, r1 = 0;
   };
+  // NSNP compatibility with the reference's rare-variant pre-scan (SparseNsnpFix); only the table shows NSNP
+  const bool nsnp_fix_on = want_table && (c.col_nsnp || !c.king_counts) && !getenv("PL2_KING_DENSE_NSNP");
+  SparseNsnpFix nsnp_fix;
   uint32_t pass_r1 = grand_r0;
   for (uint32_t pass = 1; pass <= pass_ct; ++pass) {
     const uint32_t pass_r0 = pass_r1;
@@ -1068,6 +1144,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
         return kRetMalformedInput;
       }
       if (!got) break;
+      if (nsnp_fix_on) nsnp_fix.Scan(bs.buf, static_cast<uint32_t>(got), bs.words, grand_r1, pass_r0, pass_r1, g_decode_threads);
       const auto ta = std::chrono::steady_clock::now();
       if (G == 1) {
         if (pl2gpu_king_add_variants(slabs[0].job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0)) {
@@ -1117,7 +1194,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
         if (found <= cap) break;
         cap = found;
       }
-      for (uint64_t q = 0; q < found; ++q) WriteKingTableRow(c, fmtids[fp[2 * q]], fmtids[fp[2 * q + 1]], &fc[5 * q], fk[q], &ftab);
+      for (uint64_t q = 0; q < found; ++q) WriteKingTableRow(c, fmtids[fp[2 * q]], fmtids[fp[2 * q + 1]], &fc[5 * q], fk[q], &ftab, nsnp_fix.Get(fp[2 * q], fp[2 * q + 1]));
       auto tri = [](uint64_t r) { return r ? r * (r - 1) / 2 : 0ull; };
       filter_ct += tri(row_end) - tri(row_start) - found;
     }
@@ -1203,7 +1280,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
               ++filter_ct;
               continue;
             }
-            WriteKingTableRow(c, fmtids[j], fmtids[i], cc, kinship, &ftab);
+            WriteKingTableRow(c, fmtids[j], fmtids[i], cc, kinship, &ftab, nsnp_fix.Get(j, i));
           }
         }
         p += j;
@@ -1211,6 +1288,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
       c0 = c1;
     }
     }  // slabs
+    nsnp_fix.extra.clear();
     g_clock.Mark("king: fetch results + write");
     end_jobs();
     g_clock.Mark("king: end (device free)");

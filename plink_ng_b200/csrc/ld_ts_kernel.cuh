@@ -13,7 +13,7 @@
 //
 // Tile = 128 "second" variants (rows = TMEM lanes) x 64 "first" variants (columns); k-step = 32 founders.
 // TMEM columns: [0,192) nm_a x [hom_b | nm_b | x_b], [192,256) hom_a x nm_b, [256,384) x_a x [nm_b | x_b],
-// [384,480) four A slots of 24 columns (planes nm, hom, x).  Three UMMAs (N = 192, 64, 128) = 192 tensor clk per
+// [384,504) five A slots of 24 columns (planes nm, hom, x).  Three UMMAs (N = 192, 64, 128) = 192 tensor clk per
 // k-step.  All founders are contracted inside one CTA, so nothing is accumulated in HBM: the epilogue turns the
 // six int32 sums of each pair into the 1-byte decision the host-side greedy walk looks up.
 //
@@ -33,7 +33,7 @@ constexpr uint32_t kLdtRows = 128;                 // second variants per tile
 constexpr uint32_t kLdtCols = 64;                  // first variants per tile
 constexpr uint32_t kLdtBoxBytes = 16;              // 64 founders = one stage = two k-steps
 constexpr uint32_t kLdtAccCols = 6 * kLdtCols;     // 384
-constexpr uint32_t kLdtASlots = 4;
+constexpr uint32_t kLdtASlots = 5;                 // 384 + 5 x 24 = 504 columns; the slot hand-off (~750 clk) must stay below (slots - 1) x 192 clk
 constexpr uint32_t kLdtASlotCols = 24;
 constexpr uint32_t kLdtStagesB = 4;
 constexpr uint32_t kLdtPlaneBytes = kLdtCols * 64; // one plane of one stage: 64 variants x 64 K-bytes = 4096

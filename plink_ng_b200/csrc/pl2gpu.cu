@@ -460,7 +460,7 @@ uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32
   const uint64_t tiles = CountTiles(row_start, row_end, false);
   const uint64_t npad = RoundUpU32(sample_ct, kSamplePad);
   const uint64_t need_ss = tiles * kKingTileAccWords * 4 + cap * (npad / 4) + 3ull * (cap / 32) * npad * 4 + tiles * 16;
-  // TS tensor (the default): 128 x 80 tiles, two raw blocks + two row-side re-tiled copies of the job's row tiles
+  // TS tensor (the default): 128 x 64 tiles, two raw blocks + two row-side re-tiled copies of the job's row tiles
   const uint64_t tiles_ts = CountTiles(row_start, row_end, false, kTsCols);
   const uint64_t npad_ts = RoundUpU32(sample_ct, kTsSamplePad);
   const uint64_t row_tiles = row_end > row_start ? (DivUpU32(row_end, kTileRows) - row_start / kTileRows) : 0;

@@ -82,6 +82,7 @@ template <uint32_t kId, uint32_t kThreads>
 __device__ __forceinline__ void named_bar_sync() {
   asm volatile("bar.sync %0, %1;" ::"n"(kId), "n"(kThreads) : "memory");
 }
+__device__ __forceinline__ void sts64(uint32_t addr, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory"); }
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ void prefetch_tensormap(const void* tensor_map) { asm volatile("prefetch.tensormap [%0];" ::"l"(tensor_map) : "memory"); }
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {

@@ -109,3 +109,9 @@ open("b.fam", "w").write("".join(f"f{k}\ti{k}\t0\t0\t{1 + k % 2}\t-9\n" for k in
 PY
 $P --bfile b --make-pgen --out $T/b --threads 1 > /dev/null
 cp $T/b.pgen b_mode10.pgen; cp $T/b.pvar b.pvar; cp $T/b.psam b.psam
+# --- set Q: rare-variant pre-scan accounting of the reference's KING table (NSNP), inputs from make_quirk_set.py
+python make_quirk_set.py
+$P --bfile q --make-king-table counts cols=+ibs1,+ibs --threads 2 --out $T/q_king > /dev/null
+cp $T/q_king.kin0 q_king.kin0
+$P --bfile q --make-king-table --king-table-filter -0.2 --threads 2 --out $T/q_kingp > /dev/null
+cp $T/q_kingp.kin0 q_kingp.kin0

@@ -57,6 +57,16 @@ def test_king_table_filter_byte_identical(golden_dir, tmp_path):
     assert "--king-table-filter: 662 relationships reported (4288 filtered out)." in log
 
 
+def test_king_table_rare_variant_prescan_nsnp_byte_identical(golden_dir, tmp_path):
+    """Set Q: the reference's rare-variant pre-scan makes NSNP (and the proportion columns divided by it) one higher for
+    (other homozygote, missing) pairs; the host program reproduces that (SparseNsnpFix), counts and proportions."""
+    for flags, gold in ((["--make-king-table", "counts", "cols=+ibs1,+ibs"], "q_king.kin0"), (["--make-king-table", "--king-table-filter", "-0.2"], "q_kingp.kin0")):
+        out = str(tmp_path / "q")
+        r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "q")] + flags + ["--out", out], capture_output=True, text=True, env=ENV)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert open(out + ".kin0", "rb").read() == open(os.path.join(golden_dir, gold), "rb").read(), gold
+
+
 def test_king_table_subset_byte_identical(golden_dir, tmp_path):
     """--king-table-subset (pair-list kernel): the reference's own .kin0 as the pair list + kinship threshold, and a
     hand-written IID-only list with swapped orientation and an unknown ID."""

@@ -10,7 +10,7 @@ from bench import ClockSampler
 
 out = {}
 with p.GpuContext(0) as ctx:
-    for name, n, form, secs in (("ts_n160", 160, 1, 2.5), ("ts_n80", 80, 1, 1.0), ("ss_n240", 240, 0, 2.5), ("ss_n160", 160, 0, 1.0)):
+    for name, n, form, secs in (("ts_n128", 128, 1, 2.5), ("ts_n64", 64, 1, 1.0), ("ts_n192", 192, 1, 1.0), ("ss_n240", 240, 0, 2.5)):
         s = ClockSampler(0)
         s.start()
         tops, t = ctx.int8_peak(n, form, secs)
