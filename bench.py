@@ -330,6 +330,48 @@ def secondary_legs(args, torch, p, ctx, dev, peak_tops):
                 shutil.rmtree(tmp, ignore_errors=True)
     except Exception as ex:
         sec["grm"]["cpu_baseline"] = {"error": str(ex)[-200:]}
+    # --pca approx (randomized range finder over the resident 2-bit matrix): the library call the host program makes
+    try:
+        import ctypes as C
+
+        from plink_ng_b200.capi import check, lib
+
+        n3, m3, k3 = min(args.samples, 16384), 65536, 20
+        g3 = synth_genovecs(torch, n3, 0, m3, dev)
+        g1 = np.random.default_rng(1).standard_normal((n3, 2 * k3))
+        h = C.c_void_p()
+        check(lib.pl2gpu_pca_begin(ctx.handle, n3, m3, k3, C.byref(h)), "pl2gpu_pca_begin")
+        try:
+            check(lib.pl2gpu_pca_add_variants(h, C.c_void_p(g3.data_ptr()), g3.shape[1], m3, 1, None), "pl2gpu_pca_add_variants")
+            vals, vecs = np.empty(k3), np.empty((k3, n3))
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            check(lib.pl2gpu_pca_run(h, g1.ctypes.data, vals.ctypes.data, vecs.ctypes.data), "pl2gpu_pca_run")
+            dt = time.perf_counter() - t0
+        finally:
+            lib.pl2gpu_pca_end(h)
+        col_products = 2 * k3 * (3 * k3 + 2)  # (k+1) x 2k XA columns + k x 2k and 2k(k+1) XtB columns
+        sec["pca"] = {"workload": f"--pca {k3} approx core (pl2gpu_pca_run: {k3 + 1} Y.G passes, {k3} Yt.H passes, Krylov SVD, Yt.Q, final SVD) on {n3} samples x {m3} variants, genotypes resident",
+                      "seconds": dt, "fma_equiv_per_s": n3 * m3 * col_products / dt, "column_products": col_products, "top_eigenvalue": float(vals[0])}
+        del g3
+    except Exception as ex:
+        sec["pca"] = {"error": str(ex)[-300:]}
+    try:
+        lap = os.path.join(ROOT, "oracle", "_ref", "plink2_lapack")
+        if os.path.exists(lap) and "pca" in sec and "error" not in sec["pca"]:
+            nc, mc = 8192, 32768
+            tmp = tempfile.mkdtemp(prefix="pl2pca_")
+            try:
+                prefix = os.path.join(tmp, "g")
+                write_synth_bed(prefix, nc, mc)
+                threads = effective_cores()["threads_used"]
+                dt = run_cli(lap, prefix, prefix + "_out", ["--pca", "20", "approx"], threads)
+                sec["pca"]["cpu_baseline"] = {"kind": "reference", "binary": "oracle/_ref/plink2_lapack (OpenBLAS)", "cores": threads, "seconds": dt,
+                                              "sample": f"{nc} samples x {mc} variants, whole `--pca 20 approx` run", "fma_equiv_per_s": nc * mc * 2 * 20 * 62 / dt}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as ex:
+        sec["pca"]["cpu_baseline"] = {"error": str(ex)[-200:]}
     return sec
 
 

@@ -136,32 +136,32 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
       r.w[1] = lds64(ring_i + si * kGtsRawIBytes + (grp + 2) * (kTileRows * 8));
       return r;  // released after both words went through tcgen05.st (king_ts_kernel.cuh explains why)
     };
+    // both k-steps of a ring slot are stored under ONE tcgen05.wait::st, and the next slot's words are expanded while
+    // those stores are in flight (king_ts_kernel.cuh explains why)
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4 (variant pad 256)
     Words words = load_slot(0);
-    ExpI cur = expand_i(words.w[0]);
     for (uint32_t q = 0; q < slot_iters; ++q) {
-#pragma unroll
-      for (uint32_t h = 0; h < 2; ++h) {
-        const uint32_t ks = 4 * q + grp + 2 * h;
-        const uint32_t slot = ks % kGtsASlots;
-        mbar_wait(&bar_empty_a[slot], ((ks / kGtsASlots) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t ta = ta0 + slot * kGtsASlotCols;
-        tmem_st8(ta, cur.v[0]);
-        tmem_st8(ta + 8, cur.v[1]);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&bar_full_a[slot], lane);
-        if (h == 0) {
-          cur = expand_i(words.w[1]);
-        } else {
-          mbar_arrive_warp(&bar_empty_ri[q % kGtsRawISlots], lane);
-          if (q + 1 < slot_iters) {
-            words = load_slot(q + 1);
-            cur = expand_i(words.w[0]);
-          }
-        }
+      const uint32_t ks0 = 4 * q + grp, ks1 = ks0 + 2;
+      const uint32_t s0 = ks0 % kGtsASlots, s1 = ks1 % kGtsASlots;
+      mbar_wait(&bar_empty_a[s0], ((ks0 / kGtsASlots) & 1) ^ 1);
+      mbar_wait(&bar_empty_a[s1], ((ks1 / kGtsASlots) & 1) ^ 1);
+      tc_fence_after_sync();
+      {
+        const ExpI e = expand_i(words.w[0]);
+        tmem_st8(ta0 + s0 * kGtsASlotCols, e.v[0]);
+        tmem_st8(ta0 + s0 * kGtsASlotCols + 8, e.v[1]);
       }
+      {
+        const ExpI e = expand_i(words.w[1]);
+        tmem_st8(ta0 + s1 * kGtsASlotCols, e.v[0]);
+        tmem_st8(ta0 + s1 * kGtsASlotCols + 8, e.v[1]);
+      }
+      mbar_arrive_warp(&bar_empty_ri[q % kGtsRawISlots], lane);  // both words went through tcgen05.st
+      if (q + 1 < slot_iters) words = load_slot(q + 1);
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive_warp(&bar_full_a[s0], lane);
+      mbar_arrive_warp(&bar_full_a[s1], lane);
     }
   } else if (warp < kGtsRowWarps + kGtsColWarps) {
     // ---------------- column-side producers: 2-bit words -> 11 int8 planes in shared memory ----------------

@@ -150,37 +150,40 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
       r.w[1] = lds64(ring_i + si * kTsRawIBytes + (grp + 2) * (kTileRows * 8));
       return r;  // the slot is released only after both words have gone through tcgen05.st (see below)
     };
+    // tcgen05.st -> tcgen05.wait::st is a ~300-clk round trip, and a warp that handled ONE k-step per round trip
+    // capped the whole kernel at ~230 clk per k-step (two groups) whatever the UMMA width.  So both k-steps of a ring
+    // slot are stored under one wait (the second expansion and the next slot's loads overlap the stores in flight).
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4
     Words words = load_slot(0);
-    ExpI cur = expand_i(words.w[0]);
     for (uint32_t q = 0; q < slot_iters; ++q) {
-#pragma unroll
-      for (uint32_t h = 0; h < 2; ++h) {
-        const uint32_t ks = 4 * q + grp + 2 * h;
-        const uint32_t slot = ks % kTsASlots;
-        mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
-        tc_fence_after_sync();
-        const uint32_t ta = taddr_lane + slot * kTsASlotCols;
-        tmem_st8(ta, cur.v[0]);
-        tmem_st8(ta + 8, cur.v[1]);
-        tmem_st8(ta + 16, cur.v[2]);
-        tmem_st_wait();
-        tc_fence_before_sync();
-        mbar_arrive_warp(&bar_full_a[slot], lane);
-        if (h == 0) {
-          cur = expand_i(words.w[1]);
-        } else {
-          // Release the ring slot HERE: the warp-collective tcgen05.st above could only issue once every lane's
-          // expanded registers - hence both ld.shared results - were complete.  (Releasing right after the loads
-          // is a race: the arrive can overtake a queued ld.shared, the producer refills the slot, and half a
-          // warp reads the next revolution's words - seen as 16-sample groups with slightly wrong counts.)
-          mbar_arrive_warp(&bar_empty_ri[q % kTsRawISlots], lane);
-          if (q + 1 < slot_iters) {
-            words = load_slot(q + 1);
-            cur = expand_i(words.w[0]);
-          }
-        }
+      const uint32_t ks0 = 4 * q + grp, ks1 = ks0 + 2;
+      const uint32_t s0 = ks0 % kTsASlots, s1 = ks1 % kTsASlots;
+      mbar_wait(&bar_empty_a[s0], ((ks0 / kTsASlots) & 1) ^ 1);
+      mbar_wait(&bar_empty_a[s1], ((ks1 / kTsASlots) & 1) ^ 1);
+      tc_fence_after_sync();
+      const uint32_t ta0 = taddr_lane + s0 * kTsASlotCols, ta1 = taddr_lane + s1 * kTsASlotCols;
+      {
+        const ExpI e = expand_i(words.w[0]);
+        tmem_st8(ta0, e.v[0]);
+        tmem_st8(ta0 + 8, e.v[1]);
+        tmem_st8(ta0 + 16, e.v[2]);
       }
+      {
+        const ExpI e = expand_i(words.w[1]);  // runs while the first k-step's stores are in flight
+        tmem_st8(ta1, e.v[0]);
+        tmem_st8(ta1 + 8, e.v[1]);
+        tmem_st8(ta1 + 16, e.v[2]);
+      }
+      // Release the ring slot HERE: the warp-collective tcgen05.st above could only issue once every lane's expanded
+      // registers - hence both ld.shared results - were complete.  (Releasing right after the loads is a race: the
+      // arrive can overtake a queued ld.shared, the producer refills the slot, and half a warp reads the next
+      // revolution's words - seen as 16-sample groups with slightly wrong counts.)
+      mbar_arrive_warp(&bar_empty_ri[q % kTsRawISlots], lane);
+      if (q + 1 < slot_iters) words = load_slot(q + 1);  // latency hidden behind the store round trip
+      tmem_st_wait();
+      tc_fence_before_sync();
+      mbar_arrive_warp(&bar_full_a[s0], lane);
+      mbar_arrive_warp(&bar_full_a[s1], lane);
     }
   } else if (warp < kTsIssuerWarp) {
     // ---------------- column-side producers: 2-bit words -> int8 planes in shared memory ----------------

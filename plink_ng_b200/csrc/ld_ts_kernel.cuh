@@ -127,10 +127,12 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
     struct ExpI {
       uint32_t v[3][8];
     };
-    auto fetch = [&](uint32_t n) -> ExpI {
+    auto fetch = [&](uint32_t n) -> uint2 {
       const uint32_t sa = n % kLdtRawASlots;
       mbar_wait(&bar_full_ra[sa], (n / kLdtRawASlots) & 1);
-      const uint2 w = lds64(ring_a + sa * kLdtRawABytes);
+      return lds64(ring_a + sa * kLdtRawABytes);  // the ring slot is released after the tcgen05.st of the expansion (see king_ts_kernel.cuh)
+    };
+    auto expand_i = [&](const uint2& w) -> ExpI {
       ExpI e;
       const Sel4 s0 = make_selectors(w.x), s1 = make_selectors(w.y);
       const uint32_t tabs[3] = {tab_nm, tab_hom, tab_x};
@@ -140,23 +142,26 @@ ld_ts_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__
         e.v[p][0] = a.x; e.v[p][1] = a.y; e.v[p][2] = a.z; e.v[p][3] = a.w;
         e.v[p][4] = b.x; e.v[p][5] = b.y; e.v[p][6] = b.z; e.v[p][7] = b.w;
       }
-      return e;  // the ring slot is released after the tcgen05.st of these registers (see king_ts_kernel.cuh)
+      return e;
     };
-    ExpI cur = fetch(0);
+    // the next box is fetched and expanded while this k-step's tensor-memory stores are in flight (the
+    // tcgen05.st -> wait::st round trip, ~300 clk, would otherwise bound each group to one k-step per round trip)
+    uint2 w = fetch(0);
     for (uint32_t n = 0; n < stage_iters; ++n) {
       const uint32_t ks = 2 * n + grp;
       const uint32_t slot = ks % kLdtASlots;
+      const ExpI cur = expand_i(w);
       mbar_wait(&bar_empty_a[slot], ((ks / kLdtASlots) & 1) ^ 1);
       tc_fence_after_sync();
       const uint32_t ta = taddr_lane + slot * kLdtASlotCols;
       tmem_st8(ta, cur.v[0]);
       tmem_st8(ta + 8, cur.v[1]);
       tmem_st8(ta + 16, cur.v[2]);
+      mbar_arrive_warp(&bar_empty_ra[n % kLdtRawASlots], lane);  // box n consumed: its words went through tcgen05.st
+      if (n + 1 < stage_iters) w = fetch(n + 1);
       tmem_st_wait();
       tc_fence_before_sync();
       mbar_arrive_warp(&bar_full_a[slot], lane);
-      mbar_arrive_warp(&bar_empty_ra[n % kLdtRawASlots], lane);  // box n consumed: its words went through tcgen05.st
-      if (n + 1 < stage_iters) cur = fetch(n + 1);
     }
   } else if (warp < kLdtIssuerWarp) {
     // ---------------- column side: the "first" variants; thread = (variant, 16-founder word of the stage) ----------------
