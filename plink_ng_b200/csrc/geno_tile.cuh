@@ -1,19 +1,19 @@
 // geno_tile.cuh - operand re-tiling for the "TS" tensor kernels (king_ts_kernel.cuh, grm_ts_kernel.cuh):
-// 128-row x 64-column pair tiles, row operand expanded into tensor memory, column operand into
+// 128-row x 80-column pair tiles, row operand expanded into tensor memory, column operand into
 // shared memory.  Kernels are static (header is included by several translation units).
 #pragma once
 #include "common.cuh"
 
 namespace pl2 {
 
-// 128 x 64 pair tiles: 5 (KING) / 6 (GRM) int32 accumulators take 320 / 384 of the 512 tensor-memory columns and
-// leave room for EIGHT row-operand slots.  With 80-column tiles only 4 (KING) / 2 (GRM) slots fit, and the slot
-// hand-off (tcgen05.commit -> mbarrier -> tcgen05.st -> mbarrier -> next UMMA, ~750 clk) is then longer than the
-// 3 (1) queued k-steps: the issuer was waiting for row slots 2.2 times per k-step (profiles/r02_ncu_king_ts.md).
-constexpr uint32_t kTsCols = 64;
-constexpr uint32_t kTsSamplePad = 128;  // lcm(128, 64)
+// 128 x 80 pair tiles.  Narrower tiles (128 x 64, eight row-operand slots instead of four) were measured and are
+// SLOWER (26.7 vs 24.2 ms per 16,384 x 65,536 batch): every k-step pays ~12 KB of tcgen05.st into tensor memory
+// (256 B/clk, ~48 clk) on top of its UMMA time whatever the tile width, so the widest tile that still leaves room
+// for a slot ring wins (profiles/r02_king_tile_width.md).
+constexpr uint32_t kTsCols = 80;
+constexpr uint32_t kTsSamplePad = 640;  // lcm(128, 80)
 constexpr uint32_t kTsKcJ = 64;         // variants per shared-memory stage (two k-steps)
-constexpr uint32_t kTsRawBoxBytes = 16; // inner extent of the TMA box over the raw block: the tile's 64 samples
+constexpr uint32_t kTsRawBoxBytes = 32; // inner extent of the TMA box over the raw block (>= 20 bytes = 80 samples, multiple of 16)
 
 // ---- operand re-tiling of the staged block raw[variant][pitch] (2-bit, variant-major) -------------
 // Both copies make every producer load of king_ts_kernel a contiguous run of bytes (the first TS

@@ -25,8 +25,8 @@
 
 namespace pl2 {
 
-constexpr uint32_t kGrmTileCols = 64;           // see geno_tile.cuh: leaves room for eight row-operand slots in tensor memory
-constexpr uint32_t kGrmSamplePad = 128;         // lcm(128, 64)
+constexpr uint32_t kGrmTileCols = 80;
+constexpr uint32_t kGrmSamplePad = 640;         // lcm(128, 80)
 constexpr uint32_t kGrmLimbs = 5;
 constexpr uint32_t kGrmFixedBits = 38;          // |L| * 2^F < 2^38
 constexpr uint32_t kGrmPlanesJ = 2 * kGrmLimbs + 1;

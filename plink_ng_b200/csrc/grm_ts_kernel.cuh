@@ -5,9 +5,9 @@
 // shared memory per 440 tensor clocks (127 B/clk of the 128 B/clk available) and sat at 45 % of the
 // tensor pipe.
 //
-// Tile = 128 rows x 64 cols.  TMEM columns: [0,320) digit accumulators D_0..D_4, [320,384) obs counts,
-// [384,512) eight A slots of 16 columns (planes g, m; 8 columns = 32 K-bytes per lane).
-// Per 32 variants (6 UMMAs, 352 tensor clk):  m x [d2_0 d2_1], m x [d2_2 d2_3], m x [d2_4 | m] (N = 128,
+// Tile = 128 rows x 80 cols.  TMEM columns: [0,400) digit accumulators D_0..D_4, [400,480) obs counts,
+// [480,512) two A slots of 16 columns (planes g, m; 8 columns = 32 K-bytes per lane).
+// Per 32 variants (6 UMMAs, 440 tensor clk):  m x [d2_0 d2_1], m x [d2_2 d2_3], m x [d2_4 | m] (N = 160,
 // lands on D_4 and obs), g x [d1_0 d1_1], g x [d1_2 d1_3], g x d1_4.  The m products are issued first so
 // that on the very first k-step they zero-initialise every accumulator (accumulate = 0) and the g
 // products always accumulate.
@@ -23,27 +23,27 @@
 namespace pl2 {
 
 static_assert(kGrmTileCols == kTsCols && kGrmSamplePad == kTsSamplePad && kGrmKc == kTsKcJ, "GRM TS kernel shares the KING TS tiling");
-constexpr uint32_t kGtsAccCols = (kGrmLimbs + 1) * kGrmTileCols;          // 384
-constexpr uint32_t kGtsASlots = 8;                                         // 8 x 16 columns: [384, 512)
+constexpr uint32_t kGtsAccCols = (kGrmLimbs + 1) * kGrmTileCols;          // 480
+constexpr uint32_t kGtsASlots = 2;
 constexpr uint32_t kGtsASlotCols = 16;
 constexpr uint32_t kGtsStagesJ = 3;
-constexpr uint32_t kGtsLboJ = kGrmPlanesJ * kGrmGroupsJ * kCoreBytes + 64;  // 5696: +64 keeps the K-permuted rows bank-conflict free
-constexpr uint32_t kGtsStageBytesJ = (kGrmKc / 8) * kGtsLboJ;               // 45568
+constexpr uint32_t kGtsLboJ = kGrmPlanesJ * kGrmGroupsJ * kCoreBytes + 64;  // 7104: +64 keeps the K-permuted rows bank-conflict free
+constexpr uint32_t kGtsStageBytesJ = (kGrmKc / 8) * kGtsLboJ;               // 56832
 // Operand staging as in king_ts_kernel.cuh: one producer warp keeps three shared-memory rings full with the TMA
 // unit - raw column boxes read in place from the variant-major block through a tensor map (UTMALDG), row-side
 // k-steps of the sample-major copy, and the per-variant digit tables (both UBLKCP).
 constexpr uint32_t kGtsRawJSlots = 4;
-constexpr uint32_t kGtsRawJBytes = kGrmKc * kTsRawBoxBytes;                 // 1024
+constexpr uint32_t kGtsRawJBytes = kGrmKc * kTsRawBoxBytes;                 // 2048
 constexpr uint32_t kGtsRawISlots = 2;                                       // four row-side k-steps per 4 KB copy
 constexpr uint32_t kGtsRawIBytes = 4 * kTileRows * 8;                       // 4096
 constexpr uint32_t kGtsTabSlots = 4;
 constexpr uint32_t kGtsTabBytes = kGrmTabPlanes * kGrmKc * 4;               // 3072
-constexpr uint32_t kGtsSmemOffRawJ = kGtsStagesJ * kGtsStageBytesJ;         // 136704 (multiple of 128)
+constexpr uint32_t kGtsSmemOffRawJ = kGtsStagesJ * kGtsStageBytesJ;         // 170496 (multiple of 128)
 constexpr uint32_t kGtsSmemOffRawI = kGtsSmemOffRawJ + kGtsRawJSlots * kGtsRawJBytes;
 constexpr uint32_t kGtsSmemOffTab = kGtsSmemOffRawI + kGtsRawISlots * kGtsRawIBytes;
 constexpr uint32_t kGtsSmemBytes = kGtsSmemOffTab + kGtsTabSlots * kGtsTabBytes + 1024;
 constexpr uint32_t kGtsRowWarps = 8;
-constexpr uint32_t kGtsColWarps = 8;                                        // 4 words x 64 variants per stage
+constexpr uint32_t kGtsColWarps = 10;                                       // 5 words x 64 variants per stage
 constexpr uint32_t kGtsIssuerWarp = kGtsRowWarps + kGtsColWarps;
 constexpr uint32_t kGtsThreads = 32 * (kGtsRowWarps + kGtsColWarps + 2);    // + UMMA issuer + TMA producer
 static_assert(kGtsSmemOffRawJ % 128 == 0, "TMA destination alignment (128 bytes without swizzle)");
@@ -101,14 +101,14 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
 
   if (warp < kGtsRowWarps) {
     // ---------------- row-side producers: 2-bit words -> registers -> tensor memory ----------------
-    // Group g = warp / 4 owns k-steps ks = 2 n + g and the A slots ks % 8 of its parity.  Thread = TMEM lane = sample.
+    // Group g = warp / 4 owns k-steps ks = 2 n + g and A slot g.  Thread = TMEM lane = sample.
     const uint32_t grp = warp >> 2;
     const uint32_t lq = warp & 3;
     const uint32_t row = 32 * lq + lane;
     const uint32_t thread_zero = tid * (variant_ct_padded >> 31);  // 0; keeps the tables in vector registers (geno_expand.cuh)
     const uint32_t tab_g = table_reg(kTabDosage, thread_zero), tab_m = table_reg(kTabNonmiss, thread_zero);
     const uint32_t ring_i = smem_base + kGtsSmemOffRawI + row * 8;
-    const uint32_t ta0 = tmem_base + ((32u * lq) << 16) + kGtsAccCols;
+    const uint32_t ta = tmem_base + ((32u * lq) << 16) + kGtsAccCols + grp * kGtsASlotCols;
     struct ExpI {
       uint32_t v[2][8];
     };
@@ -136,42 +136,40 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
       r.w[1] = lds64(ring_i + si * kGtsRawIBytes + (grp + 2) * (kTileRows * 8));
       return r;  // released after both words went through tcgen05.st (king_ts_kernel.cuh explains why)
     };
-    // both k-steps of a ring slot are stored under ONE tcgen05.wait::st, and the next slot's words are expanded while
-    // those stores are in flight (king_ts_kernel.cuh explains why)
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4 (variant pad 256)
     Words words = load_slot(0);
+    ExpI cur = expand_i(words.w[0]);
     for (uint32_t q = 0; q < slot_iters; ++q) {
-      const uint32_t ks0 = 4 * q + grp, ks1 = ks0 + 2;
-      const uint32_t s0 = ks0 % kGtsASlots, s1 = ks1 % kGtsASlots;
-      mbar_wait(&bar_empty_a[s0], ((ks0 / kGtsASlots) & 1) ^ 1);
-      mbar_wait(&bar_empty_a[s1], ((ks1 / kGtsASlots) & 1) ^ 1);
-      tc_fence_after_sync();
-      {
-        const ExpI e = expand_i(words.w[0]);
-        tmem_st8(ta0 + s0 * kGtsASlotCols, e.v[0]);
-        tmem_st8(ta0 + s0 * kGtsASlotCols + 8, e.v[1]);
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t n = 2 * q + h;  // k-step 2 n + grp
+        mbar_wait(&bar_empty_a[grp], (n & 1) ^ 1);
+        tc_fence_after_sync();
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[grp], lane);
+        if (h == 0) {
+          cur = expand_i(words.w[1]);
+        } else {
+          mbar_arrive_warp(&bar_empty_ri[q % kGtsRawISlots], lane);
+          if (q + 1 < slot_iters) {
+            words = load_slot(q + 1);
+            cur = expand_i(words.w[0]);
+          }
+        }
       }
-      {
-        const ExpI e = expand_i(words.w[1]);
-        tmem_st8(ta0 + s1 * kGtsASlotCols, e.v[0]);
-        tmem_st8(ta0 + s1 * kGtsASlotCols + 8, e.v[1]);
-      }
-      mbar_arrive_warp(&bar_empty_ri[q % kGtsRawISlots], lane);  // both words went through tcgen05.st
-      if (q + 1 < slot_iters) words = load_slot(q + 1);
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive_warp(&bar_full_a[s0], lane);
-      mbar_arrive_warp(&bar_full_a[s1], lane);
     }
   } else if (warp < kGtsRowWarps + kGtsColWarps) {
     // ---------------- column-side producers: 2-bit words -> 11 int8 planes in shared memory ----------------
     // Thread = (word w of the 20-byte row, variant k of the 64-variant stage); the per-variant digit
     // tables come from grm_tables_kernel.
-    const uint32_t t = tid - 32 * kGtsRowWarps;  // 0..255
-    const uint32_t combo = t >> 3;               // (k group of 8) * 4 + word: see king_ts_kernel.cuh
-    const uint32_t k = 8 * (combo / 4) + (t & 7);
-    const uint32_t w = combo % 4;
-    const uint32_t ring_j = smem_base + kGtsSmemOffRawJ + k * kTsRawBoxBytes + 4 * w;
+    const uint32_t t = tid - 32 * kGtsRowWarps;  // 0..319
+    const uint32_t combo = t >> 3;               // (k group of 8) * 5 + word: see king_ts_kernel.cuh
+    const uint32_t k = 8 * (combo / 5) + (t & 7);
+    const uint32_t w = combo % 5;
+    const uint32_t ring_j = smem_base + kGtsSmemOffRawJ + k * kTsRawBoxBytes + ((ct * (kGrmTileCols / 4)) & 15u) + 4 * w;  // box starts 16-byte aligned
     const uint32_t ring_t = smem_base + kGtsSmemOffTab + 4 * k;  // tab[slot][plane][64 variants] (grm_tab_index)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);  // K rows in the PRMT position order of the row side
     const uint32_t dst_k = (kpos >> 3) * kGtsLboJ + (kpos & 7) * 16 + w * kCoreBytes;
@@ -210,8 +208,8 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
     }
   } else if (warp == kGtsIssuerWarp) {
     // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
-    constexpr uint32_t idesc_n2 = make_idesc_i8(128, 2 * kGrmTileCols, false, true);
-    constexpr uint32_t idesc_n1 = make_idesc_i8(128, kGrmTileCols, false, true);
+    constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kGrmTileCols, false, true);
+    constexpr uint32_t idesc_n80 = make_idesc_i8(128, kGrmTileCols, false, true);
     constexpr uint32_t kPlaneStep = (kGrmGroupsJ * kCoreBytes) >> 4;  // plane step in descriptor units
     const uint32_t tmem_u = uniform_u32(tmem_base);
     const uint64_t desc0 = make_smem_desc(smem_base, kGtsLboJ, kCoreBytes);
@@ -220,23 +218,21 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
       mbar_wait(&bar_full_b[sb], ph);
 #pragma unroll
       for (uint32_t kk = 0; kk < 2; ++kk) {
-        // k-step ks = 2 it + kk lives in A slot ks % 8
-        const uint32_t ks = 2 * it + kk;
-        const uint32_t slot = ks % kGtsASlots;
-        mbar_wait(&bar_full_a[slot], (ks / kGtsASlots) & 1);
+        // k-step ks = 2 it + kk lives in A slot kk, round it
+        mbar_wait(&bar_full_a[kk], it & 1);
         tc_fence_after_sync();
         if (elect_one_sync()) {
           const uint32_t acc = (it | kk) ? 1u : 0u;  // 0 only on the very first k-step
           const uint64_t bj = desc0 + ((sb * kGtsStageBytesJ + kk * 4 * kGtsLboJ) >> 4);
-          const uint32_t a_g = tmem_u + kGtsAccCols + slot * kGtsASlotCols;
+          const uint32_t a_g = tmem_u + kGtsAccCols + kk * kGtsASlotCols;
           const uint32_t a_m = a_g + 8;
-          umma_i8_ts(tmem_u + 0, a_m, bj + 5 * kPlaneStep, idesc_n2, acc);                    // m x [d2_0 d2_1]
-          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_m, bj + 7 * kPlaneStep, idesc_n2, acc);     // m x [d2_2 d2_3]
-          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_m, bj + 9 * kPlaneStep, idesc_n2, acc);     // m x [d2_4 | m] -> D_4, obs
-          umma_i8_ts(tmem_u + 0, a_g, bj, idesc_n2, 1u);                                        // g x [d1_0 d1_1]
-          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_g, bj + 2 * kPlaneStep, idesc_n2, 1u);        // g x [d1_2 d1_3]
-          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_g, bj + 4 * kPlaneStep, idesc_n1, 1u);         // g x d1_4
-          umma_commit(&bar_empty_a[slot]);
+          umma_i8_ts(tmem_u + 0, a_m, bj + 5 * kPlaneStep, idesc_n160, acc);                    // m x [d2_0 d2_1]
+          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_m, bj + 7 * kPlaneStep, idesc_n160, acc);     // m x [d2_2 d2_3]
+          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_m, bj + 9 * kPlaneStep, idesc_n160, acc);     // m x [d2_4 | m] -> D_4, obs
+          umma_i8_ts(tmem_u + 0, a_g, bj, idesc_n160, 1u);                                        // g x [d1_0 d1_1]
+          umma_i8_ts(tmem_u + 2 * kGrmTileCols, a_g, bj + 2 * kPlaneStep, idesc_n160, 1u);        // g x [d1_2 d1_3]
+          umma_i8_ts(tmem_u + 4 * kGrmTileCols, a_g, bj + 4 * kPlaneStep, idesc_n80, 1u);         // g x d1_4
+          umma_commit(&bar_empty_a[kk]);
           if (kk == 1) umma_commit(&bar_empty_b[sb]);
         }
         __syncwarp();
@@ -253,7 +249,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
     if (elect_one_sync()) {
       const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * (kTileRows * 8);
       const uint32_t ring_j = smem_base + kGtsSmemOffRawJ, ring_i = smem_base + kGtsSmemOffRawI, ring_t = smem_base + kGtsSmemOffTab;
-      const int32_t c0 = static_cast<int32_t>(ct * (kGrmTileCols / 4));
+      const int32_t c0 = static_cast<int32_t>((ct * (kGrmTileCols / 4)) & ~15u);
       for (uint32_t it = 0; it < stage_iters; ++it) {
         if (!(it & 1)) {
           const uint32_t q = it >> 1, si = q % kGtsRawISlots;
@@ -285,7 +281,7 @@ grm_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __res
     const uint32_t rsample = 32 * lane_grp + lane;  // rows are in natural sample order here
     const uint32_t stage_g = smem_base + rsample * 8, stage_o = smem_base + kStageG + rsample * 4;
     const uint32_t taddr = tmem_base + ((32u * lane_grp) << 16);
-    // 4 column groups of 16: warps 0-3 take groups {0,2}, warps 4-7 take {1,3}
+    // 5 column groups of 16: warps 0-3 take groups {0,2,4}, warps 4-7 take {1,3}
 #pragma unroll 1
     for (uint32_t grp = warp >> 2; grp < kGrmGroupsJ; grp += 2) {
       const uint32_t c0 = grp * 16;

@@ -540,7 +540,7 @@ int TeamInit(Pl2GpuCtx* first, int first_device, uint32_t gpus, GpuTeam* team) {
 }
 
 // Rows [r0, r1) of the lower triangle cut into `parts` contiguous blocks whose interior boundaries are multiples
-// of the 128-row pair tile and which hold (nearly) the same number of 128 x 64 pair tiles - the unit the tensor
+// of the 128-row pair tile and which hold (nearly) the same number of 128 x 80 pair tiles - the unit the tensor
 // kernels' time is proportional to.  Blocks may be empty when the range holds fewer row tiles than parts.
 std::vector<uint32_t> TileAlignedBounds(uint32_t r0, uint32_t r1, uint32_t parts, bool include_diag) {
   std::vector<uint32_t> b(parts + 1, r1);
@@ -551,7 +551,7 @@ std::vector<uint32_t> TileAlignedBounds(uint32_t r0, uint32_t r1, uint32_t parts
   for (uint32_t rt = rt0; rt < rt1; ++rt) {
     const uint32_t row_end = std::min(r1, (rt + 1) * 128);
     const uint32_t cols = include_diag ? row_end : row_end - 1;
-    cum.push_back(cum.back() + (cols + 63) / 64);
+    cum.push_back(cum.back() + (cols + 79) / 80);
   }
   for (uint32_t k = 1; k < parts; ++k) {
     const double target = static_cast<double>(cum.back()) * k / parts;
@@ -1055,7 +1055,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   // variants per staged block: the full 65,536 unless the cap is so small that the two staged blocks would
   // eat most of it (then halve until they fit in a quarter of the budget)
   uint32_t batch = 65536;
-  while (batch > 2048 && 4ull * batch * ((n + 127) / 128 * 32) > budget / 4) batch /= 2;
+  while (batch > 2048 && 4ull * batch * ((n + 639) / 640 * 160) > budget / 4) batch /= 2;
   auto pass_fits = [&](uint32_t a, uint32_t b) {
     const std::vector<uint32_t> sb = TileAlignedBounds(a, b, G, false);
     for (uint32_t g = 0; g < G; ++g) {

@@ -5,14 +5,14 @@
 // available, profiles/r01_ncu_king_v1.md); here shared-memory traffic drops to ~100 B/clk and the
 // tensor pipe becomes the limiter.
 //
-// Tile = 128 rows x 64 cols.  TMEM columns: [0,320) accumulators TT|TH, HT|HH, SS (int32),
-// [320,512) EIGHT A slots of 24 columns (planes T, H, S; 8 columns = 32 K-bytes per lane).
-// Same products and the same raw accumulator semantics as king_tc_kernel (tile width 64).
+// Tile = 128 rows x 80 cols.  TMEM columns: [0,400) accumulators TT|TH, HT|HH, SS (int32),
+// [400,496) four A slots of 24 columns (planes T, H, S; 8 columns = 32 K-bytes per lane).
+// Same products and the same raw accumulator semantics as king_tc_kernel (tile width 80).
 //
 // Operand staging (round 2): one producer warp feeds two shared-memory rings with the TMA unit,
 //   * column side: the RAW variant-major 2-bit block is read in place through a 2-D tensor map
-//     (cp.async.bulk.tensor, SASS UTMALDG): box = 128 variants x 16 bytes at byte column 16 * ct (the
-//     tile's 64 samples) - no column re-tiling pass, no copy;
+//     (cp.async.bulk.tensor, SASS UTMALDG): box = 64 variants x 32 bytes at byte column 20 * ct (the
+//     tile's 80 samples are the first 20 bytes of each box row) - no column re-tiling pass, no copy;
 //   * row side: 1 KB bulk copies (UBLKCP) of the sample-major k-steps written by
 //     geno_tile_rows_kernel (the bit transpose CalcKing also needs, TransposeBitblock
 //     2.0/include/plink2_bits.cc:2065), restricted to the job's own row tiles.
@@ -28,30 +28,29 @@
 namespace pl2 {
 
 constexpr uint32_t kTsGroupsJ = kTsCols / 16;
-constexpr uint32_t kTsAccCols = 5 * kTsCols;   // 320
+constexpr uint32_t kTsAccCols = 5 * kTsCols;   // 400
 constexpr uint32_t kTsTileAccWords = kTsAccCols * kTileRows;
-constexpr uint32_t kTsASlots = 8;
+constexpr uint32_t kTsASlots = 4;
 constexpr uint32_t kTsASlotCols = 24;
 constexpr uint32_t kTsStagesJ = 4;
-constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1600: +64 keeps the K-permuted rows bank-conflict free
-constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 12800
+constexpr uint32_t kTsLboJ = (3 * kTsCols / 16) * kCoreBytes + 64;  // 1984: +64 keeps the K-permuted rows bank-conflict free
+constexpr uint32_t kTsStageBytesJ = (kTsKcJ / 8) * kTsLboJ;         // 15872
 // Both rings move 4 KB per copy (= 4 k-steps): the single producer lane spends ~3 mbarrier / TMA operations per
 // copy, and at one copy per k-step (first version: 34.2 ms vs 24.4 ms per 16,384 x 65,536 batch) it, not the
 // tensor pipe, set the pace.
-constexpr uint32_t kTsRawJSlots = 4;                                // TMA ring: raw column boxes (128 variants x 16 B = two stages)
-constexpr uint32_t kTsRawJBytes = 2 * kTsKcJ * kTsRawBoxBytes;      // 2048
+constexpr uint32_t kTsRawJSlots = 4;                                // TMA ring: raw column boxes (128 variants x 32 B = two stages)
+constexpr uint32_t kTsRawJBytes = 2 * kTsKcJ * kTsRawBoxBytes;      // 4096
 constexpr uint32_t kTsRawISlots = 4;                                // bulk-copy ring: four row-side k-steps (128 samples x 8 B each)
 constexpr uint32_t kTsRawIBytes = 4 * kTileRows * 8;                // 4096
-constexpr uint32_t kTsSmemOffRawJ = kTsStagesJ * kTsStageBytesJ;    // 51200 (multiple of 1024)
+constexpr uint32_t kTsSmemOffRawJ = kTsStagesJ * kTsStageBytesJ;    // 63488 (multiple of 1024)
 constexpr uint32_t kTsSmemOffRawI = kTsSmemOffRawJ + kTsRawJSlots * kTsRawJBytes;
 constexpr uint32_t kTsSmemBytes = kTsSmemOffRawI + kTsRawISlots * kTsRawIBytes + 1024;
 constexpr uint32_t kTsRowWarps = 8;
-constexpr uint32_t kTsColWarps = 8;            // 4 words x 64 variants per stage
+constexpr uint32_t kTsColWarps = 10;           // 5 words x 64 variants per stage
 constexpr uint32_t kTsIssuerWarp = kTsRowWarps + kTsColWarps;
 constexpr uint32_t kTsLoaderWarp = kTsIssuerWarp + 1;
 constexpr uint32_t kTsThreads = 32 * (kTsRowWarps + kTsColWarps + 2);  // + the UMMA issuer warp + the TMA producer warp
-static_assert(kTsSmemOffRawJ % 128 == 0, "TMA destination alignment");
-static_assert(kTsAccCols + kTsASlots * kTsASlotCols <= 512, "accumulators + A slots exceed tensor memory");
+static_assert(kTsSmemOffRawJ % 1024 == 0, "TMA destination alignment");
 
 __global__ void __launch_bounds__(kTsThreads, 1)
 king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __restrict__ raw_i, uint32_t row_tile_first, uint32_t variant_ct_padded /* multiple of 256 */, const uint32_t* __restrict__ tile_order, const uint32_t* __restrict__ tile_rt, const uint32_t* __restrict__ tile_tc, int32_t* __restrict__ raw_acc) {
@@ -114,8 +113,8 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
 
   if (warp < kTsRowWarps) {
     // ---------------- row-side producers: 2-bit words -> registers -> tensor memory ----------------
-    // Two groups of four warps (group = warp / 4); group g owns k-steps ks = 2 n + g, i.e. the A slots
-    // ks % 8 of its parity.  Thread = TMEM lane = sample 128 rt + 32 (warp % 4) + lane.  The words of
+    // Two groups of four warps (group = warp / 4); group g owns k-steps ks = 2 n + g and the A slots
+    // ks % 4 in {g, g + 2}.  Thread = TMEM lane = sample 128 rt + 32 (warp % 4) + lane.  The words of
     // the next k-step are expanded while the UMMAs of the previous ones run.
     const uint32_t grp = warp >> 2;
     const uint32_t lq = warp & 3;
@@ -150,51 +149,49 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
       r.w[1] = lds64(ring_i + si * kTsRawIBytes + (grp + 2) * (kTileRows * 8));
       return r;  // the slot is released only after both words have gone through tcgen05.st (see below)
     };
-    // tcgen05.st -> tcgen05.wait::st is a ~300-clk round trip, and a warp that handled ONE k-step per round trip
-    // capped the whole kernel at ~230 clk per k-step (two groups) whatever the UMMA width.  So both k-steps of a ring
-    // slot are stored under one wait (the second expansion and the next slot's loads overlap the stores in flight).
     const uint32_t slot_iters = stage_iters / 2;  // stage_iters is a multiple of 4
     Words words = load_slot(0);
+    ExpI cur = expand_i(words.w[0]);
     for (uint32_t q = 0; q < slot_iters; ++q) {
-      const uint32_t ks0 = 4 * q + grp, ks1 = ks0 + 2;
-      const uint32_t s0 = ks0 % kTsASlots, s1 = ks1 % kTsASlots;
-      mbar_wait(&bar_empty_a[s0], ((ks0 / kTsASlots) & 1) ^ 1);
-      mbar_wait(&bar_empty_a[s1], ((ks1 / kTsASlots) & 1) ^ 1);
-      tc_fence_after_sync();
-      const uint32_t ta0 = taddr_lane + s0 * kTsASlotCols, ta1 = taddr_lane + s1 * kTsASlotCols;
-      {
-        const ExpI e = expand_i(words.w[0]);
-        tmem_st8(ta0, e.v[0]);
-        tmem_st8(ta0 + 8, e.v[1]);
-        tmem_st8(ta0 + 16, e.v[2]);
+#pragma unroll
+      for (uint32_t h = 0; h < 2; ++h) {
+        const uint32_t ks = 4 * q + grp + 2 * h;
+        const uint32_t slot = ks % kTsASlots;
+        mbar_wait(&bar_empty_a[slot], ((ks / kTsASlots) & 1) ^ 1);
+        tc_fence_after_sync();
+        const uint32_t ta = taddr_lane + slot * kTsASlotCols;
+        tmem_st8(ta, cur.v[0]);
+        tmem_st8(ta + 8, cur.v[1]);
+        tmem_st8(ta + 16, cur.v[2]);
+        tmem_st_wait();
+        tc_fence_before_sync();
+        mbar_arrive_warp(&bar_full_a[slot], lane);
+        if (h == 0) {
+          cur = expand_i(words.w[1]);
+        } else {
+          // Release the ring slot HERE: the warp-collective tcgen05.st above could only issue once every lane's
+          // expanded registers - hence both ld.shared results - were complete.  (Releasing right after the loads
+          // is a race: the arrive can overtake a queued ld.shared, the producer refills the slot, and half a
+          // warp reads the next revolution's words - seen as 16-sample groups with slightly wrong counts.)
+          mbar_arrive_warp(&bar_empty_ri[q % kTsRawISlots], lane);
+          if (q + 1 < slot_iters) {
+            words = load_slot(q + 1);
+            cur = expand_i(words.w[0]);
+          }
+        }
       }
-      {
-        const ExpI e = expand_i(words.w[1]);  // runs while the first k-step's stores are in flight
-        tmem_st8(ta1, e.v[0]);
-        tmem_st8(ta1 + 8, e.v[1]);
-        tmem_st8(ta1 + 16, e.v[2]);
-      }
-      // Release the ring slot HERE: the warp-collective tcgen05.st above could only issue once every lane's expanded
-      // registers - hence both ld.shared results - were complete.  (Releasing right after the loads is a race: the
-      // arrive can overtake a queued ld.shared, the producer refills the slot, and half a warp reads the next
-      // revolution's words - seen as 16-sample groups with slightly wrong counts.)
-      mbar_arrive_warp(&bar_empty_ri[q % kTsRawISlots], lane);
-      if (q + 1 < slot_iters) words = load_slot(q + 1);  // latency hidden behind the store round trip
-      tmem_st_wait();
-      tc_fence_before_sync();
-      mbar_arrive_warp(&bar_full_a[s0], lane);
-      mbar_arrive_warp(&bar_full_a[s1], lane);
     }
   } else if (warp < kTsIssuerWarp) {
     // ---------------- column-side producers: 2-bit words -> int8 planes in shared memory ----------------
-    // Thread = (word w of the 16-byte tile row, variant k of the 64-variant stage).  A quarter-warp is
+    // Thread = (word w of the 20-byte tile row, variant k of the 64-variant stage).  A quarter-warp is
     // one (8-variant group, word) combination: conflict-free st.shared.v4 (the 8 K rows of a phase land in
-    // 8 different 16-byte bank groups); a warp reads 32 consecutive words of the 16-byte-pitch TMA box.
-    const uint32_t t = tid - 32 * kTsRowWarps;     // 0..255
-    const uint32_t combo = t >> 3;                 // 0..31 = (k group of 8) * 4 + word
-    const uint32_t k = 8 * (combo / 4) + (t & 7);
-    const uint32_t w = combo % 4;
-    const uint32_t ring_j = smem_base + kTsSmemOffRawJ + k * kTsRawBoxBytes + 4 * w;
+    // 8 different 16-byte bank groups) and 2-way ld.shared.b32 from the 32-byte-pitch TMA box.
+    const uint32_t t = tid - 32 * kTsRowWarps;     // 0..319
+    const uint32_t combo = t >> 3;                 // 0..39 = (k group of 8) * 5 + word
+    const uint32_t k = 8 * (combo / 5) + (t & 7);
+    const uint32_t w = combo % 5;
+    // the box starts at the 16-byte boundary at or below byte column 20 * ct (TMA-friendly start address)
+    const uint32_t ring_j = smem_base + kTsSmemOffRawJ + k * kTsRawBoxBytes + ((ct * (kTsCols / 4)) & 15u) + 4 * w;
     // K rows are stored in the PRMT position order of the row side (geno_expand.cuh): variant k of a
     // 16-variant group sits at row SampleToPos(k % 16)
     const uint32_t kpos = (k & ~15u) + SampleToPos(k & 15u);
@@ -247,11 +244,11 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     }
   } else if (warp == kTsIssuerWarp) {
     // ---------------- UMMA issuer: whole warp loops, one elected lane issues (umma.cuh) ----------------
-    // One outer iteration = the 4 shared-memory stages = 8 k-steps = one round of the 8 A slots, so
-    // every slot index and descriptor offset is a compile-time constant and A and B share their phase parity.
-    static_assert(kTsStagesJ == 4 && kTsASlots == 8, "issuer unrolling assumes 4 stages / 8 slots");
-    constexpr uint32_t idesc_n2 = make_idesc_i8(128, 2 * kTsCols, false, true);
-    constexpr uint32_t idesc_n1 = make_idesc_i8(128, kTsCols, false, true);
+    // One outer iteration = the 4 shared-memory stages = 8 k-steps = two rounds of the 4 A slots, so
+    // every slot index, A parity and descriptor offset is a compile-time constant.
+    static_assert(kTsStagesJ == 4 && kTsASlots == 4, "issuer unrolling assumes 4 stages / 4 slots");
+    constexpr uint32_t idesc_n160 = make_idesc_i8(128, 2 * kTsCols, false, true);
+    constexpr uint32_t idesc_n80 = make_idesc_i8(128, kTsCols, false, true);
     const uint32_t tmem_u = uniform_u32(tmem_base);
     const uint64_t desc0 = make_smem_desc(smem_base, kTsLboJ, kCoreBytes);
     for (uint32_t it0 = 0; it0 < stage_iters; it0 += kTsStagesJ) {
@@ -261,18 +258,18 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
         mbar_wait(&bar_full_b[sb], ph_b);
 #pragma unroll
         for (uint32_t kk = 0; kk < 2; ++kk) {
-          const uint32_t kq = 2 * sb + kk;            // k-step inside the outer iteration = its A slot
-          const uint32_t slot = kq;
-          mbar_wait(&bar_full_a[slot], ph_b);
+          const uint32_t kq = 2 * sb + kk;            // k-step inside the outer iteration
+          const uint32_t slot = kq % kTsASlots;
+          mbar_wait(&bar_full_a[slot], (kq / kTsASlots) & 1);
           tc_fence_after_sync();
           if (elect_one_sync()) {
             const uint32_t acc = (it0 | kq) ? 1u : 0u;
             const uint64_t b_th = desc0 + ((sb * kTsStageBytesJ + kk * 4 * kTsLboJ) >> 4);
             const uint64_t b_s = b_th + ((2 * kTsGroupsJ * kCoreBytes) >> 4);
             const uint32_t ta = tmem_u + kTsAccCols + slot * kTsASlotCols;
-            umma_i8_ts(tmem_u + 0, ta, b_th, idesc_n2, acc);
-            umma_i8_ts(tmem_u + 2 * kTsCols, ta + 8, b_th, idesc_n2, acc);
-            umma_i8_ts(tmem_u + 4 * kTsCols, ta + 16, b_s, idesc_n1, acc);
+            umma_i8_ts(tmem_u + 0, ta, b_th, idesc_n160, acc);
+            umma_i8_ts(tmem_u + 2 * kTsCols, ta + 8, b_th, idesc_n160, acc);
+            umma_i8_ts(tmem_u + 4 * kTsCols, ta + 16, b_s, idesc_n80, acc);
             umma_commit(&bar_empty_a[slot]);
             if (kk == 1) umma_commit(&bar_empty_b[sb]);
           }
@@ -287,7 +284,7 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
     if (elect_one_sync()) {
       const uint8_t* src_i = raw_i + static_cast<uint64_t>(rt - row_tile_first) * (2 * stage_iters) * (kTileRows * 8);
       const uint32_t ring_j = smem_base + kTsSmemOffRawJ, ring_i = smem_base + kTsSmemOffRawI;
-      const int32_t c0 = static_cast<int32_t>(ct * (kTsCols / 4));  // the tile's 64 samples = 16 bytes, 16-byte aligned
+      const int32_t c0 = static_cast<int32_t>((ct * (kTsCols / 4)) & ~15u);  // 20 bytes at offset 0/4/8/12 of a 32-byte box
       for (uint32_t q = 0; q < stage_iters / 2; ++q) {
         const uint32_t si = q % kTsRawISlots;
         mbar_wait(&bar_empty_ri[si], ((q / kTsRawISlots) & 1) ^ 1);
@@ -304,14 +301,14 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
 
   if (warp < kTsRowWarps) {
     // ---------------- epilogue: TMEM -> shared memory -> bulk reduce-add into the HBM accumulators ----------------
-    // The accumulators of a tile are one contiguous int32 [5 x 64 columns][128 rows] block.  Instead of a
+    // The accumulators of a tile are one contiguous int32 [5 x 80 columns][128 rows] block.  Instead of a
     // load-add-store per element from registers (latency-bound: ~16 KB in flight per SM, ~45 us per tile, i.e. >10 %
-    // of the tile), each accumulator plane (64 columns = 32 KB) is staged in shared memory - the operand stages and
+    // of the tile), each accumulator plane (80 columns = 40 KB) is staged in shared memory - the operand stages and
     // rings are idle now - and handed to the TMA unit as ONE cp.reduce.async.bulk .add.s32: the addition happens at
     // the L2, nothing is read back, and tensor memory is released as soon as the last tcgen05.ld has returned.
     mbar_wait(&bar_acc, 0);
     tc_fence_after_sync();
-    constexpr uint32_t kPlaneBytes = kTsCols * kTileRows * 4;  // 32768
+    constexpr uint32_t kPlaneBytes = kTsCols * kTileRows * 4;  // 40960
     static_assert(2 * kPlaneBytes <= kTsSmemBytes - 1024, "two staging planes must fit the dynamic shared memory");
     const uint32_t lq = warp & 3, half = warp >> 2;
     const uint32_t rsample = 32 * lq + lane;  // rows are in natural sample order here
@@ -324,7 +321,7 @@ king_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw, const uint8_t* __re
         if (tid == 0) bulk_wait_group_read<1>();
         named_bar_sync<2, 32 * kTsRowWarps>();
       }
-      // 4 chunks of 16 columns per plane and lane quarter: half 0 takes chunks 0, 2, half 1 takes 1, 3
+      // 5 chunks of 16 columns per plane and lane quarter: half 0 takes chunks 0, 2, 4, half 1 takes 1, 3
 #pragma unroll 1
       for (uint32_t cgrp = half; cgrp < kTsGroupsJ; cgrp += 2) {
         uint32_t v[16];

@@ -13,9 +13,9 @@ def row_block(sample_ct: int, rank: int, world: int, include_diag: bool = False)
     return parallel_bounds(sample_ct, 0 if include_diag else 1, rank, world)
 
 
-def row_block_tiles(sample_ct: int, rank: int, world: int, tile_rows: int = 128, tile_cols: int = 64, include_diag: bool = False):
+def row_block_tiles(sample_ct: int, rank: int, world: int, tile_rows: int = 128, tile_cols: int = 80, include_diag: bool = False):
     """Tile-aligned variant of row_block for the multi-GPU product path: boundaries are multiples of the
-    128-row pair tile and balance the number of 128 x 64 pair tiles per rank (what the tensor kernel's time is
+    128-row pair tile and balance the number of 128 x 80 pair tiles per rank (what the tensor kernel's time is
     proportional to), so no rank computes a partial row tile twice.  Pieces still concatenate to the full
     triangle in row order, like the reference's --parallel pieces."""
     first = 0 if include_diag else 1
