@@ -499,11 +499,17 @@ def b200_arm(args):
         del host_slice, host_out
 
     job.close()
+    if world > 1:
+        # tear the library's communicator down on every rank at the same point (ncclCommDestroy synchronises with
+        # its peers: closing it on rank 0 while the others already sit in the final torch barrier deadlocks)
+        barrier()
+        ctx.comm_destroy()
+        dist.barrier()
     if rank != 0:
+        ctx.close()
         if world > 1:
             dist.barrier()
             dist.destroy_process_group()
-        ctx.close()
         return
 
     # ---- measured int8 tensor peak of THIS GPU, same run (>= 2 s on all SMs, clocks sampled) ----

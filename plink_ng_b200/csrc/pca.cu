@@ -156,6 +156,23 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       c->launches++;
     }
   };
+  // PL2_TIMING=1: phase times on stderr (stream-synchronising; development aid)
+  const bool timing = getenv("PL2_TIMING") != nullptr;
+  cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;
+  if (timing) {
+    cudaEventCreate(&ev_t0);
+    cudaEventCreate(&ev_t1);
+    cudaEventRecord(ev_t0, c->stream);
+  }
+  auto mark = [&](const char* what) {
+    if (!timing) return;
+    cudaEventRecord(ev_t1, c->stream);
+    cudaEventSynchronize(ev_t1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ev_t0, ev_t1);
+    fprintf(stderr, "[timing] pca_run %-34s %9.2f ms\n", what, ms);
+    std::swap(ev_t0, ev_t1);
+  };
   do {
     if (cudaMalloc(&d_qq, static_cast<uint64_t>(m) * q * 8) != cudaSuccess || cudaMalloc(&d_u, static_cast<uint64_t>(std::max(m, n)) * q * 8) != cudaSuccess || cudaMalloc(&d_g1, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess ||
         cudaMalloc(&d_g2, static_cast<uint64_t>(npad) * c2 * 8) != cudaSuccess || cudaMalloc(&d_b, static_cast<uint64_t>(n) * q * 8) != cudaSuccess ) {
@@ -179,6 +196,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       set_error("pl2gpu_pca_run: kernel launch failed");
       break;
     }
+    mark("power iterations (Y.G / Yt.H)");
     // SVD of the Krylov matrix: left singular vectors = orthonormal basis Q of its range   :5860
     // (one-sided Jacobi, jacobi.cuh; the reference calls dgesvd)
     std::vector<double> s(q);
@@ -187,14 +205,17 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       set_error("Failed to compute SVD of Krylov matrix (%s).", err ? err : "?");
       break;
     }
+    mark("SVD of the M x q Krylov matrix");
     // B = Y^T Q (N x q, column-major)   :5870-5916
     if (cudaMemsetAsync(d_b, 0, static_cast<uint64_t>(n) * q * 8, c->stream) != cudaSuccess) break;
     launch_xtb(d_u, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
+    mark("B = Yt.Q");
     // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B   :5920
     if (JacobiSvd(c, d_b, n, n, static_cast<uint32_t>(q), k, s.data(), d_u, n, nullptr, &err)) {
       set_error("Failed to compute SVD of final matrix (%s).", err ? err : "?");
       break;
     }
+    mark("SVD of the N x q matrix B");
     if (cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
       set_error("pl2gpu_pca_run: %s", cudaGetErrorString(cudaGetLastError()));
       break;
@@ -202,6 +223,8 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     for (uint32_t p = 0; p < k; ++p) eigvals_host[p] = s[p] * s[p] * m_recip;  // :5931
     rc = 0;
   } while (0);
+  if (ev_t0) cudaEventDestroy(ev_t0);
+  if (ev_t1) cudaEventDestroy(ev_t1);
   cudaFree(d_qq);
   cudaFree(d_u);
   cudaFree(d_g1);

@@ -93,6 +93,10 @@ class GpuContext:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         check(lib.pl2gpu_comm_init(self._h, rank, world, buf), "pl2gpu_comm_init")
 
+    def comm_destroy(self):
+        """Collective teardown of the communicator (every rank calls it at the same point); idempotent."""
+        check(lib.pl2gpu_comm_destroy(self._h), "pl2gpu_comm_destroy")
+
     def selftest_umma(self, verbose: bool = True):
         check(lib.pl2gpu_selftest_umma(self._h, 1 if verbose else 0), "pl2gpu_selftest_umma")
 
