@@ -411,9 +411,18 @@ def b200_arm(args):
     ctx = p.GpuContext(local_rank)
     if world > 1:
         # NCCL lives in the library: rank 0 creates the id, torch.distributed only ships the 128 bytes
-        ids = [comm_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        ctx.comm_init(rank, world, ids[0])
+        # (NCCL prints its version banner on stdout at the first communicator init: keep stdout for the one JSON line)
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            ids = [comm_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            ctx.comm_init(rank, world, ids[0])
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
     job = KingJob(ctx, n, r0, r1, algo, max_variants_per_add=per * world)
     ctx.synchronize()
 
