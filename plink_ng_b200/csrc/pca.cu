@@ -10,7 +10,9 @@
 #include "../../include/plink2_b200.h"
 #include "common.cuh"
 #include "ld_kernels.cuh"    // geno_counts_kernel
+#include "geno_tile.cuh"
 #include "pca_kernels.cuh"
+#include "pca_ts_kernels.cuh"
 #include "jacobi.cuh"
 
 using namespace pl2;
@@ -29,6 +31,14 @@ struct Pl2PcaJob {
   uint32_t* d_counts = nullptr;
   std::vector<double> h_ztab;
   std::vector<uint32_t> h_counts;
+  // tensor path (default; PL2_PCA_ALGO=fp64 selects the CUDA-core kernels of pca_kernels.cuh as a cross-check)
+  bool tensor = true;
+  uint8_t* d_raw_i = nullptr;   // sample-major copy [row tile][k-step][128][8 B] of the whole matrix (geno_tile.cuh)
+  double* d_slope = nullptr;    // per variant: inv_stdev (0 for skipped variants)
+  double* d_icpt = nullptr;     // per variant: -2 alt_freq inv_stdev
+  std::vector<double> h_slope, h_icpt;
+  CUtensorMap tmap_raw;         // box {16 B, 128 variants} over d_raw
+  uint32_t retiled_to = 0;      // variants [0, retiled_to) are in d_raw_i (multiple of 64)
 };
 
 extern "C" {
@@ -58,12 +68,28 @@ int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_tot
   job->pitch = job->sample_ct_padded / 4;
   job->variant_cap = RoundUpU32(variant_ct_total, 128);
   job->pc_ct = pc_ct;
+  {
+    const char* algo = getenv("PL2_PCA_ALGO");
+    job->tensor = !(algo && !strcmp(algo, "fp64"));
+  }
   if (cudaMalloc(&job->d_raw, static_cast<uint64_t>(job->variant_cap) * job->pitch) != cudaSuccess || cudaMalloc(&job->d_ztab, static_cast<uint64_t>(job->variant_cap) * 32) != cudaSuccess ||
-      cudaMalloc(&job->d_counts, 16ull * 65536) != cudaSuccess) {
+      cudaMalloc(&job->d_counts, 16ull * 65536) != cudaSuccess ||
+      (job->tensor && (cudaMalloc(&job->d_raw_i, static_cast<uint64_t>(job->sample_ct_padded) * (job->variant_cap / 4)) != cudaSuccess || cudaMalloc(&job->d_slope, 8ull * job->variant_cap) != cudaSuccess ||
+                       cudaMalloc(&job->d_icpt, 8ull * job->variant_cap) != cudaSuccess))) {
     cudaGetLastError();
     set_error("pl2gpu_pca_begin: insufficient device memory to keep %u x %u genotypes resident", variant_ct_total, sample_ct);
     pl2gpu_pca_end(job);
     return 1;
+  }
+  if (job->tensor) {
+    if (cudaMemsetAsync(job->d_slope, 0, 8ull * job->variant_cap, ctx->c.stream) != cudaSuccess || cudaMemsetAsync(job->d_icpt, 0, 8ull * job->variant_cap, ctx->c.stream) != cudaSuccess ||
+        MakeRawTensorMap(&job->tmap_raw, job->d_raw, job->pitch, job->variant_cap, 16, 128) ||
+        cudaFuncSetAttribute(pca_xa_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPxaSmemBytes) != cudaSuccess ||
+        cudaFuncSetAttribute(pca_xtb_ts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPxtSmemBytes) != cudaSuccess) {
+      if (!*get_error()) set_error("pl2gpu_pca_begin: %s", cudaGetErrorString(cudaGetLastError()));
+      pl2gpu_pca_end(job);
+      return 1;
+    }
   }
   *job_ptr = job;
   return 0;
@@ -88,6 +114,8 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
     PL2_CUDA_OK(cudaMemcpyAsync(job->h_counts.data(), job->d_counts, 16ull * cur, cudaMemcpyDeviceToHost, c->stream));
     PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
     job->h_ztab.assign(4ull * cur, 0.0);
+    job->h_slope.assign(cur, 0.0);
+    job->h_icpt.assign(cur, 0.0);
     for (uint32_t v = 0; v < cur; ++v) {
       const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2];
       double ref_freq;
@@ -116,8 +144,14 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
       z[0] = intercept;
       z[1] = intercept + inv_stdev;
       z[2] = intercept + 2 * inv_stdev;
+      job->h_slope[v] = inv_stdev;
+      job->h_icpt[v] = intercept;
     }
     PL2_CUDA_OK(cudaMemcpyAsync(job->d_ztab + 4ull * job->variant_ct, job->h_ztab.data(), 32ull * cur, cudaMemcpyHostToDevice, c->stream));
+    if (job->tensor) {
+      PL2_CUDA_OK(cudaMemcpyAsync(job->d_slope + job->variant_ct, job->h_slope.data(), 8ull * cur, cudaMemcpyHostToDevice, c->stream));
+      PL2_CUDA_OK(cudaMemcpyAsync(job->d_icpt + job->variant_ct, job->h_icpt.data(), 8ull * cur, cudaMemcpyHostToDevice, c->stream));
+    }
     PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
     job->variant_ct += cur;
     done += cur;
@@ -142,19 +176,84 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr;
   int rc = 1;
   const double m_recip = 1.0 / static_cast<double>(m);
-  auto launch_xa = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
+  // ---- tensor path scratch (pca_ts_kernels.cuh): digit planes, per-column scales, split-K partial sums ----
+  const bool tensor = job->tensor;
+  uint8_t *d_gdig = nullptr, *d_hs = nullptr, *d_hi = nullptr;
+  double *d_scale = nullptr, *d_inv_scale = nullptr, *d_partial = nullptr;
+  unsigned long long* d_colmax = nullptr;
+  const uint32_t kstep_total = job->variant_cap / 32;
+  const uint32_t tiles2 = DivUpU32(npad / 128, 2);
+  uint32_t splits = std::max(1u, std::min(DivUpU32(2 * static_cast<uint32_t>(c->sm_count), tiles2), kstep_total / 64));
+  const uint32_t ksteps_per_split = RoundUpU32(DivUpU32(kstep_total, splits), 4);
+  splits = DivUpU32(kstep_total, ksteps_per_split);
+  int ts_rc = 0;
+  if (tensor) {
+    if (cudaMalloc(&d_gdig, static_cast<uint64_t>(npad) * kPcaNMax) != cudaSuccess || cudaMalloc(&d_hs, static_cast<uint64_t>(job->variant_cap) * kPcaNMax) != cudaSuccess ||
+        cudaMalloc(&d_hi, static_cast<uint64_t>(job->variant_cap) * kPcaNMax) != cudaSuccess || cudaMalloc(&d_scale, 8 * kPcaCgMax) != cudaSuccess || cudaMalloc(&d_inv_scale, 8 * kPcaCgMax) != cudaSuccess ||
+        cudaMalloc(&d_colmax, 8 * kPcaCgMax) != cudaSuccess || cudaMalloc(&d_partial, static_cast<uint64_t>(splits) * npad * kPcaCgMax * 8) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_pca_run: insufficient device memory for the digit planes");
+      cudaFree(d_gdig); cudaFree(d_hs); cudaFree(d_hi); cudaFree(d_scale); cudaFree(d_inv_scale); cudaFree(d_colmax); cudaFree(d_partial);
+      return 1;
+    }
+    // rows [variant_ct, variant_cap) must decode to "missing" in both layouts; finish the sample-major copy
+    if (job->variant_cap > m) PL2_TRY(LaunchPadGenotypes(c, job->d_raw + static_cast<uint64_t>(m) * job->pitch, job->pitch, job->sample_ct, 0, job->variant_cap - m));
+    if (job->retiled_to < job->variant_cap) {
+      const uint32_t from = job->retiled_to;
+      geno_tile_rows_kernel<<<dim3((job->variant_cap - from) / 64, npad / 64), 256, 0, c->stream>>>(job->d_raw + static_cast<uint64_t>(from) * job->pitch, job->pitch, kstep_total, 0, job->d_raw_i + static_cast<uint64_t>(from / 32) * 1024);
+      c->launches++;
+      job->retiled_to = job->variant_cap;
+    }
+  }
+  // column group: up to 48 columns, padded to a multiple of 4 (the padding columns are zero digits and never written)
+  auto group_scales = [&](const double* src, uint64_t rs, uint64_t cs, uint32_t rows, uint32_t valid, const double* mul1, const double* mul2) {
+    if (cudaMemsetAsync(d_colmax, 0, 8 * kPcaCgMax, c->stream) != cudaSuccess) ts_rc = 1;
+    pca_colmax_kernel<<<dim3(valid, std::min<uint32_t>(64, DivUpU32(rows, 256))), 256, 0, c->stream>>>(src, rs, cs, rows, mul1, mul2, d_colmax);
+    pca_scales_kernel<<<1, 64, 0, c->stream>>>(d_colmax, kPcaCgMax, d_scale, d_inv_scale);
+    c->launches += 2;
+  };
+  auto launch_xa_ts = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
+    for (uint32_t cc = 0; cc < cols_total; cc += kPcaCgMax) {
+      const uint32_t valid = std::min(kPcaCgMax, cols_total - cc), cg = RoundUpU32(valid, 4);
+      group_scales(g + cc, g_ld, 1, npad, valid, nullptr, nullptr);
+      pca_digits_kernel<<<npad / 64, 256, 0, c->stream>>>(g + cc, g_ld, 1, npad, cg, valid, nullptr, nullptr, d_scale, d_gdig, nullptr);
+      pca_xa_ts_kernel<<<job->variant_cap / 128, kPxaThreads, kPxaSmemBytes, c->stream>>>(job->tmap_raw, npad, m, d_gdig, cg, valid, job->d_slope, job->d_icpt, d_inv_scale, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld);
+      c->launches += 2;
+    }
+  };
+  auto launch_xtb_ts = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
+    for (uint32_t cc = 0; cc < cols_total; cc += kPcaCgMax) {
+      const uint32_t valid = std::min(kPcaCgMax, cols_total - cc), cg = RoundUpU32(valid, 4);
+      const double* src = hin + static_cast<uint64_t>(hcol0 + cc) * h_ld;
+      group_scales(src, 1, h_ld, m, valid, job->d_slope, job->d_icpt);
+      pca_digits_kernel<<<job->variant_cap / 64, 256, 0, c->stream>>>(src, 1, h_ld, m, cg, valid, job->d_slope, job->d_icpt, d_scale, d_hs, d_hi);
+      if (cudaMemsetAsync(d_partial, 0, static_cast<uint64_t>(splits) * npad * cg * 8, c->stream) != cudaSuccess) ts_rc = 1;
+      pca_xtb_ts_kernel<<<dim3(tiles2, splits), kPxtThreads, kPxtSmemBytes, c->stream>>>(job->d_raw_i, kstep_total, ksteps_per_split, n, d_hs, d_hi, cg, d_inv_scale, d_partial, npad);
+      pca_xtb_reduce_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(n) * cg, 256)), 256, 0, c->stream>>>(d_partial, splits, n, npad, cg, valid, 1.0, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
+      c->launches += 3;
+    }
+  };
+  auto launch_xa_fp64 = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
     for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
       const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
       pca_xa_kernel<<<DivUpU32(m, 128), 32 * DivUpU32(cols, 4), (128 * cols + 4) * 8, c->stream>>>(job->d_raw, job->pitch, npad, m, job->d_ztab, g + cc, g_ld, 0, cols, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0);
       c->launches++;
     }
   };
-  auto launch_xtb = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
+  auto launch_xtb_fp64 = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
     for (uint32_t cc = 0; cc < cols_total; cc += kPcaColsMax) {
       const uint32_t cols = std::min(kPcaColsMax, cols_total - cc);
       pca_xtb_kernel<<<DivUpU32(n, 128), 32 * DivUpU32(cols, 4), (128 * cols + 512) * 8, c->stream>>>(job->d_raw, job->pitch, n, m, job->d_ztab, hin + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld, 0, 0, cols, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
       c->launches++;
     }
+  };
+  auto launch_xa = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
+    if (tensor) launch_xa_ts(g, g_ld, hout, h_ld, hcol0, cols_total);
+    else launch_xa_fp64(g, g_ld, hout, h_ld, hcol0, cols_total);
+  };
+  auto launch_xtb = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
+    if (tensor) launch_xtb_ts(hin, h_ld, hcol0, cols_total, out, out_rs, out_cs);
+    else launch_xtb_fp64(hin, h_ld, hcol0, cols_total, out, out_rs, out_cs);
   };
   // PL2_TIMING=1: phase times on stderr (stream-synchronising; development aid)
   const bool timing = getenv("PL2_TIMING") != nullptr;
@@ -225,6 +324,17 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   } while (0);
   if (ev_t0) cudaEventDestroy(ev_t0);
   if (ev_t1) cudaEventDestroy(ev_t1);
+  if (ts_rc && !rc) {
+    set_error("pl2gpu_pca_run: a tensor-path launch failed");
+    rc = 1;
+  }
+  cudaFree(d_gdig);
+  cudaFree(d_hs);
+  cudaFree(d_hi);
+  cudaFree(d_scale);
+  cudaFree(d_inv_scale);
+  cudaFree(d_colmax);
+  cudaFree(d_partial);
   cudaFree(d_qq);
   cudaFree(d_u);
   cudaFree(d_g1);
@@ -240,6 +350,9 @@ int pl2gpu_pca_end(Pl2PcaJob* job) {
     cudaStreamSynchronize(job->ctx->c.stream);
   }
   cudaFree(job->d_raw);
+  cudaFree(job->d_raw_i);
+  cudaFree(job->d_slope);
+  cudaFree(job->d_icpt);
   cudaFree(job->d_ztab);
   cudaFree(job->d_counts);
   cudaGetLastError();

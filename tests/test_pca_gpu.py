@@ -67,10 +67,14 @@ def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
     assert np.allclose(_align(gv, rv), rv, atol=2e-4)
 
 
-def test_approx_pca_matches_oracle_same_gaussian_start(gpu_ctx):
+@pytest.mark.parametrize("algo", ["tensor", "fp64"])
+def test_approx_pca_matches_oracle_same_gaussian_start(gpu_ctx, algo, monkeypatch):
+    """Both pass implementations: the int8 tensor path (pca_ts_kernels.cuh, dense factor in 32-bit fixed point) and the
+    CUDA-core fp64 kernels (pca_kernels.cuh) kept as a cross-check."""
     from plink_ng_b200.host import pca_approx
 
-    n, m, k = 400, 6000, 5  # 2k = 10 columns: exercises the half column quad
+    monkeypatch.setenv("PL2_PCA_ALGO", algo)
+    n, m, k = 400, 6000, 5  # 2k = 10 columns: a column group padded to 12; q = 60 -> groups of 48 + 12
     geno = _structured_geno(m, n, seed=9, pops=6, fst=0.1)
     g1 = np.random.default_rng(1).standard_normal((n, 2 * k))
     want_vals, want_vecs = orc.pca_approx(geno, k, g1)
@@ -83,6 +87,21 @@ def test_approx_pca_matches_oracle_same_gaussian_start(gpu_ctx):
     g, _ = orc.grm(geno, meanimpute=True)
     ev, _ = orc.pca_exact(g, k)
     assert np.allclose(vals, ev, rtol=2e-2)
+
+
+def test_approx_pca_k20_tensor_path_matches_oracle(gpu_ctx):
+    """BASELINE's --pca 20 shape at a size numpy finishes in seconds: 40-column passes (one column group of N = 160),
+    840-column final projection (17 groups of 48 + one of 24), several 128-variant / 256-sample tiles and split-K."""
+    from plink_ng_b200.host import pca_approx
+
+    n, m, k = 1100, 9000, 20
+    geno = _structured_geno(m, n, seed=21, pops=8, fst=0.12)
+    g1 = np.random.default_rng(3).standard_normal((n, 2 * k))
+    want_vals, want_vecs = orc.pca_approx(geno, k, g1)
+    vals, vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
+    assert np.allclose(vals, want_vals, rtol=1e-6)
+    top = 7  # 8 populations -> 7 structure PCs
+    assert np.allclose(_align(vecs[:top], want_vecs[:top]), want_vecs[:top], atol=1e-5 * np.abs(want_vecs[:top]).max())
 
 
 def test_approx_pca_cli_matches_reference_files(golden_dir, tmp_path):
