@@ -212,6 +212,19 @@ int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_
  * window walk (IndepPairwiseThread, :862-1109) runs on the calling host thread. ---- */
 int pl2_indep_pairwise(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int src_is_device, uint8_t* removed_out);
 
+/* Extended form: founder_sex[founder_ct] (0 unknown, 1 male, 2 female; NULL = all unknown) selects the reference's
+ * sex-chromosome handling (IndepPairwise loader, 2.0/plink2_ld.cc:1356-1389; sums :982-998): chrX (code 23) = males
+ * with hets -> missing at weight 1 plus nonmales at weight 2, chrY (24) = nonfemale founders with hets -> missing,
+ * MT (26) = all founders with hets -> missing; allele frequencies follow LoadAlleleAndGenoCountsThread's per-class
+ * counting (2.0/plink2_data.cc:2420-2690).  flags: kPl2LdPlink1Order = `--indep-order 1` (:931-1037). */
+enum { kPl2LdPlink1Order = 1 };
+int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int src_is_device, const uint8_t* founder_sex, uint32_t flags, uint8_t* removed_out);
+/* Host half of the function face on its own (no device work): IndepPairwiseThread's greedy window walk
+ * (2.0/plink2_ld.cc:862-1109, window bookkeeping :605-689, subcontigs :2165-2268) over precomputed pair
+ * decisions pair_flags[v * band + d - 1] (second = v, first = v - d; band >= widest window - 1), load-time
+ * monomorphic marks (:902) and major-allele frequencies (minus 1 for --indep-preferred variants, :916-918). */
+int pl2_ld_prune_walk(uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, int window_is_bp, const double* maj_freq, const uint8_t* mono, const uint8_t* pair_flags, uint32_t band, uint32_t flags, uint8_t* removed_out);
+
 /* ---- measured int8 tensor peak: every SM issues back-to-back tcgen05.mma kind::i8 (M = 128, N = n_cols,
  * K = 32; form 0 = both operands in shared memory, 1 = A operand in tensor memory as the KING/GRM kernels use
  * it) for at least min_seconds; *tops_out = 2*128*n_cols*32 ops x UMMAs / elapsed (CUDA events), in TOP/s.

@@ -265,25 +265,30 @@ def lower_triangle_with_diag(mat: np.ndarray) -> np.ndarray:
 
 
 # -------------------------------------------------------------------------------- --indep-pairwise
-def ld_pair_components(x: np.ndarray, nm: np.ndarray, a: int, bs: np.ndarray):
+def ld_pair_components(x: np.ndarray, nm: np.ndarray, a: int, bs: np.ndarray, w: np.ndarray = None):
     """ComputeIndepPairwiseR2Components (2.0/plink2_ld.cc:699-723) for `second` = a against every
     `first` in bs: all six integers restricted to samples non-missing in both variants.
-    x in {+1 (code 0), 0 (het), -1 (code 2), 0 (missing)}; nm = non-missing indicator."""
+    x in {+1 (code 0), 0 (het), -1 (code 2), 0 (missing)}; nm = non-missing indicator.
+    w: per-sample integer weights - chrX adds the nonmale-only sums twice to the all-founder sums
+    (:982-998, :1064-1078, "--ld-xchr 3"), i.e. weight 1 for males and 2 for everyone else."""
     xa, na = x[a], nm[a]
+    xa2 = xa * xa
+    if w is not None:
+        xa, na, xa2 = xa * w, na * w, xa2 * w
     xb, nb = x[bs], nm[bs]
     nm_ct = nb @ na
     dot = xb @ xa
     s_b = xb @ na
     q_b = (xb * xb) @ na
     s_a = nb @ xa
-    q_a = nb @ (xa * xa)
+    q_a = nb @ xa2
     r = lambda v: np.rint(v).astype(np.int64)  # noqa: E731
     return r(nm_ct), r(s_b), r(q_b), r(s_a), r(q_a), r(dot)
 
 
-def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int, step: int, r2_thresh: float) -> np.ndarray:
-    """IndepPairwiseThread, default (non --indep-order 1) branch (2.0/plink2_ld.cc:862-1109) for one
-    subcontig.  `geno` [L, founders]; returns removed[L] bool.  Window bookkeeping follows
+def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int, step: int, r2_thresh: float, w: np.ndarray = None, order: int = 2) -> np.ndarray:
+    """IndepPairwiseThread (2.0/plink2_ld.cc:862-1109) for one subcontig: default branch (:1039-1100) or, with
+    order = 1, the PLINK 1.x pruning order of `--indep-order 1` (:931-1037).  `geno` [L, founders]; returns removed[L] bool.  Window bookkeeping follows
     LdPruneNextSubcontig (:605-633) and LdPruneNextWindow (:635-689); `bps` is None for
     variant-count windows.  The major-allele inversion of PgrGetInv1 (:1357) does not change any
     decision (cov^2 and both variances are invariant under negating a variable), so plain codes are
@@ -292,9 +297,11 @@ def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int,
     thr = r2_thresh * (1 + SMALL_EPSILON)  # :1255
     x = np.where(geno == 0, 1.0, np.where(geno == 2, -1.0, 0.0)).astype(np.float32)
     nm = (geno != 3).astype(np.float32)
-    nm_ct_v = (geno != 3).sum(axis=1)
-    plus_v = (geno == 0).sum(axis=1)
-    minus_v = (geno == 2).sum(axis=1)
+    wv = np.ones(geno.shape[1], dtype=np.int64) if w is None else np.asarray(w, dtype=np.int64)
+    nm_ct_v = (geno != 3).astype(np.int64) @ wv
+    plus_v = (geno == 0).astype(np.int64) @ wv
+    minus_v = (geno == 2).astype(np.int64) @ wv
+    wf = None if w is None else wv.astype(np.float32)
     mono = ((plus_v == 0) & (minus_v == 0)) | (plus_v == nm_ct_v) | (minus_v == nm_ct_v)  # :902
     removed = np.zeros(L, dtype=bool)
     if L < 2:
@@ -317,6 +324,15 @@ def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int,
     win = []          # tvidx per window position
     win_removed = []  # cur_window_removed bit per window position
     winpos_split = 0
+    first_unchecked = {}  # --indep-order 1: first_unchecked_tvidx per live variant (:919-921)
+
+    def over_threshold(a, firsts):
+        nm_ct, s_b, q_b, s_a, q_a, dot = ld_pair_components(x, nm, a, firsts, wf)
+        cov12 = (dot * nm_ct - s_b * s_a).astype(np.float64)
+        var1 = (q_b * nm_ct - s_b * s_b).astype(np.float64)  # first
+        var2 = (q_a * nm_ct - s_a * s_a).astype(np.float64)  # second
+        return cov12 * cov12 > thr * var1 * var2
+
     for cur in range(L):
         win.append(cur)
         if mono[cur]:
@@ -324,15 +340,58 @@ def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int,
             removed[cur] = True
         else:
             win_removed.append(False)
+            first_unchecked[cur] = cur + 1
         if cur + 1 != next_end:
             continue
+        cur_tvidx = cur + 1
+        if order == 1:
+            # PLINK 1.x order (:931-1037): sweep firsts in ascending order, each against the not-yet-checked
+            # seconds after it; repeat the sweep while it removes something
+            removed_ct = sum(win_removed)
+            while True:
+                prev_ct = removed_ct
+                first_winpos = -1
+                while True:
+                    first_winpos += 1
+                    while first_winpos < len(win) and win_removed[first_winpos]:
+                        first_winpos += 1
+                    if first_winpos >= len(win):
+                        break
+                    b = win[first_winpos]
+                    fu = first_unchecked[b]
+                    if fu == cur_tvidx:
+                        continue
+                    live = [p for p in range(first_winpos + 1, len(win)) if not win_removed[p]]  # snapshot, like BitIter0
+                    live = [p for p in live if win[p] >= fu]
+                    if not live:
+                        first_unchecked[b] = cur_tvidx
+                        continue
+                    seconds = np.array([win[p] for p in live], dtype=np.int64)
+                    # pair (first b, second a): same sextuple, var1 = first's
+                    over = np.array([over_threshold(int(a2), np.array([b]))[0] for a2 in seconds])
+                    hit = np.flatnonzero(over)
+                    if hit.size == 0:
+                        first_unchecked[b] = cur_tvidx
+                        continue
+                    h = int(hit[0])
+                    a = int(seconds[h])
+                    if maj_freq[b] > maj_freq[a] * (1 + SMALL_EPSILON):
+                        win_removed[first_winpos] = True
+                        removed[b] = True
+                    else:
+                        win_removed[live[h]] = True
+                        removed[a] = True
+                        first_unchecked[b] = win[live[h + 1]] if h + 1 < len(live) else cur_tvidx
+                removed_ct = sum(win_removed)
+                if not removed_ct > prev_ct:
+                    break
         second_stop = winpos_split if winpos_split else 1
-        for second_winpos in range(len(win) - 1, second_stop - 1, -1):
+        for second_winpos in (range(len(win) - 1, second_stop - 1, -1) if order != 1 else ()):
             a = win[second_winpos]
             firsts = np.array(win[:second_winpos], dtype=np.int64)
             if firsts.size == 0:
                 continue
-            nm_ct, s_b, q_b, s_a, q_a, dot = ld_pair_components(x, nm, a, firsts)
+            nm_ct, s_b, q_b, s_a, q_a, dot = ld_pair_components(x, nm, a, firsts, wf)
             cov12 = (dot * nm_ct - s_b * s_a).astype(np.float64)
             var1 = (q_b * nm_ct - s_b * s_b).astype(np.float64)  # first
             var2 = (q_a * nm_ct - s_a * s_a).astype(np.float64)  # second
@@ -378,15 +437,102 @@ def ld_prune_subcontig(geno: np.ndarray, maj_freq: np.ndarray, bps, window: int,
     return removed
 
 
-def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, step: int, r2_thresh: float, window_is_bp: bool = False, ref_freq: np.ndarray = None, preferred: np.ndarray = None) -> np.ndarray:
+def _chr_class(c) -> str:
+    """'x' / 'y' / 'hap' (MT) / 'dip' from a chromosome code or name (human: haploid_mask = X, Y, MT,
+    2.0/plink2_common.cc:1979)."""
+    t = str(c).upper()
+    if t.startswith("CHR"):
+        t = t[3:]
+    return {"X": "x", "23": "x", "Y": "y", "24": "y", "MT": "hap", "M": "hap", "26": "hap"}.get(t, "dip")
+
+
+def ld_ref_freqs_by_class(geno: np.ndarray, chrom: np.ndarray, sex: np.ndarray = None) -> np.ndarray:
+    """REF allele frequencies as LoadAlleleAndGenoCountsThread + ComputeAlleleFreqs produce them for founders
+    (2.0/plink2_data.cc:2420-2690, 2.0/plink2_filter.cc:2113-2151): autosomes and MT = hard-call ratio; chrY =
+    the same ratio over nonfemale founders (:2458-2483); chrX = nonmales count twice, males once, a male het is
+    half an ALT (:2642, :2685-2688).  sex: 1 male, 2 female, 0 unknown."""
+    m, n = geno.shape
+    sex = np.zeros(n, dtype=np.int64) if sex is None else np.asarray(sex)
+    male, nonfemale = sex == 1, sex != 2
+    out = ref_allele_freqs(geno)
+    cls = np.array([_chr_class(c) for c in chrom])
+    ysel = cls == "y"
+    if ysel.any():
+        out[ysel] = ref_allele_freqs(geno[ysel][:, nonfemale]) if nonfemale.any() else 0.5
+    xsel = cls == "x"
+    if xsel.any():
+        gx = geno[xsel]
+        n0, n1, n2, n3 = genotype_counts(gx)
+        m0, m1, m2, m3 = genotype_counts(gx[:, male])
+        alt1 = 4 * n2 + 2 * n1 - 2 * m2 - m1
+        wobs = (2 * (n - n3) - int(male.sum()) + m3) * 2
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f = (wobs - alt1).astype(np.float64) * (1.0 / wobs.astype(np.float64))
+        out[xsel] = np.where(wobs == 0, 0.5, f)
+    return out
+
+
+def ld_class_block(g: np.ndarray, cls: str, sex: np.ndarray):
+    """The genotype block IndepPairwise's loader builds for one chromosome class (2.0/plink2_ld.cc:1356-1389) and the
+    per-sample weights of the pair sums (:982-998): MT = hets -> missing; chrY = nonfemale founders, hets -> missing;
+    chrX = male hets -> missing, males weight 1, everyone else weight 2."""
+    male, nonfemale = sex == 1, sex != 2
+    if cls == "hap":
+        return np.where(g == 1, 3, g), None
+    if cls == "y":
+        return np.where(g == 1, 3, g)[:, nonfemale], None
+    if cls == "x":
+        return np.where((g == 1) & male[None, :], 3, g), np.where(male, 1, 2)
+    return g, None
+
+
+def ld_walk_inputs(geno: np.ndarray, chrom: np.ndarray, r2_thresh: float, band: int, sex: np.ndarray = None, preferred: np.ndarray = None):
+    """Everything the greedy walk looks at, per variant in file order: major-allele frequency (minus 1 for preferred
+    variants), the load-time monomorphic mark (:902) and the pair decisions flags[v, d - 1] for second = v,
+    first = v - d, 1 <= d <= band, within the variant's chromosome (the layout of pl2gpu_ld_band_flags)."""
+    m, n = geno.shape
+    sex = np.zeros(n, dtype=np.int64) if sex is None else np.asarray(sex)
+    majf = major_allele_freqs(ld_ref_freqs_by_class(geno, chrom, sex))
+    if preferred is not None:
+        majf = np.where(np.asarray(preferred, dtype=bool), majf - 1.0, majf)
+    thr = r2_thresh * (1 + SMALL_EPSILON)
+    mono = np.zeros(m, dtype=np.uint8)
+    flags = np.zeros((m, band), dtype=np.uint8)
+    idx_all = np.arange(m)
+    for c in dict.fromkeys(chrom.tolist()):
+        idx = idx_all[chrom == c]
+        g, w = ld_class_block(geno[idx], _chr_class(c), sex)
+        wv = np.ones(g.shape[1], dtype=np.int64) if w is None else np.asarray(w, dtype=np.int64)
+        nm_ct_v = (g != 3).astype(np.int64) @ wv
+        plus_v = (g == 0).astype(np.int64) @ wv
+        minus_v = (g == 2).astype(np.int64) @ wv
+        mono[idx] = ((plus_v == 0) & (minus_v == 0)) | (plus_v == nm_ct_v) | (minus_v == nm_ct_v)
+        x = np.where(g == 0, 1.0, np.where(g == 2, -1.0, 0.0)).astype(np.float32)
+        nm = (g != 3).astype(np.float32)
+        wf = None if w is None else wv.astype(np.float32)
+        for a in range(1, idx.size):
+            firsts = np.arange(max(0, a - band), a)
+            nm_ct, s_b, q_b, s_a, q_a, dot = ld_pair_components(x, nm, a, firsts, wf)
+            cov12 = (dot * nm_ct - s_b * s_a).astype(np.float64)
+            var1 = (q_b * nm_ct - s_b * s_b).astype(np.float64)
+            var2 = (q_a * nm_ct - s_a * s_a).astype(np.float64)
+            flags[idx[a], a - firsts - 1] = cov12 * cov12 > thr * var1 * var2
+    return majf, mono, flags
+
+
+def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, step: int, r2_thresh: float, window_is_bp: bool = False, ref_freq: np.ndarray = None, preferred: np.ndarray = None,
+             sex: np.ndarray = None, order: int = 2) -> np.ndarray:
     """LdPrune -> IndepPairwise (2.0/plink2_ld.cc:2530-2724): chr0 variants are dropped up front
     (:2542, reported in neither list), every chromosome (bp windows: every run of variants whose
     gaps are <= window, LdPruneSubcontigSplitAll :2165-2268) with >= 2 variants is an independent
     job; variants in singleton subcontigs are never examined (kept).  Returns removed[M] bool
-    (chr0 variants: False)."""
-    m = geno.shape[0]
+    (chr0 variants: False).  `geno` holds founders only; `sex` (1 male / 2 female / 0 unknown per founder)
+    matters on chrX (males: hets -> missing, weight 1; nonmales weight 2; :1371-1376, :982-998), chrY (nonfemale
+    founders only, hets -> missing, :1385-1389) and MT (hets -> missing, :1362-1364).  order = 1: `--indep-order 1`."""
+    m, n = geno.shape
+    sex = np.zeros(n, dtype=np.int64) if sex is None else np.asarray(sex)
     if ref_freq is None:
-        ref_freq = ref_allele_freqs(geno)
+        ref_freq = ld_ref_freqs_by_class(geno, chrom, sex)
     majf = major_allele_freqs(ref_freq)
     if preferred is not None:  # --indep-preferred: listed variants win every victim comparison (:916-918)
         majf = np.where(np.asarray(preferred, dtype=bool), majf - 1.0, majf)
@@ -396,6 +542,7 @@ def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, 
         idx = idx_all[chrom == c]
         if idx.size < 2:
             continue
+        cls = _chr_class(c)
         groups = []
         if window_is_bp:
             # split where variant_bp - window > previous bp (:2199-2211)
@@ -412,7 +559,8 @@ def ld_prune(geno: np.ndarray, chrom: np.ndarray, bps: np.ndarray, window: int, 
             if len(gidx) < 2:
                 continue
             gidx = np.array(gidx)
-            removed[gidx] = ld_prune_subcontig(geno[gidx], majf[gidx], bps[gidx] if window_is_bp else None, window, step, r2_thresh)
+            g, w = ld_class_block(geno[gidx], cls, sex)
+            removed[gidx] = ld_prune_subcontig(g, majf[gidx], bps[gidx] if window_is_bp else None, window, step, r2_thresh, w=w, order=order)
     return removed
 
 

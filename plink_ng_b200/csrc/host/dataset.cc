@@ -39,7 +39,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
   size_t li = 0;
   // .psam: optional '##' comment lines then a '#FID ...' / '#IID ...' header; .fam: no header, 6 columns
   while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
-  int col_fid = -1, col_iid = -1, col_sid = -1, col_pat = -1, col_mat = -1;
+  int col_fid = -1, col_iid = -1, col_sid = -1, col_pat = -1, col_mat = -1, col_sex = -1;
   if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
     std::vector<std::string> hdr = SplitWs(lines[li].substr(1));
     for (size_t c = 0; c < hdr.size(); ++c) {
@@ -48,6 +48,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
       else if (hdr[c] == "SID") col_sid = static_cast<int>(c);
       else if (hdr[c] == "PAT") col_pat = static_cast<int>(c);
       else if (hdr[c] == "MAT") col_mat = static_cast<int>(c);
+      else if (hdr[c] == "SEX") col_sex = static_cast<int>(c);
     }
     if (col_iid < 0 || (col_fid > 0)) {
       *err = "Invalid .psam header line in " + path + " (#FID or #IID must come first).";
@@ -59,6 +60,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
     col_iid = 1;
     col_pat = 2;
     col_mat = 3;
+    col_sex = 4;
   }
   out->fid_present = col_fid >= 0;
   out->sid_present = col_sid >= 0;
@@ -66,7 +68,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
     if (lines[li].empty()) continue;
     std::vector<std::string> t = SplitWs(lines[li]);
     if (t.empty()) continue;
-    const int need = std::max(std::max(col_iid, col_sid), std::max(col_pat, col_mat));
+    const int need = std::max(std::max(std::max(col_iid, col_sid), std::max(col_pat, col_mat)), col_sex);
     if (static_cast<int>(t.size()) <= need) {
       *err = "Line " + std::to_string(li + 1) + " of " + path + " has fewer tokens than expected.";
       return false;
@@ -76,6 +78,14 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
     out->sid.push_back(col_sid >= 0 ? t[col_sid] : "0");
     const bool founder = (col_pat < 0 || t[col_pat] == "0") && (col_mat < 0 || t[col_mat] == "0");
     out->is_founder.push_back(founder ? 1 : 0);
+    // SEX: '1'/'M'/'m' male, '2'/'F'/'f' female, anything else unknown (plink2_psam.cc:609-623)
+    uint8_t sex = 0;
+    if (col_sex >= 0 && t[col_sex].size() == 1) {
+      const char ch = t[col_sex][0];
+      if (ch == '1' || ch == 'M' || ch == 'm') sex = 1;
+      else if (ch == '2' || ch == 'F' || ch == 'f') sex = 2;
+    }
+    out->sex.push_back(sex);
   }
   if (out->iid.empty()) {
     *err = "No samples in " + path + ".";

@@ -14,6 +14,7 @@ namespace pl2host {
 struct SampleInfo {
   std::vector<std::string> fid, iid, sid;
   std::vector<uint8_t> is_founder;
+  std::vector<uint8_t> sex;  // 0 unknown, 1 male, 2 female (.fam column 5 / .psam SEX)
   bool fid_present = false;  // kfSampleIdFidPresent (plink2_psam.cc:104-130, :279, :823)
   bool sid_present = false;
   uint32_t size() const { return static_cast<uint32_t>(iid.size()); }

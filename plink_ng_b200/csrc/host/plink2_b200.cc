@@ -93,7 +93,7 @@ struct Cmd {
   bool pca = false, pca_approx = false, pca_meanimpute = false;
   uint32_t pc_ct = 10;
   // LD
-  bool indep_pairwise = false, indep_kb = false, bad_ld = false;
+  bool indep_pairwise = false, indep_kb = false, bad_ld = false, indep_order1 = false;
   uint32_t indep_window = 0, indep_step = 1;
   double indep_r2 = 0;
 };
@@ -333,6 +333,12 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (c->indep_kb && c->indep_step != 1) return Usage("--indep-pairwise step size must be 1 when the window is in kilobase units.");
       if (!c->indep_kb && c->indep_step > c->indep_window) return Usage("--indep-pairwise step size cannot exceed the window size.");
       if (!ParseDouble(p[next].c_str(), &c->indep_r2) || c->indep_r2 < 0 || c->indep_r2 >= 1) return Usage("Invalid --indep-pairwise r^2 threshold.");
+    } else if (flag == "--indep-order") {
+      // plink2.cc:7325-7338: 1 = PLINK 1.x pruning order, 2 = default
+      if (!need(1, 1)) return Usage("--indep-order requires one argument.");
+      const std::string m = argv[i + 1];
+      if (m == "1") c->indep_order1 = true;
+      else if (m != "2") return Usage("Invalid --indep-order mode ('1' or '2' expected).");
     } else if (flag == "--bad-ld") {
       c->bad_ld = true;
     } else {
@@ -1824,9 +1830,11 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   }
   uint32_t founder_ct = 0;
   std::vector<uint64_t> inc((n + 63) / 64, 0);
+  std::vector<uint8_t> founder_sex;  // chrX / chrY / MT handling needs it (plink2_ld.cc:1356-1389)
   for (uint32_t k = 0; k < n; ++k) {
     if (S.is_founder[k]) {
       inc[k / 64] |= 1ull << (k % 64);
+      founder_sex.push_back(S.sex[k]);
       ++founder_ct;
     }
   }
@@ -1917,9 +1925,11 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   }
   uint32_t founder_ct = 0;
   std::vector<uint64_t> inc((n + 63) / 64, 0);
+  std::vector<uint8_t> founder_sex;  // chrX / chrY / MT handling needs it (plink2_ld.cc:1356-1389)
   for (uint32_t k = 0; k < n; ++k) {
     if (S.is_founder[k]) {
       inc[k / 64] |= 1ull << (k % 64);
+      founder_sex.push_back(S.sex[k]);
       ++founder_ct;
     }
   }
@@ -1980,7 +1990,8 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("--indep-preferred: %u variant%s loaded.\n", pref_ct, pref_ct == 1 ? "" : "s");
   }
   std::vector<uint8_t> removed(m, 0);
-  const int rc = pl2_indep_pairwise(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, preferred.empty() ? nullptr : preferred.data(), 0, removed.data());
+  const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, preferred.empty() ? nullptr : preferred.data(), 0,
+                                       founder_sex.data(), c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data());
   pl2gpu_host_free(blk);
   if (rc) return GpuFail("pl2_indep_pairwise");
   // LdPruneWrite (plink2_ld.cc:2464-2528)

@@ -48,6 +48,29 @@ static __global__ void __launch_bounds__(256) geno_counts_kernel(const uint8_t* 
   }
 }
 
+// ---- sample gather for the sex-chromosome / haploid forms of the LD block (2.0/plink2_ld.cc:1356-1389):
+// output sample t of every variant row = input sample (map[t] & 0x7FFFFFFF), with a het call turned into
+// "missing" when bit 31 of map[t] is set (SetHetMissing).  A sample listed twice carries weight 2 in every sum
+// of the pair sextuple, which is exactly how chrX counts nonmales (:982-998).  One thread per output byte.
+static __global__ void __launch_bounds__(256) geno_gather_kernel(const uint8_t* __restrict__ in, uint64_t in_pitch, uint8_t* __restrict__ out, uint32_t out_pitch, const uint32_t* __restrict__ map, uint32_t out_sample_ct) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= out_pitch) return;
+  const uint8_t* row = in + static_cast<uint64_t>(blockIdx.y) * in_pitch;
+  uint32_t byte = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) {
+    const uint32_t t = 4 * b + q;
+    uint32_t code = 3;
+    if (t < out_sample_ct) {
+      const uint32_t mv = map[t], s = mv & 0x7FFFFFFFu;
+      code = (row[s >> 2] >> (2 * (s & 3))) & 3;
+      if ((mv >> 31) && code == 1) code = 3;
+    }
+    byte |= code << (2 * q);
+  }
+  out[static_cast<uint64_t>(blockIdx.y) * out_pitch + b] = static_cast<uint8_t>(byte);
+}
+
 __device__ __forceinline__ uint32_t compact_even_bits(uint64_t x) {
   x &= 0x5555555555555555ull;
   x = (x | (x >> 1)) & 0x3333333333333333ull;

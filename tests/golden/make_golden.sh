@@ -62,6 +62,17 @@ awk 'NR%7==3{print $2}' a.bim > a_pref.txt
 $P --bfile a --indep-pairwise 50 5 0.1 --indep-preferred a_pref.txt --threads 2 --out $T/a_ldp > /dev/null
 cp $T/a_ldp.prune.in a_ldpref.prune.in
 cp $T/a_ldkb.prune.in a_ldkb.prune.in
+$P --bfile a --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/a_ldo1 > /dev/null
+cp $T/a_ldo1.prune.in a_ldo1.prune.in
+# --- set X: chromosomes 1 / X / Y / XY / MT with mixed sexes and non-founders (make_x_set.py): the sex-chromosome
+# forms of --indep-pairwise, both pruning orders
+$P --dummy 120 800 0.03 --seed 11 --threads 2 --make-bed --out $T/x0 > /dev/null
+python make_x_set.py $T/x0 x
+$P --bfile x --indep-pairwise 50 5 0.2 --threads 2 --out $T/x_o2 > /dev/null
+$P --bfile x --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/x_o1 > /dev/null
+cp $T/x_o2.prune.in x_o2.prune.in; cp $T/x_o1.prune.in x_o1.prune.in
+$P --bfile x --indep-pairwise 30kb 0.3 --threads 2 --out $T/x_kb > /dev/null
+cp $T/x_kb.prune.in x_kb.prune.in
 if [ -x $PL ]; then
   $PL --bfile a --pca 4 --threads 2 --out $T/a_pca > /dev/null
   cp $T/a_pca.eigenval a_pca.eigenval; cp $T/a_pca.eigenvec a_pca.eigenvec
