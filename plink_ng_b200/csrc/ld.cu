@@ -271,7 +271,6 @@ int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant
     set_error("pl2_indep_pairwise: window size must be >= 2 and step >= 1");
     return 1;
   }
-  const bool plink1_order = (flags_in & kPl2LdPlink1Order) != 0;
   Ctx* c = &ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
   const uint8_t* src = static_cast<const uint8_t*>(genovecs);

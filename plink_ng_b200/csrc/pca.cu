@@ -14,6 +14,7 @@
 #include "pca_kernels.cuh"
 #include "pca_ts_kernels.cuh"
 #include "jacobi.cuh"
+#include "dense_fp64.cuh"
 
 using namespace pl2;
 
@@ -173,7 +174,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     set_error("pl2gpu_pca_run: need 2k(k+1) = %llu <= min(variants %u, samples %u)", static_cast<unsigned long long>(q), m, n);
     return 1;
   }
-  double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr;
+  double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr, *d_gram = nullptr, *d_gram_u = nullptr, *d_gram_partial = nullptr, *d_colscale = nullptr;
   int rc = 1;
   const double m_recip = 1.0 / static_cast<double>(m);
   // ---- tensor path scratch (pca_ts_kernels.cuh): digit planes, per-column scales, split-K partial sums ----
@@ -212,13 +213,20 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     pca_scales_kernel<<<1, 64, 0, c->stream>>>(d_colmax, kPcaCgMax, d_scale, d_inv_scale);
     c->launches += 2;
   };
+  // every dense operand goes through the tensor pipe twice: 30-bit fixed point, then the exact residual at another
+  // 30 bits (pca_digits_kernel pass 1) - 60 bits below the column maximum, so the passes lose nothing against the
+  // reference's fp64 dgemm (one 30-bit pass left the trailing, noise-level eigenvalues 2e-3 off)
+  constexpr int kPasses = 2;
   auto launch_xa_ts = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
     for (uint32_t cc = 0; cc < cols_total; cc += kPcaCgMax) {
       const uint32_t valid = std::min(kPcaCgMax, cols_total - cc), cg = RoundUpU32(valid, 4);
       group_scales(g + cc, g_ld, 1, npad, valid, nullptr, nullptr);
-      pca_digits_kernel<<<npad / 64, 256, 0, c->stream>>>(g + cc, g_ld, 1, npad, cg, valid, nullptr, nullptr, d_scale, d_gdig, nullptr);
-      pca_xa_ts_kernel<<<job->variant_cap / 128, kPxaThreads, kPxaSmemBytes, c->stream>>>(job->tmap_raw, npad, m, d_gdig, cg, valid, job->d_slope, job->d_icpt, d_inv_scale, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld);
-      c->launches += 2;
+      for (int pass = 0; pass < kPasses; ++pass) {
+        pca_digits_kernel<<<npad / 64, 256, 0, c->stream>>>(g + cc, g_ld, 1, npad, cg, valid, nullptr, nullptr, d_scale, d_gdig, nullptr, pass);
+        pca_xa_ts_kernel<<<job->variant_cap / 128, kPxaThreads, kPxaSmemBytes, c->stream>>>(job->tmap_raw, npad, m, d_gdig, cg, valid, job->d_slope, job->d_icpt, d_inv_scale, hout + static_cast<uint64_t>(hcol0 + cc) * h_ld, h_ld,
+                                                                                          pass ? 1.0 / kPcaPass1Scale : 1.0, pass);
+        c->launches += 2;
+      }
     }
   };
   auto launch_xtb_ts = [&](const double* hin, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total, double* out, uint64_t out_rs, uint64_t out_cs) {
@@ -226,11 +234,13 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       const uint32_t valid = std::min(kPcaCgMax, cols_total - cc), cg = RoundUpU32(valid, 4);
       const double* src = hin + static_cast<uint64_t>(hcol0 + cc) * h_ld;
       group_scales(src, 1, h_ld, m, valid, job->d_slope, job->d_icpt);
-      pca_digits_kernel<<<job->variant_cap / 64, 256, 0, c->stream>>>(src, 1, h_ld, m, cg, valid, job->d_slope, job->d_icpt, d_scale, d_hs, d_hi);
-      if (cudaMemsetAsync(d_partial, 0, static_cast<uint64_t>(splits) * npad * cg * 8, c->stream) != cudaSuccess) ts_rc = 1;
-      pca_xtb_ts_kernel<<<dim3(tiles2, splits), kPxtThreads, kPxtSmemBytes, c->stream>>>(job->d_raw_i, kstep_total, ksteps_per_split, n, d_hs, d_hi, cg, d_inv_scale, d_partial, npad);
-      pca_xtb_reduce_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(n) * cg, 256)), 256, 0, c->stream>>>(d_partial, splits, n, npad, cg, valid, 1.0, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
-      c->launches += 3;
+      for (int pass = 0; pass < kPasses; ++pass) {
+        pca_digits_kernel<<<job->variant_cap / 64, 256, 0, c->stream>>>(src, 1, h_ld, m, cg, valid, job->d_slope, job->d_icpt, d_scale, d_hs, d_hi, pass);
+        if (cudaMemsetAsync(d_partial, 0, static_cast<uint64_t>(splits) * npad * cg * 8, c->stream) != cudaSuccess) ts_rc = 1;
+        pca_xtb_ts_kernel<<<dim3(tiles2, splits), kPxtThreads, kPxtSmemBytes, c->stream>>>(job->d_raw_i, kstep_total, ksteps_per_split, n, d_hs, d_hi, cg, d_inv_scale, d_partial, npad);
+        pca_xtb_reduce_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(n) * cg, 256)), 256, 0, c->stream>>>(d_partial, splits, n, npad, cg, valid, pass ? 1.0 / kPcaPass1Scale : 1.0, out + static_cast<uint64_t>(cc) * out_cs, out_rs, out_cs);
+        c->launches += 3;
+      }
     }
   };
   auto launch_xa_fp64 = [&](const double* g, uint32_t g_ld, double* hout, uint64_t h_ld, uint32_t hcol0, uint32_t cols_total) {
@@ -296,25 +306,96 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       break;
     }
     mark("power iterations (Y.G / Yt.H)");
-    // SVD of the Krylov matrix: left singular vectors = orthonormal basis Q of its range   :5860
-    // (one-sided Jacobi, jacobi.cuh; the reference calls dgesvd)
+    // Orthonormal basis Q of the range of the Krylov matrix   :5860 (the reference takes the left singular vectors
+    // from dgesvd; only their span enters B = Y^T Q and everything after it).
+    //   PL2_PCA_BASIS=jacobi (default): one-sided Jacobi SVD of the whole M x q matrix (jacobi.cuh).
+    //   PL2_PCA_BASIS=bcgs: block classical Gram-Schmidt over the k + 1 Krylov blocks, three projection passes per
+    //   block (the blocks span 35 orders of magnitude, two are not enough), each followed by a Jacobi SVD of the
+    //   M x 2k residual whose unit left singular vectors replace the block.  O(M q^2) once instead of per sweep.
     std::vector<double> s(q);
     const char* err = nullptr;
-    if (JacobiSvd(c, d_qq, m, m, static_cast<uint32_t>(q), static_cast<uint32_t>(q), s.data(), d_u, m, nullptr, &err)) {
-      set_error("Failed to compute SVD of Krylov matrix (%s).", err ? err : "?");
-      break;
+    const char* basis_env = getenv("PL2_PCA_BASIS");
+    const bool bcgs = basis_env && !strcmp(basis_env, "bcgs");
+    const double* d_basis = d_u;
+    if (!bcgs) {
+      if (JacobiSvd(c, d_qq, m, m, static_cast<uint32_t>(q), static_cast<uint32_t>(q), s.data(), d_u, m, nullptr, &err)) {
+        set_error("Failed to compute SVD of Krylov matrix (%s).", err ? err : "?");
+        break;
+      }
+    } else {
+      const uint32_t q32 = static_cast<uint32_t>(q);
+      double *d_c = nullptr, *d_cpart = nullptr;
+      bool ok = cudaMalloc(&d_c, q * c2 * 8) == cudaSuccess && cudaMalloc(&d_cpart, DgemmTNPartialDoubles(c, q32, c2, m) * 8) == cudaSuccess;
+      for (uint32_t t = 0; ok && t <= k; ++t) {
+        double* w = d_qq + static_cast<uint64_t>(t) * c2 * m;
+        const uint32_t prev = t * c2;
+        for (int rep = 0; ok && rep < 3; ++rep) {
+          if (prev) {
+            ok = !DgemmTN(c, d_qq, m, prev, w, m, c2, m, d_cpart, d_c, prev) && !DgemmNN(c, d_qq, m, m, prev, d_c, prev, c2, w, m, true, nullptr);
+            if (!ok) break;
+          }
+          if (JacobiSvd(c, w, m, m, c2, c2, s.data(), d_u, m, nullptr, &err)) {
+            ok = false;
+            break;
+          }
+          ok = cudaMemcpyAsync(w, d_u, static_cast<uint64_t>(m) * c2 * 8, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+        }
+      }
+      cudaFree(d_c);
+      cudaFree(d_cpart);
+      if (!ok) {
+        cudaGetLastError();
+        set_error("Failed to orthonormalise the Krylov matrix (%s).", err ? err : "CUDA failure");
+        break;
+      }
+      d_basis = d_qq;
     }
-    mark("SVD of the M x q Krylov matrix");
+    mark(bcgs ? "orthonormal basis of the Krylov matrix (BCGS)" : "SVD of the M x q Krylov matrix");
     // B = Y^T Q (N x q, column-major)   :5870-5916
     if (cudaMemsetAsync(d_b, 0, static_cast<uint64_t>(n) * q * 8, c->stream) != cudaSuccess) break;
-    launch_xtb(d_u, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
+    launch_xtb(d_basis, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
     mark("B = Yt.Q");
-    // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B   :5920
-    if (JacobiSvd(c, d_b, n, n, static_cast<uint32_t>(q), k, s.data(), d_u, n, nullptr, &err)) {
-      set_error("Failed to compute SVD of final matrix (%s).", err ? err : "?");
-      break;
+    // Top-k left singular pairs of B (:5920, dgesvd in the reference).  Only the leading k of q are wanted and they
+    // are the well-conditioned ones, so they come from the q x q Gram matrix: G = B^T B (fp64, fixed-order split
+    // sums), eigenpairs of G by one-sided Jacobi on its columns (G V = V Lambda for a symmetric PSD matrix), then
+    // U_k = B V_k Lambda_k^-1/2.  The relative error of sigma_i is eps (sigma_1 / sigma_i)^2 - 1e-14 here - and the
+    // N x q Jacobi sweep over B (1.2 s at N = 16,384, O(N q^2) per sweep) is gone.  PL2_PCA_FINAL=jacobi keeps it.
+    const char* final_env = getenv("PL2_PCA_FINAL");
+    if (final_env && !strcmp(final_env, "jacobi")) {
+      // Q (d_u) is dead once B is formed (stream order): reuse it for the left singular vectors of B
+      if (JacobiSvd(c, d_b, n, n, static_cast<uint32_t>(q), k, s.data(), d_u, n, nullptr, &err)) {
+        set_error("Failed to compute SVD of final matrix (%s).", err ? err : "?");
+        break;
+      }
+    } else {
+      const uint32_t q32 = static_cast<uint32_t>(q);
+      if (cudaMalloc(&d_gram, q * q * 8) != cudaSuccess || cudaMalloc(&d_gram_u, q * k * 8) != cudaSuccess || cudaMalloc(&d_gram_partial, DgemmTNPartialDoubles(c, q32, q32, n) * 8) != cudaSuccess ||
+          cudaMalloc(&d_colscale, 8ull * k) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pl2gpu_pca_run: insufficient device memory for the %llu x %llu Gram matrix", static_cast<unsigned long long>(q), static_cast<unsigned long long>(q));
+        break;
+      }
+      if (DgemmTN(c, d_b, n, q32, d_b, n, q32, n, d_gram_partial, d_gram, q)) break;
+      if (JacobiSvd(c, d_gram, q, q32, q32, k, s.data(), d_gram_u, q, nullptr, &err)) {
+        set_error("Failed to compute SVD of final matrix (%s).", err ? err : "?");
+        break;
+      }
+      std::vector<double> inv_sigma(k);
+      bool ok = true;
+      for (uint32_t p = 0; p < k; ++p) {
+        ok = ok && s[p] > 0.0;
+        s[p] = sqrt(s[p]);  // eigenvalue of B^T B -> singular value of B
+        inv_sigma[p] = ok ? 1.0 / s[p] : 0.0;
+      }
+      if (!ok) {
+        set_error("Failed to compute SVD of final matrix (rank below the requested number of PCs).");
+        break;
+      }
+      if (cudaMemcpyAsync(d_colscale, inv_sigma.data(), 8ull * k, cudaMemcpyHostToDevice, c->stream) != cudaSuccess) break;
+      // Q (d_u) is dead once B is formed (stream order): reuse it for U_k (N x k, column-major)
+      if (DgemmNN(c, d_b, n, n, q32, d_gram_u, q, k, d_u, n, false, d_colscale)) break;
     }
-    mark("SVD of the N x q matrix B");
+    mark("top-k singular pairs of the N x q matrix B");
     if (cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
       set_error("pl2gpu_pca_run: %s", cudaGetErrorString(cudaGetLastError()));
       break;
@@ -335,6 +416,10 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   cudaFree(d_inv_scale);
   cudaFree(d_colmax);
   cudaFree(d_partial);
+  cudaFree(d_gram);
+  cudaFree(d_gram_u);
+  cudaFree(d_gram_partial);
+  cudaFree(d_colscale);
   cudaFree(d_qq);
   cudaFree(d_u);
   cudaFree(d_g1);

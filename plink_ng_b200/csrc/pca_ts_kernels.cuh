@@ -74,7 +74,10 @@ static __global__ void pca_scales_kernel(const unsigned long long* __restrict__ 
 // ---- fp64 -> four balanced base-256 digit planes in the canonical k-step blocks --------------------------------
 // out1 (and out2 when mul2 != nullptr): [rows_padded / 32][32 * 4 cg] bytes; rows >= `rows` are zero.
 // thread = (row, column); grid.x = rows_padded / 64 (two k-steps per CTA), 64 x cg threads in strides.
-static __global__ void __launch_bounds__(256) pca_digits_kernel(const double* __restrict__ src, uint64_t rs, uint64_t cs, uint32_t rows, uint32_t cg, uint32_t cols_valid, const double* __restrict__ mul1, const double* __restrict__ mul2, const double* __restrict__ scale, uint8_t* __restrict__ out1, uint8_t* __restrict__ out2) {
+// pass 0 encodes rn(y 2^F); pass 1 encodes the residual (y 2^F - rn(y 2^F)) 2^30 (exact in fp64), so the two passes
+// together carry 60 bits below the column maximum - more than the fp64 operand the reference's dgemm reads.
+constexpr double kPcaPass1Scale = 1073741824.0;  // 2^30
+static __global__ void __launch_bounds__(256) pca_digits_kernel(const double* __restrict__ src, uint64_t rs, uint64_t cs, uint32_t rows, uint32_t cg, uint32_t cols_valid, const double* __restrict__ mul1, const double* __restrict__ mul2, const double* __restrict__ scale, uint8_t* __restrict__ out1, uint8_t* __restrict__ out2, int pass) {
   const uint32_t n_total = kPcaDigits * cg;
   const uint32_t blk = pca_block_bytes(n_total);
   for (uint32_t idx = threadIdx.x; idx < 64 * cg; idx += blockDim.x) {
@@ -91,7 +94,9 @@ static __global__ void __launch_bounds__(256) pca_digits_kernel(const double* __
       if (!out) continue;
       const double* mul = which ? mul2 : mul1;
       const double y = (mul && r < rows) ? x * mul[r] : x;
-      long long v = __double2ll_rn(y * sc);
+      const double ys = y * sc;  // exact: sc is a power of two
+      long long v = __double2ll_rn(ys);
+      if (pass) v = __double2ll_rn((ys - static_cast<double>(v)) * kPcaPass1Scale);  // |residual| <= 0.5 -> |v| <= 2^29
 #pragma unroll
       for (uint32_t d = 0; d < kPcaDigits; ++d) {
         const long long dig = ((v + 128) & 255) - 128;  // balanced digit in [-128, 127]
@@ -117,7 +122,8 @@ constexpr uint32_t kPxaThreads = 32 * (kPxaRowWarps + 2);
 
 static __global__ void __launch_bounds__(kPxaThreads, 1)
 pca_xa_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw /* box {16 B, 128 variants} */, uint32_t sample_ct_padded /* multiple of 64 */, uint32_t variant_ct, const uint8_t* __restrict__ gdig /* [samples / 32][32 N] */, uint32_t cg, uint32_t cols_valid,
-                 const double* __restrict__ slope, const double* __restrict__ icpt, const double* __restrict__ inv_scale /* [cg] */, double* __restrict__ h /* column-major, ld = h_ld, first column = this group's */, uint64_t h_ld) {
+                 const double* __restrict__ slope, const double* __restrict__ icpt, const double* __restrict__ inv_scale /* [cg] */, double* __restrict__ h /* column-major, ld = h_ld, first column = this group's */, uint64_t h_ld,
+                 double post_scale /* 1, or 2^-30 for the residual pass */, int accumulate /* add to h instead of overwriting */) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ __align__(8) uint64_t bar_full_a[16];
   __shared__ __align__(8) uint64_t bar_empty_a[16];
@@ -268,7 +274,11 @@ pca_xa_ts_kernel(const __grid_constant__ CUtensorMap tmap_raw /* box {16 B, 128 
             sg = sg * 256 + static_cast<int32_t>(dg[d][c]);
             sm = sm * 256 + static_cast<int32_t>(dm[d][c]);
           }
-          if (c0 + c < cols_valid) h[static_cast<uint64_t>(c0 + c) * h_ld + v] = (sl * static_cast<double>(sg) + ic * static_cast<double>(sm)) * inv_scale[c0 + c];
+          if (c0 + c < cols_valid) {
+            double* dst = &h[static_cast<uint64_t>(c0 + c) * h_ld + v];
+            const double val = (sl * static_cast<double>(sg) + ic * static_cast<double>(sm)) * (inv_scale[c0 + c] * post_scale);
+            *dst = accumulate ? (*dst + val) : val;
+          }
         }
       }
     }

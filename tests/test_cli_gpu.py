@@ -171,6 +171,21 @@ def test_indep_preferred_list_byte_identical(golden_dir, tmp_path):
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldpref.prune.in"), "rb").read()
 
 
+@pytest.mark.parametrize("flags,name", [(("50", "5", "0.2"), "x_o2"), (("50", "5", "0.2", "--indep-order", "1"), "x_o1"), (("30kb", "0.3"), "x_kb")])
+def test_indep_pairwise_sex_chromosomes_byte_identical(golden_dir, tmp_path, flags, name):
+    """Set X (chr 1 / X / Y / XY / MT, males, females, unknown sex, non-founders): chrX male hets -> missing and
+    nonmales at weight 2, chrY nonfemale founders only, MT hets -> missing (2.0/plink2_ld.cc:1356-1389, :982-998)."""
+    out = str(tmp_path / "x")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "x"), "--indep-pairwise", *flags, "--out", out], capture_output=True, text=True, env=ENV)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, name + ".prune.in"), "rb").read()
+
+
+def test_indep_order_1_byte_identical(golden_dir, tmp_path):
+    out = run(golden_dir, tmp_path, "--indep-pairwise", "50", "5", "0.2", "--indep-order", "1")
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldo1.prune.in"), "rb").read()
+
+
 def test_toy_fixture_configs0(golden_dir, tmp_path):
     out = str(tmp_path / "toy")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True, env=ENV)
