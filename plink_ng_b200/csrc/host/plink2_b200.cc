@@ -77,7 +77,7 @@ struct Cmd {
   bool make_king = false, make_king_table = false;
   enum Shape { kTri, kSq, kSq0 } king_shape = kTri, rel_shape = kTri;
   enum Enc { kText, kBin, kBin4 } king_enc = kText, rel_enc = kText;
-  bool king_counts = false;
+  bool king_counts = false, king_zs = false, king_table_zs = false, grm_zs = false, rel_zs = false, freq_zs = false;
   bool col_fid_maybe = true, col_fid = false, col_id = true, col_sid_maybe = true, col_sid = false, col_nsnp = true, col_hethet = true, col_ibs0 = true, col_ibs1 = false, col_hamming = false, col_kinship = true;
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
@@ -216,7 +216,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else if (m == "square") c->king_shape = Cmd::kSq, shape_set = true;
         else if (m == "square0") c->king_shape = Cmd::kSq0, shape_set = true;
         else if (m == "triangle") c->king_shape = Cmd::kTri, shape_set = true;
-        else if (m == "zs") return Usage("--make-king 'zs' output is not supported by plink2_b200.");
+        else if (m == "zs") c->king_zs = true;
         else return Usage(("Invalid --make-king argument '" + m + "'.").c_str());
       }
       if (!shape_set) c->king_shape = (c->king_enc == Cmd::kText) ? Cmd::kTri : Cmd::kSq;  // plink2.cc:8521-8526
@@ -227,7 +227,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         if (m == "counts") c->king_counts = true;
         else if (m.compare(0, 5, "cols=") == 0) {
           if (!ParseKingCols(m.substr(5), c)) return Usage(("Invalid --make-king-table cols= argument '" + m + "'.").c_str());
-        } else if (m == "zs" || m == "rel-check") return Usage("--make-king-table zs / rel-check are not supported by plink2_b200.");
+        } else if (m == "zs") c->king_table_zs = true;
+        else if (m == "rel-check") return Usage("--make-king-table rel-check is not supported by plink2_b200 (write the same-FID pairs to a file and use --king-table-subset).");
         else return Usage(("Invalid --make-king-table argument '" + m + "'.").c_str());
       }
     } else if (flag == "--king-table-filter") {
@@ -253,7 +254,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         if (m == "cov") c->grm_cov = true;
         else if (m == "meanimpute") c->grm_meanimpute = true;
         else if (m == "id-header" || m == "idheader") c->grm_id_header = true;
-        else if (m == "zs") return Usage("--make-grm-sparse 'zs' output is not supported by plink2_b200.");
+        else if (m == "zs") c->grm_zs = true;
         else return Usage(("Invalid --make-grm-sparse argument '" + m + "'.").c_str());
       }
     } else if (flag == "--make-grm-bin" || flag == "--make-grm-list" || flag == "--make-rel") {
@@ -267,7 +268,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         if (m == "cov") c->grm_cov = true;
         else if (m == "meanimpute") c->grm_meanimpute = true;
         else if (m == "id-header" && !is_rel) c->grm_id_header = true;
-        else if (m == "zs" && flag == "--make-grm-list") return Usage("--make-grm-list 'zs' output is not supported by plink2_b200.");
+        else if (m == "zs" && flag == "--make-grm-list") c->grm_zs = true;
+        else if (m == "zs" && is_rel) c->rel_zs = true;
         else if (is_rel && m == "bin") c->rel_enc = Cmd::kBin;
         else if (is_rel && m == "bin4") c->rel_enc = Cmd::kBin4;
         else if (is_rel && m == "square") c->rel_shape = Cmd::kSq, shape_set = true;
@@ -288,7 +290,10 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
       if (c->pc_ct < 1 || c->pc_ct > 8000) return Usage("Invalid --pca PC count.");
     } else if (flag == "--freq") {
-      if (nparam) return Usage("--freq modifiers (counts, zs, cols=, bins) are not supported by plink2_b200.");
+      for (int k = 0; k < nparam; ++k) {
+        if (std::string(prm[k]) == "zs") c->freq_zs = true;
+        else return Usage("--freq modifiers other than 'zs' (counts, cols=, bins) are not supported by plink2_b200.");
+      }
       c->freq = true;
     } else if (flag == "--indep-preferred") {
       if (!need(1, 1)) return Usage("--indep-preferred requires a filename.");
@@ -917,9 +922,9 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   }
   logprintf("--king-table-subset: %llu pair%s loaded.\n", static_cast<unsigned long long>(pair_ct), pair_ct == 1 ? "" : "s");
   const IdFmt idf = KingIdFmt(c, S);
-  const std::string tab_name = c.out + ".kin0";
+  const std::string tab_name = c.out + (c.king_table_zs ? ".kin0.zst" : ".kin0");
   OutFile ftab;
-  if (!ftab.Open(tab_name)) {
+  if (!ftab.Open(tab_name, c.king_table_zs)) {
     logprintf("Error: Failed to open %s for writing.\n", tab_name.c_str());
     return kRetOpenFail;
   }
@@ -1017,8 +1022,9 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   OutFile fmat, ftab;
   std::string mat_name, tab_name;
   if (want_matrix) {
-    mat_name = PieceName(c.out + (c.king_enc == Cmd::kText ? ".king" : ".king.bin"), c);
-    if (!fmat.Open(mat_name)) {
+    const bool mat_zs = c.king_zs && c.king_enc == Cmd::kText;  // SetKingMatrixFname (:1576): text matrices only
+    mat_name = PieceName(c.out + (c.king_enc == Cmd::kText ? ".king" : ".king.bin"), c) + (mat_zs ? ".zst" : "");
+    if (!fmat.Open(mat_name, mat_zs)) {
       logprintf("Error: Failed to open %s for writing.\n", mat_name.c_str());
       return kRetOpenFail;
     }
@@ -1026,8 +1032,8 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   const IdFmt idf = KingIdFmt(c, S);
   std::vector<std::string> fmtids;
   if (want_table) {
-    tab_name = PieceName(c.out + ".kin0", c);
-    if (!ftab.Open(tab_name)) {
+    tab_name = PieceName(c.out + ".kin0", c) + (c.king_table_zs ? ".zst" : "");
+    if (!ftab.Open(tab_name, c.king_table_zs)) {
       logprintf("Error: Failed to open %s for writing.\n", tab_name.c_str());
       return kRetOpenFail;
     }
@@ -1547,9 +1553,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   }
   if (c.make_grm_list) {
     // `.grm`: one line per pair i <= j, "j+1 <tab> i+1 <tab> observation count <tab> value" (2.0/plink2_matrix_calc.cc:5082-5106)
-    const std::string gname = PieceName(c.out + ".grm", c);
+    const std::string gname = PieceName(c.out + ".grm", c) + (c.grm_zs ? ".zst" : "");
     OutFile fg;
-    if (!fg.Open(gname)) return kRetOpenFail;
+    if (!fg.Open(gname, c.grm_zs)) return kRetOpenFail;
     std::string line;
     char num[64];
     for (uint32_t a = r0; a < r1;) {
@@ -1590,9 +1596,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   if (c.make_grm_sparse) {
     // `.grm.sp` (GCTA sparse GRM): "j <tab> i <tab> value" (0-based, 8 significant digits) for every i <= j whose
     // value is not below the cutoff (2.0/plink2_matrix_calc.cc:5064-5081)
-    const std::string gname = PieceName(c.out + ".grm.sp", c);
+    const std::string gname = PieceName(c.out + ".grm.sp", c) + (c.grm_zs ? ".zst" : "");
     OutFile fg;
-    if (!fg.Open(gname)) return kRetOpenFail;
+    if (!fg.Open(gname, c.grm_zs)) return kRetOpenFail;
     for (uint32_t a = r0; a < r1;) {
       const uint32_t b = chunk_end(a);
       if (!fetch(a, b)) {
@@ -1628,13 +1634,14 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   }
   if (c.make_rel) {
     const std::string base_name = c.out + (c.rel_enc == Cmd::kText ? ".rel" : ".rel.bin");
-    const std::string rname = PieceName(base_name, c);
+    const bool rel_zs = c.rel_zs && c.rel_enc == Cmd::kText;
+    const std::string rname = PieceName(base_name, c) + (rel_zs ? ".zst" : "");
     if (c.rel_shape == Cmd::kSq && c.parallel_tot != 1) {
       logprintf("Error: --make-rel square output cannot be combined with --parallel; use square0 or triangle.\n");
       return kRetInvalidCmdline;
     }
     OutFile fr;
-    if (!fr.Open(rname)) return kRetOpenFail;
+    if (!fr.Open(rname, rel_zs)) return kRetOpenFail;
     std::vector<double> full;  // square: whole lower triangle incl. diagonal
     auto tri1 = [](uint64_t r) { return r * (r + 1) / 2; };
     if (c.rel_shape == Cmd::kSq) full.resize(tri1(n));
@@ -1851,9 +1858,9 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   BlockStreamer bs(ds, &all, founder_ct, 16384);
   if (founder_ct != n) bs.sample_include = inc.data();
   if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
-  const std::string name = c.out + ".afreq";
+  const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
   OutFile f;
-  if (!f.Open(name)) return kRetOpenFail;
+  if (!f.Open(name, c.freq_zs)) return kRetOpenFail;
   f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
   std::vector<uint32_t> counts;
   std::string err;
@@ -2030,6 +2037,19 @@ int DebugHooks(int argc, char** argv) {
       w = p8 ? dtoa_g_p8(x, w) : dtoa_g(x, w);
       *w++ = '\n';
       out.Advance(w);
+    }
+    fclose(in);
+    return out.Close() ? 0 : kRetWriteFail;
+  }
+  if (argc == 4 && !strcmp(argv[1], "--debug-zst")) {  // <in> <out.zst>: the 'zs' writer on its own (mixed small and large writes)
+    FILE* in = fopen(argv[2], "rb");
+    OutFile out;
+    if (!in || !out.Open(argv[3], true)) return kRetOpenFail;
+    std::vector<char> chunk(3 << 20);
+    size_t want = 7, got;
+    while ((got = fread(chunk.data(), 1, std::min(want, chunk.size()), in)) > 0) {
+      out.Write(chunk.data(), got);
+      want = want * 5 + 3;
     }
     fclose(in);
     return out.Close() ? 0 : kRetWriteFail;

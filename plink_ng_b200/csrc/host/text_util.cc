@@ -1,5 +1,7 @@
 #include "text_util.h"
 
+#include <dlfcn.h>
+
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -266,17 +268,54 @@ char* dtoa_g_p8(double x, char* p) {
   return q;
 }
 
-bool OutFile::Open(const std::string& path) {
+namespace {
+// the three libzstd entry points a one-shot frame needs (stable ABI since zstd 1.0)
+struct ZstdApi {
+  size_t (*compress_bound)(size_t) = nullptr;
+  size_t (*compress)(void*, size_t, const void*, size_t, int) = nullptr;
+  unsigned (*is_error)(size_t) = nullptr;
+  bool ok = false;
+};
+const ZstdApi& Zstd() {
+  static const ZstdApi api = [] {
+    ZstdApi a;
+    void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      a.compress_bound = reinterpret_cast<size_t (*)(size_t)>(dlsym(h, "ZSTD_compressBound"));
+      a.compress = reinterpret_cast<size_t (*)(void*, size_t, const void*, size_t, int)>(dlsym(h, "ZSTD_compress"));
+      a.is_error = reinterpret_cast<unsigned (*)(size_t)>(dlsym(h, "ZSTD_isError"));
+      a.ok = a.compress_bound && a.compress && a.is_error;
+    }
+    return a;
+  }();
+  return api;
+}
+}  // namespace
+
+bool OutFile::Open(const std::string& path, bool zst) {
+  zst_ = zst;
+  pos_ = 0;
+  if (zst_ && !Zstd().ok) {
+    ok_ = false;  // libzstd is not on this system: refuse rather than write an uncompressed file under a .zst name
+    return false;
+  }
   f_ = fopen(path.c_str(), "wb");
   buf_.resize(1 << 20);
-  pos_ = 0;
   ok_ = f_ != nullptr;
   return ok_;
 }
 
 void OutFile::Flush() {
   if (f_ && pos_) {
-    if (fwrite(buf_.data(), 1, pos_, f_) != pos_) ok_ = false;
+    if (zst_) {
+      const ZstdApi& z = Zstd();
+      zbuf_.resize(z.compress_bound(pos_));
+      const size_t n = z.compress(zbuf_.data(), zbuf_.size(), buf_.data(), pos_, 3);
+      if (z.is_error(n) || fwrite(zbuf_.data(), 1, n, f_) != n) ok_ = false;
+    } else if (fwrite(buf_.data(), 1, pos_, f_) != pos_) {
+      ok_ = false;
+    }
   }
   pos_ = 0;
 }
@@ -299,9 +338,25 @@ char* OutFile::Reserve(size_t n) {
 }
 
 void OutFile::Write(const void* p, size_t n) {
-  if (n >= buf_.size() / 2) {
+  if (n >= buf_.size() / 2 && !zst_) {
     Flush();
     if (f_ && fwrite(p, 1, n, f_) != n) ok_ = false;
+    return;
+  }
+  if (zst_) {  // large writes go through the frame buffer in pieces
+    const char* src = static_cast<const char*>(p);
+    while (n) {
+      const size_t room = buf_.size() - pos_;
+      if (!room) {
+        Flush();
+        continue;
+      }
+      const size_t take = n < room ? n : room;
+      memcpy(buf_.data() + pos_, src, take);
+      pos_ += take;
+      src += take;
+      n -= take;
+    }
     return;
   }
   char* d = Reserve(n);

@@ -25,7 +25,10 @@ class OutFile {
  public:
   OutFile() = default;
   ~OutFile() { Close(); }
-  bool Open(const std::string& path);
+  // zst: Zstandard-compressed output (the reference's 'zs' modifiers; its writers go through zstd's streaming
+  // API, 2.0/include/plink2_zstfile / plink2_compress_stream).  Here every flushed buffer becomes one complete
+  // frame (concatenated frames are a valid .zst stream); libzstd.so.1 is resolved at run time.
+  bool Open(const std::string& path, bool zst = false);
   bool Close();  // true iff every write succeeded
   char* Reserve(size_t n);  // pointer to >= n writable bytes
   void Advance(char* new_end) { pos_ = static_cast<size_t>(new_end - buf_.data()); }
@@ -39,6 +42,8 @@ class OutFile {
   std::vector<char> buf_;
   size_t pos_ = 0;
   bool ok_ = true;
+  bool zst_ = false;
+  std::vector<char> zbuf_;
 };
 
 std::vector<std::string> SplitWs(const std::string& line);

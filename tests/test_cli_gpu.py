@@ -186,6 +186,44 @@ def test_indep_order_1_byte_identical(golden_dir, tmp_path):
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldo1.prune.in"), "rb").read()
 
 
+def _zstd_decompress(path):
+    """All frames of a .zst file through the system libzstd (ctypes; the python zstandard module is not in this image)."""
+    import ctypes as C
+
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_findFrameCompressedSize.restype = C.c_size_t
+    z.ZSTD_findFrameCompressedSize.argtypes = [C.c_void_p, C.c_size_t]
+    z.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+    z.ZSTD_getFrameContentSize.argtypes = [C.c_void_p, C.c_size_t]
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    raw = open(path, "rb").read()
+    buf = C.create_string_buffer(raw, len(raw))
+    base = C.addressof(buf)
+    out, off = b"", 0
+    while off < len(raw):
+        fsz = z.ZSTD_findFrameCompressedSize(base + off, len(raw) - off)
+        assert not z.ZSTD_isError(fsz)
+        n = z.ZSTD_getFrameContentSize(base + off, fsz)
+        dst = C.create_string_buffer(max(int(n), 1))
+        got = z.ZSTD_decompress(dst, n, base + off, fsz)
+        assert got == n
+        out += dst.raw[:n]
+        off += fsz
+    return out
+
+
+def test_zs_outputs_decompress_to_the_reference_files(golden_dir, tmp_path):
+    """'zs' modifiers: <name>.zst holds exactly the bytes of the uncompressed report (file names per SetKingTableFname,
+    2.0/plink2_matrix_calc.cc:1576-1609)."""
+    out = run(golden_dir, tmp_path, "--make-king-table", "zs", "--make-king", "square", "zs")
+    assert _zstd_decompress(out + ".kin0.zst") == gz(golden_dir, "a_kingp.kin0.gz")
+    assert _zstd_decompress(out + ".king.zst") == gz(golden_dir, "a_kingsq.king.gz")
+    assert not os.path.exists(out + ".kin0")
+    out = run(golden_dir, tmp_path, "--freq", "zs")
+    assert _zstd_decompress(out + ".afreq.zst") == open(os.path.join(golden_dir, "a.afreq"), "rb").read()
+
+
 def test_toy_fixture_configs0(golden_dir, tmp_path):
     out = str(tmp_path / "toy")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True, env=ENV)

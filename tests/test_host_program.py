@@ -163,7 +163,7 @@ int main(int argc, char** argv) {
 @pytest.mark.parametrize("flags,fragment", [
     (("--glm",), "unsupported"),
     (("--make-grm-bin", "--make-grm-list"), "--make-grm-list cannot be used with --make-grm-bin"),
-    (("--make-grm-list", "zs"), "not supported"),
+    (("--make-king-table", "rel-check"), "not supported"),
     (("--indep-preferred", "x.txt"), "--indep-preferred must be used with --indep-pairwise"),
     (("--make-king-table", "--king-table-subset"), "--king-table-subset requires"),
     (("--pca", "0"), "Invalid --pca PC count"),
@@ -186,3 +186,33 @@ def test_no_gpu_means_loud_failure_not_a_cpu_fallback(golden_dir, tmp_path):
     assert r.returncode == 16, r.stdout + r.stderr
     assert "GPU" in r.stdout
     assert not os.path.exists(str(tmp_path / "x") + ".kin0")
+
+
+def test_zs_writer_roundtrip(tmp_path):
+    """OutFile's Zstandard mode (the 'zs' output modifiers): frames written through libzstd decompress to the input."""
+    import ctypes as C
+
+    import numpy as np
+
+    data = np.random.default_rng(0).integers(0, 7, size=5_000_000, dtype=np.uint8).tobytes()
+    (tmp_path / "in.bin").write_bytes(data)
+    subprocess.run([BIN, "--debug-zst", str(tmp_path / "in.bin"), str(tmp_path / "out.zst")], check=True)
+    raw = (tmp_path / "out.zst").read_bytes()
+    assert len(raw) < len(data) // 2
+    z = C.CDLL("libzstd.so.1")
+    z.ZSTD_findFrameCompressedSize.restype = C.c_size_t
+    z.ZSTD_findFrameCompressedSize.argtypes = [C.c_void_p, C.c_size_t]
+    z.ZSTD_getFrameContentSize.restype = C.c_ulonglong
+    z.ZSTD_getFrameContentSize.argtypes = [C.c_void_p, C.c_size_t]
+    z.ZSTD_decompress.restype = C.c_size_t
+    z.ZSTD_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+    buf = C.create_string_buffer(raw, len(raw))
+    base, off, out = C.addressof(buf), 0, b""
+    while off < len(raw):
+        fsz = z.ZSTD_findFrameCompressedSize(base + off, len(raw) - off)
+        n = z.ZSTD_getFrameContentSize(base + off, fsz)
+        dst = C.create_string_buffer(int(n))
+        assert z.ZSTD_decompress(dst, n, base + off, fsz) == n
+        out += dst.raw[:n]
+        off += fsz
+    assert out == data
