@@ -1924,12 +1924,6 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       }
     }
   }
-  for (uint32_t v = 0; v < V.size(); ++v) {
-    if (V.chr_code[v] > 22 && V.chr_code[v] != 25) {
-      logprintf("Error: --indep-pairwise on chrX/chrY/chrMT variants is not supported by plink2_b200 yet (restrict to autosomes first).\n");
-      return kRetNotYetSupported;
-    }
-  }
   uint32_t founder_ct = 0;
   std::vector<uint64_t> inc((n + 63) / 64, 0);
   std::vector<uint8_t> founder_sex;  // chrX / chrY / MT handling needs it (plink2_ld.cc:1356-1389)

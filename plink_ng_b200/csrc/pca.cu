@@ -308,14 +308,18 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     mark("power iterations (Y.G / Yt.H)");
     // Orthonormal basis Q of the range of the Krylov matrix   :5860 (the reference takes the left singular vectors
     // from dgesvd; only their span enters B = Y^T Q and everything after it).
-    //   PL2_PCA_BASIS=jacobi (default): one-sided Jacobi SVD of the whole M x q matrix (jacobi.cuh).
-    //   PL2_PCA_BASIS=bcgs: block classical Gram-Schmidt over the k + 1 Krylov blocks, three projection passes per
-    //   block (the blocks span 35 orders of magnitude, two are not enough), each followed by a Jacobi SVD of the
-    //   M x 2k residual whose unit left singular vectors replace the block.  O(M q^2) once instead of per sweep.
+    //   Default: block classical Gram-Schmidt over the k + 1 Krylov blocks, three projection passes per block (the
+    //   blocks span 35 orders of magnitude - two passes are not enough), each followed by a Jacobi SVD of the M x 2k
+    //   residual whose unit left singular vectors replace the block.  O(M q^2) once instead of per Jacobi sweep:
+    //   0.36 s instead of 7.9 s at 65,536 x 840 (profiles/r02_pca_timing.txt).
+    //   PL2_PCA_BASIS=jacobi: one-sided Jacobi SVD of the whole M x q matrix (jacobi.cuh), the round-1 form.
+    //   Both give the structure PCs to 1e-13 of the LAPACK-based restatement and differ from it by 1e-4..1e-3 in the
+    //   noise-level eigenvalues (profiles/r02_pca_basis_compare.txt): the Krylov matrix is numerically rank deficient
+    //   and every method completes the basis differently there.
     std::vector<double> s(q);
     const char* err = nullptr;
     const char* basis_env = getenv("PL2_PCA_BASIS");
-    const bool bcgs = basis_env && !strcmp(basis_env, "bcgs");
+    const bool bcgs = !(basis_env && !strcmp(basis_env, "jacobi"));
     const double* d_basis = d_u;
     if (!bcgs) {
       if (JacobiSvd(c, d_qq, m, m, static_cast<uint32_t>(q), static_cast<uint32_t>(q), s.data(), d_u, m, nullptr, &err)) {
@@ -396,7 +400,8 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       if (DgemmNN(c, d_b, n, n, q32, d_gram_u, q, k, d_u, n, false, d_colscale)) break;
     }
     mark("top-k singular pairs of the N x q matrix B");
-    if (cudaMemcpy(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    // the context's stream is non-blocking: order the copy on it (a plain cudaMemcpy would not wait for the kernels)
+    if (cudaMemcpyAsync(eigvecs_host, d_u, 8ull * k * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
       set_error("pl2gpu_pca_run: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }

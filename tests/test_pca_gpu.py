@@ -99,9 +99,31 @@ def test_approx_pca_k20_tensor_path_matches_oracle(gpu_ctx):
     g1 = np.random.default_rng(3).standard_normal((n, 2 * k))
     want_vals, want_vecs = orc.pca_approx(geno, k, g1)
     vals, vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
-    assert np.allclose(vals, want_vals, rtol=1e-6)
     top = 7  # 8 populations -> 7 structure PCs
+    assert np.allclose(vals[:top], want_vals[:top], rtol=1e-9)
     assert np.allclose(_align(vecs[:top], want_vecs[:top]), want_vecs[:top], atol=1e-5 * np.abs(want_vecs[:top]).max())
+    # The 13 noise-level eigenvalues are Ritz values over a numerically rank-deficient Krylov space (its singular
+    # values span 1e35 .. 1e-4): LAPACK's SVD in the restatement, one-sided Jacobi and block Gram-Schmidt each complete
+    # the basis differently there, and the values move by 1e-4 .. 1e-3 (profiles/r02_pca_basis_compare.txt; the
+    # reference's own comparison against PLINK 1.9 allows 9e-3, 2.0/Tests/TEST_PHASED_VCF/run_tests.sh:76-99).
+    assert np.allclose(vals[top:], want_vals[top:], rtol=3e-3)
+
+
+@pytest.mark.parametrize("basis,final", [("jacobi", "jacobi"), ("jacobi", "gram"), ("bcgs", "jacobi")])
+def test_approx_pca_alternative_factorizations_agree(gpu_ctx, monkeypatch, basis, final):
+    """The non-default ways through the two dense factorizations (PL2_PCA_BASIS / PL2_PCA_FINAL) give the same
+    structure PCs as the default (block Gram-Schmidt basis, Gram-matrix final stage)."""
+    from plink_ng_b200.host import pca_approx
+
+    n, m, k = 700, 5000, 8
+    geno = _structured_geno(m, n, seed=33, pops=6, fst=0.1)
+    g1 = np.random.default_rng(5).standard_normal((n, 2 * k))
+    ref_vals, ref_vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
+    monkeypatch.setenv("PL2_PCA_BASIS", basis)
+    monkeypatch.setenv("PL2_PCA_FINAL", final)
+    vals, vecs = pca_approx(gpu_ctx, pack_genotypes(geno), n, k, g1)
+    assert np.allclose(vals[:5], ref_vals[:5], rtol=1e-9) and np.allclose(vals, ref_vals, rtol=3e-3)
+    assert np.allclose(_align(vecs[:5], ref_vecs[:5]), ref_vecs[:5], atol=1e-6 * np.abs(ref_vecs[:5]).max())
 
 
 def test_approx_pca_cli_matches_reference_files(golden_dir, tmp_path):
