@@ -327,9 +327,10 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
         break;
       }
     } else {
-      const uint32_t q32 = static_cast<uint32_t>(q);
       double *d_c = nullptr, *d_cpart = nullptr;
-      bool ok = cudaMalloc(&d_c, q * c2 * 8) == cudaSuccess && cudaMalloc(&d_cpart, DgemmTNPartialDoubles(c, q32, c2, m) * 8) == cudaSuccess;
+      uint64_t part_doubles = 1;
+      for (uint32_t t = 1; t <= k; ++t) part_doubles = std::max(part_doubles, DgemmTNPartialDoubles(c, t * c2, c2, m));
+      bool ok = cudaMalloc(&d_c, q * c2 * 8) == cudaSuccess && cudaMalloc(&d_cpart, part_doubles * 8) == cudaSuccess;
       for (uint32_t t = 0; ok && t <= k; ++t) {
         double* w = d_qq + static_cast<uint64_t>(t) * c2 * m;
         const uint32_t prev = t * c2;

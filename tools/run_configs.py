@@ -136,8 +136,50 @@ def c4(n=50000, m=1000000):
             "kept_variants": kept, "prune_in_identical": bool(same_in), "prune_out_identical": bool(same_out), "speedup_process": t_ref / t_ours}
 
 
+def c3(n=100000, m=1000000, n_ref=8192, m_ref=32768):
+    """Config 3's job at its stated size on ONE GPU (the 8-GPU row-block form is `--gpus 8`): --make-grm-bin, then
+    --pca 20 approx (exact --pca is out of the reference's own reach at 100k samples: dsyevr on an 80 GB matrix).
+    The reference (LAPACK build, threaded OpenBLAS) is timed on an n_ref x m_ref corner of the same file and
+    scaled by pairs x variants (GRM) / samples x variants (PCA passes)."""
+    d = os.environ.get("PL2_CFG_DIR", "/tmp/pl2_c3")
+    os.makedirs(d, exist_ok=True)
+    pre = os.path.join(d, "c3")
+    gen_s = write_pgen(pre, n, m)
+    cores = bench.effective_cores()
+    env = dict(os.environ, PL2_TIMING="1")
+    out = {"config": "C3: --make-grm-bin + --pca 20 (approx), 100k samples x 1M SNPs; single B200 here", "samples": n, "variants": m,
+           "input": "mode 0x02 .pgen, %.2f GB, generated in %.1f s" % (os.path.getsize(pre + ".pgen") / 1e9, gen_s), "host_cpus": cores}
+    t_grm, r = run([BIN, "--pfile", pre, "--make-grm-bin", "--out", pre + "_b200"], env)
+    out["grm"] = {"b200_seconds_process": t_grm, "pair_snp_per_s": n * (n + 1) / 2 * m / t_grm, "phases": [ln for ln in r.stderr.split("\n") if ln.startswith("[timing]")],
+                  "grm_bin_bytes": os.path.getsize(pre + "_b200.grm.bin"), "grm_N_bin_bytes": os.path.getsize(pre + "_b200.grm.N.bin")}
+    # spot check of the written matrix: the n_ref-sample corner against the same job on the corner's own file
+    corner = np.fromfile(pre + "_b200.grm.bin", dtype=np.float32, count=n_ref * (n_ref + 1) // 2)
+    for suffix in (".grm.bin", ".grm.N.bin"):
+        os.remove(pre + "_b200" + suffix)
+    t_pca, r = run([BIN, "--pfile", pre, "--pca", "20", "approx", "--seed", "1", "--out", pre + "_b200"], env)
+    out["pca"] = {"b200_seconds_process": t_pca, "phases": [ln for ln in r.stderr.split("\n") if ln.startswith("[timing]")], "eigenval_head": open(pre + "_b200.eigenval").read().split()[:5]}
+    # reference on a corner of the same file: first n_ref samples, first m_ref variants
+    with open(pre + "_keep.txt", "w") as f:
+        f.write("".join(f"per{k}\n" for k in range(n_ref)))
+    sub = ["--keep", pre + "_keep.txt", "--chr", "1", "--from-bp", "1", "--to-bp", str(m_ref), "--threads", str(cores["threads_used"]), "--memory", "120000"]
+    lib_env = dict(os.environ)  # the LAPACK build finds the venv's OpenBLAS through its rpath
+    t_ref_grm, _ = run([REF + "_lapack", "--pfile", pre] + sub + ["--make-grm-bin", "--out", pre + "_refgrm"], lib_env)
+    t_ref_pca, _ = run([REF + "_lapack", "--pfile", pre] + sub + ["--pca", "20", "approx", "--seed", "1", "--out", pre + "_refpca"], lib_env)
+    pairs_ref = n_ref * (n_ref + 1) / 2
+    out["reference"] = {"binary": "oracle/_ref/plink2_lapack (threaded OpenBLAS)", "samples": n_ref, "variants": m_ref, "threads": cores["threads_used"],
+                        "grm_seconds_process": t_ref_grm, "grm_pair_snp_per_s": pairs_ref * m_ref / t_ref_grm, "grm_seconds_extrapolated_to_full": t_ref_grm * (n * (n + 1) / 2 * m) / (pairs_ref * m_ref),
+                        "pca_seconds_process": t_ref_pca, "pca_seconds_extrapolated_to_full": t_ref_pca * (n * m) / (n_ref * m_ref)}
+    # ours on the SAME corner (own files) for the parity of the written GRM: corner of the big matrix == small job up to the allele frequencies
+    # (the big job's frequencies come from all 100k samples, so this is a loose sanity bound, not a parity test - parity lives in tests/test_scale_gpu.py)
+    ref_grm = np.fromfile(pre + "_refgrm.grm.bin", dtype=np.float32)
+    out["grm_corner_vs_reference_corner_max_abs_diff"] = float(np.abs(corner - ref_grm).max())
+    out["speedup_grm_process_vs_extrapolated_reference"] = out["reference"]["grm_seconds_extrapolated_to_full"] / t_grm
+    out["speedup_pca_process_vs_extrapolated_reference"] = out["reference"]["pca_seconds_extrapolated_to_full"] / t_pca
+    return out
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     args = [int(x) for x in sys.argv[2:]]
-    res = c2(*args) if which == "c2" else c4(*args)
+    res = {"c2": c2, "c3": c3, "c4": c4}[which](*args)
     print(json.dumps(res))
