@@ -159,7 +159,9 @@ enum {
 };
 int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int flags, Pl2GrmJob** job_ptr);
 /* ref_freqs: host double[variant_ct] REF allele frequencies (the caller's allele_freqs); NULL =
- * compute them from this block's genotype counts as ComputeAlleleFreqs does (all samples founders).
+ * compute them from this block's genotype counts as ComputeAlleleFreqs does (all samples founders);
+ * a NaN entry means the same for that one variant (partial --read-freq files).  The same convention
+ * holds for pl2gpu_pca_add_variants and pl2_indep_pairwise[_ex].
  * Returns 2 (kPglRetDegenerateData at the call site) when a zero-variance frequency meets a
  * non-monomorphic variant, like ExpandCenteredVarmaj :3844-3868. */
 int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs);

@@ -212,6 +212,36 @@ def major_allele_freqs(ref_freq: np.ndarray) -> np.ndarray:
     return np.where(ref_freq >= 0.5, ref_freq, np.maximum(1.0 - ref_freq, 0.0))
 
 
+def read_freq_overrides(path: str, ids, ref_alleles, alt_alleles) -> np.ndarray:
+    """`--read-freq` on a PLINK 2 --freq report (ReadAlleleFreqs, 2.0/plink2_filter.cc:2242-3300, the
+    kfReadFreqColsetAltFreqs branch for biallelic variants, no pseudocount): per dataset variant the loaded REF
+    frequency, NaN where the file has no usable entry (unknown ID, allele codes that do not match, nan; OBS_CT is only
+    consulted for count columns, :3170-3175, so a frequency line with OBS_CT 0 is still loaded).
+    REF/ALT listed the other way round: the listed ALT frequency is the dataset's REF frequency (:3187-3192)."""
+    idx = {v: k for k, v in enumerate(ids)}
+    out = np.full(len(ids), np.nan)
+    with open(path) as f:
+        hdr = f.readline().rstrip("\n").lstrip("#").split("\t")
+        col = {name: i for i, name in enumerate(hdr)}
+        for ln in f:
+            t = ln.rstrip("\n").split("\t")
+            k = idx.get(t[col["ID"]])
+            if k is None:
+                continue
+            try:
+                af = float(t[col["ALT_FREQS"]])
+            except ValueError:
+                continue
+            if af != af:
+                continue
+            fr, fa = t[col["REF"]], t[col["ALT"]]
+            if fr == ref_alleles[k] and fa == alt_alleles[k]:
+                out[k] = 1.0 - af
+            elif fr == alt_alleles[k] and fa == ref_alleles[k]:
+                out[k] = af
+    return out
+
+
 # --------------------------------------------------------------------------------------------- GRM
 def centered_varmaj(geno: np.ndarray, ref_freq: np.ndarray, variance_standardize: bool = True) -> np.ndarray:
     """ExpandCenteredVarmaj + PopulateRescaledDosage (2.0/plink2_matrix_calc.cc:3839-3886,

@@ -124,7 +124,7 @@ static int GrmPrepAndLaunch(Pl2GrmJob* job, uint32_t b, uint32_t cur, bool pad_v
     const uint32_t n0 = h_counts[4ull * v], n1 = h_counts[4ull * v + 1], n2 = h_counts[4ull * v + 2], n3 = h_counts[4ull * v + 3];
     if (n3) job->variants_with_missing++;
     double ref_freq;
-    if (ref_freqs) {
+    if (ref_freqs && ref_freqs[v] == ref_freqs[v]) {  // NaN entry: compute this variant's frequency from the block
       ref_freq = ref_freqs[v];
     } else {
       const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);

@@ -42,6 +42,7 @@ struct Dataset {
   SampleInfo samples;
   VariantInfo variants;
   PgenReader reader;
+  std::vector<double> read_ref_freq;  // --read-freq: loaded REF frequency per variant, NaN = not loaded (empty: flag absent)
 };
 
 }  // namespace pl2host

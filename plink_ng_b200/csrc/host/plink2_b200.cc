@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <ctime>
 #include <string>
 #include <thread>
@@ -84,6 +85,7 @@ struct Cmd {
   // GRM
   bool freq = false;                      // --freq
   std::string indep_preferred;            // --indep-preferred <file of variant IDs>
+  std::string read_freq;                  // --read-freq <PLINK 2 --freq report>
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
   bool make_grm_sparse = false;            // --make-grm-sparse <cutoff>
@@ -295,6 +297,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else return Usage("--freq modifiers other than 'zs' (counts, cols=, bins) are not supported by plink2_b200.");
       }
       c->freq = true;
+    } else if (flag == "--read-freq") {
+      if (!need(1, 1)) return Usage("--read-freq requires a filename.");
+      c->read_freq = prm[0];
     } else if (flag == "--indep-preferred") {
       if (!need(1, 1)) return Usage("--indep-preferred requires a filename.");
       c->indep_preferred = prm[0];
@@ -1379,6 +1384,123 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
 // ------------------------------------------------------------------------------------------ GRM
 // ComputeAlleleFreqs over founders (plink2.cc:2301, plink2_filter.cc:2113-2151).  Returns false
 // when every sample is a founder (the library then derives the same numbers from each block).
+// --read-freq (ReadAlleleFreqs, 2.0/plink2_filter.cc:2242-3300): the PLINK 2 --freq report form (ID, REF, ALT,
+// ALT_FREQS columns), biallelic lines.  A line whose REF/ALT are the dataset's ALT/REF gives the dataset's REF
+// frequency directly (:3187-3192); unknown IDs, foreign allele codes and nan entries are skipped with the reference's
+// warning; OBS_CT is not consulted for frequency columns (:3170-3175).  Variants without an entry keep the
+// frequency computed from the data.
+int LoadReadFreq(const Cmd& c, Dataset* ds) {
+  const VariantInfo& V = ds->variants;
+  std::vector<std::string> lines;
+  std::string err;
+  if (!ReadLines(c.read_freq, &lines, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  size_t li = 0;
+  while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
+  if (li == lines.size()) {
+    logprintf("Error: Empty --read-freq file.\n");
+    return kRetMalformedInput;
+  }
+  int col_id = -1, col_ref = -1, col_alt = -1, col_af = -1;
+  {
+    std::string h = lines[li];
+    if (h.empty() || h[0] != '#') {
+      logprintf("Error: Unrecognized header line in --read-freq file (plink2_b200 reads PLINK 2 --freq reports only).\n");
+      return kRetMalformedInput;
+    }
+    const std::vector<std::string> hdr = SplitWs(h.substr(1));
+    for (size_t k = 0; k < hdr.size(); ++k) {
+      if (hdr[k] == "ID") col_id = static_cast<int>(k);
+      else if (hdr[k] == "REF") col_ref = static_cast<int>(k);
+      else if (hdr[k] == "ALT" || hdr[k] == "ALT1") col_alt = static_cast<int>(k);
+      else if (hdr[k] == "ALT_FREQS" || hdr[k] == "ALT1_FREQ") col_af = static_cast<int>(k);
+    }
+    if (col_id < 0 || col_ref < 0 || col_alt < 0) {
+      logprintf("Error: Missing column(s) in --read-freq file (ID, REF, ALT[1] required).\n");
+      return kRetMalformedInput;
+    }
+    if (col_af < 0) {
+      logprintf("Error: --read-freq files without an ALT_FREQS column (count / PLINK 1.x formats) are not supported by plink2_b200.\n");
+      return kRetNotYetSupported;
+    }
+    ++li;
+  }
+  logprintf("--read-freq: PLINK 2 --freq file detected.\n");
+  std::unordered_map<std::string, uint32_t> by_id;
+  std::unordered_map<std::string, uint32_t> dup;
+  by_id.reserve(static_cast<size_t>(V.size()) * 2);
+  for (uint32_t v = 0; v < V.size(); ++v) {
+    if (!by_id.emplace(V.id[v], v).second) dup.emplace(V.id[v], v);
+  }
+  ds->read_ref_freq.assign(V.size(), std::numeric_limits<double>::quiet_NaN());
+  std::vector<uint8_t> seen(V.size(), 0);
+  const int need_cols = std::max(std::max(col_id, col_ref), std::max(col_alt, col_af));
+  uint64_t loaded = 0, skipped = 0;
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    const std::vector<std::string> t = SplitWs(lines[li]);
+    if (static_cast<int>(t.size()) <= need_cols) {
+      logprintf("Error: Line %zu of --read-freq file has fewer tokens than expected.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    const auto it = by_id.find(t[col_id]);
+    if (it == by_id.end()) {
+      ++skipped;
+      continue;
+    }
+    if (dup.count(t[col_id])) {
+      logprintf("Error: --read-freq variant ID '%s' appears multiple times in main dataset.\n", t[col_id].c_str());
+      return kRetMalformedInput;
+    }
+    const uint32_t v = it->second;
+    if (seen[v]) {
+      logprintf("Error: Variant ID '%s' appears multiple times in --read-freq file.\n", t[col_id].c_str());
+      return kRetMalformedInput;
+    }
+    seen[v] = 1;
+    const bool same = t[col_ref] == V.ref[v] && t[col_alt] == V.alt[v];
+    const bool swapped = t[col_ref] == V.alt[v] && t[col_alt] == V.ref[v];
+    double af;
+    const std::string& afs = t[col_af];
+    if (!ParseDouble(afs.c_str(), &af) || af != af) {
+      if (afs == "nan" || afs == "NaN" || afs == "NA" || af != af) {
+        ++skipped;
+        continue;
+      }
+      logprintf("Error: Invalid frequencies/counts on line %zu of --read-freq file.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    if (!same && !swapped) {
+      ++skipped;
+      continue;
+    }
+    if (af < 0.0 || af > 1.0 * (1 + 1.0 / 17592186044416.0) / 0.99) {
+      logprintf("Error: Invalid frequencies/counts on line %zu of --read-freq file.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    if (af > 1.0) af = 1.0;
+    ds->read_ref_freq[v] = same ? (1.0 - af) : af;
+    ++loaded;
+  }
+  logprintf("--read-freq: Frequencies for %llu variant%s loaded.\n", static_cast<unsigned long long>(loaded), loaded == 1 ? "" : "s");
+  if (skipped) logprintf("Warning: %llu entr%s skipped due to missing variant IDs, mismatching allele codes, and/or zero observations.\n", static_cast<unsigned long long>(skipped), skipped == 1 ? "y" : "ies");
+  return 0;
+}
+
+// loaded --read-freq values take precedence over the frequencies computed from the data; a NaN entry tells the
+// library to compute that variant's frequency from the block it is given
+bool ApplyReadFreq(const Dataset& ds, const std::vector<uint32_t>& vidx, std::vector<double>* ref_freqs, bool have_freqs) {
+  if (ds.read_ref_freq.empty()) return have_freqs;
+  if (!have_freqs) ref_freqs->assign(vidx.size(), std::numeric_limits<double>::quiet_NaN());
+  for (size_t k = 0; k < vidx.size(); ++k) {
+    const double f = ds.read_ref_freq[vidx[k]];
+    if (f == f) (*ref_freqs)[k] = f;
+  }
+  return true;
+}
+
 bool FounderRefFreqs(Dataset* ds, Pl2GpuCtx* ctx, const std::vector<uint32_t>& vidx, std::vector<double>* ref_freqs, int* rc) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
@@ -1441,8 +1563,9 @@ int RunGrm(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, bool keep_for_pca, Pl2GrmJ
   ParallelBounds(n, 0, c.parallel_idx, c.parallel_tot, &r0, &r1);
   std::vector<double> ref_freqs;
   int rc = 0;
-  const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
+  bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
   if (rc) return rc;
+  have_freqs = ApplyReadFreq(*ds, vidx, &ref_freqs, have_freqs);
   const int flags = (c.grm_cov ? kPl2GrmCov : 0) | ((c.grm_meanimpute || (keep_for_pca && c.pca_meanimpute && !c.make_grm_bin && !c.make_grm_list && !c.make_grm_sparse && !c.make_rel)) ? kPl2GrmMeanimpute : 0);
   // multi-GPU team (--gpus): rows [r0, r1) in one tile-aligned slab per device (CalcGrm's own row split is
   // TriangleFill2 over threads, 2.0/plink2_matrix_calc.cc:4596); exact --pca needs the whole matrix on one device
@@ -1755,8 +1878,9 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
     }
     std::vector<double> ref_freqs;
     int rc = 0;
-    const bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
+    bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
     if (rc) return rc;
+    have_freqs = ApplyReadFreq(*ds, vidx, &ref_freqs, have_freqs);
     Pl2PcaJob* job = nullptr;
     rc = pl2gpu_pca_begin(ctx, n, static_cast<uint32_t>(vidx.size()), pc_ct, &job);
     if (rc) {
@@ -1991,7 +2115,7 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("--indep-preferred: %u variant%s loaded.\n", pref_ct, pref_ct == 1 ? "" : "s");
   }
   std::vector<uint8_t> removed(m, 0);
-  const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, nullptr, preferred.empty() ? nullptr : preferred.data(), 0,
+  const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data(), preferred.empty() ? nullptr : preferred.data(), 0,
                                        founder_sex.data(), c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data());
   pl2gpu_host_free(blk);
   if (rc) return GpuFail("pl2_indep_pairwise");
@@ -2132,6 +2256,10 @@ int main(int argc, char** argv) {
   for (uint8_t f : ds.samples.is_founder) founder_ct += f;
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
   logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
+  if (!c.read_freq.empty()) {
+    rc = LoadReadFreq(c, &ds);
+    if (rc) return rc;
+  }
   g_clock.Mark("load .psam/.pvar, open .pgen");
   g_decode_threads = EffectiveHostThreads(c.threads);
   Pl2GpuCtx* ctx = nullptr;

@@ -341,7 +341,7 @@ int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant
       const uint32_t n0 = counts[4ull * v], n1 = counts[4ull * v + 1], n2 = counts[4ull * v + 2], n3 = counts[4ull * v + 3];
       const uint32_t* cc = &cls_counts[r.cls == kDip ? 0 : 4ull * (v - r.v0)];
       double ref_freq;
-      if (ref_freqs) {
+      if (ref_freqs && ref_freqs[v] == ref_freqs[v]) {  // NaN entry: compute from the block
         ref_freq = ref_freqs[v];
       } else if (r.cls == kChrX) {
         // nonmales count twice, a male het is half an ALT (plink2_data.cc:2642, :2685-2688)

@@ -120,7 +120,7 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
     for (uint32_t v = 0; v < cur; ++v) {
       const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2];
       double ref_freq;
-      if (ref_freqs) {
+      if (ref_freqs && ref_freqs[done + v] == ref_freqs[done + v]) {  // NaN entry: compute from the block
         ref_freq = ref_freqs[done + v];
       } else {
         const uint64_t tot = 2ull * (static_cast<uint64_t>(n0) + n1 + n2);

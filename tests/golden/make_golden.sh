@@ -64,6 +64,11 @@ cp $T/a_ldp.prune.in a_ldpref.prune.in
 cp $T/a_ldkb.prune.in a_ldkb.prune.in
 $P --bfile a --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/a_ldo1 > /dev/null
 cp $T/a_ldo1.prune.in a_ldo1.prune.in
+# --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
+python make_read_freq_set.py a.afreq a_rf.afreq
+$P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null
+$P --bfile a --read-freq a_rf.afreq --indep-pairwise 50 5 0.2 --threads 2 --out $T/a_rfld > /dev/null
+cp $T/a_rf.grm.bin a_rf.grm.bin; cp $T/a_rfld.prune.in a_rfld.prune.in
 # --- set X: chromosomes 1 / X / Y / XY / MT with mixed sexes and non-founders (make_x_set.py): the sex-chromosome
 # forms of --indep-pairwise, both pruning orders
 $P --dummy 120 800 0.03 --seed 11 --threads 2 --make-bed --out $T/x0 > /dev/null

@@ -224,6 +224,18 @@ def test_zs_outputs_decompress_to_the_reference_files(golden_dir, tmp_path):
     assert _zstd_decompress(out + ".afreq.zst") == open(os.path.join(golden_dir, "a.afreq"), "rb").read()
 
 
+def test_read_freq_grm_and_prune_list(golden_dir, tmp_path):
+    """--read-freq (PLINK 2 --freq report, partial / perturbed / allele-swapped entries): GRM within fp32 rounding of
+    the reference's, prune list byte-identical."""
+    rf = os.path.join(golden_dir, "a_rf.afreq")
+    out = run(golden_dir, tmp_path, "--read-freq", rf, "--make-grm-bin")
+    got = np.fromfile(out + ".grm.bin", dtype=np.float32)
+    want = np.fromfile(os.path.join(golden_dir, "a_rf.grm.bin"), dtype=np.float32)
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-7) and not np.allclose(got, np.fromfile(os.path.join(golden_dir, "a_grm.grm.bin"), dtype=np.float32), rtol=1e-5, atol=1e-7)
+    out = run(golden_dir, tmp_path, "--read-freq", rf, "--indep-pairwise", "50", "5", "0.2")
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_rfld.prune.in"), "rb").read()
+
+
 def test_toy_fixture_configs0(golden_dir, tmp_path):
     out = str(tmp_path / "toy")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True, env=ENV)
