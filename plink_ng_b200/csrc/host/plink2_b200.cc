@@ -86,6 +86,8 @@ struct Cmd {
   bool freq = false;                      // --freq
   std::string indep_preferred;            // --indep-preferred <file of variant IDs>
   std::string read_freq;                  // --read-freq <PLINK 2 --freq report>
+  std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
+  double king_cutoff_table_thresh = -1;
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
   bool make_grm_sparse = false;            // --make-grm-sparse <cutoff>
@@ -297,6 +299,11 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else return Usage("--freq modifiers other than 'zs' (counts, cols=, bins) are not supported by plink2_b200.");
       }
       c->freq = true;
+    } else if (flag == "--king-cutoff-table") {
+      // plink2.cc:7665-7700
+      if (!need(2, 2)) return Usage("--king-cutoff-table requires a filename and a kinship threshold.");
+      c->king_cutoff_table = prm[0];
+      if (!ParseDouble(prm[1], &c->king_cutoff_table_thresh) || c->king_cutoff_table_thresh < 0 || c->king_cutoff_table_thresh >= 0.5) return Usage("Invalid --king-cutoff-table threshold.");
     } else if (flag == "--read-freq") {
       if (!need(1, 1)) return Usage("--read-freq requires a filename.");
       c->read_freq = prm[0];
@@ -384,7 +391,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq)) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -1381,6 +1388,117 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
   return 0;
 }
 
+// --king-cutoff-table (KingCutoffBatchTable, 2.0/plink2_matrix_calc.cc:643-862): the relatedness prune of --king-cutoff
+// driven by a kinship table written earlier (.kin0: [#FID1] ID1|IID1 [SID1] [FID2] ID2|IID2 [SID2] ... KINSHIP).  Pairs
+// whose kinship exceeds threshold (1 + 2^-44) become constraints; unknown IDs and non-numeric kinship cells are
+// skipped.  Host-only work in the reference too - no device involved.
+int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  std::vector<std::string> lines;
+  std::string err;
+  if (!ReadLines(c.king_cutoff_table, &lines, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  if (lines.empty() || lines[0].empty()) {
+    logprintf("Error: Empty --king-cutoff-table file.\n");
+    return kRetMalformedInput;
+  }
+  std::vector<std::string> h = SplitWs(lines[0]);
+  size_t hi = 0;
+  auto bad_header = []() {
+    logprintf("Error: Invalid header line in --king-cutoff-table file.\n");
+    return kRetMalformedInput;
+  };
+  const bool fid_present = h[0] == "#FID1" || h[0] == "FID";
+  if (fid_present) {
+    ++hi;
+  } else {
+    if (h[0].empty() || h[0][0] != '#') return bad_header();
+    h[0] = h[0].substr(1);
+  }
+  if (hi >= h.size() || (h[hi] != "ID1" && h[hi] != "IID1")) return bad_header();
+  ++hi;
+  bool sid_col = false;
+  if (hi < h.size() && h[hi] == "SID1") {
+    sid_col = true;
+    ++hi;
+  }
+  if (fid_present) {
+    if (hi >= h.size() || h[hi] != "FID2") return bad_header();
+    ++hi;
+  }
+  if (hi >= h.size() || (h[hi] != "ID2" && h[hi] != "IID2")) return bad_header();
+  ++hi;
+  if (sid_col) {
+    if (hi >= h.size() || h[hi] != "SID2") return bad_header();
+    ++hi;
+  }
+  size_t kin_col = hi;
+  while (kin_col < h.size() && h[kin_col] != "KINSHIP" && h[kin_col] != "Kinship") ++kin_col;
+  if (kin_col == h.size()) {
+    logprintf("Error: No kinship-coefficient column in --king-cutoff-table file.\n");
+    return kRetInconsistentInput;
+  }
+  const bool use_sid = sid_col && S.sid_present;
+  auto key = [&](const std::string& fid, const std::string& iid, const std::string& sid) {
+    std::string k = fid_present ? (fid + "\t" + iid) : iid;
+    if (use_sid) k += "\t" + sid;
+    return k;
+  };
+  // without a FID column only IID (and SID) identify a sample; ambiguous keys never match, like a failed xid lookup
+  std::unordered_map<std::string, int64_t> by_key;
+  by_key.reserve(static_cast<size_t>(n) * 2);
+  for (uint32_t k = 0; k < n; ++k) {
+    auto ins = by_key.emplace(key(S.fid[k], S.iid[k], S.sid[k]), k);
+    if (!ins.second) ins.first->second = -1;
+  }
+  const uint32_t wl = (n + 63) / 64;
+  std::vector<uint64_t> table(static_cast<uint64_t>(n) * wl, 0);
+  const double thresh = c.king_cutoff_table_thresh * (1.0 + 1.0 / 17592186044416.0);
+  const size_t ids_per_side = (fid_present ? 1 : 0) + 1 + (sid_col ? 1 : 0);
+  uint64_t constraint_ct = 0;
+  for (size_t li = 1; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    const std::vector<std::string> t = SplitWs(lines[li]);
+    if (t.size() <= kin_col) {
+      logprintf("Error: Fewer tokens than expected on line %zu of %s .\n", li + 1, c.king_cutoff_table.c_str());
+      return kRetMalformedInput;
+    }
+    int64_t idx[2];
+    for (int side = 0; side < 2; ++side) {
+      size_t p = side * ids_per_side;
+      const std::string fid = fid_present ? t[p++] : std::string();
+      const std::string iid = t[p++];
+      const std::string sid = sid_col ? t[p++] : std::string();
+      const auto it = by_key.find(key(fid, iid, sid));
+      idx[side] = (it == by_key.end()) ? -1 : it->second;
+    }
+    if (idx[0] < 0 || idx[1] < 0) continue;
+    if (idx[0] == idx[1]) {
+      logprintf("Error: Identical sample IDs on line %zu of --king-cutoff-table file.\n", li + 1);
+      return kRetInconsistentInput;
+    }
+    double kin;
+    if (!ParseDouble(t[kin_col].c_str(), &kin)) continue;
+    if (kin > thresh) {
+      table[static_cast<uint64_t>(idx[0]) * wl + idx[1] / 64] |= 1ull << (idx[1] % 64);
+      table[static_cast<uint64_t>(idx[1]) * wl + idx[0] / 64] |= 1ull << (idx[0] % 64);
+      ++constraint_ct;
+    }
+  }
+  logprintf("--king-cutoff-table: %llu constraint%s loaded.\n", static_cast<unsigned long long>(constraint_ct), constraint_ct == 1 ? "" : "s");
+  std::vector<uint8_t> removed;
+  KinshipPrune(&table, n, &removed);
+  std::vector<uint32_t> in, out;
+  for (uint32_t k = 0; k < n; ++k) (removed[k] ? out : in).push_back(k);
+  const std::string in_name = c.out + ".king.cutoff.in.id", out_name = c.out + ".king.cutoff.out.id";
+  if (!WriteIdFile(in_name, S, in, true) || !WriteIdFile(out_name, S, out, true)) return kRetWriteFail;
+  logprintf("--king-cutoff-table: Excluded sample ID%s written to %s , and %u remaining sample ID%s written to %s .\n", out.size() == 1 ? "" : "s", out_name.c_str(), static_cast<uint32_t>(in.size()), in.size() == 1 ? "" : "s", in_name.c_str());
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------ GRM
 // ComputeAlleleFreqs over founders (plink2.cc:2301, plink2_filter.cc:2113-2151).  Returns false
 // when every sample is a founder (the library then derives the same numbers from each block).
@@ -2261,6 +2379,19 @@ int main(int argc, char** argv) {
     if (rc) return rc;
   }
   g_clock.Mark("load .psam/.pvar, open .pgen");
+  if (!c.king_cutoff_table.empty()) {
+    if (c.king_cutoff >= 0) {
+      logprintf("Error: --king-cutoff cannot be used with --king-cutoff-table.\n");
+      return kRetInvalidCmdline;
+    }
+    rc = RunKingCutoffTable(c, &ds);
+    if (rc) return rc;
+    if (!(c.freq || c.make_king || c.make_king_table || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise)) {
+      return 0;  // table-driven pruning is host-only in the reference as well: no device is needed for it
+    }
+    logprintf("Error: chaining --king-cutoff-table sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
+    return kRetNotYetSupported;
+  }
   g_decode_threads = EffectiveHostThreads(c.threads);
   Pl2GpuCtx* ctx = nullptr;
   if (pl2gpu_ctx_create(c.device, &ctx)) {

@@ -216,3 +216,18 @@ def test_zs_writer_roundtrip(tmp_path):
         out += dst.raw[:n]
         off += fsz
     assert out == data
+
+
+def test_king_cutoff_table_matches_reference_lists(tmp_path):
+    """--king-cutoff-table is host-only work in the reference as well (KingCutoffBatchTable): the .kin0 table the
+    reference wrote for set A, threshold 0.02 -> the reference's .king.cutoff.{in,out}.id, byte for byte, no GPU needed."""
+    import gzip
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    (tmp_path / "in.kin0").write_bytes(gzip.open(os.path.join(gd, "a_kingp.kin0.gz"), "rb").read())
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bfile", os.path.join(gd, "a"), "--king-cutoff-table", str(tmp_path / "in.kin0"), "0.02", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "661 constraints loaded" in r.stdout
+    for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):
+        assert open(out + ext, "rb").read() == open(os.path.join(gd, "a_kct" + ext), "rb").read()
