@@ -227,6 +227,21 @@ int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant
  * monomorphic marks (:902) and major-allele frequencies (minus 1 for --indep-preferred variants, :916-918). */
 int pl2_ld_prune_walk(uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, int window_is_bp, const double* maj_freq, const uint8_t* mono, const uint8_t* pair_flags, uint32_t band, uint32_t flags, uint8_t* removed_out);
 
+/* ---- `--score`: replaces the per-variant dosage expansion + dgemm / difflist updates of CalcScoreThread
+ * (2.0/plink2_matrix_calc.cc:6467-6890) under ScoreReport (:6892) for diploid hard calls.  Entries (one per scored
+ * (variant, allele) line, in any order) are streamed as PgrGet rows together with, per entry, weights4[e][code] =
+ * the contribution of genotype code 0/1/2/3 (code 3 = missing: coefficient x 2 x named-allele frequency, or 0 with
+ * 'no-mean-imputation', :6605-6607) and named_dosages[e] = the named-allele dosages of codes 0, 1, 2 packed two
+ * bits each (bits 0-1, 2-3, 4-5).  pl2gpu_score_get returns per sample the weighted sum, the named-allele dosage
+ * sum over nonmissing calls (NAMED_ALLELE_DOSAGE_SUM) and the number of missing calls (ALLELE_CT = 2 x (entries -
+ * missing), :8581).  Partial sums are combined in a fixed order: results are bit-reproducible. ---- */
+typedef struct Pl2ScoreJob Pl2ScoreJob;
+int pl2gpu_score_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, Pl2ScoreJob** job_ptr);
+int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* weights4, const uint8_t* named_dosages);
+int pl2gpu_score_get(Pl2ScoreJob* job, double* score_sums, uint64_t* named_dosage_sums, uint32_t* missing_cts);
+/* Idempotent; accepts NULL. */
+int pl2gpu_score_end(Pl2ScoreJob* job);
+
 /* ---- measured int8 tensor peak: every SM issues back-to-back tcgen05.mma kind::i8 (M = 128, N = n_cols,
  * K = 32; form 0 = both operands in shared memory, 1 = A operand in tensor memory as the KING/GRM kernels use
  * it) for at least min_seconds; *tops_out = 2*128*n_cols*32 ops x UMMAs / elapsed (CUDA events), in TOP/s.

@@ -242,6 +242,61 @@ def read_freq_overrides(path: str, ids, ref_alleles, alt_alleles) -> np.ndarray:
     return out
 
 
+# ------------------------------------------------------------------------------------------- --score
+def score_file_entries(path: str, ids, ref_alleles, alt_alleles, header: bool = True, id_col: int = 0, allele_col: int = 1, coef_col: int = 2):
+    """The (variant index, named-allele index 0 = REF / 1 = ALT, coefficient) triples ScoreReport keeps, in file order
+    (2.0/plink2_matrix_calc.cc:7712-7790): unknown variant IDs and allele codes that are neither REF nor ALT are
+    skipped (and counted for the warning)."""
+    idx = {v: k for k, v in enumerate(ids)}
+    out, missing_id, missing_allele = [], 0, 0
+    with open(path) as f:
+        if header:
+            f.readline()
+        for ln in f:
+            t = ln.split()
+            if not t:
+                continue
+            k = idx.get(t[id_col])
+            if k is None:
+                missing_id += 1
+                continue
+            a = t[allele_col]
+            if a == ref_alleles[k]:
+                out.append((k, 0, float(t[coef_col])))
+            elif a == alt_alleles[k]:
+                out.append((k, 1, float(t[coef_col])))
+            else:
+                missing_allele += 1
+    return out, missing_id, missing_allele
+
+
+def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputation: bool = False):
+    """ScoreReport's default report for diploid variants (2.0/plink2_matrix_calc.cc:6892-9270): per sample
+    ALLELE_CT = 2 x nonmissing scored variants (:8581), DENOM (= 2 x scored variants, or ALLELE_CT with
+    'no-mean-imputation', :8586-8588), NAMED_ALLELE_DOSAGE_SUM over nonmissing calls, score sum = sum of coefficient x
+    named-allele dosage with a missing call replaced by 2 x the named allele's frequency (:6605-6607) unless
+    no-mean-imputation, and the average = sum x (1 / DENOM) (:8397)."""
+    n = geno.shape[1]
+    ssum = np.zeros(n)
+    dos = np.zeros(n, dtype=np.int64)
+    miss = np.zeros(n, dtype=np.int64)
+    for v, aidx, coef in entries:
+        g = geno[v]
+        named = np.where(g == 3, 0, g if aidx == 1 else 2 - g).astype(np.int64)
+        named = np.where(g == 3, 0, named)
+        f_named = (1.0 - ref_freq[v]) if aidx == 1 else ref_freq[v]
+        d = named.astype(np.float64)
+        if not no_mean_imputation:
+            d = np.where(g == 3, 2.0 * f_named, d)
+        ssum += coef * d
+        dos += named
+        miss += g == 3
+    denom_full = 2 * len(entries)
+    nallele = denom_full - 2 * miss
+    denom = nallele if no_mean_imputation else np.full(n, denom_full)
+    return nallele, denom, dos, ssum, ssum * (1.0 / denom)
+
+
 # --------------------------------------------------------------------------------------------- GRM
 def centered_varmaj(geno: np.ndarray, ref_freq: np.ndarray, variance_standardize: bool = True) -> np.ndarray:
     """ExpandCenteredVarmaj + PopulateRescaledDosage (2.0/plink2_matrix_calc.cc:3839-3886,

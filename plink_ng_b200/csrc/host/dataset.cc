@@ -40,6 +40,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
   // .psam: optional '##' comment lines then a '#FID ...' / '#IID ...' header; .fam: no header, 6 columns
   while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
   int col_fid = -1, col_iid = -1, col_sid = -1, col_pat = -1, col_mat = -1, col_sex = -1;
+  std::vector<int> pheno_cols;
   if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
     std::vector<std::string> hdr = SplitWs(lines[li].substr(1));
     for (size_t c = 0; c < hdr.size(); ++c) {
@@ -49,6 +50,10 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
       else if (hdr[c] == "PAT") col_pat = static_cast<int>(c);
       else if (hdr[c] == "MAT") col_mat = static_cast<int>(c);
       else if (hdr[c] == "SEX") col_sex = static_cast<int>(c);
+      else {
+        pheno_cols.push_back(static_cast<int>(c));
+        out->pheno_names.push_back(hdr[c]);
+      }
     }
     if (col_iid < 0 || (col_fid > 0)) {
       *err = "Invalid .psam header line in " + path + " (#FID or #IID must come first).";
@@ -61,7 +66,10 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
     col_pat = 2;
     col_mat = 3;
     col_sex = 4;
+    pheno_cols.push_back(5);
+    out->pheno_names.push_back("PHENO1");
   }
+  out->pheno_tokens.assign(pheno_cols.size(), {});
   out->fid_present = col_fid >= 0;
   out->sid_present = col_sid >= 0;
   for (; li < lines.size(); ++li) {
@@ -86,6 +94,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
       else if (ch == '2' || ch == 'F' || ch == 'f') sex = 2;
     }
     out->sex.push_back(sex);
+    for (size_t pc = 0; pc < pheno_cols.size(); ++pc) out->pheno_tokens[pc].push_back(pheno_cols[pc] < static_cast<int>(t.size()) ? t[pheno_cols[pc]] : "NA");
   }
   if (out->iid.empty()) {
     *err = "No samples in " + path + ".";

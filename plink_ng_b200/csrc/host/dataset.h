@@ -15,6 +15,10 @@ struct SampleInfo {
   std::vector<std::string> fid, iid, sid;
   std::vector<uint8_t> is_founder;
   std::vector<uint8_t> sex;  // 0 unknown, 1 male, 2 female (.fam column 5 / .psam SEX)
+  // phenotype columns as read (.fam column 6 = PHENO1; .psam: every column that is not an ID / parent / SEX column);
+  // typed when written (binary / quantitative / categorical, LoadPsam plink2_psam.cc:58)
+  std::vector<std::string> pheno_names;
+  std::vector<std::vector<std::string>> pheno_tokens;  // [phenotype][sample]
   bool fid_present = false;  // kfSampleIdFidPresent (plink2_psam.cc:104-130, :279, :823)
   bool sid_present = false;
   uint32_t size() const { return static_cast<uint32_t>(iid.size()); }

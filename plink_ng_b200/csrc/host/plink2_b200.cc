@@ -86,6 +86,11 @@ struct Cmd {
   bool freq = false;                      // --freq
   std::string indep_preferred;            // --indep-preferred <file of variant IDs>
   std::string read_freq;                  // --read-freq <PLINK 2 --freq report>
+  // --score <file> [i] [j] [k] [header | header-read] [no-mean-imputation] [zs] [cols=]
+  std::string score_file;
+  uint32_t score_id_col = 1, score_allele_col = 2, score_coef_col = 3;
+  bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false;
+  bool sc_fid_maybe = true, sc_fid = false, sc_sid_maybe = true, sc_sid = false, sc_pheno1 = false, sc_phenos = true, sc_nallele = true, sc_denom = false, sc_dosagesum = true, sc_avgs = true, sc_sums = false;
   std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
   double king_cutoff_table_thresh = -1;
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
@@ -299,6 +304,61 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else return Usage("--freq modifiers other than 'zs' (counts, cols=, bins) are not supported by plink2_b200.");
       }
       c->freq = true;
+    } else if (flag == "--score") {
+      // plink2.cc --score parsing: filename, up to three 1-based column numbers, then modifiers
+      if (nparam < 1) return Usage("--score requires a filename.");
+      c->score_file = prm[0];
+      int k = 1;
+      uint32_t nums[3], nnum = 0;
+      while (k < nparam && nnum < 3 && ParseU32(prm[k], &nums[nnum]) && nums[nnum]) ++nnum, ++k;
+      if (nnum >= 1) c->score_id_col = nums[0];
+      c->score_allele_col = nnum >= 2 ? nums[1] : c->score_id_col + 1;
+      c->score_coef_col = nnum >= 3 ? nums[2] : c->score_allele_col + 1;
+      if (c->score_id_col == c->score_allele_col || c->score_id_col == c->score_coef_col || c->score_allele_col == c->score_coef_col) return Usage("--score variant ID, allele and coefficient column numbers must be distinct.");
+      for (; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "header") c->score_header = true;
+        else if (m == "header-read") c->score_header_read = true;
+        else if (m == "no-mean-imputation") c->score_no_meanimpute = true;
+        else if (m == "zs") c->score_zs = true;
+        else if (m.compare(0, 5, "cols=") == 0) {
+          // column-set descriptor: a plain list replaces the default, +x / -x entries edit it
+          const std::string spec = m.substr(5);
+          const bool edit = !spec.empty() && (spec[0] == '+' || spec[0] == '-');
+          if (!edit) c->sc_fid_maybe = c->sc_sid_maybe = c->sc_phenos = c->sc_nallele = c->sc_dosagesum = c->sc_avgs = false;
+          size_t pos = 0;
+          while (pos <= spec.size()) {
+            size_t e = spec.find(',', pos);
+            if (e == std::string::npos) e = spec.size();
+            std::string tok = spec.substr(pos, e - pos);
+            pos = e + 1;
+            if (tok.empty()) continue;
+            bool on = true;
+            if (tok[0] == '+' || tok[0] == '-') {
+              if (!edit) return Usage("Invalid --score cols= argument (mixing +/- entries with a plain list).");
+              on = tok[0] == '+';
+              tok = tok.substr(1);
+            } else if (edit) {
+              return Usage("Invalid --score cols= argument (mixing +/- entries with a plain list).");
+            }
+            if (tok == "maybefid") c->sc_fid_maybe = on;
+            else if (tok == "fid") c->sc_fid = on;
+            else if (tok == "maybesid") c->sc_sid_maybe = on;
+            else if (tok == "sid") c->sc_sid = on;
+            else if (tok == "pheno1") c->sc_pheno1 = on;
+            else if (tok == "phenos") c->sc_phenos = on;
+            else if (tok == "nallele") c->sc_nallele = on;
+            else if (tok == "denom") c->sc_denom = on;
+            else if (tok == "dosagesum") c->sc_dosagesum = on;
+            else if (tok == "scoreavgs") c->sc_avgs = on;
+            else if (tok == "scoresums") c->sc_sums = on;
+            else return Usage(("Invalid --score cols= entry '" + tok + "'.").c_str());
+          }
+        } else {
+          return Usage(("--score modifier '" + m + "' is not supported by plink2_b200 (supported: header, header-read, no-mean-imputation, zs, cols=).").c_str());
+        }
+      }
+      if (c->score_header && c->score_header_read) return Usage("--score 'header' and 'header-read' modifiers cannot be used together.");
     } else if (flag == "--king-cutoff-table") {
       // plink2.cc:7665-7700
       if (!need(2, 2)) return Usage("--king-cutoff-table requires a filename and a kinship threshold.");
@@ -391,7 +451,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->score_file.empty())) return Usage("No command given.");
   return 0;
 }
 

@@ -1,0 +1,203 @@
+// score.cu - `--score` accumulation: replaces the dosage expansion + dgemm / difflist updates of ScoreReport's worker
+// (CalcScoreThread, 2.0/plink2_matrix_calc.cc:6467-6890, driven by ScoreReport :6892) for diploid hard calls: per
+// sample the weighted sum  sum_v w_v[g_vs]  over the scored (variant, allele) entries, the sum of named-allele dosages
+// and the number of missing calls.  The caller supplies, per entry, the four weights of the genotype codes
+// (coefficient x named-allele dosage for codes 0/1/2, coefficient x 2 x allele frequency for a missing call - or 0
+// with 'no-mean-imputation', :6605-6607) and the integer named-allele dosages, so centring / dominant / recessive
+// variants are a matter of the table the caller builds.
+//
+// Streaming, HBM/ALU-bound: every 32-bit word of a variant row (16 samples) is read once.  A CTA covers 128 words x a
+// chunk of variants and writes per-chunk partial sums; a second kernel adds the partials in chunk order, so results do
+// not depend on scheduling.
+#include <algorithm>
+#include <vector>
+
+#include "../../include/plink2_b200.h"
+#include "common.cuh"
+
+using namespace pl2;
+
+namespace {
+
+constexpr uint32_t kScoreThreads = 128;
+constexpr uint32_t kScoreTile = 64;  // variants whose tables are staged in shared memory at a time
+
+// raw: [variant][pitch] bytes (pitch multiple of 4, padding samples coded missing); w4: [variant][4] weights;
+// d4: [variant] packed named-allele dosages of codes 0..2 (2 bits each; code 3 contributes nothing).
+__global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t words, uint32_t variant_ct, uint32_t chunk_variants, const double* __restrict__ w4, const uint8_t* __restrict__ d4,
+                                                           double* __restrict__ part_sum, uint32_t* __restrict__ part_dos, uint32_t* __restrict__ part_miss, uint32_t samples_padded) {
+  __shared__ double s_w[kScoreTile * 4];
+  __shared__ uint8_t s_d[kScoreTile];
+  const uint32_t widx = blockIdx.x * kScoreThreads + threadIdx.x;
+  const uint32_t v_begin = blockIdx.y * chunk_variants, v_end = min(variant_ct, v_begin + chunk_variants);
+  double sum[16];
+  uint32_t dos[16], miss[16];
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    sum[s] = 0.0;
+    dos[s] = 0;
+    miss[s] = 0;
+  }
+  for (uint32_t v0 = v_begin; v0 < v_end; v0 += kScoreTile) {
+    const uint32_t tile = min(kScoreTile, v_end - v0);
+    __syncthreads();
+    for (uint32_t e = threadIdx.x; e < tile * 4; e += kScoreThreads) s_w[e] = w4[4ull * v0 + e];
+    for (uint32_t e = threadIdx.x; e < tile; e += kScoreThreads) s_d[e] = d4[v0 + e];
+    __syncthreads();
+    if (widx >= words) continue;
+    for (uint32_t t = 0; t < tile; ++t) {
+      const uint32_t word = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(v0 + t) * pitch + 4ull * widx);
+      const double w0 = s_w[4 * t], w1 = s_w[4 * t + 1], w2 = s_w[4 * t + 2], w3 = s_w[4 * t + 3];
+      const uint32_t dd = s_d[t];
+      const uint32_t d0 = dd & 3, d1 = (dd >> 2) & 3, d2 = (dd >> 4) & 3;
+#pragma unroll
+      for (int s = 0; s < 16; ++s) {
+        const uint32_t lo = (word >> (2 * s)) & 1, hi = (word >> (2 * s + 1)) & 1;
+        sum[s] += hi ? (lo ? w3 : w2) : (lo ? w1 : w0);
+        dos[s] += hi ? (lo ? 0u : d2) : (lo ? d1 : d0);
+        miss[s] += lo & hi;
+      }
+    }
+  }
+  if (widx >= words) return;
+  const uint64_t base = static_cast<uint64_t>(blockIdx.y) * samples_padded + 16ull * widx;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    part_sum[base + s] = sum[s];
+    part_dos[base + s] = dos[s];
+    part_miss[base + s] = miss[s];
+  }
+}
+
+__global__ void __launch_bounds__(256) score_reduce_kernel(const double* __restrict__ part_sum, const uint32_t* __restrict__ part_dos, const uint32_t* __restrict__ part_miss, uint32_t chunks, uint32_t samples_padded, uint32_t sample_ct,
+                                                          double* __restrict__ acc_sum, unsigned long long* __restrict__ acc_dos, uint32_t* __restrict__ acc_miss) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= sample_ct) return;
+  double a = acc_sum[s];
+  unsigned long long d = acc_dos[s];
+  uint32_t m = acc_miss[s];
+  for (uint32_t k = 0; k < chunks; ++k) {
+    a += part_sum[static_cast<uint64_t>(k) * samples_padded + s];
+    d += part_dos[static_cast<uint64_t>(k) * samples_padded + s];
+    m += part_miss[static_cast<uint64_t>(k) * samples_padded + s];
+  }
+  acc_sum[s] = a;
+  acc_dos[s] = d;
+  acc_miss[s] = m;
+}
+
+constexpr uint32_t kScoreStageVariants = 16384;
+constexpr uint32_t kScoreMaxChunks = 64;
+
+}  // namespace
+
+struct Pl2ScoreJob {
+  Pl2GpuCtx* ctx = nullptr;
+  uint32_t sample_ct = 0;
+  GenoStage stage;
+  double *d_w4 = nullptr, *d_part_sum = nullptr, *d_acc_sum = nullptr;
+  uint8_t* d_d4 = nullptr;
+  uint32_t *d_part_dos = nullptr, *d_part_miss = nullptr, *d_acc_miss = nullptr;
+  unsigned long long* d_acc_dos = nullptr;
+  uint64_t entries = 0;
+};
+
+extern "C" {
+
+int pl2gpu_score_end(Pl2ScoreJob* job) {
+  if (!job) return 0;
+  if (job->ctx) {
+    cudaSetDevice(job->ctx->c.device);
+    cudaStreamSynchronize(job->ctx->c.stream);
+  }
+  StageFree(&job->stage);
+  cudaFree(job->d_w4);
+  cudaFree(job->d_d4);
+  cudaFree(job->d_part_sum);
+  cudaFree(job->d_part_dos);
+  cudaFree(job->d_part_miss);
+  cudaFree(job->d_acc_sum);
+  cudaFree(job->d_acc_dos);
+  cudaFree(job->d_acc_miss);
+  cudaGetLastError();
+  delete job;
+  return 0;
+}
+
+int pl2gpu_score_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, Pl2ScoreJob** job_ptr) {
+  if (job_ptr) *job_ptr = nullptr;
+  if (!ctx || !job_ptr || !sample_ct) {
+    set_error("pl2gpu_score_begin: bad arguments");
+    return 1;
+  }
+  PL2_CUDA_OK(cudaSetDevice(ctx->c.device));
+  Pl2ScoreJob* job = new Pl2ScoreJob();
+  job->ctx = ctx;
+  job->sample_ct = sample_ct;
+  auto fail = [&]() {
+    pl2gpu_score_end(job);
+    return 1;
+  };
+  if (StageAlloc(sample_ct, kScoreStageVariants, &job->stage, 64)) return fail();
+  const uint64_t np = job->stage.sample_ct_padded;
+  if (cudaMalloc(&job->d_w4, 32ull * kScoreStageVariants) != cudaSuccess || cudaMalloc(&job->d_d4, kScoreStageVariants) != cudaSuccess || cudaMalloc(&job->d_part_sum, 8 * np * kScoreMaxChunks) != cudaSuccess ||
+      cudaMalloc(&job->d_part_dos, 4 * np * kScoreMaxChunks) != cudaSuccess || cudaMalloc(&job->d_part_miss, 4 * np * kScoreMaxChunks) != cudaSuccess || cudaMalloc(&job->d_acc_sum, 8 * np) != cudaSuccess ||
+      cudaMalloc(&job->d_acc_dos, 8 * np) != cudaSuccess || cudaMalloc(&job->d_acc_miss, 4 * np) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("pl2gpu_score_begin: insufficient device memory for %u samples", sample_ct);
+    return fail();
+  }
+  if (cudaMemsetAsync(job->d_acc_sum, 0, 8 * np, ctx->c.stream) != cudaSuccess || cudaMemsetAsync(job->d_acc_dos, 0, 8 * np, ctx->c.stream) != cudaSuccess || cudaMemsetAsync(job->d_acc_miss, 0, 4 * np, ctx->c.stream) != cudaSuccess) {
+    set_error("pl2gpu_score_begin: %s", cudaGetErrorString(cudaGetLastError()));
+    return fail();
+  }
+  *job_ptr = job;
+  return 0;
+}
+
+int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* weights4, const uint8_t* named_dosages) {
+  if (!job || (variant_ct && (!genovecs || !weights4 || !named_dosages))) {
+    set_error("pl2gpu_score_add_variants: bad arguments");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint8_t* src = static_cast<const uint8_t*>(genovecs);
+  const uint32_t np = job->stage.sample_ct_padded, words = np / 16;
+  for (uint32_t done = 0; done < variant_ct;) {
+    const uint32_t cur = std::min(kScoreStageVariants, variant_ct - done);
+    uint32_t padded = 0;
+    PL2_TRY(StageUpload(c, &job->stage, src + static_cast<uint64_t>(done) * variant_stride_bytes, variant_stride_bytes, cur, src_is_device, &padded));
+    PL2_CUDA_OK(cudaMemcpyAsync(job->d_w4, weights4 + 4ull * done, 32ull * cur, cudaMemcpyHostToDevice, c->stream));
+    PL2_CUDA_OK(cudaMemcpyAsync(job->d_d4, named_dosages + done, cur, cudaMemcpyHostToDevice, c->stream));
+    // enough chunks to fill the GPU, each a multiple of the shared-memory tile
+    const uint32_t col_ctas = DivUpU32(words, kScoreThreads);
+    uint32_t chunks = std::max(1u, std::min({kScoreMaxChunks, DivUpU32(4 * static_cast<uint32_t>(c->sm_count), col_ctas), DivUpU32(cur, kScoreTile)}));
+    const uint32_t chunk_variants = RoundUpU32(DivUpU32(cur, chunks), kScoreTile);
+    chunks = DivUpU32(cur, chunk_variants);
+    score_kernel<<<dim3(col_ctas, chunks), kScoreThreads, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, words, cur, chunk_variants, job->d_w4, job->d_d4, job->d_part_sum, job->d_part_dos, job->d_part_miss, np);
+    score_reduce_kernel<<<DivUpU32(job->sample_ct, 256), 256, 0, c->stream>>>(job->d_part_sum, job->d_part_dos, job->d_part_miss, chunks, np, job->sample_ct, job->d_acc_sum, job->d_acc_dos, job->d_acc_miss);
+    c->launches += 2;
+    PL2_CUDA_OK(cudaGetLastError());
+    PL2_CUDA_OK(cudaStreamSynchronize(c->stream));  // host tables and a host source may be reused by the caller
+    job->entries += cur;
+    done += cur;
+  }
+  return 0;
+}
+
+int pl2gpu_score_get(Pl2ScoreJob* job, double* score_sums, uint64_t* named_dosage_sums, uint32_t* missing_cts) {
+  if (!job || !score_sums) {
+    set_error("pl2gpu_score_get: bad arguments");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  PL2_CUDA_OK(cudaMemcpyAsync(score_sums, job->d_acc_sum, 8ull * job->sample_ct, cudaMemcpyDeviceToHost, c->stream));
+  if (named_dosage_sums) PL2_CUDA_OK(cudaMemcpyAsync(named_dosage_sums, job->d_acc_dos, 8ull * job->sample_ct, cudaMemcpyDeviceToHost, c->stream));
+  if (missing_cts) PL2_CUDA_OK(cudaMemcpyAsync(missing_cts, job->d_acc_miss, 4ull * job->sample_ct, cudaMemcpyDeviceToHost, c->stream));
+  PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -64,6 +64,11 @@ cp $T/a_ldp.prune.in a_ldpref.prune.in
 cp $T/a_ldkb.prune.in a_ldkb.prune.in
 $P --bfile a --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/a_ldo1 > /dev/null
 cp $T/a_ldo1.prune.in a_ldo1.prune.in
+# --score: shuffled (variant, allele, weight) lines incl. unknown IDs / foreign allele codes (make_score_set.py)
+python make_score_set.py a.bim a_score.txt
+$P --bfile a --score a_score.txt header --threads 2 --out $T/a_sc > /dev/null
+$P --bfile a --score a_score.txt header no-mean-imputation cols=+scoresums,+denom --threads 2 --out $T/a_sc2 > /dev/null
+cp $T/a_sc.sscore a_sc.sscore; cp $T/a_sc2.sscore a_sc2.sscore
 # --king-cutoff-table on the proportion table written above
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --threads 2 --out $T/a_kct > /dev/null
 cp $T/a_kct.king.cutoff.in.id a_kct.king.cutoff.in.id; cp $T/a_kct.king.cutoff.out.id a_kct.king.cutoff.out.id

@@ -24,26 +24,24 @@ BIN = os.path.join(ROOT, "plink_ng_b200", "plink2_b200")
 
 
 def write_pgen(prefix, n, m, chrom_ct=1, ld_copy=0.0):
-    """Fixed-width (mode 0x02) .pgen + .pvar + .psam of the bench generator's genotypes; with ld_copy > 0 every
-    variant copies its predecessor's genotypes for that fraction of the samples (so --indep-pairwise has work)."""
+    """Fixed-width (mode 0x02) .pgen + .pvar + .psam of the bench generator's genotypes; with ld_copy > 0 the variants
+    come in LD blocks of 8 (so --indep-pairwise has work)."""
     dev = "cuda"
     bpv = (n + 3) // 4
     t0 = time.perf_counter()
     with open(prefix + ".pgen", "wb") as f:
         f.write(bytes([0x6C, 0x1B, 0x02]) + int(m).to_bytes(4, "little") + int(n).to_bytes(4, "little") + bytes([0x40]))
-        prev = None
-        for s0 in range(0, m, 8192):
+            for s0 in range(0, m, 8192):
             s1 = min(m, s0 + 8192)
             by = bench.synth_genovecs(torch, n, s0, s1, dev)[:, :bpv].contiguous()
             if ld_copy > 0:
-                # byte-granular copying (4 samples at a time) from the previous variant: cheap, and enough to create r^2 structure
+                # LD blocks of 8 consecutive variants: members copy their block's first variant byte-wise (4 samples at a
+                # time) with probability ld_copy -> r^2 ~ ld_copy^2 against the leader, ~ ld_copy^4 between members
                 g = torch.Generator(device=dev)
                 g.manual_seed(7919 + s0)
                 mask = torch.rand((s1 - s0, bpv), generator=g, device=dev) < ld_copy
-                nxt_prev = by[-1].clone()
-                shifted = torch.cat([prev.unsqueeze(0) if prev is not None else by[:1], by[:-1]])  # each variant's (original) predecessor
-                by = torch.where(mask, shifted, by)
-                prev = nxt_prev
+                lead = by[(torch.arange(s1 - s0, device=dev) // 8) * 8]
+                by = torch.where(mask, lead, by)
             by.cpu().numpy().tofile(f)
     per_chr = -(-m // chrom_ct)
     with open(prefix + ".pvar", "w") as f:
@@ -120,7 +118,7 @@ def c4(n=50000, m=1000000):
     d = "/tmp/pl2_c4"
     os.makedirs(d, exist_ok=True)
     pre = os.path.join(d, "c4")
-    gen_s = write_pgen(pre, n, m, chrom_ct=22, ld_copy=0.6)
+    gen_s = write_pgen(pre, n, m, chrom_ct=22, ld_copy=0.9)
     cores = bench.effective_cores()
     env = dict(os.environ, PL2_TIMING="1")
     flags = ["--indep-pairwise", "500", "50", "0.2"]
