@@ -1679,20 +1679,20 @@ bool ApplyReadFreq(const Dataset& ds, const std::vector<uint32_t>& vidx, std::ve
   return true;
 }
 
-bool FounderRefFreqs(Dataset* ds, Pl2GpuCtx* ctx, const std::vector<uint32_t>& vidx, std::vector<double>* ref_freqs, int* rc) {
+bool FounderRefFreqs(Dataset* ds, Pl2GpuCtx* ctx, const std::vector<uint32_t>& vidx, std::vector<double>* ref_freqs, int* rc, bool force = false) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
   uint32_t founder_ct = 0;
   for (uint32_t k = 0; k < n; ++k) founder_ct += S.is_founder[k];
   *rc = 0;
-  if (founder_ct == n) return false;
+  if (founder_ct == n && !force) return false;
   ref_freqs->assign(vidx.size(), 0.5);
   if (!founder_ct) return true;
   std::vector<uint64_t> inc((n + 63) / 64, 0);
   for (uint32_t k = 0; k < n; ++k)
     if (S.is_founder[k]) inc[k / 64] |= 1ull << (k % 64);
   BlockStreamer bs(ds, &vidx, founder_ct, 16384);
-  bs.sample_include = inc.data();
+  if (founder_ct != n) bs.sample_include = inc.data();
   if (!bs.Init()) {
     *rc = GpuFail("pl2gpu_host_alloc");
     return true;
@@ -2127,6 +2127,259 @@ std::string ChrNameOut(uint32_t code, const std::string& as_read) {
   return "XY";
 }
 
+// ---------------------------------------------------------------------------------------- --score
+// One phenotype column as the report prints it (LoadPsam typing, 2.0/plink2_psam.cc:58: every value in
+// {-9, 0, 1, 2, NA} -> case/control with 0 / -9 / NA missing; other numbers -> quantitative with -9 / NA missing;
+// anything non-numeric -> categorical).  A column without a single nonmissing value is not a phenotype
+// ("No phenotype data present").
+struct PhenoOut {
+  std::string name;
+  std::vector<std::string> text;  // per sample
+};
+bool TypePheno(const std::string& name, const std::vector<std::string>& tok, PhenoOut* out) {
+  const size_t n = tok.size();
+  std::vector<double> val(n, 0.0);
+  std::vector<uint8_t> is_na(n, 0);
+  bool numeric = true, binary = true;
+  for (size_t k = 0; k < n && numeric; ++k) {
+    const std::string& t = tok[k];
+    if (t == "NA" || t == "nan" || t == "NaN" || t == "na") {
+      is_na[k] = 1;
+      continue;
+    }
+    double d;
+    if (!ParseDouble(t.c_str(), &d)) {
+      numeric = false;
+      break;
+    }
+    val[k] = d;
+    if (!(d == -9 || d == 0 || d == 1 || d == 2)) binary = false;
+  }
+  out->name = name;
+  out->text.assign(n, "NA");
+  bool any = false;
+  char buf[32];
+  if (!numeric) {
+    for (size_t k = 0; k < n; ++k) {
+      const bool miss = tok[k] == "NA" || tok[k] == "NONE" || tok[k] == "nan";
+      out->text[k] = miss ? "NONE" : tok[k];
+      any = any || !miss;
+    }
+    return any;
+  }
+  for (size_t k = 0; k < n; ++k) {
+    if (is_na[k] || val[k] == -9 || (binary && val[k] == 0)) continue;
+    any = true;
+    if (binary) {
+      out->text[k] = val[k] == 1 ? "1" : "2";
+    } else {
+      *dtoa_g(val[k], buf) = '\0';
+      out->text[k] = buf;
+    }
+  }
+  return any;
+}
+
+// `--score` (ScoreReport, 2.0/plink2_matrix_calc.cc:6892-9270) for diploid hard calls: default report columns plus
+// denom / scoresums, 'header' / 'header-read', 'no-mean-imputation'.  The per-sample sums come from the device
+// (pl2gpu_score_*); the file parsing, allele matching, mean-imputation weights and the report are here.
+int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size();
+  std::vector<std::string> lines;
+  std::string err;
+  if (!ReadLines(c.score_file, &lines, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  std::unordered_map<std::string, uint32_t> by_id;
+  std::unordered_map<std::string, uint32_t> dup;
+  by_id.reserve(static_cast<size_t>(V.size()) * 2);
+  for (uint32_t v = 0; v < V.size(); ++v)
+    if (!by_id.emplace(V.id[v], v).second) dup.emplace(V.id[v], v);
+  struct Entry {
+    uint32_t v;
+    uint8_t aidx;  // 0 = REF named, 1 = ALT named
+    double coef;
+  };
+  std::vector<Entry> entries;
+  std::vector<uint8_t> seen(2ull * V.size(), 0);
+  uint64_t missing_id = 0, missing_allele = 0;
+  const uint32_t need_cols = std::max(c.score_id_col, std::max(c.score_allele_col, c.score_coef_col));
+  std::string score_name = "SCORE1";
+  size_t li = 0;
+  if ((c.score_header || c.score_header_read) && !lines.empty()) {
+    if (c.score_header_read) {
+      const std::vector<std::string> h = SplitWs(lines[0]);
+      if (h.size() < need_cols) {
+        logprintf("Error: Line 1 of --score file has fewer tokens than expected.\n");
+        return kRetMalformedInput;
+      }
+      score_name = h[c.score_coef_col - 1];
+    }
+    li = 1;
+  }
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    const std::vector<std::string> t = SplitWs(lines[li]);
+    if (t.empty()) continue;
+    if (t.size() < need_cols) {
+      logprintf("Error: Line %zu of --score file has fewer tokens than expected.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    const std::string& id = t[c.score_id_col - 1];
+    const auto it = by_id.find(id);
+    if (it == by_id.end()) {
+      ++missing_id;
+      continue;
+    }
+    if (dup.count(id)) {
+      logprintf("Error: --score variant ID '%s' appears multiple times in main dataset.\n", id.c_str());
+      return kRetInconsistentInput;
+    }
+    const uint32_t v = it->second;
+    const std::string& al = t[c.score_allele_col - 1];
+    uint8_t aidx;
+    if (al == V.ref[v]) aidx = 0;
+    else if (al == V.alt[v]) aidx = 1;
+    else {
+      ++missing_allele;
+      continue;
+    }
+    if (seen[2ull * v + aidx]) {
+      logprintf("Error: --score: %s allele for variant '%s' appears multiple times in %s file.\n", aidx ? "ALT1" : "REF", id.c_str(), c.score_file.c_str());
+      return kRetMalformedInput;
+    }
+    seen[2ull * v + aidx] = 1;
+    double coef;
+    if (!ParseDouble(t[c.score_coef_col - 1].c_str(), &coef)) {
+      logprintf("Error: Line %zu of --score file has an invalid coefficient.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    if (V.chr_code[v] == 23 || V.chr_code[v] == 24 || V.chr_code[v] == 26) {
+      logprintf("Error: --score on chrX / chrY / chrMT variants (sex-dependent ploidy) is not supported by plink2_b200 yet ('%s').\n", id.c_str());
+      return kRetNotYetSupported;
+    }
+    entries.push_back({v, aidx, coef});
+  }
+  if (missing_id || missing_allele) {
+    logprintf("Warning: --score: %llu entr%s in %s %s skipped due to missing variant IDs, and %llu %s skipped due to mismatching allele codes.\n", static_cast<unsigned long long>(missing_id), missing_id == 1 ? "y" : "ies",
+              c.score_file.c_str(), missing_id == 1 ? "was" : "were", static_cast<unsigned long long>(missing_allele), missing_allele == 1 ? "was" : "were");
+  }
+  if (entries.empty()) {
+    logprintf("Error: No valid variants in --score file.\n");
+    return kRetDegenerateData;
+  }
+  // device passes run in variant order (sums are order-independent up to fp64 rounding; the device adds in a fixed order)
+  std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.v < b.v; });
+  std::vector<uint32_t> vidx(entries.size());
+  for (size_t k = 0; k < entries.size(); ++k) vidx[k] = entries[k].v;
+  // named-allele frequencies for the mean imputation: founders (ComputeAlleleFreqs), --read-freq values first
+  std::vector<double> ref_freqs;
+  {
+    int rc = 0;
+    bool have = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc, true);
+    if (rc) return rc;
+    ApplyReadFreq(*ds, vidx, &ref_freqs, have);
+  }
+  Pl2ScoreJob* job = nullptr;
+  if (pl2gpu_score_begin(ctx, n, &job)) return GpuFail("pl2gpu_score_begin");
+  struct JobGuard {
+    Pl2ScoreJob* j;
+    ~JobGuard() { pl2gpu_score_end(j); }
+  } guard{job};
+  BlockStreamer bs(ds, &vidx, n, 16384);
+  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  std::vector<double> w4;
+  std::vector<uint8_t> d4;
+  size_t base = 0;
+  for (;;) {
+    const int got = bs.Next(&err);
+    if (got < 0) {
+      logprintf("Error: %s\n", err.c_str());
+      return kRetMalformedInput;
+    }
+    if (!got) break;
+    w4.resize(4ull * got);
+    d4.resize(got);
+    for (int k = 0; k < got; ++k) {
+      const Entry& e = entries[base + k];
+      const double f_named = e.aidx ? (1.0 - ref_freqs[base + k]) : ref_freqs[base + k];
+      // genotype code = ALT allele count; named-allele dosage of codes 0, 1, 2
+      const uint32_t d0 = e.aidx ? 0 : 2, d2 = e.aidx ? 2 : 0;
+      w4[4ull * k + 0] = e.coef * static_cast<double>(d0);
+      w4[4ull * k + 1] = e.coef;
+      w4[4ull * k + 2] = e.coef * static_cast<double>(d2);
+      w4[4ull * k + 3] = c.score_no_meanimpute ? 0.0 : e.coef * (2.0 * f_named);
+      d4[k] = static_cast<uint8_t>(d0 | (1u << 2) | (d2 << 4));
+    }
+    if (pl2gpu_score_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, w4.data(), d4.data())) return GpuFail("pl2gpu_score_add_variants");
+    base += static_cast<size_t>(got);
+  }
+  std::vector<double> sums(n);
+  std::vector<uint64_t> dos(n);
+  std::vector<uint32_t> miss(n);
+  if (pl2gpu_score_get(job, sums.data(), dos.data(), miss.data())) return GpuFail("pl2gpu_score_get");
+  logprintf("--score: %zu variant%s processed.\n", entries.size(), entries.size() == 1 ? "" : "s");
+  // report (:8470-8625)
+  std::vector<PhenoOut> phenos;
+  if (c.sc_phenos || c.sc_pheno1) {
+    for (size_t pc = 0; pc < S.pheno_names.size(); ++pc) {
+      PhenoOut po;
+      if (TypePheno(S.pheno_names[pc], S.pheno_tokens[pc], &po)) phenos.push_back(std::move(po));
+      if (!c.sc_phenos && !phenos.empty()) break;  // pheno1: first active phenotype only
+    }
+  }
+  const IdFmt idf{c.sc_fid || (c.sc_fid_maybe && S.fid_present), c.sc_sid || (c.sc_sid_maybe && S.sid_present)};
+  const std::string name = c.out + (c.score_zs ? ".sscore.zst" : ".sscore");
+  OutFile f;
+  if (!f.Open(name, c.score_zs)) return kRetOpenFail;
+  std::string hdr = "#";
+  if (idf.fid) hdr += "FID\t";
+  hdr += "IID";
+  if (idf.sid) hdr += "\tSID";
+  for (const PhenoOut& po : phenos) hdr += "\t" + po.name;
+  if (c.sc_nallele) hdr += "\tALLELE_CT";
+  if (c.sc_denom) hdr += "\tDENOM";
+  if (c.sc_dosagesum) hdr += "\tNAMED_ALLELE_DOSAGE_SUM";
+  if (c.sc_avgs) hdr += "\t" + score_name + "_AVG";
+  if (c.sc_sums) hdr += "\t" + score_name + "_SUM";
+  hdr += "\n";
+  f.Puts(hdr.c_str());
+  const uint32_t denom_full = 2 * static_cast<uint32_t>(entries.size());
+  char num[64];
+  for (uint32_t k = 0; k < n; ++k) {
+    std::string row = FmtId(S, k, idf);
+    for (const PhenoOut& po : phenos) row += "\t" + po.text[k];
+    const uint32_t nallele = denom_full - 2 * miss[k];
+    const uint32_t denom = c.score_no_meanimpute ? nallele : denom_full;
+    if (c.sc_nallele) {
+      *u32toa(nallele, num) = '\0';
+      row += std::string("\t") + num;
+    }
+    if (c.sc_denom) {
+      *u32toa(denom, num) = '\0';
+      row += std::string("\t") + num;
+    }
+    if (c.sc_dosagesum) row += "\t" + std::to_string(dos[k]);
+    if (c.sc_avgs) {
+      *dtoa_g(sums[k] * (1.0 / static_cast<double>(denom)), num) = '\0';
+      row += std::string("\t") + num;
+    }
+    if (c.sc_sums) {
+      *dtoa_g(sums[k], num) = '\0';
+      row += std::string("\t") + num;
+    }
+    row += "\n";
+    f.Write(row.data(), row.size());
+  }
+  if (!f.Close()) return kRetWriteFail;
+  logprintf("--score: Results written to %s .\n", name.c_str());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------- --freq
 int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
@@ -2461,6 +2714,10 @@ int main(int argc, char** argv) {
   g_clock.Mark("pl2gpu_ctx_create");
   if (c.freq) {
     rc = RunFreq(c, &ds, ctx);
+    if (rc) return rc;
+  }
+  if (!c.score_file.empty()) {
+    rc = RunScore(c, &ds, ctx);
     if (rc) return rc;
   }
   std::vector<uint8_t> cutoff_removed;

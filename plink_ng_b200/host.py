@@ -340,3 +340,24 @@ def pca_approx(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int, pc_ct: int
         return vals, vecs
     finally:
         lib.pl2gpu_pca_end(h)
+
+
+def score_sums(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int, weights4: np.ndarray, named_dosages: np.ndarray):
+    """`--score` accumulation (pl2gpu_score_*) over an in-memory block of scored entries: genovecs [entries, words]
+    PgrGet rows, weights4 [entries, 4] fp64 contributions of genotype codes 0..3, named_dosages [entries] uint8
+    (dosages of codes 0, 1, 2 packed two bits each) -> (score sums, named-allele dosage sums, missing counts)."""
+    g = np.ascontiguousarray(genovecs)
+    w = np.ascontiguousarray(weights4, dtype=np.float64)
+    d = np.ascontiguousarray(named_dosages, dtype=np.uint8)
+    assert w.shape == (g.shape[0], 4) and d.shape == (g.shape[0],)
+    h = C.c_void_p()
+    check(lib.pl2gpu_score_begin(ctx.handle, sample_ct, C.byref(h)), "pl2gpu_score_begin")
+    try:
+        check(lib.pl2gpu_score_add_variants(h, g.ctypes.data, g.strides[0], g.shape[0], 0, w.ctypes.data, d.ctypes.data), "pl2gpu_score_add_variants")
+        sums = np.empty(sample_ct, dtype=np.float64)
+        dos = np.empty(sample_ct, dtype=np.uint64)
+        miss = np.empty(sample_ct, dtype=np.uint32)
+        check(lib.pl2gpu_score_get(h, sums.ctypes.data, dos.ctypes.data, miss.ctypes.data), "pl2gpu_score_get")
+        return sums, dos, miss
+    finally:
+        lib.pl2gpu_score_end(h)
