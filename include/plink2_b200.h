@@ -190,6 +190,14 @@ typedef struct Pl2PcaJob Pl2PcaJob;
 int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, Pl2PcaJob** job_ptr);
 int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs);
 int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, double* eigvecs_host);
+/* Multi-GPU form (contexts joined by pl2gpu_comm_init; collective call, one host thread per rank): every rank's job
+ * holds ONE shard of the variants (any split; begin / add_variants as above with the shard's own variant count),
+ * total_variant_ct = the sum over ranks.  H_t = Y G_t stays on the rank that owns the variants; G' = Y^T H is completed by
+ * one fp64 all-reduce of the N x 2k matrix per pass, likewise the Gram-Schmidt coefficients and B = Y^T Q;
+ * each M x 2k block of the basis construction is all-gathered for the (replicated) Jacobi SVD.  Every rank returns
+ * the same eigenvalues / eigenvectors. */
+int pl2gpu_pca_begin_shard(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t shard_variant_ct, uint32_t pc_ct, Pl2PcaJob** job_ptr);
+int pl2gpu_pca_run_sharded(Pl2PcaJob* job, const double* g1_host, uint64_t total_variant_ct, double* eigvals_host, double* eigvecs_host);
 int pl2gpu_pca_end(Pl2PcaJob* job);
 
 /* ---- per-variant genotype counts {hom-REF, het, hom-ALT, missing}: the hard-call part of the

@@ -2059,31 +2059,58 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
     bool have_freqs = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc);
     if (rc) return rc;
     have_freqs = ApplyReadFreq(*ds, vidx, &ref_freqs, have_freqs);
-    Pl2PcaJob* job = nullptr;
-    rc = pl2gpu_pca_begin(ctx, n, static_cast<uint32_t>(vidx.size()), pc_ct, &job);
-    if (rc) {
-      logprintf("Error: %s\n", pl2gpu_last_error());
-      return rc == 2 ? kRetDegenerateData : kRetGpuFail;
+    // --gpus G: contiguous variant shards, one per device (sizes multiple of 128 so every shard tiles evenly); the
+    // library completes the cross-shard sums with all-reduces (pl2gpu_pca_run_sharded)
+    GpuTeam team;
+    {
+      const uint32_t gpus_eff = std::max(1u, std::min<uint32_t>(c.gpus, static_cast<uint32_t>(vidx.size() / std::max<uint64_t>(q, 4096))));
+      if (gpus_eff < c.gpus) logprintf("Note: --pca approx on %u GPU%s (--gpus %u): too few variants per shard otherwise.\n", gpus_eff, gpus_eff == 1 ? "" : "s", c.gpus);
+      const int trc = TeamInit(ctx, c.device, gpus_eff, &team);
+      if (trc) return trc;
     }
-    BlockStreamer bs(ds, &vidx, n, 32768);
-    if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
-    std::string err;
-    size_t base = 0;
-    for (;;) {
-      const int got = bs.Next(&err);
-      if (got < 0) {
-        logprintf("Error: %s\n", err.c_str());
-        pl2gpu_pca_end(job);
-        return kRetMalformedInput;
+    const uint32_t G = team.size();
+    const uint32_t shard = static_cast<uint32_t>(((vidx.size() + G - 1) / G + 127) / 128 * 128);
+    std::vector<Pl2PcaJob*> jobs(G, nullptr);
+    auto end_jobs = [&]() {
+      for (Pl2PcaJob* j : jobs) pl2gpu_pca_end(j);
+    };
+    for (uint32_t r = 0; r < G; ++r) {
+      const size_t s0 = std::min<size_t>(vidx.size(), static_cast<size_t>(r) * shard), s1 = std::min<size_t>(vidx.size(), s0 + shard);
+      if (s0 == s1) {
+        logprintf("Error: --gpus %u leaves a device without variants.\n", G);
+        end_jobs();
+        return kRetInvalidCmdline;
       }
-      if (!got) break;
-      const int arc = pl2gpu_pca_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, have_freqs ? ref_freqs.data() + base : nullptr);
-      if (arc) {
+      rc = G == 1 ? pl2gpu_pca_begin(team.ctx[r], n, static_cast<uint32_t>(vidx.size()), pc_ct, &jobs[r]) : pl2gpu_pca_begin_shard(team.ctx[r], n, static_cast<uint32_t>(s1 - s0), pc_ct, &jobs[r]);
+      if (rc) {
         logprintf("Error: %s\n", pl2gpu_last_error());
-        pl2gpu_pca_end(job);
-        return arc == 2 ? kRetDegenerateData : kRetGpuFail;
+        end_jobs();
+        return rc == 2 ? kRetDegenerateData : kRetGpuFail;
       }
-      base += static_cast<size_t>(got);
+      std::vector<uint32_t> sub(vidx.begin() + s0, vidx.begin() + s1);
+      BlockStreamer bs(ds, &sub, n, 32768);
+      if (!bs.Init()) {
+        end_jobs();
+        return GpuFail("pl2gpu_host_alloc");
+      }
+      std::string err;
+      size_t base = s0;
+      for (;;) {
+        const int got = bs.Next(&err);
+        if (got < 0) {
+          logprintf("Error: %s\n", err.c_str());
+          end_jobs();
+          return kRetMalformedInput;
+        }
+        if (!got) break;
+        const int arc = pl2gpu_pca_add_variants(jobs[r], bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, have_freqs ? ref_freqs.data() + base : nullptr);
+        if (arc) {
+          logprintf("Error: %s\n", pl2gpu_last_error());
+          end_jobs();
+          return arc == 2 ? kRetDegenerateData : kRetGpuFail;
+        }
+        base += static_cast<size_t>(got);
+      }
     }
     // Gaussian start: the reference's main SFMT stream (seeded by --seed, else by time) sliced over
     // min(--threads, ceil(N*k / 262144)) Box-Muller streams (FillGaussianDArr, plink2_random.cc:89)
@@ -2094,13 +2121,26 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
     std::vector<double> g1(static_cast<uint64_t>(n) * 2 * pc_ct);
     FillGaussian(static_cast<uint64_t>(n) * pc_ct, c.threads ? c.threads : 1, &rng, g1.data());
     logprintf("Projecting random vectors, computing SVD of Krylov matrix, recovering top PCs... ");
-    if (pl2gpu_pca_run(job, g1.data(), eigvals.data(), eigvecs.data())) {
-      logprintf("\nError: %s\n", pl2gpu_last_error());
-      pl2gpu_pca_end(job);
-      return kRetGpuFail;
+    if (G == 1) {
+      if (pl2gpu_pca_run(jobs[0], g1.data(), eigvals.data(), eigvecs.data())) {
+        logprintf("\nError: %s\n", pl2gpu_last_error());
+        end_jobs();
+        return kRetGpuFail;
+      }
+    } else {
+      // collective: one host thread per rank; every rank returns the same result, rank 0's is kept
+      std::vector<std::vector<double>> vals(G, std::vector<double>(pc_ct)), vecs(G);
+      for (uint32_t r = 1; r < G; ++r) vecs[r].resize(static_cast<uint64_t>(pc_ct) * n);
+      std::string errtext;
+      const int prc = ForEachRank(G, [&](uint32_t r) { return pl2gpu_pca_run_sharded(jobs[r], g1.data(), vidx.size(), r ? vals[r].data() : eigvals.data(), r ? vecs[r].data() : eigvecs.data()); }, &errtext);
+      if (prc) {
+        logprintf("\nError: %s\n", errtext.c_str());
+        end_jobs();
+        return kRetGpuFail;
+      }
     }
     logprintf("done.\n");
-    pl2gpu_pca_end(job);
+    end_jobs();
   }
   if (!WriteEigen(c.out, S, pc_ct, eigvals.data(), eigvecs.data())) {
     logprintf("Error: File write failure.\n");

@@ -46,14 +46,14 @@ extern "C" {
 
 int pl2gpu_pca_end(Pl2PcaJob* job);
 
-int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, Pl2PcaJob** job_ptr) {
+static int PcaBeginImpl(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, bool shard, Pl2PcaJob** job_ptr) {
   *job_ptr = nullptr;
   if (!ctx || !sample_ct || !variant_ct_total || !pc_ct) {
     set_error("pl2gpu_pca_begin: bad arguments");
     return 1;
   }
   const uint64_t q = 2ull * pc_ct * (pc_ct + 1);
-  if (q > variant_ct_total) {  // :5716-5719
+  if (q > variant_ct_total && !shard) {  // :5716-5719 (a shard is judged on the total, at run time)
     set_error("Too few variants to compute %u PCs with \"--pca approx\" (%llu required).", pc_ct, static_cast<unsigned long long>(q));
     return 2;
   }
@@ -95,6 +95,9 @@ int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_tot
   *job_ptr = job;
   return 0;
 }
+
+int pl2gpu_pca_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_total, uint32_t pc_ct, Pl2PcaJob** job_ptr) { return PcaBeginImpl(ctx, sample_ct, variant_ct_total, pc_ct, false, job_ptr); }
+int pl2gpu_pca_begin_shard(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t shard_variant_ct, uint32_t pc_ct, Pl2PcaJob** job_ptr) { return PcaBeginImpl(ctx, sample_ct, shard_variant_ct, pc_ct, true, job_ptr); }
 
 int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t variant_stride_bytes, uint32_t variant_ct, int src_is_device, const double* ref_freqs) {
   if (!job || job->variant_ct + static_cast<uint64_t>(variant_ct) > job->variant_cap) {
@@ -160,7 +163,15 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
   return 0;
 }
 
-int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, double* eigvecs_host) {
+}  // extern "C"
+
+// The run itself.  sharded: the job holds ONE variant shard of a world-size team (contexts joined by pl2gpu_comm_init;
+// collective call).  Everything that contracts over variants is a partial sum on each rank and is completed by an
+// in-place fp64 all-reduce (NCCL returns the same bits on every rank, so the replicated small steps stay in lockstep):
+// G' = Y^T H per pass (N x 2k - the exchange SURVEY 8e names), the block Gram-Schmidt coefficients, B = Y^T Q.  The
+// M x 2k block of each orthonormalisation pass is all-gathered (320 bytes per variant) and every rank runs the same
+// Jacobi SVD on it, keeping its own rows.
+static int PcaRunImpl(Pl2PcaJob* job, const double* g1_host, uint64_t total_variant_ct, bool sharded, double* eigvals_host, double* eigvecs_host) {
   if (!job || !g1_host) {
     set_error("pl2gpu_pca_run: bad arguments");
     return 1;
@@ -170,13 +181,19 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   const uint32_t n = job->sample_ct, npad = job->sample_ct_padded, m = job->variant_ct, k = job->pc_ct;
   const uint32_t c2 = 2 * k;
   const uint64_t q = static_cast<uint64_t>(c2) * (k + 1);
-  if (q > m || q > n) {
-    set_error("pl2gpu_pca_run: need 2k(k+1) = %llu <= min(variants %u, samples %u)", static_cast<unsigned long long>(q), m, n);
+  const uint32_t world = sharded ? static_cast<uint32_t>(c->comm_world) : 1, rank = sharded ? static_cast<uint32_t>(c->comm_rank) : 0;
+  if (sharded && (!c->comm || !job->tensor || !m)) {
+    set_error("pl2gpu_pca_run_sharded: needs a communicator on the context, the tensor path and a non-empty shard");
+    return 1;
+  }
+  if (!sharded) total_variant_ct = m;
+  if (q > total_variant_ct || q > n) {
+    set_error("pl2gpu_pca_run: need 2k(k+1) = %llu <= min(variants %llu, samples %u)", static_cast<unsigned long long>(q), static_cast<unsigned long long>(total_variant_ct), n);
     return 1;
   }
   double *d_qq = nullptr, *d_u = nullptr, *d_g1 = nullptr, *d_g2 = nullptr, *d_b = nullptr, *d_gram = nullptr, *d_gram_u = nullptr, *d_gram_partial = nullptr, *d_colscale = nullptr;
   int rc = 1;
-  const double m_recip = 1.0 / static_cast<double>(m);
+  const double m_recip = 1.0 / static_cast<double>(total_variant_ct);
   // ---- tensor path scratch (pca_ts_kernels.cuh): digit planes, per-column scales, split-K partial sums ----
   const bool tensor = job->tensor;
   uint8_t *d_gdig = nullptr, *d_hs = nullptr, *d_hi = nullptr;
@@ -296,6 +313,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
       if (iter < k) {
         if (cudaMemsetAsync(d_g2, 0, static_cast<uint64_t>(npad) * c2 * 8, c->stream) != cudaSuccess) break;
         launch_xtb(d_qq, m, iter * c2, c2, d_g2, c2, 1);
+        if (sharded && CommAllReduceSumF64(c, d_g2, static_cast<uint64_t>(npad) * c2, c->stream)) break;
         scale_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(npad) * c2, 256)), 256, 0, c->stream>>>(d_g2, static_cast<uint64_t>(npad) * c2, m_recip);
         c->launches++;
         std::swap(d_g1, d_g2);
@@ -319,7 +337,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     std::vector<double> s(q);
     const char* err = nullptr;
     const char* basis_env = getenv("PL2_PCA_BASIS");
-    const bool bcgs = !(basis_env && !strcmp(basis_env, "jacobi"));
+    const bool bcgs = sharded || !(basis_env && !strcmp(basis_env, "jacobi"));
     const double* d_basis = d_u;
     if (!bcgs) {
       if (JacobiSvd(c, d_qq, m, m, static_cast<uint32_t>(q), static_cast<uint32_t>(q), s.data(), d_u, m, nullptr, &err)) {
@@ -327,29 +345,66 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
         break;
       }
     } else {
-      double *d_c = nullptr, *d_cpart = nullptr;
+      double *d_c = nullptr, *d_cpart = nullptr, *d_wg = nullptr, *d_wf = nullptr, *d_uf = nullptr, *d_sizes = nullptr;
       uint64_t part_doubles = 1;
       for (uint32_t t = 1; t <= k; ++t) part_doubles = std::max(part_doubles, DgemmTNPartialDoubles(c, t * c2, c2, m));
       bool ok = cudaMalloc(&d_c, q * c2 * 8) == cudaSuccess && cudaMalloc(&d_cpart, part_doubles * 8) == cudaSuccess;
+      // sharded: every rank learns the shard sizes (one all-reduce of a world-length vector), blocks are exchanged
+      // in slots of the largest shard
+      uint64_t m_pad = m;
+      if (ok && sharded) {
+        std::vector<double> sizes(world, 0.0);
+        sizes[rank] = static_cast<double>(m);
+        ok = cudaMalloc(&d_sizes, 8ull * world) == cudaSuccess && cudaMemcpyAsync(d_sizes, sizes.data(), 8ull * world, cudaMemcpyHostToDevice, c->stream) == cudaSuccess &&
+             !CommAllReduceSumF64(c, d_sizes, world, c->stream) && cudaMemcpyAsync(sizes.data(), d_sizes, 8ull * world, cudaMemcpyDeviceToHost, c->stream) == cudaSuccess &&
+             cudaStreamSynchronize(c->stream) == cudaSuccess;
+        for (uint32_t r = 0; ok && r < world; ++r) m_pad = std::max<uint64_t>(m_pad, static_cast<uint64_t>(sizes[r]));
+        const uint64_t blk = m_pad * c2 * 8;
+        ok = ok && cudaMalloc(&d_wg, blk * world) == cudaSuccess && cudaMalloc(&d_wf, blk * world) == cudaSuccess && cudaMalloc(&d_uf, blk * world) == cudaSuccess;
+      }
+      const uint64_t m_full = m_pad * world;
       for (uint32_t t = 0; ok && t <= k; ++t) {
         double* w = d_qq + static_cast<uint64_t>(t) * c2 * m;
         const uint32_t prev = t * c2;
         for (int rep = 0; ok && rep < 3; ++rep) {
           if (prev) {
-            ok = !DgemmTN(c, d_qq, m, prev, w, m, c2, m, d_cpart, d_c, prev) && !DgemmNN(c, d_qq, m, m, prev, d_c, prev, c2, w, m, true, nullptr);
+            ok = !DgemmTN(c, d_qq, m, prev, w, m, c2, m, d_cpart, d_c, prev) && !(sharded && CommAllReduceSumF64(c, d_c, static_cast<uint64_t>(prev) * c2, c->stream)) &&
+                 !DgemmNN(c, d_qq, m, m, prev, d_c, prev, c2, w, m, true, nullptr);
             if (!ok) break;
           }
-          if (JacobiSvd(c, w, m, m, c2, c2, s.data(), d_u, m, nullptr, &err)) {
-            ok = false;
-            break;
+          if (!sharded) {
+            if (JacobiSvd(c, w, m, m, c2, c2, s.data(), d_u, m, nullptr, &err)) {
+              ok = false;
+              break;
+            }
+            ok = cudaMemcpyAsync(w, d_u, static_cast<uint64_t>(m) * c2 * 8, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+          } else {
+            // my rows into my slot (zero-padded to m_pad), all-gather, repack to one column-major (world m_pad) x 2k
+            // matrix, the same Jacobi SVD on every rank, my rows of the unit left singular vectors back into the block
+            double* slot = d_wg + static_cast<uint64_t>(rank) * m_pad * c2;
+            ok = cudaMemsetAsync(slot, 0, m_pad * c2 * 8, c->stream) == cudaSuccess &&
+                 cudaMemcpy2DAsync(slot, m_pad * 8, w, static_cast<uint64_t>(m) * 8, static_cast<uint64_t>(m) * 8, c2, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess &&
+                 !CommAllGatherInPlace(c, d_wg, m_pad * c2 * 8, c->stream);
+            for (uint32_t r = 0; ok && r < world; ++r)
+              ok = cudaMemcpy2DAsync(d_wf + static_cast<uint64_t>(r) * m_pad, m_full * 8, d_wg + static_cast<uint64_t>(r) * m_pad * c2, m_pad * 8, m_pad * 8, c2, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+            if (!ok) break;
+            if (JacobiSvd(c, d_wf, m_full, static_cast<uint32_t>(m_full), c2, c2, s.data(), d_uf, m_full, nullptr, &err)) {
+              ok = false;
+              break;
+            }
+            ok = cudaMemcpy2DAsync(w, static_cast<uint64_t>(m) * 8, d_uf + static_cast<uint64_t>(rank) * m_pad, m_full * 8, static_cast<uint64_t>(m) * 8, c2, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
           }
-          ok = cudaMemcpyAsync(w, d_u, static_cast<uint64_t>(m) * c2 * 8, cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
         }
       }
       cudaFree(d_c);
       cudaFree(d_cpart);
+      cudaFree(d_wg);
+      cudaFree(d_wf);
+      cudaFree(d_uf);
+      cudaFree(d_sizes);
       if (!ok) {
         cudaGetLastError();
+        if (!err && *get_error()) break;  // a collective already recorded its message
         set_error("Failed to orthonormalise the Krylov matrix (%s).", err ? err : "CUDA failure");
         break;
       }
@@ -359,6 +414,7 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
     // B = Y^T Q (N x q, column-major)   :5870-5916
     if (cudaMemsetAsync(d_b, 0, static_cast<uint64_t>(n) * q * 8, c->stream) != cudaSuccess) break;
     launch_xtb(d_basis, m, 0, static_cast<uint32_t>(q), d_b, 1, n);
+    if (sharded && CommAllReduceSumF64(c, d_b, static_cast<uint64_t>(n) * q, c->stream)) break;
     mark("B = Yt.Q");
     // Top-k left singular pairs of B (:5920, dgesvd in the reference).  Only the leading k of q are wanted and they
     // are the well-conditioned ones, so they come from the q x q Gram matrix: G = B^T B (fp64, fixed-order split
@@ -432,6 +488,14 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
   cudaFree(d_g2);
   cudaFree(d_b);
   return rc;
+}
+
+extern "C" {
+
+int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, double* eigvecs_host) { return PcaRunImpl(job, g1_host, 0, false, eigvals_host, eigvecs_host); }
+
+int pl2gpu_pca_run_sharded(Pl2PcaJob* job, const double* g1_host, uint64_t total_variant_ct, double* eigvals_host, double* eigvecs_host) {
+  return PcaRunImpl(job, g1_host, total_variant_ct, true, eigvals_host, eigvecs_host);
 }
 
 int pl2gpu_pca_end(Pl2PcaJob* job) {

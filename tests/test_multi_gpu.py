@@ -60,3 +60,41 @@ def test_grm_two_gpus_matches_single(dummy, tmp_path):
     b = np.fromfile(two + ".grm.bin", dtype=np.float32).astype(np.float64)
     assert np.allclose(b, a, rtol=1e-5, atol=2e-8)
     assert open(ref + ".grm.N.bin", "rb").read() == open(two + ".grm.N.bin", "rb").read()
+
+
+def _write_bed(prefix, geno):
+    """geno [variants, samples] codes 0/1/2/3 (ALT count, 3 = missing) -> .bed (SNP-major) / .bim / .fam."""
+    m, n = geno.shape
+    bed_code = np.array([3, 2, 0, 1], dtype=np.uint8)[geno]  # .bed: 00 hom A1(=ALT), 01 missing, 10 het, 11 hom A2(=REF)
+    pad = (-n) % 4
+    b = np.pad(bed_code, ((0, 0), (0, pad))).reshape(m, -1, 4)
+    packed = (b[:, :, 0] | (b[:, :, 1] << 2) | (b[:, :, 2] << 4) | (b[:, :, 3] << 6)).astype(np.uint8)
+    with open(prefix + ".bed", "wb") as f:
+        f.write(bytes([0x6C, 0x1B, 0x01]))
+        packed.tofile(f)
+    with open(prefix + ".bim", "w") as f:
+        f.write("".join(f"1\tsnp{k}\t0\t{k + 1}\tA\tG\n" for k in range(m)))
+    with open(prefix + ".fam", "w") as f:
+        f.write("".join(f"0\tper{k}\t0\t0\t2\t-9\n" for k in range(n)))
+
+
+def test_pca_approx_two_gpus_matches_single(tmp_path):
+    """`--pca approx --gpus 2`: variant shards, fp64 all-reduces of the N x 2k pass matrix / the Gram-Schmidt coefficients
+    / B inside libpl2gpu.  Structure PCs must agree with the one-device run to the report's precision."""
+    if _device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from test_pca_gpu import _structured_geno
+
+    geno = _structured_geno(24000, 6000, seed=17, pops=6, fst=0.1)
+    pre = str(tmp_path / "s")
+    _write_bed(pre, geno)
+    one, two = str(tmp_path / "one"), str(tmp_path / "two")
+    sh([BIN, "--bfile", pre, "--pca", "8", "approx", "--seed", "3", "--out", one])
+    r = sh([BIN, "--bfile", pre, "--pca", "8", "approx", "--seed", "3", "--gpus", "2", "--out", two])
+    assert "on 1 GPU" not in r.stdout
+    v1, v2 = np.loadtxt(one + ".eigenval"), np.loadtxt(two + ".eigenval")
+    assert np.allclose(v2[:5], v1[:5], rtol=2e-6) and np.allclose(v2, v1, rtol=5e-3)
+    e1 = np.array([ln.split("\t")[2:] for ln in open(one + ".eigenvec").read().split("\n")[1:] if ln], dtype=float).T
+    e2 = np.array([ln.split("\t")[2:] for ln in open(two + ".eigenvec").read().split("\n")[1:] if ln], dtype=float).T
+    sg = np.sign(np.sum(e1 * e2, axis=1, keepdims=True))
+    assert np.allclose(e2[:5] * sg[:5], e1[:5], atol=2e-5 * np.abs(e1[:5]).max())

@@ -31,7 +31,7 @@ def write_pgen(prefix, n, m, chrom_ct=1, ld_copy=0.0):
     t0 = time.perf_counter()
     with open(prefix + ".pgen", "wb") as f:
         f.write(bytes([0x6C, 0x1B, 0x02]) + int(m).to_bytes(4, "little") + int(n).to_bytes(4, "little") + bytes([0x40]))
-            for s0 in range(0, m, 8192):
+        for s0 in range(0, m, 8192):
             s1 = min(m, s0 + 8192)
             by = bench.synth_genovecs(torch, n, s0, s1, dev)[:, :bpv].contiguous()
             if ld_copy > 0:
