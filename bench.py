@@ -284,6 +284,15 @@ def cpu_legs(args):
     return cpu_baseline, cli
 
 
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling
+    guide's fallback."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        return 6500.0
+
+
 # ------------------------------------------------------------------------------------- secondary
 def secondary_legs(args, torch, p, ctx, dev, peak_tops):
     """Short measurements of the other kernels of the path (not the headline metric), inputs resident."""
@@ -372,6 +381,83 @@ def secondary_legs(args, torch, p, ctx, dev, peak_tops):
                 shutil.rmtree(tmp, ignore_errors=True)
     except Exception as ex:
         sec["pca"]["cpu_baseline"] = {"error": str(ex)[-200:]}
+    # --indep-pairwise pair decisions (ld_ts_kernel) at config 4's founder count, and --score accumulation; each with the
+    # reference's own command timed on a bounded sample of the same generator's data
+    try:
+        import ctypes as C
+
+        from plink_ng_b200.capi import check, lib
+
+        nf, mv, window = min(args.samples, 50000), 131072, 500
+        g4 = synth_genovecs(torch, nf, 0, mv, dev)
+        band = window - 1
+        flags_t = torch.zeros((mv, band), dtype=torch.uint8).pin_memory()
+        for _ in range(2):
+            ctx.synchronize()
+            t0 = time.perf_counter()
+            check(lib.pl2gpu_ld_band_flags(ctx.handle, C.c_void_p(g4.data_ptr()), g4.shape[1], nf, mv, 1, band, 0.2 * (1 + 2.0 ** -44), flags_t.numpy().ctypes.data), "pl2gpu_ld_band_flags")
+            dt = time.perf_counter() - t0
+        pairs = mv * band - band * (band + 1) // 2
+        sec["ld"] = {"kernel": "ld_ts_kernel", "workload": f"pair decisions of --indep-pairwise {window} on {nf} founders x {mv} variants (whole pl2gpu_ld_band_flags call incl. staging and {flags_t.numel() / 1e6:.0f} MB of decisions to pinned host memory)",
+                     "seconds": dt, "pairs_per_s": pairs / dt, "achieved": 12 * pairs * nf / dt / 1e12, "unit": "TOP/s (int8; 6 products x 2 ops per pair and founder)", "peak": peak_tops,
+                     "frac": (12 * pairs * nf / dt / 1e12) / peak_tops if peak_tops else None}
+        del g4, flags_t
+        ref = ref_binary()
+        if ref:
+            nc, mc = 8192, 32768
+            tmp = tempfile.mkdtemp(prefix="pl2ld_")
+            try:
+                prefix = os.path.join(tmp, "g")
+                write_synth_bed(prefix, nc, mc)
+                threads = effective_cores()["threads_used"]
+                dt_ref = run_cli(ref, prefix, prefix + "_out", ["--indep-pairwise", str(window), "50", "0.2"], threads)
+                # the reference evaluates (almost) every pair of a window on unlinked data: variants x (window - 1 + step) / 2 ... bounded above by variants x band
+                sec["ld"]["cpu_baseline"] = {"kind": "reference", "cores": threads, "seconds": dt_ref, "sample": f"{nc} founders x {mc} variants on one chromosome (one compute thread per chromosome in the reference), whole `--indep-pairwise {window} 50 0.2` run",
+                                             "founder_pairs_per_s_upper_bound": nc * (mc * band) / dt_ref}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as ex:
+        sec.setdefault("ld", {})["error"] = str(ex)[-300:]
+    try:
+        import ctypes as C
+
+        from plink_ng_b200.capi import check, lib
+
+        ns, ms = args.samples, 131072
+        g5 = synth_genovecs(torch, ns, 0, ms, dev)
+        w4 = np.random.default_rng(2).normal(size=(ms, 4))
+        d4 = np.full(ms, 0 | (1 << 2) | (2 << 4), dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib.pl2gpu_score_begin(ctx.handle, ns, C.byref(h)), "pl2gpu_score_begin")
+        try:
+            for _ in range(2):
+                ctx.synchronize()
+                t0 = time.perf_counter()
+                check(lib.pl2gpu_score_add_variants(h, C.c_void_p(g5.data_ptr()), g5.shape[1], ms, 1, w4.ctypes.data, d4.ctypes.data), "pl2gpu_score_add_variants")
+                dt = time.perf_counter() - t0
+        finally:
+            lib.pl2gpu_score_end(h)
+        sec["score"] = {"kernel": "score_kernel", "workload": f"--score accumulation, {ns} samples x {ms} scored entries, genotypes resident (whole pl2gpu_score_add_variants call)", "seconds": dt,
+                        "sample_entries_per_s": ns * ms / dt, "achieved": ns * ms / 4 / dt / 1e9, "unit": "GB/s of 2-bit genotypes", "peak": hbm_peak_gbs(), "bound": "ALU (fp64 table add per sample and entry), then HBM"}
+        del g5
+        ref = ref_binary()
+        if ref:
+            nc, mc = 8192, 65536
+            tmp = tempfile.mkdtemp(prefix="pl2sc_")
+            try:
+                prefix = os.path.join(tmp, "g")
+                write_synth_bed(prefix, nc, mc)
+                with open(prefix + ".bim") as f, open(prefix + ".score", "w") as o:
+                    for k, ln in enumerate(f):
+                        t = ln.split()
+                        o.write(f"{t[1]}\t{t[4]}\t{(k % 7 - 3) * 0.01}\n")
+                threads = effective_cores()["threads_used"]
+                dt_ref = run_cli(ref, prefix, prefix + "_out", ["--score", prefix + ".score"], threads)
+                sec["score"]["cpu_baseline"] = {"kind": "reference", "cores": threads, "seconds": dt_ref, "sample": f"{nc} samples x {mc} scored variants, whole `--score` run", "sample_entries_per_s": nc * mc / dt_ref}
+            finally:
+                shutil.rmtree(tmp, ignore_errors=True)
+    except Exception as ex:
+        sec.setdefault("score", {})["error"] = str(ex)[-300:]
     return sec
 
 
