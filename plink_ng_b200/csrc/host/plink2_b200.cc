@@ -2535,28 +2535,6 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   }
   const uint32_t m = V.size();
   const uint32_t words = PgenReader::WordsFor(founder_ct);
-  std::vector<uint32_t> all(m);
-  for (uint32_t v = 0; v < m; ++v) all[v] = v;
-  BlockStreamer bs(ds, &all, founder_ct, 8192);
-  if (founder_ct != n) bs.sample_include = inc.data();
-  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
-  // the whole founder block is staged in host memory (M * ceil(F/32) * 8 bytes), then handed to the
-  // function-face entry point which windows it through the GPU
-  void* blk = nullptr;
-  if (pl2gpu_host_alloc(static_cast<uint64_t>(m) * words * 8, &blk)) return GpuFail("pl2gpu_host_alloc");
-  std::string err;
-  size_t base = 0;
-  for (;;) {
-    const int got = bs.Next(&err);
-    if (got < 0) {
-      logprintf("Error: %s\n", err.c_str());
-      pl2gpu_host_free(blk);
-      return kRetMalformedInput;
-    }
-    if (!got) break;
-    memcpy(static_cast<uint64_t*>(blk) + base * words, bs.buf, static_cast<uint64_t>(got) * words * 8);
-    base += static_cast<size_t>(got);
-  }
   // --indep-preferred (plink2_ld.cc:2577-2597, NondupIdLoad): variants whose ID is listed keep priority in
   // the pairwise victim choice (:916-918)
   std::vector<uint8_t> preferred;
@@ -2564,7 +2542,6 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     std::vector<std::string> plines;
     std::string perr;
     if (!ReadLines(c.indep_preferred, &plines, &perr)) {
-      pl2gpu_host_free(blk);
       logprintf("Error: %s\n", perr.c_str());
       return kRetOpenFail;
     }
@@ -2585,11 +2562,59 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     }
     logprintf("--indep-preferred: %u variant%s loaded.\n", pref_ct, pref_ct == 1 ? "" : "s");
   }
+  // Chromosomes are independent jobs (LdPruneSubcontigSplitAll never crosses one, plink2_ld.cc:2165-2268): each
+  // contiguous chromosome run is staged in pinned host memory and handed to the function-face entry point on its own, so
+  // the staging buffer and the decision matrix are O(largest chromosome), not O(genome).
   std::vector<uint8_t> removed(m, 0);
-  const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, m, V.chr_code.data(), V.bp.data(), c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0, ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data(), preferred.empty() ? nullptr : preferred.data(), 0,
-                                       founder_sex.data(), c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data());
+  struct ChrRun {
+    uint32_t v0, v1;
+  };
+  std::vector<ChrRun> chr_runs;
+  uint32_t longest = 0;
+  for (uint32_t s0 = 0; s0 < m;) {
+    uint32_t e = s0 + 1;
+    while (e < m && V.chr_code[e] == V.chr_code[s0]) ++e;
+    if (V.chr_code[s0] == 0) {
+      for (uint32_t v = s0; v < e; ++v) removed[v] = 2;
+    } else if (e - s0 >= 2) {
+      chr_runs.push_back({s0, e});
+      longest = std::max(longest, e - s0);
+    }
+    s0 = e;
+  }
+  void* blk = nullptr;
+  if (longest && pl2gpu_host_alloc(static_cast<uint64_t>(longest) * words * 8, &blk)) return GpuFail("pl2gpu_host_alloc");
+  for (const ChrRun& run : chr_runs) {
+    std::vector<uint32_t> vsub(run.v1 - run.v0);
+    for (uint32_t v = run.v0; v < run.v1; ++v) vsub[v - run.v0] = v;
+    BlockStreamer bs(ds, &vsub, founder_ct, 8192);
+    if (founder_ct != n) bs.sample_include = inc.data();
+    if (!bs.Init()) {
+      pl2gpu_host_free(blk);
+      return GpuFail("pl2gpu_host_alloc");
+    }
+    std::string err;
+    size_t base = 0;
+    for (;;) {
+      const int got = bs.Next(&err);
+      if (got < 0) {
+        logprintf("Error: %s\n", err.c_str());
+        pl2gpu_host_free(blk);
+        return kRetMalformedInput;
+      }
+      if (!got) break;
+      memcpy(static_cast<uint64_t*>(blk) + base * words, bs.buf, static_cast<uint64_t>(got) * words * 8);
+      base += static_cast<size_t>(got);
+    }
+    const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, run.v1 - run.v0, V.chr_code.data() + run.v0, V.bp.data() + run.v0, c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0,
+                                         ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data() + run.v0, preferred.empty() ? nullptr : preferred.data() + run.v0, 0, founder_sex.data(),
+                                         c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data() + run.v0);
+    if (rc) {
+      pl2gpu_host_free(blk);
+      return GpuFail("pl2_indep_pairwise");
+    }
+  }
   pl2gpu_host_free(blk);
-  if (rc) return GpuFail("pl2_indep_pairwise");
   // LdPruneWrite (plink2_ld.cc:2464-2528)
   const std::string in_name = c.out + ".prune.in", out_name = c.out + ".prune.out";
   OutFile fin, fout;

@@ -6,9 +6,9 @@
 // with 'no-mean-imputation', :6605-6607) and the integer named-allele dosages, so centring / dominant / recessive
 // variants are a matter of the table the caller builds.
 //
-// Streaming, HBM/ALU-bound: every 32-bit word of a variant row (16 samples) is read once.  A CTA covers 128 words x a
-// chunk of variants and writes per-chunk partial sums; a second kernel adds the partials in chunk order, so results do
-// not depend on scheduling.
+// Streaming: every 32-bit word of a variant row (16 samples) is read once.  A CTA covers 128 words x a chunk of
+// variants and writes per-chunk partial sums; a second kernel adds the partials in chunk order, so results do not
+// depend on scheduling.  The fp64 adds go through a two-variant lookup table, the integer sums are bit-parallel.
 #include <algorithm>
 #include <vector>
 
@@ -20,14 +20,22 @@ using namespace pl2;
 namespace {
 
 constexpr uint32_t kScoreThreads = 128;
-constexpr uint32_t kScoreTile = 64;  // variants whose tables are staged in shared memory at a time
+constexpr uint32_t kScoreTile = 64;  // variants whose tables are staged in shared memory at a time (even)
 
+// One thread owns one 32-bit word column (16 samples) of a chunk of variants.
+//  * fp64 sums: variants are taken in PAIRS; s_t2[pair][ca + 4 cb] = w_a[ca] + w_b[cb] (16 doubles = 128 bytes, one
+//    bank group: conflict-free for any index pattern), and the two words are merged into per-sample nibbles
+//    (x: even samples, y: odd samples), so a sample costs one bit-field extract, one LDS.64 and one DADD per TWO variants.
+//  * integer sums: the named-allele dosage (0..2) and the missing flag are added bit-parallel for all 16 samples at
+//    once in 4-bit fields (8 samples per register), spilled to 8-bit fields every 7 variants and to the 32-bit
+//    per-sample counters every 127 variants.  A REF-named entry flips hom-REF <-> hom-ALT first
+//    (w ^= (~w & 0x5555...) << 1), after which the dosage is the code itself with "missing" cleared.
 // raw: [variant][pitch] bytes (pitch multiple of 4, padding samples coded missing); w4: [variant][4] weights;
-// d4: [variant] packed named-allele dosages of codes 0..2 (2 bits each; code 3 contributes nothing).
+// d4: [variant] packed named-allele dosages of codes 0..2 (2 bits each): 0x24 = ALT named, 0x06 = REF named.
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t words, uint32_t variant_ct, uint32_t chunk_variants, const double* __restrict__ w4, const uint8_t* __restrict__ d4,
                                                            double* __restrict__ part_sum, uint32_t* __restrict__ part_dos, uint32_t* __restrict__ part_miss, uint32_t samples_padded) {
-  __shared__ double s_w[kScoreTile * 4];
-  __shared__ uint8_t s_d[kScoreTile];
+  __shared__ double s_t2[(kScoreTile / 2) * 16];
+  __shared__ uint32_t s_flip[kScoreTile];
   const uint32_t widx = blockIdx.x * kScoreThreads + threadIdx.x;
   const uint32_t v_begin = blockIdx.y * chunk_variants, v_end = min(variant_ct, v_begin + chunk_variants);
   double sum[16];
@@ -38,28 +46,84 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
     dos[s] = 0;
     miss[s] = 0;
   }
+  // 4-bit fields (even / odd samples) and 8-bit fields (sample s -> register s % 4 ... see spill lambdas)
+  uint32_t d4e = 0, d4o = 0, m4e = 0, m4o = 0;
+  uint32_t d8[4] = {0, 0, 0, 0}, m8[4] = {0, 0, 0, 0};
+  uint32_t n4 = 0, n8 = 0;
+  auto spill4 = [&]() {  // 4-bit -> 8-bit: nibble j of the even register is sample 2j, of the odd register sample 2j+1
+    d8[0] += d4e & 0x0F0F0F0Fu;         // samples 0, 4, 8, 12
+    d8[1] += (d4e >> 4) & 0x0F0F0F0Fu;  // samples 2, 6, 10, 14
+    d8[2] += d4o & 0x0F0F0F0Fu;         // samples 1, 5, 9, 13
+    d8[3] += (d4o >> 4) & 0x0F0F0F0Fu;  // samples 3, 7, 11, 15
+    m8[0] += m4e & 0x0F0F0F0Fu;
+    m8[1] += (m4e >> 4) & 0x0F0F0F0Fu;
+    m8[2] += m4o & 0x0F0F0F0Fu;
+    m8[3] += (m4o >> 4) & 0x0F0F0F0Fu;
+    d4e = d4o = m4e = m4o = 0;
+    n4 = 0;
+  };
+  auto spill8 = [&]() {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int s0 = (r == 0) ? 0 : (r == 1) ? 2 : (r == 2) ? 1 : 3;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        dos[s0 + 4 * b] += (d8[r] >> (8 * b)) & 0xFFu;
+        miss[s0 + 4 * b] += (m8[r] >> (8 * b)) & 0xFFu;
+      }
+      d8[r] = 0;
+      m8[r] = 0;
+    }
+    n8 = 0;
+  };
   for (uint32_t v0 = v_begin; v0 < v_end; v0 += kScoreTile) {
     const uint32_t tile = min(kScoreTile, v_end - v0);
+    const uint32_t pairs = (tile + 1) / 2;
     __syncthreads();
-    for (uint32_t e = threadIdx.x; e < tile * 4; e += kScoreThreads) s_w[e] = w4[4ull * v0 + e];
-    for (uint32_t e = threadIdx.x; e < tile; e += kScoreThreads) s_d[e] = d4[v0 + e];
+    for (uint32_t e = threadIdx.x; e < pairs * 16; e += kScoreThreads) {
+      const uint32_t pr = e >> 4, ca = e & 3, cb = (e >> 2) & 3;
+      const uint32_t va = v0 + 2 * pr, vb = va + 1;
+      s_t2[e] = w4[4ull * va + ca] + ((vb < v_end) ? w4[4ull * vb + cb] : 0.0);
+    }
+    for (uint32_t e = threadIdx.x; e < tile; e += kScoreThreads) s_flip[e] = (d4[v0 + e] & 3) ? 0xFFFFFFFFu : 0u;  // dosage of code 0 nonzero: REF named
     __syncthreads();
     if (widx >= words) continue;
-    for (uint32_t t = 0; t < tile; ++t) {
-      const uint32_t word = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(v0 + t) * pitch + 4ull * widx);
-      const double w0 = s_w[4 * t], w1 = s_w[4 * t + 1], w2 = s_w[4 * t + 2], w3 = s_w[4 * t + 3];
-      const uint32_t dd = s_d[t];
-      const uint32_t d0 = dd & 3, d1 = (dd >> 2) & 3, d2 = (dd >> 4) & 3;
+    for (uint32_t pr = 0; pr < pairs; ++pr) {
+      const uint32_t va = v0 + 2 * pr;
+      const bool has_b = 2 * pr + 1 < tile;
+      const uint32_t wa = *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(va) * pitch + 4ull * widx);
+      const uint32_t wb = has_b ? *reinterpret_cast<const uint32_t*>(raw + static_cast<uint64_t>(va + 1) * pitch + 4ull * widx) : 0u;
+      // fp64: combined nibbles (code_a | code_b << 2); a missing second word indexes cb = 0, whose table part is 0
+      const uint32_t x = (wa & 0x33333333u) | ((wb & 0x33333333u) << 2);
+      const uint32_t y = ((wa >> 2) & 0x33333333u) | (wb & 0xCCCCCCCCu);
+      const double* t2 = &s_t2[16 * pr];
 #pragma unroll
-      for (int s = 0; s < 16; ++s) {
-        const uint32_t lo = (word >> (2 * s)) & 1, hi = (word >> (2 * s + 1)) & 1;
-        sum[s] += hi ? (lo ? w3 : w2) : (lo ? w1 : w0);
-        dos[s] += hi ? (lo ? 0u : d2) : (lo ? d1 : d0);
-        miss[s] += lo & hi;
+      for (int j = 0; j < 8; ++j) {
+        sum[2 * j] += t2[(x >> (4 * j)) & 15u];
+        sum[2 * j + 1] += t2[(y >> (4 * j)) & 15u];
+      }
+      // integers, bit-parallel
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (h && !has_b) break;
+        uint32_t w = h ? wb : wa;
+        const uint32_t ms = w & (w >> 1) & 0x55555555u;  // missing flag at the even bit of each 2-bit field
+        w ^= ((~w & 0x55555555u) << 1) & s_flip[2 * pr + h];  // REF named: 0 <-> 2 (1 and 3 keep their value)
+        const uint32_t d = w ^ (ms * 3u);                   // missing -> 0
+        d4e += d & 0x33333333u;
+        d4o += (d >> 2) & 0x33333333u;
+        m4e += ms & 0x11111111u;
+        m4o += (ms >> 2) & 0x11111111u;
+        if (++n4 == 7) {
+          spill4();
+          if (++n8 == 18) spill8();  // 18 x 7 x 2 = 252 <= 255
+        }
       }
     }
   }
   if (widx >= words) return;
+  spill4();
+  spill8();
   const uint64_t base = static_cast<uint64_t>(blockIdx.y) * samples_padded + 16ull * widx;
 #pragma unroll
   for (int s = 0; s < 16; ++s) {
@@ -159,6 +223,12 @@ int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t v
   if (!job || (variant_ct && (!genovecs || !weights4 || !named_dosages))) {
     set_error("pl2gpu_score_add_variants: bad arguments");
     return 1;
+  }
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    if (named_dosages[v] != 0x24 && named_dosages[v] != 0x06) {
+      set_error("pl2gpu_score_add_variants: entry %u has named-allele dosages 0x%02x (0x24 = ALT named, 0x06 = REF named)", v, named_dosages[v]);
+      return 1;
+    }
   }
   Ctx* c = &job->ctx->c;
   PL2_CUDA_OK(cudaSetDevice(c->device));
