@@ -631,11 +631,15 @@ def b200_arm(args):
     achieved = ops / (kern_ms * 1e-3) / 1e12
     kname = {KING_ALGO_TENSOR_TS: "king_ts_kernel", KING_ALGO_TENSOR: "king_tc_kernel", KING_ALGO_POPCOUNT: "king_popc_kernel"}[algo]
     acc_bytes = 2 * 20 * my_pairs  # int32 x 5 accumulators read + written once per launch (tile padding excluded)
-    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": None,
+    # DRAM bytes of ONE king_ts_kernel launch at exactly this shape, from `ncu --metrics dram__bytes_read.sum,
+    # dram__bytes_write.sum -k regex:king_ts_kernel` on this command (profiles/r02_king_traffic_100k.csv): 609.5 GB read +
+    # 100.6 GB written.  Only quoted for the configuration it was captured on.
+    traffic = 609530605824 + 100556782336 if (n, mb, world, algo) == (FULL_N, 131072, 1, KING_ALGO_TENSOR_TS) else None
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TOP/s (int8)", "frac": achieved / peak, "traffic": traffic,
                 "kernel": kname, "kernel_ms": kern_ms, "kernel_ms_max_over_ranks": kern_ms_max, "peak_source": peak_src, "peak_detail": peak_detail,
                 "frac_of_nominal_4500": achieved / 4500.0, "frac_of_2x_bf16_burst": achieved / (2 * peaks["bf16_tflops"]) if peaks.get("bf16_tflops") else None,
                 "algorithmic_ops_per_launch": ops, "algorithmic_bytes_per_launch": acc_bytes + n * mb // 2,
-                "traffic_note": "see profiles/r02_ncu_king_ts.md for dram__bytes of the shipped kernel; the accumulator read-modify-write is the compulsory part, operand re-reads across the 12x12-tile launch blocks come on top (tensor-bound kernel: < 5 % of HBM bandwidth either way)",
+                "traffic_note": "bytes per launch from one ncu capture of this kernel at this shape (profiles/r02_king_traffic_100k.csv; profiles/r02_ncu_summary.md has the --set full capture at 16,384 samples): written = the accumulators once (100.6 GB); read = accumulators once + operand tiles re-fetched when the 12x12-tile launch blocks outrun the L2 (15 % of the operand requests miss at 131,072 variants per step). 710 GB in 1.75 s is 6 % of the HBM bandwidth: the kernel is tensor-bound (pipe 82.6 % active) and the re-reads cost no time",
                 "kernel_ms_note": "CUDA events recorded by the library around the king_ts_kernel launch on its stream (last timed step); the step additionally holds the copy/all-gather, padding and row re-tiling of the next batch, overlapped on the prep stream"}
     if algo == KING_ALGO_POPCOUNT:
         roofline["note"] = "popcount kernel: int8-equivalent ops shown for comparability; its own limiter is the POPC pipe"

@@ -2582,39 +2582,32 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     }
     s0 = e;
   }
-  void* blk = nullptr;
-  if (longest && pl2gpu_host_alloc(static_cast<uint64_t>(longest) * words * 8, &blk)) return GpuFail("pl2gpu_host_alloc");
+  // one pinned buffer of the longest run; every run is decoded straight into it (BlockStreamer's own buffer)
+  std::vector<uint32_t> vsub;
+  BlockStreamer bs(ds, &vsub, founder_ct, std::max(longest, 1u));
+  if (founder_ct != n) bs.sample_include = inc.data();
+  if (longest && !bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  double t_decode = 0, t_device = 0;
   for (const ChrRun& run : chr_runs) {
-    std::vector<uint32_t> vsub(run.v1 - run.v0);
+    vsub.resize(run.v1 - run.v0);
     for (uint32_t v = run.v0; v < run.v1; ++v) vsub[v - run.v0] = v;
-    BlockStreamer bs(ds, &vsub, founder_ct, 8192);
-    if (founder_ct != n) bs.sample_include = inc.data();
-    if (!bs.Init()) {
-      pl2gpu_host_free(blk);
-      return GpuFail("pl2gpu_host_alloc");
-    }
+    bs.Rewind();
     std::string err;
-    size_t base = 0;
-    for (;;) {
-      const int got = bs.Next(&err);
-      if (got < 0) {
-        logprintf("Error: %s\n", err.c_str());
-        pl2gpu_host_free(blk);
-        return kRetMalformedInput;
-      }
-      if (!got) break;
-      memcpy(static_cast<uint64_t*>(blk) + base * words, bs.buf, static_cast<uint64_t>(got) * words * 8);
-      base += static_cast<size_t>(got);
+    auto tp = std::chrono::steady_clock::now();
+    const int got = bs.Next(&err);
+    if (got != static_cast<int>(run.v1 - run.v0)) {
+      logprintf("Error: %s\n", got < 0 ? err.c_str() : "short read");
+      return kRetMalformedInput;
     }
-    const int rc = pl2_indep_pairwise_ex(ctx, blk, static_cast<uint64_t>(words) * 8, founder_ct, run.v1 - run.v0, V.chr_code.data() + run.v0, V.bp.data() + run.v0, c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0,
+    t_decode += g_clock.Since(tp);
+    tp = std::chrono::steady_clock::now();
+    const int rc = pl2_indep_pairwise_ex(ctx, bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, run.v1 - run.v0, V.chr_code.data() + run.v0, V.bp.data() + run.v0, c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0,
                                          ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data() + run.v0, preferred.empty() ? nullptr : preferred.data() + run.v0, 0, founder_sex.data(),
                                          c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data() + run.v0);
-    if (rc) {
-      pl2gpu_host_free(blk);
-      return GpuFail("pl2_indep_pairwise");
-    }
+    if (rc) return GpuFail("pl2_indep_pairwise");
+    t_device += g_clock.Since(tp);
   }
-  pl2gpu_host_free(blk);
+  if (g_clock.on) fprintf(stderr, "[timing]   ld: decode %.3f s, counts + pair decisions + greedy walk %.3f s over %zu chromosome run%s\n", t_decode, t_device, chr_runs.size(), chr_runs.size() == 1 ? "" : "s");
   // LdPruneWrite (plink2_ld.cc:2464-2528)
   const std::string in_name = c.out + ".prune.in", out_name = c.out + ".prune.out";
   OutFile fin, fout;
