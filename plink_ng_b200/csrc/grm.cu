@@ -10,6 +10,7 @@
 #include "grm_kernels.cuh"
 #include "grm_ts_kernel.cuh"
 #include "jacobi.cuh"
+#include "eig_krylov.cuh"
 #include "ld_kernels.cuh"  // geno_counts_kernel
 
 using namespace pl2;
@@ -408,18 +409,33 @@ int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, 
       set_error("pl2gpu_grm_eigen_topk: GRM contains missing values (a sample pair has no jointly observed variant)");
       break;
     }
-    if (mu > 0.0) {
-      add_diagonal_kernel<<<DivUpU32(n, 256), 256, 0, c->stream>>>(d_a, n, mu);
-      c->launches++;
-    }
+    // Small matrices: one-sided Jacobi on G + mu I (all eigenpairs, O(N^3) per sweep).  Beyond 4,096 samples - or with
+    // PL2_EIGEN=krylov - the leading pairs come from a restarted block Krylov iteration on G itself (eig_krylov.cuh):
+    // (2p + 1)(k + 8) N^2 MACs per restart instead of N^3 per sweep.  PL2_EIGEN=jacobi forces the dense form.
+    const char* eig_env = getenv("PL2_EIGEN");
+    const bool krylov = pc_ct + 8 <= n / 6 && ((eig_env && !strcmp(eig_env, "krylov")) || (!(eig_env && !strcmp(eig_env, "jacobi")) && n > 4096));
     std::vector<double> sigma(pc_ct);
     const char* err = nullptr;
-    uint32_t sweeps = 0;
-    if (JacobiSvd(c, d_a, n, n, n, pc_ct, sigma.data(), d_u, n, &sweeps, &err)) {
-      set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (%s)", err ? err : "?");
-      break;
+    if (krylov) {
+      uint32_t restarts = 0;
+      if (SymEigTopKKrylov(c, d_a, n, pc_ct, sigma.data(), d_u, &restarts, &err)) {
+        set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (%s)", err ? err : "?");
+        break;
+      }
+      if (getenv("PL2_TIMING")) fprintf(stderr, "[timing]   eigen: block Krylov, %u restarts\n", restarts);
+      mu = 0.0;
+    } else {
+      if (mu > 0.0) {
+        add_diagonal_kernel<<<DivUpU32(n, 256), 256, 0, c->stream>>>(d_a, n, mu);
+        c->launches++;
+      }
+      uint32_t sweeps = 0;
+      if (JacobiSvd(c, d_a, n, n, n, pc_ct, sigma.data(), d_u, n, &sweeps, &err)) {
+        set_error("pl2gpu_grm_eigen_topk: eigendecomposition failed (%s)", err ? err : "?");
+        break;
+      }
     }
-    if (cudaMemcpy(eigvecs_host, d_u, 8ull * pc_ct * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    if (cudaMemcpyAsync(eigvecs_host, d_u, 8ull * pc_ct * n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
       set_error("pl2gpu_grm_eigen_topk: %s", cudaGetErrorString(cudaGetLastError()));
       break;
     }

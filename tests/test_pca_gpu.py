@@ -49,6 +49,28 @@ def test_exact_pca_matches_numpy_eigh(gpu_ctx):
     assert np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-12)
 
 
+@pytest.mark.parametrize("n,m,k,force", [(1200, 6000, 8, True), (4500, 7000, 6, False)])
+def test_exact_pca_block_krylov_matches_numpy_eigh(gpu_ctx, monkeypatch, n, m, k, force):
+    """Exact --pca beyond Jacobi's reach: restarted block Krylov + Rayleigh-Ritz on the resident GRM (eig_krylov.cuh),
+    the default above 4,096 samples (forced through PL2_EIGEN at the small size).  Structure and noise-level
+    eigenvalues alike must agree with LAPACK's to 1e-8: this solver converges every wanted pair to a 1e-10 residual."""
+    if force:
+        monkeypatch.setenv("PL2_EIGEN", "krylov")
+    geno = _structured_geno(m, n, seed=n, pops=5, fst=0.08)
+    want, _ = orc.grm(geno)
+    w, v = np.linalg.eigh(want)
+    w, v = w[::-1][:k], v[:, ::-1][:, :k].T
+    with GrmJob(gpu_ctx, n) as job:
+        job.add_variants(pack_genotypes(geno))
+        vals, vecs = job.eigen_topk(k)
+    assert np.allclose(vals, w, rtol=1e-8)
+    assert np.allclose(_align(vecs[:4], v[:4]), v[:4], atol=1e-6 * np.abs(v[:4]).max())  # 4 structure PCs
+    assert np.allclose(np.linalg.norm(vecs, axis=1), 1.0, atol=1e-10)
+    # noise-level eigenvectors: compare the invariant subspace residual instead of ill-conditioned individual vectors
+    resid = want @ vecs.T - vecs.T * vals
+    assert np.abs(resid).max() < 1e-7 * vals[0]
+
+
 def test_exact_pca_cli_matches_reference_files(golden_dir, tmp_path):
     out = str(tmp_path / "p")
     env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", "0").split(",")[0])
