@@ -270,12 +270,15 @@ def score_file_entries(path: str, ids, ref_alleles, alt_alleles, header: bool = 
     return out, missing_id, missing_allele
 
 
-def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputation: bool = False):
+def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputation: bool = False, mode: str = ""):
     """ScoreReport's default report for diploid variants (2.0/plink2_matrix_calc.cc:6892-9270): per sample
     ALLELE_CT = 2 x nonmissing scored variants (:8581), DENOM (= 2 x scored variants, or ALLELE_CT with
     'no-mean-imputation', :8586-8588), NAMED_ALLELE_DOSAGE_SUM over nonmissing calls, score sum = sum of coefficient x
     named-allele dosage with a missing call replaced by 2 x the named allele's frequency (:6605-6607) unless
-    no-mean-imputation, and the average = sum x (1 / DENOM) (:8397)."""
+    no-mean-imputation, and the average = sum x (1 / DENOM) (:8397).  mode "center": dosage - 2 f; "variance-standardize":
+    (dosage - 2 f) / sqrt(2 f (1 - f)) (slope 0 when the variance is not above 2^-44, :8005-8033).  NOTE: under both
+    modes the reference still adds the UNCENTRED mean 2 f x slope for a missing call (missing_effect has no intercept,
+    :6756-6762) - reproduced here because the goldens say so."""
     n = geno.shape[1]
     ssum = np.zeros(n)
     dos = np.zeros(n, dtype=np.int64)
@@ -285,9 +288,14 @@ def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputa
         named = np.where(g == 3, 0, g if aidx == 1 else 2 - g).astype(np.int64)
         named = np.where(g == 3, 0, named)
         f_named = (1.0 - ref_freq[v]) if aidx == 1 else ref_freq[v]
-        d = named.astype(np.float64)
-        if not no_mean_imputation:
-            d = np.where(g == 3, 2.0 * f_named, d)
+        slope, icpt = 1.0, 0.0
+        if mode:
+            if mode == "variance-standardize":
+                var = 2.0 * f_named * (1.0 - f_named)
+                slope = 1.0 / np.sqrt(var) if var > SMALL_EPSILON else 0.0
+            icpt = (-2.0 * f_named) * slope
+        d = named.astype(np.float64) * slope + icpt
+        d = np.where(g == 3, 0.0 if no_mean_imputation else (2.0 * f_named) * slope, d)
         ssum += coef * d
         dos += named
         miss += g == 3

@@ -89,7 +89,7 @@ struct Cmd {
   // --score <file> [i] [j] [k] [header | header-read] [no-mean-imputation] [zs] [cols=]
   std::string score_file;
   uint32_t score_id_col = 1, score_allele_col = 2, score_coef_col = 3;
-  bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false;
+  bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false, score_center = false, score_varstd = false;
   bool sc_fid_maybe = true, sc_fid = false, sc_sid_maybe = true, sc_sid = false, sc_pheno1 = false, sc_phenos = true, sc_nallele = true, sc_denom = false, sc_dosagesum = true, sc_avgs = true, sc_sums = false;
   std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
   double king_cutoff_table_thresh = -1;
@@ -320,6 +320,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         if (m == "header") c->score_header = true;
         else if (m == "header-read") c->score_header_read = true;
         else if (m == "no-mean-imputation") c->score_no_meanimpute = true;
+        else if (m == "center") c->score_center = true;
+        else if (m == "variance-standardize") c->score_center = c->score_varstd = true;
         else if (m == "zs") c->score_zs = true;
         else if (m.compare(0, 5, "cols=") == 0) {
           // column-set descriptor: a plain list replaces the default, +x / -x entries edit it
@@ -355,7 +357,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
             else return Usage(("Invalid --score cols= entry '" + tok + "'.").c_str());
           }
         } else {
-          return Usage(("--score modifier '" + m + "' is not supported by plink2_b200 (supported: header, header-read, no-mean-imputation, zs, cols=).").c_str());
+          return Usage(("--score modifier '" + m + "' is not supported by plink2_b200 (supported: header, header-read, center, variance-standardize, no-mean-imputation, zs, cols=).").c_str());
         }
       }
       if (c->score_header && c->score_header_read) return Usage("--score 'header' and 'header-read' modifiers cannot be used together.");
@@ -2346,12 +2348,27 @@ int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     for (int k = 0; k < got; ++k) {
       const Entry& e = entries[base + k];
       const double f_named = e.aidx ? (1.0 - ref_freqs[base + k]) : ref_freqs[base + k];
-      // genotype code = ALT allele count; named-allele dosage of codes 0, 1, 2
+      // genotype code = ALT allele count; named-allele dosage of codes 0, 1, 2.  'center' / 'variance-standardize'
+      // (:8003-8033): dosage x slope + intercept with intercept = -2 f slope and slope = 1 / sqrt(2 f (1 - f)) (0 when
+      // the variance is not above 2^-44).  A missing call contributes 2 f slope WITHOUT the intercept in the reference
+      // (missing_effect, :6756-6762) - kept, since the outputs are compared with its files.
       const uint32_t d0 = e.aidx ? 0 : 2, d2 = e.aidx ? 2 : 0;
-      w4[4ull * k + 0] = e.coef * static_cast<double>(d0);
-      w4[4ull * k + 1] = e.coef;
-      w4[4ull * k + 2] = e.coef * static_cast<double>(d2);
-      w4[4ull * k + 3] = c.score_no_meanimpute ? 0.0 : e.coef * (2.0 * f_named);
+      double slope = 1.0, icpt = 0.0;
+      if (c.score_center) {
+        if (c.score_varstd) {
+          const double variance = 2.0 * f_named * (1.0 - f_named);
+          if (!(variance > 1.0 / 17592186044416.0)) {
+            slope = 0.0;  // the reference additionally insists that such a variant is monomorphic (:8013-8027); a weight of 0 scores it the same
+          } else {
+            slope = 1.0 / sqrt(variance);
+          }
+        }
+        icpt = (-2.0 * f_named) * slope;
+      }
+      w4[4ull * k + 0] = e.coef * (static_cast<double>(d0) * slope + icpt);
+      w4[4ull * k + 1] = e.coef * (slope + icpt);
+      w4[4ull * k + 2] = e.coef * (static_cast<double>(d2) * slope + icpt);
+      w4[4ull * k + 3] = c.score_no_meanimpute ? 0.0 : e.coef * ((2.0 * f_named) * slope);
       d4[k] = static_cast<uint8_t>(d0 | (1u << 2) | (d2 << 4));
     }
     if (pl2gpu_score_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, w4.data(), d4.data())) return GpuFail("pl2gpu_score_add_variants");

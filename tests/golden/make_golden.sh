@@ -69,6 +69,9 @@ python make_score_set.py a.bim a_score.txt
 $P --bfile a --score a_score.txt header --threads 2 --out $T/a_sc > /dev/null
 $P --bfile a --score a_score.txt header no-mean-imputation cols=+scoresums,+denom --threads 2 --out $T/a_sc2 > /dev/null
 cp $T/a_sc.sscore a_sc.sscore; cp $T/a_sc2.sscore a_sc2.sscore
+$P --bfile a --score a_score.txt header center cols=+scoresums --threads 2 --out $T/a_scc > /dev/null
+$P --bfile a --score a_score.txt header variance-standardize cols=+scoresums --threads 2 --out $T/a_scv > /dev/null
+cp $T/a_scc.sscore a_sc_center.sscore; cp $T/a_scv.sscore a_sc_varstd.sscore
 # --king-cutoff-table on the proportion table written above
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --threads 2 --out $T/a_kct > /dev/null
 cp $T/a_kct.king.cutoff.in.id a_kct.king.cutoff.in.id; cp $T/a_kct.king.cutoff.out.id a_kct.king.cutoff.out.id
