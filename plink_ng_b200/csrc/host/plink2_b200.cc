@@ -78,7 +78,7 @@ struct Cmd {
   bool make_king = false, make_king_table = false;
   enum Shape { kTri, kSq, kSq0 } king_shape = kTri, rel_shape = kTri;
   enum Enc { kText, kBin, kBin4 } king_enc = kText, rel_enc = kText;
-  bool king_counts = false, king_zs = false, king_table_zs = false, grm_zs = false, rel_zs = false, freq_zs = false;
+  bool king_counts = false, king_zs = false, king_table_zs = false, king_rel_check = false, grm_zs = false, rel_zs = false, freq_zs = false;
   bool col_fid_maybe = true, col_fid = false, col_id = true, col_sid_maybe = true, col_sid = false, col_nsnp = true, col_hethet = true, col_ibs0 = true, col_ibs1 = false, col_hamming = false, col_kinship = true;
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
@@ -237,7 +237,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else if (m.compare(0, 5, "cols=") == 0) {
           if (!ParseKingCols(m.substr(5), c)) return Usage(("Invalid --make-king-table cols= argument '" + m + "'.").c_str());
         } else if (m == "zs") c->king_table_zs = true;
-        else if (m == "rel-check") return Usage("--make-king-table rel-check is not supported by plink2_b200 (write the same-FID pairs to a file and use --king-table-subset).");
+        else if (m == "rel-check") c->king_rel_check = true;
         else return Usage(("Invalid --make-king-table argument '" + m + "'.").c_str());
       }
     } else if (flag == "--king-table-filter") {
@@ -867,6 +867,65 @@ void WriteKingTableRow(const Cmd& c, const std::string& id1, const std::string& 
 
 // `--make-king-table --king-table-subset <file> [thresh]` (CalcKingTableSubset, :3224; KingTableSubsetLoad,
 // :2774): KING-robust for the pairs listed in a .kin0-style file, in file order, ID1 = first listed sample.
+// PLINK 2's natural sort order (rules stated above strcmp_natural_scan_forward, 2.0/include/plink2_string.cc:375-392):
+// letters compare as if capitalised; a run of digits that starts with a NONZERO digit at the same position in both
+// strings compares by magnitude (zeros in front of it are ordinary characters, so "a01" < "a1" and "00" < "000");
+// strings that differ only in capitalisation are ordered by ASCII at their first such difference.
+int NaturalCompare(const std::string& a, const std::string& b) {
+  auto up = [](unsigned char ch) { return (ch >= 'a' && ch <= 'z') ? static_cast<unsigned char>(ch - 32) : ch; };
+  auto nz = [](unsigned char ch) { return ch >= '1' && ch <= '9'; };
+  auto dg = [](unsigned char ch) { return ch >= '0' && ch <= '9'; };
+  size_t i = 0, j = 0;
+  int tie = 0;  // decided by the first capitalisation-only difference
+  for (;;) {
+    const unsigned char ca = i < a.size() ? static_cast<unsigned char>(a[i]) : 0, cb = j < b.size() ? static_cast<unsigned char>(b[j]) : 0;
+    if (nz(ca) && nz(cb)) {
+      size_t ea = i, eb = j;
+      while (ea < a.size() && dg(static_cast<unsigned char>(a[ea]))) ++ea;
+      while (eb < b.size() && dg(static_cast<unsigned char>(b[eb]))) ++eb;
+      if (ea - i != eb - j) return (ea - i < eb - j) ? -1 : 1;
+      const int cmp = a.compare(i, ea - i, b, j, eb - j);
+      if (cmp) return cmp < 0 ? -1 : 1;
+      i = ea;
+      j = eb;
+      continue;
+    }
+    if (!ca && !cb) return tie;
+    if (ca != cb) {
+      const unsigned char ua = up(ca), ub = up(cb);
+      if (ua != ub) return ua < ub ? -1 : 1;
+      if (!tie) tie = ca < cb ? -1 : 1;
+    }
+    ++i;
+    ++j;
+  }
+}
+
+// "--make-king-table rel-check" (GetRelCheckOrKTRequirePairs, 2.0/plink2_matrix_calc.cc:2975-3043): the samples in
+// natural order of FID<tab>IID[<tab>SID]; inside every block of equal FID each sample is paired with all earlier ones,
+// the later sample listed first.
+void RelCheckPairs(const SampleInfo& S, std::vector<uint32_t>* pairs) {
+  const uint32_t n = S.size();
+  std::vector<std::string> key(n);
+  for (uint32_t k = 0; k < n; ++k) {
+    key[k] = S.fid[k] + "\t" + S.iid[k];
+    if (S.sid_present) key[k] += "\t" + S.sid[k];
+  }
+  std::vector<uint32_t> ord(n);
+  for (uint32_t k = 0; k < n; ++k) ord[k] = k;
+  std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return NaturalCompare(key[x], key[y]) < 0; });
+  for (uint32_t b0 = 0; b0 < n;) {
+    uint32_t b1 = b0 + 1;
+    while (b1 < n && S.fid[ord[b1]] == S.fid[ord[b0]]) ++b1;
+    for (uint32_t i1 = b0 + 1; i1 < b1; ++i1)
+      for (uint32_t i2 = b0; i2 < i1; ++i2) {
+        pairs->push_back(ord[i1]);
+        pairs->push_back(ord[i2]);
+      }
+    b0 = b1;
+  }
+}
+
 int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
@@ -889,6 +948,10 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("Error: No variants remaining for KING-robust calculation.\n");
     return kRetDegenerateData;
   }
+  std::vector<uint32_t> pairs;
+  if (c.king_table_subset.empty()) {
+    RelCheckPairs(S, &pairs);  // rel-check without a subset file
+  } else {
   // ---- header (:3391-3452): [#FID1|FID] (ID1|IID1) [SID1] [FID2] (ID2|IID2) [SID2] ... [KINSHIP|Kinship]
   std::vector<std::string> lines;
   std::string rerr;
@@ -958,7 +1021,6 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       return kRetInconsistentInput;
     }
   }
-  std::vector<uint32_t> pairs;
   for (size_t li = 1; li < lines.size(); ++li) {
     const std::vector<std::string> f = SplitWs(lines[li]);
     if (f.empty()) continue;
@@ -986,15 +1048,17 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       if (!ParseDouble(f[kinship_col].c_str(), &kv)) continue;  // e.g. "nan": not a number -> line skipped
       if (kv < thresh) continue;
     }
+    if (c.king_rel_check && S.fid[i1->second] != S.fid[i2->second]) continue;  // rel-check: same-FID pairs only
     pairs.push_back(i1->second);
     pairs.push_back(i2->second);
   }
+  }  // subset file
   const uint64_t pair_ct = pairs.size() / 2;
   if (!pair_ct) {
-    logprintf("Error: No valid pairs in --king-table-subset file.\n");
+    logprintf(c.king_table_subset.empty() ? "Error: No sample pairs with the same FID for --make-king-table rel-check.\n" : "Error: No valid pairs in --king-table-subset file.\n");
     return kRetInconsistentInput;
   }
-  logprintf("--king-table-subset: %llu pair%s loaded.\n", static_cast<unsigned long long>(pair_ct), pair_ct == 1 ? "" : "s");
+  logprintf("%s: %llu pair%s loaded.\n", c.king_table_subset.empty() ? "--make-king-table rel-check" : "--king-table-subset", static_cast<unsigned long long>(pair_ct), pair_ct == 1 ? "" : "s");
   const IdFmt idf = KingIdFmt(c, S);
   const std::string tab_name = c.out + (c.king_table_zs ? ".kin0.zst" : ".kin0");
   OutFile ftab;
@@ -2665,6 +2729,18 @@ int DebugHooks(int argc, char** argv) {
     fclose(in);
     return out.Close() ? 0 : kRetWriteFail;
   }
+  if (argc == 4 && !strcmp(argv[1], "--debug-natural-sort")) {  // <in: one key per line> <out: the keys in natural order>
+    std::vector<std::string> keys;
+    std::string err;
+    OutFile out;
+    if (!ReadLines(argv[2], &keys, &err) || !out.Open(argv[3])) return kRetOpenFail;
+    std::stable_sort(keys.begin(), keys.end(), [](const std::string& a, const std::string& b) { return NaturalCompare(a, b) < 0; });
+    for (const std::string& k : keys) {
+      out.Write(k.data(), k.size());
+      out.Puts("\n");
+    }
+    return out.Close() ? 0 : kRetWriteFail;
+  }
   if (argc == 4 && !strcmp(argv[1], "--debug-zst")) {  // <in> <out.zst>: the 'zs' writer on its own (mixed small and large writes)
     FILE* in = fopen(argv[2], "rb");
     OutFile out;
@@ -2796,7 +2872,13 @@ int main(int argc, char** argv) {
     if (rc) return rc;
   }
   std::vector<uint8_t> cutoff_removed;
-  if (!c.king_table_subset.empty()) {
+  bool rel_check_pairs = false;
+  if (c.king_rel_check && c.king_table_subset.empty()) {
+    // with a single FID in the dataset the modifier has no effect (the reference warns and computes the full table)
+    for (uint32_t k = 1; k < ds.samples.size() && !rel_check_pairs; ++k) rel_check_pairs = ds.samples.fid[k] != ds.samples.fid[0];
+    if (!rel_check_pairs) logprintf("Warning: --make-king-table 'rel-check' modifier has no effect since only one FID is present.\n");
+  }
+  if (!c.king_table_subset.empty() || rel_check_pairs) {
     if (!c.make_king_table || c.make_king || c.king_cutoff >= 0) {
       logprintf("Error: --king-table-subset must be used with --make-king-table (and without --make-king / --king-cutoff).\n");
       return kRetInvalidCmdline;

@@ -89,6 +89,12 @@ $P --bfile x --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/x_o1
 cp $T/x_o2.prune.in x_o2.prune.in; cp $T/x_o1.prune.in x_o1.prune.in
 $P --bfile x --indep-pairwise 30kb 0.3 --threads 2 --out $T/x_kb > /dev/null
 cp $T/x_kb.prune.in x_kb.prune.in
+# rel-check: sets R (60 samples, 2 FIDs, IIDs chosen to exercise the natural sort: leading zeros, mixed case, digit runs)
+# and S (300 random IDs over 5 FIDs) are kept as written by the script that made them (tests/golden/README in DESIGN 7)
+$P --bfile r --make-king-table rel-check counts --threads 2 --out $T/r_rc > /dev/null
+cp $T/r_rc.kin0 r_relcheck.kin0
+$P --bfile s --make-king-table rel-check --threads 2 --out $T/s_rc > /dev/null
+gzip -9 -n -c $T/s_rc.kin0 > s_relcheck.kin0.gz
 if [ -x $PL ]; then
   $PL --bfile a --pca 4 --threads 2 --out $T/a_pca > /dev/null
   cp $T/a_pca.eigenval a_pca.eigenval; cp $T/a_pca.eigenvec a_pca.eigenvec

@@ -236,6 +236,17 @@ def test_read_freq_grm_and_prune_list(golden_dir, tmp_path):
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_rfld.prune.in"), "rb").read()
 
 
+@pytest.mark.parametrize("prefix,flags,golden", [("r", ("rel-check", "counts"), "r_relcheck.kin0"), ("s", ("rel-check",), "s_relcheck.kin0.gz")])
+def test_rel_check_table_byte_identical(golden_dir, tmp_path, prefix, flags, golden):
+    """--make-king-table rel-check: same-FID pairs in PLINK 2's natural sort order of the IDs (leading zeros, mixed case,
+    digit runs; 300 random IDs over 5 FIDs in set S), counts through the pair-list kernel."""
+    out = str(tmp_path / "rc")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, prefix), "--make-king-table", *flags, "--out", out], capture_output=True, text=True, env=ENV)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want = gz(golden_dir, golden) if golden.endswith(".gz") else open(os.path.join(golden_dir, golden), "rb").read()
+    assert open(out + ".kin0", "rb").read() == want
+
+
 def test_toy_fixture_configs0(golden_dir, tmp_path):
     out = str(tmp_path / "toy")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "toy"), "--make-king", "square", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--out", out], capture_output=True, text=True, env=ENV)

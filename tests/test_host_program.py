@@ -231,3 +231,25 @@ def test_king_cutoff_table_matches_reference_lists(tmp_path):
     assert "661 constraints loaded" in r.stdout
     for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):
         assert open(out + ext, "rb").read() == open(os.path.join(gd, "a_kct" + ext), "rb").read()
+
+
+def test_natural_sort_matches_reference_order(tmp_path):
+    """The ID order behind `--make-king-table rel-check`: the reference's own table on set S (300 random IDs of the
+    alphabet aAbBzZ0019_.-x over FIDs F1 / F2 / f1 / F10 / F02) lists every FID block in natural order; the host
+    program's comparator must put the same keys in the same order."""
+    import gzip
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    rows = [ln.split("\t") for ln in gzip.open(os.path.join(gd, "s_relcheck.kin0.gz"), "rt").read().split("\n")[1:] if ln]
+    order, seen = [], set()
+    for r in rows:
+        for key in ((r[2], r[3]), (r[0], r[1])):
+            if key not in seen:
+                seen.add(key)
+                order.append(key[0] + "\t" + key[1])
+    fam = [ln.split("\t")[:2] for ln in open(os.path.join(gd, "s.fam"))]
+    keys = [f + "\t" + i for f, i in fam if f + "\t" + i in set(order)]
+    assert len(keys) == len(order) > 250 and keys != order
+    (tmp_path / "in.txt").write_text("\n".join(keys) + "\n")
+    subprocess.run([BIN, "--debug-natural-sort", str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], check=True)
+    assert (tmp_path / "out.txt").read_text().split("\n")[:-1] == order
