@@ -902,8 +902,8 @@ int NaturalCompare(const std::string& a, const std::string& b) {
 }
 
 // "--make-king-table rel-check" (GetRelCheckOrKTRequirePairs, 2.0/plink2_matrix_calc.cc:2975-3043): the samples in
-// natural order of FID<tab>IID[<tab>SID]; inside every block of equal FID each sample is paired with all earlier ones,
-// the later sample listed first.
+// natural order of FID<tab>IID[<tab>SID]; inside every block of equal FID (equal up to capitalisation, see below) each
+// sample is paired with all earlier ones, the later sample listed first.
 void RelCheckPairs(const SampleInfo& S, std::vector<uint32_t>* pairs) {
   const uint32_t n = S.size();
   std::vector<std::string> key(n);
@@ -915,8 +915,11 @@ void RelCheckPairs(const SampleInfo& S, std::vector<uint32_t>* pairs) {
   for (uint32_t k = 0; k < n; ++k) ord[k] = k;
   std::stable_sort(ord.begin(), ord.end(), [&](uint32_t x, uint32_t y) { return NaturalCompare(key[x], key[y]) < 0; });
   for (uint32_t b0 = 0; b0 < n;) {
+    // block end as the reference finds it (:3030-3042): the first sorted key not below "<FID of the block's first
+    // entry> " in natural order - which also takes in FIDs that differ from it only in capitalisation
+    const std::string bound = S.fid[ord[b0]] + " ";
     uint32_t b1 = b0 + 1;
-    while (b1 < n && S.fid[ord[b1]] == S.fid[ord[b0]]) ++b1;
+    while (b1 < n && NaturalCompare(key[ord[b1]], bound) < 0) ++b1;
     for (uint32_t i1 = b0 + 1; i1 < b1; ++i1)
       for (uint32_t i2 = b0; i2 < i1; ++i2) {
         pairs->push_back(ord[i1]);
@@ -2727,6 +2730,19 @@ int DebugHooks(int argc, char** argv) {
       out.Advance(w);
     }
     fclose(in);
+    return out.Close() ? 0 : kRetWriteFail;
+  }
+  if (argc == 4 && !strcmp(argv[1], "--debug-rel-check-pairs")) {  // <.fam/.psam> <out: FID1 IID1 FID2 IID2 per pair, table order>
+    SampleInfo S;
+    std::string err;
+    OutFile out;
+    if (!LoadSamples(argv[2], &S, &err) || !out.Open(argv[3])) return kRetOpenFail;
+    std::vector<uint32_t> pairs;
+    RelCheckPairs(S, &pairs);
+    for (size_t k = 0; k < pairs.size(); k += 2) {
+      const std::string ln = S.fid[pairs[k]] + "\t" + S.iid[pairs[k]] + "\t" + S.fid[pairs[k + 1]] + "\t" + S.iid[pairs[k + 1]] + "\n";
+      out.Write(ln.data(), ln.size());
+    }
     return out.Close() ? 0 : kRetWriteFail;
   }
   if (argc == 4 && !strcmp(argv[1], "--debug-natural-sort")) {  // <in: one key per line> <out: the keys in natural order>

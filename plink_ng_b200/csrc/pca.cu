@@ -37,7 +37,8 @@ struct Pl2PcaJob {
   uint8_t* d_raw_i = nullptr;   // sample-major copy [row tile][k-step][128][8 B] of the whole matrix (geno_tile.cuh)
   double* d_slope = nullptr;    // per variant: inv_stdev (0 for skipped variants)
   double* d_icpt = nullptr;     // per variant: -2 alt_freq inv_stdev
-  std::vector<double> h_slope, h_icpt;
+  double* d_twof = nullptr;     // per variant: 2 alt_freq (the mean-imputation value of --variant-score)
+  std::vector<double> h_slope, h_icpt, h_twof;
   CUtensorMap tmap_raw;         // box {16 B, 128 variants} over d_raw
   uint32_t retiled_to = 0;      // variants [0, retiled_to) are in d_raw_i (multiple of 64)
 };
@@ -76,7 +77,7 @@ static int PcaBeginImpl(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t variant_ct_
   if (cudaMalloc(&job->d_raw, static_cast<uint64_t>(job->variant_cap) * job->pitch) != cudaSuccess || cudaMalloc(&job->d_ztab, static_cast<uint64_t>(job->variant_cap) * 32) != cudaSuccess ||
       cudaMalloc(&job->d_counts, 16ull * 65536) != cudaSuccess ||
       (job->tensor && (cudaMalloc(&job->d_raw_i, static_cast<uint64_t>(job->sample_ct_padded) * (job->variant_cap / 4)) != cudaSuccess || cudaMalloc(&job->d_slope, 8ull * job->variant_cap) != cudaSuccess ||
-                       cudaMalloc(&job->d_icpt, 8ull * job->variant_cap) != cudaSuccess))) {
+                       cudaMalloc(&job->d_icpt, 8ull * job->variant_cap) != cudaSuccess || cudaMalloc(&job->d_twof, 8ull * job->variant_cap) != cudaSuccess))) {
     cudaGetLastError();
     set_error("pl2gpu_pca_begin: insufficient device memory to keep %u x %u genotypes resident", variant_ct_total, sample_ct);
     pl2gpu_pca_end(job);
@@ -120,6 +121,7 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
     job->h_ztab.assign(4ull * cur, 0.0);
     job->h_slope.assign(cur, 0.0);
     job->h_icpt.assign(cur, 0.0);
+    job->h_twof.assign(cur, 0.0);
     for (uint32_t v = 0; v < cur; ++v) {
       const uint32_t n0 = job->h_counts[4ull * v], n1 = job->h_counts[4ull * v + 1], n2 = job->h_counts[4ull * v + 2];
       double ref_freq;
@@ -130,6 +132,7 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
         ref_freq = tot ? (static_cast<double>(2ull * n0 + n1) * (1.0 / static_cast<double>(tot))) : 0.5;
       }
       const double alt_freq = 1.0 - ref_freq;
+      job->h_twof[v] = 2.0 * alt_freq;
       const double variance = 2 * ref_freq * alt_freq;
       if (!(variance > kSmallEpsilon)) {
         bool bad = n1 != 0;
@@ -155,6 +158,7 @@ int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t varia
     if (job->tensor) {
       PL2_CUDA_OK(cudaMemcpyAsync(job->d_slope + job->variant_ct, job->h_slope.data(), 8ull * cur, cudaMemcpyHostToDevice, c->stream));
       PL2_CUDA_OK(cudaMemcpyAsync(job->d_icpt + job->variant_ct, job->h_icpt.data(), 8ull * cur, cudaMemcpyHostToDevice, c->stream));
+      PL2_CUDA_OK(cudaMemcpyAsync(job->d_twof + job->variant_ct, job->h_twof.data(), 8ull * cur, cudaMemcpyHostToDevice, c->stream));
     }
     PL2_CUDA_OK(cudaStreamSynchronize(c->stream));
     job->variant_ct += cur;
@@ -498,6 +502,85 @@ int pl2gpu_pca_run_sharded(Pl2PcaJob* job, const double* g1_host, uint64_t total
   return PcaRunImpl(job, g1_host, total_variant_ct, true, eigvals_host, eigvecs_host);
 }
 
+// `--variant-score` (VscoreReport, 2.0/plink2_matrix_calc.cc:9274): per variant the dot product of sample weights with
+// the ALT dosages, a missing call replaced by 2 x ALT frequency.  One H = Y W pass of the approx-PCA tile path does it:
+// with Y the standardised matrix (y = (g - 2 f) / sd for a called genotype, 0 for a missing one)
+//   sum_s w_s dosage_vs  =  (Y W)_v sd_v + 2 f_v sum_s w_s ,
+// so the int8 tensor kernel runs unchanged and a small epilogue un-standardises (variants without variance: 2 f W).
+static __global__ void __launch_bounds__(256) vscore_finish_kernel(const double* __restrict__ h, uint64_t h_ld, uint32_t variant_ct, uint32_t cols, const double* __restrict__ slope, const double* __restrict__ twof, const double* __restrict__ wtot, double* __restrict__ out) {
+  const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<uint64_t>(variant_ct) * cols) return;
+  const uint32_t v = static_cast<uint32_t>(idx / cols), c = static_cast<uint32_t>(idx % cols);
+  const double sl = slope[v];
+  out[idx] = (sl != 0.0 ? h[static_cast<uint64_t>(c) * h_ld + v] / sl : 0.0) + twof[v] * wtot[c];
+}
+
+int pl2gpu_pca_vscore(Pl2PcaJob* job, const double* weights_host, uint32_t cols, double* out_host) {
+  if (!job || !weights_host || !cols || !out_host || !job->tensor || !job->variant_ct) {
+    set_error("pl2gpu_pca_vscore: bad arguments (needs a non-empty tensor-path job)");
+    return 1;
+  }
+  Ctx* c = &job->ctx->c;
+  PL2_CUDA_OK(cudaSetDevice(c->device));
+  const uint32_t n = job->sample_ct, npad = job->sample_ct_padded, m = job->variant_ct;
+  uint8_t* d_gdig = nullptr;
+  double *d_scale = nullptr, *d_inv_scale = nullptr, *d_w = nullptr, *d_h = nullptr, *d_wtot = nullptr, *d_out = nullptr;
+  unsigned long long* d_colmax = nullptr;
+  int rc = 1;
+  do {
+    if (cudaMalloc(&d_gdig, static_cast<uint64_t>(npad) * kPcaNMax) != cudaSuccess || cudaMalloc(&d_scale, 8 * kPcaCgMax) != cudaSuccess || cudaMalloc(&d_inv_scale, 8 * kPcaCgMax) != cudaSuccess ||
+        cudaMalloc(&d_colmax, 8 * kPcaCgMax) != cudaSuccess || cudaMalloc(&d_w, static_cast<uint64_t>(npad) * cols * 8) != cudaSuccess || cudaMalloc(&d_h, static_cast<uint64_t>(m) * cols * 8) != cudaSuccess ||
+        cudaMalloc(&d_wtot, 8ull * cols) != cudaSuccess || cudaMalloc(&d_out, static_cast<uint64_t>(m) * cols * 8) != cudaSuccess) {
+      cudaGetLastError();
+      set_error("pl2gpu_pca_vscore: insufficient device memory for %u score columns", cols);
+      break;
+    }
+    std::vector<double> wtot(cols, 0.0);
+    for (uint32_t s = 0; s < n; ++s)
+      for (uint32_t cc = 0; cc < cols; ++cc) wtot[cc] += weights_host[static_cast<uint64_t>(s) * cols + cc];
+    if (cudaMemsetAsync(d_w, 0, static_cast<uint64_t>(npad) * cols * 8, c->stream) != cudaSuccess || cudaMemcpyAsync(d_w, weights_host, static_cast<uint64_t>(n) * cols * 8, cudaMemcpyHostToDevice, c->stream) != cudaSuccess ||
+        cudaMemcpyAsync(d_wtot, wtot.data(), 8ull * cols, cudaMemcpyHostToDevice, c->stream) != cudaSuccess)
+      break;
+    // rows [variant_ct, variant_cap) must decode to "missing"
+    if (job->variant_cap > m && LaunchPadGenotypes(c, job->d_raw + static_cast<uint64_t>(m) * job->pitch, job->pitch, job->sample_ct, 0, job->variant_cap - m)) break;
+    bool ok = true;
+    for (uint32_t cc = 0; ok && cc < cols; cc += kPcaCgMax) {
+      const uint32_t valid = std::min(kPcaCgMax, cols - cc), cg = RoundUpU32(valid, 4);
+      ok = cudaMemsetAsync(d_colmax, 0, 8 * kPcaCgMax, c->stream) == cudaSuccess;
+      pca_colmax_kernel<<<dim3(valid, std::min<uint32_t>(64, DivUpU32(npad, 256))), 256, 0, c->stream>>>(d_w + cc, cols, 1, npad, nullptr, nullptr, d_colmax);
+      pca_scales_kernel<<<1, 64, 0, c->stream>>>(d_colmax, kPcaCgMax, d_scale, d_inv_scale);
+      c->launches += 2;
+      for (int pass = 0; pass < 2; ++pass) {
+        pca_digits_kernel<<<npad / 64, 256, 0, c->stream>>>(d_w + cc, cols, 1, npad, cg, valid, nullptr, nullptr, d_scale, d_gdig, nullptr, pass);
+        pca_xa_ts_kernel<<<job->variant_cap / 128, kPxaThreads, kPxaSmemBytes, c->stream>>>(job->tmap_raw, npad, m, d_gdig, cg, valid, job->d_slope, job->d_icpt, d_inv_scale, d_h + static_cast<uint64_t>(cc) * m, m,
+                                                                                          pass ? 1.0 / kPcaPass1Scale : 1.0, pass);
+        c->launches += 2;
+      }
+      ok = ok && cudaGetLastError() == cudaSuccess;
+    }
+    if (!ok) {
+      set_error("pl2gpu_pca_vscore: kernel launch failed");
+      break;
+    }
+    vscore_finish_kernel<<<static_cast<uint32_t>(DivUpU64(static_cast<uint64_t>(m) * cols, 256)), 256, 0, c->stream>>>(d_h, m, m, cols, job->d_slope, job->d_twof, d_wtot, d_out);
+    c->launches++;
+    if (cudaMemcpyAsync(out_host, d_out, static_cast<uint64_t>(m) * cols * 8, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess || cudaStreamSynchronize(c->stream) != cudaSuccess) {
+      set_error("pl2gpu_pca_vscore: %s", cudaGetErrorString(cudaGetLastError()));
+      break;
+    }
+    rc = 0;
+  } while (0);
+  cudaFree(d_gdig);
+  cudaFree(d_scale);
+  cudaFree(d_inv_scale);
+  cudaFree(d_colmax);
+  cudaFree(d_w);
+  cudaFree(d_h);
+  cudaFree(d_wtot);
+  cudaFree(d_out);
+  return rc;
+}
+
 int pl2gpu_pca_end(Pl2PcaJob* job) {
   if (!job) return 0;
   if (job->ctx) {
@@ -508,6 +591,7 @@ int pl2gpu_pca_end(Pl2PcaJob* job) {
   cudaFree(job->d_raw_i);
   cudaFree(job->d_slope);
   cudaFree(job->d_icpt);
+  cudaFree(job->d_twof);
   cudaFree(job->d_ztab);
   cudaFree(job->d_counts);
   cudaGetLastError();

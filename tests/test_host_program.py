@@ -253,3 +253,17 @@ def test_natural_sort_matches_reference_order(tmp_path):
     (tmp_path / "in.txt").write_text("\n".join(keys) + "\n")
     subprocess.run([BIN, "--debug-natural-sort", str(tmp_path / "in.txt"), str(tmp_path / "out.txt")], check=True)
     assert (tmp_path / "out.txt").read_text().split("\n")[:-1] == order
+
+
+def test_rel_check_pair_list_matches_reference_table(tmp_path):
+    """The pair list behind `--make-king-table rel-check` (natural sort + the reference's FID-block rule, which also joins
+    FIDs that differ only in capitalisation): ID columns of the reference's own tables, in order, for both fixtures."""
+    import gzip
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    for prefix, table in (("r", "r_relcheck.kin0"), ("s", "s_relcheck.kin0.gz")):
+        path = os.path.join(gd, table)
+        text = gzip.open(path, "rt").read() if table.endswith(".gz") else open(path).read()
+        want = ["\t".join(ln.split("\t")[:4]) for ln in text.split("\n")[1:] if ln]
+        subprocess.run([BIN, "--debug-rel-check-pairs", os.path.join(gd, prefix + ".fam"), str(tmp_path / "p.txt")], check=True)
+        assert (tmp_path / "p.txt").read_text().split("\n")[:-1] == want, prefix
