@@ -198,6 +198,12 @@ int pl2gpu_pca_run(Pl2PcaJob* job, const double* g1_host, double* eigvals_host, 
  * the same eigenvalues / eigenvectors. */
 int pl2gpu_pca_begin_shard(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t shard_variant_ct, uint32_t pc_ct, Pl2PcaJob** job_ptr);
 int pl2gpu_pca_run_sharded(Pl2PcaJob* job, const double* g1_host, uint64_t total_variant_ct, double* eigvals_host, double* eigvecs_host);
+/* `--variant-score` (VscoreReport, 2.0/plink2_matrix_calc.cc:9274) on the resident matrix of a Pl2PcaJob (begin +
+ * add_variants as above; pc_ct is irrelevant): out_host[variant][cols] = sum over samples of weights_host[sample][cols]
+ * x ALT dosage, a missing call replaced by 2 x the variant's ALT frequency (the ref_freqs given to add_variants, else
+ * the block's own).  Samples that are not scored get weight 0.  One H = Y W pass of the int8 tensor tile path plus an
+ * un-standardising epilogue; any number of score columns (48 per launch). */
+int pl2gpu_pca_vscore(Pl2PcaJob* job, const double* weights_host, uint32_t cols, double* out_host);
 int pl2gpu_pca_end(Pl2PcaJob* job);
 
 /* ---- per-variant genotype counts {hom-REF, het, hom-ALT, missing}: the hard-call part of the

@@ -305,6 +305,14 @@ def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputa
     return nallele, denom, dos, ssum, ssum * (1.0 / denom)
 
 
+def variant_scores(geno: np.ndarray, weights: np.ndarray, ref_freq: np.ndarray) -> np.ndarray:
+    """VscoreReport (2.0/plink2_matrix_calc.cc:9274): per variant the dot product of the sample weights
+    [samples, cols] with the ALT dosages, a missing call replaced by 2 x the ALT frequency (the dataset's allele
+    frequencies, not the scored subset's).  Samples outside the score file carry weight 0."""
+    d = np.where(geno == 3, (2.0 * (1.0 - ref_freq))[:, None], geno.astype(np.float64))
+    return d @ weights
+
+
 # --------------------------------------------------------------------------------------------- GRM
 def centered_varmaj(geno: np.ndarray, ref_freq: np.ndarray, variance_standardize: bool = True) -> np.ndarray:
     """ExpandCenteredVarmaj + PopulateRescaledDosage (2.0/plink2_matrix_calc.cc:3839-3886,

@@ -68,6 +68,7 @@ SIGNATURES = {
     "pl2gpu_pca_begin": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]),
     "pl2gpu_pca_add_variants": (C.c_int, [vp, vp, C.c_uint64, C.c_uint32, C.c_int, vp]),
     "pl2gpu_pca_run": (C.c_int, [vp, vp, vp, vp]),
+    "pl2gpu_pca_vscore": (C.c_int, [vp, vp, C.c_uint32, vp]),
     "pl2gpu_pca_begin_shard": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint32, vp]),
     "pl2gpu_pca_run_sharded": (C.c_int, [vp, vp, C.c_uint64, vp, vp]),
     "pl2gpu_pca_end": (C.c_int, [vp]),

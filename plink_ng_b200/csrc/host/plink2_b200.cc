@@ -91,6 +91,8 @@ struct Cmd {
   uint32_t score_id_col = 1, score_allele_col = 2, score_coef_col = 3;
   bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false, score_center = false, score_varstd = false;
   bool sc_fid_maybe = true, sc_fid = false, sc_sid_maybe = true, sc_sid = false, sc_pheno1 = false, sc_phenos = true, sc_nallele = true, sc_denom = false, sc_dosagesum = true, sc_avgs = true, sc_sums = false;
+  std::string vscore_file;                // --variant-score <file> ['zs'] ['cols=' chrom,pos,ref,alt,maybeprovref,provref,altfreq]
+  bool vscore_zs = false, vs_chrom = true, vs_pos = true, vs_ref = true, vs_alt = true, vs_maybeprovref = true, vs_provref = false, vs_altfreq = false;
   std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
   double king_cutoff_table_thresh = -1;
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
@@ -361,6 +363,44 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         }
       }
       if (c->score_header && c->score_header_read) return Usage("--score 'header' and 'header-read' modifiers cannot be used together.");
+    } else if (flag == "--variant-score" || flag == "--vscore") {
+      if (nparam < 1) return Usage("--variant-score requires a filename.");
+      c->vscore_file = prm[0];
+      for (int k = 1; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "zs") c->vscore_zs = true;
+        else if (m.compare(0, 5, "cols=") == 0) {
+          const std::string spec = m.substr(5);
+          const bool edit = !spec.empty() && (spec[0] == '+' || spec[0] == '-');
+          if (!edit) c->vs_chrom = c->vs_pos = c->vs_ref = c->vs_alt = c->vs_maybeprovref = false;
+          size_t pos = 0;
+          while (pos <= spec.size()) {
+            size_t e = spec.find(',', pos);
+            if (e == std::string::npos) e = spec.size();
+            std::string tok = spec.substr(pos, e - pos);
+            pos = e + 1;
+            if (tok.empty()) continue;
+            bool on = true;
+            if (tok[0] == '+' || tok[0] == '-') {
+              if (!edit) return Usage("Invalid --variant-score cols= argument (mixing +/- entries with a plain list).");
+              on = tok[0] == '+';
+              tok = tok.substr(1);
+            } else if (edit) {
+              return Usage("Invalid --variant-score cols= argument (mixing +/- entries with a plain list).");
+            }
+            if (tok == "chrom") c->vs_chrom = on;
+            else if (tok == "pos") c->vs_pos = on;
+            else if (tok == "ref") c->vs_ref = on;
+            else if (tok == "alt" || tok == "alt1") c->vs_alt = on;
+            else if (tok == "maybeprovref") c->vs_maybeprovref = on;
+            else if (tok == "provref") c->vs_provref = on;
+            else if (tok == "altfreq") c->vs_altfreq = on;
+            else return Usage(("--variant-score cols= entry '" + tok + "' is not supported by plink2_b200 (supported: chrom, pos, ref, alt, maybeprovref, provref, altfreq).").c_str());
+          }
+        } else {
+          return Usage(("--variant-score modifier '" + m + "' is not supported by plink2_b200 (supported: zs, cols=).").c_str());
+        }
+      }
     } else if (flag == "--king-cutoff-table") {
       // plink2.cc:7665-7700
       if (!need(2, 2)) return Usage("--king-cutoff-table requires a filename and a kinship threshold.");
@@ -453,7 +493,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->score_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -2503,6 +2543,194 @@ int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   return 0;
 }
 
+// `--variant-score` (VscoreReport, 2.0/plink2_matrix_calc.cc:9274-10100): sample weights from a file ([#FID] IID [SID]
+// + named weight columns, or headerless FID IID + VSCORE1..), per variant the weighted sum of ALT dosages with a missing
+// call replaced by 2 x ALT frequency.  The sums are one pass of the approx-PCA tensor tile path (pl2gpu_pca_vscore).
+int RunVscore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  std::vector<std::string> lines;
+  std::string err;
+  if (!ReadLines(c.vscore_file, &lines, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  size_t li = 0;
+  while (li < lines.size() && lines[li].empty()) ++li;
+  if (li == lines.size()) {
+    logprintf("Error: Empty --variant-score file.\n");
+    return kRetMalformedInput;
+  }
+  bool fid_col = true, sid_col = false;
+  std::vector<std::string> names;
+  size_t id_tokens = 2;
+  if (lines[li][0] == '#') {
+    const std::vector<std::string> h = SplitWs(lines[li].substr(1));
+    size_t t = 0;
+    fid_col = !h.empty() && h[0] == "FID";
+    if (fid_col) ++t;
+    if (t >= h.size() || h[t] != "IID") {
+      logprintf("Error: Invalid header line in --variant-score file (#FID or #IID expected first).\n");
+      return kRetMalformedInput;
+    }
+    ++t;
+    if (t < h.size() && h[t] == "SID") {
+      sid_col = true;
+      ++t;
+    }
+    id_tokens = t;
+    names.assign(h.begin() + t, h.end());
+    ++li;
+  } else {
+    const size_t tok_ct = SplitWs(lines[li]).size();
+    for (size_t k = 2; k < tok_ct; ++k) names.push_back("VSCORE" + std::to_string(k - 1));
+  }
+  const uint32_t cols = static_cast<uint32_t>(names.size());
+  if (!cols) {
+    logprintf("Error: No score columns in --variant-score file.\n");
+    return kRetMalformedInput;
+  }
+  auto key = [&](const std::string& fid, const std::string& iid, const std::string& sid) {
+    std::string k = fid_col ? (fid + "\t" + iid) : iid;
+    if (sid_col && S.sid_present) k += "\t" + sid;
+    return k;
+  };
+  std::unordered_map<std::string, int64_t> by_key;
+  by_key.reserve(static_cast<size_t>(n) * 2);
+  for (uint32_t k = 0; k < n; ++k) {
+    auto ins = by_key.emplace(key(S.fid[k], S.iid[k], S.sid[k]), k);
+    if (!ins.second) ins.first->second = -1;
+  }
+  std::vector<double> w(static_cast<uint64_t>(n) * cols, 0.0);
+  std::vector<uint8_t> seen(n, 0);
+  uint64_t skipped = 0;
+  uint32_t loaded = 0;
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    const std::vector<std::string> t = SplitWs(lines[li]);
+    if (t.size() < id_tokens + cols) {
+      logprintf("Error: Line %zu of --variant-score file has fewer tokens than expected.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    size_t q = 0;
+    const std::string fid = fid_col ? t[q++] : std::string();
+    const std::string iid = t[q++];
+    const std::string sid = sid_col ? t[q++] : std::string();
+    const auto it = by_key.find(key(fid, iid, sid));
+    if (it == by_key.end() || it->second < 0) {
+      ++skipped;
+      continue;
+    }
+    const uint32_t sidx = static_cast<uint32_t>(it->second);
+    if (seen[sidx]) {
+      logprintf("Error: Sample ID on line %zu of --variant-score file appears more than once.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    seen[sidx] = 1;
+    ++loaded;
+    for (uint32_t cc = 0; cc < cols; ++cc) {
+      double d;
+      if (!ParseDouble(t[id_tokens + cc].c_str(), &d) || d != d) {
+        logprintf("Error: Invalid coefficient on line %zu of --variant-score file.\n", li + 1);
+        return kRetMalformedInput;
+      }
+      w[static_cast<uint64_t>(sidx) * cols + cc] = d;
+    }
+  }
+  if (skipped) logprintf("Warning: %llu line%s skipped in --variant-score file.\n", static_cast<unsigned long long>(skipped), skipped == 1 ? "" : "s");
+  if (!loaded) {
+    logprintf("Error: No valid entries in --variant-score file.\n");
+    return kRetDegenerateData;
+  }
+  logprintf("--variant-score: %u score-vector%s loaded for %u sample%s.\n", cols, cols == 1 ? "" : "s", loaded, loaded == 1 ? "" : "s");
+  for (uint32_t v = 0; v < m; ++v) {
+    if (V.chr_code[v] == 23 || V.chr_code[v] == 24 || V.chr_code[v] == 26) {
+      logprintf("Error: --variant-score on chrX / chrY / chrMT variants (sex-dependent ploidy) is not supported by plink2_b200 yet.\n");
+      return kRetNotYetSupported;
+    }
+  }
+  std::vector<uint32_t> vidx(m);
+  for (uint32_t v = 0; v < m; ++v) vidx[v] = v;
+  std::vector<double> ref_freqs;
+  int rc = 0;
+  {
+    const bool have = FounderRefFreqs(ds, ctx, vidx, &ref_freqs, &rc, true);
+    if (rc) return rc;
+    ApplyReadFreq(*ds, vidx, &ref_freqs, have);
+  }
+  // the matrix is kept resident in pieces that fit comfortably; every piece is one pl2gpu_pca job
+  std::vector<double> scores(static_cast<uint64_t>(m) * cols);
+  const uint32_t piece = 262144;
+  for (uint32_t p0 = 0; p0 < m; p0 += piece) {
+    const uint32_t p1 = std::min(m, p0 + piece);
+    Pl2PcaJob* job = nullptr;
+    if (pl2gpu_pca_begin_shard(ctx, n, p1 - p0, 1, &job)) return GpuFail("pl2gpu_pca_begin_shard");
+    struct Guard {
+      Pl2PcaJob* j;
+      ~Guard() { pl2gpu_pca_end(j); }
+    } guard{job};
+    std::vector<uint32_t> sub(vidx.begin() + p0, vidx.begin() + p1);
+    BlockStreamer bs(ds, &sub, n, 32768);
+    if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+    size_t base = p0;
+    for (;;) {
+      const int got = bs.Next(&err);
+      if (got < 0) {
+        logprintf("Error: %s\n", err.c_str());
+        return kRetMalformedInput;
+      }
+      if (!got) break;
+      const int arc = pl2gpu_pca_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, ref_freqs.data() + base);
+      if (arc) {
+        logprintf("Error: %s\n", pl2gpu_last_error());
+        return arc == 2 ? kRetDegenerateData : kRetGpuFail;
+      }
+      base += static_cast<size_t>(got);
+    }
+    if (pl2gpu_pca_vscore(job, w.data(), cols, scores.data() + static_cast<uint64_t>(p0) * cols)) return GpuFail("pl2gpu_pca_vscore");
+  }
+  // report (:9900-10060): #CHROM POS ID REF ALT [PROVISIONAL_REF?] [ALT_FREQ] <score names>
+  const bool provref_col = c.vs_provref || (c.vs_maybeprovref && V.provisional_ref && c.vs_ref);
+  const std::string name = c.out + (c.vscore_zs ? ".vscore.zst" : ".vscore");
+  OutFile f;
+  if (!f.Open(name, c.vscore_zs)) return kRetOpenFail;
+  std::string hdr = "#";
+  if (c.vs_chrom) hdr += "CHROM\t";
+  if (c.vs_pos) hdr += "POS\t";
+  hdr += "ID";
+  if (c.vs_ref) hdr += "\tREF";
+  if (c.vs_alt) hdr += "\tALT";
+  if (provref_col) hdr += "\tPROVISIONAL_REF?";
+  if (c.vs_altfreq) hdr += "\tALT_FREQ";
+  for (const std::string& nm : names) hdr += "\t" + nm;
+  hdr += "\n";
+  f.Puts(hdr.c_str());
+  char num[64];
+  for (uint32_t v = 0; v < m; ++v) {
+    std::string row;
+    if (c.vs_chrom) row += ChrNameOut(V.chr_code[v], V.chr_name[v]) + "\t";
+    if (c.vs_pos) row += std::to_string(V.bp[v]) + "\t";
+    row += V.id[v];
+    if (c.vs_ref) row += "\t" + V.ref[v];
+    if (c.vs_alt) row += "\t" + V.alt[v];
+    if (provref_col) row += V.provisional_ref ? "\tY" : "\tN";
+    if (c.vs_altfreq) {
+      *dtoa_g(1.0 - ref_freqs[v], num) = '\0';
+      row += std::string("\t") + num;
+    }
+    for (uint32_t cc = 0; cc < cols; ++cc) {
+      *dtoa_g(scores[static_cast<uint64_t>(v) * cols + cc], num) = '\0';
+      row += std::string("\t") + num;
+    }
+    row += "\n";
+    f.Write(row.data(), row.size());
+  }
+  if (!f.Close()) return kRetWriteFail;
+  logprintf("--variant-score: Results written to %s .\n", name.c_str());
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- --freq
 int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
@@ -2885,6 +3113,10 @@ int main(int argc, char** argv) {
   }
   if (!c.score_file.empty()) {
     rc = RunScore(c, &ds, ctx);
+    if (rc) return rc;
+  }
+  if (!c.vscore_file.empty()) {
+    rc = RunVscore(c, &ds, ctx);
     if (rc) return rc;
   }
   std::vector<uint8_t> cutoff_removed;

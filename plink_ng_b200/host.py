@@ -361,3 +361,20 @@ def score_sums(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int, weights4: 
         return sums, dos, miss
     finally:
         lib.pl2gpu_score_end(h)
+
+
+def variant_scores(ctx: GpuContext, genovecs: np.ndarray, sample_ct: int, weights: np.ndarray, ref_freqs=None) -> np.ndarray:
+    """`--variant-score` sums (pl2gpu_pca_vscore) for an in-memory block: weights [sample_ct, cols] -> [variants, cols]."""
+    g = np.ascontiguousarray(genovecs)
+    w = np.ascontiguousarray(weights, dtype=np.float64)
+    assert w.shape[0] == sample_ct
+    rf = None if ref_freqs is None else np.ascontiguousarray(ref_freqs, dtype=np.float64)
+    h = C.c_void_p()
+    check(lib.pl2gpu_pca_begin_shard(ctx.handle, sample_ct, g.shape[0], 1, C.byref(h)), "pl2gpu_pca_begin_shard")
+    try:
+        check(lib.pl2gpu_pca_add_variants(h, g.ctypes.data, g.strides[0], g.shape[0], 0, rf.ctypes.data if rf is not None else None), "pl2gpu_pca_add_variants")
+        out = np.empty((g.shape[0], w.shape[1]), dtype=np.float64)
+        check(lib.pl2gpu_pca_vscore(h, w.ctypes.data, w.shape[1], out.ctypes.data), "pl2gpu_pca_vscore")
+        return out
+    finally:
+        lib.pl2gpu_pca_end(h)

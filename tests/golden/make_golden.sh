@@ -72,6 +72,10 @@ cp $T/a_sc.sscore a_sc.sscore; cp $T/a_sc2.sscore a_sc2.sscore
 $P --bfile a --score a_score.txt header center cols=+scoresums --threads 2 --out $T/a_scc > /dev/null
 $P --bfile a --score a_score.txt header variance-standardize cols=+scoresums --threads 2 --out $T/a_scv > /dev/null
 cp $T/a_scc.sscore a_sc_center.sscore; cp $T/a_scv.sscore a_sc_varstd.sscore
+# --variant-score: two weight columns for 89 of the 100 samples + one unknown ID (a_vscore_weights.txt is kept as written)
+$P --bfile a --variant-score a_vscore_weights.txt --threads 2 --out $T/a_vs > /dev/null
+$P --bfile a --variant-score a_vscore_weights.txt cols=+altfreq --threads 2 --out $T/a_vsf > /dev/null
+cp $T/a_vs.vscore a_vs.vscore; cp $T/a_vsf.vscore a_vs_altfreq.vscore
 # --king-cutoff-table on the proportion table written above
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --threads 2 --out $T/a_kct > /dev/null
 cp $T/a_kct.king.cutoff.in.id a_kct.king.cutoff.in.id; cp $T/a_kct.king.cutoff.out.id a_kct.king.cutoff.out.id

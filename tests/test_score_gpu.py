@@ -82,3 +82,39 @@ def test_score_header_read_names_the_column(golden_dir, tmp_path):
     assert got_h == ["#IID", "PHENO1", "ALLELE_CT", "NAMED_ALLELE_DOSAGE_SUM", "BETA_AVG"]
     _, ref = _table(os.path.join(golden_dir, "a_sc.sscore"))
     assert [g[0:4] for g in got] == [w[1:5] for w in ref]
+
+
+@pytest.mark.parametrize("n,m,cols", [(300, 1000, 3), (2000, 5000, 50)])
+def test_variant_scores_match_oracle(gpu_ctx, n, m, cols):
+    """--variant-score on the approx-PCA tile path: several 128-variant CTAs, a second column group (50 > 48 columns),
+    monomorphic variants (no variance -> the 2 f W term alone), samples with weight 0."""
+    from plink_ng_b200.host import variant_scores
+
+    rng = np.random.default_rng(n + cols)
+    geno = rng.choice(4, size=(m, n), p=[0.5, 0.3, 0.17, 0.03]).astype(np.uint8)
+    geno[5] = 0
+    geno[6] = np.where(rng.random(n) < 0.1, 3, 2)
+    w = rng.normal(size=(n, cols))
+    w[rng.random(n) < 0.2] = 0.0
+    want = orc.variant_scores(geno, w, orc.ref_allele_freqs(geno))
+    got = variant_scores(gpu_ctx, pack_genotypes(geno), n, w)
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-9 * np.abs(want).max())
+
+
+@pytest.mark.parametrize("flags,golden", [((), "a_vs.vscore"), (("cols=+altfreq",), "a_vs_altfreq.vscore")])
+def test_variant_score_cli_matches_reference_report(golden_dir, tmp_path, flags, golden):
+    out = str(tmp_path / "v")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--variant-score", os.path.join(golden_dir, "a_vscore_weights.txt"), *flags, "--out", out], capture_output=True, text=True, env=ENV)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "2 score-vectors loaded for 89 samples" in r.stdout and "1 line skipped" in r.stdout
+    got_h, got = _table(out + ".vscore")
+    ref_h, ref = _table(os.path.join(golden_dir, golden))
+    assert got_h == ref_h and len(got) == len(ref)
+    first_score = ref_h.index("W1")
+    same_text = 0
+    for g, w in zip(got, ref):
+        assert g[:first_score] == w[:first_score]  # CHROM POS ID REF ALT PROVISIONAL_REF? [ALT_FREQ]: exact
+        for col in range(first_score, len(ref_h)):
+            assert np.isclose(float(g[col]), float(w[col]), rtol=2e-5, atol=2e-9)
+            same_text += g[col] == w[col]
+    assert same_text >= 0.97 * len(ref) * (len(ref_h) - first_score)
