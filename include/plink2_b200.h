@@ -246,7 +246,8 @@ int pl2_ld_prune_walk(uint32_t variant_ct, const uint32_t* chr_codes, const uint
  * (variant, allele) line, in any order) are streamed as PgrGet rows together with, per entry, weights4[e][code] =
  * the contribution of genotype code 0/1/2/3 (code 3 = missing: coefficient x 2 x named-allele frequency, or 0 with
  * 'no-mean-imputation', :6605-6607) and named_dosages[e] = the named-allele dosages of codes 0, 1, 2 packed two
- * bits each (bits 0-1, 2-3, 4-5): 0x24 when the ALT allele is named, 0x06 when REF is.  pl2gpu_score_get returns per sample the weighted sum, the named-allele dosage
+ * bits each (bits 0-1, 2-3, 4-5): 0x24 when the ALT allele is named, 0x06 when REF is ('dominant': 0x14 / 0x05,
+ * 'recessive': 0x10 / 0x01).  pl2gpu_score_get returns per sample the weighted sum, the named-allele dosage
  * sum over nonmissing calls (NAMED_ALLELE_DOSAGE_SUM) and the number of missing calls (ALLELE_CT = 2 x (entries -
  * missing), :8581).  Partial sums are combined in a fixed order: results are bit-reproducible. ---- */
 typedef struct Pl2ScoreJob Pl2ScoreJob;

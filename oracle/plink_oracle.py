@@ -289,13 +289,17 @@ def score_report(geno: np.ndarray, entries, ref_freq: np.ndarray, no_mean_imputa
         named = np.where(g == 3, 0, named)
         f_named = (1.0 - ref_freq[v]) if aidx == 1 else ref_freq[v]
         slope, icpt = 1.0, 0.0
-        if mode:
+        if mode in ("center", "variance-standardize"):
             if mode == "variance-standardize":
                 var = 2.0 * f_named * (1.0 - f_named)
                 slope = 1.0 / np.sqrt(var) if var > SMALL_EPSILON else 0.0
             icpt = (-2.0 * f_named) * slope
+        miss_dosage = 2.0 * f_named
+        if mode in ("dominant", "recessive"):  # copies -> min(copies, 1) / max(copies - 1, 0); a missing call -> ONE x f (:6747-6762)
+            named = np.minimum(named, 1) if mode == "dominant" else np.maximum(named - 1, 0)
+            miss_dosage = f_named
         d = named.astype(np.float64) * slope + icpt
-        d = np.where(g == 3, 0.0 if no_mean_imputation else (2.0 * f_named) * slope, d)
+        d = np.where(g == 3, 0.0 if no_mean_imputation else miss_dosage * slope, d)
         ssum += coef * d
         dos += named
         miss += g == 3

@@ -89,7 +89,7 @@ struct Cmd {
   // --score <file> [i] [j] [k] [header | header-read] [no-mean-imputation] [zs] [cols=]
   std::string score_file;
   uint32_t score_id_col = 1, score_allele_col = 2, score_coef_col = 3;
-  bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false, score_center = false, score_varstd = false;
+  bool score_header = false, score_header_read = false, score_no_meanimpute = false, score_zs = false, score_center = false, score_varstd = false, score_dominant = false, score_recessive = false, score_list_variants = false;
   bool sc_fid_maybe = true, sc_fid = false, sc_sid_maybe = true, sc_sid = false, sc_pheno1 = false, sc_phenos = true, sc_nallele = true, sc_denom = false, sc_dosagesum = true, sc_avgs = true, sc_sums = false;
   std::string vscore_file;                // --variant-score <file> ['zs'] ['cols=' chrom,pos,ref,alt,maybeprovref,provref,altfreq]
   bool vscore_zs = false, vs_chrom = true, vs_pos = true, vs_ref = true, vs_alt = true, vs_maybeprovref = true, vs_provref = false, vs_altfreq = false;
@@ -324,6 +324,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         else if (m == "no-mean-imputation") c->score_no_meanimpute = true;
         else if (m == "center") c->score_center = true;
         else if (m == "variance-standardize") c->score_center = c->score_varstd = true;
+        else if (m == "dominant") c->score_dominant = true;
+        else if (m == "recessive") c->score_recessive = true;
+        else if (m == "list-variants") c->score_list_variants = true;
         else if (m == "zs") c->score_zs = true;
         else if (m.compare(0, 5, "cols=") == 0) {
           // column-set descriptor: a plain list replaces the default, +x / -x entries edit it
@@ -359,10 +362,11 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
             else return Usage(("Invalid --score cols= entry '" + tok + "'.").c_str());
           }
         } else {
-          return Usage(("--score modifier '" + m + "' is not supported by plink2_b200 (supported: header, header-read, center, variance-standardize, no-mean-imputation, zs, cols=).").c_str());
+          return Usage(("--score modifier '" + m + "' is not supported by plink2_b200 (supported: header, header-read, center, variance-standardize, dominant, recessive, no-mean-imputation, list-variants, zs, cols=).").c_str());
         }
       }
       if (c->score_header && c->score_header_read) return Usage("--score 'header' and 'header-read' modifiers cannot be used together.");
+      if ((c->score_dominant || c->score_recessive) && (c->score_center || (c->score_dominant && c->score_recessive))) return Usage("--score 'dominant' / 'recessive' cannot be combined with each other or with 'center' / 'variance-standardize'.");
     } else if (flag == "--variant-score" || flag == "--vscore") {
       if (nparam < 1) return Usage("--variant-score requires a filename.");
       c->vscore_file = prm[0];
@@ -2420,6 +2424,17 @@ int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("Error: No valid variants in --score file.\n");
     return kRetDegenerateData;
   }
+  // <out>.sscore.vars lists the variants in score-file order, each once (:7790-7800)
+  std::vector<uint32_t> file_order;
+  if (c.score_list_variants) {
+    std::vector<uint8_t> listed(V.size(), 0);
+    for (const Entry& e : entries) {
+      if (!listed[e.v]) {
+        listed[e.v] = 1;
+        file_order.push_back(e.v);
+      }
+    }
+  }
   // device passes run in variant order (sums are order-independent up to fp64 rounding; the device adds in a fixed order)
   std::stable_sort(entries.begin(), entries.end(), [](const Entry& a, const Entry& b) { return a.v < b.v; });
   std::vector<uint32_t> vidx(entries.size());
@@ -2472,11 +2487,21 @@ int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
         }
         icpt = (-2.0 * f_named) * slope;
       }
-      w4[4ull * k + 0] = e.coef * (static_cast<double>(d0) * slope + icpt);
-      w4[4ull * k + 1] = e.coef * (slope + icpt);
-      w4[4ull * k + 2] = e.coef * (static_cast<double>(d2) * slope + icpt);
-      w4[4ull * k + 3] = c.score_no_meanimpute ? 0.0 : e.coef * ((2.0 * f_named) * slope);
-      d4[k] = static_cast<uint8_t>(d0 | (1u << 2) | (d2 << 4));
+      // 'dominant' / 'recessive' (:6747-6762): copies -> min(copies, 1) / max(copies - 1, 0), a missing call -> ONE x f
+      uint32_t e0 = d0, e1 = 1, e2 = d2;
+      double miss_dosage = 2.0 * f_named;
+      if (c.score_dominant) {
+        e0 = d0 ? 1 : 0, e2 = d2 ? 1 : 0;
+        miss_dosage = f_named;
+      } else if (c.score_recessive) {
+        e0 = d0 ? 1 : 0, e1 = 0, e2 = d2 ? 1 : 0;
+        miss_dosage = f_named;
+      }
+      w4[4ull * k + 0] = e.coef * (static_cast<double>(e0) * slope + icpt);
+      w4[4ull * k + 1] = e.coef * (static_cast<double>(e1) * slope + icpt);
+      w4[4ull * k + 2] = e.coef * (static_cast<double>(e2) * slope + icpt);
+      w4[4ull * k + 3] = c.score_no_meanimpute ? 0.0 : e.coef * (miss_dosage * slope);
+      d4[k] = static_cast<uint8_t>(e0 | (e1 << 2) | (e2 << 4));
     }
     if (pl2gpu_score_add_variants(job, bs.buf, static_cast<uint64_t>(bs.words) * 8, static_cast<uint32_t>(got), 0, w4.data(), d4.data())) return GpuFail("pl2gpu_score_add_variants");
     base += static_cast<size_t>(got);
@@ -2486,6 +2511,17 @@ int RunScore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   std::vector<uint32_t> miss(n);
   if (pl2gpu_score_get(job, sums.data(), dos.data(), miss.data())) return GpuFail("pl2gpu_score_get");
   logprintf("--score: %zu variant%s processed.\n", entries.size(), entries.size() == 1 ? "" : "s");
+  if (c.score_list_variants) {
+    OutFile fv;
+    const std::string vname = c.out + ".sscore.vars";
+    if (!fv.Open(vname)) return kRetOpenFail;
+    for (const uint32_t v : file_order) {
+      fv.Write(V.id[v].data(), V.id[v].size());
+      fv.Puts("\n");
+    }
+    if (!fv.Close()) return kRetWriteFail;
+    logprintf("Variant list written to %s .\n", vname.c_str());
+  }
   // report (:8470-8625)
   std::vector<PhenoOut> phenos;
   if (c.sc_phenos || c.sc_pheno1) {

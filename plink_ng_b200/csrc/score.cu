@@ -31,11 +31,13 @@ constexpr uint32_t kScoreTile = 64;  // variants whose tables are staged in shar
 //    per-sample counters every 127 variants.  A REF-named entry flips hom-REF <-> hom-ALT first
 //    (w ^= (~w & 0x5555...) << 1), after which the dosage is the code itself with "missing" cleared.
 // raw: [variant][pitch] bytes (pitch multiple of 4, padding samples coded missing); w4: [variant][4] weights;
-// d4: [variant] packed named-allele dosages of codes 0..2 (2 bits each): 0x24 = ALT named, 0x06 = REF named.
+// d4: [variant] packed named-allele dosages of codes 0..2 (2 bits each): 0x24 = ALT named, 0x06 = REF named; the
+// 'dominant' / 'recessive' forms 0x14 / 0x05 and 0x10 / 0x01 count min(copies, 1) / max(copies - 1, 0).
 __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __restrict__ raw, uint32_t pitch, uint32_t words, uint32_t variant_ct, uint32_t chunk_variants, const double* __restrict__ w4, const uint8_t* __restrict__ d4,
                                                            double* __restrict__ part_sum, uint32_t* __restrict__ part_dos, uint32_t* __restrict__ part_miss, uint32_t samples_padded) {
   __shared__ double s_t2[(kScoreTile / 2) * 16];
   __shared__ uint32_t s_flip[kScoreTile];
+  __shared__ uint8_t s_mode[kScoreTile];  // 0 additive, 1 dominant (dosage min(count, 1)), 2 recessive (max(count - 1, 0))
   const uint32_t widx = blockIdx.x * kScoreThreads + threadIdx.x;
   const uint32_t v_begin = blockIdx.y * chunk_variants, v_end = min(variant_ct, v_begin + chunk_variants);
   double sum[16];
@@ -85,7 +87,11 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
       const uint32_t va = v0 + 2 * pr, vb = va + 1;
       s_t2[e] = w4[4ull * va + ca] + ((vb < v_end) ? w4[4ull * vb + cb] : 0.0);
     }
-    for (uint32_t e = threadIdx.x; e < tile; e += kScoreThreads) s_flip[e] = (d4[v0 + e] & 3) ? 0xFFFFFFFFu : 0u;  // dosage of code 0 nonzero: REF named
+    for (uint32_t e = threadIdx.x; e < tile; e += kScoreThreads) {
+      const uint32_t dd = d4[v0 + e], da = dd & 3, db = (dd >> 2) & 3, dc = (dd >> 4) & 3;
+      s_flip[e] = da ? 0xFFFFFFFFu : 0u;  // dosage of code 0 nonzero: REF named
+      s_mode[e] = (da == 2 || dc == 2) ? 0 : (db ? 1 : 2);
+    }
     __syncthreads();
     if (widx >= words) continue;
     for (uint32_t pr = 0; pr < pairs; ++pr) {
@@ -109,7 +115,10 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
         uint32_t w = h ? wb : wa;
         const uint32_t ms = w & (w >> 1) & 0x55555555u;  // missing flag at the even bit of each 2-bit field
         w ^= ((~w & 0x55555555u) << 1) & s_flip[2 * pr + h];  // REF named: 0 <-> 2 (1 and 3 keep their value)
-        const uint32_t d = w ^ (ms * 3u);                   // missing -> 0
+        uint32_t d = w ^ (ms * 3u);                         // missing -> 0
+        const uint32_t mode = s_mode[2 * pr + h];
+        if (mode == 1) d = (d | (d >> 1)) & 0x55555555u;    // dominant: 1 for one or two copies
+        else if (mode == 2) d = (d >> 1) & 0x55555555u;     // recessive: 1 for two copies
         d4e += d & 0x33333333u;
         d4o += (d >> 2) & 0x33333333u;
         m4e += ms & 0x11111111u;
@@ -225,8 +234,9 @@ int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t v
     return 1;
   }
   for (uint32_t v = 0; v < variant_ct; ++v) {
-    if (named_dosages[v] != 0x24 && named_dosages[v] != 0x06) {
-      set_error("pl2gpu_score_add_variants: entry %u has named-allele dosages 0x%02x (0x24 = ALT named, 0x06 = REF named)", v, named_dosages[v]);
+    const uint8_t dd = named_dosages[v];
+    if (dd != 0x24 && dd != 0x06 && dd != 0x14 && dd != 0x05 && dd != 0x10 && dd != 0x01) {
+      set_error("pl2gpu_score_add_variants: entry %u has named-allele dosages 0x%02x (ALT / REF named: additive 0x24 / 0x06, dominant 0x14 / 0x05, recessive 0x10 / 0x01)", v, dd);
       return 1;
     }
   }

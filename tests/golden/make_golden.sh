@@ -72,6 +72,9 @@ cp $T/a_sc.sscore a_sc.sscore; cp $T/a_sc2.sscore a_sc2.sscore
 $P --bfile a --score a_score.txt header center cols=+scoresums --threads 2 --out $T/a_scc > /dev/null
 $P --bfile a --score a_score.txt header variance-standardize cols=+scoresums --threads 2 --out $T/a_scv > /dev/null
 cp $T/a_scc.sscore a_sc_center.sscore; cp $T/a_scv.sscore a_sc_varstd.sscore
+$P --bfile a --score a_score.txt header dominant list-variants cols=+scoresums,+denom --threads 2 --out $T/a_scd > /dev/null
+$P --bfile a --score a_score.txt header recessive cols=+scoresums,+denom --threads 2 --out $T/a_scr > /dev/null
+cp $T/a_scd.sscore a_sc_dominant.sscore; cp $T/a_scr.sscore a_sc_recessive.sscore; cp $T/a_scd.sscore.vars a_sc.sscore.vars
 # --variant-score: two weight columns for 89 of the 100 samples + one unknown ID (a_vscore_weights.txt is kept as written)
 $P --bfile a --variant-score a_vscore_weights.txt --threads 2 --out $T/a_vs > /dev/null
 $P --bfile a --variant-score a_vscore_weights.txt cols=+altfreq --threads 2 --out $T/a_vsf > /dev/null

@@ -52,7 +52,8 @@ def _table(path):
 
 
 @pytest.mark.parametrize("flags,golden", [(("header",), "a_sc.sscore"), (("header", "no-mean-imputation", "cols=+scoresums,+denom"), "a_sc2.sscore"),
-                                          (("header", "center", "cols=+scoresums"), "a_sc_center.sscore"), (("header", "variance-standardize", "cols=+scoresums"), "a_sc_varstd.sscore")])
+                                          (("header", "center", "cols=+scoresums"), "a_sc_center.sscore"), (("header", "variance-standardize", "cols=+scoresums"), "a_sc_varstd.sscore"),
+                                          (("header", "dominant", "list-variants", "cols=+scoresums,+denom"), "a_sc_dominant.sscore"), (("header", "recessive", "cols=+scoresums,+denom"), "a_sc_recessive.sscore")])
 def test_score_cli_matches_reference_report(golden_dir, tmp_path, flags, golden):
     out = str(tmp_path / "s")
     r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "a"), "--score", os.path.join(golden_dir, "a_score.txt"), *flags, "--out", out], capture_output=True, text=True, env=ENV)
@@ -71,6 +72,8 @@ def test_score_cli_matches_reference_report(golden_dir, tmp_path, flags, golden)
                 assert np.isclose(float(g[col]), float(w[col]), rtol=2e-5, atol=2e-9)  # 6 significant digits printed
                 same_text += g[col] == w[col]
     assert same_text >= 0.97 * len(ref) * sum(is_float)  # fp64 sums in a different order: a last printed digit may move
+    if "list-variants" in flags:
+        assert open(out + ".sscore.vars", "rb").read() == open(os.path.join(golden_dir, "a_sc.sscore.vars"), "rb").read()
 
 
 def test_score_header_read_names_the_column(golden_dir, tmp_path):
