@@ -163,7 +163,7 @@ int main(int argc, char** argv) {
 @pytest.mark.parametrize("flags,fragment", [
     (("--glm",), "unsupported"),
     (("--make-grm-bin", "--make-grm-list"), "--make-grm-list cannot be used with --make-grm-bin"),
-    (("--score", "w.txt", "dominant"), "not supported"),
+    (("--score", "w.txt", "se"), "not supported"),
     (("--indep-preferred", "x.txt"), "--indep-preferred must be used with --indep-pairwise"),
     (("--make-king-table", "--king-table-subset"), "--king-table-subset requires"),
     (("--pca", "0"), "Invalid --pca PC count"),
