@@ -1,7 +1,7 @@
 """Triage: reference vs plink2_b200 on --dummy data, reports WHERE the kinship matrix / table differ."""
 import os, subprocess, sys, tempfile
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 REF, BIN = os.path.join(ROOT, "oracle/_ref/plink2"), os.path.join(ROOT, "plink_ng_b200/plink2_b200")
 n, m = int(sys.argv[1]), int(sys.argv[2])
 extra = sys.argv[3:]

@@ -5,7 +5,7 @@
 set -e
 D=$(mktemp -d); P=oracle/_ref/plink2
 python - "$D" <<'PY'
-import sys, bench
+import sys; sys.path.insert(0, "."); import bench
 bench.write_synth_bed(sys.argv[1] + "/g", 16384, 65536)
 PY
 $P --bfile $D/g --make-pgen --threads 16 --out $D/m10 > /dev/null

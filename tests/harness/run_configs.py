@@ -3,8 +3,8 @@ with the unmodified reference binary timed beside them on the same files (config
 same file, scaled by variant count - the full CPU run would take ~40 min on this box's 16-CPU quota; config 4:
 the whole file).  Writes one JSON object per config to stdout / gpurun_out/configs_r02.json.
 
-  python tools/run_configs.py c2 [samples variants ref_variants]     (defaults 50000 500000 50000)
-  python tools/run_configs.py c4 [founders variants]                 (defaults 50000 1000000, 22 chromosomes)
+  python tests/harness/run_configs.py c2 [samples variants ref_variants]     (defaults 50000 500000 50000)
+  python tests/harness/run_configs.py c4 [founders variants]                 (defaults 50000 1000000, 22 chromosomes)
 """
 import json
 import os
@@ -12,7 +12,7 @@ import subprocess
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import torch

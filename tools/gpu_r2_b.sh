@@ -15,7 +15,7 @@ if grep -q "king ts == popcount: True" gpurun_out/min_king.log; then
   echo "== int8 peak"; timeout 120 python tools/int8_peak.py 2>&1 | tail -2 | tee gpurun_out/int8_peak.json
   echo "== quick bench"; SKIP_POPC=1 SKIP_SS=1 timeout 300 python tools/quick_king_bench.py 16384 65536 2>&1 | tail -4 | tee gpurun_out/quick_bench.log
   echo "== ld bench"; timeout 300 python tools/ld_bench.py 2>&1 | tail -6 | tee gpurun_out/ld_bench.log
-  echo "== debug cli"; REPS=12 timeout 600 python tools/debug_king_cli.py 3000 4096 --gpu-memory 640 2>&1 | grep -v "^rc" | tail -40 | tee gpurun_out/debug_cli.log
+  echo "== debug cli"; REPS=12 timeout 600 python tests/harness/debug_king_cli.py 3000 4096 --gpu-memory 640 2>&1 | grep -v "^rc" | tail -40 | tee gpurun_out/debug_cli.log
   echo "== pytest"; ( time timeout 1800 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_full.log 2>&1; tail -25 gpurun_out/pytest_full.log ) 2>&1 | tee gpurun_out/pytest_gpu.log
   grep -n "differs from" -A6 gpurun_out/pytest_full.log | head -40
 fi
