@@ -176,8 +176,47 @@ def c3(n=100000, m=1000000, n_ref=8192, m_ref=32768):
     return out
 
 
+def c5(n=200000, m=131072, pairs_checked=20000):
+    """Config 5's per-GPU situation on ONE GPU: a KING job whose accumulators (20 bytes x N(N-1)/2 = 400 GB at 200k
+    samples) do not fit the device, so the host program makes several passes over the file on its own (no --gpu-memory).
+    Parity at this size: the rows our dense multipass run reports above a kinship threshold are recomputed by the
+    REFERENCE through its pair-list path (--king-table-subset on our table, same file) and compared byte for byte."""
+    d = os.environ.get("PL2_CFG_DIR", "/tmp/pl2_c5")
+    os.makedirs(d, exist_ok=True)
+    pre = os.path.join(d, "c5")
+    gen_s = write_pgen(pre, n, m)
+    cores = bench.effective_cores()
+    env = dict(os.environ, PL2_TIMING="1")
+    import plink_ng_b200 as p
+    from plink_ng_b200.host import KingJob
+    mm = np.memmap(pre + ".pgen", dtype=np.uint8, mode="r", offset=12).reshape(m, (n + 3) // 4)
+    corner = np.ascontiguousarray(mm[:, :1024]).view("<u8")
+    with p.GpuContext(0) as cx, KingJob(cx, 4096) as job:
+        job.add_variants(corner)
+        kin = job.kinship()
+    pairs = n * (n - 1) // 2
+    # ~pairs_checked rows expected above the threshold under a normal approximation of the kinship distribution
+    from statistics import NormalDist
+    z = NormalDist().inv_cdf(1.0 - pairs_checked / pairs)
+    thr = repr(float(np.median(kin) + z * kin.std()))
+    del mm, corner, kin
+    flags = ["--make-king-table", "counts", "--king-table-filter", thr]
+    # NSNP as the plain dense count: the reference's pair-list path has no rare-variant pre-scan, so its NSNP lacks the
+    # +1 quirk of its own dense path that the host program otherwise reproduces (DESIGN.md section 7)
+    t_ours, r = run([BIN, "--pfile", pre] + flags + ["--out", pre + "_b200"], dict(env, PL2_KING_DENSE_NSNP="1"))
+    phases = [ln for ln in r.stderr.split("\n") if ln.startswith("[timing]")]
+    passes = max([int(ln.split("pass ")[1].split("/")[1].split(":")[0]) for ln in (r.stdout + r.stderr).replace("\r", "\n").split("\n") if "--make-king-table pass " in ln] or [1])
+    rows = sum(1 for _ in open(pre + "_b200.kin0")) - 1
+    t_ref, _ = run([REF, "--pfile", pre, "--make-king-table", "counts", "--king-table-subset", pre + "_b200.kin0", "--threads", str(cores["threads_used"]), "--memory", "120000", "--out", pre + "_ref"])
+    same = open(pre + "_ref.kin0", "rb").read() == open(pre + "_b200.kin0", "rb").read()
+    return {"config": "C5 share: --make-king-table, 200k samples x 131,072 SNPs on one B200 (accumulators 400 GB > HBM: natural multipass)", "samples": n, "variants": m,
+            "input": "mode 0x02 .pgen, %.2f GB, generated in %.1f s" % (os.path.getsize(pre + ".pgen") / 1e9, gen_s), "passes": passes, "b200_seconds_process": t_ours, "b200_pair_snp_per_s": pairs * m / t_ours,
+            "b200_phases": phases[-12:], "kinship_threshold": thr, "table_rows": rows,
+            "reference_pair_list": {"command": "--make-king-table counts --king-table-subset <our table>", "seconds_process": t_ref, "threads": cores["threads_used"], "rows_identical_to_ours": bool(same)}, "host_cpus": cores}
+
+
 if __name__ == "__main__":
     which = sys.argv[1]
     args = [int(x) for x in sys.argv[2:]]
-    res = {"c2": c2, "c3": c3, "c4": c4}[which](*args)
+    res = {"c2": c2, "c3": c3, "c4": c4, "c5": c5}[which](*args)
     print(json.dumps(res))
