@@ -41,12 +41,17 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
   const uint32_t widx = blockIdx.x * kScoreThreads + threadIdx.x;
   const uint32_t v_begin = blockIdx.y * chunk_variants, v_end = min(variant_ct, v_begin + chunk_variants);
   double sum[16];
-  uint32_t dos[16], miss[16];
 #pragma unroll
-  for (int s = 0; s < 16; ++s) {
-    sum[s] = 0.0;
-    dos[s] = 0;
-    miss[s] = 0;
+  for (int s = 0; s < 16; ++s) sum[s] = 0.0;
+  // the integer partial sums live in this thread's own 16 slots of the per-chunk partial arrays (zeroed here, added to
+  // at every 8-bit spill): 32 registers fewer than keeping them in the thread
+  const uint64_t base = static_cast<uint64_t>(blockIdx.y) * samples_padded + 16ull * widx;
+  if (widx < words) {
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+      part_dos[base + s] = 0;
+      part_miss[base + s] = 0;
+    }
   }
   // 4-bit fields (even / odd samples) and 8-bit fields (sample s -> register s % 4 ... see spill lambdas)
   uint32_t d4e = 0, d4o = 0, m4e = 0, m4o = 0;
@@ -70,8 +75,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
       const int s0 = (r == 0) ? 0 : (r == 1) ? 2 : (r == 2) ? 1 : 3;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        dos[s0 + 4 * b] += (d8[r] >> (8 * b)) & 0xFFu;
-        miss[s0 + 4 * b] += (m8[r] >> (8 * b)) & 0xFFu;
+        part_dos[base + s0 + 4 * b] += (d8[r] >> (8 * b)) & 0xFFu;
+        part_miss[base + s0 + 4 * b] += (m8[r] >> (8 * b)) & 0xFFu;
       }
       d8[r] = 0;
       m8[r] = 0;
@@ -133,13 +138,8 @@ __global__ void __launch_bounds__(kScoreThreads) score_kernel(const uint8_t* __r
   if (widx >= words) return;
   spill4();
   spill8();
-  const uint64_t base = static_cast<uint64_t>(blockIdx.y) * samples_padded + 16ull * widx;
 #pragma unroll
-  for (int s = 0; s < 16; ++s) {
-    part_sum[base + s] = sum[s];
-    part_dos[base + s] = dos[s];
-    part_miss[base + s] = miss[s];
-  }
+  for (int s = 0; s < 16; ++s) part_sum[base + s] = sum[s];
 }
 
 __global__ void __launch_bounds__(256) score_reduce_kernel(const double* __restrict__ part_sum, const uint32_t* __restrict__ part_dos, const uint32_t* __restrict__ part_miss, uint32_t chunks, uint32_t samples_padded, uint32_t sample_ct,
@@ -252,7 +252,7 @@ int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t v
     PL2_CUDA_OK(cudaMemcpyAsync(job->d_d4, named_dosages + done, cur, cudaMemcpyHostToDevice, c->stream));
     // enough chunks to fill the GPU, each a multiple of the shared-memory tile
     const uint32_t col_ctas = DivUpU32(words, kScoreThreads);
-    uint32_t chunks = std::max(1u, std::min({kScoreMaxChunks, DivUpU32(4 * static_cast<uint32_t>(c->sm_count), col_ctas), DivUpU32(cur, kScoreTile)}));
+    uint32_t chunks = std::max(1u, std::min({kScoreMaxChunks, DivUpU32(7 * static_cast<uint32_t>(c->sm_count), col_ctas), DivUpU32(cur, kScoreTile)}));
     const uint32_t chunk_variants = RoundUpU32(DivUpU32(cur, chunks), kScoreTile);
     chunks = DivUpU32(cur, chunk_variants);
     score_kernel<<<dim3(col_ctas, chunks), kScoreThreads, 0, c->stream>>>(job->stage.d_raw, job->stage.pitch, words, cur, chunk_variants, job->d_w4, job->d_d4, job->d_part_sum, job->d_part_dos, job->d_part_miss, np);
