@@ -83,3 +83,71 @@ def test_tile_aligned_row_blocks_cover_triangle_and_balance():
             if n == 100000:
                 areas = [pairs_in_rows(a, b) for a, b in blocks]
                 assert max(areas) / (sum(areas) / world) < 1.01
+
+
+def _pca_worker(rank, world, port, out_dir):
+    """Variant-sharded approx PCA (pl2gpu_pca_run_sharded's decomposition) restated in numpy over gloo: H_t stays on the
+    rank that owns the variants, G' = Y^T H is an all-reduce of the N x 2k matrix, the Krylov basis is orthonormalised
+    block by block with all-reduced Gram-Schmidt coefficients and an all-gathered block, B = Y^T Q is an all-reduce."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import plink_oracle as orc
+
+    rng = np.random.default_rng(0)
+    n, m, k = 120, 700, 3
+    geno = rng.choice(4, size=(m, n), p=[0.45, 0.35, 0.17, 0.03]).astype(np.uint8)
+    g1 = np.random.default_rng(1).standard_normal((n, 2 * k))
+    y = orc.centered_varmaj(geno, orc.ref_allele_freqs(geno), True)
+    shard = ((m + world - 1) // world + 127) // 128 * 128
+    ys = y[rank * shard : min(m, (rank + 1) * shard)]
+    c2 = 2 * k
+
+    def allreduce(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    g = g1.copy()
+    blocks = []
+    for it in range(k + 1):
+        h = ys @ g
+        blocks.append(h)
+        if it < k:
+            g = allreduce(ys.T @ h) * (1.0 / m)
+    q_blocks = []
+    for t, w in enumerate(blocks):
+        w = w.copy()
+        for _ in range(3):
+            if q_blocks:
+                qp = np.concatenate(q_blocks, axis=1)
+                w = w - qp @ allreduce(qp.T @ w)
+            # all-gather the block (padded to the largest shard), the same SVD on every rank, own rows back
+            slot = torch.zeros((world, shard, c2), dtype=torch.float64)
+            mine = torch.zeros((shard, c2), dtype=torch.float64)
+            mine[: w.shape[0]] = torch.from_numpy(w)
+            dist.all_gather(list(slot.unbind(0)), mine)
+            full = slot.reshape(world * shard, c2).numpy()
+            u, _, _ = np.linalg.svd(full, full_matrices=False)
+            w = u[rank * shard : rank * shard + w.shape[0]]
+        q_blocks.append(w)
+    q = np.concatenate(q_blocks, axis=1)
+    b = allreduce(ys.T @ q)
+    ub, sb, _ = np.linalg.svd(b, full_matrices=False)
+    np.save(os.path.join(out_dir, f"vals_{rank}.npy"), sb[:k] ** 2 / m)
+    if rank == 0:
+        want, _ = orc.pca_approx(geno, k, g1)
+        np.save(os.path.join(out_dir, "want.npy"), want)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_two_rank_variant_sharded_pca_decomposition(tmp_path):
+    world = 2
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_pca_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    vals = [np.load(tmp_path / f"vals_{r}.npy") for r in range(world)]
+    want = np.load(tmp_path / "want.npy")
+    assert np.array_equal(vals[0], vals[1])  # every rank ends with the same numbers
+    assert np.allclose(vals[0], want, rtol=1e-6)
