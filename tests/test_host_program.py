@@ -267,3 +267,15 @@ def test_rel_check_pair_list_matches_reference_table(tmp_path):
         want = ["\t".join(ln.split("\t")[:4]) for ln in text.split("\n")[1:] if ln]
         subprocess.run([BIN, "--debug-rel-check-pairs", os.path.join(gd, prefix + ".fam"), str(tmp_path / "p.txt")], check=True)
         assert (tmp_path / "p.txt").read_text().split("\n")[:-1] == want, prefix
+
+
+def test_read_freq_parser_counts_match_the_reference_log(tmp_path):
+    """--read-freq parsing happens before any device is touched: the counts the reference logs for the same file
+    ("Frequencies for 849 variants loaded", "60 entries skipped") must come out on a box without a GPU too (the run then
+    stops with exit code 16 at GPU initialisation, or completes when a device is present)."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    r = subprocess.run([BIN, "--bfile", os.path.join(gd, "a"), "--read-freq", os.path.join(gd, "a_rf.afreq"), "--make-grm-bin", "--out", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode in (0, 16), r.stdout + r.stderr
+    assert "--read-freq: PLINK 2 --freq file detected." in r.stdout
+    assert "--read-freq: Frequencies for 849 variants loaded." in r.stdout
+    assert "Warning: 60 entries skipped" in r.stdout
