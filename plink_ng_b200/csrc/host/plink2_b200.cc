@@ -2772,20 +2772,20 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
   const uint32_t n = S.size(), m = V.size();
-  for (uint32_t v = 0; v < m; ++v) {
-    if (V.chr_code[v] > 22 && V.chr_code[v] != 25) {
-      logprintf("Error: --freq on chrX/chrY/chrMT variants (sex-dependent ploidy) is not supported by plink2_b200 yet.\n");
-      return kRetNotYetSupported;
-    }
-  }
-  uint32_t founder_ct = 0;
-  std::vector<uint64_t> inc((n + 63) / 64, 0);
-  std::vector<uint8_t> founder_sex;  // chrX / chrY / MT handling needs it (plink2_ld.cc:1356-1389)
+  uint32_t founder_ct = 0, male_ct = 0, nonfemale_ct = 0;
+  std::vector<uint64_t> inc((n + 63) / 64, 0), inc_male((n + 63) / 64, 0), inc_nonfemale((n + 63) / 64, 0);
   for (uint32_t k = 0; k < n; ++k) {
     if (S.is_founder[k]) {
       inc[k / 64] |= 1ull << (k % 64);
-      founder_sex.push_back(S.sex[k]);
       ++founder_ct;
+      if (S.sex[k] == 1) {
+        inc_male[k / 64] |= 1ull << (k % 64);
+        ++male_ct;
+      }
+      if (S.sex[k] != 2) {
+        inc_nonfemale[k / 64] |= 1ull << (k % 64);
+        ++nonfemale_ct;
+      }
     }
   }
   if (!founder_ct) {
@@ -2796,54 +2796,86 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("Error: --freq on a .pgen with per-variant provisional-REF flags is not supported by plink2_b200 yet.\n");
     return kRetNotYetSupported;
   }
-  std::vector<uint32_t> all(m);
-  for (uint32_t v = 0; v < m; ++v) all[v] = v;
-  BlockStreamer bs(ds, &all, founder_ct, 16384);
-  if (founder_ct != n) bs.sample_include = inc.data();
-  if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+  // genotype counts on the device for a variant list over a sample subset (LoadAlleleAndGenoCountsThread's counting,
+  // 2.0/plink2_data.cc:2304): all founders for every variant, founder males for chrX, nonfemale founders for chrY
+  auto count_pass = [&](const std::vector<uint32_t>& vidx, const uint64_t* include, uint32_t sample_ct, std::vector<uint32_t>* out) -> int {
+    out->assign(4ull * vidx.size(), 0);
+    if (vidx.empty() || !sample_ct) return 0;
+    BlockStreamer bs(ds, &vidx, sample_ct, 16384);
+    if (sample_ct != n) bs.sample_include = include;
+    if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+    std::string err;
+    size_t base = 0;
+    for (;;) {
+      const int got = bs.Next(&err);
+      if (got < 0) {
+        logprintf("Error: %s\n", err.c_str());
+        return kRetMalformedInput;
+      }
+      if (!got) break;
+      if (pl2gpu_geno_counts(ctx, bs.buf, static_cast<uint64_t>(bs.words) * 8, sample_ct, static_cast<uint32_t>(got), 0, out->data() + 4ull * base)) return GpuFail("pl2gpu_geno_counts");
+      base += static_cast<size_t>(got);
+    }
+    return 0;
+  };
+  std::vector<uint32_t> all(m), xv, yv;
+  for (uint32_t v = 0; v < m; ++v) {
+    all[v] = v;
+    if (V.chr_code[v] == 23) xv.push_back(v);
+    else if (V.chr_code[v] == 24) yv.push_back(v);
+  }
+  std::vector<uint32_t> counts, xmale, ynonfemale;
+  int rc = count_pass(all, inc.data(), founder_ct, &counts);
+  if (!rc) rc = count_pass(xv, inc_male.data(), male_ct, &xmale);
+  if (!rc) rc = count_pass(yv, inc_nonfemale.data(), nonfemale_ct, &ynonfemale);
+  if (rc) return rc;
   const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
   OutFile f;
   if (!f.Open(name, c.freq_zs)) return kRetOpenFail;
   f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
-  std::vector<uint32_t> counts;
-  std::string err;
-  size_t base = 0;
-  for (;;) {
-    const int got = bs.Next(&err);
-    if (got < 0) {
-      logprintf("Error: %s\n", err.c_str());
-      return kRetMalformedInput;
+  size_t xi = 0, yi = 0;
+  for (uint32_t v = 0; v < m; ++v) {
+    const uint64_t n0 = counts[4ull * v], n1 = counts[4ull * v + 1], n2 = counts[4ull * v + 2], n3 = counts[4ull * v + 3];
+    // allele "ddosages" in 1/32768 units, as the reference accumulates them (plink2_data.cc:2420-2690): diploid x2;
+    // MT and chrY (nonfemale founders) haploid, a het counting half; chrX nonmales twice, males once
+    uint64_t alt_dd, tot_dd;
+    if (V.chr_code[v] == 23) {
+      const uint32_t* mc = &xmale[4 * xi++];
+      const uint64_t alt1 = 4 * n2 + 2 * n1 - 2ull * mc[2] - mc[1];
+      const uint64_t wobs = (2 * (founder_ct - n3) - male_ct + mc[3]) * 2;
+      alt_dd = alt1 * 16384ull;
+      tot_dd = wobs * 16384ull;
+    } else if (V.chr_code[v] == 24) {
+      const uint32_t* yc = &ynonfemale[4 * yi++];
+      alt_dd = (yc[1] + 2ull * yc[2]) * 16384ull;
+      tot_dd = 2ull * (static_cast<uint64_t>(yc[0]) + yc[1] + yc[2]) * 16384ull;
+    } else if (V.chr_code[v] == 26) {
+      alt_dd = (n1 + 2 * n2) * 16384ull;
+      tot_dd = 2 * (n0 + n1 + n2) * 16384ull;
+    } else {
+      alt_dd = (n1 + 2 * n2) * 32768ull;
+      tot_dd = 2 * (n0 + n1 + n2) * 32768ull;
     }
-    if (!got) break;
-    counts.resize(4ull * got);
-    if (pl2gpu_geno_counts(ctx, bs.buf, static_cast<uint64_t>(bs.words) * 8, founder_ct, static_cast<uint32_t>(got), 0, counts.data())) return GpuFail("pl2gpu_geno_counts");
-    for (int k = 0; k < got; ++k) {
-      const uint32_t v = static_cast<uint32_t>(base) + k;
-      const uint64_t n0 = counts[4ull * k], n1 = counts[4ull * k + 1], n2 = counts[4ull * k + 2];
-      // allele "ddosages" in 1/32768 units, as the reference accumulates them (:3746-3772, :3833)
-      const uint64_t alt_dd = (n1 + 2 * n2) * 32768ull, tot_dd = 2 * (n0 + n1 + n2) * 32768ull;
-      const double recip = tot_dd ? 1.0 / static_cast<double>(tot_dd) : 0.0;
-      char* w = f.Reserve(V.chr_name[v].size() + V.id[v].size() + V.ref[v].size() + V.alt[v].size() + 96);
-      auto puts = [&](const std::string& t) {
-        memcpy(w, t.data(), t.size());
-        w += t.size();
-        *w++ = '\t';
-      };
-      puts(ChrNameOut(V.chr_code[v], V.chr_name[v]));
-      puts(V.id[v]);
-      puts(V.ref[v]);
-      puts(V.alt[v]);
-      if (V.provisional_ref) {
-        *w++ = 'Y';
-        *w++ = '\t';
-      }
-      w = dtoa_g(static_cast<double>(alt_dd) * recip, w);
+    const double recip = tot_dd ? 1.0 / static_cast<double>(tot_dd) : 0.0;
+    char* w = f.Reserve(V.chr_name[v].size() + V.id[v].size() + V.ref[v].size() + V.alt[v].size() + 96);
+    auto puts = [&](const std::string& t) {
+      memcpy(w, t.data(), t.size());
+      w += t.size();
       *w++ = '\t';
-      w = u32toa(static_cast<uint32_t>(tot_dd / 32768ull), w);
-      *w++ = '\n';
-      f.Advance(w);
+    };
+    puts(ChrNameOut(V.chr_code[v], V.chr_name[v]));
+    puts(V.id[v]);
+    puts(V.ref[v]);
+    puts(V.alt[v]);
+    if (V.provisional_ref) {
+      *w++ = 'Y';
+      *w++ = '\t';
     }
-    base += static_cast<size_t>(got);
+    w = dtoa_g(static_cast<double>(alt_dd) * recip, w);
+    *w++ = '\t';
+    w = u32toa(static_cast<uint32_t>(tot_dd / 32768ull), w);
+    *w++ = '\n';
+    f.Advance(w);
   }
   if (!f.Close()) return kRetWriteFail;
   logprintf("--freq: Allele frequencies (founders only) written to %s .\n", name.c_str());

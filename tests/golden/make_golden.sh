@@ -96,6 +96,8 @@ $P --bfile x --indep-pairwise 50 5 0.2 --indep-order 1 --threads 2 --out $T/x_o1
 cp $T/x_o2.prune.in x_o2.prune.in; cp $T/x_o1.prune.in x_o1.prune.in
 $P --bfile x --indep-pairwise 30kb 0.3 --threads 2 --out $T/x_kb > /dev/null
 cp $T/x_kb.prune.in x_kb.prune.in
+$P --bfile x --freq --threads 2 --out $T/x_f > /dev/null
+cp $T/x_f.afreq x.afreq
 # rel-check: sets R (60 samples, 2 FIDs, IIDs chosen to exercise the natural sort: leading zeros, mixed case, digit runs)
 # and S (300 random IDs over 5 FIDs) are kept as written by the script that made them (tests/golden/README in DESIGN 7)
 $P --bfile r --make-king-table rel-check counts --threads 2 --out $T/r_rc > /dev/null

@@ -166,6 +166,14 @@ def test_freq_byte_identical(golden_dir, tmp_path, inp, name):
     assert open(out + ".afreq", "rb").read() == open(os.path.join(golden_dir, name), "rb").read()
 
 
+def test_freq_sex_chromosomes_byte_identical(golden_dir, tmp_path):
+    """--freq on set X: chrX (nonmales twice, a male het half an ALT), chrY (nonfemale founders), MT (haploid counts)."""
+    out = str(tmp_path / "xf")
+    r = subprocess.run([BIN, "--bfile", os.path.join(golden_dir, "x"), "--freq", "--out", out], capture_output=True, text=True, env=ENV)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".afreq", "rb").read() == open(os.path.join(golden_dir, "x.afreq"), "rb").read()
+
+
 def test_indep_preferred_list_byte_identical(golden_dir, tmp_path):
     out = run(golden_dir, tmp_path, "--indep-pairwise", "50", "5", "0.1", "--indep-preferred", os.path.join(golden_dir, "a_pref.txt"))
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(golden_dir, "a_ldpref.prune.in"), "rb").read()
