@@ -95,6 +95,8 @@ struct Cmd {
   bool vscore_zs = false, vs_chrom = true, vs_pos = true, vs_ref = true, vs_alt = true, vs_maybeprovref = true, vs_provref = false, vs_altfreq = false;
   std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
   double king_cutoff_table_thresh = -1;
+  std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
+  double king_cutoff_prefix_thresh = -1;
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
   double king_table_subset_thresh = -DBL_MAX;
   bool make_grm_sparse = false;            // --make-grm-sparse <cutoff>
@@ -249,8 +251,11 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       c->king_table_subset = prm[0];
       if (nparam == 2 && !ParseDouble(prm[1], &c->king_table_subset_thresh)) return Usage("Invalid --king-table-subset threshold.");
     } else if (flag == "--king-cutoff") {
-      if (nparam == 2) return Usage("--king-cutoff with a precomputed matrix prefix is not supported by plink2_b200.");
-      if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
+      if (nparam == 2) {
+        // plink2.cc:7671-7700: <prefix> <threshold> prunes from a matrix written earlier by --make-king bin[4] triangle
+        c->king_cutoff_prefix = prm[0];
+        if (!ParseDouble(prm[1], &c->king_cutoff_prefix_thresh) || c->king_cutoff_prefix_thresh < 0 || c->king_cutoff_prefix_thresh >= 0.5) return Usage((std::string("Invalid --king-cutoff[-table] argument '") + prm[1] + "'.").c_str());
+      } else if (!need(1, 1) || !ParseDouble(prm[0], &c->king_cutoff) || c->king_cutoff < 0 || c->king_cutoff >= 0.5) return Usage("Invalid --king-cutoff argument.");
     } else if (flag == "--make-grm-sparse") {
       // <cutoff> ['cov'] ['meanimpute'] ['id-header']   (plink2.cc:9178-9226)
       if (!need(1, 5)) return Usage("--make-grm-sparse requires a relationship cutoff.");
@@ -497,7 +502,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -1058,16 +1063,11 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     }
     kinship_col = k;
   }
-  // ---- sample lookup: FID<tab>IID when the file has FID columns, IID alone otherwise
+  // ---- sample lookup by FID<tab>IID.  A file without FID columns reads every ID with FID 0 (XidRead,
+  // plink2_common.cc:1280-1284), so it only names samples whose own FID is 0 - the reference's behaviour, kept as is
   std::unordered_map<std::string, uint32_t> lookup;
   lookup.reserve(static_cast<size_t>(n) * 2);
-  for (uint32_t k = 0; k < n; ++k) {
-    const std::string key = fid_present ? (S.fid[k] + "\t" + S.iid[k]) : S.iid[k];
-    if (!lookup.emplace(key, k).second && !fid_present) {
-      logprintf("Error: Duplicate sample ID '%s' (the --king-table-subset file has no FID columns).\n", key.c_str());
-      return kRetInconsistentInput;
-    }
-  }
+  for (uint32_t k = 0; k < n; ++k) lookup.emplace(S.fid[k] + "\t" + S.iid[k], k);
   for (size_t li = 1; li < lines.size(); ++li) {
     const std::vector<std::string> f = SplitWs(lines[li]);
     if (f.empty()) continue;
@@ -1076,10 +1076,10 @@ int RunKingSubset(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       return kRetMalformedInput;
     }
     size_t q = 0;
-    std::string k1 = fid_present ? (f[q] + "\t" + f[q + 1]) : f[q];
+    std::string k1 = fid_present ? (f[q] + "\t" + f[q + 1]) : ("0\t" + f[q]);
     q += fid_present ? 2 : 1;
     if (sid_cols) ++q;
-    std::string k2 = fid_present ? (f[q] + "\t" + f[q + 1]) : f[q];
+    std::string k2 = fid_present ? (f[q] + "\t" + f[q + 1]) : ("0\t" + f[q]);
     const auto i1 = lookup.find(k1), i2 = lookup.find(k2);
     if (i1 == lookup.end() || i2 == lookup.end()) continue;  // not loaded: skipped silently, as in the reference
     if (i1->second == i2->second) {
@@ -1616,15 +1616,15 @@ int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
   }
   const bool use_sid = sid_col && S.sid_present;
   auto key = [&](const std::string& fid, const std::string& iid, const std::string& sid) {
-    std::string k = fid_present ? (fid + "\t" + iid) : iid;
+    std::string k = (fid_present ? fid : std::string("0")) + "\t" + iid;  // no FID column: FID 0 (XidRead, plink2_common.cc:1280)
     if (use_sid) k += "\t" + sid;
     return k;
   };
-  // without a FID column only IID (and SID) identify a sample; ambiguous keys never match, like a failed xid lookup
+  // a file without FID columns therefore only names samples whose own FID is 0, as in the reference
   std::unordered_map<std::string, int64_t> by_key;
   by_key.reserve(static_cast<size_t>(n) * 2);
   for (uint32_t k = 0; k < n; ++k) {
-    auto ins = by_key.emplace(key(S.fid[k], S.iid[k], S.sid[k]), k);
+    auto ins = by_key.emplace(S.fid[k] + "\t" + S.iid[k] + (use_sid ? "\t" + S.sid[k] : std::string()), k);
     if (!ins.second) ins.first->second = -1;
   }
   const uint32_t wl = (n + 63) / 64;
@@ -1669,6 +1669,153 @@ int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
   const std::string in_name = c.out + ".king.cutoff.in.id", out_name = c.out + ".king.cutoff.out.id";
   if (!WriteIdFile(in_name, S, in, true) || !WriteIdFile(out_name, S, out, true)) return kRetWriteFail;
   logprintf("--king-cutoff-table: Excluded sample ID%s written to %s , and %u remaining sample ID%s written to %s .\n", out.size() == 1 ? "" : "s", out_name.c_str(), static_cast<uint32_t>(in.size()), in.size() == 1 ? "" : "s", in_name.c_str());
+  return 0;
+}
+
+// --king-cutoff <prefix> <threshold> (KingCutoffBatchBinary, 2.0/plink2_matrix_calc.cc:393-640): the relatedness
+// prune driven by a matrix written earlier with `--make-king bin[4] triangle`.  <prefix>.king.id names the matrix rows
+// (header #FID IID [SID] / #IID [SID], or headerless FID IID / IID lines).  Like the reference, lines whose ID is not
+// loaded are dropped BEFORE rows are numbered (:441-460), so the .bin file has to be exactly the triangle over the
+// matched IDs - in practice every listed ID must be loaded; loaded samples absent from the file carry no constraint.
+// A file without a FID column only matches samples whose FID is 0 (XidRead, plink2_common.cc:1280-1284).
+// <prefix>.king.bin holds row i's i leading entries,
+// fp64 when the file size says so, else fp32 (compared against the threshold rounded to fp32, :566); a square file is
+// refused.  Host-only in the reference too.
+int RunKingCutoffBinary(const Cmd& c, Dataset* ds) {
+  const SampleInfo& S = ds->samples;
+  const uint32_t n = S.size();
+  const std::string id_name = c.king_cutoff_prefix + ".king.id", bin_name = c.king_cutoff_prefix + ".king.bin";
+  std::vector<std::string> lines;
+  std::string err;
+  if (!ReadLines(id_name, &lines, &err)) {
+    logprintf("Error: %s\n", err.c_str());
+    return kRetOpenFail;
+  }
+  size_t li = 0;
+  auto is_id_header = [](const std::string& l) { return l.compare(0, 4, "#FID") == 0 || l.compare(0, 4, "#IID") == 0; };
+  while (li < lines.size() && (lines[li].empty() || (lines[li][0] == '#' && !is_id_header(lines[li])))) ++li;
+  if (li == lines.size()) {
+    logprintf("Error: Empty --king-cutoff ID file.\n");
+    return kRetMalformedInput;
+  }
+  bool fid_col = true, sid_col = false, one_or_two = false;
+  if (lines[li][0] == '#') {
+    const std::vector<std::string> h = SplitWs(lines[li].substr(1));
+    size_t t = 0;
+    fid_col = h[0] == "FID";
+    if (fid_col) ++t;
+    if (t >= h.size() || h[t] != "IID") {
+      logprintf("Error: No IID column on line %zu of --king-cutoff file.\n", li + 1);
+      return kRetMalformedInput;
+    }
+    ++t;
+    sid_col = t < h.size() && h[t] == "SID";
+    ++li;
+  } else {
+    one_or_two = true;  // headerless: "FID IID" lines, or a lone IID (then FID is 0)
+  }
+  const bool use_sid = sid_col && S.sid_present;
+  auto key = [&](const std::string& fid, const std::string& iid, const std::string& sid) {
+    std::string k = (fid.empty() ? std::string("0") : fid) + "\t" + iid;
+    if (use_sid) k += "\t" + sid;
+    return k;
+  };
+  std::unordered_map<std::string, int64_t> by_key;
+  by_key.reserve(static_cast<size_t>(n) * 2);
+  for (uint32_t k = 0; k < n; ++k) {
+    auto ins = by_key.emplace(key(S.fid[k], S.iid[k], S.sid[k]), k);
+    if (!ins.second) ins.first->second = -1;
+  }
+  // king_to_sample[row of the matrix] = loaded sample index
+  std::vector<int64_t> king_to_sample;
+  std::vector<uint8_t> seen(n, 0);
+  for (; li < lines.size(); ++li) {
+    if (lines[li].empty()) continue;
+    const std::vector<std::string> t = SplitWs(lines[li]);
+    const size_t want = (fid_col && !one_or_two ? 2 : 1) + (sid_col ? 1 : 0);
+    if (t.size() < want) {
+      logprintf("Error: Fewer tokens than expected on line %zu of %s .\n", li + 1, id_name.c_str());
+      return kRetMalformedInput;
+    }
+    size_t q = 0;
+    std::string fid, iid, sid;
+    if (one_or_two) {
+      if (t.size() >= 2) {
+        fid = t[0];
+        iid = t[1];
+      } else {
+        fid = "0";
+        iid = t[0];
+      }
+    } else {
+      if (fid_col) fid = t[q++];
+      iid = t[q++];
+      if (sid_col) sid = t[q++];
+    }
+    const auto it = by_key.find(key(fid, iid, sid));
+    if (it == by_key.end() || it->second < 0) continue;
+    if (seen[it->second]) {
+      logprintf("Error: Duplicate sample ID \"%s %s\" in %s .\n", fid.empty() ? "0" : fid.c_str(), iid.c_str(), id_name.c_str());
+      return kRetMalformedInput;
+    }
+    seen[it->second] = 1;
+    king_to_sample.push_back(it->second);
+  }
+  const uint64_t kn = king_to_sample.size();
+  FILE* f = fopen(bin_name.c_str(), "rb");
+  if (!f) {
+    logprintf("Error: Failed to open %s : %s.\n", bin_name.c_str(), strerror(errno));
+    return kRetOpenFail;
+  }
+  struct Closer {
+    FILE* f;
+    ~Closer() { fclose(f); }
+  } closer{f};
+  if (fseeko(f, 0, SEEK_END)) return kRetReadFail;
+  const uint64_t fsize = static_cast<uint64_t>(ftello(f));
+  const uint64_t tri = kn ? kn * (kn - 1) / 2 : 0;
+  const bool is_double = fsize == tri * 8;
+  if (!is_double && fsize != tri * 4) {
+    if (fsize == kn * kn * 8 || fsize == kn * kn * 4) {
+      logprintf("Error: --king-cutoff currently requires a *triangular* .bin file; the provided\nfile appears to be square.\n");
+    } else {
+      logprintf("Error: Invalid --king-cutoff .bin file size (expected %llu or %llu bytes).\n", static_cast<unsigned long long>(tri * 4), static_cast<unsigned long long>(tri * 8));
+    }
+    return kRetMalformedInput;
+  }
+  const uint32_t wl = (n + 63) / 64;
+  std::vector<uint64_t> table(static_cast<uint64_t>(n) * wl, 0);
+  const uint32_t esz = is_double ? 8 : 4;
+  const float thresh_f = static_cast<float>(c.king_cutoff_prefix_thresh);
+  const double thresh_d = c.king_cutoff_prefix_thresh;
+  std::vector<unsigned char> row(kn * esz + 8);
+  uint64_t constraint_ct = 0;
+  rewind(f);
+  for (uint64_t i = 1; i < kn; ++i) {
+    if (fread(row.data(), i * esz, 1, f) != 1) {
+      logprintf("Error: %s read failure.\n", bin_name.c_str());
+      return kRetReadFail;
+    }
+    const uint64_t si = static_cast<uint64_t>(king_to_sample[i]);
+    const float* rf = reinterpret_cast<const float*>(row.data());
+    const double* rd = reinterpret_cast<const double*>(row.data());
+    for (uint64_t j = 0; j < i; ++j) {
+      if (is_double ? (rd[j] > thresh_d) : (rf[j] > thresh_f)) {
+        const uint64_t sj = static_cast<uint64_t>(king_to_sample[j]);
+        table[si * wl + sj / 64] |= 1ull << (sj % 64);
+        table[sj * wl + si / 64] |= 1ull << (si % 64);
+        ++constraint_ct;
+      }
+    }
+  }
+  logprintf("--king-cutoff: %llu constraint%s loaded.\n", static_cast<unsigned long long>(constraint_ct), constraint_ct == 1 ? "" : "s");
+  std::vector<uint8_t> removed;
+  KinshipPrune(&table, n, &removed);
+  std::vector<uint32_t> in, out;
+  for (uint32_t k = 0; k < n; ++k) (removed[k] ? out : in).push_back(k);
+  const std::string in_name = c.out + ".king.cutoff.in.id", out_name = c.out + ".king.cutoff.out.id";
+  if (!WriteIdFile(in_name, S, in, true) || !WriteIdFile(out_name, S, out, true)) return kRetWriteFail;
+  logprintf("--king-cutoff: Excluded sample ID%s written to %s , and %u remaining sample ID%s written to %s .\n", out.size() == 1 ? "" : "s", out_name.c_str(), static_cast<uint32_t>(in.size()), in.size() == 1 ? "" : "s", in_name.c_str());
   return 0;
 }
 
@@ -2628,14 +2775,14 @@ int RunVscore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     return kRetMalformedInput;
   }
   auto key = [&](const std::string& fid, const std::string& iid, const std::string& sid) {
-    std::string k = fid_col ? (fid + "\t" + iid) : iid;
+    std::string k = (fid_col ? fid : std::string("0")) + "\t" + iid;  // no FID column: FID 0 (XidRead, plink2_common.cc:1280)
     if (sid_col && S.sid_present) k += "\t" + sid;
     return k;
   };
   std::unordered_map<std::string, int64_t> by_key;
   by_key.reserve(static_cast<size_t>(n) * 2);
   for (uint32_t k = 0; k < n; ++k) {
-    auto ins = by_key.emplace(key(S.fid[k], S.iid[k], S.sid[k]), k);
+    auto ins = by_key.emplace(S.fid[k] + "\t" + S.iid[k] + ((sid_col && S.sid_present) ? "\t" + S.sid[k] : std::string()), k);
     if (!ins.second) ins.first->second = -1;
   }
   std::vector<double> w(static_cast<uint64_t>(n) * cols, 0.0);
@@ -3137,7 +3284,7 @@ int main(int argc, char** argv) {
   if (rc) return rc;
   // CUDA initialisation (0.5 - 3 s on a cold box) runs beside the loading of the sample / variant files; commands that
   // need no device (--king-cutoff-table on its own) never start it
-  const bool needs_gpu = c.king_cutoff_table.empty();
+  const bool needs_gpu = c.king_cutoff_table.empty() && c.king_cutoff_prefix.empty();
   Pl2GpuCtx* ctx = nullptr;
   int ctx_rc = 0;
   std::string ctx_err;
@@ -3174,17 +3321,17 @@ int main(int argc, char** argv) {
     if (rc) return rc;
   }
   g_clock.Mark("load .psam/.pvar, open .pgen");
-  if (!c.king_cutoff_table.empty()) {
-    if (c.king_cutoff >= 0) {
+  if (!c.king_cutoff_table.empty() || !c.king_cutoff_prefix.empty()) {
+    if (!c.king_cutoff_table.empty() && (c.king_cutoff >= 0 || !c.king_cutoff_prefix.empty())) {
       logprintf("Error: --king-cutoff cannot be used with --king-cutoff-table.\n");
       return kRetInvalidCmdline;
     }
-    rc = RunKingCutoffTable(c, &ds);
+    rc = c.king_cutoff_table.empty() ? RunKingCutoffBinary(c, &ds) : RunKingCutoffTable(c, &ds);
     if (rc) return rc;
     if (!(c.freq || c.make_king || c.make_king_table || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise)) {
       return 0;  // table-driven pruning is host-only in the reference as well: no device is needed for it
     }
-    logprintf("Error: chaining --king-cutoff-table sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
+    logprintf("Error: chaining file-driven --king-cutoff[-table] sample removal into later commands is not supported by plink2_b200.\n");
     return kRetNotYetSupported;
   }
   g_decode_threads = EffectiveHostThreads(c.threads);

@@ -82,6 +82,15 @@ cp $T/a_vs.vscore a_vs.vscore; cp $T/a_vsf.vscore a_vs_altfreq.vscore
 # --king-cutoff-table on the proportion table written above
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --threads 2 --out $T/a_kct > /dev/null
 cp $T/a_kct.king.cutoff.in.id a_kct.king.cutoff.in.id; cp $T/a_kct.king.cutoff.out.id a_kct.king.cutoff.out.id
+# --king-cutoff <prefix> <threshold>: (1) the fp32 triangle written above (a_king.king.bin + a_kingsq.king.id),
+# (2) an fp64 triangle over a shuffled 80-ID subset with unknown IDs mixed in (make_king_cutoff_set.py)
+cp a_king.king.bin $T/kc4.king.bin; cp a_kingsq.king.id $T/kc4.king.id
+$P --bfile a --king-cutoff $T/kc4 0.02 --threads 2 --out $T/a_kc4 > /dev/null
+cp $T/a_kc4.king.cutoff.in.id a_kc4.king.cutoff.in.id; cp $T/a_kc4.king.cutoff.out.id a_kc4.king.cutoff.out.id
+$P --bfile a --make-king bin triangle --threads 2 --out $T/k8 > /dev/null
+python make_king_cutoff_set.py $T/k8.king.bin $T/k8.king.id a_kc8
+$P --bfile a --king-cutoff a_kc8 0.03 --threads 2 --out $T/a_kc8o > /dev/null
+cp $T/a_kc8o.king.cutoff.in.id a_kc8.king.cutoff.in.id; cp $T/a_kc8o.king.cutoff.out.id a_kc8.king.cutoff.out.id
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null

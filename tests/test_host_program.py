@@ -231,6 +231,45 @@ def test_king_cutoff_table_matches_reference_lists(tmp_path):
     assert "661 constraints loaded" in r.stdout
     for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):
         assert open(out + ext, "rb").read() == open(os.path.join(gd, "a_kct" + ext), "rb").read()
+    # set R has real FIDs.  A table without FID columns reads its IDs with FID 0 (XidRead, plink2_common.cc:1280), so it
+    # names nobody there: the reference loads 0 constraints from the first table and 1 from the second (checked here).
+    (tmp_path / "iid.kin0").write_text("#IID1\tIID2\tKINSHIP\n9\tp\t0.4\n")
+    (tmp_path / "fid.kin0").write_text("#FID1\tIID1\tFID2\tIID2\tKINSHIP\nF1\t9\tF1\tp\t0.4\n")
+    for name, want in (("iid.kin0", "0 constraints loaded"), ("fid.kin0", "1 constraint loaded")):
+        r = subprocess.run([BIN, "--bfile", os.path.join(gd, "r"), "--king-cutoff-table", str(tmp_path / name), "0.1", "--out", out], capture_output=True, text=True)
+        assert r.returncode == 0 and want in r.stdout, r.stdout + r.stderr
+
+
+def test_king_cutoff_matrix_prefix_matches_reference_lists(tmp_path):
+    """`--king-cutoff <prefix> <threshold>` (KingCutoffBatchBinary, 2.0/plink2_matrix_calc.cc:393): (1) the reference's
+    fp32 triangle over set A - 661 constraints against the threshold rounded to fp32, where the fp64 matrix gives 662;
+    (2) an fp64 triangle over a shuffled 80-ID subset whose ID file also lists three unknown samples.  Host-only work:
+    lists byte-identical to the reference's, no GPU needed.  A square matrix and an IID-only ID file on a FID-bearing
+    dataset fail the way the reference does."""
+    import shutil
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    shutil.copy(os.path.join(gd, "a_king.king.bin"), tmp_path / "kc4.king.bin")
+    shutil.copy(os.path.join(gd, "a_kingsq.king.id"), tmp_path / "kc4.king.id")
+    for prefix, thr, want, gold in ((str(tmp_path / "kc4"), "0.02", "661 constraints", "a_kc4"), (os.path.join(gd, "a_kc8"), "0.03", "250 constraints", "a_kc8")):
+        out = str(tmp_path / ("o_" + gold))
+        r = subprocess.run([BIN, "--bfile", os.path.join(gd, "a"), "--king-cutoff", prefix, thr, "--out", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert want + " loaded" in r.stdout
+        for ext in (".king.cutoff.in.id", ".king.cutoff.out.id"):
+            assert open(out + ext, "rb").read() == open(os.path.join(gd, gold + ext), "rb").read()
+    # square matrix: refused
+    n = 100
+    (tmp_path / "sq.king.bin").write_bytes(b"\0" * (4 * n * n))
+    shutil.copy(os.path.join(gd, "a_kingsq.king.id"), tmp_path / "sq.king.id")
+    r = subprocess.run([BIN, "--bfile", os.path.join(gd, "a"), "--king-cutoff", str(tmp_path / "sq"), "0.1", "--out", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode != 0 and "appears to be square" in r.stdout + r.stderr
+    # set R carries real FIDs: an ID file without a FID column reads every ID with FID 0 and matches nothing
+    fam = [l.split() for l in open(os.path.join(gd, "r.fam"))]
+    (tmp_path / "r.king.id").write_text("#IID\n" + "".join(f[1] + "\n" for f in fam))
+    (tmp_path / "r.king.bin").write_bytes(b"\0" * (4 * len(fam) * (len(fam) - 1) // 2))
+    r = subprocess.run([BIN, "--bfile", os.path.join(gd, "r"), "--king-cutoff", str(tmp_path / "r"), "0.1", "--out", str(tmp_path / "x")], capture_output=True, text=True)
+    assert r.returncode != 0 and "expected 0 or 0 bytes" in r.stdout + r.stderr
 
 
 def test_natural_sort_matches_reference_order(tmp_path):
