@@ -7,8 +7,6 @@
 
 namespace pl2host {
 
-namespace {
-
 // human chromosome codes (the reference's default chr-set): 1-22, X=23, Y=24, XY=25, MT=26, 0 unplaced
 bool ParseChr(const std::string& tok, uint32_t* code) {
   const char* s = tok.c_str();
@@ -31,7 +29,17 @@ bool ParseChr(const std::string& tok, uint32_t* code) {
   return true;
 }
 
-}  // namespace
+std::string ChrNameOut(uint32_t code, const std::string& as_read) {
+  if (code <= 22) return std::to_string(code);
+  if (code == 23) return "X";
+  if (code == 24) return "Y";
+  if (code == 26) return "MT";
+  std::string u = as_read;
+  if (u.size() > 3 && (u[0] == 'c' || u[0] == 'C') && (u[1] == 'h' || u[1] == 'H') && (u[2] == 'r' || u[2] == 'R')) u = u.substr(3);
+  for (auto& ch : u) ch = static_cast<char>(toupper(ch));
+  if (u == "PAR1" || u == "PAR2") return u;
+  return "XY";
+}
 
 bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
   std::vector<std::string> lines;
@@ -84,6 +92,8 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
     out->fid.push_back(col_fid >= 0 ? t[col_fid] : "0");
     out->iid.push_back(t[col_iid]);
     out->sid.push_back(col_sid >= 0 ? t[col_sid] : "0");
+    out->pat.push_back(col_pat >= 0 ? t[col_pat] : "0");
+    out->mat.push_back(col_mat >= 0 ? t[col_mat] : "0");
     const bool founder = (col_pat < 0 || t[col_pat] == "0") && (col_mat < 0 || t[col_mat] == "0");
     out->is_founder.push_back(founder ? 1 : 0);
     // SEX: '1'/'M'/'m' male, '2'/'F'/'f' female, anything else unknown (plink2_psam.cc:609-623)
@@ -108,7 +118,7 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
   if (!ReadLines(path, &lines, err)) return false;
   size_t li = 0;
   while (li < lines.size() && lines[li].size() >= 2 && lines[li][0] == '#' && lines[li][1] == '#') ++li;
-  int col_chr, col_pos, col_id, col_ref = -1, col_alt = -1;
+  int col_chr, col_pos, col_id, col_ref = -1, col_alt = -1, col_cm = -1;
   bool is_bim = false;
   if (li < lines.size() && !lines[li].empty() && lines[li][0] == '#') {
     // .pvar header: #CHROM POS ID REF ALT ...
@@ -120,6 +130,7 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
       else if (hdr[c] == "ID") col_id = static_cast<int>(c);
       else if (hdr[c] == "REF") col_ref = static_cast<int>(c);
       else if (hdr[c] == "ALT") col_alt = static_cast<int>(c);
+      else if (hdr[c] == "CM") col_cm = static_cast<int>(c);
     }
     if (col_chr != 0 || col_pos < 0 || col_id < 0) {
       *err = "Invalid .pvar header line in " + path + ".";
@@ -133,14 +144,16 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     col_pos = 3;
     col_alt = 4;
     col_ref = 5;
+    col_cm = 2;
     is_bim = true;
   }
   for (; li < lines.size(); ++li) {
     if (lines[li].empty()) continue;
     std::vector<std::string> t = SplitWs(lines[li]);
     if (t.empty()) continue;
-    int cpos = col_pos, cref = col_ref, calt = col_alt;
+    int cpos = col_pos, cref = col_ref, calt = col_alt, ccm = col_cm;
     if (is_bim && t.size() == 5) {
+      ccm = -1;
       cpos = 2;
       calt = 3;
       cref = 4;
@@ -160,6 +173,7 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     out->chr_name.push_back(t[col_chr]);
     out->ref.push_back(cref >= 0 && cref < static_cast<int>(t.size()) ? t[cref] : std::string("."));
     out->alt.push_back(calt >= 0 && calt < static_cast<int>(t.size()) ? t[calt] : std::string("."));
+    if (col_cm >= 0) out->cm.push_back(ccm >= 0 && ccm < static_cast<int>(t.size()) ? t[ccm] : std::string("0"));
   }
   return true;
 }

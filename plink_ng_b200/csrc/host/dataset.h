@@ -13,12 +13,14 @@ namespace pl2host {
 
 struct SampleInfo {
   std::vector<std::string> fid, iid, sid;
+  std::vector<std::string> pat, mat;  // parental IDs as written ("0" when the column is absent)
   std::vector<uint8_t> is_founder;
   std::vector<uint8_t> sex;  // 0 unknown, 1 male, 2 female (.fam column 5 / .psam SEX)
   // phenotype columns as read (.fam column 6 = PHENO1; .psam: every column that is not an ID / parent / SEX column);
   // typed when written (binary / quantitative / categorical, LoadPsam plink2_psam.cc:58)
   std::vector<std::string> pheno_names;
   std::vector<std::vector<std::string>> pheno_tokens;  // [phenotype][sample]
+  std::vector<std::string> fam_pheno;  // .fam column 6 as --make-bed writes it (typed over all loaded samples); empty: all -9
   bool fid_present = false;  // kfSampleIdFidPresent (plink2_psam.cc:104-130, :279, :823)
   bool sid_present = false;
   uint32_t size() const { return static_cast<uint32_t>(iid.size()); }
@@ -29,10 +31,16 @@ struct VariantInfo {
   std::vector<uint32_t> bp;
   std::vector<std::string> id;
   std::vector<std::string> chr_name, ref, alt;  // as written in the file (.bim: REF = column 6, ALT = column 5)
+  std::vector<std::string> cm;                  // centimorgan token (.bim column 3 / .pvar CM column); empty: no such column
   bool provisional_ref = false;                 // .bim input: REF alleles are provisional (PROVISIONAL_REF? = Y)
   uint32_t size() const { return static_cast<uint32_t>(id.size()); }
 };
 
+// chromosome token -> code (optional chr prefix, case-insensitive X / Y / XY / PAR1 / PAR2 / MT / M, 0..26)
+bool ParseChr(const std::string& tok, uint32_t* code);
+// Chromosome as the reference prints it under its default output encoding (kfChrOutputMT; chrtoa / ChrNameStd,
+// 2.0/plink2_common.cc:2150-2227): bare number for autosomes, X / Y / XY / MT, PAR1 / PAR2 kept.
+std::string ChrNameOut(uint32_t code, const std::string& as_read);
 bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err);
 bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err);
 
@@ -47,6 +55,9 @@ struct Dataset {
   VariantInfo variants;
   PgenReader reader;
   std::vector<double> read_ref_freq;  // --read-freq: loaded REF frequency per variant, NaN = not loaded (empty: flag absent)
+  // raw index of every kept sample / variant once a filter ran (empty: nothing filtered); `samples`, `variants` and
+  // the reader's view are always compacted together (filters.cc)
+  std::vector<uint32_t> sample_raw, variant_raw;
 };
 
 }  // namespace pl2host

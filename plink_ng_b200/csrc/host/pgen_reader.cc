@@ -340,14 +340,56 @@ bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std
   return true;
 }
 
-bool PgenReader::Get(uint32_t vidx, uint64_t* genovec, std::string* err) { return DecodeRecord(&state_, vidx, genovec, err); }
-
-bool PgenReader::GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) {
-  return GetSubsetWith(&state_, vidx, sample_include, sample_ct, genovec, err);
+void PgenReader::SetView(std::vector<uint32_t> variant_map, std::vector<uint64_t> sample_keep, uint32_t kept_sample_ct) {
+  vmap_ = std::move(variant_map);
+  sample_keep_ = std::move(sample_keep);
+  view_sample_ct_ = sample_keep_.empty() ? raw_sample_ct_ : kept_sample_ct;
 }
 
-bool PgenReader::GetBlock(const uint32_t* vidx, uint32_t count, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* dst, uint64_t stride_words, uint32_t thread_ct, std::string* err) {
+const uint64_t* PgenReader::RawInclude(const uint64_t* view_include, uint32_t* sample_ct, std::vector<uint64_t>* scratch) const {
+  if (sample_keep_.empty()) return view_include;
+  if (!view_include) {
+    *sample_ct = view_sample_ct_;
+    return sample_keep_.data();
+  }
+  // bit k of view_include belongs to the k-th set bit of sample_keep_: deposit 64 raw samples at a time
+  scratch->assign(sample_keep_.size(), 0);
+  uint64_t pos = 0;  // view bits consumed
+  for (size_t w = 0; w < sample_keep_.size(); ++w) {
+    const uint64_t keep = sample_keep_[w];
+    const uint32_t cnt = static_cast<uint32_t>(__builtin_popcountll(keep));
+    if (!cnt) continue;
+    const uint32_t sh = static_cast<uint32_t>(pos & 63);
+    uint64_t bits = view_include[pos >> 6] >> sh;
+    if (sh && sh + cnt > 64) bits |= view_include[(pos >> 6) + 1] << (64 - sh);
+    (*scratch)[w] = _pdep_u64(bits, keep);
+    pos += cnt;
+  }
+  return scratch->data();
+}
+
+bool PgenReader::Get(uint32_t vidx, uint64_t* genovec, std::string* err) {
+  if (sample_keep_.empty()) return DecodeRecord(&state_, RawV(vidx), genovec, err);
+  return GetSubsetWith(&state_, RawV(vidx), sample_keep_.data(), view_sample_ct_, genovec, err);
+}
+
+bool PgenReader::GetSubset(uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) {
+  std::vector<uint64_t> scratch;
+  const uint64_t* raw_include = RawInclude(sample_include, &sample_ct, &scratch);
+  return GetSubsetWith(&state_, RawV(vidx), raw_include, sample_ct, genovec, err);
+}
+
+bool PgenReader::GetBlock(const uint32_t* view_vidx, uint32_t count, const uint64_t* view_include, uint32_t sample_ct, uint64_t* dst, uint64_t stride_words, uint32_t thread_ct, std::string* err) {
   if (!count) return true;
+  std::vector<uint64_t> include_scratch;
+  std::vector<uint32_t> raw_vidx;
+  const uint64_t* sample_include = RawInclude(view_include, &sample_ct, &include_scratch);
+  const uint32_t* vidx = view_vidx;
+  if (!vmap_.empty()) {
+    raw_vidx.resize(count);
+    for (uint32_t k = 0; k < count; ++k) raw_vidx[k] = vmap_[view_vidx[k]];
+    vidx = raw_vidx.data();
+  }
   thread_ct = std::max(1u, std::min(thread_ct, (count + 255) / 256));  // at least 256 variants per worker
   if (thread_ct == 1) {
     for (uint32_t k = 0; k < count; ++k) {

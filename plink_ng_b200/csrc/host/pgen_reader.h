@@ -30,6 +30,14 @@ class PgenReader {
   // uint64 words per variant for n samples: ceil(n / 32)
   static uint32_t WordsFor(uint32_t n) { return (n + 31) / 32; }
 
+  // Filtered view (the role of the variant_include / sample_include bitsets every reference command receives after
+  // the --extract / --chr / --keep / ... filters ran, 2.0/plink2.cc:1423-1665): once set, variant indices passed to
+  // Get / GetSubset / GetBlock are positions in `variant_map` (empty = identity) and sample counts / sample_include
+  // bitsets are over the kept samples (`sample_keep` = bitset over raw samples, empty = all).  Callers compact their
+  // sample / variant tables the same way and never see raw indices again.
+  void SetView(std::vector<uint32_t> variant_map, std::vector<uint64_t> sample_keep, uint32_t kept_sample_ct);
+  uint32_t view_sample_ct() const { return view_sample_ct_; }
+
   // PgrGet without subsetting: all raw samples of variant `vidx` into genovec[WordsFor(raw_sample_ct)].
   // Codes 0 hom-REF, 1 het, 2 hom-ALT, 3 missing; trailing entries of the last word are zero.
   bool Get(uint32_t vidx, uint64_t* genovec, std::string* err);
@@ -65,6 +73,13 @@ class PgenReader {
   std::vector<uint8_t> vrtypes_;  // mode 0x10
   std::vector<uint64_t> rec_off_; // mode 0x10: [raw_variant_ct + 1]
   DecodeState state_;             // used by Get / GetSubset (single-threaded callers)
+  // filtered view
+  std::vector<uint32_t> vmap_;         // view variant index -> raw variant index (empty: identity)
+  std::vector<uint64_t> sample_keep_;  // raw-sample bitset of the view (empty: all samples)
+  uint32_t view_sample_ct_ = 0;
+  uint32_t RawV(uint32_t v) const { return vmap_.empty() ? v : vmap_[v]; }
+  // view-space include (nullptr = every kept sample) -> raw-space include, or nullptr when that is "all raw samples"
+  const uint64_t* RawInclude(const uint64_t* view_include, uint32_t* sample_ct, std::vector<uint64_t>* scratch) const;
 };
 
 }  // namespace pl2host

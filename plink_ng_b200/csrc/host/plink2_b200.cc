@@ -28,6 +28,7 @@
 
 #include "../../../include/plink2_b200.h"
 #include "dataset.h"
+#include "filters.h"
 #include "pca.h"
 #include "sfmt.h"
 #include "text_util.h"
@@ -95,6 +96,9 @@ struct Cmd {
   bool vscore_zs = false, vs_chrom = true, vs_pos = true, vs_ref = true, vs_alt = true, vs_maybeprovref = true, vs_provref = false, vs_altfreq = false;
   std::string king_cutoff_table;          // --king-cutoff-table <.kin0 file> <threshold>
   double king_cutoff_table_thresh = -1;
+  FilterSpec filters;                     // --keep / --remove / --keep-fam / --remove-fam / --extract / --exclude / --chr / --not-chr / --autosome[-xy]
+  bool make_bed = false;                  // --make-bed: the filtered view as .bed/.bim/.fam (host-only)
+  bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
   std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
   double king_cutoff_prefix_thresh = -1;
   std::string king_table_subset;          // --king-table-subset <file> [kinship threshold]
@@ -410,6 +414,24 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
           return Usage(("--variant-score modifier '" + m + "' is not supported by plink2_b200 (supported: zs, cols=).").c_str());
         }
       }
+    } else if (flag == "--keep" || flag == "--remove" || flag == "--keep-fam" || flag == "--remove-fam" || flag == "--extract" || flag == "--exclude") {
+      // plink2.cc:7624, :10813, :5618, :5672: one or more files each
+      if (nparam < 1) return Usage((flag + " requires at least one filename.").c_str());
+      std::vector<std::string>& dst = flag == "--keep" ? c->filters.keep : flag == "--remove" ? c->filters.remove : flag == "--keep-fam" ? c->filters.keep_fam : flag == "--remove-fam" ? c->filters.remove_fam : flag == "--extract" ? c->filters.extract : c->filters.exclude;
+      if ((flag == "--extract" || flag == "--exclude") && (!strcmp(prm[0], "range") || !strcmp(prm[0], "bed0") || !strcmp(prm[0], "bed1")) && nparam > 1) return Usage((flag + " " + prm[0] + " (positional ranges) is not supported by plink2_b200; list variant IDs instead.").c_str());
+      for (int k = 0; k < nparam; ++k) dst.push_back(prm[k]);
+    } else if (flag == "--chr" || flag == "--not-chr") {
+      if (nparam < 1) return Usage((flag + " requires at least one chromosome code.").c_str());
+      std::string perr;
+      if (!ParseChrList(std::vector<std::string>(prm, prm + nparam), flag.c_str() + 2, flag == "--chr" ? &c->filters.chr_mask : &c->filters.not_chr_mask, &perr)) return Usage(perr.c_str());
+    } else if (flag == "--autosome" || flag == "--autosome-xy" || flag == "--autosome-par") {
+      if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
+      (flag == "--autosome" ? c->filters.autosome : c->filters.autosome_xy) = true;
+    } else if (flag == "--debug-founders-bed") {
+      c->debug_founders_bed = c->make_bed = true;
+    } else if (flag == "--make-bed") {
+      if (!need(0, 0)) return Usage("--make-bed modifiers are not supported by plink2_b200.");
+      c->make_bed = true;
     } else if (flag == "--king-cutoff-table") {
       // plink2.cc:7665-7700
       if (!need(2, 2)) return Usage("--king-cutoff-table requires a filename and a kinship threshold.");
@@ -502,7 +524,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->make_bed || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -1565,7 +1587,7 @@ int RunKing(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint8_t>* cut
 // driven by a kinship table written earlier (.kin0: [#FID1] ID1|IID1 [SID1] [FID2] ID2|IID2 [SID2] ... KINSHIP).  Pairs
 // whose kinship exceeds threshold (1 + 2^-44) become constraints; unknown IDs and non-numeric kinship cells are
 // skipped.  Host-only work in the reference too - no device involved.
-int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
+int RunKingCutoffTable(const Cmd& c, Dataset* ds, std::vector<uint8_t>* removed_out) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
   std::vector<std::string> lines;
@@ -1662,7 +1684,7 @@ int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
     }
   }
   logprintf("--king-cutoff-table: %llu constraint%s loaded.\n", static_cast<unsigned long long>(constraint_ct), constraint_ct == 1 ? "" : "s");
-  std::vector<uint8_t> removed;
+  std::vector<uint8_t>& removed = *removed_out;
   KinshipPrune(&table, n, &removed);
   std::vector<uint32_t> in, out;
   for (uint32_t k = 0; k < n; ++k) (removed[k] ? out : in).push_back(k);
@@ -1681,7 +1703,7 @@ int RunKingCutoffTable(const Cmd& c, Dataset* ds) {
 // <prefix>.king.bin holds row i's i leading entries,
 // fp64 when the file size says so, else fp32 (compared against the threshold rounded to fp32, :566); a square file is
 // refused.  Host-only in the reference too.
-int RunKingCutoffBinary(const Cmd& c, Dataset* ds) {
+int RunKingCutoffBinary(const Cmd& c, Dataset* ds, std::vector<uint8_t>* removed_out) {
   const SampleInfo& S = ds->samples;
   const uint32_t n = S.size();
   const std::string id_name = c.king_cutoff_prefix + ".king.id", bin_name = c.king_cutoff_prefix + ".king.bin";
@@ -1809,7 +1831,7 @@ int RunKingCutoffBinary(const Cmd& c, Dataset* ds) {
     }
   }
   logprintf("--king-cutoff: %llu constraint%s loaded.\n", static_cast<unsigned long long>(constraint_ct), constraint_ct == 1 ? "" : "s");
-  std::vector<uint8_t> removed;
+  std::vector<uint8_t>& removed = *removed_out;
   KinshipPrune(&table, n, &removed);
   std::vector<uint32_t> in, out;
   for (uint32_t k = 0; k < n; ++k) (removed[k] ? out : in).push_back(k);
@@ -2410,23 +2432,6 @@ int RunPca(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx, Pl2GrmJob* grm_job) {
   return 0;
 }
 
-// --------------------------------------------------------------------------------------- LD prune
-// `--freq` (WriteAlleleFreqs, 2.0/plink2_misc.cc:3573; counts from the LoadAlleleAndGenoCounts pass,
-// 2.0/plink2.cc:2280): founder ALT allele frequencies of biallelic hard calls -> <out>.afreq.
-// Chromosome as the reference prints it under its default output encoding (kfChrOutputMT; chrtoa /
-// ChrNameStd, 2.0/plink2_common.cc:2150-2227): bare number for autosomes, X / Y / XY / MT, PAR1 / PAR2 kept.
-std::string ChrNameOut(uint32_t code, const std::string& as_read) {
-  if (code <= 22) return std::to_string(code);
-  if (code == 23) return "X";
-  if (code == 24) return "Y";
-  if (code == 26) return "MT";
-  std::string u = as_read;
-  if (u.size() > 3 && (u[0] == 'c' || u[0] == 'C') && (u[1] == 'h' || u[1] == 'H') && (u[2] == 'r' || u[2] == 'R')) u = u.substr(3);
-  for (auto& ch : u) ch = static_cast<char>(toupper(ch));
-  if (u == "PAR1" || u == "PAR2") return u;
-  return "XY";
-}
-
 // ---------------------------------------------------------------------------------------- --score
 // One phenotype column as the report prints it (LoadPsam typing, 2.0/plink2_psam.cc:58: every value in
 // {-9, 0, 1, 2, NA} -> case/control with 0 / -9 / NA missing; other numbers -> quantitative with -9 / NA missing;
@@ -2435,6 +2440,7 @@ std::string ChrNameOut(uint32_t code, const std::string& as_read) {
 struct PhenoOut {
   std::string name;
   std::vector<std::string> text;  // per sample
+  bool categorical = false;
 };
 bool TypePheno(const std::string& name, const std::vector<std::string>& tok, PhenoOut* out) {
   const size_t n = tok.size();
@@ -2456,6 +2462,7 @@ bool TypePheno(const std::string& name, const std::vector<std::string>& tok, Phe
     if (!(d == -9 || d == 0 || d == 1 || d == 2)) binary = false;
   }
   out->name = name;
+  out->categorical = !numeric;
   out->text.assign(n, "NA");
   bool any = false;
   char buf[32];
@@ -2915,7 +2922,11 @@ int RunVscore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
 }
 
 // ---------------------------------------------------------------------------------------- --freq
-int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+// `--freq` (WriteAlleleFreqs, 2.0/plink2_misc.cc:3573; counts from the LoadAlleleAndGenoCounts pass,
+// 2.0/plink2.cc:2280): founder ALT allele frequencies of biallelic hard calls -> <out>.afreq.
+// Founder allele "ddosage" totals per variant, in 1/32768 units as the reference accumulates them: alt_dd[v] / tot_dd[v]
+// is the ALT frequency `--freq` prints and every later command consumes (allele_freqs, plink2.cc:2301).
+int FounderAlleleDosages(Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint64_t>* alt_dd_out, std::vector<uint64_t>* tot_dd_out) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
   const uint32_t n = S.size(), m = V.size();
@@ -2936,12 +2947,8 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     }
   }
   if (!founder_ct) {
-    logprintf("Error: No founders for --freq.\n");
+    logprintf("Error: No founders to estimate allele frequencies from.\n");
     return kRetDegenerateData;
-  }
-  if (ds->reader.nonref_flags_storage() == 3) {
-    logprintf("Error: --freq on a .pgen with per-variant provisional-REF flags is not supported by plink2_b200 yet.\n");
-    return kRetNotYetSupported;
   }
   // genotype counts on the device for a variant list over a sample subset (LoadAlleleAndGenoCountsThread's counting,
   // 2.0/plink2_data.cc:2304): all founders for every variant, founder males for chrX, nonfemale founders for chrY
@@ -2976,10 +2983,8 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   if (!rc) rc = count_pass(xv, inc_male.data(), male_ct, &xmale);
   if (!rc) rc = count_pass(yv, inc_nonfemale.data(), nonfemale_ct, &ynonfemale);
   if (rc) return rc;
-  const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
-  OutFile f;
-  if (!f.Open(name, c.freq_zs)) return kRetOpenFail;
-  f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
+  alt_dd_out->assign(m, 0);
+  tot_dd_out->assign(m, 0);
   size_t xi = 0, yi = 0;
   for (uint32_t v = 0; v < m; ++v) {
     const uint64_t n0 = counts[4ull * v], n1 = counts[4ull * v + 1], n2 = counts[4ull * v + 2], n3 = counts[4ull * v + 3];
@@ -3003,6 +3008,28 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       alt_dd = (n1 + 2 * n2) * 32768ull;
       tot_dd = 2 * (n0 + n1 + n2) * 32768ull;
     }
+    (*alt_dd_out)[v] = alt_dd;
+    (*tot_dd_out)[v] = tot_dd;
+  }
+  return 0;
+}
+
+int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const VariantInfo& V = ds->variants;
+  const uint32_t m = V.size();
+  if (ds->reader.nonref_flags_storage() == 3) {
+    logprintf("Error: --freq on a .pgen with per-variant provisional-REF flags is not supported by plink2_b200 yet.\n");
+    return kRetNotYetSupported;
+  }
+  std::vector<uint64_t> alt_dds, tot_dds;
+  const int rc = FounderAlleleDosages(ds, ctx, &alt_dds, &tot_dds);
+  if (rc) return rc;
+  const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
+  OutFile f;
+  if (!f.Open(name, c.freq_zs)) return kRetOpenFail;
+  f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
+  for (uint32_t v = 0; v < m; ++v) {
+    const uint64_t alt_dd = alt_dds[v], tot_dd = tot_dds[v];
     const double recip = tot_dd ? 1.0 / static_cast<double>(tot_dd) : 0.0;
     char* w = f.Reserve(V.chr_name[v].size() + V.id[v].size() + V.ref[v].size() + V.alt[v].size() + 96);
     auto puts = [&](const std::string& t) {
@@ -3283,8 +3310,10 @@ int main(int argc, char** argv) {
   int rc = ParseArgs(argc, argv, &c);
   if (rc) return rc;
   // CUDA initialisation (0.5 - 3 s on a cold box) runs beside the loading of the sample / variant files; commands that
-  // need no device (--king-cutoff-table on its own) never start it
-  const bool needs_gpu = c.king_cutoff_table.empty() && c.king_cutoff_prefix.empty();
+  // need no device
+  // (file-driven --king-cutoff[-table] and --make-bed on their own) never start it
+  const bool gpu_command = c.freq || c.make_king || c.make_king_table || c.king_cutoff >= 0 || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
+  const bool needs_gpu = gpu_command;
   Pl2GpuCtx* ctx = nullptr;
   int ctx_rc = 0;
   std::string ctx_err;
@@ -3316,23 +3345,84 @@ int main(int argc, char** argv) {
   for (uint8_t f : ds.samples.is_founder) founder_ct += f;
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
   logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
+  {  // .fam phenotype column of --make-bed: the first case/control or quantitative phenotype, typed over all loaded samples
+    for (size_t p = 0; p < ds.samples.pheno_names.size() && ds.samples.fam_pheno.empty(); ++p) {
+      PhenoOut po;
+      if (!TypePheno(ds.samples.pheno_names[p], ds.samples.pheno_tokens[p], &po)) continue;
+      if (po.categorical) continue;  // .fam files don't support categorical phenotypes (WriteFam, plink2_data.cc:1219)
+      for (std::string& t : po.text)
+        if (t == "NA") t = "-9";
+      ds.samples.fam_pheno = std::move(po.text);
+    }
+  }
+  if (c.filters.any()) {
+    std::vector<std::string> flog;
+    const int frc = ApplyFilters(c.filters, &ds, &flog, &err);
+    for (const std::string& l : flog) logprintf("%s\n", l.c_str());
+    if (frc) {
+      logprintf("Error: %s\n", err.c_str());
+      return frc;
+    }
+  }
   if (!c.read_freq.empty()) {
     rc = LoadReadFreq(c, &ds);
     if (rc) return rc;
   }
   g_clock.Mark("load .psam/.pvar, open .pgen");
+  // ---- relatedness prune from a file, then the commands that see its survivors (Plink2Core order, plink2.cc:2523-2581)
+  std::vector<uint8_t> cutoff_removed;
+  const bool later_gpu_command = c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
   if (!c.king_cutoff_table.empty() || !c.king_cutoff_prefix.empty()) {
     if (!c.king_cutoff_table.empty() && (c.king_cutoff >= 0 || !c.king_cutoff_prefix.empty())) {
       logprintf("Error: --king-cutoff cannot be used with --king-cutoff-table.\n");
       return kRetInvalidCmdline;
     }
-    rc = c.king_cutoff_table.empty() ? RunKingCutoffBinary(c, &ds) : RunKingCutoffTable(c, &ds);
-    if (rc) return rc;
-    if (!(c.freq || c.make_king || c.make_king_table || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise)) {
-      return 0;  // table-driven pruning is host-only in the reference as well: no device is needed for it
+    if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
+      logprintf("Error: file-driven --king-cutoff[-table] cannot be combined with --make-king[-table] in plink2_b200.\n");
+      return kRetInvalidCmdline;
     }
-    logprintf("Error: chaining file-driven --king-cutoff[-table] sample removal into later commands is not supported by plink2_b200.\n");
-    return kRetNotYetSupported;
+    rc = c.king_cutoff_table.empty() ? RunKingCutoffBinary(c, &ds, &cutoff_removed) : RunKingCutoffTable(c, &ds, &cutoff_removed);
+    if (rc) return rc;
+  }
+  auto write_bed = [&]() -> int {
+    std::vector<uint64_t> finc;
+    uint32_t fct = 0;
+    if (c.debug_founders_bed) {
+      finc.assign((ds.samples.size() + 63) / 64, 0);
+      for (uint32_t k = 0; k < ds.samples.size(); ++k) {
+        if (ds.samples.is_founder[k]) {
+          finc[k / 64] |= 1ull << (k % 64);
+          ++fct;
+        }
+      }
+    }
+    const int wrc = WriteBedFileset(&ds, c.out, EffectiveHostThreads(c.threads), &err, c.debug_founders_bed ? finc.data() : nullptr, fct);
+    if (wrc) {
+      logprintf("Error: %s\n", err.c_str());
+      return wrc;
+    }
+    logprintf("--make-bed: %s.bed + %s.bim + %s.fam written.\n", c.out.c_str(), c.out.c_str(), c.out.c_str());
+    return 0;
+  };
+  auto any_removed = [&]() { return std::find(cutoff_removed.begin(), cutoff_removed.end(), 1) != cutoff_removed.end(); };
+  auto drop_removed = [&]() {
+    std::vector<uint8_t> keep(cutoff_removed.size());
+    for (size_t k = 0; k < keep.size(); ++k) keep[k] = !cutoff_removed[k];
+    KeepSamples(&ds, keep);
+    cutoff_removed.clear();
+  };
+  if (!needs_gpu) {
+    if (gpu_command) {
+      // a file-driven prune followed by device commands: the device is needed after all
+      logprintf("Error: internal: device command without a device context.\n");
+      return kRetGpuFail;
+    }
+    if (c.make_bed) {
+      if (any_removed()) drop_removed();
+      rc = write_bed();
+      if (rc) return rc;
+    }
+    return 0;  // file-driven pruning and --make-bed are host-only in the reference as well: no device is needed
   }
   g_decode_threads = EffectiveHostThreads(c.threads);
   if (ctx_thread.joinable()) ctx_thread.join();
@@ -3342,18 +3432,9 @@ int main(int argc, char** argv) {
   }
   g_clock.Mark("pl2gpu_ctx_create (overlapped with the file loading above)");
   if (c.freq) {
-    rc = RunFreq(c, &ds, ctx);
+    rc = RunFreq(c, &ds, ctx);  // before any relatedness prune, like the reference's LoadAlleleAndGenoCounts stage
     if (rc) return rc;
   }
-  if (!c.score_file.empty()) {
-    rc = RunScore(c, &ds, ctx);
-    if (rc) return rc;
-  }
-  if (!c.vscore_file.empty()) {
-    rc = RunVscore(c, &ds, ctx);
-    if (rc) return rc;
-  }
-  std::vector<uint8_t> cutoff_removed;
   bool rel_check_pairs = false;
   if (c.king_rel_check && c.king_table_subset.empty()) {
     // with a single FID in the dataset the modifier has no effect (the reference warns and computes the full table)
@@ -3370,10 +3451,36 @@ int main(int argc, char** argv) {
   } else if (c.make_king || c.make_king_table || c.king_cutoff >= 0) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
     if (rc) return rc;
-    if (c.king_cutoff >= 0 && (c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise)) {
-      logprintf("Error: chaining --king-cutoff sample removal into later commands is not supported by plink2_b200; rerun with --keep on the .king.cutoff.in.id list.\n");
-      return kRetNotYetSupported;
+  }
+  if (any_removed() && (later_gpu_command || c.make_bed)) {
+    // The commands after a relatedness prune see the surviving samples, but keep the allele frequencies estimated
+    // BEFORE it: the reference computes allele_freqs once (plink2.cc:2280-2304) and only narrows sample_include /
+    // founder_info afterwards (UpdateSampleSubsets, :2580).  Freeze those frequencies as per-variant overrides
+    // (the --read-freq mechanism), then drop the samples from the view.
+    if (later_gpu_command) {
+      std::vector<uint64_t> alt_dd, tot_dd;
+      rc = FounderAlleleDosages(&ds, ctx, &alt_dd, &tot_dd);
+      if (rc) return rc;
+      if (ds.read_ref_freq.empty()) ds.read_ref_freq.assign(ds.variants.size(), std::numeric_limits<double>::quiet_NaN());
+      for (uint32_t v = 0; v < ds.variants.size(); ++v) {
+        if (ds.read_ref_freq[v] == ds.read_ref_freq[v]) continue;
+        ds.read_ref_freq[v] = tot_dd[v] ? static_cast<double>(tot_dd[v] - alt_dd[v]) * (1.0 / static_cast<double>(tot_dd[v])) : 0.5;
+      }
     }
+    drop_removed();
+    logprintf("%u sample%s remaining after the relatedness prune.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s");
+  }
+  if (c.make_bed) {
+    rc = write_bed();
+    if (rc) return rc;
+  }
+  if (!c.score_file.empty()) {
+    rc = RunScore(c, &ds, ctx);
+    if (rc) return rc;
+  }
+  if (!c.vscore_file.empty()) {
+    rc = RunVscore(c, &ds, ctx);
+    if (rc) return rc;
   }
   Pl2GrmJob* grm_job = nullptr;
   std::vector<uint32_t> grm_vidx;

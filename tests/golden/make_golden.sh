@@ -91,6 +91,21 @@ $P --bfile a --make-king bin triangle --threads 2 --out $T/k8 > /dev/null
 python make_king_cutoff_set.py $T/k8.king.bin $T/k8.king.id a_kc8
 $P --bfile a --king-cutoff a_kc8 0.03 --threads 2 --out $T/a_kc8o > /dev/null
 cp $T/a_kc8o.king.cutoff.in.id a_kc8.king.cutoff.in.id; cp $T/a_kc8o.king.cutoff.out.id a_kc8.king.cutoff.out.id
+# --- filters in front of the commands, pinned through --make-bed (host-only): ID lists from make_filter_set.py
+python make_filter_set.py
+$P --bfile x --keep x_keep1.txt x_keep2.txt --remove x_remove.txt --extract x_extract.txt --exclude x_exclude.txt --make-bed --threads 2 --out $T/x_filt > /dev/null
+for e in bed bim fam; do cp $T/x_filt.$e x_filt.$e; done
+$P --bfile x --keep x_keep1.txt x_keep2.txt --remove x_remove.txt --extract x_extract.txt --exclude x_exclude.txt --keep-founders --make-bed --threads 2 --out $T/x_ff > /dev/null
+cp $T/x_ff.bed x_filt_founders.bed   # founders of the filtered view: what the founder-only commands decode
+$P --bfile x --chr 1,X,Y --not-chr Y --make-bed --threads 2 --out $T/x_chr > /dev/null
+cp $T/x_chr.bim x_chr.bim; cp $T/x_chr.bed x_chr.bed
+$P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --remove x_remove.txt --exclude x_exclude.txt --make-bed --threads 2 --out $T/a_filt > /dev/null
+for e in bed bim fam; do cp $T/a_filt.$e a_filt.$e; done
+$P --bfile s --keep-fam s_keepfam.txt --remove-fam s_removefam.txt --make-bed --threads 2 --out $T/s_fam > /dev/null
+cp $T/s_fam.fam s_famfilt.fam; cp $T/s_fam.bed s_famfilt.bed
+# relatedness prune from a table, then --make-bed on the survivors
+$P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
+cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null

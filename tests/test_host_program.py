@@ -272,6 +272,89 @@ def test_king_cutoff_matrix_prefix_matches_reference_lists(tmp_path):
     assert r.returncode != 0 and "expected 0 or 0 bytes" in r.stdout + r.stderr
 
 
+FILTER_CASES = [
+    # (dataset arguments, filter arguments, golden prefix, extensions compared)
+    (["--bfile", "x"], ["--keep", "x_keep1.txt", "x_keep2.txt", "--remove", "x_remove.txt", "--extract", "x_extract.txt", "--exclude", "x_exclude.txt"], "x_filt", ("bed", "bim", "fam")),
+    (["--bfile", "x"], ["--chr", "1,X,Y", "--not-chr", "Y"], "x_chr", ("bed", "bim")),
+    (["--pgen", "a_mode10.pgen", "--pvar", "a.pvar", "--psam", "a.psam"], ["--remove", "x_remove.txt", "--exclude", "x_exclude.txt"], "a_filt", ("bed", "bim", "fam")),
+    (["--bfile", "s"], ["--keep-fam", "s_keepfam.txt", "--remove-fam", "s_removefam.txt"], "s_famfilt", ("bed", "fam")),
+]
+
+
+@pytest.mark.parametrize("case", range(len(FILTER_CASES)))
+def test_filters_and_make_bed_match_reference(tmp_path, case):
+    """The sample / variant filters in front of every command (--keep, --remove, --keep-fam, --remove-fam, --extract,
+    --exclude, --chr, --not-chr) compact the dataset and install a view in the genotype reader; --make-bed writes that
+    view.  Host-only, so checked here: .bed / .bim / .fam byte-identical to the reference's --make-bed under the same
+    filters, for a .bed input with sex chromosomes, an LD-compressed .pgen, and FID-based lists."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    data, filt, gold, exts = FILTER_CASES[case]
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN] + data + filt + ["--make-bed", "--threads", "3", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in exts:
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, gold + "." + ext), "rb").read(), ext
+    if case == 0:
+        assert "--keep: 80 samples remaining." in r.stdout and "--remove: 60 samples remaining." in r.stdout
+        assert "--extract: 500 variants remaining." in r.stdout and "--exclude: 420 variants remaining." in r.stdout
+        assert "duplicate ID in --keep" in r.stdout
+
+
+def test_founder_subset_of_a_filtered_view(tmp_path):
+    """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
+    bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
+    --debug-founders-bed flag writes exactly that decode; the reference's --keep-founders under the same filters gives
+    the expected bytes."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN] + FILTER_CASES[0][0] + FILTER_CASES[0][1] + ["--debug-founders-bed", "--threads", "2", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".bed", "rb").read() == open(os.path.join(gd, "x_filt_founders.bed"), "rb").read()
+
+
+def test_make_bed_round_trips_every_input_mode(tmp_path):
+    """Without filters --make-bed must reproduce the .bed the fixtures were converted from: .bed input, fixed-width
+    .pgen (mode 0x02) and variable-width .pgen with difflist / LD-compressed records (mode 0x10)."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    for data in (["--bfile", "a"], ["--pgen", "a_mode02.pgen", "--pvar", "a.pvar", "--psam", "a.psam"], ["--pgen", "a_mode10.pgen", "--pvar", "a.pvar", "--psam", "a.psam"], ["--pgen", "b_mode10.pgen", "--pvar", "b.pvar", "--psam", "b.psam"]):
+        out = str(tmp_path / "o")
+        r = subprocess.run([BIN] + data + ["--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        want = "b" if data[1].startswith("b") else "a"
+        assert open(out + ".bed", "rb").read() == open(os.path.join(gd, want + ".bed"), "rb").read(), data
+        assert open(out + ".bim", "rb").read() == open(os.path.join(gd, want + ".bim"), "rb").read(), data
+
+
+def test_filter_edge_cases(tmp_path):
+    """An ID list without a FID column names only FID-0 samples (set S carries real FIDs -> nobody left, the
+    reference's error); unknown chromosome codes and reversed ranges are refused at the command line."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bfile", "s", "--keep", "s_keep_iid.txt", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 7 and "--keep: 0 samples remaining." in r.stdout and "No samples remaining after main filters." in r.stdout
+    r = subprocess.run([BIN, "--bfile", "x", "--chr", "1,X-Y", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "cannot be the end of a range" in r.stdout + r.stderr
+    r = subprocess.run([BIN, "--bfile", "x", "--chr", "5-3", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "is not greater than" in r.stdout + r.stderr
+    r = subprocess.run([BIN, "--bfile", "x", "--extract", "no_such_file.txt", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 3
+
+
+def test_relatedness_prune_feeds_later_commands(tmp_path):
+    """`--king-cutoff-table ... --make-bed`: the samples removed by the prune are gone from the later command's view,
+    as in the reference (plink2.cc:2523-2581) - .fam / .bed identical to the reference's chained run."""
+    import gzip
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    (tmp_path / "in.kin0").write_bytes(gzip.open(os.path.join(gd, "a_kingp.kin0.gz"), "rb").read())
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bfile", os.path.join(gd, "a"), "--king-cutoff-table", str(tmp_path / "in.kin0"), "0.02", "--make-bed", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("fam", "bed"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "a_kctb." + ext), "rb").read(), ext
+    assert open(out + ".king.cutoff.in.id", "rb").read() == open(os.path.join(gd, "a_kct.king.cutoff.in.id"), "rb").read()
+
+
 def test_natural_sort_matches_reference_order(tmp_path):
     """The ID order behind `--make-king-table rel-check`: the reference's own table on set S (300 random IDs of the
     alphabet aAbBzZ0019_.-x over FIDs F1 / F2 / f1 / F10 / F02) lists every FID block in natural order; the host
