@@ -3083,8 +3083,8 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       ++founder_ct;
     }
   }
-  if (founder_ct < 50 && !c.bad_ld) {  // plink2.cc:2065
-    logprintf("Error: This run estimates linkage disequilibrium between variants, but there are less than 50 founders in the current dataset.  LD estimates would be very noisy; use --bad-ld to override.\n");
+  if (!founder_ct) {
+    logprintf("Error: No founders left for --indep-pairwise.\n");
     return kRetDegenerateData;
   }
   const uint32_t m = V.size();
@@ -3364,6 +3364,16 @@ int main(int argc, char** argv) {
       return frc;
     }
   }
+  if (c.indep_pairwise && !c.bad_ld) {
+    // plink2.cc:2065: checked once the main filters ran and BEFORE any relatedness prune - a --king-cutoff that
+    // leaves fewer than 50 founders does not stop the LD prune chained behind it
+    uint32_t fct = 0;
+    for (uint8_t f : ds.samples.is_founder) fct += f;
+    if (fct < 50) {
+      logprintf("Error: This run estimates linkage disequilibrium between variants, but there are less than 50 %s to estimate from.  (Strictly speaking, you can also override this error with --bad-ld, but this is almost always a bad idea.)\n", ds.samples.size() < 50 ? "samples" : "founders");
+      return kRetDegenerateData;
+    }
+  }
   if (!c.read_freq.empty()) {
     rc = LoadReadFreq(c, &ds);
     if (rc) return rc;
@@ -3412,11 +3422,6 @@ int main(int argc, char** argv) {
     cutoff_removed.clear();
   };
   if (!needs_gpu) {
-    if (gpu_command) {
-      // a file-driven prune followed by device commands: the device is needed after all
-      logprintf("Error: internal: device command without a device context.\n");
-      return kRetGpuFail;
-    }
     if (c.make_bed) {
       if (any_removed()) drop_removed();
       rc = write_bed();

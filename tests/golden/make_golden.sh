@@ -106,6 +106,16 @@ cp $T/s_fam.fam s_famfilt.fam; cp $T/s_fam.bed s_famfilt.bed
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed
+# the same filters / prune chaining through the device commands (tests/test_filters_gpu.py, tools/check_r2s.py)
+XF="--keep x_keep1.txt x_keep2.txt --remove x_remove.txt --extract x_extract.txt --exclude x_exclude.txt"
+$P --bfile x $XF --make-king-table --threads 2 --out $T/g1 > /dev/null; gzip -9 -n -c $T/g1.kin0 > g_xfilt.kin0.gz
+$P --bfile x $XF --indep-pairwise 50 5 0.2 --threads 2 --out $T/g2 > /dev/null; cp $T/g2.prune.in g_xfilt.prune.in
+$P --bfile x $XF --freq --threads 2 --out $T/g3 > /dev/null; cp $T/g3.afreq g_xfilt.afreq
+$P --bfile a --king-cutoff 0.02 --indep-pairwise 50 5 0.2 --threads 2 --out $T/g4 > /dev/null; cp $T/g4.prune.in g_acut.prune.in
+$P --bfile a --king-cutoff 0.02 --make-grm-bin --threads 2 --out $T/g5 > /dev/null; cp $T/g5.grm.bin g_acut.grm.bin
+$PL --bfile a --king-cutoff-table $T/in.kin0 0.02 --pca 3 --threads 2 --out $T/g6 > /dev/null; cp $T/g6.eigenval g_akct.eigenval; cp $T/g6.eigenvec g_akct.eigenvec
+$P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --remove x_remove.txt --exclude x_exclude.txt --make-king-table --threads 2 --out $T/g7 > /dev/null; gzip -9 -n -c $T/g7.kin0 > g_afilt.kin0.gz
+$P --bfile a --king-cutoff 0.02 --score a_score.txt header cols=+scoresums,+denom --threads 2 --out $T/g8 > /dev/null; cp $T/g8.sscore g_acut.sscore
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null

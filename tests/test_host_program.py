@@ -338,6 +338,9 @@ def test_filter_edge_cases(tmp_path):
     assert r.returncode != 0 and "is not greater than" in r.stdout + r.stderr
     r = subprocess.run([BIN, "--bfile", "x", "--extract", "no_such_file.txt", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
     assert r.returncode == 3
+    # the LD sample-size guard runs on what the main filters left, before any device work (plink2.cc:2065)
+    r = subprocess.run([BIN, "--bfile", "x", "--keep", "x_keep2.txt", "--indep-pairwise", "50", "5", "0.2", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 13 and "less than 50 samples" in r.stdout
 
 
 def test_relatedness_prune_feeds_later_commands(tmp_path):
