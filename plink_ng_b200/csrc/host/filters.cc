@@ -206,6 +206,7 @@ void KeepVariants(Dataset* ds, const std::vector<uint8_t>& keep) {
 }
 
 int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* log, std::string* err) {
+  // (count-based thresholds are applied by the caller after --read-freq: ApplyCountFilters in the host program)
   // ---- variants: chromosome flags (applied while the reference loads the .pvar), then --extract, then --exclude
   {
     const VariantInfo& V = ds->variants;
@@ -288,7 +289,153 @@ int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* 
     }
     KeepSamples(ds, seen);
   }
+  if (spec.excl_males || spec.excl_females || spec.excl_nosex) {
+    const SampleInfo& S = ds->samples;
+    std::vector<uint8_t> keep(S.size());
+    uint32_t removed = 0;
+    for (uint32_t k = 0; k < S.size(); ++k) {
+      keep[k] = !((S.sex[k] == 1 && spec.excl_males) || (S.sex[k] == 2 && spec.excl_females) || (S.sex[k] == 0 && spec.excl_nosex));
+      removed += !keep[k];
+    }
+    log->push_back(Plural(removed, "sample") + " removed due to sex filter(s).");
+    if (removed == S.size()) {
+      *err = "No samples remaining after main filters.";
+      return 7;
+    }
+    if (removed) KeepSamples(ds, keep);
+  }
+  if (spec.founders_only) {
+    const SampleInfo& S = ds->samples;
+    std::vector<uint8_t> keep(S.size());
+    uint32_t removed = 0;
+    for (uint32_t k = 0; k < S.size(); ++k) {
+      keep[k] = (S.is_founder[k] != 0) == (spec.founders_only == 1);
+      removed += !keep[k];
+    }
+    log->push_back(std::string("--keep-") + (spec.founders_only == 1 ? "" : "non") + "founders: " + Plural(removed, "sample") + " removed.");
+    if (removed == S.size()) {
+      *err = "No samples remaining after main filters.";
+      return 7;
+    }
+    if (removed) KeepSamples(ds, keep);
+  }
   return 0;
+}
+
+int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  const uint32_t words = PgenReader::WordsFor(n);
+  // one 0b01 lane per member sample, in genovec layout (32 samples per word)
+  enum { kAll, kMale, kFounder, kFounderMale, kFounderNonfemale, kSets };
+  std::vector<uint64_t> lane[kSets];
+  for (auto& l : lane) l.assign(words, 0);
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint64_t bit = 1ull << (2 * (k & 31));
+    const bool f = S.is_founder[k] != 0;
+    lane[kAll][k >> 5] |= bit;
+    if (S.sex[k] == 1) lane[kMale][k >> 5] |= bit;
+    if (f) lane[kFounder][k >> 5] |= bit;
+    if (f && S.sex[k] == 1) lane[kFounderMale][k >> 5] |= bit;
+    if (f && S.sex[k] != 2) lane[kFounderNonfemale][k >> 5] |= bit;
+  }
+  std::vector<uint32_t>* out[kSets] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  if (vc) {
+    out[kAll] = &vc->all;
+    out[kMale] = &vc->male;
+    out[kFounder] = &vc->founder;
+    out[kFounderMale] = &vc->founder_male;
+    out[kFounderNonfemale] = &vc->founder_nonfemale;
+    for (auto* o : out) o->assign(4ull * m, 0);
+  }
+  uint32_t set_size[kSets];
+  for (int s = 0; s < kSets; ++s) {
+    uint64_t c = 0;
+    for (uint64_t w : lane[s]) c += static_cast<uint64_t>(__builtin_popcountll(w));
+    set_size[s] = static_cast<uint32_t>(c);
+  }
+  if (sample_missing) sample_missing->assign(n, 0);
+  uint32_t y_ct = 0;
+  const uint32_t batch = 8192;
+  std::vector<uint64_t> buf(static_cast<size_t>(batch) * words);
+  std::vector<uint32_t> vidx(batch);
+  thread_ct = std::max(1u, thread_ct);
+  std::vector<std::vector<uint32_t>> miss_part(sample_missing ? thread_ct : 0, std::vector<uint32_t>(sample_missing ? n : 0, 0));
+  const uint64_t kLo = 0x5555555555555555ull;
+  for (uint32_t v0 = 0; v0 < m; v0 += batch) {
+    const uint32_t cnt = std::min(batch, m - v0);
+    for (uint32_t k = 0; k < cnt; ++k) vidx[k] = v0 + k;
+    if (!ds->reader.GetBlock(vidx.data(), cnt, nullptr, n, buf.data(), words, thread_ct, err)) return 6;
+    auto work = [&](uint32_t t) {
+      const uint32_t k0 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * t / thread_ct), k1 = static_cast<uint32_t>(static_cast<uint64_t>(cnt) * (t + 1) / thread_ct);
+      for (uint32_t k = k0; k < k1; ++k) {
+        const uint64_t* row = buf.data() + static_cast<size_t>(k) * words;
+        const uint32_t v = v0 + k;
+        const bool is_y = V.chr_code[v] == 24;
+        uint32_t c[kSets][3] = {};
+        for (uint32_t w = 0; w < words; ++w) {
+          const uint64_t g = row[w], lo = g & kLo, hi = (g >> 1) & kLo;
+          const uint64_t het = lo & ~hi, alt = hi & ~lo, mis = lo & hi;
+          if (vc) {
+            for (int s = 0; s < kSets; ++s) {
+              const uint64_t l = lane[s][w];
+              c[s][0] += static_cast<uint32_t>(__builtin_popcountll(het & l));
+              c[s][1] += static_cast<uint32_t>(__builtin_popcountll(alt & l));
+              c[s][2] += static_cast<uint32_t>(__builtin_popcountll(mis & l));
+            }
+          }
+          if (sample_missing) {
+            uint64_t mm = mis & (is_y ? lane[kMale][w] : lane[kAll][w]);
+            while (mm) {
+              const uint32_t b = static_cast<uint32_t>(__builtin_ctzll(mm));
+              ++miss_part[t][w * 32 + (b >> 1)];
+              mm &= mm - 1;
+            }
+          }
+        }
+        if (vc) {
+          for (int s = 0; s < kSets; ++s) {
+            uint32_t* dst = out[s]->data() + 4ull * v;
+            dst[1] = c[s][0];
+            dst[2] = c[s][1];
+            dst[3] = c[s][2];
+            dst[0] = set_size[s] - c[s][0] - c[s][1] - c[s][2];
+          }
+        }
+      }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < thread_ct; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto& x : th) x.join();
+    for (uint32_t k = 0; k < cnt; ++k) y_ct += V.chr_code[v0 + k] == 24;
+  }
+  if (sample_missing)
+    for (const auto& part : miss_part)
+      for (uint32_t k = 0; k < n; ++k) (*sample_missing)[k] += part[k];
+  if (variant_ct_y) *variant_ct_y = y_ct;
+  return 0;
+}
+
+void FounderAlleleDd(const VariantGenoCounts& vc, uint32_t v, uint32_t chr_code, uint32_t founder_ct, uint32_t founder_male_ct, uint64_t* alt_dd, uint64_t* tot_dd) {
+  const uint32_t* f = &vc.founder[4ull * v];
+  const uint64_t n0 = f[0], n1 = f[1], n2 = f[2], n3 = f[3];
+  if (chr_code == 23) {  // nonmales twice, males once (a male het counts half of each allele)
+    const uint32_t* mc = &vc.founder_male[4ull * v];
+    *alt_dd = (4 * n2 + 2 * n1 - 2ull * mc[2] - mc[1]) * 16384ull;
+    *tot_dd = (2 * (founder_ct - n3) - founder_male_ct + mc[3]) * 2 * 16384ull;
+  } else if (chr_code == 24) {  // nonfemale founders, haploid
+    const uint32_t* y = &vc.founder_nonfemale[4ull * v];
+    *alt_dd = (y[1] + 2ull * y[2]) * 16384ull;
+    *tot_dd = 2ull * (static_cast<uint64_t>(y[0]) + y[1] + y[2]) * 16384ull;
+  } else if (chr_code == 26) {
+    *alt_dd = (n1 + 2 * n2) * 16384ull;
+    *tot_dd = 2 * (n0 + n1 + n2) * 16384ull;
+  } else {
+    *alt_dd = (n1 + 2 * n2) * 32768ull;
+    *tot_dd = 2 * (n0 + n1 + n2) * 32768ull;
+  }
 }
 
 int WriteBedFileset(Dataset* ds, const std::string& out_prefix, uint32_t thread_ct, std::string* err, const uint64_t* sample_include, uint32_t include_ct) {

@@ -17,7 +17,17 @@ struct FilterSpec {
   std::vector<std::string> extract, exclude;                    // variant-ID token files (TokenExtractExclude)
   std::vector<uint8_t> chr_mask, not_chr_mask;                  // 27 flags each when the flag was given
   bool autosome = false, autosome_xy = false;
-  bool any() const { return !(keep.empty() && remove.empty() && keep_fam.empty() && remove_fam.empty() && extract.empty() && exclude.empty() && chr_mask.empty() && not_chr_mask.empty()) || autosome || autosome_xy; }
+  bool excl_males = false, excl_females = false, excl_nosex = false;  // --keep-males / --remove-females / ... (plink2.cc:1688)
+  int founders_only = 0;                                               // 1 --keep-founders, 2 --keep-nonfounders (:1705)
+  // thresholds on genotype counts (applied after --read-freq was loaded; plink2.cc:1748, :2338, :2460)
+  double mind = 1.0, geno = 1.0, min_maf = 0.0, max_maf = 1.0;
+  uint64_t min_mac = 0, max_mac = ~0ull;  // allele counts (the reference's ddosage bounds / 32768)
+  bool any_count_filter() const { return mind < 1.0 || geno < 1.0 || min_maf != 0.0 || max_maf != 1.0 || min_mac || max_mac != ~0ull; }
+  bool any() const {
+    if (excl_males || excl_females || excl_nosex || founders_only) return true;
+    return any_id_filter();
+  }
+  bool any_id_filter() const { return !(keep.empty() && remove.empty() && keep_fam.empty() && remove_fam.empty() && extract.empty() && exclude.empty() && chr_mask.empty() && not_chr_mask.empty()) || autosome || autosome_xy; }
 };
 
 // "1-4,22,X" style arguments (ParseChrRanges, plink2_common.cc:3695) -> 27 flags.  False + *err on a bad token.
@@ -26,6 +36,18 @@ bool ParseChrList(const std::vector<std::string>& args, const char* flag, std::v
 // Applies the filters in the reference's order.  Log lines ("--keep: 61 samples remaining.") are appended to *log.
 // Returns 0, or a PglErr-valued code with *err set (3 open failure, 6 malformed file, 7 nothing left).
 int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* log, std::string* err);
+
+// Genotype counts of the current view, one host pass (the roles of LoadSampleMissingCts and LoadAlleleAndGenoCounts,
+// 2.0/plink2_data.cc, for hard calls).  Per variant [4]: code counts 0 / 1 / 2 / 3 over the named sample set.
+struct VariantGenoCounts {
+  std::vector<uint32_t> all, male;                            // every sample; males (chrY missingness)
+  std::vector<uint32_t> founder, founder_male, founder_nonfemale;  // allele-frequency sets (autosomes / chrX / chrY)
+};
+// sample_missing[k]: missing calls of sample k over all variants, chrY variants counted for males only (then
+// *variant_ct_y = number of chrY variants).  Either output may be null.
+int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err);
+// REF allele "ddosage" pair of a variant from those counts (the numbers behind --freq; see RunFreq)
+void FounderAlleleDd(const VariantGenoCounts& vc, uint32_t v, uint32_t chr_code, uint32_t founder_ct, uint32_t founder_male_ct, uint64_t* alt_dd, uint64_t* tot_dd);
 
 // keep[k] != 0: sample / variant k (current numbering) stays.  Compacts the tables and updates the reader view.
 void KeepSamples(Dataset* ds, const std::vector<uint8_t>& keep);

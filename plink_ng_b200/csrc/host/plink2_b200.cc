@@ -427,6 +427,43 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--autosome" || flag == "--autosome-xy" || flag == "--autosome-par") {
       if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
       (flag == "--autosome" ? c->filters.autosome : c->filters.autosome_xy) = true;
+    } else if (flag == "--keep-founders" || flag == "--keep-nonfounders") {
+      if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
+      if (c->filters.founders_only) return Usage("--keep-nonfounders cannot be used with --keep-founders.");
+      c->filters.founders_only = flag == "--keep-founders" ? 1 : 2;
+    } else if (flag == "--keep-males" || flag == "--keep-females" || flag == "--keep-nosex" || flag == "--remove-males" || flag == "--remove-females" || flag == "--remove-nosex") {
+      // plink2.cc sex filters: keep-X excludes the other two classes, remove-X excludes X
+      if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
+      const bool keep = flag[2] == 'k';
+      const std::string cls = flag.substr(keep ? 7 : 9);
+      if (keep) {
+        c->filters.excl_males = c->filters.excl_males || cls != "males";
+        c->filters.excl_females = c->filters.excl_females || cls != "females";
+        c->filters.excl_nosex = c->filters.excl_nosex || cls != "nosex";
+      } else {
+        (cls == "males" ? c->filters.excl_males : cls == "females" ? c->filters.excl_females : c->filters.excl_nosex) = true;
+      }
+    } else if (flag == "--mind" || flag == "--geno") {
+      // [threshold], default 0.1 (plink2.cc:6487-6511); the 'dosage' / 'hh-missing' modifiers are not supported
+      double thr = 0.1;
+      if (!need(0, 1) || (nparam == 1 && (!ParseDouble(prm[0], &thr) || thr < 0.0 || thr > 1.0))) return Usage(("Invalid " + flag + " argument.").c_str());
+      (flag == "--mind" ? c->filters.mind : c->filters.geno) = thr;
+    } else if (flag == "--maf" || flag == "--max-maf") {
+      double thr = 0.01;
+      if (flag == "--max-maf" ? !need(1, 1) : !need(0, 1)) return Usage(("Invalid " + flag + " argument sequence.").c_str());
+      if (nparam == 1 && (!ParseDouble(prm[0], &thr) || thr < 0.0 || thr > 1.0)) return Usage(("Invalid " + flag + " argument '" + prm[0] + "' (a number in [0, 1]; allele-selector suffixes are not supported).").c_str());
+      (flag == "--maf" ? c->filters.min_maf : c->filters.max_maf) = thr;
+    } else if (flag == "--mac" || flag == "--max-mac") {
+      double cnt;
+      if (!need(1, 1) || !ParseDouble(prm[0], &cnt) || cnt < 0.0 || cnt > 2147483646.0) return Usage(("Invalid " + flag + " argument.").c_str());
+      // the reference compares allele "ddosages" (1/32768 units), so the thresholds are scaled the same way
+      if (flag == "--mac") {  // rounded up (plink2.cc:8800-8807)
+        const int32_t int_part = static_cast<int32_t>(cnt);
+        const double frac = cnt - int_part;
+        c->filters.min_mac = static_cast<uint64_t>(int_part) * 32768ull + (frac > 0.0 ? 1 + static_cast<uint64_t>(frac * (32768.0 * (1 - 1.0 / 17592186044416.0))) : 0);
+      } else {
+        c->filters.max_mac = static_cast<uint64_t>(static_cast<int64_t>(cnt * 32768.0));  // :8849
+      }
     } else if (flag == "--debug-founders-bed") {
       c->debug_founders_bed = c->make_bed = true;
     } else if (flag == "--make-bed") {
@@ -3288,6 +3325,118 @@ int DebugHooks(int argc, char** argv) {
   return -1;
 }
 
+// --mind, --geno, --maf / --max-maf / --mac / --max-mac on hard calls: one host counting pass each for the sample and
+// the variant thresholds (MindFilter plink2_filter.cc:3329, EnforceGenoThresh :3498, EnforceFreqConstraints :3791).
+// chrY: missingness over males only; frequencies are the founder frequencies --freq reports (or --read-freq's).
+int ApplyCountFilters(const Cmd& c, Dataset* ds) {
+  const FilterSpec& f = c.filters;
+  const double eps = 1.0 / 17592186044416.0;  // kSmallEpsilon = 2^-44
+  const uint32_t threads = EffectiveHostThreads(c.threads);
+  std::string err;
+  if (f.mind < 1.0) {
+    std::vector<uint32_t> miss;
+    uint32_t y_ct = 0;
+    const int rc = CountGenotypes(ds, threads, nullptr, &miss, &y_ct, &err);
+    if (rc) {
+      logprintf("Error: %s\n", err.c_str());
+      return rc;
+    }
+    const SampleInfo& S = ds->samples;
+    const uint32_t n = S.size(), m = ds->variants.size();
+    const double thr = f.mind * (1 + eps);
+    const uint32_t max_nonmale = static_cast<uint32_t>(static_cast<int32_t>(static_cast<double>(m - y_ct) * thr)), max_male = static_cast<uint32_t>(static_cast<int32_t>(static_cast<double>(m) * thr));
+    std::vector<uint8_t> keep(n, 1);
+    std::vector<uint32_t> gone;
+    for (uint32_t k = 0; k < n; ++k) {
+      if (miss[k] > (S.sex[k] == 1 ? max_male : max_nonmale)) {
+        keep[k] = 0;
+        gone.push_back(k);
+      }
+    }
+    logprintf("%zu sample%s removed due to missing genotype data (--mind).\n", gone.size(), gone.size() == 1 ? "" : "s");
+    if (!gone.empty()) {
+      const std::string name = c.out + ".mindrem.id";
+      if (!WriteIdFile(name, S, gone, true)) return kRetWriteFail;
+      logprintf("ID%s written to %s .\n", gone.size() == 1 ? "" : "s", name.c_str());
+      if (gone.size() == n) {
+        logprintf("Error: No samples remaining after main filters.\n");
+        return kRetInconsistentInput;
+      }
+      KeepSamples(ds, keep);
+    }
+  }
+  if (f.geno < 1.0 || f.min_maf != 0.0 || f.max_maf != 1.0 || f.min_mac || f.max_mac != ~0ull) {
+    VariantGenoCounts vc;
+    const int rc = CountGenotypes(ds, threads, &vc, nullptr, nullptr, &err);
+    if (rc) {
+      logprintf("Error: %s\n", err.c_str());
+      return rc;
+    }
+    const SampleInfo& S = ds->samples;
+    const VariantInfo& V = ds->variants;
+    const uint32_t n = S.size(), m = V.size();
+    uint32_t male_ct = 0, founder_ct = 0, founder_male_ct = 0;
+    for (uint32_t k = 0; k < n; ++k) {
+      male_ct += S.sex[k] == 1;
+      founder_ct += S.is_founder[k] != 0;
+      founder_male_ct += S.is_founder[k] && S.sex[k] == 1;
+    }
+    if ((f.min_mac || f.max_mac != ~0ull) && founder_ct != n) {  // plink2.cc:2102
+      logprintf("Error: --mac/--max-mac specified, but with neither --ac-founders nor --nonfounders; and nonfounders are present.\n");
+      return kRetInconsistentInput;
+    }
+    std::vector<uint8_t> keep(m, 1);
+    uint32_t left = m;
+    if (f.geno < 1.0) {
+      const double thr = f.geno * (1 + eps);
+      const uint32_t max_nony = static_cast<uint32_t>(static_cast<int32_t>(thr * static_cast<double>(n))), max_y = static_cast<uint32_t>(static_cast<int32_t>(thr * static_cast<double>(male_ct)));
+      uint32_t removed = 0;
+      for (uint32_t v = 0; v < m; ++v) {
+        const bool is_y = V.chr_code[v] == 24;
+        if ((is_y ? vc.male[4ull * v + 3] : vc.all[4ull * v + 3]) > (is_y ? max_y : max_nony)) {
+          keep[v] = 0;
+          ++removed;
+        }
+      }
+      left -= removed;
+      logprintf("--geno: %u variant%s removed due to missing genotype data.\n", removed, removed == 1 ? "" : "s");
+    }
+    if (f.min_maf != 0.0 || f.max_maf != 1.0 || f.min_mac || f.max_mac != ~0ull) {
+      const bool freq_filter = f.min_maf != 0.0 || f.max_maf != 1.0;
+      const double lo = f.min_maf * (1.0 - eps), hi = f.max_maf * (1.0 + eps);
+      uint32_t removed = 0;
+      for (uint32_t v = 0; v < m; ++v) {
+        if (!keep[v]) continue;
+        uint64_t alt_dd, tot_dd;
+        FounderAlleleDd(vc, v, V.chr_code[v], founder_ct, founder_male_ct, &alt_dd, &tot_dd);
+        bool drop = false;
+        if (freq_filter) {
+          double ref_freq = tot_dd ? static_cast<double>(tot_dd - alt_dd) * (1.0 / static_cast<double>(tot_dd)) : 0.5;
+          if (!ds->read_ref_freq.empty() && ds->read_ref_freq[v] == ds->read_ref_freq[v]) ref_freq = ds->read_ref_freq[v];
+          const double nonref = 1.0 - ref_freq, maf = nonref < ref_freq ? nonref : ref_freq;
+          drop = (f.min_maf != 0.0 && maf < lo) || (f.max_maf < 1.0 && maf > hi);
+        }
+        if (!drop && (f.min_mac || f.max_mac != ~0ull)) {
+          const uint64_t nonmajor = std::min(alt_dd, tot_dd - alt_dd);
+          drop = (f.min_mac && nonmajor < f.min_mac) || (f.max_mac != ~0ull && nonmajor > f.max_mac);
+        }
+        if (drop) {
+          keep[v] = 0;
+          ++removed;
+        }
+      }
+      left -= removed;
+      logprintf("%u variant%s removed due to allele frequency threshold(s) (--maf/--max-maf/--mac/--max-mac).\n", removed, removed == 1 ? "" : "s");
+    }
+    if (!left) {
+      logprintf("Error: No variants remaining after main filters.\n");
+      return kRetInconsistentInput;
+    }
+    if (left != m) KeepVariants(ds, keep);
+  }
+  return 0;
+}
+
 int main(int argc, char** argv) {
   {
     const int dbg = DebugHooks(argc, argv);
@@ -3376,6 +3525,10 @@ int main(int argc, char** argv) {
   }
   if (!c.read_freq.empty()) {
     rc = LoadReadFreq(c, &ds);
+    if (rc) return rc;
+  }
+  if (c.filters.any_count_filter()) {
+    rc = ApplyCountFilters(c, &ds);
     if (rc) return rc;
   }
   g_clock.Mark("load .psam/.pvar, open .pgen");

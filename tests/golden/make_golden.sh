@@ -103,6 +103,14 @@ $P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --remove x_remove.txt --excl
 for e in bed bim fam; do cp $T/a_filt.$e a_filt.$e; done
 $P --bfile s --keep-fam s_keepfam.txt --remove-fam s_removefam.txt --make-bed --threads 2 --out $T/s_fam > /dev/null
 cp $T/s_fam.fam s_famfilt.fam; cp $T/s_fam.bed s_famfilt.bed
+# count-based QC thresholds (--mind, --geno, --maf / --max-maf / --mac) and the sex / founder filters
+$P --bfile x --keep x_keep1.txt x_keep2.txt --mind 0.035 --geno 0.02 --maf 0.05 --make-bed --threads 2 --out $T/x_qc > /dev/null
+for e in bed bim fam mindrem.id; do cp $T/x_qc.$e x_qc.$e; done
+$P --bfile x --keep-founders --mac 30 --max-maf 0.45 --make-bed --threads 2 --out $T/x_mac > /dev/null; cp $T/x_mac.bim x_mac.bim; cp $T/x_mac.fam x_mac.fam
+$P --bfile x --remove-nosex --keep-nonfounders --make-bed --threads 2 --out $T/x_sex > /dev/null; cp $T/x_sex.fam x_sex.fam
+$P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --geno 0.03 --mind 0.04 --maf 0.2 --make-bed --threads 2 --out $T/a_qc > /dev/null
+for e in bed bim fam; do cp $T/a_qc.$e a_qc.$e; done
+$P --bfile a --read-freq a_rf.afreq --exclude x_exclude.txt --maf 0.3 --make-bed --threads 2 --out $T/a_rfmaf > /dev/null; cp $T/a_rfmaf.bim a_rfmaf.bim   # --maf on loaded frequencies
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

@@ -300,6 +300,36 @@ def test_filters_and_make_bed_match_reference(tmp_path, case):
         assert "duplicate ID in --keep" in r.stdout
 
 
+QC_CASES = [
+    (["--bfile", "x"], ["--keep", "x_keep1.txt", "x_keep2.txt", "--mind", "0.035", "--geno", "0.02", "--maf", "0.05"], "x_qc", ("bed", "bim", "fam", "mindrem.id")),
+    (["--bfile", "x"], ["--keep-founders", "--mac", "30", "--max-maf", "0.45"], "x_mac", ("bim", "fam")),
+    (["--bfile", "x"], ["--remove-nosex", "--keep-nonfounders"], "x_sex", ("fam",)),
+    (["--pgen", "a_mode10.pgen", "--pvar", "a.pvar", "--psam", "a.psam"], ["--geno", "0.03", "--mind", "0.04", "--maf", "0.2"], "a_qc", ("bed", "bim", "fam")),
+    (["--bfile", "a"], ["--read-freq", "a_rf.afreq", "--exclude", "x_exclude.txt", "--maf", "0.3"], "a_rfmaf", ("bim",)),  # thresholds on LOADED frequencies
+]
+
+
+@pytest.mark.parametrize("case", range(len(QC_CASES)))
+def test_count_based_filters_match_reference(tmp_path, case):
+    """--mind, --geno, --maf / --max-maf / --mac and the sex / founder filters: one host counting pass over the view
+    (chrY missingness over males only, founder frequencies with the chrX / chrY / MT allele accounting of --freq),
+    thresholds with the reference's 2^-44 guard.  Same survivors as the reference, byte for byte, through --make-bed."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    data, filt, gold, exts = QC_CASES[case]
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN] + data + filt + ["--make-bed", "--threads", "3", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in exts:
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, gold + "." + ext), "rb").read(), ext
+    if case == 0:
+        assert "27 samples removed due to missing genotype data (--mind)." in r.stdout
+        assert "--geno: 283 variants removed" in r.stdout and "65 variants removed due to allele frequency threshold(s)" in r.stdout
+    if case == 1:
+        # nonfounders present: the reference refuses allele-count thresholds without --ac-founders / --nonfounders
+        r = subprocess.run([BIN] + data + ["--mac", "30", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+        assert r.returncode == 7 and "nonfounders are present" in r.stdout
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
