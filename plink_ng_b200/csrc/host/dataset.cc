@@ -171,8 +171,10 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     out->bp.push_back(static_cast<uint32_t>(strtoul(t[cpos].c_str(), nullptr, 10)));
     out->id.push_back(t[col_id]);
     out->chr_name.push_back(t[col_chr]);
-    out->ref.push_back(cref >= 0 && cref < static_cast<int>(t.size()) ? t[cref] : std::string("."));
-    out->alt.push_back(calt >= 0 && calt < static_cast<int>(t.size()) ? t[calt] : std::string("."));
+    // a lone '0' is the input missing-allele code and is stored as '.' (LoadPvar, plink2_pvar.cc: input_missing_geno_char)
+    auto allele = [&](int col) { return col >= 0 && col < static_cast<int>(t.size()) && t[col] != "0" ? t[col] : std::string("."); };
+    out->ref.push_back(allele(cref));
+    out->alt.push_back(allele(calt));
     if (col_cm >= 0) out->cm.push_back(ccm >= 0 && ccm < static_cast<int>(t.size()) ? t[ccm] : std::string("0"));
   }
   return true;

@@ -227,6 +227,32 @@ int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* 
       log->push_back(std::to_string(m - left) + " variant" + (m - left == 1 ? "" : "s") + " excluded by chromosome filter, " + std::to_string(left) + " remaining.");
       changed = true;
     }
+    if (spec.snps_only) {
+      auto acgt_or_missing = [](char ch) { return ch == '.' || ch == '0' || strchr("ACGTacgt", ch) != nullptr; };
+      uint32_t left = 0;
+      for (uint32_t v = 0; v < m; ++v) {
+        if (keep[v]) {
+          bool ok = V.ref[v].size() == 1 && V.alt[v].size() == 1;
+          if (ok && spec.snps_only == 2) ok = acgt_or_missing(V.ref[v][0]) && acgt_or_missing(V.alt[v][0]);
+          keep[v] = ok;
+          left += ok;
+        }
+      }
+      log->push_back("--snps-only: " + Plural(left, "variant") + " remaining.");
+      changed = true;
+    }
+    if (spec.from_bp != -1 || spec.to_bp != -1) {
+      uint32_t left = 0;
+      for (uint32_t v = 0; v < m; ++v) {
+        if (keep[v]) {
+          const int64_t bp = V.bp[v];
+          keep[v] = (spec.from_bp == -1 || bp >= spec.from_bp) && (spec.to_bp == -1 || bp <= spec.to_bp);
+          left += keep[v];
+        }
+      }
+      log->push_back("--from-bp/--to-bp: " + Plural(left, "variant") + " remaining.");
+      changed = true;
+    }
     for (int pass = 0; pass < 2; ++pass) {
       const std::vector<std::string>& files = pass ? spec.exclude : spec.extract;
       if (files.empty()) continue;

@@ -98,6 +98,7 @@ struct Cmd {
   double king_cutoff_table_thresh = -1;
   FilterSpec filters;                     // --keep / --remove / --keep-fam / --remove-fam / --extract / --exclude / --chr / --not-chr / --autosome[-xy]
   bool make_bed = false;                  // --make-bed: the filtered view as .bed/.bim/.fam (host-only)
+  bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
   std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
   double king_cutoff_prefix_thresh = -1;
@@ -427,6 +428,30 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--autosome" || flag == "--autosome-xy" || flag == "--autosome-par") {
       if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
       (flag == "--autosome" ? c->filters.autosome : c->filters.autosome_xy) = true;
+    } else if (flag == "--snps-only") {
+      if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "just-acgt"))) return Usage("Invalid --snps-only argument (only 'just-acgt' is accepted).");
+      c->filters.snps_only = 1 + nparam;
+    } else if (flag == "--from-bp" || flag == "--from-kb" || flag == "--from-mb" || flag == "--to-bp" || flag == "--to-kb" || flag == "--to-mb") {
+      // plink2.cc:6221-6249, :11986-12014: lower bounds round up, upper bounds down, both with the 2^-44 guard
+      const bool is_from = flag[2] == 'f';
+      double dxx;
+      if (!need(1, 1) || !ParseDouble(prm[0], &dxx)) return Usage(("Invalid " + flag + " argument.").c_str());
+      const char unit = flag[flag.size() - 2];
+      if (unit == 'k') dxx *= 1000;
+      else if (unit == 'm') dxx *= 1000000;
+      const double eps = 1.0 / 17592186044416.0;
+      if (is_from) {
+        if (c->filters.from_bp != -1) return Usage("Multiple --from-bp/-kb/-mb values.");
+        if (dxx > 2147483646.0) return Usage("--from-bp/-kb/-mb argument too large.");
+        c->filters.from_bp = dxx <= 0.0 ? 0 : 1 + static_cast<int32_t>(dxx * (1 - eps));
+      } else {
+        if (c->filters.to_bp != -1) return Usage("Multiple --to-bp/-kb/-mb values.");
+        if (dxx < 0) return Usage("Negative --to-bp/-kb/-mb argument.");
+        c->filters.to_bp = dxx >= 2147483646.0 ? 0x7ffffffe : static_cast<int32_t>(dxx * (1 + eps));
+      }
+    } else if (flag == "--write-snplist" || flag == "--write-samples") {
+      if (!need(0, 0)) return Usage((flag + " modifiers are not supported by plink2_b200.").c_str());
+      (flag == "--write-snplist" ? c->write_snplist : c->write_samples) = true;
     } else if (flag == "--keep-founders" || flag == "--keep-nonfounders") {
       if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
       if (c->filters.founders_only) return Usage("--keep-nonfounders cannot be used with --keep-founders.");
@@ -561,7 +586,13 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     }
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->make_bed || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (c->filters.from_bp != -1 || c->filters.to_bp != -1) {
+    uint32_t named = 0;
+    for (uint8_t f : c->filters.chr_mask) named += f;
+    if (named != 1) return Usage("--from-bp/-kb/-mb and --to-bp/-kb/-mb must be used with --chr, and only one chromosome.");
+    if (c->filters.from_bp != -1 && c->filters.to_bp != -1 && c->filters.from_bp > c->filters.to_bp) return Usage("--to-bp/-kb/-mb argument is smaller than --from-bp/-kb/-mb argument.");
+  }
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->make_bed || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -3531,6 +3562,24 @@ int main(int argc, char** argv) {
     rc = ApplyCountFilters(c, &ds);
     if (rc) return rc;
   }
+  if (c.write_snplist) {  // WriteSnplist / --write-samples (plink2.cc:2030-2062): what the main filters left
+    OutFile f;
+    const std::string name = c.out + ".snplist";
+    if (!f.Open(name)) return kRetOpenFail;
+    for (const std::string& id : ds.variants.id) {
+      f.Write(id.data(), id.size());
+      f.Write("\n", 1);
+    }
+    if (!f.Close()) return kRetWriteFail;
+    logprintf("--write-snplist: Variant IDs written to %s .\n", name.c_str());
+  }
+  if (c.write_samples) {
+    std::vector<uint32_t> all(ds.samples.size());
+    for (uint32_t k = 0; k < all.size(); ++k) all[k] = k;
+    const std::string name = c.out + ".id";
+    if (!WriteIdFile(name, ds.samples, all, true)) return kRetWriteFail;
+    logprintf("--write-samples: Sample IDs written to %s .\n", name.c_str());
+  }
   g_clock.Mark("load .psam/.pvar, open .pgen");
   // ---- relatedness prune from a file, then the commands that see its survivors (Plink2Core order, plink2.cc:2523-2581)
   std::vector<uint8_t> cutoff_removed;
@@ -3580,7 +3629,8 @@ int main(int argc, char** argv) {
       rc = write_bed();
       if (rc) return rc;
     }
-    return 0;  // file-driven pruning and --make-bed are host-only in the reference as well: no device is needed
+    return 0;  // (--write-snplist / --write-samples were written above)
+    // file-driven pruning and --make-bed are host-only in the reference as well: no device is needed
   }
   g_decode_threads = EffectiveHostThreads(c.threads);
   if (ctx_thread.joinable()) ctx_thread.join();

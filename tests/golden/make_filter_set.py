@@ -24,3 +24,13 @@ open("s_keepfam.txt", "w").write("\n".join(fids[:3]) + "\n")
 open("s_removefam.txt", "w").write(fids[1] + "\n")
 ks = rnd.sample(fam, 150)
 open("s_keep_iid.txt", "w").write("#IID\n" + "".join("%s\n" % f[1] for f in ks))
+# set X's .bim with awkward allele codes for --snps-only [just-acgt]: indels, symbolic alleles, lower case, missing codes
+rnd = random.Random(3)
+rows = [l.rstrip("\n").split("\t") for l in open("x.bim")]
+codes = ["A", "C", "G", "T", "a", "c", "N", "AT", "GCC", ".", "0", "*", "I", "D", "<DEL>", "t"]
+for r in rows:
+    if rnd.random() < 0.4:
+        r[4] = rnd.choice(codes)
+    if rnd.random() < 0.25:
+        r[5] = rnd.choice(codes)
+open("x_alleles.bim", "w").write("".join("\t".join(r) + "\n" for r in rows))

@@ -111,6 +111,10 @@ $P --bfile x --remove-nosex --keep-nonfounders --make-bed --threads 2 --out $T/x
 $P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --geno 0.03 --mind 0.04 --maf 0.2 --make-bed --threads 2 --out $T/a_qc > /dev/null
 for e in bed bim fam; do cp $T/a_qc.$e a_qc.$e; done
 $P --bfile a --read-freq a_rf.afreq --exclude x_exclude.txt --maf 0.3 --make-bed --threads 2 --out $T/a_rfmaf > /dev/null; cp $T/a_rfmaf.bim a_rfmaf.bim   # --maf on loaded frequencies
+# --snps-only [just-acgt] on awkward allele codes (x_alleles.bim), --from-kb/--to-kb, --write-snplist / --write-samples
+$P --bed x.bed --bim x_alleles.bim --fam x.fam --snps-only --make-bed --threads 2 --out $T/s1 > /dev/null; cp $T/s1.bim x_snps.bim
+$P --bed x.bed --bim x_alleles.bim --fam x.fam --snps-only just-acgt --make-bed --threads 2 --out $T/s2 > /dev/null; cp $T/s2.bim x_acgt.bim
+$P --bfile x --chr 1 --from-kb 0.1001 --to-kb 0.25 --keep x_keep2.txt --write-snplist --write-samples --threads 2 --out $T/s3 > /dev/null; cp $T/s3.snplist x_bp.snplist; cp $T/s3.id x_bp.id
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

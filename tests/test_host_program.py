@@ -330,6 +330,24 @@ def test_count_based_filters_match_reference(tmp_path, case):
         assert r.returncode == 7 and "nonfounders are present" in r.stdout
 
 
+def test_allele_and_position_filters_and_id_lists(tmp_path):
+    """--snps-only [just-acgt] on a .bim with indels, symbolic alleles, lower case and both missing-allele codes (a lone
+    '0' is stored and written as '.'), --chr + --from-kb/--to-kb (lower bound rounded up, upper bound down), and the
+    --write-snplist / --write-samples lists of what the filters left - all as the reference writes them."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    for mod, gold in (([], "x_snps.bim"), (["just-acgt"], "x_acgt.bim")):
+        r = subprocess.run([BIN, "--bed", "x.bed", "--bim", "x_alleles.bim", "--fam", "x.fam", "--snps-only"] + mod + ["--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert open(out + ".bim", "rb").read() == open(os.path.join(gd, gold), "rb").read(), gold
+    r = subprocess.run([BIN, "--bfile", "x", "--chr", "1", "--from-kb", "0.1001", "--to-kb", "0.25", "--keep", "x_keep2.txt", "--write-snplist", "--write-samples", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".snplist", "rb").read() == open(os.path.join(gd, "x_bp.snplist"), "rb").read()
+    assert open(out + ".id", "rb").read() == open(os.path.join(gd, "x_bp.id"), "rb").read()
+    r = subprocess.run([BIN, "--bfile", "x", "--chr", "1,2", "--from-bp", "5", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "only one chromosome" in r.stdout + r.stderr
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
