@@ -174,6 +174,7 @@ bool ParseKingCols(const std::string& spec, Cmd* c) {
 
 int ParseArgs(int argc, char** argv, Cmd* c) {
   std::string bfile, pfile, bed, bim, fam;
+  bool pfile_vzs = false;
   for (int i = 1; i < argc;) {
     const std::string flag = argv[i];
     int j = i + 1;
@@ -185,8 +186,10 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (!need(1, 1)) return Usage("--bfile requires a prefix.");
       bfile = prm[0];
     } else if (flag == "--pfile") {
-      if (!need(1, 1)) return Usage("--pfile requires a prefix.");
+      // 'vzs': the .pvar is Zstandard-compressed (<prefix>.pvar.zst), plink2.cc --pfile
+      if (!need(1, 2) || (nparam == 2 && strcmp(prm[1], "vzs"))) return Usage("--pfile requires a prefix (optionally followed by 'vzs').");
       pfile = prm[0];
+      pfile_vzs = nparam == 2;
     } else if (flag == "--bed" || flag == "--pgen") {
       if (!need(1, 1)) return Usage("--bed/--pgen requires a filename.");
       c->pgen = prm[0];
@@ -564,7 +567,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     c->psam = bfile + ".fam";
   } else if (!pfile.empty()) {
     c->pgen = pfile + ".pgen";
-    c->pvar = pfile + ".pvar";
+    c->pvar = pfile + (pfile_vzs ? ".pvar.zst" : ".pvar");
     c->psam = pfile + ".psam";
   }
   if (!c->gpu_memory_mib) {

@@ -1,5 +1,7 @@
 #include "text_util.h"
 
+#include <algorithm>
+
 #include <dlfcn.h>
 
 #include <cfloat>
@@ -380,16 +382,157 @@ std::vector<std::string> SplitWs(const std::string& line) {
   return out;
 }
 
+namespace {
+// Streaming decompressors resolved at run time (no link-time dependency, like the 'zs' writer): zstd for .zst input,
+// zlib for gzip / bgzf input.  The reference's TextStream reads all three transparently for every text input
+// (2.0/include/plink2_text.cc: plain / gzip / bgzf / zstd by magic number), so --pfile ... vzs, a .kin0.zst written by a
+// previous run, or a gzipped score file just work.
+struct ZInBuf {
+  const void* src;
+  size_t size, pos;
+};
+struct ZOutBuf {
+  void* dst;
+  size_t size, pos;
+};
+bool ZstdDecompressAll(const std::string& in, std::string* out, std::string* err) {
+  void* h = dlopen("libzstd.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libzstd.so", RTLD_NOW | RTLD_GLOBAL);
+  auto create = h ? reinterpret_cast<void* (*)()>(dlsym(h, "ZSTD_createDStream")) : nullptr;
+  auto release = h ? reinterpret_cast<size_t (*)(void*)>(dlsym(h, "ZSTD_freeDStream")) : nullptr;
+  auto step = h ? reinterpret_cast<size_t (*)(void*, ZOutBuf*, ZInBuf*)>(dlsym(h, "ZSTD_decompressStream")) : nullptr;
+  auto is_error = h ? reinterpret_cast<unsigned (*)(size_t)>(dlsym(h, "ZSTD_isError")) : nullptr;
+  if (!create || !release || !step || !is_error) {
+    *err = "libzstd is not available to read a Zstandard-compressed input file.";
+    return false;
+  }
+  void* ds = create();
+  std::vector<char> chunk(1 << 20);
+  ZInBuf ib{in.data(), in.size(), 0};
+  size_t last = 0;
+  while (ib.pos < ib.size) {  // concatenated frames: a return value of 0 ends a frame, the next call starts the next
+    ZOutBuf ob{chunk.data(), chunk.size(), 0};
+    last = step(ds, &ob, &ib);
+    if (is_error(last)) {
+      release(ds);
+      *err = "Malformed Zstandard stream.";
+      return false;
+    }
+    out->append(chunk.data(), ob.pos);
+  }
+  for (;;) {  // drain what is still buffered inside the decoder
+    ZOutBuf ob{chunk.data(), chunk.size(), 0};
+    const size_t rc = step(ds, &ob, &ib);
+    if (is_error(rc)) break;
+    out->append(chunk.data(), ob.pos);
+    if (!ob.pos) break;
+  }
+  release(ds);
+  if (last != 0) {
+    *err = "Truncated Zstandard stream.";
+    return false;
+  }
+  return true;
+}
+
+// zlib's z_stream, as laid out by every zlib 1.2+ build on LP64
+struct ZStream {
+  const unsigned char* next_in;
+  unsigned avail_in;
+  unsigned long total_in;
+  unsigned char* next_out;
+  unsigned avail_out;
+  unsigned long total_out;
+  const char* msg;
+  void* state;
+  void* zalloc;
+  void* zfree;
+  void* opaque;
+  int data_type;
+  unsigned long adler, reserved;
+};
+bool GzipDecompressAll(const std::string& in, std::string* out, std::string* err) {
+  void* h = dlopen("libz.so.1", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libz.so", RTLD_NOW | RTLD_GLOBAL);
+  auto init2 = h ? reinterpret_cast<int (*)(ZStream*, int, const char*, int)>(dlsym(h, "inflateInit2_")) : nullptr;
+  auto inflate = h ? reinterpret_cast<int (*)(ZStream*, int)>(dlsym(h, "inflate")) : nullptr;
+  auto reset = h ? reinterpret_cast<int (*)(ZStream*)>(dlsym(h, "inflateReset")) : nullptr;
+  auto end = h ? reinterpret_cast<int (*)(ZStream*)>(dlsym(h, "inflateEnd")) : nullptr;
+  auto version = h ? reinterpret_cast<const char* (*)()>(dlsym(h, "zlibVersion")) : nullptr;
+  if (!init2 || !inflate || !reset || !end || !version) {
+    *err = "zlib is not available to read a gzip-compressed input file.";
+    return false;
+  }
+  ZStream zs;
+  memset(&zs, 0, sizeof(zs));
+  if (init2(&zs, 15 + 16, version(), static_cast<int>(sizeof(ZStream))) != 0) {
+    *err = "zlib initialisation failed.";
+    return false;
+  }
+  std::vector<unsigned char> chunk(1 << 20);
+  zs.next_in = reinterpret_cast<const unsigned char*>(in.data());
+  size_t left = in.size();
+  bool ok = true;
+  while (left || zs.avail_in) {
+    if (!zs.avail_in) {
+      const unsigned take = static_cast<unsigned>(std::min<size_t>(left, 1u << 30));
+      zs.avail_in = take;
+      left -= take;
+    }
+    zs.next_out = chunk.data();
+    zs.avail_out = static_cast<unsigned>(chunk.size());
+    const int rc = inflate(&zs, 0);
+    out->append(reinterpret_cast<const char*>(chunk.data()), chunk.size() - zs.avail_out);
+    if (rc == 1) {  // Z_STREAM_END: bgzf and `cat a.gz b.gz` are sequences of members
+      if (!zs.avail_in && !left) break;
+      reset(&zs);
+    } else if (rc != 0) {
+      ok = false;
+      break;
+    }
+  }
+  end(&zs);
+  if (!ok) *err = "Malformed gzip stream.";
+  return ok;
+}
+}  // namespace
+
 bool ReadLines(const std::string& path, std::vector<std::string>* lines, std::string* err) {
-  std::ifstream in(path);
-  if (!in) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
     *err = "Failed to open " + path + ".";
     return false;
   }
-  std::string ln;
-  while (std::getline(in, ln)) {
-    if (!ln.empty() && ln.back() == '\r') ln.pop_back();
-    lines->push_back(ln);
+  std::string raw;
+  {
+    std::vector<char> chunk(1 << 20);
+    size_t got;
+    while ((got = fread(chunk.data(), 1, chunk.size(), f)) > 0) raw.append(chunk.data(), got);
+    fclose(f);
+  }
+  std::string text;
+  const unsigned char* b = reinterpret_cast<const unsigned char*>(raw.data());
+  if (raw.size() >= 4 && b[0] == 0x28 && b[1] == 0xB5 && b[2] == 0x2F && b[3] == 0xFD) {
+    if (!ZstdDecompressAll(raw, &text, err)) {
+      *err += " (" + path + ")";
+      return false;
+    }
+  } else if (raw.size() >= 2 && b[0] == 0x1F && b[1] == 0x8B) {
+    if (!GzipDecompressAll(raw, &text, err)) {
+      *err += " (" + path + ")";
+      return false;
+    }
+  } else {
+    text.swap(raw);
+  }
+  size_t pos = 0;
+  while (pos < text.size()) {
+    size_t end = text.find('\n', pos);
+    if (end == std::string::npos) end = text.size();
+    size_t stop = end;
+    if (stop > pos && text[stop - 1] == '\r') --stop;
+    lines->emplace_back(text, pos, stop - pos);
+    pos = end + 1;
   }
   return true;
 }

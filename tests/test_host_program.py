@@ -348,6 +348,39 @@ def test_allele_and_position_filters_and_id_lists(tmp_path):
     assert r.returncode != 0 and "only one chromosome" in r.stdout + r.stderr
 
 
+def test_compressed_text_inputs(tmp_path):
+    """Every text input goes through one reader that recognises Zstandard and gzip (incl. multi-member / bgzf) by magic
+    number, like the reference's TextStream: a .pvar.zst written by the reference, gzipped ID lists (one of them two
+    concatenated members), the gzipped golden .kin0 as a --king-cutoff-table input, and a .zst written by this program's
+    own 'zs' writer fed back in."""
+    import gzip
+
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bed", "x.bed", "--pvar", "x.pvar.zst", "--fam", "x.fam", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".bim", "rb").read() == open(os.path.join(gd, "x.bim"), "rb").read()
+    assert open(out + ".bed", "rb").read() == open(os.path.join(gd, "x.bed"), "rb").read()
+    k1 = open(os.path.join(gd, "x_keep1.txt"), "rb").read().split(b"\n")
+    (tmp_path / "k1.gz").write_bytes(gzip.compress(b"\n".join(k1[:5]) + b"\n") + gzip.compress(b"\n".join(k1[5:])))
+    (tmp_path / "k2.gz").write_bytes(gzip.compress(open(os.path.join(gd, "x_keep2.txt"), "rb").read()))
+    r = subprocess.run([BIN, "--bfile", "x", "--keep", str(tmp_path / "k1.gz"), str(tmp_path / "k2.gz"), "--remove", "x_remove.txt", "--extract", "x_extract.txt", "--exclude", "x_exclude.txt", "--make-bed", "--out", out],
+                       capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("bed", "bim", "fam"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "x_filt." + ext), "rb").read(), ext
+    r = subprocess.run([BIN, "--bfile", "a", "--king-cutoff-table", "a_kingp.kin0.gz", "0.02", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0 and "661 constraints loaded" in r.stdout
+    (tmp_path / "in.kin0").write_bytes(gzip.open(os.path.join(gd, "a_kingp.kin0.gz"), "rb").read())
+    assert subprocess.run([BIN, "--debug-zst", str(tmp_path / "in.kin0"), str(tmp_path / "in.kin0.zst")]).returncode == 0
+    r = subprocess.run([BIN, "--bfile", "a", "--king-cutoff-table", str(tmp_path / "in.kin0.zst"), "0.02", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0 and "661 constraints loaded" in r.stdout
+    assert open(out + ".king.cutoff.in.id", "rb").read() == open(os.path.join(gd, "a_kct.king.cutoff.in.id"), "rb").read()
+    (tmp_path / "bad.zst").write_bytes(open(tmp_path / "in.kin0.zst", "rb").read()[:200])
+    r = subprocess.run([BIN, "--bfile", "a", "--king-cutoff-table", str(tmp_path / "bad.zst"), "0.02", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "Zstandard" in r.stdout
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
