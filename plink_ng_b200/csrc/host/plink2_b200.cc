@@ -30,6 +30,7 @@
 #include "dataset.h"
 #include "filters.h"
 #include "pca.h"
+#include "ped_import.h"
 #include "sfmt.h"
 #include "text_util.h"
 
@@ -68,6 +69,8 @@ PhaseClock g_clock;
 
 struct Cmd {
   std::string pgen, pvar, psam, out = "plink2";
+  std::string ped, map;           // --ped + --map / --pedmap: legacy text fileset, converted to <out>-temporary.bed/.bim/.fam first
+  bool keep_autoconv = false;     // --keep-autoconv: leave the converted fileset in place (as <out>.bed/.bim/.fam)
   uint32_t parallel_idx = 0, parallel_tot = 1;
   uint32_t threads = 0;
   uint64_t seed = 0;
@@ -199,6 +202,16 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--fam" || flag == "--psam") {
       if (!need(1, 1)) return Usage("--fam/--psam requires a filename.");
       c->psam = prm[0];
+    } else if (flag == "--ped" || flag == "--map") {
+      if (!need(1, 1)) return Usage((flag + " requires a filename.").c_str());
+      (flag == "--ped" ? c->ped : c->map) = prm[0];
+    } else if (flag == "--pedmap") {
+      if (!need(1, 1)) return Usage("--pedmap requires a prefix.");
+      c->ped = std::string(prm[0]) + ".ped";
+      c->map = std::string(prm[0]) + ".map";
+    } else if (flag == "--keep-autoconv") {
+      if (!need(0, 0)) return Usage("--keep-autoconv modifiers are not supported by plink2_b200.");
+      c->keep_autoconv = true;
     } else if (flag == "--out") {
       if (!need(1, 1)) return Usage("--out requires a prefix.");
       c->out = prm[0];
@@ -574,6 +587,14 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     const char* e = getenv("PL2_GPU_MEM_MIB");
     uint32_t mib;
     if (e && ParseU32(e, &mib)) c->gpu_memory_mib = mib;
+  }
+  if (!c->ped.empty() || !c->map.empty()) {
+    if (c->ped.empty() || c->map.empty()) return Usage("--ped and --map must be used together (or use --pedmap <prefix>).");
+    if (!c->pgen.empty() || !c->pvar.empty() || !c->psam.empty()) return Usage("--ped/--map cannot be combined with another input fileset.");
+    const std::string prefix = c->out + (c->keep_autoconv ? "" : "-temporary");
+    c->pgen = prefix + ".bed";
+    c->pvar = prefix + ".bim";
+    c->psam = prefix + ".fam";
   }
   if (c->pgen.empty() || c->pvar.empty() || c->psam.empty()) return Usage("No input dataset (--bfile / --pfile / --bed+--bim+--fam / --pgen+--pvar+--psam).");
   if (!c->indep_preferred.empty() && !c->indep_pairwise) return Usage("--indep-preferred must be used with --indep-pairwise.");
@@ -3515,6 +3536,26 @@ int main(int argc, char** argv) {
   }
   Dataset ds;
   std::string err;
+  // --ped/--map: convert first (PedmapToPgen's role); the temporary fileset is removed when the run ends
+  struct TempFileset {
+    std::vector<std::string> paths;
+    void Remove() {
+      for (const std::string& p : paths) unlink(p.c_str());
+      paths.clear();
+    }
+    ~TempFileset() { Remove(); }
+  } temp_files;
+  if (!c.ped.empty()) {
+    const std::string prefix = c.pgen.substr(0, c.pgen.size() - 4);
+    uint32_t pn = 0, pm = 0;
+    rc = PedmapToBed(c.ped, c.map, prefix, &pn, &pm, &err);
+    if (!c.keep_autoconv) temp_files.paths = {c.pgen, c.pvar, c.psam};
+    if (rc) {
+      logprintf("Error: %s\n", err.c_str());
+      return rc;
+    }
+    logprintf("--pedmap: %u sample%s, %u variant%s; %s.bed + %s.bim + %s.fam written%s.\n", pn, pn == 1 ? "" : "s", pm, pm == 1 ? "" : "s", prefix.c_str(), prefix.c_str(), prefix.c_str(), c.keep_autoconv ? "" : " (temporary)");
+  }
   if (!LoadSamples(c.psam, &ds.samples, &err) || !LoadVariants(c.pvar, &ds.variants, &err)) {
     logprintf("Error: %s\n", err.c_str());
     return kRetOpenFail;
@@ -3722,5 +3763,6 @@ int main(int argc, char** argv) {
   fflush(stderr);
   // All output files are closed.  Skip the explicit CUDA teardown (context destroy + pinned-memory
   // unmapping cost ~1.4 s here); the driver reclaims the device when the process exits.
+  temp_files.Remove();
   _exit(0);
 }

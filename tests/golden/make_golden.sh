@@ -157,6 +157,10 @@ if [ -x $PL ]; then
   $PL --bfile a --pca 3 approx --seed 11 --threads 2 --out $T/a_pcaa > /dev/null
   cp $T/a_pcaa.eigenval a_pcaa.eigenval; cp $T/a_pcaa.eigenvec a_pcaa.eigenvec
 fi
+# --- set P: legacy text filesets (make_ped_set.py) through the reference's --pedmap import
+python make_ped_set.py
+$P --pedmap p --make-bed --threads 2 --out $T/p > /dev/null; for e in bed bim fam; do cp $T/p.$e p.$e; done
+$P --ped pc.ped --map pc.map --make-bed --threads 2 --out $T/pc > /dev/null; cp $T/pc.bed pc.bed; cp $T/pc.bim pc.bim
 # --- set T: the reference's own toy fixture (1.9/toy.ped + toy.map; BASELINE.json configs[0])
 if [ -f /root/reference/1.9/toy.ped ]; then
   $P --ped /root/reference/1.9/toy.ped --map /root/reference/1.9/toy.map --make-bed --out $T/toy > /dev/null

@@ -381,6 +381,40 @@ def test_compressed_text_inputs(tmp_path):
     assert r.returncode != 0 and "Zstandard" in r.stdout
 
 
+def test_ped_map_import_matches_reference(tmp_path):
+    """--pedmap / --ped + --map: the legacy text fileset is converted to a temporary binary fileset first (REF = major
+    allele, provisional alleles in order of appearance, negative-bp variants dropped, both .ped layouts), then read
+    like any other input.  --make-bed of the result is byte-identical to the reference's for set P (multi-character
+    alleles, missing calls, comment line, 4-column .map) and its compound-genotypes twin; the temporary files are gone
+    afterwards; half-missing and third-allele calls are refused with the reference's messages."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--pedmap", "p", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("bed", "bim", "fam"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "p." + ext), "rb").read(), ext
+    assert not [f for f in os.listdir(tmp_path) if "temporary" in f]
+    r = subprocess.run([BIN, "--ped", "pc.ped", "--map", "pc.map", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("bed", "bim"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "pc." + ext), "rb").read(), ext
+    (tmp_path / "h.map").write_text("1 v1 0 10\n1 v2 0 20\n")
+    (tmp_path / "h.ped").write_text("0 a 0 0 1 1 A A C 0\n")
+    r = subprocess.run([BIN, "--pedmap", str(tmp_path / "h"), "--make-bed", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 6 and "Half-missing genotype on line 1" in r.stdout
+    (tmp_path / "h.ped").write_text("0 a 0 0 1 1 A C G G\n0 b 0 0 1 1 A T G G\n")
+    r = subprocess.run([BIN, "--pedmap", str(tmp_path / "h"), "--make-bed", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 6 and "Multiallelic variant" in r.stdout
+    # BASELINE.json configs[0] is a .ped/.map pair (2 samples x 2 variants, one all-missing call, one unseen ALT): its
+    # content, typed in here, must import to the toy.bed/.bim/.fam the reference produced from its own copy
+    (tmp_path / "toy.ped").write_text("1 1000000000 0 0 1 1 0 0 A A\n1 1000000001 0 0 1 2 C C A G\n")
+    (tmp_path / "toy.map").write_text("1\trs0\t0\t1000\n1\trs10\t0\t1001\n")
+    r = subprocess.run([BIN, "--pedmap", str(tmp_path / "toy"), "--make-bed", "--out", out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("bed", "bim", "fam"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "toy." + ext), "rb").read(), ext
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
