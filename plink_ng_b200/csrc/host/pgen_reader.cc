@@ -392,9 +392,14 @@ bool PgenReader::GetBlock(const uint32_t* view_vidx, uint32_t count, const uint6
   }
   thread_ct = std::max(1u, std::min(thread_ct, (count + 255) / 256));  // at least 256 variants per worker
   if (thread_ct == 1) {
+    // own decode state (not state_): GetBlock may be called from several host threads at once (one per device in the
+    // multi-GPU LD prune), and a short block must not share the LD-base cache of Get / GetSubset
+    DecodeState st;
+    st.ldbase.assign(WordsFor(raw_sample_ct_), 0);
+    st.scratch.assign(WordsFor(raw_sample_ct_), 0);
     for (uint32_t k = 0; k < count; ++k) {
       uint64_t* row = dst + static_cast<uint64_t>(k) * stride_words;
-      if (!(sample_include ? GetSubsetWith(&state_, vidx[k], sample_include, sample_ct, row, err) : DecodeRecord(&state_, vidx[k], row, err))) return false;
+      if (!(sample_include ? GetSubsetWith(&st, vidx[k], sample_include, sample_ct, row, err) : DecodeRecord(&st, vidx[k], row, err))) return false;
     }
     return true;
   }

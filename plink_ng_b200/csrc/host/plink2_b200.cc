@@ -12,6 +12,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
 #include <unordered_map>
 #include <chrono>
 #include <cfloat>
@@ -703,6 +704,7 @@ struct BlockStreamer {
   uint32_t cap;
   size_t pos = 0;
   uint32_t spare = 0;  // extra rows behind the block (filler for sharded uploads)
+  uint32_t threads = 0;  // decode threads for this streamer (0: g_decode_threads)
   BlockStreamer(Dataset* d, const std::vector<uint32_t>* v, uint32_t n_samples, uint32_t batch, uint32_t spare_rows = 0) : ds(d), vidx(v), sample_ct(n_samples), words(PgenReader::WordsFor(n_samples)), cap(batch), spare(spare_rows) {}
   ~BlockStreamer() { pl2gpu_host_free(buf); }
   bool Init() {
@@ -716,7 +718,7 @@ struct BlockStreamer {
   int Next(std::string* err) {
     const uint32_t n = static_cast<uint32_t>(std::min<size_t>(cap, vidx->size() - pos));
     if (!n) return 0;
-    if (!ds->reader.GetBlock(vidx->data() + pos, n, sample_include, sample_ct, buf, words, g_decode_threads, err)) return -1;
+    if (!ds->reader.GetBlock(vidx->data() + pos, n, sample_include, sample_ct, buf, words, threads ? threads : g_decode_threads, err)) return -1;
     pos += n;
     return static_cast<int>(n);
   }
@@ -3228,30 +3230,87 @@ int RunLdPrune(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     }
     s0 = e;
   }
-  // one pinned buffer of the longest run; every run is decoded straight into it (BlockStreamer's own buffer)
-  std::vector<uint32_t> vsub;
-  BlockStreamer bs(ds, &vsub, founder_ct, std::max(longest, 1u));
-  if (founder_ct != n) bs.sample_include = inc.data();
-  if (longest && !bs.Init()) return GpuFail("pl2gpu_host_alloc");
-  double t_decode = 0, t_device = 0;
-  for (const ChrRun& run : chr_runs) {
-    vsub.resize(run.v1 - run.v0);
-    for (uint32_t v = run.v0; v < run.v1; ++v) vsub[v - run.v0] = v;
-    bs.Rewind();
-    std::string err;
-    auto tp = std::chrono::steady_clock::now();
-    const int got = bs.Next(&err);
-    if (got != static_cast<int>(run.v1 - run.v0)) {
-      logprintf("Error: %s\n", got < 0 ? err.c_str() : "short read");
-      return kRetMalformedInput;
+  // One worker per device ("LD prune = chromosomes -> GPUs, no collective"): each owns a pinned
+  // buffer of the longest run, decodes a run straight into it and hands it to the function-face entry point on ITS
+  // context; runs are taken largest first from a shared counter and write disjoint slices of `removed`.  With one
+  // device this is the plain loop over the runs in file order.
+  const uint32_t worker_ct = std::max(1u, std::min<uint32_t>({c.gpus, static_cast<uint32_t>(chr_runs.size()), static_cast<uint32_t>(std::max(1, pl2gpu_device_count() - c.device))}));
+  if (c.gpus > 1 && worker_ct < c.gpus) logprintf("Note: --indep-pairwise on %u GPU%s (--gpus %u): one chromosome per device at a time.\n", worker_ct, worker_ct == 1 ? "" : "s", c.gpus);
+  std::vector<Pl2GpuCtx*> ld_ctx(1, ctx);
+  struct CtxGuard {
+    std::vector<Pl2GpuCtx*>* v;
+    ~CtxGuard() {
+      for (size_t g = 1; g < v->size(); ++g) pl2gpu_ctx_destroy((*v)[g]);
     }
-    t_decode += g_clock.Since(tp);
-    tp = std::chrono::steady_clock::now();
-    const int rc = pl2_indep_pairwise_ex(ctx, bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, run.v1 - run.v0, V.chr_code.data() + run.v0, V.bp.data() + run.v0, c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0,
-                                         ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data() + run.v0, preferred.empty() ? nullptr : preferred.data() + run.v0, 0, founder_sex.data(),
-                                         c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data() + run.v0);
-    if (rc) return GpuFail("pl2_indep_pairwise");
-    t_device += g_clock.Since(tp);
+  } ctx_guard{&ld_ctx};
+  for (uint32_t g = 1; g < worker_ct; ++g) {
+    Pl2GpuCtx* cx = nullptr;
+    if (pl2gpu_ctx_create(c.device + static_cast<int>(g), &cx)) return GpuFail("pl2gpu_ctx_create");
+    ld_ctx.push_back(cx);
+  }
+  std::vector<uint32_t> order(chr_runs.size());
+  for (uint32_t k = 0; k < order.size(); ++k) order[k] = k;
+  if (worker_ct > 1) std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return chr_runs[a].v1 - chr_runs[a].v0 > chr_runs[b].v1 - chr_runs[b].v0; });
+  std::atomic<uint32_t> next_run{0};
+  std::vector<double> t_decode_w(worker_ct, 0.0), t_device_w(worker_ct, 0.0);
+  std::vector<int> worker_rc(worker_ct, 0);
+  std::vector<std::string> worker_msg(worker_ct);
+  auto worker = [&](uint32_t g) {
+    std::vector<uint32_t> vsub;
+    BlockStreamer bs(ds, &vsub, founder_ct, std::max(longest, 1u));
+    bs.threads = std::max(1u, g_decode_threads / worker_ct);
+    if (founder_ct != n) bs.sample_include = inc.data();
+    if (longest && !bs.Init()) {
+      worker_rc[g] = kRetGpuFail;
+      worker_msg[g] = std::string("pl2gpu_host_alloc: ") + pl2gpu_last_error();
+      return;
+    }
+    for (;;) {
+      const uint32_t slot = next_run.fetch_add(1);
+      if (slot >= order.size()) return;
+      for (uint32_t w = 0; w < worker_ct; ++w)
+        if (worker_rc[w]) return;  // another worker failed: stop taking work
+      const ChrRun& run = chr_runs[order[slot]];
+      vsub.resize(run.v1 - run.v0);
+      for (uint32_t v = run.v0; v < run.v1; ++v) vsub[v - run.v0] = v;
+      bs.Rewind();
+      std::string err;
+      auto tp = std::chrono::steady_clock::now();
+      const int got = bs.Next(&err);
+      if (got != static_cast<int>(run.v1 - run.v0)) {
+        worker_rc[g] = kRetMalformedInput;
+        worker_msg[g] = got < 0 ? err : "short read";
+        return;
+      }
+      t_decode_w[g] += g_clock.Since(tp);
+      tp = std::chrono::steady_clock::now();
+      const int rc = pl2_indep_pairwise_ex(ld_ctx[g], bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, run.v1 - run.v0, V.chr_code.data() + run.v0, V.bp.data() + run.v0, c.indep_window, c.indep_step, c.indep_r2, c.indep_kb ? 1 : 0,
+                                           ds->read_ref_freq.empty() ? nullptr : ds->read_ref_freq.data() + run.v0, preferred.empty() ? nullptr : preferred.data() + run.v0, 0, founder_sex.data(),
+                                           c.indep_order1 ? kPl2LdPlink1Order : 0, removed.data() + run.v0);
+      if (rc) {
+        worker_rc[g] = kRetGpuFail;
+        worker_msg[g] = std::string("pl2_indep_pairwise: ") + pl2gpu_last_error();  // thread-local in the library
+        return;
+      }
+      t_device_w[g] += g_clock.Since(tp);
+    }
+  };
+  {
+    std::vector<std::thread> th;
+    for (uint32_t g = 1; g < worker_ct; ++g) th.emplace_back(worker, g);
+    worker(0);
+    for (auto& t : th) t.join();
+  }
+  for (uint32_t g = 0; g < worker_ct; ++g) {
+    if (worker_rc[g]) {
+      logprintf("Error: %s\n", worker_msg[g].c_str());
+      return worker_rc[g];
+    }
+  }
+  double t_decode = 0, t_device = 0;
+  for (uint32_t g = 0; g < worker_ct; ++g) {
+    t_decode = std::max(t_decode, t_decode_w[g]);
+    t_device = std::max(t_device, t_device_w[g]);
   }
   if (g_clock.on) fprintf(stderr, "[timing]   ld: decode %.3f s, counts + pair decisions + greedy walk %.3f s over %zu chromosome run%s\n", t_decode, t_device, chr_runs.size(), chr_runs.size() == 1 ? "" : "s");
   // LdPruneWrite (plink2_ld.cc:2464-2528)
