@@ -13,10 +13,6 @@ for g in 1 2; do
 done
 cmp gpurun_out/ldmg/x1.prune.in gpurun_out/ldmg/x2.prune.in && echo "x: 1 vs 2 GPUs identical" || fail=1
 cmp gpurun_out/ldmg/xk1.prune.in gpurun_out/ldmg/xk2.prune.in && echo "x kb/order1: 1 vs 2 GPUs identical" || fail=1
-python - <<'PY' || fail=1
-import sys
-sys.path.insert(0, ".")
-print("compare gpurun_out/ldmg/x2.prune.in with the golden list used by tests/test_cli_gpu.py (set X, 50 5 0.2) by hand if needed")
-PY
+true
 echo "failures: $fail"
 exit $fail
