@@ -129,6 +129,12 @@ $P --bfile a --king-cutoff 0.02 --make-grm-bin --threads 2 --out $T/g5 > /dev/nu
 $PL --bfile a --king-cutoff-table $T/in.kin0 0.02 --pca 3 --threads 2 --out $T/g6 > /dev/null; cp $T/g6.eigenval g_akct.eigenval; cp $T/g6.eigenvec g_akct.eigenvec
 $P --pgen a_mode10.pgen --pvar a.pvar --psam a.psam --remove x_remove.txt --exclude x_exclude.txt --make-king-table --threads 2 --out $T/g7 > /dev/null; gzip -9 -n -c $T/g7.kin0 > g_afilt.kin0.gz
 $P --bfile a --king-cutoff 0.02 --score a_score.txt header cols=+scoresums,+denom --threads 2 --out $T/g8 > /dev/null; cp $T/g8.sscore g_acut.sscore
+# host orchestration of the LD prune, replayed on the CPU through tests/harness/mock_pl2gpu.cc: several chromosome runs of
+# uneven length (one of them a singleton), a prune chained behind --king-cutoff-table, a filtered view
+awk 'BEGIN{OFS="\t"} {c=(NR<=120)?1:(NR<=480)?2:(NR<=500)?3:(NR<=501)?4:(NR<=800)?5:7; $1=c; print}' a.bim > a_chr6.bim
+$P --bed a.bed --bim a_chr6.bim --fam a.fam --indep-pairwise 50 5 0.2 --threads 2 --out $T/c6 > /dev/null; cp $T/c6.prune.in a_chr6.prune.in
+$P --bfile a --king-cutoff-table $T/in.kin0 0.02 --indep-pairwise 50 5 0.2 --threads 2 --out $T/kl > /dev/null; cp $T/kl.prune.in g_akct.prune.in
+$P --bfile a --remove x_remove.txt --exclude x_exclude.txt --indep-pairwise 50 5 0.2 --threads 2 --out $T/fl > /dev/null; cp $T/fl.prune.in g_afilt.prune.in
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null

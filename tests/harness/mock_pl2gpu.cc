@@ -1,0 +1,140 @@
+// mock_pl2gpu.cc - TEST INFRASTRUCTURE, never shipped and never linked into the product: a CPU stand-in for the few
+// libpl2gpu entry points the `--indep-pairwise` / `--freq`-style host drivers call, injected with LD_PRELOAD so that
+// the HOST ORCHESTRATION of plink2_b200 (filter view -> founder decode, chromosome runs spread over several device
+// workers, relatedness-prune chaining with frozen allele frequencies) can be exercised in the CPU-only container.
+// Like oracle/, it restates the reference's arithmetic (ComputeIndepPairwiseR2Components + the r^2 test,
+// 2.0/plink2_ld.cc:699-723, :1085-1090; genotype counts) in plain loops; the greedy window walk is NOT restated - the
+// real, exported pl2_ld_prune_walk of libpl2gpu.so (host code) is called.  Autosomal (diploid) chromosomes only.
+// Build: g++ -O2 -std=c++17 -ffp-contract=off -shared -fPIC -o mock_pl2gpu.so mock_pl2gpu.cc
+// PL2_MOCK_DEVICES = number of devices to report; PL2_MOCK_LOG = file that receives one line per entry-point call.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct Pl2GpuCtx {
+  int device;
+};
+
+extern "C" int pl2_ld_prune_walk(uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr, int window_is_bp, const double* maj_freq, const uint8_t* mono,
+                                 const uint8_t* pair_flags, uint32_t band, uint32_t flags, uint8_t* removed_out);
+
+namespace {
+thread_local std::string t_err;
+std::mutex g_log_mu;
+void Log(const char* fmt, int a, unsigned b) {
+  const char* path = getenv("PL2_MOCK_LOG");
+  if (!path) return;
+  std::lock_guard<std::mutex> lock(g_log_mu);
+  if (FILE* f = fopen(path, "a")) {
+    fprintf(f, fmt, a, b);
+    fclose(f);
+  }
+}
+inline uint32_t Code(const uint8_t* row, uint32_t s) { return (row[s >> 2] >> (2 * (s & 3))) & 3; }
+}  // namespace
+
+extern "C" {
+
+int pl2gpu_device_count(void) {
+  const char* e = getenv("PL2_MOCK_DEVICES");
+  return e ? atoi(e) : 1;
+}
+const char* pl2gpu_last_error(void) { return t_err.c_str(); }
+int pl2gpu_ctx_create(int device_idx, Pl2GpuCtx** ctx_ptr) {
+  if (device_idx < 0 || device_idx >= pl2gpu_device_count()) {
+    t_err = "mock: no such device";
+    return 1;
+  }
+  *ctx_ptr = new Pl2GpuCtx{device_idx};
+  Log("ctx_create device=%d n=%u\n", device_idx, 0);
+  return 0;
+}
+int pl2gpu_ctx_destroy(Pl2GpuCtx* ctx) {
+  delete ctx;
+  return 0;
+}
+int pl2gpu_ctx_synchronize(Pl2GpuCtx*) { return 0; }
+int pl2gpu_host_alloc(uint64_t bytes, void** ptr) {
+  *ptr = malloc(bytes ? bytes : 1);
+  return *ptr ? 0 : 1;
+}
+int pl2gpu_host_free(void* ptr) {
+  free(ptr);
+  return 0;
+}
+
+int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t sample_ct, uint32_t variant_ct, int, uint32_t* counts) {
+  Log("geno_counts device=%d variants=%u\n", ctx->device, variant_ct);
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    uint32_t c[4] = {0, 0, 0, 0};
+    for (uint32_t s = 0; s < sample_ct; ++s) ++c[Code(row, s)];
+    memcpy(counts + 4ull * v, c, sizeof(c));
+  }
+  return 0;
+}
+
+int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr,
+                          double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int, const uint8_t*, uint32_t flags_in, uint8_t* removed_out) {
+  Log("indep_pairwise device=%d variants=%u\n", ctx->device, variant_ct);
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    if (chr_codes[v] < 1 || chr_codes[v] > 22) {
+      t_err = "mock: autosomes only";
+      return 1;
+    }
+  }
+  if (window_is_bp) {
+    t_err = "mock: variant-count windows only";
+    return 1;
+  }
+  const uint32_t n = founder_ct, m = variant_ct;
+  std::vector<int8_t> x(static_cast<size_t>(m) * n), nm(static_cast<size_t>(m) * n);
+  std::vector<double> maj(m);
+  std::vector<uint8_t> mono(m);
+  for (uint32_t v = 0; v < m; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    uint64_t c[4] = {0, 0, 0, 0};
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint32_t g = Code(row, s);
+      ++c[g];
+      x[static_cast<size_t>(v) * n + s] = g == 0 ? 1 : (g == 2 ? -1 : 0);
+      nm[static_cast<size_t>(v) * n + s] = g != 3;
+    }
+    const uint64_t tot = 2 * (c[0] + c[1] + c[2]);
+    double f = tot ? static_cast<double>(2 * c[0] + c[1]) * (1.0 / static_cast<double>(tot)) : 0.5;
+    if (ref_freqs && ref_freqs[v] == ref_freqs[v]) f = ref_freqs[v];
+    maj[v] = (f < 0.5 ? 1.0 - f : f) - ((preferred && preferred[v]) ? 1.0 : 0.0);
+    const uint64_t nmc = c[0] + c[1] + c[2];
+    mono[v] = (c[0] == 0 && c[2] == 0) || c[0] == nmc || c[2] == nmc;  // plink2_ld.cc:902
+  }
+  const uint32_t band = window_size - 1;
+  const double thr = r2_thresh * (1.0 + 1.0 / 17592186044416.0);
+  std::vector<uint8_t> flags(static_cast<size_t>(m) * band, 0);
+  for (uint32_t v = 1; v < m; ++v) {
+    for (uint32_t d = 1; d <= band && d <= v; ++d) {
+      const uint32_t b = v - d;  // first
+      if (chr_codes[b] != chr_codes[v]) break;
+      const int8_t *xa = &x[static_cast<size_t>(v) * n], *na = &nm[static_cast<size_t>(v) * n], *xb = &x[static_cast<size_t>(b) * n], *nb = &nm[static_cast<size_t>(b) * n];
+      int64_t nm_ct = 0, dot = 0, s_b = 0, q_b = 0, s_a = 0, q_a = 0;
+      for (uint32_t s = 0; s < n; ++s) {
+        nm_ct += nb[s] * na[s];
+        dot += xb[s] * xa[s];
+        s_b += xb[s] * na[s];
+        q_b += xb[s] * xb[s] * na[s];
+        s_a += nb[s] * xa[s];
+        q_a += nb[s] * xa[s] * xa[s];
+      }
+      const double cov12 = static_cast<double>(dot * nm_ct - s_b * s_a);
+      const double var1 = static_cast<double>(q_b * nm_ct - s_b * s_b), var2 = static_cast<double>(q_a * nm_ct - s_a * s_a);
+      flags[static_cast<size_t>(v) * band + d - 1] = cov12 * cov12 > thr * var1 * var2;
+    }
+  }
+  return pl2_ld_prune_walk(m, chr_codes, variant_bps, window_size, window_incr, 0, maj.data(), mono.data(), flags.data(), band, flags_in, removed_out);
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+"""CPU: the HOST ORCHESTRATION of plink2_b200 around the device calls, replayed without a GPU.  A test-only stand-in
+for the handful of libpl2gpu entry points the LD-prune driver uses (tests/harness/mock_pl2gpu.cc: plain-loop pair
+decisions and genotype counts; the greedy walk is the product's own exported pl2_ld_prune_walk) is injected with
+LD_PRELOAD, so the real host program runs its real code paths: chromosome runs handed to several device workers, a
+relatedness prune chained in front of the LD prune with frozen allele frequencies, and the filtered view feeding the
+founder decode.  Expected lists were written by the reference binary for the same command lines.  The product itself
+never loads this library; without it (and without a GPU) every device command fails loudly, which is also checked."""
+import gzip
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GD = os.path.join(ROOT, "tests", "golden")
+BIN = os.path.join(ROOT, "plink_ng_b200", "plink2_b200")
+
+
+@pytest.fixture(scope="module")
+def mock_so(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("mock") / "mock_pl2gpu.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "harness", "mock_pl2gpu.cc")], check=True)
+    return so
+
+
+def _run(mock_so, args, out, devices=1, log=None):
+    env = dict(os.environ, LD_PRELOAD=mock_so, PL2_MOCK_DEVICES=str(devices))
+    if log:
+        env["PL2_MOCK_LOG"] = log
+    r = subprocess.run([BIN] + args + ["--out", out], capture_output=True, text=True, env=env, cwd=GD)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def test_single_worker_ld_prune_matches_reference(mock_so, tmp_path):
+    out = str(tmp_path / "o")
+    _run(mock_so, ["--bfile", "a", "--indep-pairwise", "50", "5", "0.2"], out)
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "a_ld.prune.in"), "rb").read()
+
+
+@pytest.mark.parametrize("gpus,devices", [(1, 1), (3, 3), (8, 2)])
+def test_chromosome_runs_over_several_device_workers(mock_so, tmp_path, gpus, devices):
+    """Six chromosomes of 120 / 360 / 20 / 1 / 299 / 200 variants: the singleton is never examined, the other five runs are
+    taken largest-first by min(--gpus, runs, visible devices) workers, each on its own context, and the merged keep-list
+    is the reference's whatever the split."""
+    out, log = str(tmp_path / "o"), str(tmp_path / "mock.log")
+    stdout = _run(mock_so, ["--bed", "a.bed", "--bim", "a_chr6.bim", "--fam", "a.fam", "--gpus", str(gpus), "--indep-pairwise", "50", "5", "0.2"], out, devices=devices, log=log)
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "a_chr6.prune.in"), "rb").read()
+    calls = [ln.split() for ln in open(log)]
+    runs = sorted(int(c[2].split("=")[1]) for c in calls if c[0] == "indep_pairwise")
+    assert runs == [20, 120, 200, 299, 360]
+    used = {c[1] for c in calls if c[0] == "indep_pairwise"}
+    workers = min(gpus, devices, 5)
+    assert {c[1] for c in calls if c[0] == "ctx_create"} == {"device=%d" % g for g in range(workers)}
+    assert used <= {"device=%d" % g for g in range(workers)} and (workers == 1 or len(used) > 1)
+    if workers < gpus:
+        assert "Note: --indep-pairwise on %d GPU" % workers in stdout
+
+
+def test_relatedness_prune_chained_in_front_of_ld_prune(mock_so, tmp_path):
+    """--king-cutoff-table leaves 50 founders; the LD prune behind it sees only them but keeps the allele frequencies (and
+    so the major alleles / tie-breaks) of all 100 - the reference's own chained run gives the expected list.  The
+    50-founder guard is applied before the prune, so the chained run is not refused."""
+    (tmp_path / "in.kin0").write_bytes(gzip.open(os.path.join(GD, "a_kingp.kin0.gz"), "rb").read())
+    out, log = str(tmp_path / "o"), str(tmp_path / "mock.log")
+    stdout = _run(mock_so, ["--bfile", "a", "--king-cutoff-table", str(tmp_path / "in.kin0"), "0.02", "--indep-pairwise", "50", "5", "0.2"], out, log=log)
+    assert "50 samples remaining after the relatedness prune." in stdout
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "g_akct.prune.in"), "rb").read()
+    calls = [ln.split()[0] for ln in open(log)]
+    assert calls.index("geno_counts") < calls.index("indep_pairwise")  # frequencies frozen from the pre-prune founders first
+
+
+def test_filtered_view_feeds_the_ld_prune(mock_so, tmp_path):
+    out = str(tmp_path / "o")
+    _run(mock_so, ["--bfile", "a", "--remove", "x_remove.txt", "--exclude", "x_exclude.txt", "--indep-pairwise", "50", "5", "0.2"], out)
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "g_afilt.prune.in"), "rb").read()
+
+
+def test_without_the_stand_in_device_commands_fail_loudly(tmp_path):
+    """No GPU in this container and no mock: the product must refuse, not fall back to anything."""
+    import shutil
+
+    if shutil.which("nvidia-smi") and subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0:
+        pytest.skip("a GPU is visible")
+    r = subprocess.run([BIN, "--bfile", "a", "--indep-pairwise", "50", "5", "0.2", "--out", str(tmp_path / "o")], capture_output=True, text=True, cwd=GD)
+    assert r.returncode == 16 and "GPU initialisation failed" in r.stdout
