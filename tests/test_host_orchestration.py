@@ -84,3 +84,14 @@ def test_without_the_stand_in_device_commands_fail_loudly(tmp_path):
         pytest.skip("a GPU is visible")
     r = subprocess.run([BIN, "--bfile", "a", "--indep-pairwise", "50", "5", "0.2", "--out", str(tmp_path / "o")], capture_output=True, text=True, cwd=GD)
     assert r.returncode == 16 and "GPU initialisation failed" in r.stdout
+
+
+@pytest.mark.parametrize("args,gold", [(["--bfile", "x"], "x.afreq"),
+                                       (["--bfile", "x", "--keep", "x_keep1.txt", "x_keep2.txt", "--remove", "x_remove.txt", "--extract", "x_extract.txt", "--exclude", "x_exclude.txt"], "g_xfilt.afreq")])
+def test_freq_driver_on_sex_chromosomes_and_filtered_view(mock_so, tmp_path, args, gold):
+    """--freq's host side: three counting passes (founders; founder males on chrX; nonfemale founders on chrY) over
+    subsets of the view, the reference's ddosage accounting and report format.  With exact counts from the stand-in the
+    report is the reference's byte for byte, unfiltered and under the filter fixture."""
+    out = str(tmp_path / "o")
+    _run(mock_so, args + ["--freq"], out)
+    assert open(out + ".afreq", "rb").read() == open(os.path.join(GD, gold), "rb").read()
