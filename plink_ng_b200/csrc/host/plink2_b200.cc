@@ -8,6 +8,7 @@
 // CalcKing / CalcGrm / LdPruneWrite.  File decoding, text formatting and the sequential graph /
 // window logic run here on the host; every pairwise accumulation runs on the GPU - there is no
 // CPU fallback and the program exits with kPglRetGpuFail-style status when the device is missing.
+#include <immintrin.h>
 #include <sched.h>
 #include <unistd.h>
 
@@ -102,6 +103,10 @@ struct Cmd {
   double king_cutoff_table_thresh = -1;
   FilterSpec filters;                     // --keep / --remove / --keep-fam / --remove-fam / --extract / --exclude / --chr / --not-chr / --autosome[-xy]
   bool make_bed = false;                  // --make-bed: the filtered view as .bed/.bim/.fam (host-only)
+  // --r2-unphased ['zs'] + --ld-window <#var+1> / --ld-window-kb <kb> / --ld-window-r2 <min> (plink2.cc:7908-7963, :11181-11204)
+  bool r2_unphased = false, r2_zs = false;
+  uint32_t ld_var_radius = 0x7fffffff, ld_bp_radius = 0xFFFFFFFFu;  // UINT32_MAX: --ld-window-kb not given (default 1000 kb)
+  double ld_min_r2 = 2.0;                                             // 2.0: not given (default 0.2 (1 - 2^-44))
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
   std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
@@ -445,6 +450,27 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--autosome" || flag == "--autosome-xy" || flag == "--autosome-par") {
       if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
       (flag == "--autosome" ? c->filters.autosome : c->filters.autosome_xy) = true;
+    } else if (flag == "--r2-unphased") {
+      // table form only; matrix shapes / encodings, 'inter-chr', 'ref-based', cols= are not supported
+      for (int k = 0; k < nparam; ++k) {
+        if (!strcmp(prm[k], "zs")) c->r2_zs = true;
+        else return Usage((std::string("--r2-unphased modifier '") + prm[k] + "' is not supported by plink2_b200 (supported: zs).").c_str());
+      }
+      c->r2_unphased = true;
+    } else if (flag == "--ld-window") {
+      uint32_t u;
+      if (!need(1, 1) || !ParseU32(prm[0], &u) || u < 2) return Usage("Invalid --ld-window argument.");
+      c->ld_var_radius = u - 1;
+    } else if (flag == "--ld-window-kb") {
+      double dxx;
+      if (!need(1, 1) || !ParseDouble(prm[0], &dxx) || dxx < 0) return Usage("Invalid --ld-window-kb argument.");
+      dxx *= 1000 * (1 + 1.0 / 17592186044416.0);
+      c->ld_bp_radius = dxx > 2147483646 ? 2147483646u : static_cast<uint32_t>(static_cast<int32_t>(dxx));
+    } else if (flag == "--ld-window-r2") {
+      double dxx;
+      if (!need(1, 1) || !ParseDouble(prm[0], &dxx) || dxx > 1.0) return Usage("Invalid --ld-window-r2 argument.");
+      if (dxx > 0.0) dxx *= 1 - 1.0 / 17592186044416.0;
+      c->ld_min_r2 = dxx;
     } else if (flag == "--snps-only") {
       if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "just-acgt"))) return Usage("Invalid --snps-only argument (only 'just-acgt' is accepted).");
       c->filters.snps_only = 1 + nparam;
@@ -617,7 +643,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     if (named != 1) return Usage("--from-bp/-kb/-mb and --to-bp/-kb/-mb must be used with --chr, and only one chromosome.");
     if (c->filters.from_bp != -1 && c->filters.to_bp != -1 && c->filters.from_bp > c->filters.to_bp) return Usage("--to-bp/-kb/-mb argument is smaller than --from-bp/-kb/-mb argument.");
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->make_bed || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->r2_unphased || c->make_bed || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -3439,6 +3465,165 @@ int DebugHooks(int argc, char** argv) {
   return -1;
 }
 
+// `--r2-unphased` table (VcorTable, 2.0/plink2_ld.cc:11025; per-pair statistic ComputeR2 :6654-6682, report filter
+// :10814-10818): squared correlation of the founders' hard-call dosages for every variant pair on one chromosome within
+// --ld-window-kb (default 1000) / --ld-window, reported when r^2 >= --ld-window-r2 (default 0.2).
+// Division of labour: the DEVICE screens every pair of the band with the pair-decision kernel the LD prune uses
+// (pl2gpu_ld_band_flags: cov^2 > t var1 var2 on the exact integer sextuple, t a hair below the report threshold, so
+// the flagged set is a superset); the HOST recomputes the sextuple of the few flagged pairs from bit planes of the
+// block it already holds and applies the reference's own arithmetic (int64 -> double, cov^2 / (var0 var1), >= threshold).
+// chrX uses a sex-aware statistic in the reference (ComputeXR2) and is refused here.
+int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  const uint32_t bp_radius = c.ld_bp_radius == 0xFFFFFFFFu ? 1000000u : c.ld_bp_radius;
+  const double min_r2 = c.ld_min_r2 == 2.0 ? 0.2 * (1 - 1.0 / 17592186044416.0) : c.ld_min_r2;
+  if (!(min_r2 > 0.0)) {
+    logprintf("Error: --r2-unphased needs a positive --ld-window-r2 in plink2_b200 (the device screens pairs against it).\n");
+    return kRetNotYetSupported;
+  }
+  for (uint32_t v = 0; v < m; ++v) {
+    if (V.chr_code[v] == 23) {
+      logprintf("Error: --r2-unphased on chrX (sex-aware statistic) is not supported by plink2_b200; add --not-chr X.\n");
+      return kRetNotYetSupported;
+    }
+  }
+  // founders; on chrY the reference sets female founders to missing (InterleavedSetMissing, plink2_ld.cc:11845), which
+  // for a statistic over samples non-missing in both variants is the same as leaving them out
+  uint32_t all_founder_ct = 0, y_founder_ct = 0;
+  std::vector<uint64_t> inc_all((n + 63) / 64, 0), inc_y((n + 63) / 64, 0);
+  for (uint32_t k = 0; k < n; ++k) {
+    if (S.is_founder[k]) {
+      inc_all[k / 64] |= 1ull << (k % 64);
+      ++all_founder_ct;
+      if (S.sex[k] != 2) {
+        inc_y[k / 64] |= 1ull << (k % 64);
+        ++y_founder_ct;
+      }
+    }
+  }
+  if (!all_founder_ct) {
+    logprintf("Error: No founders for --r2-unphased.\n");
+    return kRetDegenerateData;
+  }
+  logprintf("Running --r2-unphased with the following filters:\n");
+  if (c.ld_var_radius < 0x7fffffff) logprintf("  --ld-window: %u\n", c.ld_var_radius + 1);
+  logprintf("  --ld-window-kb: %g\n", 0.001 * bp_radius);
+  logprintf("  --ld-window-r2: %g\n", min_r2);
+  const std::string name = c.out + (c.r2_zs ? ".vcor.zst" : ".vcor");
+  OutFile f;
+  if (!f.Open(name, c.r2_zs)) return kRetOpenFail;
+  f.Puts("#CHROM_A\tPOS_A\tID_A\tCHROM_B\tPOS_B\tID_B\tUNPHASED_R2\n");
+  uint64_t reported = 0, flagged_total = 0;
+  for (uint32_t s0 = 0; s0 < m;) {
+    uint32_t e = s0 + 1;
+    while (e < m && V.chr_code[e] == V.chr_code[s0]) ++e;
+    const uint32_t len = e - s0;
+    const bool is_y = V.chr_code[s0] == 24;
+    const uint32_t founder_ct = is_y ? y_founder_ct : all_founder_ct;
+    const std::vector<uint64_t>& inc = is_y ? inc_y : inc_all;
+    const uint32_t words = PgenReader::WordsFor(founder_ct);
+    const uint32_t pw = (founder_ct + 63) / 64;  // plane words per variant
+    if (len >= 2 && founder_ct) {
+      // window end per first variant a: [a + 1, win_end[a]) holds the partners within both radii; band = widest window
+      std::vector<uint32_t> win_end(len);
+      uint32_t band = 0, hi = 0;
+      for (uint32_t a = 0; a < len; ++a) {
+        if (hi < a + 1) hi = a + 1;
+        while (hi < len && V.bp[s0 + hi] - V.bp[s0 + a] <= bp_radius) ++hi;
+        win_end[a] = std::min<uint64_t>(hi, static_cast<uint64_t>(a) + 1 + c.ld_var_radius);
+        band = std::max(band, win_end[a] - a - 1);
+      }
+      if (band) {
+        if (static_cast<uint64_t>(len) * band > (1ull << 33)) {
+          logprintf("Error: --r2-unphased window too wide for plink2_b200 on this chromosome (%u variants x %u partners); narrow --ld-window-kb / --ld-window.\n", len, band);
+          return kRetNotYetSupported;
+        }
+        std::vector<uint32_t> vsub(len);
+        for (uint32_t k = 0; k < len; ++k) vsub[k] = s0 + k;
+        BlockStreamer bs(ds, &vsub, founder_ct, len);
+        if (founder_ct != n) bs.sample_include = inc.data();
+        if (!bs.Init()) return GpuFail("pl2gpu_host_alloc");
+        std::string err;
+        if (bs.Next(&err) != static_cast<int>(len)) {
+          logprintf("Error: %s\n", err.empty() ? "short read" : err.c_str());
+          return kRetMalformedInput;
+        }
+        std::vector<uint8_t> flags(static_cast<uint64_t>(len) * band);
+        if (pl2gpu_ld_band_flags(ctx, bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, len, 0, band, min_r2 * (1 - 1e-9), flags.data())) return GpuFail("pl2gpu_ld_band_flags");
+        // bit planes of the block: het / hom-ALT / non-missing, one bit per founder
+        std::vector<uint64_t> p_one(static_cast<uint64_t>(len) * pw, 0), p_two(static_cast<uint64_t>(len) * pw, 0), p_nm(static_cast<uint64_t>(len) * pw, 0);
+        for (uint32_t k = 0; k < len; ++k) {
+          const uint64_t* row = bs.buf + static_cast<uint64_t>(k) * words;
+          for (uint32_t w = 0; w < words; ++w) {
+            const uint64_t g = row[w];
+            const uint64_t lo = _pext_u64(g, 0x5555555555555555ull), hi2 = _pext_u64(g, 0xAAAAAAAAAAAAAAAAull);
+            uint64_t valid = 0xFFFFFFFFull;
+            if (w == words - 1 && (founder_ct & 31)) valid = (1ull << (founder_ct & 31)) - 1;
+            const uint64_t one = lo & ~hi2 & valid, two = hi2 & ~lo & valid, nm = ~(lo & hi2) & valid;
+            const uint32_t sh = 32 * (w & 1);
+            p_one[static_cast<uint64_t>(k) * pw + (w >> 1)] |= one << sh;
+            p_two[static_cast<uint64_t>(k) * pw + (w >> 1)] |= two << sh;
+            p_nm[static_cast<uint64_t>(k) * pw + (w >> 1)] |= nm << sh;
+          }
+        }
+        for (uint32_t a = 0; a < len; ++a) {
+          for (uint32_t b = a + 1; b < win_end[a]; ++b) {
+            if (!flags[static_cast<uint64_t>(b) * band + (b - a - 1)]) continue;
+            ++flagged_total;
+            const uint64_t *o0 = &p_one[static_cast<uint64_t>(a) * pw], *t0 = &p_two[static_cast<uint64_t>(a) * pw], *n0 = &p_nm[static_cast<uint64_t>(a) * pw];
+            const uint64_t *o1 = &p_one[static_cast<uint64_t>(b) * pw], *t1 = &p_two[static_cast<uint64_t>(b) * pw], *n1 = &p_nm[static_cast<uint64_t>(b) * pw];
+            int64_t obs = 0, sum0 = 0, sum1 = 0, ssq0 = 0, ssq1 = 0, dot = 0;
+            for (uint32_t w = 0; w < pw; ++w) {
+              const uint64_t valid = n0[w] & n1[w];
+              const int64_t a1 = __builtin_popcountll(o0[w] & valid), a2 = __builtin_popcountll(t0[w] & valid), b1 = __builtin_popcountll(o1[w] & valid), b2 = __builtin_popcountll(t1[w] & valid);
+              obs += __builtin_popcountll(valid);
+              sum0 += a1 + 2 * a2;
+              ssq0 += a1 + 4 * a2;
+              sum1 += b1 + 2 * b2;
+              ssq1 += b1 + 4 * b2;
+              dot += __builtin_popcountll(o0[w] & o1[w]) + 2 * (__builtin_popcountll(o0[w] & t1[w]) + __builtin_popcountll(t0[w] & o1[w])) + 4 * __builtin_popcountll(t0[w] & t1[w]);
+            }
+            if (!obs) continue;
+            const int64_t var0 = ssq0 * obs - sum0 * sum0, var1 = ssq1 * obs - sum1 * sum1;
+            const double variance_prod = static_cast<double>(var0) * static_cast<double>(var1);
+            if (variance_prod == 0.0) continue;
+            const double cov01 = static_cast<double>(dot * obs - sum0 * sum1);
+            const double r2 = cov01 * cov01 / variance_prod;
+            if (!(r2 >= min_r2)) continue;
+            const uint32_t va = s0 + a, vb = s0 + b;
+            const std::string chr = ChrNameOut(V.chr_code[va], V.chr_name[va]);
+            char* w = f.Reserve(2 * chr.size() + V.id[va].size() + V.id[vb].size() + 96);
+            auto put = [&](const std::string& t) {
+              memcpy(w, t.data(), t.size());
+              w += t.size();
+              *w++ = '\t';
+            };
+            put(chr);
+            w = u32toa(V.bp[va], w);
+            *w++ = '\t';
+            put(V.id[va]);
+            put(chr);
+            w = u32toa(V.bp[vb], w);
+            *w++ = '\t';
+            put(V.id[vb]);
+            w = dtoa_g(r2, w);
+            *w++ = '\n';
+            f.Advance(w);
+            ++reported;
+          }
+        }
+      }
+    }
+    s0 = e;
+  }
+  if (!f.Close()) return kRetWriteFail;
+  if (g_clock.on) fprintf(stderr, "[timing]   r2: %llu pairs flagged by the device screen, %llu reported\n", static_cast<unsigned long long>(flagged_total), static_cast<unsigned long long>(reported));
+  logprintf("--r2-unphased: Results written to %s .\n", name.c_str());
+  return 0;
+}
+
 // --mind, --geno, --maf / --max-maf / --mac / --max-mac on hard calls: one host counting pass each for the sample and
 // the variant thresholds (MindFilter plink2_filter.cc:3329, EnforceGenoThresh :3498, EnforceFreqConstraints :3791).
 // chrY: missingness over males only; frequencies are the founder frequencies --freq reports (or --read-freq's).
@@ -3575,7 +3760,7 @@ int main(int argc, char** argv) {
   // CUDA initialisation (0.5 - 3 s on a cold box) runs beside the loading of the sample / variant files; commands that
   // need no device
   // (file-driven --king-cutoff[-table] and --make-bed on their own) never start it
-  const bool gpu_command = c.freq || c.make_king || c.make_king_table || c.king_cutoff >= 0 || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
+  const bool gpu_command = c.freq || c.r2_unphased || c.make_king || c.make_king_table || c.king_cutoff >= 0 || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
   const bool needs_gpu = gpu_command;
   Pl2GpuCtx* ctx = nullptr;
   int ctx_rc = 0;
@@ -3686,7 +3871,7 @@ int main(int argc, char** argv) {
   g_clock.Mark("load .psam/.pvar, open .pgen");
   // ---- relatedness prune from a file, then the commands that see its survivors (Plink2Core order, plink2.cc:2523-2581)
   std::vector<uint8_t> cutoff_removed;
-  const bool later_gpu_command = c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
+  const bool later_gpu_command = c.r2_unphased || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
   if (!c.king_cutoff_table.empty() || !c.king_cutoff_prefix.empty()) {
     if (!c.king_cutoff_table.empty() && (c.king_cutoff >= 0 || !c.king_cutoff_prefix.empty())) {
       logprintf("Error: --king-cutoff cannot be used with --king-cutoff-table.\n");
@@ -3811,6 +3996,10 @@ int main(int argc, char** argv) {
   }
   if (c.indep_pairwise) {
     rc = RunLdPrune(c, &ds, ctx);
+    if (rc) return rc;
+  }
+  if (c.r2_unphased) {
+    rc = RunR2Unphased(c, &ds, ctx);
     if (rc) return rc;
   }
   pl2gpu_ctx_synchronize(ctx);

@@ -135,6 +135,11 @@ awk 'BEGIN{OFS="\t"} {c=(NR<=120)?1:(NR<=480)?2:(NR<=500)?3:(NR<=501)?4:(NR<=800
 $P --bed a.bed --bim a_chr6.bim --fam a.fam --indep-pairwise 50 5 0.2 --threads 2 --out $T/c6 > /dev/null; cp $T/c6.prune.in a_chr6.prune.in
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --indep-pairwise 50 5 0.2 --threads 2 --out $T/kl > /dev/null; cp $T/kl.prune.in g_akct.prune.in
 $P --bfile a --remove x_remove.txt --exclude x_exclude.txt --indep-pairwise 50 5 0.2 --threads 2 --out $T/fl > /dev/null; cp $T/fl.prune.in g_afilt.prune.in
+# --r2-unphased tables: all pairs of set A at the default filters, a 7-variant / r^2 >= 0.5 window, and set X without chrX
+# under --keep (chrY: female founders count as missing; MT / XY like autosomes; non-founders ignored)
+$P --bfile a --r2-unphased --threads 2 --out $T/r1 > /dev/null; gzip -9 -n -c $T/r1.vcor > a_r2.vcor.gz
+$P --bfile a --r2-unphased --ld-window 7 --ld-window-r2 0.5 --threads 2 --out $T/r2 > /dev/null; gzip -9 -n -c $T/r2.vcor > a_r2w.vcor.gz
+$P --bfile x --not-chr X --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.3 --ld-window-kb 0.1 --threads 2 --out $T/r3 > /dev/null; gzip -9 -n -c $T/r3.vcor > x_r2.vcor.gz
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null

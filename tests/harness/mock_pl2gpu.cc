@@ -79,6 +79,42 @@ int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, ui
   return 0;
 }
 
+// pair-decision band on its own (the screening pass of --r2-unphased): flags[v * band + d - 1] = cov^2 > t var1 var2
+// for second = v, first = v - d, exact integer sextuple over samples non-missing in both (plink2_ld.cc:699-723)
+int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, int, uint32_t band, double thresh, uint8_t* flags_host) {
+  Log("ld_band_flags device=%d variants=%u\n", ctx->device, variant_ct);
+  const uint32_t n = founder_ct, m = variant_ct;
+  std::vector<int8_t> x(static_cast<size_t>(m) * n), nm(static_cast<size_t>(m) * n);
+  for (uint32_t v = 0; v < m; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    for (uint32_t s = 0; s < n; ++s) {
+      const uint32_t g = Code(row, s);
+      x[static_cast<size_t>(v) * n + s] = g == 0 ? 1 : (g == 2 ? -1 : 0);
+      nm[static_cast<size_t>(v) * n + s] = g != 3;
+    }
+  }
+  memset(flags_host, 0, static_cast<size_t>(m) * band);
+  for (uint32_t v = 1; v < m; ++v) {
+    for (uint32_t d = 1; d <= band && d <= v; ++d) {
+      const uint32_t b = v - d;
+      const int8_t *xa = &x[static_cast<size_t>(v) * n], *na = &nm[static_cast<size_t>(v) * n], *xb = &x[static_cast<size_t>(b) * n], *nb = &nm[static_cast<size_t>(b) * n];
+      int64_t nm_ct = 0, dot = 0, s_b = 0, q_b = 0, s_a = 0, q_a = 0;
+      for (uint32_t s = 0; s < n; ++s) {
+        nm_ct += nb[s] * na[s];
+        dot += xb[s] * xa[s];
+        s_b += xb[s] * na[s];
+        q_b += xb[s] * xb[s] * na[s];
+        s_a += nb[s] * xa[s];
+        q_a += nb[s] * xa[s] * xa[s];
+      }
+      const double cov12 = static_cast<double>(dot * nm_ct - s_b * s_a);
+      const double var1 = static_cast<double>(q_b * nm_ct - s_b * s_b), var2 = static_cast<double>(q_a * nm_ct - s_a * s_a);
+      flags_host[static_cast<size_t>(v) * band + d - 1] = cov12 * cov12 > thresh * var1 * var2;
+    }
+  }
+  return 0;
+}
+
 int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, const uint32_t* chr_codes, const uint32_t* variant_bps, uint32_t window_size, uint32_t window_incr,
                           double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int, const uint8_t*, uint32_t flags_in, uint8_t* removed_out) {
   Log("indep_pairwise device=%d variants=%u\n", ctx->device, variant_ct);

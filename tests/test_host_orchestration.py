@@ -95,3 +95,23 @@ def test_freq_driver_on_sex_chromosomes_and_filtered_view(mock_so, tmp_path, arg
     out = str(tmp_path / "o")
     _run(mock_so, args + ["--freq"], out)
     assert open(out + ".afreq", "rb").read() == open(os.path.join(GD, gold), "rb").read()
+
+
+@pytest.mark.parametrize("args,gold", [(["--bfile", "a", "--r2-unphased"], "a_r2.vcor.gz"),
+                                       (["--bfile", "a", "--r2-unphased", "--ld-window", "7", "--ld-window-r2", "0.5"], "a_r2w.vcor.gz"),
+                                       (["--bfile", "x", "--not-chr", "X", "--keep", "x_keep1.txt", "x_keep2.txt", "--r2-unphased", "--ld-window-r2", "0.3", "--ld-window-kb", "0.1"], "x_r2.vcor.gz")])
+def test_r2_unphased_table_matches_reference(mock_so, tmp_path, args, gold):
+    """--r2-unphased: the device screens every pair of the band (here: the stand-in's plain loops behind the same entry
+    point, pl2gpu_ld_band_flags), the host recomputes the flagged pairs from bit planes with the reference's arithmetic
+    and applies the window / threshold rules.  Tables byte-identical to the reference's: 499,500 candidate pairs of set
+    A, a variant-count window, and set X without chrX (female founders missing on chrY, non-founders ignored)."""
+    out = str(tmp_path / "o")
+    _run(mock_so, args, out)
+    assert open(out + ".vcor", "rb").read() == gzip.open(os.path.join(GD, gold), "rb").read()
+
+
+def test_r2_unphased_refuses_what_it_does_not_cover(mock_so, tmp_path):
+    env = dict(os.environ, LD_PRELOAD=mock_so)
+    for args, msg in ((["--bfile", "x", "--r2-unphased"], "chrX"), (["--bfile", "a", "--r2-unphased", "--ld-window-r2", "0"], "positive --ld-window-r2"), (["--bfile", "a", "--r2-unphased", "square"], "not supported")):
+        r = subprocess.run([BIN] + args + ["--out", str(tmp_path / "o")], capture_output=True, text=True, env=env, cwd=GD)
+        assert r.returncode != 0 and msg in r.stdout + r.stderr, (args, r.stdout)
