@@ -3757,9 +3757,8 @@ int main(int argc, char** argv) {
   }
   int rc = ParseArgs(argc, argv, &c);
   if (rc) return rc;
-  // CUDA initialisation (0.5 - 3 s on a cold box) runs beside the loading of the sample / variant files; commands that
-  // need no device
-  // (file-driven --king-cutoff[-table] and --make-bed on their own) never start it
+  // CUDA initialisation (0.5 - 3 s on a cold box) runs beside the loading of the sample / variant files; runs that need
+  // no device (file-driven --king-cutoff[-table], --make-bed, --write-snplist / --write-samples on their own) never start it
   const bool gpu_command = c.freq || c.r2_unphased || c.make_king || c.make_king_table || c.king_cutoff >= 0 || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty();
   const bool needs_gpu = gpu_command;
   Pl2GpuCtx* ctx = nullptr;
@@ -3917,8 +3916,7 @@ int main(int argc, char** argv) {
       rc = write_bed();
       if (rc) return rc;
     }
-    return 0;  // (--write-snplist / --write-samples were written above)
-    // file-driven pruning and --make-bed are host-only in the reference as well: no device is needed
+    return 0;  // host-only run (the ID lists were written above); these steps need no device in the reference either
   }
   g_decode_threads = EffectiveHostThreads(c.threads);
   if (ctx_thread.joinable()) ctx_thread.join();
