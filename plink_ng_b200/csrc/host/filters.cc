@@ -348,7 +348,7 @@ int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* 
   return 0;
 }
 
-int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err) {
+int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err, bool all_as_founders) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
   const uint32_t n = S.size(), m = V.size();
@@ -359,7 +359,7 @@ int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::
   for (auto& l : lane) l.assign(words, 0);
   for (uint32_t k = 0; k < n; ++k) {
     const uint64_t bit = 1ull << (2 * (k & 31));
-    const bool f = S.is_founder[k] != 0;
+    const bool f = all_as_founders || S.is_founder[k] != 0;
     lane[kAll][k >> 5] |= bit;
     if (S.sex[k] == 1) lane[kMale][k >> 5] |= bit;
     if (f) lane[kFounder][k >> 5] |= bit;

@@ -47,7 +47,8 @@ struct VariantGenoCounts {
 };
 // sample_missing[k]: missing calls of sample k over all variants, chrY variants counted for males only (then
 // *variant_ct_y = number of chrY variants).  Either output may be null.
-int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err);
+// all_as_founders (--nonfounders): the three "founder" sets are taken over every sample.
+int CountGenotypes(Dataset* ds, uint32_t thread_ct, VariantGenoCounts* vc, std::vector<uint32_t>* sample_missing, uint32_t* variant_ct_y, std::string* err, bool all_as_founders = false);
 // REF allele "ddosage" pair of a variant from those counts (the numbers behind --freq; see RunFreq)
 void FounderAlleleDd(const VariantGenoCounts& vc, uint32_t v, uint32_t chr_code, uint32_t founder_ct, uint32_t founder_male_ct, uint64_t* alt_dd, uint64_t* tot_dd);
 

@@ -107,6 +107,7 @@ struct Cmd {
   bool r2_unphased = false, r2_zs = false;
   uint32_t ld_var_radius = 0x7fffffff, ld_bp_radius = 0xFFFFFFFFu;  // UINT32_MAX: --ld-window-kb not given (default 1000 kb)
   double ld_min_r2 = 2.0;                                             // 2.0: not given (default 0.2 (1 - 2^-44))
+  bool nonfounders = false;  // --nonfounders: allele frequencies (and everything derived from them) from all samples, not founders only
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
   std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
@@ -495,6 +496,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--write-snplist" || flag == "--write-samples") {
       if (!need(0, 0)) return Usage((flag + " modifiers are not supported by plink2_b200.").c_str());
       (flag == "--write-snplist" ? c->write_snplist : c->write_samples) = true;
+    } else if (flag == "--nonfounders") {
+      if (!need(0, 0)) return Usage("--nonfounders takes no arguments.");
+      c->nonfounders = true;
     } else if (flag == "--keep-founders" || flag == "--keep-nonfounders") {
       if (!need(0, 0)) return Usage((flag + " takes no arguments.").c_str());
       if (c->filters.founders_only) return Usage("--keep-nonfounders cannot be used with --keep-founders.");
@@ -3046,14 +3050,14 @@ int RunVscore(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
 // 2.0/plink2.cc:2280): founder ALT allele frequencies of biallelic hard calls -> <out>.afreq.
 // Founder allele "ddosage" totals per variant, in 1/32768 units as the reference accumulates them: alt_dd[v] / tot_dd[v]
 // is the ALT frequency `--freq` prints and every later command consumes (allele_freqs, plink2.cc:2301).
-int FounderAlleleDosages(Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint64_t>* alt_dd_out, std::vector<uint64_t>* tot_dd_out) {
+int FounderAlleleDosages(Dataset* ds, Pl2GpuCtx* ctx, std::vector<uint64_t>* alt_dd_out, std::vector<uint64_t>* tot_dd_out, bool all_samples = false) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
   const uint32_t n = S.size(), m = V.size();
   uint32_t founder_ct = 0, male_ct = 0, nonfemale_ct = 0;
   std::vector<uint64_t> inc((n + 63) / 64, 0), inc_male((n + 63) / 64, 0), inc_nonfemale((n + 63) / 64, 0);
   for (uint32_t k = 0; k < n; ++k) {
-    if (S.is_founder[k]) {
+    if (S.is_founder[k] || all_samples) {  // --nonfounders: allele_ddosages over every sample (plink2.cc:2301)
       inc[k / 64] |= 1ull << (k % 64);
       ++founder_ct;
       if (S.sex[k] == 1) {
@@ -3142,7 +3146,7 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     return kRetNotYetSupported;
   }
   std::vector<uint64_t> alt_dds, tot_dds;
-  const int rc = FounderAlleleDosages(ds, ctx, &alt_dds, &tot_dds);
+  const int rc = FounderAlleleDosages(ds, ctx, &alt_dds, &tot_dds, c.nonfounders);
   if (rc) return rc;
   const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
   OutFile f;
@@ -3172,7 +3176,7 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     f.Advance(w);
   }
   if (!f.Close()) return kRetWriteFail;
-  logprintf("--freq: Allele frequencies (founders only) written to %s .\n", name.c_str());
+  logprintf("--freq: Allele frequencies (%s) written to %s .\n", c.nonfounders ? "all samples" : "founders only", name.c_str());
   return 0;
 }
 
@@ -3666,7 +3670,7 @@ int ApplyCountFilters(const Cmd& c, Dataset* ds) {
   }
   if (f.geno < 1.0 || f.min_maf != 0.0 || f.max_maf != 1.0 || f.min_mac || f.max_mac != ~0ull) {
     VariantGenoCounts vc;
-    const int rc = CountGenotypes(ds, threads, &vc, nullptr, nullptr, &err);
+    const int rc = CountGenotypes(ds, threads, &vc, nullptr, nullptr, &err, c.nonfounders);
     if (rc) {
       logprintf("Error: %s\n", err.c_str());
       return rc;
@@ -3677,8 +3681,8 @@ int ApplyCountFilters(const Cmd& c, Dataset* ds) {
     uint32_t male_ct = 0, founder_ct = 0, founder_male_ct = 0;
     for (uint32_t k = 0; k < n; ++k) {
       male_ct += S.sex[k] == 1;
-      founder_ct += S.is_founder[k] != 0;
-      founder_male_ct += S.is_founder[k] && S.sex[k] == 1;
+      founder_ct += S.is_founder[k] != 0 || c.nonfounders;
+      founder_male_ct += (S.is_founder[k] || c.nonfounders) && S.sex[k] == 1;
     }
     if ((f.min_mac || f.max_mac != ~0ull) && founder_ct != n) {  // plink2.cc:2102
       logprintf("Error: --mac/--max-mac specified, but with neither --ac-founders nor --nonfounders; and nonfounders are present.\n");
@@ -3848,6 +3852,26 @@ int main(int argc, char** argv) {
   if (c.filters.any_count_filter()) {
     rc = ApplyCountFilters(c, &ds);
     if (rc) return rc;
+  }
+  if (c.nonfounders && (c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty())) {
+    // --nonfounders: allele frequencies from every sample (plink2.cc:2301).  One host counting pass, frozen as per-variant
+    // overrides (the --read-freq mechanism) so that every later command - whose own founder-only estimate would differ -
+    // uses them; entries loaded with --read-freq keep precedence.
+    VariantGenoCounts vc;
+    rc = CountGenotypes(&ds, EffectiveHostThreads(c.threads), &vc, nullptr, nullptr, &err, true);
+    if (rc) {
+      logprintf("Error: %s\n", err.c_str());
+      return rc;
+    }
+    uint32_t male_ct = 0;
+    for (uint8_t sx : ds.samples.sex) male_ct += sx == 1;
+    if (ds.read_ref_freq.empty()) ds.read_ref_freq.assign(ds.variants.size(), std::numeric_limits<double>::quiet_NaN());
+    for (uint32_t v = 0; v < ds.variants.size(); ++v) {
+      if (ds.read_ref_freq[v] == ds.read_ref_freq[v]) continue;
+      uint64_t alt_dd, tot_dd;
+      FounderAlleleDd(vc, v, ds.variants.chr_code[v], ds.samples.size(), male_ct, &alt_dd, &tot_dd);
+      ds.read_ref_freq[v] = tot_dd ? static_cast<double>(tot_dd - alt_dd) * (1.0 / static_cast<double>(tot_dd)) : 0.5;
+    }
   }
   if (c.write_snplist) {  // WriteSnplist / --write-samples (plink2.cc:2030-2062): what the main filters left
     OutFile f;

@@ -116,6 +116,10 @@ $P --bed x.bed --bim x_alleles.bim --fam x.fam --snps-only --make-bed --threads 
 $P --bed x.bed --bim x_alleles.bim --fam x.fam --snps-only just-acgt --make-bed --threads 2 --out $T/s2 > /dev/null; cp $T/s2.bim x_acgt.bim
 $P --bfile x --chr 1 --from-kb 0.1001 --to-kb 0.25 --keep x_keep2.txt --write-snplist --write-samples --threads 2 --out $T/s3 > /dev/null; cp $T/s3.snplist x_bp.snplist; cp $T/s3.id x_bp.id
 $P --bfile x --make-pgen vzs --threads 2 --out $T/xz > /dev/null; cp $T/xz.pvar.zst x.pvar.zst   # Zstandard-compressed .pvar as the reference writes it
+# --nonfounders: allele frequencies (thresholds, --freq report, LD tie-breaks) from all 120 samples of set X, not its 116 founders
+$P --bfile x --nonfounders --maf 0.1 --mac 30 --make-bed --threads 2 --out $T/n1 > /dev/null; cp $T/n1.bim x_nf.bim
+$P --bfile x --nonfounders --freq --threads 2 --out $T/n2 > /dev/null; cp $T/n2.afreq x_nf.afreq
+$P --bfile x --chr 1 --nonfounders --indep-pairwise 50 5 0.2 --threads 2 --out $T/n3 > /dev/null; cp $T/n3.prune.in x_nf.prune.in
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

@@ -115,3 +115,16 @@ def test_r2_unphased_refuses_what_it_does_not_cover(mock_so, tmp_path):
     for args, msg in ((["--bfile", "x", "--r2-unphased"], "chrX"), (["--bfile", "a", "--r2-unphased", "--ld-window-r2", "0"], "positive --ld-window-r2"), (["--bfile", "a", "--r2-unphased", "square"], "not supported")):
         r = subprocess.run([BIN] + args + ["--out", str(tmp_path / "o")], capture_output=True, text=True, env=env, cwd=GD)
         assert r.returncode != 0 and msg in r.stdout + r.stderr, (args, r.stdout)
+
+
+def test_nonfounders_frequencies_reach_the_device_commands(mock_so, tmp_path):
+    """--nonfounders: the --freq report counts every sample, and the LD prune - whose r^2 still comes from the founders -
+    breaks ties with all-sample frequencies (frozen as per-variant overrides by one host counting pass).  Set X has four
+    non-founders, enough to change both outputs; expected files are the reference's."""
+    out = str(tmp_path / "o")
+    stdout = _run(mock_so, ["--bfile", "x", "--nonfounders", "--freq"], out)
+    assert "(all samples)" in stdout
+    assert open(out + ".afreq", "rb").read() == open(os.path.join(GD, "x_nf.afreq"), "rb").read()
+    assert open(out + ".afreq", "rb").read() != open(os.path.join(GD, "x.afreq"), "rb").read()
+    _run(mock_so, ["--bfile", "x", "--chr", "1", "--nonfounders", "--indep-pairwise", "50", "5", "0.2"], out)
+    assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "x_nf.prune.in"), "rb").read()
