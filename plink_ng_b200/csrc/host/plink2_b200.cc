@@ -84,7 +84,7 @@ struct Cmd {
   bool make_king = false, make_king_table = false;
   enum Shape { kTri, kSq, kSq0 } king_shape = kTri, rel_shape = kTri;
   enum Enc { kText, kBin, kBin4 } king_enc = kText, rel_enc = kText;
-  bool king_counts = false, king_zs = false, king_table_zs = false, king_rel_check = false, grm_zs = false, rel_zs = false, freq_zs = false;
+  bool king_counts = false, king_zs = false, king_table_zs = false, king_rel_check = false, grm_zs = false, rel_zs = false, freq_zs = false, freq_counts = false;
   bool col_fid_maybe = true, col_fid = false, col_id = true, col_sid_maybe = true, col_sid = false, col_nsnp = true, col_hethet = true, col_ibs0 = true, col_ibs1 = false, col_hamming = false, col_kinship = true;
   double king_table_filter = -DBL_MAX;
   double king_cutoff = -1;
@@ -336,7 +336,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--freq") {
       for (int k = 0; k < nparam; ++k) {
         if (std::string(prm[k]) == "zs") c->freq_zs = true;
-        else return Usage("--freq modifiers other than 'zs' (counts, cols=, bins) are not supported by plink2_b200.");
+        else if (std::string(prm[k]) == "counts") c->freq_counts = true;
+        else return Usage("--freq modifiers other than 'zs' and 'counts' (cols=, bins) are not supported by plink2_b200.");
       }
       c->freq = true;
     } else if (flag == "--score") {
@@ -3148,10 +3149,18 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   std::vector<uint64_t> alt_dds, tot_dds;
   const int rc = FounderAlleleDosages(ds, ctx, &alt_dds, &tot_dds, c.nonfounders);
   if (rc) return rc;
-  const std::string name = c.out + (c.freq_zs ? ".afreq.zst" : ".afreq");
+  if (c.freq_counts && !c.nonfounders) {  // plink2.cc:2102
+    for (uint8_t fo : ds->samples.is_founder) {
+      if (!fo) {
+        logprintf("Error: \"--freq counts\" specified, but with neither --ac-founders nor --nonfounders; and nonfounders are present.\n");
+        return kRetInconsistentInput;
+      }
+    }
+  }
+  const std::string name = c.out + (c.freq_counts ? ".acount" : ".afreq") + (c.freq_zs ? ".zst" : "");
   OutFile f;
   if (!f.Open(name, c.freq_zs)) return kRetOpenFail;
-  f.Puts(V.provisional_ref ? "#CHROM\tID\tREF\tALT\tPROVISIONAL_REF?\tALT_FREQS\tOBS_CT\n" : "#CHROM\tID\tREF\tALT\tALT_FREQS\tOBS_CT\n");
+  f.Puts((std::string("#CHROM\tID\tREF\tALT\t") + (V.provisional_ref ? "PROVISIONAL_REF?\t" : "") + (c.freq_counts ? "ALT_CTS" : "ALT_FREQS") + "\tOBS_CT\n").c_str());
   for (uint32_t v = 0; v < m; ++v) {
     const uint64_t alt_dd = alt_dds[v], tot_dd = tot_dds[v];
     const double recip = tot_dd ? 1.0 / static_cast<double>(tot_dd) : 0.0;
@@ -3169,14 +3178,15 @@ int RunFreq(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
       *w++ = 'Y';
       *w++ = '\t';
     }
-    w = dtoa_g(static_cast<double>(alt_dd) * recip, w);
+    // 'counts': the allele dosage itself (1/32768 units -> alleles; halves appear for haploid hets)
+    w = dtoa_g(c.freq_counts ? static_cast<double>(alt_dd) * (1.0 / 32768.0) : static_cast<double>(alt_dd) * recip, w);
     *w++ = '\t';
     w = u32toa(static_cast<uint32_t>(tot_dd / 32768ull), w);
     *w++ = '\n';
     f.Advance(w);
   }
   if (!f.Close()) return kRetWriteFail;
-  logprintf("--freq: Allele frequencies (%s) written to %s .\n", c.nonfounders ? "all samples" : "founders only", name.c_str());
+  logprintf("--freq%s: Allele %s (%s) written to %s .\n", c.freq_counts ? " counts" : "", c.freq_counts ? "counts" : "frequencies", c.nonfounders ? "all samples" : "founders only", name.c_str());
   return 0;
 }
 

@@ -119,6 +119,7 @@ $P --bfile x --make-pgen vzs --threads 2 --out $T/xz > /dev/null; cp $T/xz.pvar.
 # --nonfounders: allele frequencies (thresholds, --freq report, LD tie-breaks) from all 120 samples of set X, not its 116 founders
 $P --bfile x --nonfounders --maf 0.1 --mac 30 --make-bed --threads 2 --out $T/n1 > /dev/null; cp $T/n1.bim x_nf.bim
 $P --bfile x --nonfounders --freq --threads 2 --out $T/n2 > /dev/null; cp $T/n2.afreq x_nf.afreq
+$P --bfile x --nonfounders --freq counts --threads 2 --out $T/n4 > /dev/null; cp $T/n4.acount x_nf.acount
 $P --bfile x --chr 1 --nonfounders --indep-pairwise 50 5 0.2 --threads 2 --out $T/n3 > /dev/null; cp $T/n3.prune.in x_nf.prune.in
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null

@@ -126,5 +126,7 @@ def test_nonfounders_frequencies_reach_the_device_commands(mock_so, tmp_path):
     assert "(all samples)" in stdout
     assert open(out + ".afreq", "rb").read() == open(os.path.join(GD, "x_nf.afreq"), "rb").read()
     assert open(out + ".afreq", "rb").read() != open(os.path.join(GD, "x.afreq"), "rb").read()
+    _run(mock_so, ["--bfile", "x", "--nonfounders", "--freq", "counts"], out)  # allele dosages: halves for haploid hets on MT
+    assert open(out + ".acount", "rb").read() == open(os.path.join(GD, "x_nf.acount"), "rb").read()
     _run(mock_so, ["--bfile", "x", "--chr", "1", "--nonfounders", "--indep-pairwise", "50", "5", "0.2"], out)
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "x_nf.prune.in"), "rb").read()
