@@ -79,6 +79,98 @@ int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, ui
   return 0;
 }
 
+// ---- KING pair counts (IncrKing, 2.0/plink2_matrix_calc.cc:1255-1295): the job keeps the variants it was given and counts on
+// request.  counts[pair][5] = IBS0, HETHET, HET2HOM1, HET1HOM2, HOMHOM for pair (j, i), i < j, rows j in reference order.
+}  // extern "C"
+struct Pl2KingJob {
+  uint32_t n, r0, r1;
+  std::vector<uint8_t> codes;  // [variant][sample]
+  uint64_t variants = 0;
+};
+namespace {
+void PairCounts(const Pl2KingJob* job, uint32_t j, uint32_t i, uint32_t* c5) {
+  uint32_t c[5] = {0, 0, 0, 0, 0};
+  for (uint64_t v = 0; v < job->variants; ++v) {
+    const uint8_t gi = job->codes[v * job->n + i], gj = job->codes[v * job->n + j];
+    const bool hi = gi == 0 || gi == 2, hj = gj == 0 || gj == 2, ti = gi == 1, tj = gj == 1;
+    c[0] += hi && hj && gi != gj;
+    c[1] += ti && tj;
+    c[2] += hi && tj;  // sample 2 (= j, the larger index) het, sample 1 hom
+    c[3] += hj && ti;
+    c[4] += hi && hj;
+  }
+  memcpy(c5, c, sizeof(c));
+}
+double Kinship(const uint32_t* c) {
+  const double num = 4.0 * c[0] + c[3] + c[2], den = 4.0 * (c[1] + static_cast<double>(c[2] < c[3] ? c[2] : c[3]));
+  return 0.5 - num / den;
+}
+}  // namespace
+extern "C" {
+int pl2gpu_ctx_mem_info(Pl2GpuCtx*, uint64_t* free_bytes, uint64_t* total_bytes) {
+  const char* e = getenv("PL2_MOCK_MEM_MIB");
+  const uint64_t mib = e ? strtoull(e, nullptr, 10) : 81920;
+  *free_bytes = *total_bytes = mib << 20;
+  return 0;
+}
+uint64_t pl2gpu_king_mem_required(uint32_t sample_ct, uint32_t row_start, uint32_t row_end, uint32_t) {
+  return 2048ull * (static_cast<uint64_t>(row_end) * (row_end - 1) / 2 - static_cast<uint64_t>(row_start) * (row_start ? row_start - 1 : 0) / 2) + 4096ull * sample_ct;
+}
+int pl2gpu_king_begin_ex(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int, uint32_t, Pl2KingJob** job_ptr) {
+  Log("king_begin device=%d rows=%u\n", ctx->device, row_end - row_start);
+  *job_ptr = new Pl2KingJob{sample_ct, row_start, row_end, {}, 0};
+  return 0;
+}
+int pl2gpu_king_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int algo, Pl2KingJob** job_ptr) { return pl2gpu_king_begin_ex(ctx, sample_ct, row_start, row_end, algo, 0, job_ptr); }
+int pl2gpu_king_add_variants(Pl2KingJob* job, const void* genovecs, uint64_t stride, uint32_t variant_ct, int) {
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    for (uint32_t s = 0; s < job->n; ++s) job->codes.push_back(static_cast<uint8_t>(Code(row, s)));
+  }
+  job->variants += variant_ct;
+  return 0;
+}
+int pl2gpu_king_get_counts(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, uint32_t* dst, int) {
+  for (uint32_t j = out_row_start; j < out_row_end; ++j)
+    for (uint32_t i = 0; i < j; ++i, dst += 5) PairCounts(job, j, i, dst);
+  return 0;
+}
+int pl2gpu_king_get_kinship(Pl2KingJob* job, uint32_t out_row_start, uint32_t out_row_end, double* dst, int) {
+  for (uint32_t j = out_row_start; j < out_row_end; ++j) {
+    for (uint32_t i = 0; i < j; ++i) {
+      uint32_t c[5];
+      PairCounts(job, j, i, c);
+      *dst++ = Kinship(c);
+    }
+  }
+  return 0;
+}
+int pl2gpu_king_get_filtered(Pl2KingJob* job, uint32_t r0, uint32_t r1, double min_kinship, uint64_t max_out, uint32_t* pairs_out, uint32_t* counts_out, double* kinship_out, uint64_t* n_found) {
+  uint64_t k = 0;
+  for (uint32_t j = r0; j < r1; ++j) {
+    for (uint32_t i = 0; i < j; ++i) {
+      uint32_t c[5];
+      PairCounts(job, j, i, c);
+      const double kin = Kinship(c);
+      if (kin < min_kinship) continue;
+      if (k < max_out) {
+        pairs_out[2 * k] = j;
+        pairs_out[2 * k + 1] = i;
+        memcpy(counts_out + 5 * k, c, sizeof(c));
+        kinship_out[k] = kin;
+      }
+      ++k;
+    }
+  }
+  *n_found = k;
+  return 0;
+}
+uint64_t pl2gpu_king_variants_added(Pl2KingJob* job) { return job->variants; }
+int pl2gpu_king_end(Pl2KingJob* job) {
+  delete job;
+  return 0;
+}
+
 // pair-decision band on its own (the screening pass of --r2-unphased): flags[v * band + d - 1] = cov^2 > t var1 var2
 // for second = v, first = v - d, exact integer sextuple over samples non-missing in both (plink2_ld.cc:699-723)
 int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, int, uint32_t band, double thresh, uint8_t* flags_host) {

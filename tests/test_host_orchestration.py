@@ -130,3 +130,47 @@ def test_nonfounders_frequencies_reach_the_device_commands(mock_so, tmp_path):
     assert open(out + ".acount", "rb").read() == open(os.path.join(GD, "x_nf.acount"), "rb").read()
     _run(mock_so, ["--bfile", "x", "--chr", "1", "--nonfounders", "--indep-pairwise", "50", "5", "0.2"], out)
     assert open(out + ".prune.in", "rb").read() == open(os.path.join(GD, "x_nf.prune.in"), "rb").read()
+
+
+def _gold(name):
+    p = os.path.join(GD, name)
+    return gzip.open(p, "rb").read() if name.endswith(".gz") else open(p, "rb").read()
+
+
+KING_CASES = [
+    (["--bfile", "a", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--make-king", "bin4", "triangle"], {".kin0": "a_king.kin0.gz", ".king.bin": "a_king.king.bin"}),
+    (["--bfile", "a", "--make-king-table"], {".kin0": "a_kingp.kin0.gz"}),
+    (["--bfile", "a", "--make-king", "square"], {".king": "a_kingsq.king.gz", ".king.id": "a_kingsq.king.id"}),
+    (["--bfile", "a", "--make-king-table", "counts", "--king-table-filter", "0.02"], {".kin0": "a_kingfilt.kin0"}),
+    (["--bfile", "a", "--make-king-table", "counts", "--parallel", "2", "3"], {".kin0.2": "a_kingpar.kin0.2.gz"}),
+    (["--bfile", "q", "--make-king-table", "counts", "cols=+ibs1,+ibs"], {".kin0": "q_king.kin0"}),
+    (["--bfile", "x", "--keep", "x_keep1.txt", "x_keep2.txt", "--remove", "x_remove.txt", "--extract", "x_extract.txt", "--exclude", "x_exclude.txt", "--make-king-table"], {".kin0": "g_xfilt.kin0.gz"}),
+    (["--bfile", "a", "--gpu-memory", "4", "--make-king-table", "counts", "cols=+ibs1,+ibs", "--make-king", "bin4", "triangle"], {".kin0": "a_king.kin0.gz", ".king.bin": "a_king.king.bin"}),
+]
+
+
+@pytest.mark.parametrize("case", range(len(KING_CASES)))
+def test_king_driver_replayed_on_the_cpu(mock_so, tmp_path, case):
+    """RunKing around a stand-in KING job (plain-loop pair counts): table / matrix writers, the device-side filter's
+    contract, a --parallel piece, the rare-variant NSNP accounting of set Q, a filtered view, and - with the device memory
+    capped at 4 MiB - three passes over the variants.  Files byte-identical to the reference's."""
+    args, files = KING_CASES[case]
+    out = str(tmp_path / "o")
+    stdout = _run(mock_so, args, out)
+    for ext, gold in files.items():
+        assert open(out + ext, "rb").read() == _gold(gold), ext
+    if "--gpu-memory" in args:
+        assert "3 passes over the variants" in stdout
+
+
+def test_king_cutoff_chained_into_the_ld_prune(mock_so, tmp_path):
+    """`--king-cutoff 0.02 --indep-pairwise 50 5 0.2` in one run, all of it through the host program: KING pass, greedy
+    relatedness prune (49 survivors), allele frequencies frozen from the 100 pre-prune founders, survivors dropped from
+    the view, LD prune - the reference's chained list.  (The 50-founder guard applies to the pre-prune dataset.)"""
+    out, log = str(tmp_path / "o"), str(tmp_path / "mock.log")
+    stdout = _run(mock_so, ["--bfile", "a", "--king-cutoff", "0.02", "--indep-pairwise", "50", "5", "0.2"], out, log=log)
+    assert "49 samples remaining after the relatedness prune." in stdout
+    assert open(out + ".king.cutoff.in.id", "rb").read() == _gold("a_cut.king.cutoff.in.id")
+    assert open(out + ".prune.in", "rb").read() == _gold("g_acut.prune.in")
+    calls = [ln.split()[0] for ln in open(log)]
+    assert calls.index("king_begin") < calls.index("geno_counts") < calls.index("indep_pairwise")
