@@ -85,3 +85,20 @@ def test_king_cutoff_table_feeds_pca(golden_dir, tmp_path):
     assert got.shape == want.shape == (50, 3)
     sign = np.sign((got * want).sum(axis=0))
     assert np.allclose(got * sign, want, atol=2e-5)
+
+
+def test_king_cutoff_feeds_ld_prune(golden_dir, tmp_path):
+    """`--king-cutoff 0.02 --indep-pairwise 50 5 0.2`: 49 survivors (below the 50-founder guard, which applies to the
+    pre-prune dataset), frequencies frozen before the prune - the reference's chained keep-list."""
+    out = _run(golden_dir, tmp_path, ["--bfile", "a", "--king-cutoff", "0.02", "--indep-pairwise", "50", "5", "0.2"])
+    assert open(out + ".prune.in", "rb").read() == _gold(golden_dir, "g_acut.prune.in")
+    assert open(out + ".king.cutoff.in.id", "rb").read() == _gold(golden_dir, "a_cut.king.cutoff.in.id")
+
+
+@pytest.mark.parametrize("args,gold", [(["--bfile", "a", "--r2-unphased"], "a_r2.vcor.gz"),
+                                       (["--bfile", "a", "--r2-unphased", "--ld-window", "7", "--ld-window-r2", "0.5"], "a_r2w.vcor.gz"),
+                                       (["--bfile", "x", "--not-chr", "X", "--keep", "x_keep1.txt", "x_keep2.txt", "--r2-unphased", "--ld-window-r2", "0.3", "--ld-window-kb", "0.1"], "x_r2.vcor.gz")])
+def test_r2_unphased_tables_byte_identical(golden_dir, tmp_path, args, gold):
+    """--r2-unphased: pair band screened on the device (pl2gpu_ld_band_flags), flagged pairs finished on the host."""
+    out = _run(golden_dir, tmp_path, args)
+    assert open(out + ".vcor", "rb").read() == _gold(golden_dir, gold)

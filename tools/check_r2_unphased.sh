@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # --r2-unphased on the device (screen = pl2gpu_ld_band_flags) against the reference's tables.  One GPU, seconds.
-# NOT YET RUN ON HARDWARE: the host half is pinned on the CPU through tests/test_host_orchestration.py (stand-in library);
-# the device entry point it calls is the one tests/test_ld_gpu.py validates.
+# Run on the B200 as part of tools/gpu_quick.sh (profiles/r02_quick_check.txt): identical.  The host half is also pinned
+# on the CPU through tests/test_host_orchestration.py (stand-in library).
 set -u
 mkdir -p gpurun_out/r2u
 B=$PWD/plink_ng_b200/plink2_b200
