@@ -227,6 +227,22 @@ int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* 
       log->push_back(std::to_string(m - left) + " variant" + (m - left == 1 ? "" : "s") + " excluded by chromosome filter, " + std::to_string(left) + " remaining.");
       changed = true;
     }
+    if (spec.min_alleles || spec.max_alleles != 0xFFFFFFFFu) {
+      // allele count = REF + comma-separated ALTs; a lone missing ALT code counts as no ALT allele (:1944-1948).  This is
+      // what lets a file with some multiallelic records through: "--max-alleles 2" drops them before anything is decoded.
+      uint32_t left = 0;
+      for (uint32_t v = 0; v < m; ++v) {
+        if (keep[v]) {
+          const std::string& alt = V.alt[v];
+          uint32_t ct = 2 + static_cast<uint32_t>(std::count(alt.begin(), alt.end(), ','));
+          if (alt == ".") ct = 1;
+          keep[v] = ct >= spec.min_alleles && ct <= spec.max_alleles;
+          left += keep[v];
+        }
+      }
+      log->push_back(std::to_string(m - left) + " variant" + (m - left == 1 ? "" : "s") + " excluded by --min-alleles / --max-alleles, " + std::to_string(left) + " remaining.");
+      changed = true;
+    }
     if (spec.snps_only) {
       auto acgt_or_missing = [](char ch) { return ch == '.' || ch == '0' || strchr("ACGTacgt", ch) != nullptr; };
       uint32_t left = 0;

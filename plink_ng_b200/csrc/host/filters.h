@@ -17,6 +17,7 @@ struct FilterSpec {
   std::vector<std::string> extract, exclude;                    // variant-ID token files (TokenExtractExclude)
   std::vector<uint8_t> chr_mask, not_chr_mask;                  // 27 flags each when the flag was given
   bool autosome = false, autosome_xy = false;
+  uint32_t min_alleles = 0, max_alleles = 0xFFFFFFFFu;  // --min-alleles / --max-alleles (LoadPvar, plink2_pvar.cc:1939-1952)
   int snps_only = 0;                      // 1 --snps-only, 2 --snps-only just-acgt (LoadPvar, plink2_pvar.cc:1917-1931)
   int64_t from_bp = -1, to_bp = -1;       // --from-bp/-kb/-mb, --to-bp/-kb/-mb: with --chr naming one chromosome (plink2.cc:764-787)
   bool excl_males = false, excl_females = false, excl_nosex = false;  // --keep-males / --remove-females / ... (plink2.cc:1688)
@@ -29,7 +30,7 @@ struct FilterSpec {
     if (excl_males || excl_females || excl_nosex || founders_only) return true;
     return any_id_filter();
   }
-  bool any_id_filter() const { return !(keep.empty() && remove.empty() && keep_fam.empty() && remove_fam.empty() && extract.empty() && exclude.empty() && chr_mask.empty() && not_chr_mask.empty()) || autosome || autosome_xy || snps_only || from_bp != -1 || to_bp != -1; }
+  bool any_id_filter() const { return !(keep.empty() && remove.empty() && keep_fam.empty() && remove_fam.empty() && extract.empty() && exclude.empty() && chr_mask.empty() && not_chr_mask.empty()) || autosome || autosome_xy || min_alleles || max_alleles != 0xFFFFFFFFu || snps_only || from_bp != -1 || to_bp != -1; }
 };
 
 // "1-4,22,X" style arguments (ParseChrRanges, plink2_common.cc:3695) -> 27 flags.  False + *err on a bad token.

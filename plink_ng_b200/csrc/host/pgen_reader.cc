@@ -235,7 +235,7 @@ malformed:
   return false;
 }
 
-bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err) const {
+bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err, bool as_ld_base) const {
   const uint8_t* rec;
   uint32_t len;
   if (!ReadRecordBytes(vidx, &rec, &len, err)) return false;
@@ -258,8 +258,8 @@ bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std
     return true;
   }
   const uint32_t vrtype = (mode_ == 0x02) ? 0 : vrtypes_[vidx];
-  if (vrtype & 8) {
-    *err = "multiallelic variant records are not supported by the pairwise-genotype commands (split them first)";
+  if ((vrtype & 8) && !as_ld_base) {
+    *err = "multiallelic variant records are not supported by the pairwise-genotype commands (drop them with --max-alleles 2, or split them first)";
     return false;
   }
   const uint8_t* end = rec + len;
@@ -306,7 +306,7 @@ bool PgenReader::DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std
         --b;
       } while ((vrtypes_[b] & 6) == 2);
       if (st->ldbase_vidx != b) {
-        if (!DecodeRecord(st, b, st->ldbase.data(), err)) return false;
+        if (!DecodeRecord(st, b, st->ldbase.data(), err, true)) return false;
         st->ldbase_vidx = b;
       }
       memcpy(dst, st->ldbase.data(), words * 8ull);

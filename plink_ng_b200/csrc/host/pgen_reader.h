@@ -56,7 +56,9 @@ class PgenReader {
     std::vector<uint64_t> ldbase, scratch;
     uint32_t ldbase_vidx = 0xFFFFFFFFu;
   };
-  bool DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err) const;
+  // as_ld_base: only the main track of `vidx` is wanted, as the base of an LD-compressed neighbour - a multiallelic
+  // record is acceptable then (its main track has the biallelic layout; the allele patches that follow are not read)
+  bool DecodeRecord(DecodeState* st, uint32_t vidx, uint64_t* dst, std::string* err, bool as_ld_base = false) const;
   bool GetSubsetWith(DecodeState* st, uint32_t vidx, const uint64_t* sample_include, uint32_t sample_ct, uint64_t* genovec, std::string* err) const;
   bool ReadRecordBytes(uint32_t vidx, const uint8_t** rec, uint32_t* len, std::string* err) const;
   bool ParseDifflistAndApply(const uint8_t* p, const uint8_t* end, bool with_values, uint64_t* genovec, uint32_t fixed_value, std::string* err, const uint8_t** after) const;

@@ -473,6 +473,10 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (!need(1, 1) || !ParseDouble(prm[0], &dxx) || dxx > 1.0) return Usage("Invalid --ld-window-r2 argument.");
       if (dxx > 0.0) dxx *= 1 - 1.0 / 17592186044416.0;
       c->ld_min_r2 = dxx;
+    } else if (flag == "--max-alleles" || flag == "--min-alleles") {
+      uint32_t u;
+      if (!need(1, 1) || !ParseU32(prm[0], &u) || !u) return Usage(("Invalid " + flag + " argument.").c_str());
+      (flag == "--max-alleles" ? c->filters.max_alleles : c->filters.min_alleles) = u;
     } else if (flag == "--snps-only") {
       if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "just-acgt"))) return Usage("Invalid --snps-only argument (only 'just-acgt' is accepted).");
       c->filters.snps_only = 1 + nparam;

@@ -177,6 +177,10 @@ fi
 python make_ped_set.py
 $P --pedmap p --make-bed --threads 2 --out $T/p > /dev/null; for e in bed bim fam; do cp $T/p.$e p.$e; done
 $P --ped pc.ped --map pc.map --make-bed --threads 2 --out $T/pc > /dev/null; cp $T/pc.bed pc.bed; cp $T/pc.bim pc.bim
+# --- set MA: a .pgen with multiallelic records, one of them the LD base of a biallelic record (make_multiallelic_set.py)
+python make_multiallelic_set.py
+$P --vcf ma.vcf --make-pgen --threads 2 --out $T/ma > /dev/null; cp $T/ma.pgen ma.pgen; cp $T/ma.pvar ma.pvar; cp $T/ma.psam ma.psam; rm ma.vcf
+$P --pfile ma --max-alleles 2 --make-bed --threads 2 --out $T/ma_bi > /dev/null; cp $T/ma_bi.bed ma_bi.bed; cp $T/ma_bi.bim ma_bi.bim
 # --- set T: the reference's own toy fixture (1.9/toy.ped + toy.map; BASELINE.json configs[0])
 if [ -f /root/reference/1.9/toy.ped ]; then
   $P --ped /root/reference/1.9/toy.ped --map /root/reference/1.9/toy.map --make-bed --out $T/toy > /dev/null

@@ -416,6 +416,23 @@ def test_ped_map_import_matches_reference(tmp_path):
         assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "toy." + ext), "rb").read(), ext
 
 
+def test_max_alleles_lets_a_file_with_multiallelic_records_through(tmp_path):
+    """Real .pgen files carry some multiallelic variants; `--max-alleles 2` (what plink2 users pass) removes them in the
+    variant view, so their records are never decoded as data.  One of them IS still read - as the LD base of the
+    biallelic record behind it, whose main track has the biallelic layout.  Result byte-identical to the reference's,
+    multi-threaded and single-threaded; without the filter the file is refused with a pointer to the flag."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    for threads in ("1", "4"):
+        r = subprocess.run([BIN, "--pfile", "ma", "--max-alleles", "2", "--threads", threads, "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "20 variants excluded" in r.stdout
+        for ext in ("bed", "bim"):
+            assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "ma_bi." + ext), "rb").read(), ext
+    r = subprocess.run([BIN, "--pfile", "ma", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "--max-alleles 2" in r.stdout
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
