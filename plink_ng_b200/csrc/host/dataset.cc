@@ -175,6 +175,8 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
     auto allele = [&](int col) { return col >= 0 && col < static_cast<int>(t.size()) && t[col] != "0" ? t[col] : std::string("."); };
     out->ref.push_back(allele(cref));
     out->alt.push_back(allele(calt));
+    auto is_zero = [&](int col) { return col >= 0 && col < static_cast<int>(t.size()) && t[col] == "0"; };
+    out->zero_allele.push_back(static_cast<uint8_t>((is_zero(cref) ? 1 : 0) | (is_zero(calt) ? 2 : 0)));
     if (col_cm >= 0) out->cm.push_back(ccm >= 0 && ccm < static_cast<int>(t.size()) ? t[ccm] : std::string("0"));
   }
   return true;

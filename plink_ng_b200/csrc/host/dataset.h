@@ -31,6 +31,7 @@ struct VariantInfo {
   std::vector<uint32_t> bp;
   std::vector<std::string> id;
   std::vector<std::string> chr_name, ref, alt;  // as written in the file (.bim: REF = column 6, ALT = column 5)
+  std::vector<uint8_t> zero_allele;             // bit 0 / 1: REF / ALT was written as the '0' missing code (stored as '.')
   std::vector<std::string> cm;                  // centimorgan token (.bim column 3 / .pvar CM column); empty: no such column
   bool provisional_ref = false;                 // .bim input: REF alleles are provisional (PROVISIONAL_REF? = Y)
   uint32_t size() const { return static_cast<uint32_t>(id.size()); }

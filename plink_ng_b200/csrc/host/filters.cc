@@ -201,6 +201,7 @@ void KeepVariants(Dataset* ds, const std::vector<uint8_t>& keep) {
   Compact(&V.ref, keep);
   Compact(&V.alt, keep);
   Compact(&V.cm, keep);
+  Compact(&V.zero_allele, keep);
   Compact(&ds->read_ref_freq, keep);
   InstallView(ds);
 }

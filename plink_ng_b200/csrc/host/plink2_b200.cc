@@ -107,6 +107,8 @@ struct Cmd {
   bool r2_unphased = false, r2_zs = false;
   uint32_t ld_var_radius = 0x7fffffff, ld_bp_radius = 0xFFFFFFFFu;  // UINT32_MAX: --ld-window-kb not given (default 1000 kb)
   double ld_min_r2 = 2.0;                                             // 2.0: not given (default 0.2 (1 - 2^-44))
+  std::string var_id_template;   // --set-all-var-ids / --set-missing-var-ids <template> ('@' chromosome, '#' bp, $r $a $1 $2 alleles)
+  bool var_id_all = false;
   bool nonfounders = false;  // --nonfounders: allele frequencies (and everything derived from them) from all samples, not founders only
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
@@ -473,6 +475,12 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       if (!need(1, 1) || !ParseDouble(prm[0], &dxx) || dxx > 1.0) return Usage("Invalid --ld-window-r2 argument.");
       if (dxx > 0.0) dxx *= 1 - 1.0 / 17592186044416.0;
       c->ld_min_r2 = dxx;
+    } else if (flag == "--set-all-var-ids" || flag == "--set-missing-var-ids") {
+      if (!need(1, 1)) return Usage((flag + " requires a template string.").c_str());
+      if (!c->var_id_template.empty()) return Usage("--set-all-var-ids cannot be used with --set-missing-var-ids in plink2_b200.");
+      c->var_id_template = prm[0];
+      c->var_id_all = flag == "--set-all-var-ids";
+      if (c->var_id_template.find('@') == std::string::npos || c->var_id_template.find('#') == std::string::npos) return Usage((flag + " template must contain '@' (chromosome) and '#' (bp coordinate).").c_str());
     } else if (flag == "--max-alleles" || flag == "--min-alleles") {
       uint32_t u;
       if (!need(1, 1) || !ParseU32(prm[0], &u) || !u) return Usage(("Invalid " + flag + " argument.").c_str());
@@ -3830,6 +3838,36 @@ int main(int argc, char** argv) {
   for (uint8_t f : ds.samples.is_founder) founder_ct += f;
   logprintf("%u sample%s (%u founder%s) loaded from %s.\n", ds.samples.size(), ds.samples.size() == 1 ? "" : "s", founder_ct, founder_ct == 1 ? "" : "s", c.psam.c_str());
   logprintf("%u variant%s loaded from %s.\n", ds.variants.size(), ds.variants.size() == 1 ? "" : "s", c.pvar.c_str());
+  if (!c.var_id_template.empty()) {
+    // variant IDs from a template, assigned while the .pvar is loaded in the reference (plink2_pvar.cc VaridTemplate*):
+    // before any ID-based filter.  Alleles longer than 23 characters are refused (--new-id-max-allele-len default).
+    VariantInfo& V = ds.variants;
+    uint32_t changed = 0;
+    for (uint32_t v = 0; v < V.size(); ++v) {
+      if (!c.var_id_all && V.id[v] != ".") continue;
+      // the template sees the allele codes as written in the file: a '0' missing code stays '0' in the ID
+      const std::string ref = (V.zero_allele[v] & 1) ? std::string("0") : V.ref[v];
+      const std::string alt1 = (V.zero_allele[v] & 2) ? std::string("0") : V.alt[v].substr(0, V.alt[v].find(','));
+      if (ref.size() > 23 || alt1.size() > 23) {
+        logprintf("Error: Allele code of variant %u is longer than 23 characters; plink2_b200 does not implement --new-id-max-allele-len.\n", v + 1);
+        return kRetInconsistentInput;
+      }
+      const bool ref_first = strcmp(ref.c_str(), alt1.c_str()) <= 0;
+      std::string id;
+      const std::string& t = c.var_id_template;
+      for (size_t k = 0; k < t.size(); ++k) {
+        if (t[k] == '@') id += ChrNameOut(V.chr_code[v], V.chr_name[v]);
+        else if (t[k] == '#') id += std::to_string(V.bp[v]);
+        else if (t[k] == '$' && k + 1 < t.size() && strchr("ra12", t[k + 1])) {
+          const char sel = t[++k];
+          id += sel == 'r' ? ref : sel == 'a' ? alt1 : ((sel == '1') == ref_first) ? ref : alt1;
+        } else id += t[k];
+      }
+      V.id[v] = id;
+      ++changed;
+    }
+    logprintf("--set-%s-var-ids: %u variant ID%s assigned.\n", c.var_id_all ? "all" : "missing", changed, changed == 1 ? "" : "s");
+  }
   {  // .fam phenotype column of --make-bed: the first case/control or quantitative phenotype, typed over all loaded samples
     for (size_t p = 0; p < ds.samples.pheno_names.size() && ds.samples.fam_pheno.empty(); ++p) {
       PhenoOut po;

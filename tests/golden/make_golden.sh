@@ -121,6 +121,9 @@ $P --bfile x --nonfounders --maf 0.1 --mac 30 --make-bed --threads 2 --out $T/n1
 $P --bfile x --nonfounders --freq --threads 2 --out $T/n2 > /dev/null; cp $T/n2.afreq x_nf.afreq
 $P --bfile x --nonfounders --freq counts --threads 2 --out $T/n4 > /dev/null; cp $T/n4.acount x_nf.acount
 $P --bfile x --chr 1 --nonfounders --indep-pairwise 50 5 0.2 --threads 2 --out $T/n3 > /dev/null; cp $T/n3.prune.in x_nf.prune.in
+# --set-missing-var-ids on a .bim whose every third ID is '.' (alleles incl. '0' codes, multi-character and symbolic ones)
+awk 'BEGIN{OFS="\t"} {if (NR%3==0) $2="."; print}' x_alleles.bim > x_noid.bim
+$P --bed x.bed --bim x_noid.bim --fam x.fam --set-missing-var-ids '@:#:$1:$2' --make-bed --threads 2 --out $T/v1 > /dev/null; cp $T/v1.bim x_setid.bim
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

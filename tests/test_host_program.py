@@ -433,6 +433,21 @@ def test_max_alleles_lets_a_file_with_multiallelic_records_through(tmp_path):
     assert r.returncode != 0 and "--max-alleles 2" in r.stdout
 
 
+def test_variant_id_templates(tmp_path):
+    """--set-missing-var-ids / --set-all-var-ids (the usual fix for the duplicate '.' IDs that --indep-pairwise refuses):
+    '@' chromosome, '#' position, $r / $a / $1 / $2 alleles - a '0' missing-allele code stays '0' inside the ID even
+    though the allele itself is stored as '.'.  IDs as the reference assigns them."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bed", "x.bed", "--bim", "x_noid.bim", "--fam", "x.fam", "--set-missing-var-ids", "@:#:$1:$2", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert open(out + ".bim", "rb").read() == open(os.path.join(gd, "x_setid.bim"), "rb").read()
+    r = subprocess.run([BIN, "--bfile", "x", "--set-all-var-ids", "@_#", "--chr", "MT", "--write-snplist", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0 and open(out + ".snplist").read().split()[:2] == ["MT_700", "MT_701"]
+    r = subprocess.run([BIN, "--bfile", "x", "--set-all-var-ids", "nochrom", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0 and "template must contain" in r.stdout + r.stderr
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
