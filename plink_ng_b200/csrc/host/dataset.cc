@@ -30,6 +30,7 @@ bool ParseChr(const std::string& tok, uint32_t* code) {
 }
 
 std::string ChrNameOut(uint32_t code, const std::string& as_read) {
+  if (code > 26) return as_read;  // --allow-extra-chr contig: as written
   if (code <= 22) return std::to_string(code);
   if (code == 23) return "X";
   if (code == 24) return "Y";
@@ -113,7 +114,8 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
   return true;
 }
 
-bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
+bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err, bool allow_extra_chr) {
+  std::vector<std::string> extra_names;
   std::vector<std::string> lines;
   if (!ReadLines(path, &lines, err)) return false;
   size_t li = 0;
@@ -163,8 +165,13 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err) {
       return false;
     }
     uint32_t code;
-    if (!ParseChr(t[col_chr], &code)) {
-      *err = "Invalid chromosome code '" + t[col_chr] + "' on line " + std::to_string(li + 1) + " of " + path + " (contigs outside the human chromosome set are not supported).";
+    if (!ParseChr(t[col_chr], &code) && allow_extra_chr) {
+      size_t k = 0;
+      while (k < extra_names.size() && extra_names[k] != t[col_chr]) ++k;
+      if (k == extra_names.size()) extra_names.push_back(t[col_chr]);
+      code = 27 + static_cast<uint32_t>(k);
+    } else if (!ParseChr(t[col_chr], &code)) {
+      *err = "Invalid chromosome code '" + t[col_chr] + "' on line " + std::to_string(li + 1) + " of " + path + " (use --allow-extra-chr to keep contigs outside the human chromosome set).";
       return false;
     }
     out->chr_code.push_back(code);

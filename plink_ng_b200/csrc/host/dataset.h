@@ -43,7 +43,10 @@ bool ParseChr(const std::string& tok, uint32_t* code);
 // 2.0/plink2_common.cc:2150-2227): bare number for autosomes, X / Y / XY / MT, PAR1 / PAR2 kept.
 std::string ChrNameOut(uint32_t code, const std::string& as_read);
 bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err);
-bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err);
+// allow_extra_chr (--allow-extra-chr): a name outside the human set becomes its own diploid, autosome-like contig with a
+// code >= 27 (one per distinct name, in order of appearance), printed as written - the reference's treatment of
+// unrecognised contigs (not haploid, not in the --autosome set, kept by KING / GRM, its own LD-prune unit).
+bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err, bool allow_extra_chr = false);
 
 inline bool IsAutosome(uint32_t chr_code) { return chr_code >= 1 && chr_code <= 22; }
 // CountNonAutosomalVariants(..., count_x=1, count_mt=1) semantics used by CalcKing/CalcGrm

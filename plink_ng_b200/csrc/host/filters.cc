@@ -219,9 +219,9 @@ int ApplyFilters(const FilterSpec& spec, Dataset* ds, std::vector<std::string>* 
       for (uint32_t v = 0; v < m; ++v) {
         const uint32_t c = V.chr_code[v];
         bool ok = true;
-        if (!spec.chr_mask.empty()) ok = spec.chr_mask[c];
+        if (!spec.chr_mask.empty()) ok = c < 27 && spec.chr_mask[c];
         if (spec.autosome || spec.autosome_xy) ok = ok && ((c >= 1 && c <= 22) || (spec.autosome_xy && c == 25));
-        if (!spec.not_chr_mask.empty() && spec.not_chr_mask[c]) ok = false;
+        if (!spec.not_chr_mask.empty() && c < 27 && spec.not_chr_mask[c]) ok = false;
         keep[v] = ok;
         left += ok;
       }

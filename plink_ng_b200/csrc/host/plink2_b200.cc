@@ -109,6 +109,7 @@ struct Cmd {
   double ld_min_r2 = 2.0;                                             // 2.0: not given (default 0.2 (1 - 2^-44))
   std::string var_id_template;   // --set-all-var-ids / --set-missing-var-ids <template> ('@' chromosome, '#' bp, $r $a $1 $2 alleles)
   bool var_id_all = false;
+  bool allow_extra_chr = false;  // --allow-extra-chr: unrecognised contig names are kept as autosome-like contigs
   bool nonfounders = false;  // --nonfounders: allele frequencies (and everything derived from them) from all samples, not founders only
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
@@ -481,6 +482,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       c->var_id_template = prm[0];
       c->var_id_all = flag == "--set-all-var-ids";
       if (c->var_id_template.find('@') == std::string::npos || c->var_id_template.find('#') == std::string::npos) return Usage((flag + " template must contain '@' (chromosome) and '#' (bp coordinate).").c_str());
+    } else if (flag == "--allow-extra-chr") {
+      if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "0"))) return Usage("Invalid --allow-extra-chr argument.");
+      c->allow_extra_chr = true;
     } else if (flag == "--max-alleles" || flag == "--min-alleles") {
       uint32_t u;
       if (!need(1, 1) || !ParseU32(prm[0], &u) || !u) return Usage(("Invalid " + flag + " argument.").c_str());
@@ -3825,7 +3829,7 @@ int main(int argc, char** argv) {
     }
     logprintf("--pedmap: %u sample%s, %u variant%s; %s.bed + %s.bim + %s.fam written%s.\n", pn, pn == 1 ? "" : "s", pm, pm == 1 ? "" : "s", prefix.c_str(), prefix.c_str(), prefix.c_str(), c.keep_autoconv ? "" : " (temporary)");
   }
-  if (!LoadSamples(c.psam, &ds.samples, &err) || !LoadVariants(c.pvar, &ds.variants, &err)) {
+  if (!LoadSamples(c.psam, &ds.samples, &err) || !LoadVariants(c.pvar, &ds.variants, &err, c.allow_extra_chr)) {
     logprintf("Error: %s\n", err.c_str());
     return kRetOpenFail;
   }

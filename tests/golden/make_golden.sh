@@ -124,6 +124,11 @@ $P --bfile x --chr 1 --nonfounders --indep-pairwise 50 5 0.2 --threads 2 --out $
 # --set-missing-var-ids on a .bim whose every third ID is '.' (alleles incl. '0' codes, multi-character and symbolic ones)
 awk 'BEGIN{OFS="\t"} {if (NR%3==0) $2="."; print}' x_alleles.bim > x_noid.bim
 $P --bed x.bed --bim x_noid.bim --fam x.fam --set-missing-var-ids '@:#:$1:$2' --make-bed --threads 2 --out $T/v1 > /dev/null; cp $T/v1.bim x_setid.bim
+# --allow-extra-chr: set X with its XY block renamed chrUn_KI270 and half of MT renamed GL000.1 (diploid, autosome-like contigs)
+awk 'BEGIN{OFS="\t"} {if ($1=="XY") $1="chrUn_KI270"; if ($1=="MT" && ++k<=50) $1="GL000.1"; print}' x.bim > x_contigs.bim
+$P --bed x.bed --bim x_contigs.bim --fam x.fam --allow-extra-chr --not-chr 1,X --make-bed --threads 2 --out $T/e1 > /dev/null; cp $T/e1.bim x_contigs_sub.bim
+$P --bed x.bed --bim x_contigs.bim --fam x.fam --allow-extra-chr --not-chr X,Y,MT --indep-pairwise 50 5 0.2 --threads 2 --out $T/e2 > /dev/null; cp $T/e2.prune.in x_contigs.prune.in
+$P --bed x.bed --bim x_contigs.bim --fam x.fam --allow-extra-chr --make-king-table --threads 2 --out $T/e3 > /dev/null; gzip -9 -n -c $T/e3.kin0 > x_contigs.kin0.gz
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

@@ -211,8 +211,8 @@ int pl2_indep_pairwise_ex(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride,
                           double r2_thresh, int window_is_bp, const double* ref_freqs, const uint8_t* preferred, int, const uint8_t*, uint32_t flags_in, uint8_t* removed_out) {
   Log("indep_pairwise device=%d variants=%u\n", ctx->device, variant_ct);
   for (uint32_t v = 0; v < variant_ct; ++v) {
-    if (chr_codes[v] < 1 || chr_codes[v] > 22) {
-      t_err = "mock: autosomes only";
+    if (chr_codes[v] == 0 || chr_codes[v] == 23 || chr_codes[v] == 24 || chr_codes[v] == 26) {  // the diploid class of ld.cu's ClassOf
+      t_err = "mock: diploid chromosomes only";
       return 1;
     }
   }

@@ -174,3 +174,19 @@ def test_king_cutoff_chained_into_the_ld_prune(mock_so, tmp_path):
     assert open(out + ".prune.in", "rb").read() == _gold("g_acut.prune.in")
     calls = [ln.split()[0] for ln in open(log)]
     assert calls.index("king_begin") < calls.index("geno_counts") < calls.index("indep_pairwise")
+
+
+def test_extra_contigs_are_diploid_autosome_like_units(mock_so, tmp_path):
+    """--allow-extra-chr: unrecognised contig names (here chrUn_KI270 and GL000.1 carved out of set X) get their own
+    codes, are printed as written, stay out of --autosome / numeric --not-chr lists, are kept by KING, and are LD-pruned
+    as diploid chromosomes of their own - outputs identical to the reference's; without the flag the file is refused."""
+    data = ["--bed", "x.bed", "--bim", "x_contigs.bim", "--fam", "x.fam", "--allow-extra-chr"]
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN] + data + ["--not-chr", "1,X", "--make-bed", "--out", out], capture_output=True, text=True, cwd=GD)
+    assert r.returncode == 0 and open(out + ".bim", "rb").read() == _gold("x_contigs_sub.bim")
+    _run(mock_so, data + ["--not-chr", "X,Y,MT", "--indep-pairwise", "50", "5", "0.2"], out)
+    assert open(out + ".prune.in", "rb").read() == _gold("x_contigs.prune.in")
+    _run(mock_so, data + ["--make-king-table"], out)
+    assert open(out + ".kin0", "rb").read() == _gold("x_contigs.kin0.gz")
+    r = subprocess.run([BIN] + data[:-1] + ["--make-bed", "--out", out], capture_output=True, text=True, cwd=GD)
+    assert r.returncode != 0 and "--allow-extra-chr" in r.stdout
