@@ -552,3 +552,37 @@ def test_read_freq_parser_counts_match_the_reference_log(tmp_path):
     assert "--read-freq: PLINK 2 --freq file detected." in r.stdout
     assert "--read-freq: Frequencies for 849 variants loaded." in r.stdout
     assert "Warning: 60 entries skipped" in r.stdout
+
+
+def test_view_and_subset_decode_against_a_numpy_model(tmp_path):
+    """Property test of the reader view: random --keep lists (so the raw-sample keep bitset has arbitrary gaps across
+    the 32- and 64-sample word boundaries) composed with a random founder subset of the view (the sample_include a
+    founder-only command passes), on set S's genotypes (300 samples = five 64-sample words) under a .fam with about half the samples marked as non-founders.
+    The .bed the program writes for "founders of the kept samples" must equal the same selection done with numpy."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    rng = np.random.default_rng(2026)
+    fam = [ln.split() for ln in open(os.path.join(gd, "s.fam"))]
+    n = len(fam)
+    geno = orc.read_bed(os.path.join(gd, "s.bed"), n)  # [variants, samples], codes 0..3
+    to_bed = np.array([3, 2, 0, 1], dtype=np.uint8)  # PLINK 2 code -> .bed code
+    for trial in range(12):
+        nonfounder = rng.random(n) < 0.5
+        with open(tmp_path / "t.fam", "w") as f:
+            for k, row in enumerate(fam):
+                f.write(" ".join([row[0], row[1], "p%d" % k if nonfounder[k] else "0", "0", row[4], row[5]]) + "\n")
+        kept = rng.random(n) < rng.uniform(0.2, 0.95)
+        kept[rng.integers(0, n)] = True
+        if not (kept & ~nonfounder).any():
+            continue
+        (tmp_path / "keep.txt").write_text("".join("%s %s\n" % (fam[k][0], fam[k][1]) for k in range(n) if kept[k]))
+        out = str(tmp_path / "o")
+        r = subprocess.run([BIN, "--bed", os.path.join(gd, "s.bed"), "--bim", os.path.join(gd, "s.bim"), "--fam", str(tmp_path / "t.fam"), "--keep", str(tmp_path / "keep.txt"), "--debug-founders-bed",
+                            "--threads", str(1 + trial % 3), "--out", out], capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout + r.stderr
+        sel = np.flatnonzero(kept & ~nonfounder)
+        codes = to_bed[geno[:, sel]]
+        pad = (-len(sel)) % 4
+        if pad:
+            codes = np.concatenate([codes, np.zeros((codes.shape[0], pad), dtype=np.uint8)], axis=1)
+        packed = (codes[:, 0::4] | (codes[:, 1::4] << 2) | (codes[:, 2::4] << 4) | (codes[:, 3::4] << 6)).astype(np.uint8)
+        assert open(out + ".bed", "rb").read() == b"\x6c\x1b\x01" + packed.tobytes(), trial
