@@ -566,4 +566,86 @@ int WriteBedFileset(Dataset* ds, const std::string& out_prefix, uint32_t thread_
   return 0;
 }
 
+int WritePgenFileset(Dataset* ds, const std::string& out_prefix, uint32_t thread_ct, bool provisional_ref, std::string* err) {
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  char num[40];
+  {  // .psam
+    bool any_fid = false, any_parent = false;
+    for (uint32_t k = 0; k < n; ++k) {
+      any_fid = any_fid || S.fid[k] != "0";
+      any_parent = any_parent || S.pat[k] != "0" || S.mat[k] != "0";
+    }
+    OutFile f;
+    if (!f.Open(out_prefix + ".psam")) {
+      *err = "Failed to open " + out_prefix + ".psam for writing.";
+      return 3;
+    }
+    std::string h = any_fid ? "#FID\tIID" : "#IID";
+    if (S.sid_present) h += "\tSID";
+    if (any_parent) h += "\tPAT\tMAT";
+    h += "\tSEX";
+    if (!S.fam_pheno.empty()) h += "\tPHENO1";
+    h += "\n";
+    f.Write(h.data(), h.size());
+    for (uint32_t k = 0; k < n; ++k) {
+      std::string line = any_fid ? (S.fid[k] + "\t" + S.iid[k]) : S.iid[k];
+      if (S.sid_present) line += "\t" + S.sid[k];
+      if (any_parent) line += "\t" + S.pat[k] + "\t" + S.mat[k];
+      line += S.sex[k] == 1 ? "\t1" : S.sex[k] == 2 ? "\t2" : "\tNA";
+      if (!S.fam_pheno.empty()) line += "\t" + (S.fam_pheno[k] == "-9" ? std::string("NA") : S.fam_pheno[k]);
+      line += "\n";
+      f.Write(line.data(), line.size());
+    }
+    if (!f.Close()) return 5;
+  }
+  {  // .pvar
+    bool any_cm = false;
+    for (const std::string& cm : V.cm) any_cm = any_cm || strtod(cm.c_str(), nullptr) != 0.0;
+    OutFile f;
+    if (!f.Open(out_prefix + ".pvar")) {
+      *err = "Failed to open " + out_prefix + ".pvar for writing.";
+      return 3;
+    }
+    f.Puts(any_cm ? "#CHROM\tPOS\tID\tREF\tALT\tCM\n" : "#CHROM\tPOS\tID\tREF\tALT\n");
+    for (uint32_t v = 0; v < m; ++v) {
+      std::string line = ChrNameOut(V.chr_code[v], V.chr_name[v]) + "\t" + std::to_string(V.bp[v]) + "\t" + V.id[v] + "\t" + V.ref[v] + "\t" + V.alt[v];
+      if (any_cm) {
+        *dtoa_g(strtod(V.cm[v].c_str(), nullptr), num) = '\0';
+        line += std::string("\t") + num;
+      }
+      line += "\n";
+      f.Write(line.data(), line.size());
+    }
+    if (!f.Close()) return 5;
+  }
+  OutFile f;
+  if (!f.Open(out_prefix + ".pgen")) {
+    *err = "Failed to open " + out_prefix + ".pgen for writing.";
+    return 3;
+  }
+  uint8_t hdr[12] = {0x6c, 0x1b, 0x02, 0, 0, 0, 0, 0, 0, 0, 0, static_cast<uint8_t>(provisional_ref ? 0x80 : 0x40)};
+  for (int b = 0; b < 4; ++b) {
+    hdr[3 + b] = static_cast<uint8_t>(m >> (8 * b));
+    hdr[7 + b] = static_cast<uint8_t>(n >> (8 * b));
+  }
+  f.Write(hdr, 12);
+  const uint32_t words = PgenReader::WordsFor(n), bytes = (n + 3) / 4;
+  const uint32_t batch = 4096;
+  std::vector<uint64_t> buf(static_cast<size_t>(batch) * words);
+  std::vector<uint32_t> vidx(batch);
+  for (uint32_t v0 = 0; v0 < m; v0 += batch) {
+    const uint32_t cnt = std::min(batch, m - v0);
+    for (uint32_t k = 0; k < cnt; ++k) vidx[k] = v0 + k;
+    if (!ds->reader.GetBlock(vidx.data(), cnt, nullptr, n, buf.data(), words, thread_ct, err)) return 6;
+    for (uint32_t k = 0; k < cnt; ++k) f.Write(buf.data() + static_cast<size_t>(k) * words, bytes);  // trailing entries are already 0
+  }
+  if (!f.Close()) {
+    *err = "File write failure.";
+    return 5;
+  }
+  return 0;
+}
+
 }  // namespace pl2host

@@ -63,4 +63,11 @@ void KeepVariants(Dataset* ds, const std::vector<uint8_t>& keep);
 // the founder-only commands (LD prune, allele frequencies) use.
 int WriteBedFileset(Dataset* ds, const std::string& out_prefix, uint32_t thread_ct, std::string* err, const uint64_t* sample_include = nullptr, uint32_t include_ct = 0);
 
+// --make-pgen (host-only): the current view as <prefix>.pgen in the fixed-width storage mode 0x02 (pgen_spec.tex:137-139:
+// 12-byte header, then ceil(n / 4) bytes of 2-bit hard calls per variant - no compression, every reader accepts it) with
+// <prefix>.pvar (#CHROM POS ID REF ALT [CM], CM only when a nonzero value exists) and <prefix>.psam ([#FID] IID [PAT MAT]
+// SEX [PHENO1], FID / parents only when some value is not 0; the column rules of the reference's writers).
+// provisional_ref: header bits 6-7 (2 = every REF allele provisional, 1 = all trusted).
+int WritePgenFileset(Dataset* ds, const std::string& out_prefix, uint32_t thread_ct, bool provisional_ref, std::string* err);
+
 }  // namespace pl2host

@@ -112,6 +112,7 @@ struct Cmd {
   bool allow_extra_chr = false;  // --allow-extra-chr: unrecognised contig names are kept as autosome-like contigs
   bool nonfounders = false;  // --nonfounders: allele frequencies (and everything derived from them) from all samples, not founders only
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
+  bool make_pgen = false;                 // --make-pgen: the filtered view as fixed-width .pgen + .pvar + .psam (host-only)
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
   std::string king_cutoff_prefix;         // --king-cutoff <prefix of .king.id + triangular .king.bin> <threshold>
   double king_cutoff_prefix_thresh = -1;
@@ -555,6 +556,9 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
       }
     } else if (flag == "--debug-founders-bed") {
       c->debug_founders_bed = c->make_bed = true;
+    } else if (flag == "--make-pgen") {
+      if (!need(0, 0)) return Usage("--make-pgen modifiers are not supported by plink2_b200 (the output is always the uncompressed fixed-width mode).");
+      c->make_pgen = true;
     } else if (flag == "--make-bed") {
       if (!need(0, 0)) return Usage("--make-bed modifiers are not supported by plink2_b200.");
       c->make_bed = true;
@@ -664,7 +668,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     if (named != 1) return Usage("--from-bp/-kb/-mb and --to-bp/-kb/-mb must be used with --chr, and only one chromosome.");
     if (c->filters.from_bp != -1 && c->filters.to_bp != -1 && c->filters.from_bp > c->filters.to_bp) return Usage("--to-bp/-kb/-mb argument is smaller than --from-bp/-kb/-mb argument.");
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->r2_unphased || c->make_bed || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->r2_unphased || c->make_bed || c->make_pgen || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -3983,6 +3987,19 @@ int main(int argc, char** argv) {
     logprintf("--make-bed: %s.bed + %s.bim + %s.fam written.\n", c.out.c_str(), c.out.c_str(), c.out.c_str());
     return 0;
   };
+  auto write_pgen = [&]() -> int {
+    if (ds.reader.nonref_flags_storage() == 3) {
+      logprintf("Error: --make-pgen from a .pgen with per-variant provisional-REF flags is not supported by plink2_b200.\n");
+      return kRetNotYetSupported;
+    }
+    const int wrc = WritePgenFileset(&ds, c.out, EffectiveHostThreads(c.threads), ds.reader.nonref_flags_storage() != 1, &err);
+    if (wrc) {
+      logprintf("Error: %s\n", err.c_str());
+      return wrc;
+    }
+    logprintf("--make-pgen: %s.pgen + %s.pvar + %s.psam written.\n", c.out.c_str(), c.out.c_str(), c.out.c_str());
+    return 0;
+  };
   auto any_removed = [&]() { return std::find(cutoff_removed.begin(), cutoff_removed.end(), 1) != cutoff_removed.end(); };
   auto drop_removed = [&]() {
     std::vector<uint8_t> keep(cutoff_removed.size());
@@ -3991,9 +4008,10 @@ int main(int argc, char** argv) {
     cutoff_removed.clear();
   };
   if (!needs_gpu) {
-    if (c.make_bed) {
+    if (c.make_bed || c.make_pgen) {
       if (any_removed()) drop_removed();
-      rc = write_bed();
+      rc = c.make_bed ? write_bed() : 0;
+      if (!rc && c.make_pgen) rc = write_pgen();
       if (rc) return rc;
     }
     return 0;  // host-only run (the ID lists were written above); these steps need no device in the reference either
@@ -4026,7 +4044,7 @@ int main(int argc, char** argv) {
     rc = RunKing(c, &ds, ctx, &cutoff_removed);
     if (rc) return rc;
   }
-  if (any_removed() && (later_gpu_command || c.make_bed)) {
+  if (any_removed() && (later_gpu_command || c.make_bed || c.make_pgen)) {
     // The commands after a relatedness prune see the surviving samples, but keep the allele frequencies estimated
     // BEFORE it: the reference computes allele_freqs once (plink2.cc:2280-2304) and only narrows sample_include /
     // founder_info afterwards (UpdateSampleSubsets, :2580).  Freeze those frequencies as per-variant overrides
@@ -4046,6 +4064,10 @@ int main(int argc, char** argv) {
   }
   if (c.make_bed) {
     rc = write_bed();
+    if (rc) return rc;
+  }
+  if (c.make_pgen) {
+    rc = write_pgen();
     if (rc) return rc;
   }
   if (!c.score_file.empty()) {

@@ -448,6 +448,32 @@ def test_variant_id_templates(tmp_path):
     assert r.returncode != 0 and "template must contain" in r.stdout + r.stderr
 
 
+def test_make_pgen_writes_a_fileset_every_reader_accepts(tmp_path):
+    """--make-pgen: fixed-width .pgen (storage mode 0x02) + .pvar + .psam of the filtered view.  The text files are the
+    reference's byte for byte (column rules: FID / PAT+MAT / CM / PHENO1 only when informative); the .pgen is read
+    back by this program's own reader - and by the reference binary when it is available in the checkout - and must
+    reproduce the .bed the reference wrote for the same view."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bfile", "x", "--keep", "x_keep1.txt", "x_keep2.txt", "--extract", "x_extract.txt", "--make-pgen", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("pvar", "psam"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "x_mp." + ext), "rb").read(), ext
+    raw = open(out + ".pgen", "rb").read()
+    assert raw[:3] == b"\x6c\x1b\x02" and int.from_bytes(raw[3:7], "little") == 500 and int.from_bytes(raw[7:11], "little") == 80 and raw[11] == 0x80
+    back = str(tmp_path / "back")
+    r = subprocess.run([BIN, "--pfile", out, "--make-bed", "--out", back], capture_output=True, text=True)
+    assert r.returncode == 0 and open(back + ".bed", "rb").read() == open(os.path.join(gd, "x_mp.bed"), "rb").read()
+    ref = os.path.join(ROOT, "oracle", "_ref", "plink2")
+    if os.path.exists(ref):
+        r = subprocess.run([ref, "--pfile", out, "--make-bed", "--out", back + "_ref"], capture_output=True, text=True)
+        assert r.returncode == 0 and open(back + "_ref.bed", "rb").read() == open(os.path.join(gd, "x_mp.bed"), "rb").read()
+    r = subprocess.run([BIN, "--pedmap", "p", "--make-pgen", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("pvar", "psam"):  # CM column (a nonzero centimorgan exists), PAT / MAT columns, NA sex and phenotype
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "p_mp." + ext), "rb").read(), ext
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
