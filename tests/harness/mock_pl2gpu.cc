@@ -171,6 +171,134 @@ int pl2gpu_king_end(Pl2KingJob* job) {
   return 0;
 }
 
+// ---- GRM job (ExpandCenteredVarmaj + CalcGrm, 2.0/plink2_matrix_calc.cc:3839-3886, :4285, :4769-4788): variants kept as
+// codes + REF frequency; values computed on request in plain fp64 loops.  eigen_topk: cyclic Jacobi on the full matrix.
+}  // extern "C"
+struct Pl2GrmJob {
+  uint32_t n, r0, r1;
+  int flags;
+  std::vector<uint8_t> codes;   // [variant][sample]
+  std::vector<double> ref_freq;  // per variant
+  uint64_t variants = 0;
+};
+namespace {
+void GrmMatrix(const Pl2GrmJob* job, std::vector<double>* g, std::vector<double>* obs) {
+  const uint32_t n = job->n;
+  const bool meanimpute = job->flags & 1, cov = job->flags & 2;
+  g->assign(static_cast<size_t>(n) * n, 0.0);
+  obs->assign(static_cast<size_t>(n) * n, 0.0);
+  std::vector<double> z(n);
+  std::vector<uint8_t> nm(n);
+  for (uint64_t v = 0; v < job->variants; ++v) {
+    const uint8_t* c = &job->codes[v * n];
+    const double f = job->ref_freq[v], alt2 = 2.0 * (1.0 - f);
+    const double var = 2.0 * f * (1.0 - f);
+    const double inv_sd = cov ? 1.0 : (var > 0.0 ? 1.0 / sqrt(var) : 0.0);
+    for (uint32_t s = 0; s < n; ++s) {
+      nm[s] = c[s] != 3;
+      z[s] = nm[s] ? (static_cast<double>(c[s]) - alt2) * inv_sd : 0.0;
+      if (!cov && var <= 0.0) z[s] = 0.0;
+    }
+    for (uint32_t j = 0; j < n; ++j)
+      for (uint32_t i = 0; i <= j; ++i) {
+        (*g)[static_cast<size_t>(j) * n + i] += z[j] * z[i];
+        (*obs)[static_cast<size_t>(j) * n + i] += nm[j] && nm[i];
+      }
+  }
+  for (uint32_t j = 0; j < n; ++j)
+    for (uint32_t i = 0; i <= j; ++i) {
+      const double d = meanimpute ? static_cast<double>(job->variants) : (*obs)[static_cast<size_t>(j) * n + i];
+      (*g)[static_cast<size_t>(j) * n + i] /= d;
+    }
+}
+}  // namespace
+extern "C" {
+int pl2gpu_grm_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t row_start, uint32_t row_end, int flags, Pl2GrmJob** job_ptr) {
+  Log("grm_begin device=%d rows=%u\n", ctx->device, row_end - row_start);
+  *job_ptr = new Pl2GrmJob{sample_ct, row_start, row_end, flags, {}, {}, 0};
+  return 0;
+}
+int pl2gpu_grm_add_variants(Pl2GrmJob* job, const void* genovecs, uint64_t stride, uint32_t variant_ct, int, const double* ref_freqs) {
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    uint64_t c[4] = {0, 0, 0, 0};
+    for (uint32_t s = 0; s < job->n; ++s) {
+      const uint32_t g = Code(row, s);
+      ++c[g];
+      job->codes.push_back(static_cast<uint8_t>(g));
+    }
+    const uint64_t tot = 2 * (c[0] + c[1] + c[2]);
+    double f = tot ? static_cast<double>(2 * c[0] + c[1]) * (1.0 / static_cast<double>(tot)) : 0.5;
+    if (ref_freqs && ref_freqs[v] == ref_freqs[v]) f = ref_freqs[v];
+    job->ref_freq.push_back(f);
+  }
+  job->variants += variant_ct;
+  return 0;
+}
+int pl2gpu_grm_get_rows(Pl2GrmJob* job, uint32_t r0, uint32_t r1, double* dst_grm, float* dst_obs, uint64_t row_stride, int) {
+  std::vector<double> g, obs;
+  GrmMatrix(job, &g, &obs);
+  for (uint32_t j = r0; j < r1; ++j)
+    for (uint32_t i = 0; i <= j; ++i) {
+      dst_grm[static_cast<uint64_t>(j - r0) * row_stride + i] = g[static_cast<size_t>(j) * job->n + i];
+      if (dst_obs) dst_obs[static_cast<uint64_t>(j - r0) * row_stride + i] = static_cast<float>(obs[static_cast<size_t>(j) * job->n + i]);
+    }
+  return 0;
+}
+uint64_t pl2gpu_grm_variants_added(Pl2GrmJob* job) { return job->variants; }
+int pl2gpu_grm_eigen_topk(Pl2GrmJob* job, uint32_t pc_ct, double* eigvals_host, double* eigvecs_host) {
+  const uint32_t n = job->n;
+  std::vector<double> a, obs;
+  GrmMatrix(job, &a, &obs);
+  for (uint32_t j = 0; j < n; ++j)
+    for (uint32_t i = 0; i < j; ++i) a[static_cast<size_t>(i) * n + j] = a[static_cast<size_t>(j) * n + i];
+  std::vector<double> vmat(static_cast<size_t>(n) * n, 0.0);
+  for (uint32_t k = 0; k < n; ++k) vmat[static_cast<size_t>(k) * n + k] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0;
+    for (uint32_t p = 0; p < n; ++p)
+      for (uint32_t q = p + 1; q < n; ++q) off += a[static_cast<size_t>(p) * n + q] * a[static_cast<size_t>(p) * n + q];
+    if (off < 1e-26) break;
+    for (uint32_t p = 0; p < n; ++p) {
+      for (uint32_t q = p + 1; q < n; ++q) {
+        const double apq = a[static_cast<size_t>(p) * n + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[static_cast<size_t>(q) * n + q] - a[static_cast<size_t>(p) * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)), cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+        for (uint32_t k = 0; k < n; ++k) {
+          const double akp = a[static_cast<size_t>(k) * n + p], akq = a[static_cast<size_t>(k) * n + q];
+          a[static_cast<size_t>(k) * n + p] = cs * akp - sn * akq;
+          a[static_cast<size_t>(k) * n + q] = sn * akp + cs * akq;
+        }
+        for (uint32_t k = 0; k < n; ++k) {
+          const double apk = a[static_cast<size_t>(p) * n + k], aqk = a[static_cast<size_t>(q) * n + k];
+          a[static_cast<size_t>(p) * n + k] = cs * apk - sn * aqk;
+          a[static_cast<size_t>(q) * n + k] = sn * apk + cs * aqk;
+        }
+        for (uint32_t k = 0; k < n; ++k) {
+          const double vkp = vmat[static_cast<size_t>(k) * n + p], vkq = vmat[static_cast<size_t>(k) * n + q];
+          vmat[static_cast<size_t>(k) * n + p] = cs * vkp - sn * vkq;
+          vmat[static_cast<size_t>(k) * n + q] = sn * vkp + cs * vkq;
+        }
+      }
+    }
+  }
+  std::vector<uint32_t> order(n);
+  for (uint32_t k = 0; k < n; ++k) order[k] = k;
+  for (uint32_t x = 0; x < n; ++x)
+    for (uint32_t y = x + 1; y < n; ++y)
+      if (a[static_cast<size_t>(order[y]) * n + order[y]] > a[static_cast<size_t>(order[x]) * n + order[x]]) std::swap(order[x], order[y]);
+  for (uint32_t pc = 0; pc < pc_ct; ++pc) {
+    eigvals_host[pc] = a[static_cast<size_t>(order[pc]) * n + order[pc]];
+    for (uint32_t s = 0; s < n; ++s) eigvecs_host[static_cast<size_t>(pc) * n + s] = vmat[static_cast<size_t>(s) * n + order[pc]];
+  }
+  return 0;
+}
+int pl2gpu_grm_end(Pl2GrmJob* job) {
+  delete job;
+  return 0;
+}
+
 // pair-decision band on its own (the screening pass of --r2-unphased): flags[v * band + d - 1] = cov^2 > t var1 var2
 // for second = v, first = v - d, exact integer sextuple over samples non-missing in both (plink2_ld.cc:699-723)
 int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, int, uint32_t band, double thresh, uint8_t* flags_host) {

@@ -22,5 +22,6 @@ LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --king-cutoff 0.02 --indep-pairwis
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --not-chr X --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.3 --ld-window-kb 0.1 --out $W/b3 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --nonfounders --freq counts --out $W/b4 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --gpu-memory 4 --make-king-table counts cols=+ibs1,+ibs --make-king bin4 triangle --out $W/b5 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --make-grm-sparse 0.02 --pca 4 --out $W/b6 2>&1 | flt
 LD_PRELOAD="$LT $W/mock_tsan.so" PL2_MOCK_DEVICES=3 $W/tsan --bed a.bed --bim a_chr6.bim --fam a.fam --gpus 3 --threads 6 --indep-pairwise 50 5 0.2 --out $W/t1 2>&1 | flt
 cmp $W/b1.prune.in a_chr6.prune.in && cmp $W/t1.prune.in a_chr6.prune.in && cmp $W/b2.prune.in g_acut.prune.in && echo "sanitizer replay: outputs as expected, no reports above"

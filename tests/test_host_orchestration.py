@@ -190,3 +190,71 @@ def test_extra_contigs_are_diploid_autosome_like_units(mock_so, tmp_path):
     assert open(out + ".kin0", "rb").read() == _gold("x_contigs.kin0.gz")
     r = subprocess.run([BIN] + data[:-1] + ["--make-bed", "--out", out], capture_output=True, text=True, cwd=GD)
     assert r.returncode != 0 and "--allow-extra-chr" in r.stdout
+
+
+def _f32_close(path, gold):
+    import numpy as np
+
+    got = np.fromfile(path, dtype=np.float32)
+    ref = np.frombuffer(_gold(gold), dtype=np.float32)
+    assert got.shape == ref.shape
+    assert np.all(np.abs(got.astype(np.float64) - ref.astype(np.float64)) <= 1.2e-7 * np.abs(ref) + 5e-10)
+
+
+def _text_close(path, gold, rtol=1.2e-5, atol=1e-9):
+    got = open(path).read().split("\n")
+    ref = _gold(gold).decode().split("\n")
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
+        if a != b:
+            ta, tb = a.split("\t"), b.split("\t")
+            assert len(ta) == len(tb)
+            for x, y in zip(ta, tb):
+                assert x == y or abs(float(x) - float(y)) <= rtol * abs(float(y)) + atol, (a, b)
+
+
+def test_grm_driver_and_writers_replayed_on_the_cpu(mock_so, tmp_path):
+    """RunGrm around a stand-in GRM job (plain fp64 loops): every output form of the relationship matrix against the
+    reference's files - .grm.bin / .grm.N.bin / .grm.id, the text list, the sparse list, --make-rel cov bin4 and square
+    text, meanimpute, and --read-freq frequencies reaching the standardisation."""
+    out = str(tmp_path / "o")
+    _run(mock_so, ["--bfile", "a", "--make-grm-bin"], out)
+    _f32_close(out + ".grm.bin", "a_grm.grm.bin")
+    assert open(out + ".grm.N.bin", "rb").read() == _gold("a_grm.grm.N.bin") and open(out + ".grm.id", "rb").read() == _gold("a_grm.grm.id")
+    _run(mock_so, ["--bfile", "a", "--make-grm-list"], out)
+    _text_close(out + ".grm", "a_grml.grm.gz")
+    _run(mock_so, ["--bfile", "a", "--make-grm-sparse", "0.02"], out)
+    got = {tuple(ln.split("\t")[:2]): float(ln.split("\t")[2]) for ln in open(out + ".grm.sp").read().split("\n") if ln}
+    ref = {tuple(ln.split("\t")[:2]): float(ln.split("\t")[2]) for ln in _gold("a_grmsp.grm.sp").decode().split("\n") if ln}
+    assert all(abs(got.get(k, ref.get(k)) - 0.02) < 1e-8 for k in set(got) ^ set(ref))
+    assert all(abs(got[k] - ref[k]) <= 2e-9 + 1.5e-8 * abs(ref[k]) for k in set(got) & set(ref)) and len(ref) == 1380
+    _run(mock_so, ["--bfile", "a", "--make-rel", "cov", "bin4", "triangle"], out)
+    _f32_close(out + ".rel.bin", "a_relcov.rel.bin")
+    _run(mock_so, ["--bfile", "a", "--make-rel", "square"], out)
+    _text_close(out + ".rel", "a_rel.rel.gz")
+    _run(mock_so, ["--bfile", "a", "--make-grm-bin", "meanimpute"], out)
+    _f32_close(out + ".grm.bin", "a_grmmi.grm.bin")
+    _run(mock_so, ["--bfile", "a", "--read-freq", "a_rf.afreq", "--make-grm-bin"], out)
+    _f32_close(out + ".grm.bin", "a_rf.grm.bin")
+
+
+def test_exact_pca_driver_and_prune_chaining_replayed_on_the_cpu(mock_so, tmp_path):
+    """Exact --pca on the stand-in's eigen-solver (eigenvalues + eigenvectors up to sign vs the reference), then the two
+    chained forms checked on the B200 as well: --king-cutoff -> --make-grm-bin and --king-cutoff-table -> --pca, both with
+    the pre-prune allele frequencies."""
+    import numpy as np
+
+    out = str(tmp_path / "o")
+    _run(mock_so, ["--bfile", "a", "--pca", "4"], out)
+    assert np.allclose(np.loadtxt(out + ".eigenval"), np.loadtxt(os.path.join(GD, "a_pca.eigenval")), rtol=2e-5)
+    got = np.loadtxt(out + ".eigenvec", skiprows=1, usecols=(2, 3, 4, 5))
+    want = np.loadtxt(os.path.join(GD, "a_pca.eigenvec"), skiprows=1, usecols=(2, 3, 4, 5))
+    assert np.allclose(got * np.sign((got * want).sum(axis=0)), want, atol=2e-5)
+    _run(mock_so, ["--bfile", "a", "--king-cutoff", "0.02", "--make-grm-bin"], out)
+    _f32_close(out + ".grm.bin", "g_acut.grm.bin")
+    (tmp_path / "in.kin0").write_bytes(_gold("a_kingp.kin0.gz"))
+    _run(mock_so, ["--bfile", "a", "--king-cutoff-table", str(tmp_path / "in.kin0"), "0.02", "--pca", "3"], out)
+    assert np.allclose(np.loadtxt(out + ".eigenval"), np.loadtxt(os.path.join(GD, "g_akct.eigenval")), rtol=2e-5)
+    got = np.loadtxt(out + ".eigenvec", skiprows=1, usecols=(2, 3, 4))
+    want = np.loadtxt(os.path.join(GD, "g_akct.eigenvec"), skiprows=1, usecols=(2, 3, 4))
+    assert got.shape == want.shape == (50, 3) and np.allclose(got * np.sign((got * want).sum(axis=0)), want, atol=2e-5)
