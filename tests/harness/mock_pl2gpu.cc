@@ -299,6 +299,43 @@ int pl2gpu_grm_end(Pl2GrmJob* job) {
   return 0;
 }
 
+// ---- --score accumulation (contract in include/plink2_b200.h): per entry a 4-entry weight table and packed dosages
+}  // extern "C"
+struct Pl2ScoreJob {
+  uint32_t n;
+  std::vector<double> sums;
+  std::vector<uint64_t> dosage;
+  std::vector<uint32_t> missing;
+};
+extern "C" {
+int pl2gpu_score_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, Pl2ScoreJob** job_ptr) {
+  Log("score_begin device=%d n=%u\n", ctx->device, sample_ct);
+  *job_ptr = new Pl2ScoreJob{sample_ct, std::vector<double>(sample_ct, 0.0), std::vector<uint64_t>(sample_ct, 0), std::vector<uint32_t>(sample_ct, 0)};
+  return 0;
+}
+int pl2gpu_score_add_variants(Pl2ScoreJob* job, const void* genovecs, uint64_t stride, uint32_t variant_ct, int, const double* weights4, const uint8_t* named_dosages) {
+  for (uint32_t e = 0; e < variant_ct; ++e) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + e * stride;
+    for (uint32_t s = 0; s < job->n; ++s) {
+      const uint32_t g = Code(row, s);
+      job->sums[s] += weights4[4ull * e + g];
+      if (g == 3) ++job->missing[s];
+      else job->dosage[s] += (named_dosages[e] >> (2 * g)) & 3;
+    }
+  }
+  return 0;
+}
+int pl2gpu_score_get(Pl2ScoreJob* job, double* score_sums, uint64_t* named_dosage_sums, uint32_t* missing_cts) {
+  memcpy(score_sums, job->sums.data(), job->n * sizeof(double));
+  memcpy(named_dosage_sums, job->dosage.data(), job->n * sizeof(uint64_t));
+  memcpy(missing_cts, job->missing.data(), job->n * sizeof(uint32_t));
+  return 0;
+}
+int pl2gpu_score_end(Pl2ScoreJob* job) {
+  delete job;
+  return 0;
+}
+
 // pair-decision band on its own (the screening pass of --r2-unphased): flags[v * band + d - 1] = cov^2 > t var1 var2
 // for second = v, first = v - d, exact integer sextuple over samples non-missing in both (plink2_ld.cc:699-723)
 int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, int, uint32_t band, double thresh, uint8_t* flags_host) {

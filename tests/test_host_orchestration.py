@@ -258,3 +258,27 @@ def test_exact_pca_driver_and_prune_chaining_replayed_on_the_cpu(mock_so, tmp_pa
     got = np.loadtxt(out + ".eigenvec", skiprows=1, usecols=(2, 3, 4))
     want = np.loadtxt(os.path.join(GD, "g_akct.eigenvec"), skiprows=1, usecols=(2, 3, 4))
     assert got.shape == want.shape == (50, 3) and np.allclose(got * np.sign((got * want).sum(axis=0)), want, atol=2e-5)
+
+
+SCORE_CASES = [(("header",), "a_sc.sscore"), (("header", "no-mean-imputation", "cols=+scoresums,+denom"), "a_sc2.sscore"), (("header", "center", "cols=+scoresums"), "a_sc_center.sscore"),
+               (("header", "variance-standardize", "cols=+scoresums"), "a_sc_varstd.sscore"), (("header", "dominant", "list-variants", "cols=+scoresums,+denom"), "a_sc_dominant.sscore"),
+               (("header", "recessive", "cols=+scoresums,+denom"), "a_sc_recessive.sscore")]
+
+
+@pytest.mark.parametrize("flags,gold", SCORE_CASES)
+def test_score_driver_replayed_on_the_cpu(mock_so, tmp_path, flags, gold):
+    """RunScore (file parsing, allele matching, mean-imputation / centering / dominance weight tables, report columns)
+    around a stand-in accumulator: the reference's .sscore reports, integer columns exactly and averages / sums to the
+    printed digits."""
+    out = str(tmp_path / "o")
+    stdout = _run(mock_so, ["--bfile", "a", "--score", "a_score.txt"] + list(flags), out)
+    assert "400 variants processed" in stdout and "7 were skipped due to mismatching allele codes" in stdout
+    _text_close(out + ".sscore", gold, rtol=2e-5, atol=2e-9)
+    if "list-variants" in flags:
+        assert open(out + ".sscore.vars", "rb").read() == _gold("a_sc.sscore.vars")
+
+
+def test_score_after_a_relatedness_prune_uses_frozen_frequencies(mock_so, tmp_path):
+    out = str(tmp_path / "o")
+    _run(mock_so, ["--bfile", "a", "--king-cutoff", "0.02", "--score", "a_score.txt", "header", "cols=+scoresums,+denom"], out)
+    _text_close(out + ".sscore", "g_acut.sscore", rtol=2e-5, atol=2e-9)
