@@ -336,6 +336,77 @@ int pl2gpu_score_end(Pl2ScoreJob* job) {
   return 0;
 }
 
+// ---- --variant-score on a "PCA job": only begin / add_variants / vscore / end are provided (no approx-PCA stand-in)
+}  // extern "C"
+struct Pl2PcaJob {
+  uint32_t n;
+  std::vector<uint8_t> codes;
+  std::vector<double> alt_freq;
+  uint64_t variants = 0;
+};
+struct Pl2KingPairJob {
+  Pl2KingJob king;
+  std::vector<uint32_t> pairs;
+};
+extern "C" {
+int pl2gpu_pca_begin_shard(Pl2GpuCtx* ctx, uint32_t sample_ct, uint32_t, uint32_t, Pl2PcaJob** job_ptr) {
+  Log("pca_begin device=%d n=%u\n", ctx->device, sample_ct);
+  *job_ptr = new Pl2PcaJob{sample_ct, {}, {}, 0};
+  return 0;
+}
+int pl2gpu_pca_add_variants(Pl2PcaJob* job, const void* genovecs, uint64_t stride, uint32_t variant_ct, int, const double* ref_freqs) {
+  for (uint32_t v = 0; v < variant_ct; ++v) {
+    const uint8_t* row = static_cast<const uint8_t*>(genovecs) + v * stride;
+    uint64_t c[4] = {0, 0, 0, 0};
+    for (uint32_t s = 0; s < job->n; ++s) {
+      const uint32_t g = Code(row, s);
+      ++c[g];
+      job->codes.push_back(static_cast<uint8_t>(g));
+    }
+    const uint64_t tot = 2 * (c[0] + c[1] + c[2]);
+    double f = tot ? static_cast<double>(2 * c[0] + c[1]) * (1.0 / static_cast<double>(tot)) : 0.5;
+    if (ref_freqs && ref_freqs[v] == ref_freqs[v]) f = ref_freqs[v];
+    job->alt_freq.push_back(1.0 - f);
+  }
+  job->variants += variant_ct;
+  return 0;
+}
+int pl2gpu_pca_vscore(Pl2PcaJob* job, const double* weights_host, uint32_t cols, double* out_host) {
+  for (uint64_t v = 0; v < job->variants; ++v) {
+    for (uint32_t c = 0; c < cols; ++c) {
+      double acc = 0.0;
+      for (uint32_t s = 0; s < job->n; ++s) {
+        const uint8_t g = job->codes[v * job->n + s];
+        acc += weights_host[static_cast<size_t>(s) * cols + c] * (g == 3 ? 2.0 * job->alt_freq[v] : static_cast<double>(g));
+      }
+      out_host[v * cols + c] = acc;
+    }
+  }
+  return 0;
+}
+int pl2gpu_pca_end(Pl2PcaJob* job) {
+  delete job;
+  return 0;
+}
+// ---- pair-list KING (--king-table-subset, rel-check): counts for the listed pairs {j, i} only
+int pl2gpu_king_pairs_begin(Pl2GpuCtx* ctx, uint32_t sample_ct, const uint32_t* pairs_host, uint64_t pair_ct, Pl2KingPairJob** job_ptr) {
+  Log("king_pairs_begin device=%d pairs=%u\n", ctx->device, static_cast<unsigned>(pair_ct));
+  *job_ptr = new Pl2KingPairJob{Pl2KingJob{sample_ct, 0, sample_ct, {}, 0}, std::vector<uint32_t>(pairs_host, pairs_host + 2 * pair_ct)};
+  return 0;
+}
+int pl2gpu_king_pairs_add_variants(Pl2KingPairJob* job, const void* genovecs, uint64_t stride, uint32_t variant_ct, int src) { return pl2gpu_king_add_variants(&job->king, genovecs, stride, variant_ct, src); }
+int pl2gpu_king_pairs_get_counts(Pl2KingPairJob* job, uint64_t pair_start, uint64_t pair_end, uint32_t* dst, int) {
+  for (uint64_t k = pair_start; k < pair_end; ++k, dst += 5) {
+    const uint32_t a = job->pairs[2 * k], b = job->pairs[2 * k + 1];
+    PairCounts(&job->king, b, a, dst);  // "1" = the first listed sample, "2" = the second (no reordering by index)
+  }
+  return 0;
+}
+int pl2gpu_king_pairs_end(Pl2KingPairJob* job) {
+  delete job;
+  return 0;
+}
+
 // pair-decision band on its own (the screening pass of --r2-unphased): flags[v * band + d - 1] = cov^2 > t var1 var2
 // for second = v, first = v - d, exact integer sextuple over samples non-missing in both (plink2_ld.cc:699-723)
 int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t stride, uint32_t founder_ct, uint32_t variant_ct, int, uint32_t band, double thresh, uint8_t* flags_host) {

@@ -282,3 +282,23 @@ def test_score_after_a_relatedness_prune_uses_frozen_frequencies(mock_so, tmp_pa
     out = str(tmp_path / "o")
     _run(mock_so, ["--bfile", "a", "--king-cutoff", "0.02", "--score", "a_score.txt", "header", "cols=+scoresums,+denom"], out)
     _text_close(out + ".sscore", "g_acut.sscore", rtol=2e-5, atol=2e-9)
+
+
+def test_pair_list_king_and_variant_score_drivers_replayed_on_the_cpu(mock_so, tmp_path):
+    """The remaining device-backed drivers: pair-list KING (--king-table-subset with the reference's own table as the
+    list + threshold, an IID-only list, rel-check's natural-sort pair lists on two fixtures) and --variant-score (weights
+    file parsing, per-variant sums, report columns) - files as the reference wrote them."""
+    out = str(tmp_path / "o")
+    (tmp_path / "in.kin0").write_bytes(_gold("a_kingp.kin0.gz"))
+    _run(mock_so, ["--bfile", "a", "--make-king-table", "counts", "--king-table-subset", str(tmp_path / "in.kin0"), "-0.05"], out)
+    assert open(out + ".kin0", "rb").read() == _gold("a_kingsub.kin0.gz")
+    _run(mock_so, ["--bfile", "a", "--make-king-table", "counts", "cols=+ibs1", "--king-table-subset", "a_sub2.txt"], out)
+    assert open(out + ".kin0", "rb").read() == _gold("a_kingsub2.kin0")
+    _run(mock_so, ["--bfile", "r", "--make-king-table", "rel-check", "counts"], out)
+    assert open(out + ".kin0", "rb").read() == _gold("r_relcheck.kin0")
+    _run(mock_so, ["--bfile", "s", "--make-king-table", "rel-check"], out)
+    assert open(out + ".kin0", "rb").read() == _gold("s_relcheck.kin0.gz")
+    _run(mock_so, ["--bfile", "a", "--variant-score", "a_vscore_weights.txt"], out)
+    _text_close(out + ".vscore", "a_vs.vscore", rtol=2e-5, atol=1e-9)
+    _run(mock_so, ["--bfile", "a", "--variant-score", "a_vscore_weights.txt", "cols=+altfreq"], out)
+    _text_close(out + ".vscore", "a_vs_altfreq.vscore", rtol=2e-5, atol=1e-9)
