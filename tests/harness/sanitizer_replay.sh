@@ -23,5 +23,10 @@ LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --not-chr X --keep x_keep1.txt x_k
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --nonfounders --freq counts --out $W/b4 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --gpu-memory 4 --make-king-table counts cols=+ibs1,+ibs --make-king bin4 triangle --out $W/b5 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --make-grm-sparse 0.02 --pca 4 --out $W/b6 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --king-cutoff 0.02 --score a_score.txt header dominant list-variants cols=+scoresums,+denom --out $W/b7 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --variant-score a_vscore_weights.txt cols=+altfreq zs --out $W/b8 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile s --make-king-table rel-check --out $W/b9 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --make-king-table counts cols=+ibs1 --king-table-subset a_sub2.txt --out $W/b10 2>&1 | flt
+LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --keep x_keep2.txt --mind 0.05 --make-rel square zs --make-grm-list --out $W/b11 2>&1 | flt
 LD_PRELOAD="$LT $W/mock_tsan.so" PL2_MOCK_DEVICES=3 $W/tsan --bed a.bed --bim a_chr6.bim --fam a.fam --gpus 3 --threads 6 --indep-pairwise 50 5 0.2 --out $W/t1 2>&1 | flt
 cmp $W/b1.prune.in a_chr6.prune.in && cmp $W/t1.prune.in a_chr6.prune.in && cmp $W/b2.prune.in g_acut.prune.in && echo "sanitizer replay: outputs as expected, no reports above"
