@@ -25,7 +25,8 @@ struct FilterSpec {
   // thresholds on genotype counts (applied after --read-freq was loaded; plink2.cc:1748, :2338, :2460)
   double mind = 1.0, geno = 1.0, min_maf = 0.0, max_maf = 1.0;
   uint64_t min_mac = 0, max_mac = ~0ull;  // allele counts (the reference's ddosage bounds / 32768)
-  bool any_count_filter() const { return mind < 1.0 || geno < 1.0 || min_maf != 0.0 || max_maf != 1.0 || min_mac || max_mac != ~0ull; }
+  uint32_t min_bp_space = 0;              // --bp-space: applied last (EnforceMinBpSpace, plink2_filter.cc:3904; plink2.cc:2479)
+  bool any_count_filter() const { return mind < 1.0 || geno < 1.0 || min_maf != 0.0 || max_maf != 1.0 || min_mac || max_mac != ~0ull || min_bp_space; }
   bool any() const {
     if (excl_males || excl_females || excl_nosex || founders_only) return true;
     return any_id_filter();

@@ -486,6 +486,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--allow-extra-chr") {
       if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "0"))) return Usage("Invalid --allow-extra-chr argument.");
       c->allow_extra_chr = true;
+    } else if (flag == "--bp-space") {
+      if (!need(1, 1) || !ParseU32(prm[0], &c->filters.min_bp_space) || !c->filters.min_bp_space) return Usage("Invalid --bp-space argument.");
     } else if (flag == "--max-alleles" || flag == "--min-alleles") {
       uint32_t u;
       if (!need(1, 1) || !ParseU32(prm[0], &u) || !u) return Usage(("Invalid " + flag + " argument.").c_str());
@@ -3766,6 +3768,25 @@ int ApplyCountFilters(const Cmd& c, Dataset* ds) {
       return kRetInconsistentInput;
     }
     if (left != m) KeepVariants(ds, keep);
+  }
+  if (f.min_bp_space) {
+    // within a chromosome a variant closer than the given distance to the last KEPT variant is removed
+    const VariantInfo& V = ds->variants;
+    const uint32_t m = V.size();
+    std::vector<uint8_t> keep(m, 1);
+    uint32_t removed = 0, last_bp = 0;
+    for (uint32_t v = 0; v < m; ++v) {
+      if (!v || V.chr_code[v] != V.chr_code[v - 1]) {
+        last_bp = V.bp[v];
+      } else if (V.bp[v] < last_bp + f.min_bp_space) {
+        keep[v] = 0;
+        ++removed;
+      } else {
+        last_bp = V.bp[v];
+      }
+    }
+    logprintf("--bp-space: %u variant%s removed (%u remaining).\n", removed, removed == 1 ? "" : "s", m - removed);
+    if (removed) KeepVariants(ds, keep);
   }
   return 0;
 }

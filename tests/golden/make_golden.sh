@@ -133,6 +133,7 @@ $P --bed x.bed --bim x_contigs.bim --fam x.fam --allow-extra-chr --make-king-tab
 $P --bfile x --keep x_keep1.txt x_keep2.txt --extract x_extract.txt --make-pgen --threads 2 --out $T/mp > /dev/null; cp $T/mp.pvar x_mp.pvar; cp $T/mp.psam x_mp.psam
 $P --bfile x --keep x_keep1.txt x_keep2.txt --extract x_extract.txt --make-bed --threads 2 --out $T/mb > /dev/null; cp $T/mb.bed x_mp.bed
 $P --pedmap p --make-pgen --threads 2 --out $T/pp > /dev/null; cp $T/pp.pvar p_mp.pvar; cp $T/pp.psam p_mp.psam
+$P --bfile x --bp-space 7 --maf 0.05 --chr 1,X,MT --make-bed --threads 2 --out $T/bs > /dev/null; cp $T/bs.bim x_bpspace.bim   # --bp-space runs after the frequency thresholds
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

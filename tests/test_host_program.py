@@ -307,6 +307,7 @@ QC_CASES = [
     (["--pgen", "a_mode10.pgen", "--pvar", "a.pvar", "--psam", "a.psam"], ["--geno", "0.03", "--mind", "0.04", "--maf", "0.2"], "a_qc", ("bed", "bim", "fam")),
     (["--bfile", "a"], ["--read-freq", "a_rf.afreq", "--exclude", "x_exclude.txt", "--maf", "0.3"], "a_rfmaf", ("bim",)),  # thresholds on LOADED frequencies
     (["--bfile", "x"], ["--nonfounders", "--maf", "0.1", "--mac", "30"], "x_nf", ("bim",)),  # frequencies / allele counts over all samples
+    (["--bfile", "x"], ["--bp-space", "7", "--maf", "0.05", "--chr", "1,X,MT"], "x_bpspace", ("bim",)),  # spacing filter applied after the frequency thresholds
 ]
 
 
