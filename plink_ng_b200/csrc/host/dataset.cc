@@ -29,17 +29,42 @@ bool ParseChr(const std::string& tok, uint32_t* code) {
   return true;
 }
 
+namespace {
+bool g_out_chr_prefix = false;
+int g_out_chr_mode = 2;  // 0 numeric (23..26), 1 "M", 2 "MT"
+}  // namespace
+
+bool SetOutputChrStyle(const std::string& mt_code) {
+  std::string t = mt_code;
+  g_out_chr_prefix = t.size() > 3 && t.compare(0, 3, "chr") == 0;
+  if (g_out_chr_prefix) t = t.substr(3);
+  if (t == "26") g_out_chr_mode = 0;
+  else if (t == "M") g_out_chr_mode = 1;
+  else if (t == "MT") g_out_chr_mode = 2;
+  else return false;
+  return true;
+}
+
 std::string ChrNameOut(uint32_t code, const std::string& as_read) {
   if (code > 26) return as_read;  // --allow-extra-chr contig: as written
-  if (code <= 22) return std::to_string(code);
-  if (code == 23) return "X";
-  if (code == 24) return "Y";
-  if (code == 26) return "MT";
+  const std::string prefix = g_out_chr_prefix ? "chr" : "";
+  if (code <= 22 || g_out_chr_mode == 0) {
+    if (code == 25 && g_out_chr_mode == 0) {
+      std::string u = as_read;
+      if (u.size() > 3 && (u[0] == 'c' || u[0] == 'C') && (u[1] == 'h' || u[1] == 'H') && (u[2] == 'r' || u[2] == 'R')) u = u.substr(3);
+      for (auto& ch : u) ch = static_cast<char>(toupper(ch));
+      if (u == "PAR1" || u == "PAR2") return prefix + u;
+    }
+    return prefix + std::to_string(code);
+  }
+  if (code == 23) return prefix + "X";
+  if (code == 24) return prefix + "Y";
+  if (code == 26) return prefix + (g_out_chr_mode == 1 ? "M" : "MT");
   std::string u = as_read;
   if (u.size() > 3 && (u[0] == 'c' || u[0] == 'C') && (u[1] == 'h' || u[1] == 'H') && (u[2] == 'r' || u[2] == 'R')) u = u.substr(3);
   for (auto& ch : u) ch = static_cast<char>(toupper(ch));
-  if (u == "PAR1" || u == "PAR2") return u;
-  return "XY";
+  if (u == "PAR1" || u == "PAR2") return prefix + u;
+  return prefix + "XY";
 }
 
 bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {

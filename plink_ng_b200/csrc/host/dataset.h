@@ -42,6 +42,9 @@ bool ParseChr(const std::string& tok, uint32_t* code);
 // Chromosome as the reference prints it under its default output encoding (kfChrOutputMT; chrtoa / ChrNameStd,
 // 2.0/plink2_common.cc:2150-2227): bare number for autosomes, X / Y / XY / MT, PAR1 / PAR2 kept.
 std::string ChrNameOut(uint32_t code, const std::string& as_read);
+// --output-chr <26 | M | MT | chr26 | chrM | chrMT>: the mitochondrial spelling names the scheme (numeric 23-26 vs X / Y /
+// XY / M[T], optional chr prefix); extra contigs are never touched.  Returns false for an unknown scheme.
+bool SetOutputChrStyle(const std::string& mt_code);
 bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err);
 // allow_extra_chr (--allow-extra-chr): a name outside the human set becomes its own diploid, autosome-like contig with a
 // code >= 27 (one per distinct name, in order of appearance), printed as written - the reference's treatment of

@@ -486,6 +486,8 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     } else if (flag == "--allow-extra-chr") {
       if (!need(0, 1) || (nparam == 1 && strcmp(prm[0], "0"))) return Usage("Invalid --allow-extra-chr argument.");
       c->allow_extra_chr = true;
+    } else if (flag == "--output-chr") {
+      if (!need(1, 1) || !SetOutputChrStyle(prm[0])) return Usage("Invalid --output-chr argument (26, M, MT, chr26, chrM or chrMT).");
     } else if (flag == "--bp-space") {
       if (!need(1, 1) || !ParseU32(prm[0], &c->filters.min_bp_space) || !c->filters.min_bp_space) return Usage("Invalid --bp-space argument.");
     } else if (flag == "--max-alleles" || flag == "--min-alleles") {

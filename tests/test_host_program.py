@@ -475,6 +475,26 @@ def test_make_pgen_writes_a_fileset_every_reader_accepts(tmp_path):
         assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "p_mp." + ext), "rb").read(), ext
 
 
+def test_output_chr_styles(tmp_path):
+    """--output-chr: 26 / M / MT with or without the chr prefix, for every file that prints a chromosome (here .bim and,
+    through the '@' of an ID template, the IDs); extra contigs are left as written.  Spellings as the reference prints
+    them for set X (1, X, Y, XY, MT)."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    want = {"26": ["1", "23", "24", "25", "26"], "M": ["1", "X", "Y", "XY", "M"], "chrMT": ["chr1", "chrX", "chrY", "chrXY", "chrMT"], "chr26": ["chr1", "chr23", "chr24", "chr25", "chr26"]}
+    for code, names in want.items():
+        r = subprocess.run([BIN, "--bfile", "x", "--output-chr", code, "--set-all-var-ids", "@:#", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+        assert r.returncode == 0, r.stdout + r.stderr
+        rows = [ln.split("\t") for ln in open(out + ".bim")]
+        seen = list(dict.fromkeys(r_[0] for r_ in rows))
+        assert seen == names
+        assert all(r_[1] == r_[0] + ":" + r_[3] for r_ in rows)
+    r = subprocess.run([BIN, "--bed", "x.bed", "--bim", "x_contigs.bim", "--fam", "x.fam", "--allow-extra-chr", "--output-chr", "chrM", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0 and list(dict.fromkeys(ln.split("\t")[0] for ln in open(out + ".bim"))) == ["chr1", "chrX", "chrY", "chrUn_KI270", "GL000.1", "chrM"]
+    r = subprocess.run([BIN, "--bfile", "x", "--output-chr", "0M", "--make-bed", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode != 0
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
