@@ -141,6 +141,7 @@ bool LoadSamples(const std::string& path, SampleInfo* out, std::string* err) {
 
 bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err, bool allow_extra_chr) {
   std::vector<std::string> extra_names;
+  std::vector<uint8_t> seen_chr;
   std::vector<std::string> lines;
   if (!ReadLines(path, &lines, err)) return false;
   size_t li = 0;
@@ -199,6 +200,16 @@ bool LoadVariants(const std::string& path, VariantInfo* out, std::string* err, b
       *err = "Invalid chromosome code '" + t[col_chr] + "' on line " + std::to_string(li + 1) + " of " + path + " (use --allow-extra-chr to keep contigs outside the human chromosome set).";
       return false;
     }
+    // every chromosome must be one contiguous block (the reference: "has a split chromosome", LoadPvar) - the
+    // per-chromosome drivers (LD prune, r^2 tables, frequency passes) rely on it
+    if (!out->chr_code.empty() && code != out->chr_code.back()) {
+      if (code < seen_chr.size() && seen_chr[code]) {
+        *err = path + " has a split chromosome ('" + t[col_chr] + "' on line " + std::to_string(li + 1) + " after other chromosomes); sort the variants first (plink2 --make-pgen --sort-vars).";
+        return false;
+      }
+    }
+    if (code >= seen_chr.size()) seen_chr.resize(code + 1, 0);
+    seen_chr[code] = 1;
     out->chr_code.push_back(code);
     out->bp.push_back(static_cast<uint32_t>(strtoul(t[cpos].c_str(), nullptr, 10)));
     out->id.push_back(t[col_id]);

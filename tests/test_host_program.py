@@ -495,6 +495,17 @@ def test_output_chr_styles(tmp_path):
     assert r.returncode != 0
 
 
+def test_split_chromosome_is_refused(tmp_path):
+    """A chromosome that reappears after another one is an input error in the reference ("has a split chromosome") and
+    would silently become two LD-prune units here, so it is refused at load."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    rows = open(os.path.join(gd, "a.bim")).read().split("\n")
+    rows[10] = "2" + rows[10][1:]
+    (tmp_path / "split.bim").write_text("\n".join(rows))
+    r = subprocess.run([BIN, "--bed", os.path.join(gd, "a.bed"), "--bim", str(tmp_path / "split.bim"), "--fam", os.path.join(gd, "a.fam"), "--make-bed", "--out", str(tmp_path / "o")], capture_output=True, text=True)
+    assert r.returncode != 0 and "split chromosome" in r.stdout
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
