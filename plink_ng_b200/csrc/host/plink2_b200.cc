@@ -111,6 +111,7 @@ struct Cmd {
   bool var_id_all = false;
   bool allow_extra_chr = false;  // --allow-extra-chr: unrecognised contig names are kept as autosome-like contigs
   bool nonfounders = false;  // --nonfounders: allele frequencies (and everything derived from them) from all samples, not founders only
+  bool missing_report = false, missing_sample = true, missing_variant = true, missing_zs = false;  // --missing ['sample-only' | 'variant-only'] ['zs']
   bool write_snplist = false, write_samples = false;  // --write-snplist / --write-samples: the IDs that survived the filters
   bool make_pgen = false;                 // --make-pgen: the filtered view as fixed-width .pgen + .pvar + .psam (host-only)
   bool debug_founders_bed = false;        // --debug-founders-bed: .bed of the view's founders only (test hook for subset-of-view decoding)
@@ -515,6 +516,16 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
         if (dxx < 0) return Usage("Negative --to-bp/-kb/-mb argument.");
         c->filters.to_bp = dxx >= 2147483646.0 ? 0x7ffffffe : static_cast<int32_t>(dxx * (1 + eps));
       }
+    } else if (flag == "--missing") {
+      for (int k = 0; k < nparam; ++k) {
+        const std::string m = prm[k];
+        if (m == "zs") c->missing_zs = true;
+        else if (m == "sample-only") c->missing_variant = false;
+        else if (m == "variant-only") c->missing_sample = false;
+        else return Usage(("--missing modifier '" + m + "' is not supported by plink2_b200 (supported: sample-only, variant-only, zs).").c_str());
+      }
+      if (!c->missing_sample && !c->missing_variant) return Usage("--missing 'sample-only' and 'variant-only' cannot be used together.");
+      c->missing_report = true;
     } else if (flag == "--write-snplist" || flag == "--write-samples") {
       if (!need(0, 0)) return Usage((flag + " modifiers are not supported by plink2_b200.").c_str());
       (flag == "--write-snplist" ? c->write_snplist : c->write_samples) = true;
@@ -672,7 +683,7 @@ int ParseArgs(int argc, char** argv, Cmd* c) {
     if (named != 1) return Usage("--from-bp/-kb/-mb and --to-bp/-kb/-mb must be used with --chr, and only one chromosome.");
     if (c->filters.from_bp != -1 && c->filters.to_bp != -1 && c->filters.from_bp > c->filters.to_bp) return Usage("--to-bp/-kb/-mb argument is smaller than --from-bp/-kb/-mb argument.");
   }
-  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->r2_unphased || c->make_bed || c->make_pgen || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
+  if (!(c->make_king || c->make_king_table || c->king_cutoff >= 0 || c->make_grm_bin || c->make_grm_list || c->make_grm_sparse || c->make_rel || c->pca || c->indep_pairwise || c->freq || c->r2_unphased || c->make_bed || c->make_pgen || c->missing_report || c->write_snplist || c->write_samples || !c->king_cutoff_table.empty() || !c->king_cutoff_prefix.empty() || !c->score_file.empty() || !c->vscore_file.empty())) return Usage("No command given.");
   return 0;
 }
 
@@ -3662,6 +3673,70 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   return 0;
 }
 
+// --missing (WriteMissingnessReports, 2.0/plink2_misc.cc): .smiss / .vmiss from one host counting pass.  Written where the
+// reference writes them: after the sample filters (incl. --mind), BEFORE the variant thresholds (--geno, --maf, ...).
+int WriteMissingReports(const Cmd& c, Dataset* ds) {
+  int rc;
+  std::string err;
+  // --missing (WriteMissingnessReports, 2.0/plink2_misc.cc): .smiss / .vmiss from one host counting pass over what the
+  // filters left.  chrY calls are counted for males only (OBS_CT of a chrY variant = male count; a non-male's OBS_CT
+  // excludes the chrY variants).  PHENOx columns say whether that phenotype is missing (Y) or not (N).
+  VariantGenoCounts vc;
+  std::vector<uint32_t> smiss;
+  uint32_t y_ct = 0;
+  rc = CountGenotypes(ds, EffectiveHostThreads(c.threads), &vc, &smiss, &y_ct, &err);
+  if (rc) {
+    logprintf("Error: %s\n", err.c_str());
+    return rc;
+  }
+  const SampleInfo& S = ds->samples;
+  const VariantInfo& V = ds->variants;
+  const uint32_t n = S.size(), m = V.size();
+  uint32_t male_ct = 0;
+  for (uint8_t sx : S.sex) male_ct += sx == 1;
+  char num[40];
+  if (c.missing_sample) {
+    std::vector<PhenoOut> phenos;
+    for (size_t p = 0; p < S.pheno_names.size(); ++p) {
+      PhenoOut po;
+      if (TypePheno(S.pheno_names[p], S.pheno_tokens[p], &po)) phenos.push_back(std::move(po));
+    }
+    const std::string name = c.out + (c.missing_zs ? ".smiss.zst" : ".smiss");
+    OutFile f;
+    if (!f.Open(name, c.missing_zs)) return kRetOpenFail;
+    std::string h = std::string("#") + (S.fid_present ? "FID\t" : "") + "IID" + (S.sid_present ? "\tSID" : "");
+    for (const PhenoOut& po : phenos) h += "\t" + po.name;
+    h += "\tMISSING_CT\tOBS_CT\tF_MISS\n";
+    f.Puts(h.c_str());
+    for (uint32_t k = 0; k < n; ++k) {
+      std::string ln = (S.fid_present ? S.fid[k] + "\t" : std::string()) + S.iid[k] + (S.sid_present ? "\t" + S.sid[k] : std::string());
+      for (const PhenoOut& po : phenos) ln += (po.text[k] == "NA" || po.text[k] == "NONE") ? "\tY" : "\tN";
+      const uint32_t obs = m - (S.sex[k] == 1 ? 0 : y_ct);
+      *dtoa_g(obs ? static_cast<double>(smiss[k]) / static_cast<double>(obs) : std::numeric_limits<double>::quiet_NaN(), num) = '\0';
+      ln += "\t" + std::to_string(smiss[k]) + "\t" + std::to_string(obs) + "\t" + num + "\n";
+      f.Puts(ln.c_str());
+    }
+    if (!f.Close()) return kRetWriteFail;
+    logprintf("--missing: Sample missing data report written to %s .\n", name.c_str());
+  }
+  if (c.missing_variant) {
+    const std::string name = c.out + (c.missing_zs ? ".vmiss.zst" : ".vmiss");
+    OutFile f;
+    if (!f.Open(name, c.missing_zs)) return kRetOpenFail;
+    f.Puts("#CHROM\tID\tMISSING_CT\tOBS_CT\tF_MISS\n");
+    for (uint32_t v = 0; v < m; ++v) {
+      const bool is_y = V.chr_code[v] == 24;
+      const uint32_t miss = is_y ? vc.male[4ull * v + 3] : vc.all[4ull * v + 3], obs = is_y ? male_ct : n;
+      *dtoa_g(obs ? static_cast<double>(miss) / static_cast<double>(obs) : std::numeric_limits<double>::quiet_NaN(), num) = '\0';
+      const std::string ln = ChrNameOut(V.chr_code[v], V.chr_name[v]) + "\t" + V.id[v] + "\t" + std::to_string(miss) + "\t" + std::to_string(obs) + "\t" + num + "\n";
+      f.Puts(ln.c_str());
+    }
+    if (!f.Close()) return kRetWriteFail;
+    logprintf("--missing: Variant missing data report written to %s .\n", name.c_str());
+  }
+  return 0;
+}
+
 // --mind, --geno, --maf / --max-maf / --mac / --max-mac on hard calls: one host counting pass each for the sample and
 // the variant thresholds (MindFilter plink2_filter.cc:3329, EnforceGenoThresh :3498, EnforceFreqConstraints :3791).
 // chrY: missingness over males only; frequencies are the founder frequencies --freq reports (or --read-freq's).
@@ -3701,6 +3776,10 @@ int ApplyCountFilters(const Cmd& c, Dataset* ds) {
       }
       KeepSamples(ds, keep);
     }
+  }
+  if (c.missing_report) {
+    const int mrc = WriteMissingReports(c, ds);
+    if (mrc) return mrc;
   }
   if (f.geno < 1.0 || f.min_maf != 0.0 || f.max_maf != 1.0 || f.min_mac || f.max_mac != ~0ull) {
     VariantGenoCounts vc;
@@ -3932,7 +4011,7 @@ int main(int argc, char** argv) {
     rc = LoadReadFreq(c, &ds);
     if (rc) return rc;
   }
-  if (c.filters.any_count_filter()) {
+  if (c.filters.any_count_filter() || c.missing_report) {
     rc = ApplyCountFilters(c, &ds);
     if (rc) return rc;
   }

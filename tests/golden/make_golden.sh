@@ -134,6 +134,8 @@ $P --bfile x --keep x_keep1.txt x_keep2.txt --extract x_extract.txt --make-pgen 
 $P --bfile x --keep x_keep1.txt x_keep2.txt --extract x_extract.txt --make-bed --threads 2 --out $T/mb > /dev/null; cp $T/mb.bed x_mp.bed
 $P --pedmap p --make-pgen --threads 2 --out $T/pp > /dev/null; cp $T/pp.pvar p_mp.pvar; cp $T/pp.psam p_mp.psam
 $P --bfile x --bp-space 7 --maf 0.05 --chr 1,X,MT --make-bed --threads 2 --out $T/bs > /dev/null; cp $T/bs.bim x_bpspace.bim   # --bp-space runs after the frequency thresholds
+# --missing: written after the sample filters (incl. --mind) and before the variant thresholds
+$P --bfile x --keep x_keep1.txt x_keep2.txt --mind 0.05 --geno 0.05 --missing --threads 2 --out $T/ms > /dev/null; cp $T/ms.smiss x_miss.smiss; cp $T/ms.vmiss x_miss.vmiss
 # relatedness prune from a table, then --make-bed on the survivors
 $P --bfile a --king-cutoff-table $T/in.kin0 0.02 --make-bed --threads 2 --out $T/a_kctb > /dev/null
 cp $T/a_kctb.fam a_kctb.fam; cp $T/a_kctb.bed a_kctb.bed

@@ -506,6 +506,19 @@ def test_split_chromosome_is_refused(tmp_path):
     assert r.returncode != 0 and "split chromosome" in r.stdout
 
 
+def test_missing_reports(tmp_path):
+    """--missing: .smiss / .vmiss as the reference writes them - for the samples the filters (incl. --mind) left, but
+    over the variants BEFORE --geno; chrY calls counted for males only; PHENO1 column = phenotype missing Y/N."""
+    gd = os.path.join(ROOT, "tests", "golden")
+    out = str(tmp_path / "o")
+    r = subprocess.run([BIN, "--bfile", "x", "--keep", "x_keep1.txt", "x_keep2.txt", "--mind", "0.05", "--geno", "0.05", "--missing", "--out", out], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0, r.stdout + r.stderr
+    for ext in ("smiss", "vmiss"):
+        assert open(out + "." + ext, "rb").read() == open(os.path.join(gd, "x_miss." + ext), "rb").read(), ext
+    r = subprocess.run([BIN, "--bfile", "x", "--missing", "variant-only", "zs", "--out", out + "2"], capture_output=True, text=True, cwd=gd)
+    assert r.returncode == 0 and os.path.exists(out + "2.vmiss.zst") and not os.path.exists(out + "2.smiss.zst")
+
+
 def test_founder_subset_of_a_filtered_view(tmp_path):
     """LD prune and the allele-frequency pass decode only the founders of whatever the filters left: a sample_include
     bitset over the VIEW's samples, composed with the view's own raw-sample bitset inside the reader.  The hidden
