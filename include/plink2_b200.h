@@ -216,7 +216,9 @@ int pl2gpu_geno_counts(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_st
  * SumSsqWords / SumSsqNmWords, 2.0/plink2_ld.cc:699-723, :235, :317, :578) and the r^2 test
  * (:1085-1090) for every pair that can share a window.  flags_host[v * band + (d - 1)], 1 <= d <= band,
  * is 1 iff for second = v, first = v - d:  cov12^2 > prune_ld_thresh * var1 * var2  (exact int64
- * sextuple -> fp64, unfused multiplies).  genovecs: founders only, PgrGet layout. ---- */
+ * sextuple -> fp64, unfused multiplies).  genovecs: founders only, PgrGet layout.  Besides the LD prune, the same
+ * call is the screening pass of `--r2-unphased` tables (threshold set a hair below --ld-window-r2; the few flagged
+ * pairs are then finished on the host with ComputeR2's arithmetic, 2.0/plink2_ld.cc:6654-6682). ---- */
 int pl2gpu_ld_band_flags(Pl2GpuCtx* ctx, const void* genovecs, uint64_t variant_stride_bytes, uint32_t founder_ct, uint32_t variant_ct, int src_is_device, uint32_t band, double prune_ld_thresh, uint8_t* flags_host);
 
 /* ---- function face of LdPrune -> IndepPairwise (2.0/plink2_ld.h:160, 2.0/plink2_ld.cc:2530, :1116)
