@@ -3521,7 +3521,7 @@ int DebugHooks(int argc, char** argv) {
 // (pl2gpu_ld_band_flags: cov^2 > t var1 var2 on the exact integer sextuple, t a hair below the report threshold, so
 // the flagged set is a superset); the HOST recomputes the sextuple of the few flagged pairs from bit planes of the
 // block it already holds and applies the reference's own arithmetic (int64 -> double, cov^2 / (var0 var1), >= threshold).
-// chrX uses a sex-aware statistic in the reference (ComputeXR2) and is refused here.
+// chrX pairs use the reference's sex-aware statistic (ComputeXR2) and are evaluated on the host without a device screen.
 int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const SampleInfo& S = ds->samples;
   const VariantInfo& V = ds->variants;
@@ -3532,18 +3532,15 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     logprintf("Error: --r2-unphased needs a positive --ld-window-r2 in plink2_b200 (the device screens pairs against it).\n");
     return kRetNotYetSupported;
   }
-  for (uint32_t v = 0; v < m; ++v) {
-    if (V.chr_code[v] == 23) {
-      logprintf("Error: --r2-unphased on chrX (sex-aware statistic) is not supported by plink2_b200; add --not-chr X.\n");
-      return kRetNotYetSupported;
-    }
-  }
   // founders; on chrY the reference sets female founders to missing (InterleavedSetMissing, plink2_ld.cc:11845), which
   // for a statistic over samples non-missing in both variants is the same as leaving them out
   uint32_t all_founder_ct = 0, y_founder_ct = 0;
   std::vector<uint64_t> inc_all((n + 63) / 64, 0), inc_y((n + 63) / 64, 0);
+  std::vector<uint64_t> male_plane;  // one bit per founder (founder order): male
   for (uint32_t k = 0; k < n; ++k) {
     if (S.is_founder[k]) {
+      if ((all_founder_ct & 63) == 0) male_plane.push_back(0);
+      if (S.sex[k] == 1) male_plane.back() |= 1ull << (all_founder_ct & 63);
       inc_all[k / 64] |= 1ull << (k % 64);
       ++all_founder_ct;
       if (S.sex[k] != 2) {
@@ -3570,6 +3567,10 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
     while (e < m && V.chr_code[e] == V.chr_code[s0]) ++e;
     const uint32_t len = e - s0;
     const bool is_y = V.chr_code[s0] == 24;
+    // chrX: the reference's sex-aware statistic (ComputeXR2, plink2_ld.cc:7122-7187: every sum taken over all founders
+    // minus half of the same sum over the male founders, genotypes counted as NON-MAJOR alleles).  The unweighted device
+    // screen is not a superset for it, so every pair of the window is evaluated on the host for this chromosome.
+    const bool is_x = V.chr_code[s0] == 23;
     const uint32_t founder_ct = is_y ? y_founder_ct : all_founder_ct;
     const std::vector<uint64_t>& inc = is_y ? inc_y : inc_all;
     const uint32_t words = PgenReader::WordsFor(founder_ct);
@@ -3599,8 +3600,8 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
           logprintf("Error: %s\n", err.empty() ? "short read" : err.c_str());
           return kRetMalformedInput;
         }
-        std::vector<uint8_t> flags(static_cast<uint64_t>(len) * band);
-        if (pl2gpu_ld_band_flags(ctx, bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, len, 0, band, min_r2 * (1 - 1e-9), flags.data())) return GpuFail("pl2gpu_ld_band_flags");
+        std::vector<uint8_t> flags(is_x ? 0 : static_cast<uint64_t>(len) * band);
+        if (!is_x && pl2gpu_ld_band_flags(ctx, bs.buf, static_cast<uint64_t>(words) * 8, founder_ct, len, 0, band, min_r2 * (1 - 1e-9), flags.data())) return GpuFail("pl2gpu_ld_band_flags");
         // bit planes of the block: het / hom-ALT / non-missing, one bit per founder
         std::vector<uint64_t> p_one(static_cast<uint64_t>(len) * pw, 0), p_two(static_cast<uint64_t>(len) * pw, 0), p_nm(static_cast<uint64_t>(len) * pw, 0);
         for (uint32_t k = 0; k < len; ++k) {
@@ -3616,10 +3617,33 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
             p_two[static_cast<uint64_t>(k) * pw + (w >> 1)] |= two << sh;
             p_nm[static_cast<uint64_t>(k) * pw + (w >> 1)] |= nm << sh;
           }
+          if (is_x) {
+            // count NON-MAJOR alleles: when ALT is the major allele (founder REF frequency below 1/2, chrX accounting of
+            // --freq, or the loaded / frozen value) hom-REF becomes the "two" class
+            uint64_t n1 = 0, n2 = 0, m1 = 0, m2 = 0, nmc = 0, mnm = 0;
+            for (uint32_t w = 0; w < pw; ++w) {
+              const uint64_t o = p_one[static_cast<uint64_t>(k) * pw + w], t2 = p_two[static_cast<uint64_t>(k) * pw + w], nm = p_nm[static_cast<uint64_t>(k) * pw + w], ml = male_plane[w];
+              n1 += __builtin_popcountll(o);
+              n2 += __builtin_popcountll(t2);
+              nmc += __builtin_popcountll(nm);
+              m1 += __builtin_popcountll(o & ml);
+              m2 += __builtin_popcountll(t2 & ml);
+              mnm += __builtin_popcountll(nm & ml);
+            }
+            const uint64_t alt1 = 4 * n2 + 2 * n1 - 2 * m2 - m1, wobs = (2 * nmc - mnm) * 2;  // = (2 (F - n3) - males + m3) * 2
+            double ref_freq = wobs ? static_cast<double>(wobs - alt1) * (1.0 / static_cast<double>(wobs)) : 0.5;
+            if (!ds->read_ref_freq.empty() && ds->read_ref_freq[s0 + k] == ds->read_ref_freq[s0 + k]) ref_freq = ds->read_ref_freq[s0 + k];
+            if (ref_freq < 0.5) {
+              for (uint32_t w = 0; w < pw; ++w) {
+                uint64_t& t2 = p_two[static_cast<uint64_t>(k) * pw + w];
+                t2 = p_nm[static_cast<uint64_t>(k) * pw + w] & ~p_one[static_cast<uint64_t>(k) * pw + w] & ~t2;
+              }
+            }
+          }
         }
         for (uint32_t a = 0; a < len; ++a) {
           for (uint32_t b = a + 1; b < win_end[a]; ++b) {
-            if (!flags[static_cast<uint64_t>(b) * band + (b - a - 1)]) continue;
+            if (!is_x && !flags[static_cast<uint64_t>(b) * band + (b - a - 1)]) continue;
             ++flagged_total;
             const uint64_t *o0 = &p_one[static_cast<uint64_t>(a) * pw], *t0 = &p_two[static_cast<uint64_t>(a) * pw], *n0 = &p_nm[static_cast<uint64_t>(a) * pw];
             const uint64_t *o1 = &p_one[static_cast<uint64_t>(b) * pw], *t1 = &p_two[static_cast<uint64_t>(b) * pw], *n1 = &p_nm[static_cast<uint64_t>(b) * pw];
@@ -3635,11 +3659,33 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
               dot += __builtin_popcountll(o0[w] & o1[w]) + 2 * (__builtin_popcountll(o0[w] & t1[w]) + __builtin_popcountll(t0[w] & o1[w])) + 4 * __builtin_popcountll(t0[w] & t1[w]);
             }
             if (!obs) continue;
-            const int64_t var0 = ssq0 * obs - sum0 * sum0, var1 = ssq1 * obs - sum1 * sum1;
-            const double variance_prod = static_cast<double>(var0) * static_cast<double>(var1);
-            if (variance_prod == 0.0) continue;
-            const double cov01 = static_cast<double>(dot * obs - sum0 * sum1);
-            const double r2 = cov01 * cov01 / variance_prod;
+            double r2;
+            if (is_x) {
+              int64_t mobs = 0, msum0 = 0, msum1 = 0, mssq0 = 0, mssq1 = 0, mdot = 0;
+              for (uint32_t w = 0; w < pw; ++w) {
+                const uint64_t ml = male_plane[w], valid = n0[w] & n1[w] & ml;
+                const int64_t a1 = __builtin_popcountll(o0[w] & valid), a2 = __builtin_popcountll(t0[w] & valid), b1 = __builtin_popcountll(o1[w] & valid), b2 = __builtin_popcountll(t1[w] & valid);
+                mobs += __builtin_popcountll(valid);
+                msum0 += a1 + 2 * a2;
+                mssq0 += a1 + 4 * a2;
+                msum1 += b1 + 2 * b2;
+                mssq1 += b1 + 4 * b2;
+                mdot += __builtin_popcountll(o0[w] & o1[w] & ml) + 2 * (__builtin_popcountll(o0[w] & t1[w] & ml) + __builtin_popcountll(t0[w] & o1[w] & ml)) + 4 * __builtin_popcountll(t0[w] & t1[w] & ml);
+              }
+              const double dw = 0.5;  // male_downwt for two chrX variants
+              const double wobs = std::fma(-dw, static_cast<double>(mobs), static_cast<double>(obs)), wn0 = std::fma(-dw, static_cast<double>(msum0), static_cast<double>(sum0)), wn1 = std::fma(-dw, static_cast<double>(msum1), static_cast<double>(sum1));
+              const double ws0 = std::fma(-dw, static_cast<double>(mssq0), static_cast<double>(ssq0)), ws1 = std::fma(-dw, static_cast<double>(mssq1), static_cast<double>(ssq1)), wd = std::fma(-dw, static_cast<double>(mdot), static_cast<double>(dot));
+              const double variance0 = std::fma(ws0, wobs, -wn0 * wn0), variance1 = std::fma(ws1, wobs, -wn1 * wn1);
+              if (variance0 <= 0.0 || variance1 <= 0.0) continue;
+              const double cov01 = std::fma(wd, wobs, -wn0 * wn1);
+              r2 = std::min(1.0, cov01 * cov01 / (variance0 * variance1));
+            } else {
+              const int64_t var0 = ssq0 * obs - sum0 * sum0, var1 = ssq1 * obs - sum1 * sum1;
+              const double variance_prod = static_cast<double>(var0) * static_cast<double>(var1);
+              if (variance_prod == 0.0) continue;
+              const double cov01 = static_cast<double>(dot * obs - sum0 * sum1);
+              r2 = cov01 * cov01 / variance_prod;
+            }
             if (!(r2 >= min_r2)) continue;
             const uint32_t va = s0 + a, vb = s0 + b;
             const std::string chr = ChrNameOut(V.chr_code[va], V.chr_name[va]);
@@ -4015,7 +4061,7 @@ int main(int argc, char** argv) {
     rc = ApplyCountFilters(c, &ds);
     if (rc) return rc;
   }
-  if (c.nonfounders && (c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty())) {
+  if (c.nonfounders && (c.r2_unphased || c.make_grm_bin || c.make_grm_list || c.make_grm_sparse || c.make_rel || c.pca || c.indep_pairwise || !c.score_file.empty() || !c.vscore_file.empty())) {
     // --nonfounders: allele frequencies from every sample (plink2.cc:2301).  One host counting pass, frozen as per-variant
     // overrides (the --read-freq mechanism) so that every later command - whose own founder-only estimate would differ -
     // uses them; entries loaded with --read-freq keep precedence.

@@ -160,6 +160,9 @@ $P --bfile a --remove x_remove.txt --exclude x_exclude.txt --indep-pairwise 50 5
 $P --bfile a --r2-unphased --threads 2 --out $T/r1 > /dev/null; gzip -9 -n -c $T/r1.vcor > a_r2.vcor.gz
 $P --bfile a --r2-unphased --ld-window 7 --ld-window-r2 0.5 --threads 2 --out $T/r2 > /dev/null; gzip -9 -n -c $T/r2.vcor > a_r2w.vcor.gz
 $P --bfile x --not-chr X --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.3 --ld-window-kb 0.1 --threads 2 --out $T/r3 > /dev/null; gzip -9 -n -c $T/r3.vcor > x_r2.vcor.gz
+# chrX r^2 (male-downweighted statistic, non-major-allele coding): set X under --keep with every chromosome, and --nonfounders on X + Y
+$P --bfile x --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.1 --ld-window-kb 0.05 --threads 2 --out $T/r4 > /dev/null; gzip -9 -n -c $T/r4.vcor > x_r2x.vcor.gz
+$P --bfile x --nonfounders --r2-unphased --ld-window-r2 0.1 --chr X,Y --threads 2 --out $T/r5 > /dev/null; gzip -9 -n -c $T/r5.vcor > x_r2nf.vcor.gz
 # --read-freq: a perturbed / partial / allele-swapped copy of a.afreq (make_read_freq_set.py)
 python make_read_freq_set.py a.afreq a_rf.afreq
 $P --bfile a --read-freq a_rf.afreq --make-grm-bin --threads 2 --out $T/a_rf > /dev/null
