@@ -3641,10 +3641,13 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
             }
           }
         }
-        for (uint32_t a = 0; a < len; ++a) {
+        // rows are independent: host threads each take rows a = t, t + T, ... of a block of rows and write their lines to
+        // per-row strings, which are emitted in row order (the table order of the reference)
+        auto process_row = [&](uint32_t a, std::string* out_text, uint64_t* flagged_ct, uint64_t* reported_ct) {
+          char line[64];
           for (uint32_t b = a + 1; b < win_end[a]; ++b) {
             if (!is_x && !flags[static_cast<uint64_t>(b) * band + (b - a - 1)]) continue;
-            ++flagged_total;
+            ++*flagged_ct;
             const uint64_t *o0 = &p_one[static_cast<uint64_t>(a) * pw], *t0 = &p_two[static_cast<uint64_t>(a) * pw], *n0 = &p_nm[static_cast<uint64_t>(a) * pw];
             const uint64_t *o1 = &p_one[static_cast<uint64_t>(b) * pw], *t1 = &p_two[static_cast<uint64_t>(b) * pw], *n1 = &p_nm[static_cast<uint64_t>(b) * pw];
             int64_t obs = 0, sum0 = 0, sum1 = 0, ssq0 = 0, ssq1 = 0, dot = 0;
@@ -3689,25 +3692,47 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
             if (!(r2 >= min_r2)) continue;
             const uint32_t va = s0 + a, vb = s0 + b;
             const std::string chr = ChrNameOut(V.chr_code[va], V.chr_name[va]);
-            char* w = f.Reserve(2 * chr.size() + V.id[va].size() + V.id[vb].size() + 96);
-            auto put = [&](const std::string& t) {
-              memcpy(w, t.data(), t.size());
-              w += t.size();
-              *w++ = '\t';
-            };
-            put(chr);
-            w = u32toa(V.bp[va], w);
-            *w++ = '\t';
-            put(V.id[va]);
-            put(chr);
-            w = u32toa(V.bp[vb], w);
-            *w++ = '\t';
-            put(V.id[vb]);
-            w = dtoa_g(r2, w);
-            *w++ = '\n';
-            f.Advance(w);
-            ++reported;
+            *out_text += chr;
+            *out_text += '\t';
+            *u32toa(V.bp[va], line) = '\0';
+            *out_text += line;
+            *out_text += '\t';
+            *out_text += V.id[va];
+            *out_text += '\t';
+            *out_text += chr;
+            *out_text += '\t';
+            *u32toa(V.bp[vb], line) = '\0';
+            *out_text += line;
+            *out_text += '\t';
+            *out_text += V.id[vb];
+            *out_text += '\t';
+            *dtoa_g(r2, line) = '\0';
+            *out_text += line;
+            *out_text += '\n';
+            ++*reported_ct;
           }
+        };
+        const uint32_t worker_ct = std::max(1u, std::min(EffectiveHostThreads(c.threads), 64u));
+        const uint32_t row_block = 8192;
+        std::vector<std::string> row_text(std::min(row_block, len));
+        std::vector<uint64_t> flagged_w(worker_ct, 0), reported_w(worker_ct, 0);
+        for (uint32_t a0 = 0; a0 < len; a0 += row_block) {
+          const uint32_t a1 = std::min(len, a0 + row_block);
+          auto work = [&](uint32_t t) {
+            for (uint32_t a = a0 + t; a < a1; a += worker_ct) {
+              row_text[a - a0].clear();
+              process_row(a, &row_text[a - a0], &flagged_w[t], &reported_w[t]);
+            }
+          };
+          std::vector<std::thread> th;
+          for (uint32_t t = 1; t < worker_ct; ++t) th.emplace_back(work, t);
+          work(0);
+          for (auto& x : th) x.join();
+          for (uint32_t a = a0; a < a1; ++a) f.Write(row_text[a - a0].data(), row_text[a - a0].size());
+        }
+        for (uint32_t t = 0; t < worker_ct; ++t) {
+          flagged_total += flagged_w[t];
+          reported += reported_w[t];
         }
       }
     }

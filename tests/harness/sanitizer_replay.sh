@@ -29,5 +29,6 @@ LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile s --make-king-table rel-check --out 
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile a --make-king-table counts cols=+ibs1 --king-table-subset a_sub2.txt --out $W/b10 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --keep x_keep2.txt --mind 0.05 --make-rel square zs --make-grm-list --out $W/b11 2>&1 | flt
 LD_PRELOAD="$LA $W/mock.so" $W/asan --bfile x --nonfounders --r2-unphased --ld-window-r2 0.1 --out $W/b12 2>&1 | flt
+LD_PRELOAD="$LT $W/mock_tsan.so" $W/tsan --bfile x --r2-unphased --ld-window-r2 0.05 --threads 5 --out $W/t2 2>&1 | flt
 LD_PRELOAD="$LT $W/mock_tsan.so" PL2_MOCK_DEVICES=3 $W/tsan --bed a.bed --bim a_chr6.bim --fam a.fam --gpus 3 --threads 6 --indep-pairwise 50 5 0.2 --out $W/t1 2>&1 | flt
 cmp $W/b1.prune.in a_chr6.prune.in && cmp $W/t1.prune.in a_chr6.prune.in && cmp $W/b2.prune.in g_acut.prune.in && echo "sanitizer replay: outputs as expected, no reports above"
