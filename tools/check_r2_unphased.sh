@@ -12,4 +12,7 @@ chk() { name=$1; gold=$2; shift 2; $B "$@" --out ../../gpurun_out/r2u/$name > ..
 chk a_all a_r2.vcor.gz --bfile a --r2-unphased
 chk a_win a_r2w.vcor.gz --bfile a --r2-unphased --ld-window 7 --ld-window-r2 0.5
 chk x_keep x_r2.vcor.gz --bfile x --not-chr X --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.3 --ld-window-kb 0.1
+# chrX rows are computed on the host (no device screen); these two tables were added after the last GPU slot
+chk x_chrx x_r2x.vcor.gz --bfile x --keep x_keep1.txt x_keep2.txt --r2-unphased --ld-window-r2 0.1 --ld-window-kb 0.05
+chk x_nf x_r2nf.vcor.gz --bfile x --nonfounders --r2-unphased --ld-window-r2 0.1 --chr X,Y
 echo "failures: $fail"; exit $fail
