@@ -3528,6 +3528,10 @@ int RunR2Unphased(const Cmd& c, Dataset* ds, Pl2GpuCtx* ctx) {
   const uint32_t n = S.size(), m = V.size();
   const uint32_t bp_radius = c.ld_bp_radius == 0xFFFFFFFFu ? 1000000u : c.ld_bp_radius;
   const double min_r2 = c.ld_min_r2 == 2.0 ? 0.2 * (1 - 1.0 / 17592186044416.0) : c.ld_min_r2;
+  if (c.parallel_tot != 1) {
+    logprintf("Error: --r2-unphased cannot be used with --parallel in plink2_b200.\n");
+    return kRetNotYetSupported;
+  }
   if (!(min_r2 > 0.0)) {
     logprintf("Error: --r2-unphased needs a positive --ld-window-r2 in plink2_b200 (the device screens pairs against it).\n");
     return kRetNotYetSupported;
